@@ -1,0 +1,189 @@
+"""Aligned program batches: the host-side input of the interpreter.
+
+These are duck-type mirrors of the reference's ``OperatorBatch`` / ``ProgramBatch`` /
+``ProgramCollaterBase`` (reference: src/nsvqa/data/data_pipeline.py:31-290, 626-783) so the parity tests and
+the bench can build inputs on a box where the reference is absent.  The interpreter consumes either these
+or the reference's own objects: it only reads ``_op_batch_list[i]._op_name / _arguments / _mask /
+_is_terminal``, ``_dependencies``, ``_object_features``, ``_object_batch_index``, ``_answers``.
+
+Slot alignment rule (reference ``collate_programs`` :647-746): for every branch, slot 0 is a ``select`` for all
+questions; the op of question k that follows r relates and f filters (since the last relate) lands in slot
+(r, filter, f) or (r, relate); slots are emitted ordered by r, filters before the relate; one terminal slot per
+distinct terminal operator, depending on the last slot of every branch.
+"""
+
+import math
+
+import numpy as np
+import torch
+
+QUERY_TERMINALS = ('query_attr', 'choose_attr', 'choose_rel')
+BINARY, QUERY, STATEMENT = 0, 1, 2
+
+
+def flatten_options(list_of_lists):
+    """[[a,b],None,[c]] -> ([a,b,None,c], [0,0,1,2]) (reference util.flatten_list, util.py:51-56)."""
+    flat, owner = [], []
+    for q, sub in enumerate(list_of_lists):
+        for item in (sub if sub is not None else [None]):
+            flat.append(item)
+            owner.append(q)
+    return flat, owner
+
+
+class OperatorBatch(object):
+    """One aligned op slot: per-position argument columns + a 0/1 participation mask."""
+
+    def __init__(self, op_name, arguments, question_num, is_terminal, mask=None):
+        self._op_name = op_name
+        self._is_terminal = is_terminal
+        self._op_id = None
+        self._question_num = question_num
+
+        rows = list(arguments[:question_num]) + [None] * max(0, question_num - len(arguments))
+        width = next((len(r) for r in rows if isinstance(r, list)), 0)
+        rows = [list(r) if r is not None else [None] * width for r in rows]
+        # column-major: _arguments[pos][question]
+        self._arguments = [list(col) for col in zip(*rows)] if width > 0 and len(arguments) > 0 else []
+
+        self._predicate_num = question_num
+        self._question_index = None
+        self._predicate_question_map = None
+        if self._arguments and any(isinstance(el, list) and len(el) > 1 for el in self._arguments[0]):
+            flat, owner = flatten_options(self._arguments[0])
+            self._predicate_num = len(flat)
+            if self._predicate_num != question_num:
+                self._question_index = torch.tensor(owner, dtype=torch.int64)
+
+        self._mask = None if mask is None else torch.as_tensor(np.asarray(mask), dtype=torch.float32)
+
+    def create_sparse_map(self):
+        if self._question_index is not None:
+            idx = torch.stack([torch.arange(self._predicate_num, dtype=torch.int64), self._question_index])
+            self._predicate_question_map = torch.sparse_coo_tensor(
+                idx, torch.ones(self._predicate_num), (self._predicate_num, self._question_num))
+
+    def __repr__(self):
+        return 'OperatorBatch(%s, terminal=%s, args=%s)' % (self._op_name, self._is_terminal, self._arguments)
+
+
+class ProgramBatch(object):
+
+    _serial = 0
+
+    def __init__(self, device, op_batch_list, dependencies, answers, object_features, object_batch_index=None,
+                 original_dicts=None, meta_data=None):
+        self._op_batch_list = op_batch_list
+        self._dependencies = dependencies
+        self._answers = answers
+        self._object_features = object_features
+        self._object_batch_index = None if object_batch_index is None else torch.as_tensor(object_batch_index)
+        self._original_dicts = original_dicts
+        self._meta_data = meta_data
+        self._device = device
+        self._batch_size = op_batch_list[0]._question_num if op_batch_list else 0
+        ProgramBatch._serial += 1
+        for i, ob in enumerate(op_batch_list):
+            if ob._op_id is None:
+                ob._op_id = '%d:%d' % (ProgramBatch._serial, i)
+        last = op_batch_list[-1]._op_name if op_batch_list else None
+        self._question_type = QUERY if last in QUERY_TERMINALS else BINARY
+
+    @property
+    def device(self):
+        return self._device
+
+    def batch_size(self):
+        return self._batch_size
+
+    def create_sparse_tensors(self):
+        for ob in self._op_batch_list:
+            ob.create_sparse_map()
+
+    def pin_memory(self):
+        if isinstance(self._object_features, torch.Tensor):
+            self._object_features = self._object_features.pin_memory()
+        if self._object_batch_index is not None:
+            self._object_batch_index = self._object_batch_index.pin_memory()
+        return self
+
+    def to_cuda(self, device, non_blocking=True):
+        feats = self._object_features.cuda(device, non_blocking=non_blocking)
+        bidx = self._object_batch_index.cuda(device, non_blocking=non_blocking)
+        pb = ProgramBatch(torch.device('cuda', device) if isinstance(device, int) else device, self._op_batch_list,
+                          self._dependencies, self._answers, feats, bidx, self._original_dicts, self._meta_data)
+        return pb
+
+
+def align_programs(questions, starter='select', separator='relate', filler='filter'):
+    """Align the programs of a list of question dicts into op slots; returns (slots, dependencies)."""
+    n = len(questions)
+    branch_num = max(len(q['program']['branches']) for q in questions)
+    slots, deps, branch_ends = [], [], []
+
+    for b in range(branch_num):
+        first = [q['program']['branches'][b][0] for q in questions]
+        slots.append(OperatorBatch(starter, [op['arguments'] if op['operator'] == starter else ['_'] for op in first],
+                                   n, False, mask=np.ones(n, dtype=np.float32)))
+        deps.append([])
+
+        # key (relates_so_far, is_relate, filter_position) -> per-question argument rows
+        table = {}
+        for k, q in enumerate(questions):
+            rel_seen, fil_seen = 0, 0
+            for op in q['program']['branches'][b][1:]:
+                if op['operator'] == filler:
+                    key = (rel_seen, 0, fil_seen)
+                    fil_seen += 1
+                elif op['operator'] == separator:
+                    key = (rel_seen, 1, 0)
+                    rel_seen += 1
+                    fil_seen = 0
+                else:
+                    continue
+                entry = table.setdefault(key, ([None] * n, np.zeros(n, dtype=np.float32)))
+                entry[0][k] = op['arguments']
+                entry[1][k] = 1.0
+
+        for key in sorted(table):
+            args, mask = table[key]
+            deps.append([len(slots) - 1])
+            slots.append(OperatorBatch(separator if key[1] else filler, args, n, False, mask=mask))
+        branch_ends.append(len(slots) - 1)
+
+    terminals = {}
+    for k, q in enumerate(questions):
+        last = q['program']['last_op']
+        entry = terminals.setdefault(last['operator'], ([None] * n, np.zeros(n, dtype=np.float32)))
+        entry[0][k] = last['arguments']
+        entry[1][k] = 1.0
+    for name, (args, mask) in terminals.items():
+        slots.append(OperatorBatch(name, args, n, True, mask=mask))
+        deps.append(list(branch_ends))
+    return slots, deps
+
+
+class ProgramCollater(object):
+    """Splits a list of questions into ``split_num`` contiguous program batches (reference :754-783)."""
+
+    def __init__(self, split_num=1, object_source=None):
+        self._split_num = split_num
+        self._object_source = object_source  # callable(questions) -> (features (T, D+6), batch_index (T,))
+
+    def collate(self, questions):
+        n = len(questions)
+        parts = min(self._split_num, n)
+        size = math.ceil(n / parts)
+        out = []
+        for i in range(parts):
+            chunk = questions[i * size:min((i + 1) * size, n)]
+            if not chunk:
+                break
+            slots, deps = align_programs(chunk)
+            feats, bidx = self._object_source(chunk) if self._object_source is not None else (None, None)
+            pb = ProgramBatch(torch.device('cpu'), slots, deps, [q['answer'] for q in chunk], feats, bidx,
+                              [q.get('original_dict') for q in chunk], meta_data=None)
+            for ob in pb._op_batch_list:
+                ob._op_id = '%d:%s' % (i, ob._op_id)
+            out.append(pb)
+        return out

@@ -1,0 +1,94 @@
+"""Generates tests/golden/*.pt by running the UNMODIFIED reference (see ref_harness.py).
+
+Run here (build container, /root/reference present):  python tests/golden/make_golden.py
+Each fixture holds the synthetic inputs (vocabulary dicts, question dicts, box features, the reference's own
+initial state dict) and what the reference produced from them in fp32 and fp64: training-mode log-probabilities,
+loss/B, gradients of the 12 oracle parameter tensors, eval-mode answers, and (one fixture) the scene tables.
+"""
+
+import json
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+from ref_harness import ReferenceRun, synthetic_metadata  # noqa: E402
+from dfol_vqa_b200 import synth  # noqa: E402
+from dfol_vqa_b200.ontology import Ontology  # noqa: E402
+
+DIMS = dict(box=40, feat=24, hidden=16, emb=20)
+VOCAB = dict(concept_num=96, relation_num=12, category_num=4, class_num=3, seed=0)
+
+
+def build_case(terminal, batch, n_max, min_hops, max_hops, seed, split_num=1, relate_prob=0.4, ragged=True):
+    md = synthetic_metadata(**VOCAB)
+    ont = Ontology(attribute_dict=md['attribute_dict'], class_dict=md['class_dict'], vocabulary=md['vocabulary'],
+                   relations=md['relations'], embedding_dim=DIMS['emb'])
+    questions = synth.make_questions(ont, batch, terminal, min_hops, max_hops, seed=seed, relate_prob=relate_prob)
+    counts = synth.object_counts(batch, n_max, ragged, seed=seed)
+    feats, bidx = synth.make_object_features(counts, DIMS['box'], seed=seed + 1)
+
+    out = {'terminal': terminal, 'dims': DIMS, 'vocab': VOCAB, 'metadata': md, 'questions': json.dumps(questions),
+           'counts': counts, 'features': feats, 'batch_index': bidx, 'split_num': split_num}
+    for tag, dtype in (('ref32', torch.float32), ('ref64', torch.float64)):
+        run = ReferenceRun(md, DIMS, seed=seed, dtype=dtype)
+        if tag == 'ref32':
+            state = {k: v for k, v in run.state_dict().items() if k.startswith(('_featurizer.', '_oracle.'))}
+            out['state'] = state
+        else:
+            run.load_state_dict({**run.state_dict(), **out['state']})
+        f = feats.to(dtype)
+        pbs = run.collate(questions, f, bidx, split_num=split_num)
+        result, loss, grads = run.loss_and_grads(pbs)
+        ev = run.forward(pbs, is_training=False)
+        rec = {'log_probability': result['log_probability'].detach().clone(), 'loss': loss.clone(),
+               'grads': {k: g for k, g in grads.items() if k in out['state']}, 'type': int(result['type']),
+               'answer': ev['answer'], 'eval_log_probability': ev['log_probability'].detach().clone()}
+        if int(result['type']) == 1:
+            rec['options'] = [list(o) for o in result['options']]
+        if tag == 'ref32' and terminal == 'verify_rel':
+            a, r, idx = run.scene_tables(pbs[0])
+            rec['scene'] = {'attr': a, 'rel': r, 'index': idx}
+        out[tag] = rec
+    return out
+
+
+CASES = [
+    # terminal, batch, n_max, min_hops, max_hops, seed, split
+    ('exist', 6, 7, 0, 4, 11, 1),
+    ('and', 6, 7, 1, 4, 12, 1),
+    ('or', 6, 7, 1, 4, 13, 1),
+    ('verify_attrs', 6, 7, 0, 3, 14, 1),
+    ('verify_rel', 6, 7, 0, 3, 15, 1),
+    ('choose_attr', 6, 7, 0, 3, 16, 1),
+    ('choose_rel', 6, 7, 0, 3, 17, 1),
+    ('query_attr', 6, 7, 0, 3, 18, 1),
+    ('all_same', 6, 7, 0, 3, 19, 1),
+    ('all_different', 6, 7, 0, 3, 20, 1),
+    ('two_same', 6, 7, 0, 4, 21, 1),
+    ('two_different', 6, 7, 0, 4, 22, 1),
+    ('compare', 6, 7, 0, 4, 23, 1),
+    ('exist', 6, 6, 1, 5, 31, 3),      # three program batches: gather_results + loss / total questions
+    # (equal-size sub-batches: on CPU the reference stacks the per-batch results, data_parallel.py:36)
+    ('choose_attr', 6, 5, 0, 2, 32, 2),
+]
+
+
+def main():
+    for terminal, batch, n_max, lo, hi, seed, split in CASES:
+        case = build_case(terminal, batch, n_max, lo, hi, seed, split)
+        name = 'golden_%s_s%d.pt' % (terminal, split)
+        torch.save(case, os.path.join(HERE, name))
+        r32, r64 = case['ref32'], case['ref64']
+        lp = r32['log_probability']
+        err = ((lp.double() - r64['log_probability']).abs() / r64['log_probability'].abs().clamp(min=1e-3)).max()
+        print('%-16s split=%d lp[%d] range [%.3g, %.3g] loss %.4f  fp32-vs-fp64 rel %.2e  %d bytes' % (
+            terminal, split, lp.numel(), lp.min(), lp.max(), float(r32['loss']), float(err),
+            os.path.getsize(os.path.join(HERE, name))))
+
+
+if __name__ == '__main__':
+    main()
