@@ -1,0 +1,310 @@
+"""Program compiler: lowers an aligned ``ProgramBatch`` (strings, masks, option lists) to the int32 bytecode the
+interpreter kernels execute (include/dfol_b200.h, DFOL_OP_* / DFOL_F_*).
+
+What is resolved here, on the host, once per batch (reference behaviour in parentheses):
+  * slot participation: ``None`` / '' / '_' predicates and mask-0 questions emit no instruction -- the kernels never
+    see them (FilterBatch/RelateBatch pass-through, batch_base_ops.py:315-317, :385; interpreter mask gate,
+    batch_base_interpreter.py:166-167);
+  * token -> table column (ClassifierOracle, classifier_oracle.py:51-56, :87-96) and ``not(x)`` detection
+    (util.detect_negations, util.py:68-85) including the op-slot-wide "round trip" flag: when any predicate of a
+    slot is negated the reference passes every other predicate of that slot through slog(exp(.))
+    (batch_base_ops.py:212-213);
+  * the op-slot-wide option-normalisation flag (ClassifierOracle._build_map, classifier_oracle.py:22-42: the
+    per-object softmax over a question's options is applied iff ANY question of the slot has more than one);
+  * variable-name tracking, which decides the option sets of query_attr / all_same / two_same
+    (batch_gqa_ops.py:171-177, :305, :583, :655);
+  * offsets of the compact gradient slices the backward kernel writes, one per (instruction, table operand).
+"""
+
+import re
+
+import numpy as np
+
+from . import capi
+
+_NEG_RE = re.compile(r"not\((\w|\s)+\)")
+
+BINARY, QUERY, STATEMENT = 0, 1, 2
+K = capi.K  # constants mirrored from include/dfol_b200.h
+
+
+def _split_neg(token):
+    t = token.strip()
+    if _NEG_RE.match(t) is not None:
+        return True, t[4:-1]
+    return False, t
+
+
+def _blank(tok):
+    return tok is None or tok.strip() in ('', '_')
+
+
+def _roundup4(x):
+    return (x + 3) // 4 * 4
+
+
+class CompiledPrograms(object):
+    """Bytecode + result metadata of one program batch."""
+
+    __slots__ = ('instr', 'q_instr', 'opts', 'lp_num', 'kind', 'options', 'seg', 'names', 'question_num',
+                 'g_attr_size', 'g_rel_size', 'attr_slices', 'rel_slices', 'terminal', 'lp_owner', 'device_cache',
+                 'alg_bytes')
+
+
+class ProgramCompiler(object):
+
+    def __init__(self, ontology, normalize=True, hard_mode=False):
+        self.ont = ontology
+        self.normalize = normalize
+        self.hard_mode = hard_mode
+        self._a2i = ontology._vocabulary['arg_to_idx']
+        self._rel_rev = ontology._relation_reveresed_index
+        self._option_cache = {}
+
+    def _attr_word(self, tok):
+        neg, t = _split_neg(tok)
+        return (self._a2i[t] - 1), neg
+
+    def _rel_word(self, tok):
+        neg, t = _split_neg(tok)
+        return self._rel_rev[self._a2i[t] - 1], neg
+
+    def _query(self, category, name):
+        key = category if category not in ('name', 'type') else name
+        return self.ont.query(key)
+
+    def compile(self, program_batch, object_counts, give_answer=False):
+        pb = program_batch
+        slots = pb._op_batch_list
+        deps = pb._dependencies
+        B = len(object_counts)
+        hard = K.F_HARD if (give_answer and self.hard_mode) else 0
+        a_stride = [_roundup4(n) for n in object_counts]
+        r_stride = [_roundup4(n * n) for n in object_counts]
+
+        prog = [[] for _ in range(B)]        # per question: list of instruction tuples
+        names = [None] * B                   # current variable name per question
+        branch_names = []                    # names at the end of each finished branch
+        opts = []
+        ga = [0]                             # running offsets of the gradient slices
+        gr = [0]
+        attr_slices = []                     # (question, column, g offset) per attribute operand
+        rel_slices = []
+        lp_num = 0
+        result = {'kind': None, 'options': [], 'seg': None, 'terminal': None, 'lp_owner': None}
+        branch_count = 0
+
+        def attr_slice(q, cols):
+            """Reserve consecutive gradient slices (stride a_stride[q]) for attribute columns ``cols`` of image q."""
+            cols = cols if isinstance(cols, (list, tuple)) else [cols]
+            off = ga[0]
+            for k, c in enumerate(cols):
+                attr_slices.append((q, c, off + k * a_stride[q]))
+            ga[0] += len(cols) * a_stride[q]
+            return off
+
+        def rel_slice(q, cols):
+            cols = cols if isinstance(cols, (list, tuple)) else [cols]
+            off = gr[0]
+            for k, c in enumerate(cols):
+                rel_slices.append((q, c, off + k * r_stride[q]))
+            gr[0] += len(cols) * r_stride[q]
+            return off
+
+        def emit(q, op, flags=0, a0=-1, a1=-1, a2=-1, out=-1, ga0=-1, ga1=-1, grr=-1):
+            prog[q].append((op, flags | hard if op >= K.OP_EXIST else flags, a0, a1, a2, out, ga0, ga1, grr, 0, 0, 0))
+
+        def name_flags(name_tok, roundtrip):
+            """(column, flags) of the name select of a relate-like op."""
+            if name_tok is None or name_tok.lower() in ('_', 'scene'):
+                return -1, 0
+            col, neg = self._attr_word(name_tok)
+            return col, (K.F_NAME_NEG if neg else 0) | (K.F_NAME_ROUNDTRIP if roundtrip and not neg else 0)
+
+        def option_words(q, option_lists, kind):
+            """Append question q's option columns to ``opts``; returns (start, count, columns)."""
+            key = (kind, tuple(option_lists))
+            hit = self._option_cache.get(key)
+            if hit is None:
+                words, cols = [], []
+                for tok in option_lists:
+                    col, neg = self._attr_word(tok) if kind == 'attr' else self._rel_word(tok)
+                    words.append(col | (K.OPT_NEG if neg else 0))
+                    cols.append(col)
+                hit = (words, cols)
+                self._option_cache[key] = hit
+            start = len(opts)
+            opts.extend(hit[0])
+            return start, len(hit[0]), hit[1]
+
+        for i, slot in enumerate(slots):
+            name = slot._op_name
+            args = slot._arguments
+            mask = slot._mask
+            mask = [1.0] * B if mask is None else [float(m) for m in mask]
+            terminal = getattr(slot, '_is_terminal', False) or name in capi.TERMINAL_NAMES
+            if not terminal and name == 'select':
+                if branch_count >= 1:
+                    assert branch_count == 1, 'at most two branches per program'
+                    branch_names.append(list(names))
+                    for q in range(B):
+                        emit(q, K.OP_PUSH)
+                branch_count += 1
+                toks = args[0] if args else [None] * B
+                blank = [t is None or t.lower() in ('_', 'scene') for t in toks]
+                any_neg = any(_split_neg(t)[0] for t, b in zip(toks, blank) if not b)
+                for q in range(B):
+                    if blank[q]:
+                        names[q] = 'entity'
+                        emit(q, K.OP_SELECT, 0, -1)
+                    else:
+                        names[q] = toks[q]
+                        col, neg = self._attr_word(toks[q])
+                        fl = (K.F_NEG if neg else 0) | (K.F_ROUNDTRIP if any_neg and not neg else 0)
+                        emit(q, K.OP_SELECT, fl, col, ga0=attr_slice(q, col))
+            elif not terminal and name == 'filter':
+                toks = args[0]
+                valid = [mask[q] > 0 and not _blank(toks[q]) for q in range(B)]
+                # negation detection spans every non-blank predicate of the slot (mask-0 questions carry None)
+                any_neg = any(_split_neg(t)[0] for t in toks if not _blank(t))
+                for q in range(B):
+                    if valid[q]:
+                        col, neg = self._attr_word(toks[q])
+                        fl = (K.F_NEG if neg else 0) | (K.F_ROUNDTRIP if any_neg and not neg else 0)
+                        emit(q, K.OP_FILTER, fl, col, ga0=attr_slice(q, col))
+            elif name in ('relate', 'verify_rel'):
+                rels, subj, nms = args[0], args[1], args[2]
+                any_neg = any(_split_neg(t)[0] for t in rels if not _blank(t))
+                name_valid = [not (t is None or t.lower() in ('_', 'scene')) for t in nms]
+                any_name_neg = any(_split_neg(t)[0] for t, v in zip(nms, name_valid) if v)
+                for q in range(B):
+                    if mask[q] > 0 and not _blank(rels[q]):
+                        col, neg = self._rel_word(rels[q])
+                        ncol, nfl = name_flags(nms[q], any_name_neg)
+                        fl = (K.F_NEG if neg else 0) | (K.F_ROUNDTRIP if any_neg and not neg else 0) | nfl
+                        fl |= K.F_SUBJECT if subj[q] else 0
+                        emit(q, K.OP_RELATE, fl, col, ncol, ga1=attr_slice(q, ncol) if ncol >= 0 else -1,
+                             grr=rel_slice(q, col))
+                        names[q] = nms[q] if name_valid[q] else 'entity'
+                if name == 'verify_rel':
+                    assert all(m > 0 for m in mask), 'one terminal operator per program batch'
+                    for q in range(B):
+                        emit(q, K.OP_EXIST, out=q)
+                    lp_num = B
+                    result.update(kind=BINARY, terminal=name, lp_owner=list(range(B)))
+                    break
+            else:
+                assert all(m > 0 for m in mask), 'one terminal operator per program batch'
+                result['terminal'] = name
+                if name in ('exist', 'end', 'and', 'or'):
+                    op = {'exist': K.OP_EXIST, 'end': K.OP_EXIST, 'and': K.OP_AND, 'or': K.OP_OR}[name]
+                    for q in range(B):
+                        emit(q, op, out=q)
+                    lp_num = B
+                    result.update(kind=STATEMENT if name == 'end' else BINARY, lp_owner=list(range(B)))
+                elif name == 'verify_attrs':
+                    lists = args[0]
+                    any_neg = any(_split_neg(t)[0] for l in lists for t in l)
+                    for q in range(B):
+                        start, cnt, cols = option_words(q, lists[q], 'attr')
+                        emit(q, K.OP_VERIFY_ATTRS, K.F_ROUNDTRIP if any_neg else 0, start, cnt, out=q,
+                             ga0=attr_slice(q, cols))
+                    lp_num = B
+                    result.update(kind=BINARY, lp_owner=list(range(B)))
+                elif name in ('choose_attr', 'query_attr', 'all_same', 'all_different', 'two_same', 'two_different'):
+                    if name == 'choose_attr':
+                        lists = args[0]
+                    else:
+                        base_names = branch_names[0] if name in ('two_same', 'two_different') else names
+                        lists = [self._query(c, nm) for c, nm in zip(args[0], base_names)]
+                    any_neg = any(_split_neg(t)[0] for l in lists for t in l)
+                    norm = self.normalize and any(len(l) > 1 for l in lists)
+                    fl = (K.F_ROUNDTRIP if any_neg else 0) | (K.F_NORMALISE if norm else 0)
+                    if name in ('choose_attr', 'query_attr'):
+                        seg, owner = [0], []
+                        for q in range(B):
+                            start, cnt, cols = option_words(q, lists[q], 'attr')
+                            emit(q, K.OP_CHOOSE_ATTR, fl, start, cnt, out=lp_num,
+                                 ga0=attr_slice(q, cols))
+                            lp_num += cnt
+                            seg.append(lp_num)
+                            owner += [q] * cnt
+                        result.update(kind=QUERY, options=[list(l) for l in lists], seg=seg, lp_owner=owner)
+                    else:
+                        op = K.OP_ALL_SAME if name.startswith('all') else K.OP_TWO_SAME
+                        if name.endswith('different'):
+                            fl |= K.F_NEGATE_RESULT
+                        for q in range(B):
+                            start, cnt, cols = option_words(q, lists[q], 'attr')
+                            emit(q, op, fl, start, cnt, out=q,
+                                 ga0=attr_slice(q, cols))
+                        lp_num = B
+                        result.update(kind=BINARY, lp_owner=list(range(B)))
+                elif name == 'choose_rel':
+                    lists, subj, nms = args[0], args[1], args[2]
+                    any_neg = any(_split_neg(t)[0] for l in lists for t in l)
+                    norm = self.normalize and any(len(l) > 1 for l in lists)
+                    name_valid = [not (t is None or t.lower() in ('_', 'scene')) for t in nms]
+                    any_name_neg = any(_split_neg(t)[0] for t, v in zip(nms, name_valid) if v)
+                    seg, owner = [0], []
+                    for q in range(B):
+                        start, cnt, cols = option_words(q, lists[q], 'rel')
+                        ncol, nfl = name_flags(nms[q], any_name_neg)
+                        fl = (K.F_ROUNDTRIP if any_neg else 0) | (K.F_NORMALISE if norm else 0) | nfl
+                        fl |= K.F_SUBJECT if subj[q] else 0
+                        emit(q, K.OP_CHOOSE_REL, fl, start, cnt, ncol, out=lp_num,
+                             ga1=attr_slice(q, ncol) if ncol >= 0 else -1,
+                             grr=rel_slice(q, cols))
+                        lp_num += cnt
+                        seg.append(lp_num)
+                        owner += [q] * cnt
+                    result.update(kind=QUERY, options=[list(l) for l in lists], seg=seg, lp_owner=owner)
+                elif name == 'compare':
+                    toks, less = args[0], args[1]
+                    any_neg = any(_split_neg(t)[0] for t in toks if not _blank(t))
+                    for q in range(B):
+                        fl = K.F_IS_LESS if less[q] else 0
+                        if _blank(toks[q]):
+                            emit(q, K.OP_COMPARE, fl, -1, out=2 * q)
+                        else:
+                            col, neg = self._attr_word(toks[q])
+                            fl |= (K.F_NEG if neg else 0) | (K.F_ROUNDTRIP if any_neg and not neg else 0)
+                            emit(q, K.OP_COMPARE, fl, col, out=2 * q, ga0=attr_slice(q, col))
+                    lp_num = 2 * B
+                    result.update(kind=QUERY, options=list(zip(branch_names[0], names)),
+                                  seg=list(range(0, 2 * B + 1, 2)), lp_owner=[q for q in range(B) for _ in (0, 1)])
+                else:
+                    raise NotImplementedError('operator %r is outside the hot path' % name)
+                break
+
+        if result['kind'] is None:
+            # last slot is not terminal: implicit 'end' (batch_gqa_interpreter.py:75-76)
+            for q in range(B):
+                emit(q, K.OP_EXIST, out=q)
+            lp_num = B
+            result.update(kind=STATEMENT, terminal='end', lp_owner=list(range(B)))
+
+        cp = CompiledPrograms()
+        q_instr = np.zeros(B + 1, dtype=np.int32)
+        q_instr[1:] = np.cumsum([len(p) for p in prog])
+        flat = [ins for p in prog for ins in p]
+        cp.instr = np.asarray(flat, dtype=np.int32).reshape(-1, K.INSTR_WORDS)
+        cp.q_instr = q_instr
+        cp.opts = np.asarray(opts if opts else [0], dtype=np.int32)
+        cp.lp_num = lp_num
+        cp.kind = result['kind']
+        cp.options = result['options']
+        cp.seg = None if result['seg'] is None else np.asarray(result['seg'], dtype=np.int32)
+        cp.names = list(names)
+        cp.question_num = B
+        cp.g_attr_size = max(ga[0], 1)
+        cp.g_rel_size = max(gr[0], 1)
+        cp.attr_slices = attr_slices
+        cp.rel_slices = rel_slices
+        cp.terminal = result['terminal']
+        cp.lp_owner = result['lp_owner']
+        cp.device_cache = None
+        # algorithmic bytes of one forward pass: every table slice read once + the log-probabilities written
+        cp.alg_bytes = 4.0 * (sum(object_counts[q] for q, _, _ in attr_slices) +
+                              sum(object_counts[q] ** 2 for q, _, _ in rel_slices) + lp_num)
+        return cp

@@ -1,0 +1,281 @@
+// Forward program interpreter: one thread block per question walks its compiled FOL program; the attention
+// vector stays in shared memory for the whole program, every table slice is read exactly once from its
+// per-image contiguous block (see include/dfol_b200.h for the contract and reference citations).
+#include "program_common.cuh"
+
+namespace dfol {
+
+struct FwdShared {
+  float cur[MAXN];
+  float saved[MAXN];
+  float nw[MAXN];
+  float res[MAXN];
+  float inner[MAXN];
+  float den[MAXN];
+  BlockScratch sc;
+};
+
+// cur-like vector of a select: zeros, plus the name predicate (GQASelectBatch, batch_gqa_ops.py:168-183)
+__device__ __forceinline__ void select_into(float* dst, const Image& im, int col, bool neg, bool rt) {
+  const int t = threadIdx.x;
+  if (t < im.n) dst[t] = (col >= 0) ? post_ll(attr_raw(im, col, t), neg, rt) : 0.0f;
+  __syncthreads();
+}
+
+// Attribute option lists (FilterBatch with a predicate->question map + ClassifierOracle normalisation,
+// classifier_oracle.py:61-80): den[t] = sum_k exp(raw_k[t]).
+__device__ __forceinline__ void option_denominators(const Image& im, const int32_t* opts, int count, float* den,
+                                                    BlockScratch& sc) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float acc[NCHUNK];
+#pragma unroll
+  for (int j = 0; j < NCHUNK; ++j) acc[j] = 0.f;
+  for (int k = w; k < count; k += PROG_WARPS) {
+    const int col = opts[k] & ~DFOL_OPT_NEG;
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) {
+      const int t = lane + 32 * j;
+      if (t < im.n) acc[j] += expf(attr_raw(im, col, t));
+    }
+  }
+  reduce_columns(acc, im.n, den, sc, false);
+}
+
+__device__ __forceinline__ float option_ll(const Image& im, int word, int t, bool normalise, bool rt,
+                                           const float* den) {
+  float r = attr_raw(im, word & ~DFOL_OPT_NEG, t);
+  if (normalise) r -= slog(den[t]);
+  return post_ll(r, (word & DFOL_OPT_NEG) != 0, rt);
+}
+
+// warp-level exists over x(t) = base[t] + ll_k[t]; lanes own t = lane + 32 j. Returns lnot(S) to all lanes.
+__device__ __forceinline__ float warp_exists(const float x[NCHUNK], int n, bool hard, float* s_out) {
+  const int lane = threadIdx.x & 31;
+  float s = hard ? 0.0f : 0.0f;
+  bool first = true;
+#pragma unroll
+  for (int j = 0; j < NCHUNK; ++j) {
+    const int t = lane + 32 * j;
+    if (t < n) {
+      const float v = lnot(x[j]);
+      if (hard) { s = first ? v : fminf(s, v); first = false; }
+      else s += v;
+    }
+  }
+  s = hard ? warp_min(s) : warp_sum(s);
+  if (s_out) *s_out = s;
+  return lnot(s);
+}
+
+__global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
+    const int32_t* __restrict__ instr, const int32_t* __restrict__ q_instr, const int32_t* __restrict__ opts,
+    const float* __restrict__ attr_ll, const int64_t* __restrict__ attr_blk, const int32_t* __restrict__ attr_stride,
+    const float* __restrict__ rel_ll, const int64_t* __restrict__ rel_blk, const int32_t* __restrict__ rel_stride,
+    const int32_t* __restrict__ img_n, float* __restrict__ lp_out, float* __restrict__ tape, int tape_stride) {
+  __shared__ FwdShared sm;
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  Image im;
+  im.n = img_n[q];
+  im.attr = attr_ll + attr_blk[q];
+  im.astride = attr_stride[q];
+  im.rel = rel_ll + rel_blk[q];
+  im.rstride = rel_stride[q];
+  const int n = im.n;
+
+  if (tid < MAXN) { sm.cur[tid] = 0.f; sm.saved[tid] = 0.f; }
+  __syncthreads();
+
+  for (int ip = q_instr[q]; ip < q_instr[q + 1]; ++ip) {
+    const Instr I = load_instr(instr, ip);
+    const bool neg = I.flags & DFOL_F_NEG, rt = I.flags & DFOL_F_ROUNDTRIP;
+    const bool hard = I.flags & DFOL_F_HARD, normalise = I.flags & DFOL_F_NORMALISE;
+    if (tape != nullptr && tid < n) tape[(long long)ip * tape_stride + tid] = sm.cur[tid];
+
+    switch (I.op) {
+      case DFOL_OP_SELECT:
+        select_into(sm.cur, im, I.a0, neg, rt);
+        break;
+
+      case DFOL_OP_FILTER:  // a'[t] = a[t] + ll[t]  (_forward_core arity 1)
+        if (tid < n) sm.cur[tid] += post_ll(attr_raw(im, I.a0, tid), neg, rt);
+        __syncthreads();
+        break;
+
+      case DFOL_OP_PUSH:
+        if (tid < n) sm.saved[tid] = sm.cur[tid];
+        __syncthreads();
+        break;
+
+      case DFOL_OP_RELATE: {
+        select_into(sm.nw, im, I.a1, I.flags & DFOL_F_NAME_NEG, I.flags & DFOL_F_NAME_ROUNDTRIP);
+        RelOption L{&im, nullptr, 1, 0, false, rt, I.a0, neg};
+        const bool subj = I.flags & DFOL_F_SUBJECT;
+        relate_forward(n, L, subj ? sm.nw : sm.cur, subj ? sm.cur : sm.nw, subj, sm.res, sm.inner, sm.sc);
+        if (tid < n) sm.cur[tid] = sm.res[tid];
+        __syncthreads();
+        break;
+      }
+
+      case DFOL_OP_EXIST: {
+        const float lp = exists_block(sm.cur, n, hard, sm.sc, nullptr);
+        if (tid == 0) lp_out[I.out] = lp;
+        break;
+      }
+
+      case DFOL_OP_AND:
+      case DFOL_OP_OR: {
+        const float e1 = exists_block(sm.saved, n, hard, sm.sc, nullptr);
+        const float e2 = exists_block(sm.cur, n, hard, sm.sc, nullptr);
+        if (tid == 0)
+          lp_out[I.out] = (I.op == DFOL_OP_AND) ? e1 + e2 : slog(1.0f - (1.0f - expf(e1)) * (1.0f - expf(e2)));
+        break;
+      }
+
+      case DFOL_OP_VERIFY_ATTRS: {
+        // sum over the question's attributes of (a + ll_k), then exists (GQAVerifyAttrsBatch :452-473)
+        const int32_t* op = opts + I.a0;
+        float acc[NCHUNK];
+#pragma unroll
+        for (int j = 0; j < NCHUNK; ++j) acc[j] = 0.f;
+        for (int k = w; k < I.a1; k += PROG_WARPS) {
+#pragma unroll
+          for (int j = 0; j < NCHUNK; ++j) {
+            const int t = lane + 32 * j;
+            if (t < n) acc[j] += sm.cur[t] + option_ll(im, op[k], t, false, rt, nullptr);
+          }
+        }
+        reduce_columns(acc, n, sm.res, sm.sc, false);
+        const float lp = exists_block(sm.res, n, hard, sm.sc, nullptr);
+        if (tid == 0) lp_out[I.out] = lp;
+        break;
+      }
+
+      case DFOL_OP_CHOOSE_ATTR: {
+        const int32_t* op = opts + I.a0;
+        if (normalise) option_denominators(im, op, I.a1, sm.den, sm.sc);
+        for (int k = w; k < I.a1; k += PROG_WARPS) {
+          float x[NCHUNK];
+#pragma unroll
+          for (int j = 0; j < NCHUNK; ++j) {
+            const int t = lane + 32 * j;
+            x[j] = (t < n) ? sm.cur[t] + option_ll(im, op[k], t, normalise, rt, sm.den) : 0.f;
+          }
+          const float lp = warp_exists(x, n, hard, nullptr);
+          if (lane == 0) lp_out[I.out + k] = lp;
+        }
+        __syncthreads();
+        break;
+      }
+
+      case DFOL_OP_ALL_SAME: {
+        // per option: q_k = forall_t lnot(a + lnot(a + ll_k)); lp = lnot(sum_k lnot(q_k))  (:582-608)
+        const int32_t* op = opts + I.a0;
+        if (normalise) option_denominators(im, op, I.a1, sm.den, sm.sc);
+        float part = 0.f;
+        for (int k = w; k < I.a1; k += PROG_WARPS) {
+          float s = 0.f;
+          bool first = true;
+#pragma unroll
+          for (int j = 0; j < NCHUNK; ++j) {
+            const int t = lane + 32 * j;
+            if (t < n) {
+              const float a = sm.cur[t];
+              const float y = lnot(a + lnot(a + option_ll(im, op[k], t, normalise, rt, sm.den)));
+              const float r = roundtrip(y);
+              if (hard) { s = first ? r : fminf(s, r); first = false; }
+              else s += r;
+            }
+          }
+          s = hard ? warp_min(s) : warp_sum(s);
+          part += lnot(roundtrip(s));
+        }
+        float Q = block_sum(lane == 0 ? part : 0.f, sm.sc);
+        float lp = lnot(Q);
+        if (I.flags & DFOL_F_NEGATE_RESULT) lp = lnot(lp);
+        if (tid == 0) lp_out[I.out] = lp;
+        break;
+      }
+
+      case DFOL_OP_TWO_SAME: {
+        const int32_t* op = opts + I.a0;
+        if (normalise) option_denominators(im, op, I.a1, sm.den, sm.sc);
+        float part = 0.f;
+        for (int k = w; k < I.a1; k += PROG_WARPS) {
+          float x1[NCHUNK], x2[NCHUNK];
+#pragma unroll
+          for (int j = 0; j < NCHUNK; ++j) {
+            const int t = lane + 32 * j;
+            const float l = (t < n) ? option_ll(im, op[k], t, normalise, rt, sm.den) : 0.f;
+            x1[j] = (t < n) ? sm.saved[t] + l : 0.f;
+            x2[j] = (t < n) ? sm.cur[t] + l : 0.f;
+          }
+          const float e1 = warp_exists(x1, n, hard, nullptr);
+          const float e2 = warp_exists(x2, n, hard, nullptr);
+          part += lnot(e1 + e2);
+        }
+        float Q = block_sum(lane == 0 ? part : 0.f, sm.sc);
+        float lp = lnot(Q);
+        if (I.flags & DFOL_F_NEGATE_RESULT) lp = lnot(lp);
+        if (tid == 0) lp_out[I.out] = lp;
+        break;
+      }
+
+      case DFOL_OP_COMPARE: {
+        // filter both branches by the attribute, exists, log-softmax over the two, flip by is_less (:730-738)
+        if (tid < n) {
+          const float l = (I.a0 >= 0) ? post_ll(attr_raw(im, I.a0, tid), neg, rt) : 0.0f;
+          sm.res[tid] = sm.saved[tid] + l;
+          sm.nw[tid] = sm.cur[tid] + l;
+        }
+        __syncthreads();
+        const float e1 = exists_block(sm.res, n, hard, sm.sc, nullptr);
+        const float e2 = exists_block(sm.nw, n, hard, sm.sc, nullptr);
+        if (tid == 0) {
+          const float mx = fmaxf(e1, e2);
+          const float lse = logf(expf(e1 - mx) + expf(e2 - mx));
+          const float z1 = e1 - mx - lse, z2 = e2 - mx - lse;
+          const float alpha = (I.flags & DFOL_F_IS_LESS) ? 1.0f : 0.0f;
+          lp_out[I.out] = slog(alpha + (1.0f - 2.0f * alpha) * expf(z1));
+          lp_out[I.out + 1] = slog(alpha + (1.0f - 2.0f * alpha) * expf(z2));
+        }
+        break;
+      }
+
+      case DFOL_OP_CHOOSE_REL: {
+        select_into(sm.nw, im, I.a2, I.flags & DFOL_F_NAME_NEG, I.flags & DFOL_F_NAME_ROUNDTRIP);
+        const bool subj = I.flags & DFOL_F_SUBJECT;
+        for (int k = 0; k < I.a1; ++k) {
+          RelOption L{&im, opts + I.a0, I.a1, k, normalise, rt, -1, false};
+          relate_forward(n, L, subj ? sm.nw : sm.cur, subj ? sm.cur : sm.nw, subj, sm.res, sm.inner, sm.sc);
+          const float lp = exists_block(sm.res, n, hard, sm.sc, nullptr);
+          if (tid == 0) lp_out[I.out + k] = lp;
+          __syncthreads();
+        }
+        break;
+      }
+
+      default:
+        break;
+    }
+  }
+}
+
+}  // namespace dfol
+
+using namespace dfol;
+
+extern "C" int dfol_program_fwd(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
+                                const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
+                                const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride,
+                                const int32_t* img_n, float* lp_out, float* tape, int tape_stride, void* stream) {
+  DFOL_REQUIRE(instr && q_instr && attr_ll && attr_blk && attr_stride && rel_ll && rel_blk && rel_stride && img_n &&
+                   lp_out,
+               "dfol_program_fwd: null pointer");
+  DFOL_REQUIRE(tape == nullptr || tape_stride >= 1, "dfol_program_fwd: bad tape stride");
+  if (question_num == 0) return 0;
+  program_fwd_kernel<<<question_num, PROG_THREADS, 0, (cudaStream_t)stream>>>(
+      instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, lp_out, tape,
+      tape_stride);
+  return finish_launch("dfol_program_fwd");
+}

@@ -1,0 +1,472 @@
+"""Host orchestration of the reasoning path: scene layout, scene build (visual oracle), program execution, and the
+hand-derived backward pass, all as launches of libdfol_b200 kernels on the current CUDA stream.
+
+Reference path being replaced: BatchInterpreterBase.build_scene + forward (nsvqa/nn/interpreter/
+batch_base_interpreter.py:45-183) and the autograd backward of everything it calls.  PyTorch is used for device
+memory (torch.empty / zeros), the stream, and index plumbing only.
+"""
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import K, call, ptr
+
+DEFAULT_LL = -30.0
+
+
+def _roundup(x, m):
+    return (x + m - 1) // m * m
+
+
+class SceneLayout(object):
+    """Row/offset tables of one program batch (see the layout comment in include/dfol_b200.h)."""
+
+    _cache = {}
+
+    def __init__(self, counts, concept_num, relation_num, device):
+        n = np.asarray(counts, dtype=np.int64)
+        assert n.ndim == 1 and n.size > 0 and int(n.min()) >= 1, 'every image needs at least one object'
+        self.counts = [int(v) for v in n]
+        self.B = int(n.size)
+        self.T = int(n.sum())
+        self.P = int((n * n).sum())
+        self.max_n = int(n.max())
+        a_stride = (n + 3) // 4 * 4
+        r_stride = (n * n + 3) // 4 * 4
+        obj_row = np.concatenate([[0], np.cumsum(n)])
+        pair_row = np.concatenate([[0], np.cumsum(n * n)])
+        attr_blk = concept_num * np.concatenate([[0], np.cumsum(a_stride)])
+        rel_blk = relation_num * np.concatenate([[0], np.cumsum(r_stride)])
+        self.attr_size = int(attr_blk[-1])
+        self.rel_size = int(rel_blk[-1])
+        assert self.P < 2 ** 31 and self.T < 2 ** 31
+
+        def dev(a, dtype):
+            return torch.from_numpy(np.ascontiguousarray(a.astype(dtype))).to(device, non_blocking=True)
+
+        self.img_n = dev(n, np.int32)
+        self.img_nn = dev(n * n, np.int32)
+        self.obj_row = dev(obj_row, np.int32)
+        self.pair_row = dev(pair_row, np.int32)
+        self.attr_stride = dev(a_stride, np.int32)
+        self.rel_stride = dev(r_stride, np.int32)
+        self.attr_blk = dev(attr_blk[:-1], np.int64)
+        self.rel_blk = dev(rel_blk[:-1], np.int64)
+        img = torch.arange(self.B, device=device, dtype=torch.int32)
+        self.obj_img = torch.repeat_interleave(img, self.img_n.long())
+        self.pair_img = torch.repeat_interleave(img, self.img_nn.long())
+        self.a_stride_host = a_stride
+        self.r_stride_host = r_stride
+
+    @classmethod
+    def get(cls, counts, concept_num, relation_num, device):
+        key = (tuple(int(c) for c in counts), concept_num, relation_num, str(device))
+        hit = cls._cache.get(key)
+        if hit is None:
+            if len(cls._cache) > 64:
+                cls._cache.clear()
+            hit = cls(counts, concept_num, relation_num, device)
+            cls._cache[key] = hit
+        return hit
+
+
+def gemm_f32(A, B, C, bias=None, act=K.ACT_NONE, accumulate=False, split_k=1, mul_src=None, mul_mode=K.MUL_NONE,
+             table=None, stream=None):
+    """C = epilogue(A @ B) with A (M,K) and B (K,N) arbitrary-stride fp32 views; see dfol_gemm_f32."""
+    M, Kd = A.shape
+    Kb, N = B.shape
+    assert Kd == Kb
+    if table is None:
+        assert C.shape == (M, N) and C.stride(1) == 1
+        ldc, store, maps, diag = C.stride(0), 0, (None, None, None, None, None), 0.0
+    else:
+        ldc, store = 0, 1
+        maps = (ptr(table['row_img']), ptr(table['img_row']), ptr(table['img_blk']), ptr(table['img_stride']),
+                ptr(table.get('img_n')))
+        diag = table.get('diag', DEFAULT_LL)
+    if capi.trace is not None:
+        capi.next_meta = {'tag': 'gemm_f32[%dx%dx%d]%s' % (M, N, Kd, ' table' if store else ''),
+                          'flops': 2.0 * M * N * Kd}
+    call('dfol_gemm_f32', ptr(A), A.stride(0), A.stride(1), ptr(B), B.stride(0), B.stride(1), ptr(C), ldc, ptr(bias),
+         M, N, Kd, act, int(accumulate), split_k, ptr(mul_src), 0 if mul_src is None else mul_src.stride(0), mul_mode,
+         store, maps[0], maps[1], maps[2], maps[3], maps[4], diag, stream)
+
+
+def _split_for(k):
+    return int(max(1, min(512, k // 2048)))
+
+
+class OracleWeights(object):
+    """Views of the 12 parameter tensors (reference key order)."""
+
+    def __init__(self, featurizer_layers, attribute_layers, relation_layers, embedding_layer):
+        assert len(featurizer_layers) == 1, 'featurizer_layers_config must be [] (single Linear + Sigmoid)'
+        assert len(attribute_layers) >= 1 and len(relation_layers) >= 1
+        self.feat = featurizer_layers[0]
+        self.attr = attribute_layers
+        self.rel = relation_layers
+        self.emb = embedding_layer
+        assert self.emb.bias is not None, 'freeze_embedding_bias is not supported by the fused path'
+
+    def parameters(self):
+        out = [self.feat.weight, self.feat.bias]
+        for l in self.attr + self.rel:
+            out += [l.weight, l.bias]
+        out += [self.emb.weight, self.emb.bias]
+        return out
+
+
+class Scene(object):
+    """Device tensors of one built scene (tables + the activations saved for backward)."""
+    pass
+
+
+class ReasoningEngine(object):
+
+    def __init__(self, weights, relation_index, gemm_mode='fp32'):
+        self.w = weights
+        self.rel_index_host = list(relation_index)
+        self._rel_index = None
+        self.gemm_mode = gemm_mode
+        if gemm_mode not in ('fp32', 'bf16'):
+            raise ValueError('gemm_mode must be fp32 or bf16')
+
+    def rel_index(self, device):
+        if self._rel_index is None or self._rel_index.device != device:
+            self._rel_index = torch.tensor(self.rel_index_host, dtype=torch.int64, device=device)
+        return self._rel_index
+
+    # ------------------------------------------------------------------------------------------ forward
+
+    # ------------------------------------------------------------------------------------------ bf16 forward
+
+    @staticmethod
+    def _cast16(src, ld, st, rows=None):
+        """bf16 copy of a 2-D fp32 view with rows padded to ``ld`` elements (zeros)."""
+        r, c = src.shape
+        out = torch.empty(r, ld, device=src.device, dtype=torch.bfloat16)
+        call('dfol_cast_bf16', ptr(src), src.stride(0), ptr(out), ld, r, c, st)
+        return out
+
+    @staticmethod
+    def _tc(A16, B16, C, N, Kp, bias, act, st, table=None):
+        """C = epilogue(A16[:, :Kp] @ B16[:N, :Kp]^T) on the tensor cores (dfol_gemm_bf16_tc)."""
+        M = A16.shape[0]
+        if table is None:
+            out_bf16 = int(C.dtype == torch.bfloat16)
+            ldc, store, maps, diag = C.stride(0), 0, (None, None, None, None, None), 0.0
+        else:
+            out_bf16, ldc, store = 0, 0, 1
+            maps = (ptr(table['row_img']), ptr(table['img_row']), ptr(table['img_blk']), ptr(table['img_stride']),
+                    ptr(table.get('img_n')))
+            diag = table.get('diag', DEFAULT_LL)
+        if capi.trace is not None:
+            capi.next_meta = {'tag': 'gemm_bf16_tc[%dx%dx%d]%s' % (M, N, Kp, ' table' if store else ''),
+                              'flops': 2.0 * M * N * Kp}
+        call('dfol_gemm_bf16_tc', ptr(A16), A16.stride(0), ptr(B16), B16.stride(0), ptr(C), ldc, ptr(bias), M, N, Kp,
+             act, out_bf16, store, maps[0], maps[1], maps[2], maps[3], maps[4], diag, st)
+
+    def build_scene_bf16(self, features, layout):
+        """Same tables as build_scene with every dense contraction on tcgen05 tensor cores (bf16 operands, fp32
+        accumulation in TMEM).  Forward only in this round: activations are kept in bf16."""
+        capi.lib()
+        w = self.w
+        dev = features.device
+        st = capi.stream_ptr(dev)
+        T, width = features.shape
+        D = width - 6
+        F = w.feat.weight.shape[0]
+        ldo = F + 4
+        assert len(w.attr) == 2 and len(w.rel) == 2, 'bf16 path: one hidden layer per network (reference configs)'
+        H, E = w.rel[0].weight.shape[0], w.rel[1].weight.shape[0]
+        Ha = w.attr[0].weight.shape[0]
+        sc = Scene()
+        sc.layout = layout
+        sc.features = features
+        Dp, Op, Hp, Hap, Ep = (_roundup(v, 64) for v in (D, ldo, H, Ha, E))
+
+        # featurizer (fp32 obj: the pair kernel and the position columns need it), then its bf16 copy
+        x16 = self._cast16(features[:, :D], Dp, st)
+        wf16 = self._cast16(w.feat.weight, Dp, st)
+        obj = torch.empty(T, ldo, device=dev, dtype=torch.float32)
+        self._tc(x16, wf16, obj, F, Dp, w.feat.bias, K.ACT_SIGMOID, st)
+        call('dfol_box_position', ptr(features), features.stride(0), D, ptr(obj), ldo, F, T, st)
+        obj16 = self._cast16(obj, Op, st)
+        sc.obj = obj
+
+        # attribute chain
+        wa1 = self._cast16(w.attr[0].weight, Op, st)
+        wa2 = self._cast16(w.attr[1].weight, Hap, st)
+        we16 = self._cast16(w.emb.weight, Ep, st)
+        h1a = torch.empty(T, Hap, device=dev, dtype=torch.bfloat16)
+        self._tc(obj16, wa1, h1a, Ha, Op, w.attr[0].bias, K.ACT_ELU, st)
+        h2a = torch.empty(T, Ep, device=dev, dtype=torch.bfloat16)
+        self._tc(h1a, wa2, h2a, E, Hap, w.attr[1].bias, K.ACT_SIGMOID, st)
+        attr_ll = torch.empty(layout.attr_size, device=dev, dtype=torch.float32)
+        obj_table = {'row_img': layout.obj_img, 'img_row': layout.obj_row, 'img_blk': layout.attr_blk,
+                     'img_stride': layout.attr_stride}
+        self._tc(h2a, we16, attr_ll, w.emb.weight.shape[0], Ep, w.emb.bias, K.ACT_LOGSIGMOID, st, table=obj_table)
+        sc.attr_ll = attr_ll
+        sc.attr_h = [h1a, h2a]
+
+        # relation chain: U|V in one GEMM (N = 2H), pair hidden layer in bf16, two tensor-core layers over pairs
+        first = w.rel[0]
+        wuv = torch.empty(2 * H, Op, device=dev, dtype=torch.bfloat16)
+        call('dfol_cast_bf16', ptr(first.weight[:, :ldo]), first.weight.stride(0), ptr(wuv), Op, H, ldo, st)
+        call('dfol_cast_bf16', ptr(first.weight[:, ldo:2 * ldo]), first.weight.stride(0), ptr(wuv[H:]), Op, H, ldo, st)
+        uv = torch.empty(T, 2 * H, device=dev, dtype=torch.float32)
+        self._tc(obj16, wuv, uv, 2 * H, Op, None, K.ACT_NONE, st)
+        wg = first.weight[:, 2 * ldo:]
+        h1r = torch.empty(layout.P, Hp, device=dev, dtype=torch.bfloat16)
+        call('dfol_pair_hidden_fwd', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo, ptr(wg), first.weight.stride(0),
+             ptr(first.bias), ptr(h1r), Hp, H, K.ACT_ELU, 1, ptr(layout.pair_img), ptr(layout.pair_row),
+             ptr(layout.obj_row), ptr(layout.img_n), layout.P, st)
+        wr2 = self._cast16(w.rel[1].weight, Hp, st)
+        h2r = torch.empty(layout.P, Ep, device=dev, dtype=torch.bfloat16)
+        self._tc(h1r, wr2, h2r, E, Hp, w.rel[1].bias, K.ACT_SIGMOID, st)
+        ridx = self.rel_index(dev)
+        sc.w_rel = w.emb.weight.detach().index_select(0, ridx).contiguous()
+        sc.b_rel = w.emb.bias.detach().index_select(0, ridx).contiguous()
+        wrel16 = self._cast16(sc.w_rel, Ep, st)
+        rel_ll = torch.empty(layout.rel_size, device=dev, dtype=torch.float32)
+        pair_table = {'row_img': layout.pair_img, 'img_row': layout.pair_row, 'img_blk': layout.rel_blk,
+                      'img_stride': layout.rel_stride, 'img_n': layout.img_n, 'diag': DEFAULT_LL}
+        self._tc(h2r, wrel16, rel_ll, sc.w_rel.shape[0], Ep, sc.b_rel, K.ACT_LOGSIGMOID, st, table=pair_table)
+        sc.rel_ll = rel_ll
+        sc.rel_h = [h1r, h2r]
+        sc.uv = uv
+        return sc
+
+    def build_scene(self, features, layout, keep_for_backward=True):
+        """Featurizer + attribute / relation tables (K1-K6 of SURVEY.md §2.1)."""
+        if self.gemm_mode == 'bf16':
+            return self.build_scene_bf16(features, layout)
+        capi.lib()
+        w = self.w
+        dev = features.device
+        st = capi.stream_ptr(dev)
+        T, width = features.shape
+        D = width - 6
+        assert T == layout.T and features.dtype == torch.float32 and features.stride(1) == 1
+        F = w.feat.weight.shape[0]
+        ldo = F + 4
+        sc = Scene()
+        sc.layout = layout
+        sc.features = features
+
+        # featurizer: obj = [sigmoid(X Wf^T + b) | box position]
+        obj = torch.empty(T, ldo, device=dev, dtype=torch.float32)
+        gemm_f32(features[:, :D], w.feat.weight.t(), obj[:, :F], w.feat.bias, K.ACT_SIGMOID, stream=st)
+        call('dfol_box_position', ptr(features), features.stride(0), D, ptr(obj), ldo, F, T, st)
+        sc.obj = obj
+
+        # attribute chain -> attribute table (all C concept columns)
+        h = obj
+        sc.attr_h = []
+        for i, layer in enumerate(w.attr):
+            out = torch.empty(T, layer.weight.shape[0], device=dev, dtype=torch.float32)
+            gemm_f32(h, layer.weight.t(), out, layer.bias, K.ACT_ELU if i < len(w.attr) - 1 else K.ACT_SIGMOID,
+                     stream=st)
+            sc.attr_h.append(out)
+            h = out
+        C = w.emb.weight.shape[0]
+        attr_ll = torch.empty(layout.attr_size, device=dev, dtype=torch.float32)
+        obj_table = {'row_img': layout.obj_img, 'img_row': layout.obj_row, 'img_blk': layout.attr_blk,
+                     'img_stride': layout.attr_stride}
+        gemm_f32(h, w.emb.weight.t(), attr_ll, w.emb.bias, K.ACT_LOGSIGMOID, table=obj_table, stream=st)
+        sc.attr_ll = attr_ll
+
+        # relation chain: first layer through the U/V decomposition, then dense layers over all pair rows
+        first = w.rel[0]
+        H = first.weight.shape[0]
+        assert first.weight.shape[1] == 2 * ldo + 4, 'relation network input must be 2*(F+4)+4'
+        uv = torch.empty(T, 2 * H, device=dev, dtype=torch.float32)
+        gemm_f32(obj, first.weight[:, :ldo].t(), uv[:, :H], stream=st)
+        gemm_f32(obj, first.weight[:, ldo:2 * ldo].t(), uv[:, H:], stream=st)
+        sc.uv = uv
+        wg = first.weight[:, 2 * ldo:]
+        h1 = torch.empty(layout.P, H, device=dev, dtype=torch.float32)
+        act1 = K.ACT_ELU if len(w.rel) > 1 else K.ACT_SIGMOID
+        call('dfol_pair_hidden_fwd', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo, ptr(wg), first.weight.stride(0),
+             ptr(first.bias), ptr(h1), H, H, act1, 0, ptr(layout.pair_img), ptr(layout.pair_row),
+             ptr(layout.obj_row), ptr(layout.img_n), layout.P, st)
+        sc.rel_h = [h1]
+        h = h1
+        for i, layer in enumerate(w.rel[1:], start=1):
+            out = torch.empty(layout.P, layer.weight.shape[0], device=dev, dtype=torch.float32)
+            gemm_f32(h, layer.weight.t(), out, layer.bias, K.ACT_ELU if i < len(w.rel) - 1 else K.ACT_SIGMOID,
+                     stream=st)
+            sc.rel_h.append(out)
+            h = out
+        ridx = self.rel_index(dev)
+        sc.w_rel = w.emb.weight.detach().index_select(0, ridx).contiguous()
+        sc.b_rel = w.emb.bias.detach().index_select(0, ridx).contiguous()
+        rel_ll = torch.empty(layout.rel_size, device=dev, dtype=torch.float32)
+        pair_table = {'row_img': layout.pair_img, 'img_row': layout.pair_row, 'img_blk': layout.rel_blk,
+                      'img_stride': layout.rel_stride, 'img_n': layout.img_n, 'diag': DEFAULT_LL}
+        gemm_f32(h, sc.w_rel.t(), rel_ll, sc.b_rel, K.ACT_LOGSIGMOID, table=pair_table, stream=st)
+        sc.rel_ll = rel_ll
+        return sc
+
+    def upload_programs(self, cp, device):
+        """Device copies of the bytecode of a CompiledPrograms (cached on the object)."""
+        if cp.device_cache is None or cp.device_cache['device'] != device:
+            def dev(a):
+                return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
+            cache = {'device': device, 'instr': dev(cp.instr), 'q_instr': dev(cp.q_instr), 'opts': dev(cp.opts)}
+            if cp.seg is not None:
+                cache['seg'] = dev(cp.seg)
+            cp.device_cache = cache
+        return cp.device_cache
+
+    def run_programs(self, cp, scene, save_tape=True):
+        """Executes the compiled programs; returns lp (cp.lp_num,) and the tape (or None)."""
+        lay = scene.layout
+        dev = scene.attr_ll.device
+        st = capi.stream_ptr(dev)
+        assert lay.max_n <= 128, 'the interpreter kernels support at most 128 objects per image'
+        d = self.upload_programs(cp, dev)
+        lp = torch.empty(max(cp.lp_num, 1), device=dev, dtype=torch.float32)
+        n_instr = cp.instr.shape[0]
+        stride = _roundup(lay.max_n, 4)
+        tape = torch.empty(max(n_instr, 1) * stride, device=dev, dtype=torch.float32) if save_tape else None
+        if capi.trace is not None:
+            capi.next_meta = {'tag': 'program_fwd', 'bytes': cp.alg_bytes}
+        call('dfol_program_fwd', ptr(d['instr']), ptr(d['q_instr']), ptr(d['opts']), cp.question_num,
+             ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride), ptr(scene.rel_ll), ptr(lay.rel_blk),
+             ptr(lay.rel_stride), ptr(lay.img_n), ptr(lp), ptr(tape), stride, st)
+        return lp[:cp.lp_num], tape
+
+    # ------------------------------------------------------------------------------------------ backward
+
+    def _slice_tables(self, slices, B, device, key, cp):
+        """Per-image grouped slice tables for dfol_table_layer_bwd."""
+        cache = cp.device_cache
+        if key in cache:
+            return cache[key]
+        if slices:
+            arr = np.asarray(slices, dtype=np.int64)  # (question, column, g offset)
+            order = np.argsort(arr[:, 0], kind='stable')
+            arr = arr[order]
+            counts = np.bincount(arr[:, 0], minlength=B)
+        else:
+            arr = np.zeros((0, 3), dtype=np.int64)
+            counts = np.zeros(B, dtype=np.int64)
+        img_slice = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+
+        def dev(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
+        pad = arr if arr.shape[0] else np.zeros((1, 3), dtype=np.int64)
+        out = {'goff': dev(pad[:, 2].astype(np.int32)), 'col': dev(pad[:, 1].astype(np.int32)),
+               'img_slice': dev(img_slice), 'count': int(arr.shape[0])}
+        cache[key] = out
+        return out
+
+    def backward(self, cp, scene, tape, d_lp, grads):
+        """d loss / d parameters given d loss / d lp.  ``grads``: dict param tensor id -> fp32 grad tensor of the
+        parameter's shape (accumulated into; callers zero them)."""
+        if self.gemm_mode != 'fp32':
+            raise NotImplementedError('backward through the bf16 tensor-core scene build is not implemented yet; '
+                                      'train in gemm_mode="fp32"')
+        w = self.w
+        lay = scene.layout
+        dev = scene.attr_ll.device
+        st = capi.stream_ptr(dev)
+        d = self.upload_programs(cp, dev)
+        stride = _roundup(lay.max_n, 4)
+        g_attr = torch.zeros(cp.g_attr_size, device=dev, dtype=torch.float32)
+        g_rel = torch.zeros(cp.g_rel_size, device=dev, dtype=torch.float32)
+        call('dfol_program_bwd', ptr(d['instr']), ptr(d['q_instr']), ptr(d['opts']), cp.question_num,
+             ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride), ptr(scene.rel_ll), ptr(lay.rel_blk),
+             ptr(lay.rel_stride), ptr(lay.img_n), ptr(d_lp), ptr(tape), stride, ptr(g_attr), ptr(g_rel), st)
+
+        def G(p):
+            return grads[id(p)]
+
+        T, P = lay.T, lay.P
+        obj = scene.obj
+        F = w.feat.weight.shape[0]
+        ldo = F + 4
+        E = w.emb.weight.shape[1]
+        d_obj = torch.zeros(T, ldo, device=dev, dtype=torch.float32)
+
+        # ---- attribute table layer (sparse slices) -> dense chain backward
+        sa = self._slice_tables(cp.attr_slices, lay.B, dev, 'attr_slices', cp)
+        h_last = scene.attr_h[-1]
+        d_h = torch.zeros(T, E, device=dev, dtype=torch.float32)
+        if sa['count']:
+            call('dfol_table_layer_bwd', ptr(g_attr), ptr(sa['goff']), ptr(sa['col']), ptr(sa['col']),
+                 ptr(sa['img_slice']), lay.B, ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride),
+                 ptr(lay.obj_row), ptr(lay.img_n), ptr(w.emb.weight), w.emb.weight.stride(0), ptr(h_last),
+                 h_last.stride(0), E, ptr(d_h), d_h.stride(0), ptr(G(w.emb.weight)), ptr(G(w.emb.bias)), st)
+        self._mlp_backward(w.attr, [obj] + scene.attr_h, d_h, d_obj, grads, st, first_layer_input_grad=True)
+
+        # ---- relation table layer -> dense layers -> pair hidden layer
+        sr = self._slice_tables(cp.rel_slices, lay.B, dev, 'rel_slices', cp)
+        if sr['count']:
+            nR = scene.w_rel.shape[0]
+            h_last = scene.rel_h[-1]
+            d_h = torch.zeros(P, E, device=dev, dtype=torch.float32)
+            dw_rel = torch.zeros(nR, E, device=dev, dtype=torch.float32)
+            db_rel = torch.zeros(nR, device=dev, dtype=torch.float32)
+            call('dfol_table_layer_bwd', ptr(g_rel), ptr(sr['goff']), ptr(sr['col']), ptr(sr['col']),
+                 ptr(sr['img_slice']), lay.B, ptr(scene.rel_ll), ptr(lay.rel_blk), ptr(lay.rel_stride),
+                 ptr(lay.pair_row), ptr(lay.img_nn), ptr(scene.w_rel), E, ptr(h_last), h_last.stride(0), E,
+                 ptr(d_h), d_h.stride(0), ptr(dw_rel), ptr(db_rel), st)
+            ridx = self.rel_index(dev)
+            G(w.emb.weight).index_add_(0, ridx, dw_rel)
+            G(w.emb.bias).index_add_(0, ridx, db_rel)
+            # dense layers above the pair hidden layer
+            d_h1 = self._mlp_backward(w.rel[1:], scene.rel_h, d_h, None, grads, st, first_layer_input_grad=False)
+            first = w.rel[0]
+            H = first.weight.shape[0]
+            duv = torch.zeros(T, 2 * H, device=dev, dtype=torch.float32)
+            gw1 = G(first.weight)
+            act1 = K.ACT_ELU if len(w.rel) > 1 else K.ACT_SIGMOID
+            call('dfol_pair_hidden_bwd', ptr(d_h1), d_h1.stride(0), ptr(scene.rel_h[0]), scene.rel_h[0].stride(0),
+                 ptr(obj[:, F:]), ldo, ptr(duv), duv.stride(0), ptr(gw1[:, 2 * ldo:]), gw1.stride(0),
+                 ptr(G(first.bias)), H, act1, ptr(lay.pair_row), ptr(lay.obj_row), ptr(lay.img_n), lay.B, st)
+            sk = _split_for(T)
+            gemm_f32(duv[:, :H].t(), obj, gw1[:, :ldo], accumulate=(sk == 1), split_k=sk, stream=st)
+            gemm_f32(duv[:, H:].t(), obj, gw1[:, ldo:2 * ldo], accumulate=(sk == 1), split_k=sk, stream=st)
+            gemm_f32(duv[:, :H], first.weight[:, :ldo], d_obj, accumulate=True, stream=st)
+            gemm_f32(duv[:, H:], first.weight[:, ldo:2 * ldo], d_obj, accumulate=True, stream=st)
+
+        # ---- featurizer: d pre = d obj[:, :F] * f (1 - f)
+        call('dfol_act_grad_mul', ptr(d_obj), ldo, ptr(obj), ldo, T, F, K.ACT_SIGMOID, st)
+        call('dfol_colsum', ptr(d_obj), ldo, T, F, ptr(G(w.feat.bias)), st)
+        D = scene.features.shape[1] - 6
+        sk = _split_for(T)
+        gemm_f32(d_obj[:, :F].t(), scene.features[:, :D], G(w.feat.weight), accumulate=(sk == 1), split_k=sk, stream=st)
+
+    def _mlp_backward(self, layers, acts, d_out, d_in_accum, grads, st, first_layer_input_grad):
+        """Backward through [Linear+act]* given d loss / d (last activation OUTPUT).
+
+        ``acts`` = [input, h_1, ..., h_L] (saved outputs), ``layers`` the L Linear modules. Returns d loss / d input
+        (accumulated into ``d_in_accum`` if given, else a fresh tensor) -- or d_out itself when L == 0.
+        """
+        L = len(layers)
+        if L == 0:
+            return d_out
+        assert len(acts) == L + 1
+        d_h = d_out
+        for i in range(L - 1, -1, -1):
+            layer = layers[i]
+            h_out, h_in = acts[i + 1], acts[i]
+            rows, width = h_out.shape
+            act = K.ACT_SIGMOID if i == L - 1 else K.ACT_ELU
+            # dZ = dH * act'(h) in place
+            call('dfol_act_grad_mul', ptr(d_h), d_h.stride(0), ptr(h_out), h_out.stride(0), rows, width, act, st)
+            call('dfol_colsum', ptr(d_h), d_h.stride(0), rows, width, ptr(grads[id(layer.bias)]), st)
+            sk = _split_for(rows)
+            gemm_f32(d_h.t(), h_in, grads[id(layer.weight)], accumulate=(sk == 1), split_k=sk, stream=st)
+            if i > 0 or first_layer_input_grad or d_in_accum is None:
+                if i == 0 and d_in_accum is not None:
+                    gemm_f32(d_h, layer.weight, d_in_accum, accumulate=True, stream=st)
+                    d_h = d_in_accum
+                else:
+                    nxt = torch.empty(rows, h_in.shape[1], device=d_h.device, dtype=torch.float32)
+                    gemm_f32(d_h, layer.weight, nxt, stream=st)
+                    d_h = nxt
+        return d_h

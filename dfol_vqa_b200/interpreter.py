@@ -1,0 +1,328 @@
+"""Drop-in modules for the reference's reasoning path, backed by libdfol_b200.
+
+  FastBoxFeaturizer     <-> BatchGQABoxFeaturizer   (reference: src/nsvqa/data/batch_gqa_boxfeatures_pipeline.py:193-281)
+  FastClassifierOracle  <-> ClassifierOracle        (reference: src/nsvqa/nn/vision/classifier_oracle.py:11-156)
+  FastGQAInterpreter    <-> BatchGQAInterpreter     (reference: src/nsvqa/nn/interpreter/batch_gqa_interpreter.py:13-86,
+                                                     batch_base_interpreter.py:14-183)
+
+Same constructor arguments, same ``forward(program_batch_list, is_training, return_trace, modulator_switch)`` and
+result dict, same state-dict key names (the networks are held under the same attribute paths), so they can be
+swapped in under gqa_interpreter_experiments.py.  ``result['log_probability']`` is attached to
+the autograd graph through one custom Function whose backward runs the hand-written backward kernels, so the
+reference trainer's loss / ``loss.backward()`` / clip / Adam work unchanged.  ``FusedTrainStep`` is the fast
+path: loss, gradient all-reduce, clip and Adam without leaving our kernels.
+"""
+
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import capi
+from .capi import K, call, ptr
+from .compiler import BINARY, QUERY, STATEMENT, ProgramCompiler
+from .engine import OracleWeights, ReasoningEngine, SceneLayout
+from .networks import dropout_p, linear_layers
+
+YES = ('yes', 'yeah', 'yep', 'yup', 'aye', 'yea')
+
+
+class FastBoxFeaturizer(nn.Module):
+
+    def __init__(self, featurizer_network=None):
+        super(FastBoxFeaturizer, self).__init__()
+        if featurizer_network is None:
+            raise NotImplementedError('the fused path needs the featurizer network (Linear + Sigmoid)')
+        self._featurizer_network = featurizer_network
+
+
+class FastClassifierOracle(nn.Module):
+
+    def __init__(self, ontology, attribute_network, relation_network, embedding_network, normalize=False, cached=False):
+        super(FastClassifierOracle, self).__init__()
+        self._ontology = ontology
+        self._feature_dim = 1
+        self._attribute_network = attribute_network
+        self._relation_network = relation_network
+        self._embedding_network = embedding_network
+        self._normalize = normalize
+        self._cached = cached
+
+
+class _ReasoningFunction(torch.autograd.Function):
+    """features + oracle parameters -> log-probabilities of one program batch."""
+
+    @staticmethod
+    def forward(ctx, engine, cp, layout, features, need_grad, *params):
+        scene = engine.build_scene(features, layout)
+        lp, tape = engine.run_programs(cp, scene, save_tape=need_grad)
+        ctx.engine, ctx.cp, ctx.scene, ctx.tape, ctx.params = engine, cp, scene, tape, params
+        return lp
+
+    @staticmethod
+    def backward(ctx, d_lp):
+        params = ctx.params
+        grads = {id(p): torch.zeros_like(p, dtype=torch.float32) for p in params}
+        ctx.engine.backward(ctx.cp, ctx.scene, ctx.tape, d_lp.contiguous().float(), grads)
+        ctx.scene = ctx.tape = None
+        return (None, None, None, None, None) + tuple(grads[id(p)] if p.requires_grad else None for p in params)
+
+
+class FastGQAInterpreter(nn.Module):
+
+    def __init__(self, name, oracle, ontology, featurizer=None, trainable_module_type=None, feature_dim=1,
+                 trainable_gate=False, likelihood_threshold=0, hard_mode=False, attention_transfer_state_dim=0,
+                 forward_attention_network=None, backward_attention_network=None, attention_output_network=None,
+                 apply_modulation_everywhere=True, cached=False, visual_rule_learner=None, calibrator=None,
+                 gemm_mode=None):
+        super(FastGQAInterpreter, self).__init__()
+        if trainable_module_type is not None or trainable_gate or feature_dim != 1:
+            raise NotImplementedError('trainable logic gates / operator MLPs are outside the hot path (SURVEY.md §2)')
+        if forward_attention_network is not None or backward_attention_network is not None or \
+                attention_output_network is not None:
+            raise NotImplementedError('attention-transfer calibrator: SURVEY.md §8(f) row 1 (next)')
+        if visual_rule_learner is not None or calibrator is not None:
+            raise NotImplementedError('visual rule learner / calibrator are not part of the reference hot path')
+        if featurizer is None:
+            raise NotImplementedError('the fused path needs the box featurizer')
+        self._name = name
+        self._featurizer = featurizer
+        self._oracle = oracle
+        self._ontology = ontology
+        self._likelihood_threshold = likelihood_threshold
+        self._hard_mode = hard_mode
+        self._global_step = nn.Parameter(torch.tensor([0], dtype=torch.float), requires_grad=False)
+        self._has_modulator = False
+        self._cached = cached
+        self._gemm_mode = gemm_mode or os.environ.get('DFOL_GEMM_MODE', 'fp32')
+
+        for net in (featurizer._featurizer_network, oracle._attribute_network, oracle._relation_network,
+                    oracle._embedding_network):
+            if dropout_p(net) > 0:
+                self._dropout = dropout_p(net)
+        self._weights = OracleWeights(linear_layers(featurizer._featurizer_network),
+                                      linear_layers(oracle._attribute_network),
+                                      linear_layers(oracle._relation_network),
+                                      linear_layers(oracle._embedding_network)[0])
+        self._engine = ReasoningEngine(self._weights, ontology._relation_index, self._gemm_mode)
+        self._compiler = ProgramCompiler(ontology, normalize=oracle._normalize, hard_mode=hard_mode)
+
+    _dropout = 0.0
+
+    # ---- reference surface -------------------------------------------------------------------------------
+
+    def parameter_count(self):
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    def save(self, export_path_base):
+        torch.save(self.state_dict(), os.path.join(export_path_base, self._name))
+
+    def load(self, import_path_base):
+        self.load_state_dict(torch.load(os.path.join(import_path_base, self._name)), strict=False)
+
+    def oracle_parameters(self):
+        return self._weights.parameters()
+
+    # ---- helpers -----------------------------------------------------------------------------------------
+
+    @staticmethod
+    def _object_counts(pb):
+        cached = getattr(pb, '_dfol_counts', None)
+        if cached is not None:
+            return cached
+        bidx = pb._object_batch_index
+        host = bidx.cpu() if bidx.is_cuda else bidx
+        host = host.to(torch.int64)
+        assert bool((host[1:] >= host[:-1]).all()), 'object rows must be grouped by image'
+        counts = torch.bincount(host).tolist()
+        pb._dfol_counts = counts
+        return counts
+
+    def compiled(self, pb, give_answer):
+        cache = getattr(pb, '_dfol_compiled', None)
+        if cache is None:
+            cache = {}
+            pb._dfol_compiled = cache
+        key = bool(give_answer and self._hard_mode)
+        if key not in cache:
+            cache[key] = self._compiler.compile(pb, self._object_counts(pb), give_answer=give_answer)
+        return cache[key]
+
+    def _check_mode(self, is_training):
+        if is_training and self.training and self._dropout > 0:
+            raise NotImplementedError('dropout > 0 in training mode is not implemented in the fused path yet '
+                                      '(set dropout: 0.0); SURVEY.md §7 hard parts')
+
+    # ---- forward -----------------------------------------------------------------------------------------
+
+    def forward(self, program_batch_list, is_training, return_trace=False, modulator_switch=True):
+        self._check_mode(is_training)
+        give_answer = not is_training
+        params = self._weights.parameters()
+        need_grad = is_training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        lps, metas, traces = [], [], []
+        for pb in program_batch_list:
+            feats = pb._object_features
+            if not feats.is_cuda:
+                raise RuntimeError('dfol_vqa_b200 runs on CUDA only (no CPU fallback): move the program batch to the '
+                                   'GPU first (ProgramBatch.to_cuda)')
+            feats = feats.float().contiguous()
+            counts = self._object_counts(pb)
+            layout = SceneLayout.get(counts, self._weights.emb.weight.shape[0], len(self._ontology._relation_index),
+                                     feats.device)
+            cp = self.compiled(pb, give_answer)
+            lp = _ReasoningFunction.apply(self._engine, cp, layout, feats, need_grad, *params)
+            lps.append(lp)
+            metas.append(cp)
+            traces.append([])
+        result = self._gather(lps, metas, give_answer)
+        if return_trace:
+            return result, traces
+        return result
+
+    def _gather(self, lps, metas, give_answer):
+        """gather_results (reference: nsvqa/nn/interpreter/data_parallel.py:15-50) + host-side answers."""
+        kind = metas[0].kind
+        lp = lps[0] if len(lps) == 1 else torch.cat(lps)
+        answer, answer_lp, options = [], [], []
+        if kind == QUERY:
+            for cp in metas:
+                options += [list(o) if not isinstance(o, tuple) else o for o in cp.options]
+        elif kind == BINARY:
+            options = ['no', 'yes']
+        if give_answer:
+            host = lp.detach().cpu().numpy()
+            start = 0
+            for cp in metas:
+                a, alp = self._answers(cp, host[start:start + cp.lp_num])
+                answer += a
+                answer_lp += alp
+                start += cp.lp_num
+        return {'answer': answer, 'log_probability': lp, 'options': options, 'variable_set': None, 'type': kind,
+                'cumulative_loss': 0, 'variable_sets_num': 0, 'answer_log_probability': answer_lp}
+
+    def _answers(self, cp, lp):
+        """Host-side answer lists from the log-probabilities (reference: batch_gqa_ops.py:222-225, 404-407, 744-748,
+        util.find_max_ind util.py:64-66)."""
+        if cp.kind == STATEMENT:
+            return [[n] for n in cp.names], []
+        if cp.kind == BINARY:
+            p = np.exp(lp.astype(np.float32))
+            ans = [['yes'] if v > 0.5 else ['no'] for v in p]
+            alp = [[math.log(float(v))] if v > 0.5 else [math.log(1.0 - float(v))] for v in p]
+            return ans, alp
+        if cp.terminal == 'compare':
+            ans, alp = [], []
+            for q, opt in enumerate(cp.options):
+                pair = lp[2 * q:2 * q + 2]
+                k = int(np.argmax(pair))
+                ans.append([opt[k]])
+                alp.append([float(pair[k])])
+            return ans, alp
+        ans, alp = [], []
+        p = np.exp(lp.astype(np.float32))
+        for q, opts in enumerate(cp.options):
+            a, b = int(cp.seg[q]), int(cp.seg[q + 1])
+            seg = p[a:b]
+            keep = (seg == seg.max()) & (seg > self._likelihood_threshold)
+            ans.append([o for o, k in zip(opts, keep) if k])
+            alp.append([float(v) for v, k in zip(lp[a:b], keep) if k])
+        return ans, alp
+
+
+def targets_of(cp, answers):
+    """Loss targets of VQATrainer._compute_loss (reference: nsvqa/train/trainer.py:185-230) as a float array."""
+    if cp.kind == BINARY:
+        return np.asarray([1.0 if a in YES else 0.0 for a in answers], dtype=np.float32)
+    if cp.kind == QUERY:
+        return np.asarray([1.0 if a == o else 0.0 for a, op in zip(answers, cp.options) for o in op], dtype=np.float32)
+    return np.zeros(cp.lp_num, dtype=np.float32)
+
+
+class FusedTrainStep(object):
+    """One training step of VQATrainer._train_batch (reference: nsvqa/train/trainer.py:429-442) without leaving
+    libdfol_b200: scene + programs forward, loss, backward, (NCCL gradient all-reduce), clip_grad_norm_, Adam.
+
+    All trainable oracle parameters are re-homed into one flat fp32 bucket (gradients likewise), so the
+    data-parallel exchange is a single all-reduce and clip/Adam are one kernel each over the bucket.
+    """
+
+    def __init__(self, interpreter, lr=1e-4, weight_decay=1e-10, clip_norm=0.65, betas=(0.9, 0.999), eps=1e-8,
+                 process_group=None):
+        self.interp = interpreter
+        self.engine = interpreter._engine
+        self.lr, self.wd, self.clip = lr, weight_decay, clip_norm
+        self.betas, self.eps = betas, eps
+        self.group = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        params = interpreter.oracle_parameters()
+        self.params = params
+        dev = params[0].device
+        sizes = [p.numel() for p in params]
+        self.flat = torch.empty(sum(sizes), device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros_like(self.flat)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.grads = {}
+        off = 0
+        for p, n in zip(params, sizes):
+            self.flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + n].view_as(p)
+            self.grads[id(p)] = self.flat_grad[off:off + n].view_as(p)
+            off += n
+        self.step_count = 0
+        self.scalars = torch.zeros(2, device=dev, dtype=torch.float32)  # [loss, grad sumsq]
+
+    def _targets(self, pb, cp, dev):
+        t = getattr(pb, '_dfol_targets', None)
+        if t is None or t.device != dev:
+            t = torch.from_numpy(targets_of(cp, pb._answers)).to(dev, non_blocking=True)
+            pb._dfol_targets = t
+        return t
+
+    def forward_backward(self, program_batch_list, global_question_num=None):
+        """Accumulates gradients of loss / global_question_num into the flat bucket; returns the device loss scalar
+        (local share)."""
+        interp = self.interp
+        interp._check_mode(True)
+        total = global_question_num or sum(pb.batch_size() for pb in program_batch_list)
+        scale = 1.0 / float(total)
+        self.flat_grad.zero_()
+        self.scalars.zero_()
+        for pb in program_batch_list:
+            feats = pb._object_features
+            if not feats.is_cuda:
+                raise RuntimeError('dfol_vqa_b200 runs on CUDA only (no CPU fallback)')
+            dev = feats.device
+            st = capi.stream_ptr(dev)
+            counts = interp._object_counts(pb)
+            layout = SceneLayout.get(counts, interp._weights.emb.weight.shape[0],
+                                     len(interp._ontology._relation_index), dev)
+            cp = interp.compiled(pb, False)
+            scene = self.engine.build_scene(feats, layout)
+            lp, tape = self.engine.run_programs(cp, scene, save_tape=True)
+            target = self._targets(pb, cp, dev)
+            d_lp = torch.empty_like(lp)
+            seg = self.engine.upload_programs(cp, dev).get('seg')
+            call('dfol_loss_fwd_bwd', ptr(lp), ptr(target), ptr(seg), cp.question_num, cp.lp_num, cp.kind, scale,
+                 ptr(self.scalars), ptr(d_lp), st)
+            self.engine.backward(cp, scene, tape, d_lp, self.grads)
+        return self.scalars[0]
+
+    def optimizer_step(self):
+        dev = self.flat.device
+        st = capi.stream_ptr(dev)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_grad, group=self.group)
+        self.step_count += 1
+        call('dfol_sumsq', ptr(self.flat_grad), self.flat_grad.numel(), ptr(self.scalars[1:]), st)
+        call('dfol_adam_step', ptr(self.flat), ptr(self.flat_grad), ptr(self.m), ptr(self.v), self.flat.numel(),
+             ptr(self.scalars[1:]), self.clip, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+             self.step_count, st)
+
+    def step(self, program_batch_list, global_question_num=None):
+        loss = self.forward_backward(program_batch_list, global_question_num)
+        self.optimizer_step()
+        return loss

@@ -1,0 +1,206 @@
+/*
+ * dfol_b200.h -- C ABI of libdfol_b200.so: the B200 (sm_100a) kernels of the differentiable-FOL reasoning path.
+ *
+ * The reference (microsoft/DFOL-VQA) is pure Python/PyTorch and has no FFI; each entry point below states the
+ * reference interface it replaces (file:line under src/ of the reference).  INTEGRATION.md shows the binding a
+ * reference maintainer would add (ctypes).
+ *
+ * Conventions:
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless named h_*;
+ *  - the caller owns all buffers (including workspaces); the library never allocates, frees or keeps a pointer;
+ *  - every call is asynchronous on the given stream (cudaStream_t passed as void*); no host synchronisation;
+ *  - return value 0 = success, >0 = cudaError_t of the launch, <0 = argument error; dfol_last_error() returns a
+ *    thread-local message for the last non-zero return;
+ *  - fp32 tables; indices int32 (int64 for element offsets of the big tables).
+ *
+ * Device layout of a scene (one program batch = B questions = B images, image b has N_b objects):
+ *  - object rows are concatenated raggedly: image b owns rows [obj_row[b], obj_row[b+1]);
+ *  - pair rows enumerate (b, s, o) for ALL s,o in [0,N_b) (self pairs included; their table entries are -30):
+ *    image b owns pair rows [pair_row[b], pair_row[b+1]), local index l = s*N_b + o;
+ *  - attribute table: image block b starts at element attr_blk[b] and is [C][attr_stride[b]] (concept-major,
+ *    attr_stride[b] = N_b rounded up to 4) -- a Filter reads one contiguous row of N_b floats;
+ *  - relation table: image block b starts at element rel_blk[b] and is [nR][rel_stride[b]] with
+ *    rel_stride[b] = N_b*N_b rounded up to 4 -- a Relate reads one contiguous N_b x N_b tile.
+ */
+#ifndef DFOL_B200_H
+#define DFOL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFOL_ABI_VERSION 1
+
+/* activation codes (RegularMLP / EmbeddingLayer, gqa_interpreter_experiments.py:28-33, :71-72) */
+#define DFOL_ACT_NONE 0
+#define DFOL_ACT_ELU 1
+#define DFOL_ACT_SIGMOID 2
+#define DFOL_ACT_LOGSIGMOID 3
+
+/* epilogue multiplier codes for backward GEMMs: dZ = dH * act'(.) evaluated from the saved activation */
+#define DFOL_MUL_NONE 0
+#define DFOL_MUL_SIGMOID_GRAD 1 /* h*(1-h) */
+#define DFOL_MUL_ELU_GRAD 2     /* h>0 ? 1 : h+1 */
+
+int dfol_version(void);
+const char* dfol_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Dense contractions of the visual oracle.
+ * Replaces the nn.Linear + activation chains of RegularMLP / EmbeddingLayer (gqa_interpreter_experiments.py:
+ * 18-77) as called from featurize_scene (nsvqa/data/batch_gqa_boxfeatures_pipeline.py:204) and
+ * ClassifierOracle.compute_all_log_likelihood_2 (nsvqa/nn/vision/classifier_oracle.py:145-156), and their
+ * autograd backward.
+ *
+ * C = epilogue( sum_k A(m,k) * B(k,n) ),  A(m,k) = A[m*sam + k*sak],  B(k,n) = B[k*sbk + n*sbn]  (fp32).
+ * epilogue: + bias[n]; activation `act`; * multiplier from mul_src[m*ld_mul + n]; then
+ *   store == 0: C[m*ldc + n]  (accumulate != 0 adds to the existing value)
+ *   store == 1: per-image transposed table store, C[img_blk[b] + n*img_stride[b] + (m - img_row[b])] with
+ *               b = row_img[m]; if img_n != NULL rows with s == o (self pairs) are written as diag_value.
+ * split_k > 1 splits K over grid.z and atomically adds into C (C must be zeroed; bias/act/mul must be off).
+ * fp32 SIMT kernel: the parity path (bit-level behaviour of fp32 FMA accumulation).
+ */
+int dfol_gemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C,
+                  int64_t ldc, const float* bias, int M, int N, int K, int act, int accumulate, int split_k,
+                  const float* mul_src, int64_t ld_mul, int mul_mode, int store, const int32_t* row_img,
+                  const int32_t* img_row, const int64_t* img_blk, const int32_t* img_stride, const int32_t* img_n,
+                  float diag_value, void* stream);
+
+/* bf16 tensor-core GEMM (tcgen05.mma, TMA-staged operands, fp32 accumulation in TMEM), same epilogue contract.
+ * A is [M,K] row-major bf16 (lda elements), B is [N,K] row-major bf16 (ldb elements) i.e. C = A * B^T.
+ * K must be a multiple of 64 (pad with zeros), lda/ldb >= K and multiples of 8, A/B 16-byte aligned.
+ * store == 0: row-major C with ldc elements per row, bf16 if out_bf16 != 0 else fp32; columns N <= n < ldc are
+ * written as ZERO so that C can be the (K-padded) A operand of the next layer.  store == 1: fp32 table store.
+ * The TMA tensor maps are encoded inside the call (host side, no device work). */
+int dfol_gemm_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                      const float* bias, int M, int N, int K, int act, int out_bf16, int store,
+                      const int32_t* row_img, const int32_t* img_row, const int64_t* img_blk,
+                      const int32_t* img_stride, const int32_t* img_n, float diag_value, void* stream);
+
+/* fp32 -> bf16 cast with row padding: dst[r*ldd + c] = bf16(src[r*lds + c]) for c < cols, 0 for cols <= c < ldd */
+int dfol_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Featurizer tail + pairwise hidden layer.
+ * dfol_box_position: obj[t, F:F+4] = [x,y,w,h] / max([W,H,W,H],1)   (batch_gqa_boxfeatures_pipeline.py:208-211)
+ * dfol_pair_hidden_fwd: first layer of the relation network on the pair feature
+ *   [obj_s | obj_o | dist | asin(dy/dist) | sign(x_o-x_s) | sign(y_o-y_s)]  (:257-279), evaluated WITHOUT
+ *   materialising the (P,2F+12) pair matrix:  h = act( U[s] + V[o] + Wg . geo(s,o) + b )  where
+ *   U = obj.Ws^T, V = obj.Wo^T are the two halves of the first Linear (uv[t, 0:H] = U, uv[t, H:2H] = V) and Wg its
+ *   last four input columns (wg[h*ldw + j], j<4).  One output row per pair row (self pairs included); fp32, or
+ *   bf16 with columns H..ldh zero-filled when out_bf16 != 0 (operand of the next tensor-core GEMM).
+ * dfol_pair_hidden_bwd: given dH (pair rows x H) and the saved H: dZ = dH*act'(H); duv[s,0:H] += sum_o dZ,
+ *   duv[o,H:2H] += sum_s dZ, dwg[h*ldw + j] += sum dZ*geo_j, db[h] += sum dZ  (duv, dwg, db must be zeroed).
+ */
+int dfol_box_position(const float* features, int64_t ldf, int feature_dim, float* obj, int64_t ldo, int out_col,
+                      int64_t rows, void* stream);
+int dfol_pair_hidden_fwd(const float* uv, int64_t lduv, const float* obj_pos, int64_t ldpos, const float* wg,
+                         int64_t ldw, const float* bias, void* h_out, int64_t ldh, int H, int act, int out_bf16,
+                         const int32_t* pair_img, const int32_t* pair_row, const int32_t* obj_row,
+                         const int32_t* img_n, int64_t pair_rows, void* stream);
+int dfol_pair_hidden_bwd(const float* dh, int64_t lddh, const float* h_saved, int64_t ldh, const float* obj_pos,
+                         int64_t ldpos, float* duv, int64_t lduv, float* dwg, int64_t ldw, float* dbias, int H,
+                         int act, const int32_t* pair_row, const int32_t* obj_row, const int32_t* img_n,
+                         int image_num, void* stream);
+
+/* in place dH[m,n] *= act'(.) evaluated from the saved activation output H[m,n] (act = DFOL_ACT_*) */
+int dfol_act_grad_mul(float* dH, int64_t lddh, const float* H, int64_t ldh, int64_t rows, int cols, int act,
+                      void* stream);
+
+/* column sums: out[n] += sum_m X[m*ldx + n]  (bias gradients) */
+int dfol_colsum(const float* X, int64_t ldx, int64_t M, int N, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Program interpreter: executes compiled FOL programs, one thread block per question.
+ * Replaces BatchInterpreterBase.forward's execution loop (nsvqa/nn/interpreter/batch_base_interpreter.py:
+ * 147-172), the op modules (batch_gqa_ops.py:160-780, batch_base_ops.py:42-215, 311-405, 483-596), the
+ * per-op oracle gather (nsvqa/nn/vision/classifier_oracle.py:44-137), BatchVariableSet.log_probability /
+ * gate (batch_base_types.py:103-168) and the log-space primitives (util.py:17-47).
+ *
+ * instr: int32[n_instr][DFOL_INSTR_WORDS], question q executes instr[q_instr[q] .. q_instr[q+1]).
+ * opts : int32 option columns (bit 30 = negated) referenced by terminal instructions.
+ * lp_out: log-probabilities, written at instr.out (+k per option).
+ * tape  : optional [n_instr][tape_stride] floats, the attention BEFORE each instruction (for backward).
+ * Backward: d_lp (same indexing as lp_out) -> g_attr / g_rel: compact gradient slices w.r.t. the RAW table
+ * entries each instruction read (offsets in instr words GA0/GA1/GR; slices of one option list are consecutive
+ * with stride attr_stride[b] / rel_stride[b]); buffers must be zeroed by the caller.
+ */
+#define DFOL_INSTR_WORDS 12
+#define DFOL_I_OP 0
+#define DFOL_I_FLAGS 1
+#define DFOL_I_A0 2   /* concept / relation column, or first option index */
+#define DFOL_I_A1 3   /* option count, or name column of a relate */
+#define DFOL_I_A2 4   /* name column of choose_rel */
+#define DFOL_I_OUT 5  /* index into lp_out */
+#define DFOL_I_GA0 6  /* g_attr offset of the primary attribute operand (or of option 0) */
+#define DFOL_I_GA1 7  /* g_attr offset of the name operand of relate / choose_rel */
+#define DFOL_I_GR 8   /* g_rel offset of the relation operand (or of option 0) */
+
+#define DFOL_OP_SELECT 1
+#define DFOL_OP_FILTER 2
+#define DFOL_OP_RELATE 3
+#define DFOL_OP_PUSH 4        /* end of the first branch: saved = cur */
+#define DFOL_OP_EXIST 16      /* exist / end / tail of verify_rel */
+#define DFOL_OP_AND 17
+#define DFOL_OP_OR 18
+#define DFOL_OP_VERIFY_ATTRS 19
+#define DFOL_OP_CHOOSE_ATTR 20 /* choose_attr / query_attr */
+#define DFOL_OP_CHOOSE_REL 21
+#define DFOL_OP_ALL_SAME 22    /* flag NEGATE_RESULT -> all_different */
+#define DFOL_OP_TWO_SAME 23    /* flag NEGATE_RESULT -> two_different */
+#define DFOL_OP_COMPARE 24
+
+#define DFOL_F_NEG 1            /* primary predicate is not(.) */
+#define DFOL_F_ROUNDTRIP 2      /* some predicate of the op slot is negated: ll <- slog(exp(ll)) for the others */
+#define DFOL_F_SUBJECT 4        /* relate: the new object is the subject */
+#define DFOL_F_NAME_NEG 8
+#define DFOL_F_NAME_ROUNDTRIP 16
+#define DFOL_F_NORMALISE 32     /* softmax over the question's options (per object / per pair) */
+#define DFOL_F_NEGATE_RESULT 64
+#define DFOL_F_IS_LESS 128
+#define DFOL_F_HARD 256         /* hard-mode quantifier (min instead of sum), eval only */
+#define DFOL_OPT_NEG (1 << 30)
+
+int dfol_program_fwd(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
+                     const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
+                     const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride, const int32_t* img_n,
+                     float* lp_out, float* tape, int tape_stride, void* stream);
+int dfol_program_bwd(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
+                     const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
+                     const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride, const int32_t* img_n,
+                     const float* d_lp, const float* tape, int tape_stride, float* g_attr, float* g_rel,
+                     void* stream);
+
+/* Loss of VQATrainer._compute_loss (nsvqa/train/trainer.py:181-262) and its derivative w.r.t. lp.
+ * kind 0 BINARY: BCE(exp(lp), target) summed; 1 QUERY: sum_q slog(sum_{k in q} e^{lp_k}) - sum_k target_k lp_k
+ * (seg[q]..seg[q+1] are question q's predicates); 2 STATEMENT: -sum lp.  loss_out[0] += scale * loss,
+ * d_lp = scale * dloss/dlp (scale = 1 / total question count, trainer.py:434-435). */
+int dfol_loss_fwd_bwd(const float* lp, const float* target, const int32_t* seg, int n_seg, int n_lp, int kind,
+                      float scale, float* loss_out, float* d_lp, void* stream);
+
+/* Backward of the table (last) layer, consuming the compact gradient slices of dfol_program_bwd.
+ * For slice j = (image b, table column c): dz[l] = g[goff[j] + l] * (1 - exp(LL[b][c][l])) (logsigmoid');
+ * dH[(row0[b] + l), :] += dz[l] * W[wrow[j], :];  dW[wrow[j], :] += sum_l dz[l] * Hsaved[row0[b] + l, :];
+ * db[wrow[j]] += sum_l dz[l].  Slices are grouped by image: image b owns slices [img_slice[b], img_slice[b+1]).
+ * dH rows of an image are owned by one thread block (no atomics); dW/db use atomics.  All outputs zeroed by the
+ * caller (dH must be zero for images without slices). */
+int dfol_table_layer_bwd(const float* g, const int32_t* slice_goff, const int32_t* slice_col,
+                         const int32_t* slice_wrow, const int32_t* img_slice, int image_num, const float* ll,
+                         const int64_t* blk, const int32_t* stride, const int32_t* row0, const int32_t* img_rows,
+                         const float* W, int64_t ldw, const float* h_saved, int64_t ldh, int E, float* dH,
+                         int64_t lddh, float* dW, float* db, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Optimiser step on the flat parameter bucket: clip_grad_norm_ + Adam (trainer.py:438-441,
+ * gqa_interpreter_experiments.py:261: torch.optim.Adam(lr, weight_decay) = L2 added to the gradient).
+ * dfol_sumsq: out[0] += sum g^2.  dfol_adam_step: coef = min(1, clip / (sqrt(sumsq[0]) + 1e-6)) applied to g. */
+int dfol_sumsq(const float* g, int64_t n, float* out, void* stream);
+int dfol_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq, float clip_norm,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFOL_B200_H */

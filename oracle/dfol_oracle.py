@@ -446,10 +446,11 @@ def compute_loss(results, answer_lists):
         return -lp.sum()
     answers = [a for al in answer_lists for a in al]
     if kind == BINARY:
-        target = torch.tensor([1.0 if a in YES else 0.0 for a in answers], dtype=lp.dtype)
+        target = torch.tensor([1.0 if a in YES else 0.0 for a in answers], dtype=lp.dtype, device=lp.device)
         return F.binary_cross_entropy(lp.exp(), target, reduction='sum')
     options = [o for r in results for o in r['options']]
-    target = torch.tensor([1.0 if a == o else 0.0 for a, op in zip(answers, options) for o in op], dtype=lp.dtype)
+    target = torch.tensor([1.0 if a == o else 0.0 for a, op in zip(answers, options) for o in op], dtype=lp.dtype,
+                          device=lp.device)
     sizes = [len(op) for op in options]
     total = lp.new_zeros(())
     start = 0

@@ -77,9 +77,25 @@ CASES = [
 ]
 
 
+def well_conditioned(case):
+    """No saturated outputs: log(1 - e^x) near x = 0 amplifies one-ulp differences between exp/log
+    implementations (SURVEY.md §7 'ill-conditioned log(1-e^x)'), which would make parity on such a fixture a test
+    of libm rounding, not of the algorithm.  Saturated cases are covered separately by the oracle-vs-CUDA tests
+    with a probability-space tolerance."""
+    lp = case['ref32']['log_probability']
+    l32, l64 = float(case['ref32']['loss']), float(case['ref64']['loss'])
+    return float(lp.max()) < -1e-3 and float(lp.min()) > -12.0 and abs(l32 - l64) <= 2e-6 * max(1.0, abs(l64))
+
+
 def main():
     for terminal, batch, n_max, lo, hi, seed, split in CASES:
-        case = build_case(terminal, batch, n_max, lo, hi, seed, split)
+        for attempt in range(50):  # deterministic seed search for a well-conditioned fixture
+            case = build_case(terminal, batch, n_max, lo, hi, seed + 100 * attempt, split)
+            if well_conditioned(case):
+                break
+        else:
+            raise RuntimeError('no well-conditioned seed for %s' % terminal)
+        case['seed'] = seed + 100 * attempt
         name = 'golden_%s_s%d.pt' % (terminal, split)
         torch.save(case, os.path.join(HERE, name))
         r32, r64 = case['ref32'], case['ref64']

@@ -1,0 +1,223 @@
+"""Kernel-level GPU tests through the C ABI: GEMMs (fp32 SIMT and bf16 tcgen05), loss, Adam, bf16-mode forward."""
+
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import dfol_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _table_maps(counts, ncols, pairs, dev):
+    n = np.asarray(counts, dtype=np.int64)
+    rows = n * n if pairs else n
+    stride = (rows + 3) // 4 * 4
+    row0 = np.concatenate([[0], np.cumsum(rows)])
+    blk = ncols * np.concatenate([[0], np.cumsum(stride)])
+    t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a.astype(d))).to(dev)
+    maps = {'row_img': torch.repeat_interleave(torch.arange(len(counts), dtype=torch.int32), torch.from_numpy(rows)).to(dev),
+            'img_row': t(row0, np.int32), 'img_blk': t(blk[:-1], np.int64), 'img_stride': t(stride, np.int32)}
+    if pairs:
+        maps['img_n'] = t(n, np.int32)
+        maps['diag'] = -30.0
+    return maps, int(row0[-1]), int(blk[-1]), row0, blk, stride
+
+
+def _act(x, act):
+    if act == 1:
+        return torch.nn.functional.elu(x)
+    if act == 2:
+        return torch.sigmoid(x)
+    if act == 3:
+        return torch.nn.functional.logsigmoid(x)
+    return x
+
+
+@pytest.mark.parametrize('M,N,K', [(1, 1, 1), (130, 70, 33), (257, 300, 256), (1000, 333, 300), (64, 512, 2048)])
+@pytest.mark.parametrize('act', [0, 1, 2, 3])
+def test_gemm_f32_forward(M, N, K, act):
+    from dfol_vqa_b200.engine import gemm_f32
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K + 3, generator=g)[:, :K]
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    C = torch.empty(M, N, device='cuda')
+    gemm_f32(A.cuda(), W.cuda().t(), C, b.cuda(), act)
+    ref = _act(A.double() @ W.double().t() + b.double(), act)
+    tol = 2e-5 * max(1.0, (K / 256) ** 0.5)
+    assert torch.allclose(C.cpu().double(), ref, rtol=tol, atol=tol)
+
+
+def test_gemm_f32_variants():
+    from dfol_vqa_b200.engine import gemm_f32
+    from dfol_vqa_b200.capi import K as KK
+    g = torch.Generator().manual_seed(3)
+    M, N, Kd = 300, 130, 5000
+    dZ = torch.randn(Kd, M, generator=g).cuda()      # wgrad: C = dZ^T @ X, K = rows
+    X = torch.randn(Kd, N, generator=g).cuda()
+    C = torch.zeros(M, N, device='cuda')
+    gemm_f32(dZ.t(), X, C, split_k=8)
+    ref = dZ.double().t() @ X.double()
+    assert torch.allclose(C.double(), ref, rtol=1e-4, atol=1e-3)
+    C2 = torch.ones(M, N, device='cuda')
+    gemm_f32(dZ.t(), X, C2, accumulate=True)
+    assert torch.allclose(C2.double(), ref + 1.0, rtol=1e-4, atol=1e-3)
+    # dgrad with fused activation-derivative multiplier
+    W = torch.randn(N, 77, generator=g).cuda()
+    Hs = torch.rand(Kd, 77, generator=g).cuda() - 0.3
+    D = torch.empty(Kd, 77, device='cuda')
+    gemm_f32(X, W, D, mul_src=Hs, mul_mode=KK.MUL_ELU_GRAD)
+    ref = (X.double() @ W.double()) * torch.where(Hs > 0, torch.ones_like(Hs), Hs + 1).double()
+    assert torch.allclose(D.double(), ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('pairs', [False, True])
+@pytest.mark.parametrize('impl', ['f32', 'tc'])
+def test_gemm_table_store(pairs, impl):
+    """Per-image transposed table store (+ -30 on self pairs) of both GEMM kernels."""
+    from dfol_vqa_b200.engine import gemm_f32, ReasoningEngine
+    counts = [5, 12, 3, 9, 16]
+    ncols, Kd = 37, 128
+    dev = torch.device('cuda')
+    maps, M, size, row0, blk, stride = _table_maps(counts, ncols, pairs, dev)
+    g = torch.Generator().manual_seed(11)
+    A = torch.randn(M, Kd, generator=g)
+    W = torch.randn(ncols, Kd, generator=g) / Kd ** 0.5
+    b = torch.randn(ncols, generator=g)
+    out = torch.full((size,), float('nan'), device=dev)
+    if impl == 'f32':
+        gemm_f32(A.cuda(), W.cuda().t(), out, b.cuda(), 3, table=maps)
+        ref = _act(A.double() @ W.double().t() + b.double(), 3)
+        tol = dict(rtol=2e-5, atol=2e-6)
+    else:
+        A16, W16 = A.cuda().bfloat16(), W.cuda().bfloat16()
+        ReasoningEngine._tc(A16, W16, out, ncols, Kd, b.cuda(), 3, None, table=maps)
+        ref = _act(A16.cpu().double() @ W16.cpu().double().t() + b.double(), 3)
+        tol = dict(rtol=2e-3, atol=2e-3)
+    out = out.cpu().double()
+    for i, n in enumerate(counts):
+        rows = n * n if pairs else n
+        block = out[int(blk[i]):int(blk[i]) + ncols * int(stride[i])].view(ncols, int(stride[i]))[:, :rows].t()
+        want = ref[int(row0[i]):int(row0[i]) + rows].clone()
+        if pairs:
+            diag = torch.arange(n) * n + torch.arange(n)
+            want[diag] = -30.0
+        assert torch.allclose(block, want, **tol), (i, (block - want).abs().max())
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 16, 64), (300, 300, 256), (1000, 333, 320), (77, 512, 576), (4608, 2335, 320)])
+@pytest.mark.parametrize('act,out16', [(0, False), (2, True), (1, True), (3, False)])
+def test_gemm_bf16_tcgen05(M, N, K, act, out16):
+    """tcgen05/TMA GEMM vs an fp64 product of the same bf16 operands; padding columns of C must be zero."""
+    from dfol_vqa_b200.engine import ReasoningEngine
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g)).cuda().bfloat16()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
+    b = torch.randn(N, generator=g).cuda()
+    ldc = (N + 63) // 64 * 64
+    C = torch.full((M, ldc), float('nan'), device='cuda', dtype=torch.bfloat16 if out16 else torch.float32)
+    ReasoningEngine._tc(A, W, C, N, K, b, act, None)
+    torch.cuda.synchronize()
+    ref = _act(A.cpu().double() @ W.cpu().double().t() + b.cpu().double(), act)
+    got = C.cpu().double()
+    tol = dict(rtol=1.5e-2, atol=1.5e-2) if out16 else dict(rtol=2e-3, atol=2e-3)
+    assert torch.allclose(got[:, :N], ref, **tol), (got[:, :N] - ref).abs().max()
+    assert bool((got[:, N:] == 0).all())
+
+
+@pytest.mark.parametrize('kind', [0, 1, 2])
+def test_loss_kernel(kind):
+    from dfol_vqa_b200.capi import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(5 + kind)
+    n = 37
+    lp = (-torch.rand(n, generator=g) * 4).requires_grad_(True)
+    seg = [0, 3, 5, 12, 20, 37]
+    if kind == 0:
+        target = (torch.rand(n, generator=g) > 0.5).float()
+        ref = torch.nn.functional.binary_cross_entropy(lp.exp(), target, reduction='sum')
+    elif kind == 1:
+        target = torch.zeros(n)
+        target[[1, 4, 7, 15, 30]] = 1
+        ref = sum(orc.safe_log(lp[a:b].exp().sum()) for a, b in zip(seg[:-1], seg[1:])) - (target * lp).sum()
+    else:
+        target = torch.zeros(n)
+        ref = -lp.sum()
+    scale = 1.0 / 6
+    (ref * scale).backward()
+    out = torch.zeros(1, device='cuda')
+    dlp = torch.empty(n, device='cuda')
+    segd = torch.tensor(seg, dtype=torch.int32, device='cuda')
+    lpd, td = lp.detach().cuda(), target.cuda()   # keep the operands alive until the stream has consumed them
+    call('dfol_loss_fwd_bwd', ptr(lpd), ptr(td), ptr(segd), len(seg) - 1, n, kind, scale, ptr(out), ptr(dlp),
+         stream_ptr())
+    assert abs(float(out) - float(ref) * scale) <= 1e-5 * abs(float(ref) * scale) + 1e-7
+    assert torch.allclose(dlp.cpu(), lp.grad, rtol=1e-5, atol=1e-7)
+
+
+def test_clip_adam_matches_torch():
+    """clip_grad_norm_(0.65) + torch.optim.Adam(lr, weight_decay) for three steps (reference trainer.py:438-441)."""
+    from dfol_vqa_b200.capi import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(9)
+    p0 = torch.randn(5000, generator=g)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-2, weight_decay=1e-3)
+    p = p0.clone().cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        grad = torch.randn(5000, generator=g) * (3.0 if step == 2 else 0.001)
+        p_ref.grad = grad.clone()
+        torch.nn.utils.clip_grad_norm_([p_ref], 0.65)
+        opt.step()
+        ss = torch.zeros(1, device='cuda')
+        gd = grad.cuda()
+        call('dfol_sumsq', ptr(gd), gd.numel(), ptr(ss), stream_ptr())
+        call('dfol_adam_step', ptr(p), ptr(gd), ptr(m), ptr(v), p.numel(), ptr(ss), 0.65, 1e-2, 0.9, 0.999, 1e-8, 1e-3,
+             step, stream_ptr())
+        assert torch.allclose(p.cpu(), p_ref.detach(), rtol=1e-5, atol=1e-6), step
+
+
+@pytest.mark.parametrize('terminal', ['exist', 'verify_rel', 'query_attr', 'choose_rel'])
+def test_bf16_mode_answer_logits(terminal):
+    """bf16-GEMM mode (tcgen05 scene build): answer logits within 2e-2 of the fp32 oracle and identical argmax
+    answers (north_star tolerance)."""
+    from dfol_vqa_b200 import synth
+    from dfol_vqa_b200.ontology import synthetic_ontology
+    from dfol_vqa_b200.programs import ProgramCollater
+    dims = dict(box=2048, feat=512, hidden=256, emb=300)
+    ont = synthetic_ontology(400, 60, 6, 5, seed=3, embedding_dim=300)
+    interp = helpers.build_interpreter(ont, dims, seed=5, gemm_mode='bf16')
+    questions = synth.make_questions(ont, 12, terminal, 1, 4, seed=21)
+    counts = synth.object_counts(12, 40, True, seed=22)
+    feats, bidx = synth.make_object_features(counts, 2048, seed=23)
+    pbs = ProgramCollater(1, lambda qs: (feats, bidx)).collate(questions)
+    params = helpers.oracle_params(interp)
+    with torch.no_grad():
+        results, _ = orc.run_step(ont, params, ProgramCollater(1, lambda qs: (feats, bidx)).collate(
+            json.loads(json.dumps(questions))), is_training=False)
+    interp.eval()
+    with torch.no_grad():
+        out = interp(helpers.to_cuda(pbs), False)
+    lp = out['log_probability'].cpu()
+    ref = results[0]['log_probability']
+    assert (lp - ref).abs().max() <= 2e-2 * max(1.0, float(ref.abs().max())), float((lp - ref).abs().max())
+    # identical answers wherever the oracle's decision margin exceeds the bf16 tolerance
+    p = ref.exp()
+    checked = 0
+    if out['type'] == 0:
+        for q, (a, b) in enumerate(zip(out['answer'], results[0]['answer'])):
+            if abs(float(p[q]) - 0.5) > 0.05:
+                assert a == b, (q, a, b)
+                checked += 1
+    else:
+        start = 0
+        for q, opts in enumerate(results[0]['options']):
+            seg = p[start:start + len(opts)].sort(descending=True)[0]
+            start += len(opts)
+            if len(opts) == 1 or float(seg[0] - seg[1]) > 0.05 * float(seg[0]):
+                assert sorted(out['answer'][q]) == sorted(results[0]['answer'][q]), q
+                checked += 1
+    assert checked > 0

@@ -1,0 +1,171 @@
+"""Parity of the CUDA path (through the C ABI) with the reference goldens and with the CPU oracle. Needs a GPU."""
+
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import dfol_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _ids(p):
+    return p.split('golden_')[-1][:-3]
+
+
+def _align(ours_opts, ref_opts, lp):
+    perm, start = [], 0
+    for mine, theirs in zip(ours_opts, ref_opts):
+        perm += [start + theirs.index(m) for m in mine]
+        start += len(theirs)
+    return lp[perm]
+
+
+@pytest.mark.parametrize('path', helpers.golden_files(), ids=_ids)
+def test_forward_backward_matches_reference_golden(path):
+    """fp32 mode: log-probabilities, loss and all 12 parameter gradients against the recorded reference run."""
+    from dfol_vqa_b200.interpreter import FusedTrainStep
+    case = helpers.load_golden(path)
+    ont = helpers.ontology_of(case)
+    interp = helpers.build_interpreter(ont, case['dims'], case['state'])
+    pbs = helpers.to_cuda(helpers.program_batches_of(case))
+    ref32, ref64 = case['ref32'], case['ref64']
+
+    # (1) drop-in surface: forward in training mode + torch autograd through the custom Function
+    interp.train()
+    result = interp(pbs, True)
+    lp = result['log_probability']
+    assert result['type'] == ref32['type']
+    ref_lp, ref64_lp = ref32['log_probability'], ref64['log_probability']
+    if ref32['type'] == 1 and case['terminal'] != 'compare':
+        assert [sorted(o) for o in result['options']] == [sorted(o) for o in ref32['options']]
+        ref_lp = _align(result['options'], ref32['options'], ref_lp)
+        ref64_lp = _align(result['options'], ref32['options'], ref64_lp)
+    ok, worst = helpers.close_to_reference(lp.detach().cpu(), ref_lp, ref64_lp)
+    assert ok, ('log_probability', worst)
+
+    # loss exactly as the reference trainer computes it, then autograd into our backward kernels
+    answers = [a for pb in pbs for a in pb._answers]
+    res_cpu_like = {'log_probability': lp, 'type': result['type'], 'options': result['options']}
+    loss = orc.compute_loss([res_cpu_like], [answers]) / len(answers)
+    loss.backward()
+    assert abs(float(loss) - float(ref32['loss'])) <= 1e-5 * max(1.0, abs(float(ref32['loss']))) + \
+        4 * abs(float(ref32['loss']) - float(ref64['loss']))
+    sd_keys = {id(p): k for k, p in interp.named_parameters()}
+    checked = 0
+    for p in interp.oracle_parameters():
+        k = sd_keys[id(p)]
+        g32, g64 = ref32['grads'][k], ref64['grads'][k]
+        scale = g64.abs().max().clamp(min=1e-12)
+        err = (p.grad.detach().cpu().double() - g32.double()).abs().max()
+        noise = (g32.double() - g64).abs().max()
+        assert err <= 1e-5 * scale + 4 * noise + 1e-9, (k, float(err), float(scale), float(noise))
+        checked += 1
+    assert checked == 12
+
+    # (2) fused train step: same gradients in the flat bucket, loss from the loss kernel
+    interp.zero_grad()
+    step = FusedTrainStep(interp)
+    loss2 = step.forward_backward(pbs)
+    assert abs(float(loss2) - float(ref32['loss'])) <= 1e-5 * max(1.0, abs(float(ref32['loss']))) + \
+        4 * abs(float(ref32['loss']) - float(ref64['loss']))
+    for p in interp.oracle_parameters():
+        k = sd_keys[id(p)]
+        g32, g64 = ref32['grads'][k], ref64['grads'][k]
+        scale = g64.abs().max().clamp(min=1e-12)
+        err = (step.grads[id(p)].cpu().double() - g32.double()).abs().max()
+        noise = (g32.double() - g64).abs().max()
+        assert err <= 1e-5 * scale + 4 * noise + 1e-9, ('fused', k, float(err), float(scale))
+
+
+@pytest.mark.parametrize('path', helpers.golden_files(), ids=_ids)
+def test_eval_answers_match_reference_golden(path):
+    case = helpers.load_golden(path)
+    ont = helpers.ontology_of(case)
+    interp = helpers.build_interpreter(ont, case['dims'], case['state'])
+    pbs = helpers.to_cuda(helpers.program_batches_of(case))
+    interp.eval()
+    with torch.no_grad():
+        result = interp(pbs, False)
+    assert [sorted(a) for a in result['answer']] == [sorted(a) for a in case['ref32']['answer']]
+
+
+def test_scene_tables_match_reference_golden():
+    """Attribute / relation tables of the fused scene build against the reference's compute_all_log_likelihood_2."""
+    from dfol_vqa_b200.engine import SceneLayout
+    path = [p for p in helpers.golden_files() if 'verify_rel' in p][0]
+    case = helpers.load_golden(path)
+    ont = helpers.ontology_of(case)
+    interp = helpers.build_interpreter(ont, case['dims'], case['state'])
+    counts = case['counts']
+    C, nR = len(ont._vocabulary['idx_to_arg']), len(ont._relation_index)
+    layout = SceneLayout.get(counts, C, nR, torch.device('cuda', 0))
+    scene = interp._engine.build_scene(case['features'].cuda(), layout)
+    ref = case['ref32']['scene']
+    attr = scene.attr_ll.cpu()
+    a_blk, a_str = layout.attr_blk.cpu(), layout.attr_stride.cpu()
+    rows = []
+    for b, n in enumerate(counts):
+        blk = attr[int(a_blk[b]):int(a_blk[b]) + C * int(a_str[b])].view(C, int(a_str[b]))
+        rows.append(blk[:, :n].t())
+    assert torch.allclose(torch.cat(rows), ref['attr'], rtol=1e-5, atol=1e-6)
+    rel = scene.rel_ll.cpu()
+    r_blk, r_str = layout.rel_blk.cpu(), layout.rel_stride.cpu()
+    img, s, o = ref['index']
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    mine = []
+    for b, si, oi in zip(img.tolist(), s.tolist(), o.tolist()):
+        n = counts[b]
+        blk = rel[int(r_blk[b]):int(r_blk[b]) + nR * int(r_str[b])].view(nR, int(r_str[b]))
+        mine.append(blk[:, (si - starts[b]) * n + (oi - starts[b])])
+    assert torch.allclose(torch.stack(mine), ref['rel'], rtol=1e-5, atol=1e-6)
+    for b, n in enumerate(counts):
+        blk = rel[int(r_blk[b]):int(r_blk[b]) + nR * int(r_str[b])].view(nR, int(r_str[b]))
+        assert bool((blk[:, [i * n + i for i in range(n)]] == -30.0).all())
+
+
+@pytest.mark.parametrize('terminal,batch,n_max,ragged', [
+    ('exist', 16, 48, False), ('verify_rel', 12, 37, True), ('query_attr', 8, 24, True), ('choose_rel', 8, 100, False),
+    ('and', 10, 48, True), ('two_same', 6, 31, True), ('compare', 6, 20, True), ('all_same', 6, 17, True)])
+def test_cuda_matches_oracle_at_reference_dims(terminal, batch, n_max, ragged):
+    """Full-size oracle dims (2048 -> 512 -> 256 -> 300 -> C) on a 400-concept synthetic vocabulary, up to N = 100:
+    fp32 CUDA path vs the CPU oracle run in fp32 and fp64 on the same seeded inputs (forward + all gradients)."""
+    from dfol_vqa_b200 import synth
+    from dfol_vqa_b200.ontology import synthetic_ontology
+    from dfol_vqa_b200.programs import ProgramCollater
+    from dfol_vqa_b200.interpreter import FusedTrainStep
+    dims = dict(box=2048, feat=512, hidden=256, emb=300)
+    ont = synthetic_ontology(400, 60, 6, 5, seed=3, embedding_dim=300)
+    interp = helpers.build_interpreter(ont, dims, seed=5)
+    questions = synth.make_questions(ont, batch, terminal, 1, 5, seed=7)
+    counts = synth.object_counts(batch, n_max, ragged, seed=9)
+    feats, bidx = synth.make_object_features(counts, 2048, seed=11)
+    pbs = ProgramCollater(1, lambda qs: (feats, bidx)).collate(questions)
+
+    outs = {}
+    for dtype in (torch.float32, torch.float64):
+        params = helpers.oracle_params(interp, dtype, requires_grad=True)
+        pb_cpu = ProgramCollater(1, lambda qs: (feats.to(dtype), bidx)).collate(json.loads(json.dumps(questions)))
+        results, loss = orc.run_step(ont, params, pb_cpu, is_training=True)
+        loss.backward()
+        outs[dtype] = (results[0]['log_probability'].detach(), loss.detach(), {k: v.grad for k, v in params.items()})
+
+    step = FusedTrainStep(interp)
+    loss = step.forward_backward(helpers.to_cuda(pbs))
+    interp.eval()
+    result = interp(helpers.to_cuda(pbs), True)
+    lp32, l32, g32 = outs[torch.float32]
+    lp64, l64, g64 = outs[torch.float64]
+    ok, worst = helpers.close_to_reference(result['log_probability'].detach().cpu(), lp32, lp64)
+    assert ok, worst
+    assert abs(float(loss) - float(l32)) <= 1e-5 * max(1.0, abs(float(l32))) + 4 * abs(float(l32) - float(l64))
+    keys = {id(p): k for k, p in interp.named_parameters()}
+    for p in interp.oracle_parameters():
+        k = keys[id(p)]
+        scale = g64[k].abs().max().clamp(min=1e-12)
+        err = (step.grads[id(p)].cpu().double() - g32[k].double()).abs().max()
+        noise = (g32[k].double() - g64[k]).abs().max()
+        assert err <= 1e-5 * scale + 4 * noise + 1e-9, (k, float(err), float(scale), float(noise))
