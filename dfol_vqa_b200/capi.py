@@ -43,7 +43,7 @@ _SIGNATURES = {
     'dfol_cast_bf16': (c_int, [P, c_int64, P, c_int64, c_int64, c_int, P]),
     'dfol_box_position': (c_int, [P, c_int64, c_int, P, c_int64, c_int, c_int64, P]),
     'dfol_pair_hidden_fwd': (c_int, [P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int, c_int, c_int, P, P,
-                                     P, P, c_int64, P]),
+                                     P, c_int, c_int, P]),
     'dfol_pair_hidden_bwd': (c_int, [P, c_int64, P, c_int64, P, c_int64, P, c_int64, P, c_int64, P, c_int, c_int,
                                      P, P, P, c_int, P]),
     'dfol_colsum': (c_int, [P, c_int64, c_int64, c_int, P, P]),
@@ -53,6 +53,9 @@ _SIGNATURES = {
     'dfol_loss_fwd_bwd': (c_int, [P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
     'dfol_table_layer_bwd': (c_int, [P, P, P, P, P, c_int, P, P, P, P, P, P, c_int64, P, c_int64, c_int, P,
                                      c_int64, P, P, P]),
+    'dfol_table_layer_bwd_fused': (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, c_int64, P, c_int64, c_int,
+                                           c_int, P, c_int64, P, P, P]),
+    'dfol_table_grad_dense': (c_int, [P, P, P, P, c_int, P, P, P, P, P, P, c_int64, P]),
     'dfol_sumsq': (c_int, [P, c_int64, P, P]),
     'dfol_adam_step': (c_int, [P, P, P, P, c_int64, P, c_float, c_float, c_float, c_float, c_float, c_float, c_int,
                                P]),

@@ -92,15 +92,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
       : "r"(taddr));
 }
 
-__device__ __forceinline__ float act_fast(float x, int act) {
-  switch (act) {
-    case DFOL_ACT_ELU: return x > 0.0f ? x : __expf(x) - 1.0f;
-    case DFOL_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-x));
-    case DFOL_ACT_LOGSIGMOID: return fminf(x, 0.0f) - __logf(1.0f + __expf(-fabsf(x)));
-    default: return x;
-  }
+template <int ACT>
+__device__ __forceinline__ float act_fast(float x) {
+  if (ACT == DFOL_ACT_ELU) return x > 0.0f ? x : __expf(x) - 1.0f;
+  if (ACT == DFOL_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-x));
+  if (ACT == DFOL_ACT_LOGSIGMOID) return fminf(x, 0.0f) - __logf(1.0f + __expf(-fabsf(x)));
+  return x;
 }
 
+constexpr int ST_F32 = 0, ST_BF16 = 1, ST_TABLE = 2;
+
+// Tiles are enumerated N-fastest (blockIdx.x = N tile) so that the N tiles sharing one 128-row A tile run
+// back-to-back and A is read from HBM once.
+template <int ACT, int STORE>
 __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                   const __grid_constant__ CUtensorMap tmap_b,
                                                                   TcParams p) {
@@ -109,9 +113,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc_kernel(const __grid_c
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float bias_s[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * p.BN;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * p.BN;
   const int num_kb = p.K / TC_BK;
   const uint32_t a_bytes = TC_BM * TC_BK * 2, b_bytes = (uint32_t)p.BN * TC_BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -129,6 +134,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc_kernel(const __grid_c
                  "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  if (warp >= 2) {  // stage the bias of this N tile (zero beyond N) while the pipeline fills
+    for (int i = threadIdx.x - 64; i < p.BN; i += TC_THREADS - 64)
+      bias_s[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -136,6 +145,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc_kernel(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % p.stages;
         const uint32_t phase = (kb / p.stages) & 1;
@@ -169,71 +180,80 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc_kernel(const __grid_c
     }
   } else {
     // ---------------- epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) ----------------
-    mbar_wait(&tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quad = warp & 3;
     const int m = m0 + quad * 32 + lane;
     const bool row_ok = m < p.M;
-    long long tbase = 0;
-    int tstride = 0;
+    float* tdst = nullptr;
+    long long tstride = 0;
     bool is_diag = false;
-    if (p.store == 1 && row_ok) {
+    if (STORE == ST_TABLE && row_ok) {
       const int b = p.row_img[m];
       const int l = m - p.img_row[b];
-      tbase = p.img_blk[b] + l;
       tstride = p.img_stride[b];
+      tdst = reinterpret_cast<float*>(p.C) + p.img_blk[b] + l + (long long)n0 * tstride;
       if (p.img_n != nullptr) {
         const int n_obj = p.img_n[b];
         is_diag = (l / n_obj) == (l % n_obj);
       }
     }
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+    const float diag = p.diag_value;
+    const int n_valid = p.N - n0;        // columns of this tile that carry data
+    const int n_cover = p.n_store - n0;  // columns of this tile that are stored (zero beyond n_valid)
+    mbar_wait(&tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    for (int c0 = 0; c0 < p.BN && c0 < n_cover; c0 += 16) {
       uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld16(trow + (uint32_t)c0, r);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int nb = n0 + c0;
-      if (!row_ok || nb >= p.n_store) continue;
+      if (!row_ok) continue;
       float v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = nb + j;
-        float x = __uint_as_float(r[j]);
-        if (n < p.N) {
-          if (p.bias != nullptr) x += __ldg(p.bias + n);
-          x = act_fast(x, p.act);
-        } else {
-          x = 0.0f;
-        }
-        v[j] = x;
-      }
-      if (p.store == 1) {
-        float* C = reinterpret_cast<float*>(p.C);
+      for (int j = 0; j < 16; ++j) v[j] = act_fast<ACT>(__uint_as_float(r[j]) + bias_s[c0 + j]);
+      if (STORE == ST_TABLE) {
+        float* d = tdst + (long long)c0 * tstride;
+        if (c0 + 16 <= n_valid) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (nb + j < p.N) C[tbase + (long long)(nb + j) * tstride] = is_diag ? p.diag_value : v[j];
-      } else if (p.out_bf16) {
-        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)m * p.ldc + nb;
-        if (nb + 16 <= p.n_store) {
-          uint32_t packed[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            packed[j] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(crow);
-          dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-          dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+          for (int j = 0; j < 16; ++j) d[j * tstride] = is_diag ? diag : v[j];
         } else {
-          for (int j = 0; j < 16 && nb + j < p.n_store; ++j) crow[j] = __float2bfloat16(v[j]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < n_valid) d[j * tstride] = is_diag ? diag : v[j];
         }
       } else {
-        float* crow = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
-        if (nb + 16 <= p.n_store && (p.ldc & 3) == 0) {
-          float4* dst = reinterpret_cast<float4*>(crow);
+        if (c0 + 16 > n_valid) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j >= n_valid) v[j] = 0.0f;  // K padding of the next layer
+        }
+        if (STORE == ST_BF16) {
+          __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)m * p.ldc + n0 + c0;
+          if (c0 + 16 <= n_cover) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(crow);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < n_cover) crow[j] = __float2bfloat16(v[j]);
+          }
         } else {
-          for (int j = 0; j < 16 && nb + j < p.n_store; ++j) crow[j] = v[j];
+          float* crow = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + n0 + c0;
+          if (c0 + 16 <= n_cover && (p.ldc & 3) == 0) {
+            float4* dst = reinterpret_cast<float4*>(crow);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < n_cover) crow[j] = v[j];
+          }
         }
       }
     }
@@ -244,6 +264,23 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc_kernel(const __grid_c
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
   }
+}
+
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, TcParams);
+
+template <int STORE>
+static TcKernel pick_act(int act) {
+  switch (act) {
+    case DFOL_ACT_ELU: return gemm_bf16_tc_kernel<DFOL_ACT_ELU, STORE>;
+    case DFOL_ACT_SIGMOID: return gemm_bf16_tc_kernel<DFOL_ACT_SIGMOID, STORE>;
+    case DFOL_ACT_LOGSIGMOID: return gemm_bf16_tc_kernel<DFOL_ACT_LOGSIGMOID, STORE>;
+    default: return gemm_bf16_tc_kernel<DFOL_ACT_NONE, STORE>;
+  }
+}
+static TcKernel pick_kernel(int act, int store_kind) {
+  if (store_kind == ST_TABLE) return pick_act<ST_TABLE>(act);
+  if (store_kind == ST_BF16) return pick_act<ST_BF16>(act);
+  return pick_act<ST_F32>(act);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -318,18 +355,18 @@ extern "C" int dfol_gemm_bf16_tc(const void* A, int64_t lda, const void* B, int6
   if (stages > K / TC_BK) stages = K / TC_BK;
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  TcKernel kernel = pick_kernel(act, store == 1 ? ST_TABLE : (out_bf16 ? ST_BF16 : ST_F32));
+  {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { set_error("dfol_gemm_bf16_tc: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_set = true;
   }
   alignas(64) CUtensorMap ma, mb;
   int rc = encode_map(&ma, A, M, K, lda, TC_BM);
   if (rc != 0) return rc;
   rc = encode_map(&mb, B, N, K, ldb, BN);
   if (rc != 0) return rc;
-  dim3 grid((M + TC_BM - 1) / TC_BM, n_tiles);
-  gemm_bf16_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, p);
+  dim3 grid(n_tiles, (M + TC_BM - 1) / TC_BM);
+  DFOL_REQUIRE(grid.y <= 65535, "dfol_gemm_bf16_tc: M too large for one launch (%d row tiles)", (int)grid.y);
+  kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, p);
   return finish_launch("dfol_gemm_bf16_tc");
 }

@@ -33,40 +33,92 @@ __device__ __forceinline__ void pair_geometry(const float* ps, const float* po, 
   g[3] = (sy > 0.0f) ? 1.0f : (sy < 0.0f ? -1.0f : 0.0f);
 }
 
-// One warp per pair row, lanes over hidden units: h = act(U[s] + V[o] + Wg.geo + b).
+// Pair hidden layer h[(s,o), :] = act(U[s] + V[o] + Wg.geo(s,o) + b), tiled so that every U/V row is fetched from
+// L2 once per 8x32 pair tile instead of once per pair: one block per (image, 8 subjects, 32 objects); warp w owns
+// subject s0+w and keeps its U row slice, the geometry weights and the bias of its hidden units in registers; the
+// 32 V rows and the tile's pair geometry sit in shared memory. Lanes own hidden units 4*lane + 128*i (H <= 512).
+// FAST selects the approximate intrinsics of the bf16 tensor-core mode; fp32 parity mode uses accurate functions.
+constexpr int PH_TS = 8, PH_TO = 32, PH_MAXG = 4;  // H <= 128 * PH_MAXG
+
+template <bool FAST, bool BF16OUT>
 __global__ void __launch_bounds__(256) pair_hidden_fwd_kernel(
     const float* __restrict__ uv, long long lduv, const float* __restrict__ pos, long long ldpos,
     const float* __restrict__ wg, long long ldw, const float* __restrict__ bias, void* __restrict__ hout,
-    long long ldh, int H, int act, int out_bf16, const int32_t* __restrict__ pair_img, const int32_t* __restrict__ pair_row,
-    const int32_t* __restrict__ obj_row, const int32_t* __restrict__ img_n, long long pair_rows) {
-  const int lane = threadIdx.x & 31;
-  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= pair_rows) return;
-  const int b = pair_img[row];
+    long long ldh, int H, int act, const int32_t* __restrict__ pair_row, const int32_t* __restrict__ obj_row,
+    const int32_t* __restrict__ img_n, int tiles_o) {
+  extern __shared__ float4 vsm[];                       // [PH_TO][H/4] V rows
+  float4* geo = vsm + PH_TO * (H / 4);                  // [PH_TS][PH_TO] pair geometry
+  const int b = blockIdx.y;
   const int n = img_n[b];
-  const int l = (int)(row - pair_row[b]);
-  const int s = l / n, o = l - s * n;
-  const long long ts = obj_row[b] + s, to = obj_row[b] + o;
-  float g[4];
-  pair_geometry(pos + ts * ldpos, pos + to * ldpos, g);
-  if (s == o) { g[0] = 0.f; g[1] = 0.f; g[2] = 0.f; g[3] = 0.f; }  // self pairs are not part of the path
-  const float* u = uv + ts * lduv;
-  const float* v = uv + to * lduv + H;
-  float* out = reinterpret_cast<float*>(hout) + row * ldh;
-  __nv_bfloat16* out16 = reinterpret_cast<__nv_bfloat16*>(hout) + row * ldh;
-  if (out_bf16)
-    for (int h = H + lane; h < ldh; h += 32) out16[h] = __float2bfloat16(0.0f);  // K padding of the next GEMM
-  for (int h = lane; h < H; h += 32) {
-    const float* w = wg + h * ldw;
-    float z = u[h] + v[h];
-    z += w[0] * g[0];
-    z += w[1] * g[1];
-    z += w[2] * g[2];
-    z += w[3] * g[3];
-    z += bias[h];
-    const float a = act_apply(z, act);
-    if (out_bf16) out16[h] = __float2bfloat16(a);
-    else out[h] = a;
+  const int s0 = (blockIdx.x / tiles_o) * PH_TS, o0 = (blockIdx.x % tiles_o) * PH_TO;
+  if (s0 >= n || o0 >= n) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long t0 = obj_row[b];
+  const int H4 = H / 4;
+  const int no = min(PH_TO, n - o0);
+  for (int idx = threadIdx.x; idx < no * H4; idx += blockDim.x) {
+    const int o = idx / H4, q = idx - o * H4;
+    vsm[o * H4 + q] = __ldg(reinterpret_cast<const float4*>(uv + (t0 + o0 + o) * lduv + H) + q);
+  }
+  {
+    const int si = threadIdx.x / PH_TO, oi = threadIdx.x % PH_TO;  // 256 threads = 8 x 32 pairs
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (s0 + si < n && oi < no && s0 + si != o0 + oi)
+      pair_geometry(pos + (t0 + s0 + si) * ldpos, pos + (t0 + o0 + oi) * ldpos, g);
+    geo[si * PH_TO + oi] = make_float4(g[0], g[1], g[2], g[3]);
+  }
+  __syncthreads();
+  const int s = s0 + warp;
+  if (s >= n) return;
+  // per-lane constants: U[s], geometry weights and bias of hidden units 4*(lane + 32 i) .. +3
+  float4 u[PH_MAXG], bz[PH_MAXG], w0[PH_MAXG], w1[PH_MAXG], w2[PH_MAXG], w3[PH_MAXG];
+#pragma unroll
+  for (int i = 0; i < PH_MAXG; ++i) {
+    const int q = lane + 32 * i;
+    if (q < H4) {
+      u[i] = __ldg(reinterpret_cast<const float4*>(uv + (t0 + s) * lduv) + q);
+      bz[i] = make_float4(bias[4 * q], bias[4 * q + 1], bias[4 * q + 2], bias[4 * q + 3]);
+      const float* w = wg + (long long)(4 * q) * ldw;
+      w0[i] = make_float4(w[0], w[1], w[2], w[3]);
+      w1[i] = make_float4(w[ldw], w[ldw + 1], w[ldw + 2], w[ldw + 3]);
+      w2[i] = make_float4(w[2 * ldw], w[2 * ldw + 1], w[2 * ldw + 2], w[2 * ldw + 3]);
+      w3[i] = make_float4(w[3 * ldw], w[3 * ldw + 1], w[3 * ldw + 2], w[3 * ldw + 3]);
+    }
+  }
+  auto activate = [&](float t) -> float {
+    if (FAST) {
+      return (act == DFOL_ACT_ELU) ? (t > 0.0f ? t : __expf(t) - 1.0f)
+                                   : (act == DFOL_ACT_SIGMOID ? __fdividef(1.0f, 1.0f + __expf(-t)) : t);
+    }
+    return act_apply(t, act);
+  };
+  for (int oi = 0; oi < no; ++oi) {
+    const float4 g = geo[warp * PH_TO + oi];
+    const long long row = (long long)pair_row[b] + (long long)s * n + o0 + oi;
+#pragma unroll
+    for (int i = 0; i < PH_MAXG; ++i) {
+      const int q = lane + 32 * i;
+      if (q < H4) {
+        const float4 v = vsm[oi * H4 + q];
+        // same association as the unfused sum: ((((u + v) + w0 g0) + w1 g1) + w2 g2) + w3 g3) + b
+        float a0 = u[i].x + v.x, a1 = u[i].y + v.y, a2 = u[i].z + v.z, a3 = u[i].w + v.w;
+        a0 += w0[i].x * g.x; a0 += w0[i].y * g.y; a0 += w0[i].z * g.z; a0 += w0[i].w * g.w; a0 += bz[i].x;
+        a1 += w1[i].x * g.x; a1 += w1[i].y * g.y; a1 += w1[i].z * g.z; a1 += w1[i].w * g.w; a1 += bz[i].y;
+        a2 += w2[i].x * g.x; a2 += w2[i].y * g.y; a2 += w2[i].z * g.z; a2 += w2[i].w * g.w; a2 += bz[i].z;
+        a3 += w3[i].x * g.x; a3 += w3[i].y * g.y; a3 += w3[i].z * g.z; a3 += w3[i].w * g.w; a3 += bz[i].w;
+        a0 = activate(a0); a1 = activate(a1); a2 = activate(a2); a3 = activate(a3);
+        if (BF16OUT) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(hout) + row * ldh + 4 * q) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        } else {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(hout) + row * ldh + 4 * q) = make_float4(a0, a1, a2, a3);
+        }
+      }
+    }
+    if (BF16OUT)  // K padding of the next tensor-core GEMM
+      for (int h = H + lane; h < ldh; h += 32)
+        reinterpret_cast<__nv_bfloat16*>(hout)[row * ldh + h] = __float2bfloat16(0.0f);
   }
 }
 
@@ -199,6 +251,100 @@ __global__ void __launch_bounds__(256) table_layer_bwd_kernel(
   }
 }
 
+
+// Fused backward of the table layer for images with at most SMAX touched table columns (the relation table:
+// a program touches a handful of relations). One block per (64-row chunk, image):
+//   dz_j[l] = g_j[l] * (1 - exp(LL_j[l]))                                   (logsigmoid')
+//   dZ[row, e] = (sum_j dz_j[l] W[wrow_j, e]) * act'(H[row, e])             written once, no read-modify-write
+//   dW[wrow_j, e] += sum_l dz_j[l] H[row, e];  db[wrow_j] += sum_l dz_j[l]  (atomics, one per block and e)
+// Rows of images without slices are written as zero, so dZ needs no memset.
+template <int SMAX>
+__global__ void __launch_bounds__(256) table_layer_bwd_fused_kernel(
+    const float* __restrict__ g, const int32_t* __restrict__ slice_goff, const int32_t* __restrict__ slice_col,
+    const int32_t* __restrict__ slice_wrow, const int32_t* __restrict__ img_slice, const float* __restrict__ ll,
+    const int64_t* __restrict__ blk, const int32_t* __restrict__ stride, const int32_t* __restrict__ row0,
+    const int32_t* __restrict__ img_rows, const float* __restrict__ W, long long ldw,
+    const float* __restrict__ hs, long long ldh, int E, int act, float* __restrict__ dZ, long long lddz,
+    float* __restrict__ dW, float* __restrict__ db) {
+  constexpr int R = 64;
+  __shared__ float dz_s[SMAX][R];
+  __shared__ int wrow_s[SMAX];
+  const int b = blockIdx.y;
+  const int rows = img_rows[b];
+  const int c = blockIdx.x * R;
+  if (c >= rows) return;
+  const int cn = min(R, rows - c);
+  const long long r0 = (long long)row0[b] + c;
+  const int j0 = img_slice[b];
+  const int S = min(img_slice[b + 1] - j0, SMAX);
+  if (S == 0) {
+    for (int idx = threadIdx.x; idx < cn * E; idx += blockDim.x) {
+      const int l = idx / E, e = idx - l * E;
+      dZ[(r0 + l) * lddz + e] = 0.0f;
+    }
+    return;
+  }
+  const int st = stride[b];
+  for (int idx = threadIdx.x; idx < S * R; idx += blockDim.x) {
+    const int j = idx / R, l = idx - j * R;
+    float v = 0.0f;
+    if (l < cn) {
+      const float gv = g[slice_goff[j0 + j] + c + l];
+      if (gv != 0.0f) v = gv * (1.0f - expf(ll[blk[b] + (long long)slice_col[j0 + j] * st + c + l]));
+    }
+    dz_s[j][l] = v;
+  }
+  if (threadIdx.x < S) wrow_s[threadIdx.x] = slice_wrow[j0 + threadIdx.x];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < S) {
+    float t = dz_s[warp][lane] + dz_s[warp][lane + 32];
+    t = warp_sum(t);
+    if (lane == 0 && t != 0.0f) atomicAdd(db + wrow_s[warp], t);
+  }
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float wj[SMAX], dwj[SMAX];
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+      wj[j] = (j < S) ? W[(long long)wrow_s[j] * ldw + e] : 0.0f;
+      dwj[j] = 0.0f;
+    }
+    for (int l = 0; l < cn; ++l) {
+      const float h = hs[(r0 + l) * ldh + e];
+      float out = 0.0f;
+#pragma unroll
+      for (int j = 0; j < SMAX; ++j) {
+        const float dz = dz_s[j][l];
+        out += dz * wj[j];
+        dwj[j] += dz * h;
+      }
+      dZ[(r0 + l) * lddz + e] = out * act_grad_from_output(h, act);
+    }
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j)
+      if (j < S && dwj[j] != 0.0f) atomicAdd(dW + (long long)wrow_s[j] * ldw + e, dwj[j]);
+  }
+}
+
+// Scatter the compact gradient slices into a dense (rows x columns) matrix with logsigmoid' applied:
+// dZ[row0[b] + l, col] += g[l] * (1 - exp(LL[b][col][l])). One warp per slice.
+__global__ void __launch_bounds__(256) table_grad_dense_kernel(
+    const float* __restrict__ g, const int32_t* __restrict__ slice_goff, const int32_t* __restrict__ slice_col,
+    const int32_t* __restrict__ slice_img, int slice_num, const float* __restrict__ ll,
+    const int64_t* __restrict__ blk, const int32_t* __restrict__ stride, const int32_t* __restrict__ row0,
+    const int32_t* __restrict__ img_rows, float* __restrict__ dZ, long long lddz) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= slice_num) return;
+  const int b = slice_img[j], col = slice_col[j];
+  const int rows = img_rows[b];
+  const float* gj = g + slice_goff[j];
+  const float* lj = ll + blk[b] + (long long)col * stride[b];
+  for (int l = threadIdx.x & 31; l < rows; l += 32) {
+    const float gv = gj[l];
+    if (gv != 0.0f) atomicAdd(dZ + ((long long)row0[b] + l) * lddz + col, gv * (1.0f - expf(lj[l])));
+  }
+}
+
 }  // namespace dfol
 
 using namespace dfol;
@@ -215,15 +361,31 @@ extern "C" int dfol_box_position(const float* features, int64_t ldf, int feature
 
 extern "C" int dfol_pair_hidden_fwd(const float* uv, int64_t lduv, const float* obj_pos, int64_t ldpos,
                                     const float* wg, int64_t ldw, const float* bias, void* h_out, int64_t ldh, int H,
-                                    int act, int out_bf16, const int32_t* pair_img, const int32_t* pair_row,
-                                    const int32_t* obj_row, const int32_t* img_n, int64_t pair_rows, void* stream) {
-  DFOL_REQUIRE(uv && obj_pos && wg && bias && h_out && pair_img && pair_row && obj_row && img_n,
+                                    int act, int out_bf16, const int32_t* pair_row, const int32_t* obj_row,
+                                    const int32_t* img_n, int image_num, int max_n, void* stream) {
+  DFOL_REQUIRE(uv && obj_pos && wg && bias && h_out && pair_row && obj_row && img_n,
                "dfol_pair_hidden_fwd: null pointer");
-  if (pair_rows == 0) return 0;
-  const int warps = 8;
-  pair_hidden_fwd_kernel<<<(unsigned)((pair_rows + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
-      uv, lduv, obj_pos, ldpos, wg, ldw, bias, h_out, ldh, H, act, out_bf16, pair_img, pair_row, obj_row, img_n,
-      pair_rows);
+  if (image_num == 0) return 0;
+  DFOL_REQUIRE((H % 4) == 0 && (lduv % 4) == 0 && (ldh % 4) == 0 && (reinterpret_cast<uintptr_t>(uv) % 16) == 0 &&
+                   (reinterpret_cast<uintptr_t>(h_out) % 16) == 0,
+               "dfol_pair_hidden_fwd: H, lduv, ldh must be multiples of 4 and buffers 16-byte aligned");
+  DFOL_REQUIRE(H <= 128 * PH_MAXG, "dfol_pair_hidden_fwd: hidden width above %d is not supported", 128 * PH_MAXG);
+  DFOL_REQUIRE(max_n >= 1 && image_num >= 1, "dfol_pair_hidden_fwd: empty batch");
+  const int tiles_s = (max_n + PH_TS - 1) / PH_TS, tiles_o = (max_n + PH_TO - 1) / PH_TO;
+  dim3 grid(tiles_s * tiles_o, image_num);
+  const size_t smem = (size_t)(PH_TO * (H / 4) + PH_TS * PH_TO) * sizeof(float4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_bf16) {
+    auto kern = pair_hidden_fwd_kernel<true, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, 256, smem, st>>>(uv, lduv, obj_pos, ldpos, wg, ldw, bias, h_out, ldh, H, act, pair_row, obj_row,
+                                  img_n, tiles_o);
+  } else {
+    auto kern = pair_hidden_fwd_kernel<false, false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, 256, smem, st>>>(uv, lduv, obj_pos, ldpos, wg, ldw, bias, h_out, ldh, H, act, pair_row, obj_row,
+                                  img_n, tiles_o);
+  }
   return finish_launch("dfol_pair_hidden_fwd");
 }
 
@@ -285,4 +447,34 @@ extern "C" int dfol_table_layer_bwd(const float* g, const int32_t* slice_goff, c
       g, slice_goff, slice_col, slice_wrow, img_slice, ll, blk, stride, row0, img_rows, W, ldw, h_saved, ldh, E, dH,
       lddh, dW, db);
   return finish_launch("dfol_table_layer_bwd");
+}
+
+extern "C" int dfol_table_layer_bwd_fused(const float* g, const int32_t* slice_goff, const int32_t* slice_col,
+                                          const int32_t* slice_wrow, const int32_t* img_slice, int image_num,
+                                          int max_rows, const float* ll, const int64_t* blk, const int32_t* stride,
+                                          const int32_t* row0, const int32_t* img_rows, const float* W, int64_t ldw,
+                                          const float* h_saved, int64_t ldh, int E, int act, float* dZ, int64_t lddz,
+                                          float* dW, float* db, void* stream) {
+  DFOL_REQUIRE(g && slice_goff && slice_col && slice_wrow && img_slice && ll && blk && stride && row0 && img_rows &&
+                   W && h_saved && dZ && dW && db,
+               "dfol_table_layer_bwd_fused: null pointer");
+  if (image_num == 0 || max_rows == 0) return 0;
+  dim3 grid((max_rows + 63) / 64, image_num);
+  DFOL_REQUIRE(grid.y <= 65535, "dfol_table_layer_bwd_fused: too many images");
+  table_layer_bwd_fused_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      g, slice_goff, slice_col, slice_wrow, img_slice, ll, blk, stride, row0, img_rows, W, ldw, h_saved, ldh, E, act,
+      dZ, lddz, dW, db);
+  return finish_launch("dfol_table_layer_bwd_fused");
+}
+
+extern "C" int dfol_table_grad_dense(const float* g, const int32_t* slice_goff, const int32_t* slice_col,
+                                     const int32_t* slice_img, int slice_num, const float* ll, const int64_t* blk,
+                                     const int32_t* stride, const int32_t* row0, const int32_t* img_rows, float* dZ,
+                                     int64_t lddz, void* stream) {
+  DFOL_REQUIRE(g && slice_goff && slice_col && slice_img && ll && blk && stride && row0 && img_rows && dZ,
+               "dfol_table_grad_dense: null pointer");
+  if (slice_num == 0) return 0;
+  table_grad_dense_kernel<<<(slice_num + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+      g, slice_goff, slice_col, slice_img, slice_num, ll, blk, stride, row0, img_rows, dZ, lddz);
+  return finish_launch("dfol_table_grad_dense");
 }

@@ -220,8 +220,8 @@ class ReasoningEngine(object):
         wg = first.weight[:, 2 * ldo:]
         h1r = torch.empty(layout.P, Hp, device=dev, dtype=torch.bfloat16)
         call('dfol_pair_hidden_fwd', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo, ptr(wg), first.weight.stride(0),
-             ptr(first.bias), ptr(h1r), Hp, H, K.ACT_ELU, 1, ptr(layout.pair_img), ptr(layout.pair_row),
-             ptr(layout.obj_row), ptr(layout.img_n), layout.P, st)
+             ptr(first.bias), ptr(h1r), Hp, H, K.ACT_ELU, 1, ptr(layout.pair_row), ptr(layout.obj_row),
+             ptr(layout.img_n), layout.B, layout.max_n, st)
         wr2 = self._cast16(w.rel[1].weight, Hp, st)
         h2r = torch.empty(layout.P, Ep, device=dev, dtype=torch.bfloat16)
         self._tc(h1r, wr2, h2r, E, Hp, w.rel[1].bias, K.ACT_SIGMOID, st)
@@ -289,8 +289,8 @@ class ReasoningEngine(object):
         h1 = torch.empty(layout.P, H, device=dev, dtype=torch.float32)
         act1 = K.ACT_ELU if len(w.rel) > 1 else K.ACT_SIGMOID
         call('dfol_pair_hidden_fwd', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo, ptr(wg), first.weight.stride(0),
-             ptr(first.bias), ptr(h1), H, H, act1, 0, ptr(layout.pair_img), ptr(layout.pair_row),
-             ptr(layout.obj_row), ptr(layout.img_n), layout.P, st)
+             ptr(first.bias), ptr(h1), H, H, act1, 0, ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_n),
+             layout.B, layout.max_n, st)
         sc.rel_h = [h1]
         h = h1
         for i, layer in enumerate(w.rel[1:], start=1):
@@ -359,7 +359,8 @@ class ReasoningEngine(object):
             return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
         pad = arr if arr.shape[0] else np.zeros((1, 3), dtype=np.int64)
         out = {'goff': dev(pad[:, 2].astype(np.int32)), 'col': dev(pad[:, 1].astype(np.int32)),
-               'img_slice': dev(img_slice), 'count': int(arr.shape[0])}
+               'img': dev(pad[:, 0].astype(np.int32)), 'img_slice': dev(img_slice), 'count': int(arr.shape[0]),
+               'max_per_image': int(counts.max()) if counts.size else 0}
         cache[key] = out
         return out
 
@@ -394,31 +395,29 @@ class ReasoningEngine(object):
         # ---- attribute table layer (sparse slices) -> dense chain backward
         sa = self._slice_tables(cp.attr_slices, lay.B, dev, 'attr_slices', cp)
         h_last = scene.attr_h[-1]
-        d_h = torch.zeros(T, E, device=dev, dtype=torch.float32)
-        if sa['count']:
-            call('dfol_table_layer_bwd', ptr(g_attr), ptr(sa['goff']), ptr(sa['col']), ptr(sa['col']),
-                 ptr(sa['img_slice']), lay.B, ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride),
-                 ptr(lay.obj_row), ptr(lay.img_n), ptr(w.emb.weight), w.emb.weight.stride(0), ptr(h_last),
-                 h_last.stride(0), E, ptr(d_h), d_h.stride(0), ptr(G(w.emb.weight)), ptr(G(w.emb.bias)), st)
-        self._mlp_backward(w.attr, [obj] + scene.attr_h, d_h, d_obj, grads, st, first_layer_input_grad=True)
+        d_h, is_dz = self._table_backward(
+            g_attr, sa, scene.attr_ll, lay.attr_blk, lay.attr_stride, lay.obj_row, lay.img_n, lay.max_n, T,
+            w.emb.weight, G(w.emb.weight), G(w.emb.bias), h_last, K.ACT_SIGMOID, st)
+        self._mlp_backward(w.attr, [obj] + scene.attr_h, d_h, d_obj, grads, st, first_layer_input_grad=True,
+                           d_out_is_dz=is_dz)
 
         # ---- relation table layer -> dense layers -> pair hidden layer
         sr = self._slice_tables(cp.rel_slices, lay.B, dev, 'rel_slices', cp)
         if sr['count']:
             nR = scene.w_rel.shape[0]
             h_last = scene.rel_h[-1]
-            d_h = torch.zeros(P, E, device=dev, dtype=torch.float32)
             dw_rel = torch.zeros(nR, E, device=dev, dtype=torch.float32)
             db_rel = torch.zeros(nR, device=dev, dtype=torch.float32)
-            call('dfol_table_layer_bwd', ptr(g_rel), ptr(sr['goff']), ptr(sr['col']), ptr(sr['col']),
-                 ptr(sr['img_slice']), lay.B, ptr(scene.rel_ll), ptr(lay.rel_blk), ptr(lay.rel_stride),
-                 ptr(lay.pair_row), ptr(lay.img_nn), ptr(scene.w_rel), E, ptr(h_last), h_last.stride(0), E,
-                 ptr(d_h), d_h.stride(0), ptr(dw_rel), ptr(db_rel), st)
+            fuse = K.ACT_SIGMOID if len(w.rel) > 1 else K.ACT_NONE
+            d_h, is_dz = self._table_backward(
+                g_rel, sr, scene.rel_ll, lay.rel_blk, lay.rel_stride, lay.pair_row, lay.img_nn, lay.max_n ** 2, P,
+                scene.w_rel, dw_rel, db_rel, h_last, fuse, st)
             ridx = self.rel_index(dev)
             G(w.emb.weight).index_add_(0, ridx, dw_rel)
             G(w.emb.bias).index_add_(0, ridx, db_rel)
             # dense layers above the pair hidden layer
-            d_h1 = self._mlp_backward(w.rel[1:], scene.rel_h, d_h, None, grads, st, first_layer_input_grad=False)
+            d_h1 = self._mlp_backward(w.rel[1:], scene.rel_h, d_h, None, grads, st, first_layer_input_grad=False,
+                                      d_out_is_dz=is_dz and len(w.rel) > 1)
             first = w.rel[0]
             H = first.weight.shape[0]
             duv = torch.zeros(T, 2 * H, device=dev, dtype=torch.float32)
@@ -440,7 +439,36 @@ class ReasoningEngine(object):
         sk = _split_for(T)
         gemm_f32(d_obj[:, :F].t(), scene.features[:, :D], G(w.feat.weight), accumulate=(sk == 1), split_k=sk, stream=st)
 
-    def _mlp_backward(self, layers, acts, d_out, d_in_accum, grads, st, first_layer_input_grad):
+    def _table_backward(self, g, tabs, ll, blk, stride, row0, img_rows, max_rows, rows_total, W, dW, db, h_last,
+                        fuse_act, st):
+        """Backward of a table layer LL = logsigmoid(h_last W^T + b) from the compact program gradient slices.
+
+        Returns (d, is_dz): d = d loss / d h_last, already multiplied by ``fuse_act``'(h_last) when is_dz is true.
+        Few slices per image (relations, binary programs): one fused pass.  Many (attribute option lists): scatter to
+        a dense d logits matrix and use GEMMs."""
+        dev = ll.device
+        E = W.shape[1]
+        if tabs['count'] == 0:
+            return torch.zeros(rows_total, E, device=dev, dtype=torch.float32), False
+        if tabs['max_per_image'] <= 8:
+            d = torch.empty(rows_total, E, device=dev, dtype=torch.float32)
+            call('dfol_table_layer_bwd_fused', ptr(g), ptr(tabs['goff']), ptr(tabs['col']), ptr(tabs['col']),
+                 ptr(tabs['img_slice']), len(tabs['img_slice']) - 1, max_rows, ptr(ll), ptr(blk), ptr(stride),
+                 ptr(row0), ptr(img_rows), ptr(W), W.stride(0), ptr(h_last), h_last.stride(0), E, fuse_act, ptr(d),
+                 d.stride(0), ptr(dW), ptr(db), st)
+            return d, fuse_act != K.ACT_NONE
+        C = W.shape[0]
+        dz = torch.zeros(rows_total, C, device=dev, dtype=torch.float32)
+        call('dfol_table_grad_dense', ptr(g), ptr(tabs['goff']), ptr(tabs['col']), ptr(tabs['img']), tabs['count'],
+             ptr(ll), ptr(blk), ptr(stride), ptr(row0), ptr(img_rows), ptr(dz), C, st)
+        call('dfol_colsum', ptr(dz), C, rows_total, C, ptr(db), st)
+        sk = _split_for(rows_total)
+        gemm_f32(dz.t(), h_last, dW, accumulate=(sk == 1), split_k=sk, stream=st)
+        d = torch.empty(rows_total, E, device=dev, dtype=torch.float32)
+        gemm_f32(dz, W, d, stream=st)
+        return d, False
+
+    def _mlp_backward(self, layers, acts, d_out, d_in_accum, grads, st, first_layer_input_grad, d_out_is_dz=False):
         """Backward through [Linear+act]* given d loss / d (last activation OUTPUT).
 
         ``acts`` = [input, h_1, ..., h_L] (saved outputs), ``layers`` the L Linear modules. Returns d loss / d input
@@ -456,8 +484,9 @@ class ReasoningEngine(object):
             h_out, h_in = acts[i + 1], acts[i]
             rows, width = h_out.shape
             act = K.ACT_SIGMOID if i == L - 1 else K.ACT_ELU
-            # dZ = dH * act'(h) in place
-            call('dfol_act_grad_mul', ptr(d_h), d_h.stride(0), ptr(h_out), h_out.stride(0), rows, width, act, st)
+            # dZ = dH * act'(h) in place (already applied by the fused table-layer kernel for the last layer)
+            if not (d_out_is_dz and i == L - 1):
+                call('dfol_act_grad_mul', ptr(d_h), d_h.stride(0), ptr(h_out), h_out.stride(0), rows, width, act, st)
             call('dfol_colsum', ptr(d_h), d_h.stride(0), rows, width, ptr(grads[id(layer.bias)]), st)
             sk = _split_for(rows)
             gemm_f32(d_h.t(), h_in, grads[id(layer.weight)], accumulate=(sk == 1), split_k=sk, stream=st)

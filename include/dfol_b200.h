@@ -98,8 +98,8 @@ int dfol_box_position(const float* features, int64_t ldf, int feature_dim, float
                       int64_t rows, void* stream);
 int dfol_pair_hidden_fwd(const float* uv, int64_t lduv, const float* obj_pos, int64_t ldpos, const float* wg,
                          int64_t ldw, const float* bias, void* h_out, int64_t ldh, int H, int act, int out_bf16,
-                         const int32_t* pair_img, const int32_t* pair_row, const int32_t* obj_row,
-                         const int32_t* img_n, int64_t pair_rows, void* stream);
+                         const int32_t* pair_row, const int32_t* obj_row, const int32_t* img_n, int image_num,
+                         int max_n, void* stream);
 int dfol_pair_hidden_bwd(const float* dh, int64_t lddh, const float* h_saved, int64_t ldh, const float* obj_pos,
                          int64_t ldpos, float* duv, int64_t lduv, float* dwg, int64_t ldw, float* dbias, int H,
                          int act, const int32_t* pair_row, const int32_t* obj_row, const int32_t* img_n,
@@ -191,6 +191,25 @@ int dfol_table_layer_bwd(const float* g, const int32_t* slice_goff, const int32_
                          const int64_t* blk, const int32_t* stride, const int32_t* row0, const int32_t* img_rows,
                          const float* W, int64_t ldw, const float* h_saved, int64_t ldh, int E, float* dH,
                          int64_t lddh, float* dW, float* db, void* stream);
+
+/* Fused variant for tables where an image touches at most 8 columns (the relation table): one pass over the rows
+ * of every image, writes dZ = (sum_j dz_j W[wrow_j]) * act'(Hsaved) for ALL rows (zero where an image has no
+ * slice: dZ needs no memset), accumulates dW / db with atomics.  max_rows = largest img_rows[b].
+ * The caller guarantees img_slice[b+1] - img_slice[b] <= 8 for every image (otherwise use the general kernels). */
+int dfol_table_layer_bwd_fused(const float* g, const int32_t* slice_goff, const int32_t* slice_col,
+                               const int32_t* slice_wrow, const int32_t* img_slice, int image_num, int max_rows,
+                               const float* ll, const int64_t* blk, const int32_t* stride, const int32_t* row0,
+                               const int32_t* img_rows, const float* W, int64_t ldw, const float* h_saved,
+                               int64_t ldh, int E, int act, float* dZ, int64_t lddz, float* dW, float* db,
+                               void* stream);
+
+/* Dense variant for tables where images touch many columns (attribute options): scatters the slices into a zeroed
+ * dense (rows x columns) matrix with logsigmoid' applied, dZ[row0[b] + l, col_j] += g_j[l] * (1 - exp(LL_j[l]));
+ * the layer backward is then two ordinary GEMMs (dH = dZ.W, dW = dZ^T.H) and a column sum. */
+int dfol_table_grad_dense(const float* g, const int32_t* slice_goff, const int32_t* slice_col,
+                          const int32_t* slice_img, int slice_num, const float* ll, const int64_t* blk,
+                          const int32_t* stride, const int32_t* row0, const int32_t* img_rows, float* dZ,
+                          int64_t lddz, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Optimiser step on the flat parameter bucket: clip_grad_norm_ + Adam (trainer.py:438-441,
