@@ -25,6 +25,7 @@ from .capi import K, call, ptr
 from .compiler import BINARY, QUERY, STATEMENT, ProgramCompiler
 from .engine import OracleWeights, ReasoningEngine, SceneLayout
 from .networks import dropout_p, linear_layers
+from .parallel import FlatBucket
 
 YES = ('yes', 'yeah', 'yep', 'yup', 'aye', 'yea')
 
@@ -260,18 +261,10 @@ class FusedTrainStep(object):
         params = interpreter.oracle_parameters()
         self.params = params
         dev = params[0].device
-        sizes = [p.numel() for p in params]
-        self.flat = torch.empty(sum(sizes), device=dev, dtype=torch.float32)
-        self.flat_grad = torch.zeros_like(self.flat)
+        self.bucket = FlatBucket(params)
+        self.flat, self.flat_grad, self.grads = self.bucket.flat, self.bucket.flat_grad, self.bucket.grads
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
-        self.grads = {}
-        off = 0
-        for p, n in zip(params, sizes):
-            self.flat[off:off + n].copy_(p.data.reshape(-1))
-            p.data = self.flat[off:off + n].view_as(p)
-            self.grads[id(p)] = self.flat_grad[off:off + n].view_as(p)
-            off += n
         self.step_count = 0
         self.scalars = torch.zeros(2, device=dev, dtype=torch.float32)  # [loss, grad sumsq]
 
@@ -315,7 +308,7 @@ class FusedTrainStep(object):
         dev = self.flat.device
         st = capi.stream_ptr(dev)
         if self.world > 1:
-            torch.distributed.all_reduce(self.flat_grad, group=self.group)
+            self.bucket.all_reduce(self.group)
         self.step_count += 1
         call('dfol_sumsq', ptr(self.flat_grad), self.flat_grad.numel(), ptr(self.scalars[1:]), st)
         call('dfol_adam_step', ptr(self.flat), ptr(self.flat_grad), ptr(self.m), ptr(self.v), self.flat.numel(),

@@ -1,0 +1,98 @@
+"""World-size-2 gloo test of the data-parallel host logic (question sharding + flat-bucket gradient all-reduce).
+
+Each rank computes, with the CPU oracle, the gradients of (its shard's summed loss) / (GLOBAL question count) --
+exactly what FusedTrainStep does with the CUDA kernels -- re-homes them in a FlatBucket and all-reduces; the result
+must equal the single-process gradients of the whole batch (reference semantics: trainer.py:434-435)."""
+
+import json
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import helpers
+import dfol_oracle as orc
+from dfol_vqa_b200 import synth
+from dfol_vqa_b200.ontology import synthetic_ontology
+from dfol_vqa_b200.parallel import FlatBucket, shard_questions, shard_range
+from dfol_vqa_b200.programs import ProgramCollater
+
+DIMS = dict(box=24, feat=16, hidden=8, emb=12)
+
+
+def _setup():
+    ont = synthetic_ontology(64, 8, 3, 3, seed=2, embedding_dim=DIMS['emb'])
+    questions = synth.make_questions(ont, 7, 'verify_rel', 1, 3, seed=4)
+    counts = synth.object_counts(7, 6, True, seed=5)
+    feats, bidx = synth.make_object_features(counts, DIMS['box'], seed=6)
+    from dfol_vqa_b200.networks import build_networks
+    torch.manual_seed(1)
+    nets = build_networks(helpers.model_config(DIMS), ont)
+    names = {'featurizer_network': '_featurizer._featurizer_network', 'attribute_network': '_oracle._attribute_network',
+             'relation_network': '_oracle._relation_network', 'embedding_network': '_oracle._embedding_network'}
+    params = {}
+    for key, prefix in names.items():
+        for k, v in nets[key].state_dict().items():
+            params[prefix + '.' + k] = v.clone()
+    return ont, questions, counts, feats, bidx, params
+
+
+def _grads(ont, params, questions, counts, feats, bidx, lo, hi, total):
+    starts = [0]
+    for c in counts:
+        starts.append(starts[-1] + c)
+    f = feats[starts[lo]:starts[hi]]
+    b = bidx[starts[lo]:starts[hi]] - lo
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    pbs = ProgramCollater(1, lambda qs: (f, b)).collate(json.loads(json.dumps(questions[lo:hi])))
+    interp = orc.OracleInterpreter(ont, p)
+    results = [interp.run(pb, True) for pb in pbs]
+    loss = orc.compute_loss(results, [pb._answers for pb in pbs]) / total
+    loss.backward()
+    return p, loss.detach()
+
+
+def _worker(rank, world, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    ont, questions, counts, feats, bidx, params = _setup()
+    lo, hi = shard_range(len(questions), rank, world)
+    assert shard_questions(questions, rank, world) == questions[lo:hi]
+    p, loss = _grads(ont, params, questions, counts, feats, bidx, lo, hi, len(questions))
+    keys = sorted(p)
+    bucket = FlatBucket([p[k] for k in keys])
+    for k in keys:
+        if p[k].grad is not None:
+            bucket.grads[id(p[k])].copy_(p[k].grad)
+    bucket.all_reduce()
+    dist.all_reduce(loss)
+    if rank == 0:
+        torch.save({'flat_grad': bucket.flat_grad.clone(), 'loss': loss, 'keys': keys}, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_equals_full_batch(tmp_path):
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / 'dp.pt')
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    ont, questions, counts, feats, bidx, params = _setup()
+    p, loss = _grads(ont, params, questions, counts, feats, bidx, 0, len(questions), len(questions))
+    ref = torch.cat([(p[k].grad if p[k].grad is not None else torch.zeros_like(p[k])).reshape(-1) for k in got['keys']])
+    assert torch.allclose(got['flat_grad'], ref, rtol=1e-5, atol=1e-7)
+    assert abs(float(got['loss']) - float(loss)) <= 1e-6 * max(1.0, abs(float(loss)))
+
+
+def test_shard_ranges_cover_everything():
+    for total in (1, 7, 256, 4096):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
