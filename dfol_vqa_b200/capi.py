@@ -54,7 +54,13 @@ _SIGNATURES = {
     'dfol_table_layer_bwd': (c_int, [P, P, P, P, P, c_int, P, P, P, P, P, P, c_int64, P, c_int64, c_int, P,
                                      c_int64, P, P, P]),
     'dfol_table_layer_bwd_fused': (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, c_int64, P, c_int64, c_int,
-                                           c_int, P, c_int64, P, P, P]),
+                                           c_int, P, c_int64, c_int, c_int, P, P, P]),
+    'dfol_gemm_bf16_tc_dgrad': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, P, c_int64, c_int,
+                                        P]),
+    'dfol_gemm_bf16_tc_wgrad': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int64, P]),
+    'dfol_pair_hidden_bwd_bf16': (c_int, [P, c_int64, P, c_int64, P, c_int64, P, c_int64, P, c_int, P, P, P, c_int,
+                                          c_int, P]),
+    'dfol_colsum_bf16': (c_int, [P, c_int64, c_int64, c_int, P, P]),
     'dfol_table_grad_dense': (c_int, [P, P, P, P, c_int, P, P, P, P, P, P, c_int64, P]),
     'dfol_sumsq': (c_int, [P, c_int64, P, P]),
     'dfol_adam_step': (c_int, [P, P, P, P, c_int64, P, c_float, c_float, c_float, c_float, c_float, c_float, c_int,

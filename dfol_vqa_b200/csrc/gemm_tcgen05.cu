@@ -9,10 +9,7 @@
 // One 128 x BN output tile per CTA, BN <= 256 chosen by the host so that two CTAs fit on an SM (<= 256 TMEM
 // columns and ~110 KB smem each): while one CTA drains its accumulator through the epilogue the other one issues
 // MMAs.  Every mbarrier wait is bounded (trap instead of hanging the GPU).
-#include <cuda.h>
-#include <cuda_bf16.h>
-
-#include "dfol_common.cuh"
+#include "tc_common.cuh"
 
 namespace dfol {
 
@@ -31,66 +28,9 @@ struct TcParams {
   int act, out_bf16, store;
   const int32_t* row_img; const int32_t* img_row; const int64_t* img_blk; const int32_t* img_stride;
   const int32_t* img_n; float diag_value;
+  // optional epilogue multiplier (backward): v *= act'(h) with h = mul_src[m * ld_mul + n] (bf16), DFOL_MUL_*
+  const __nv_bfloat16* mul_src; long long ld_mul; int mul_mode;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (long long spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (spin > (1ll << 26)) __trap();  // never hang the device: a lost arrival becomes a launch error
-  }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major, 128-byte swizzle, rows of 128 B packed densely: stride between 8-row groups = 1024 B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address, 16-byte units
-  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset
-  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
 
 template <int ACT>
 __device__ __forceinline__ float act_fast(float x) {
@@ -210,6 +150,22 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc_kernel(const __grid_c
       float v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = act_fast<ACT>(__uint_as_float(r[j]) + bias_s[c0 + j]);
+      if (STORE != ST_TABLE && p.mul_mode != DFOL_MUL_NONE && c0 + 16 <= n_valid) {
+        const uint4* hp = reinterpret_cast<const uint4*>(p.mul_src + (long long)m * p.ld_mul + n0 + c0);
+        const uint4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+        const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
+          if (p.mul_mode == DFOL_MUL_SIGMOID_GRAD) {
+            v[2 * j] *= h.x * (1.0f - h.x);
+            v[2 * j + 1] *= h.y * (1.0f - h.y);
+          } else {
+            v[2 * j] *= (h.x > 0.0f ? 1.0f : h.x + 1.0f);
+            v[2 * j + 1] *= (h.y > 0.0f ? 1.0f : h.y + 1.0f);
+          }
+        }
+      }
       if (STORE == ST_TABLE) {
         float* d = tdst + (long long)c0 * tstride;
         if (c0 + 16 <= n_valid) {
@@ -283,61 +239,31 @@ static TcKernel pick_kernel(int act, int store_kind) {
   return pick_act<ST_F32>(act);
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
 }  // namespace dfol
 
 using namespace dfol;
 
-// 2D bf16 tensor map, 128-byte swizzle, box = box_rows x 64 elements (out-of-bounds elements read as zero).
-static int encode_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld_elems, int box_rows) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  DFOL_REQUIRE(fn != nullptr, "dfol_gemm_bf16_tc: cuTensorMapEncodeTiled unavailable (driver)");
-  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("dfol_gemm_bf16_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return -2;
-  }
-  return 0;
-}
-
-extern "C" int dfol_gemm_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
-                                 const float* bias, int M, int N, int K, int act, int out_bf16, int store,
-                                 const int32_t* row_img, const int32_t* img_row, const int64_t* img_blk,
-                                 const int32_t* img_stride, const int32_t* img_n, float diag_value, void* stream) {
-  DFOL_REQUIRE(A && B && C, "dfol_gemm_bf16_tc: null pointer");
-  DFOL_REQUIRE(M > 0 && N > 0 && K > 0 && (K % TC_BK) == 0, "dfol_gemm_bf16_tc: K must be a positive multiple of 64");
+static int launch_tc(const char* who, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                     const float* bias, int M, int N, int K, int act, int out_bf16, int store, const int32_t* row_img,
+                     const int32_t* img_row, const int64_t* img_blk, const int32_t* img_stride, const int32_t* img_n,
+                     float diag_value, const void* mul_src, int64_t ld_mul, int mul_mode, void* stream) {
+  DFOL_REQUIRE(A && B && C, "%s: null pointer", who);
+  DFOL_REQUIRE(M > 0 && N > 0 && K > 0 && (K % TC_BK) == 0, "%s: K must be a positive multiple of 64", who);
   DFOL_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && lda >= K && ldb >= K,
-               "dfol_gemm_bf16_tc: lda/ldb must be >= K and multiples of 8 elements");
+               "%s: lda/ldb must be >= K and multiples of 8 elements", who);
   DFOL_REQUIRE((reinterpret_cast<uintptr_t>(A) % 16) == 0 && (reinterpret_cast<uintptr_t>(B) % 16) == 0,
-               "dfol_gemm_bf16_tc: operands must be 16-byte aligned");
-  DFOL_REQUIRE(store == 0 || (row_img && img_row && img_blk && img_stride), "dfol_gemm_bf16_tc: table maps missing");
-  DFOL_REQUIRE(store == 0 || !out_bf16, "dfol_gemm_bf16_tc: tables are fp32");
+               "%s: operands must be 16-byte aligned", who);
+  DFOL_REQUIRE(store == 0 || (row_img && img_row && img_blk && img_stride), "%s: table maps missing", who);
+  DFOL_REQUIRE(store == 0 || !out_bf16, "%s: tables are fp32", who);
+  DFOL_REQUIRE(mul_mode == DFOL_MUL_NONE ||
+                   (mul_src && store == 0 && (N % 16) == 0 && (ld_mul % 8) == 0 &&
+                    (reinterpret_cast<uintptr_t>(mul_src) % 16) == 0),
+               "%s: multiplier needs a 16-byte aligned bf16 source, ld %% 8 == 0 and N %% 16 == 0", who);
   // columns to cover: row-major outputs are zero-filled up to ldc (the next layer's K padding)
   int n_store = N;
   if (store == 0) {
-    DFOL_REQUIRE(ldc >= N, "dfol_gemm_bf16_tc: ldc < N");
-    DFOL_REQUIRE(!out_bf16 || (ldc % 8) == 0, "dfol_gemm_bf16_tc: bf16 output needs ldc %% 8 == 0");
+    DFOL_REQUIRE(ldc >= N, "%s: ldc < N", who);
+    DFOL_REQUIRE(!out_bf16 || (ldc % 8) == 0, "%s: bf16 output needs ldc %% 8 == 0", who);
     n_store = (int)ldc;
   }
   const int cover = (n_store + 15) / 16 * 16;
@@ -348,6 +274,7 @@ extern "C" int dfol_gemm_bf16_tc(const void* A, int64_t lda, const void* B, int6
   p.act = act; p.out_bf16 = out_bf16; p.store = store;
   p.row_img = row_img; p.img_row = img_row; p.img_blk = img_blk; p.img_stride = img_stride; p.img_n = img_n;
   p.diag_value = diag_value;
+  p.mul_src = reinterpret_cast<const __nv_bfloat16*>(mul_src); p.ld_mul = ld_mul; p.mul_mode = mul_mode;
   const int stage_bytes = (TC_BM + BN) * TC_BK * 2;
   int stages = (110 * 1024) / stage_bytes;  // two CTAs per SM
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -358,15 +285,30 @@ extern "C" int dfol_gemm_bf16_tc(const void* A, int64_t lda, const void* B, int6
   TcKernel kernel = pick_kernel(act, store == 1 ? ST_TABLE : (out_bf16 ? ST_BF16 : ST_F32));
   {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) { set_error("dfol_gemm_bf16_tc: %s", cudaGetErrorString(e)); return (int)e; }
+    if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return (int)e; }
   }
   alignas(64) CUtensorMap ma, mb;
-  int rc = encode_map(&ma, A, M, K, lda, TC_BM);
+  int rc = encode_map_bf16(&ma, A, M, K, lda, TC_BM);
   if (rc != 0) return rc;
-  rc = encode_map(&mb, B, N, K, ldb, BN);
+  rc = encode_map_bf16(&mb, B, N, K, ldb, BN);
   if (rc != 0) return rc;
   dim3 grid(n_tiles, (M + TC_BM - 1) / TC_BM);
-  DFOL_REQUIRE(grid.y <= 65535, "dfol_gemm_bf16_tc: M too large for one launch (%d row tiles)", (int)grid.y);
+  DFOL_REQUIRE(grid.y <= 65535, "%s: M too large for one launch (%d row tiles)", who, (int)grid.y);
   kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, p);
-  return finish_launch("dfol_gemm_bf16_tc");
+  return finish_launch(who);
+}
+
+extern "C" int dfol_gemm_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                                 const float* bias, int M, int N, int K, int act, int out_bf16, int store,
+                                 const int32_t* row_img, const int32_t* img_row, const int64_t* img_blk,
+                                 const int32_t* img_stride, const int32_t* img_n, float diag_value, void* stream) {
+  return launch_tc("dfol_gemm_bf16_tc", A, lda, B, ldb, C, ldc, bias, M, N, K, act, out_bf16, store, row_img, img_row,
+                   img_blk, img_stride, img_n, diag_value, nullptr, 0, DFOL_MUL_NONE, stream);
+}
+
+extern "C" int dfol_gemm_bf16_tc_dgrad(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX,
+                                       int64_t lddx, int M, int N, int K, const void* h_saved, int64_t ldh,
+                                       int mul_mode, void* stream) {
+  return launch_tc("dfol_gemm_bf16_tc_dgrad", dZ, lddz, Wt, ldwt, dX, lddx, nullptr, M, N, K, DFOL_ACT_NONE, 1, 0,
+                   nullptr, nullptr, nullptr, nullptr, nullptr, 0.0f, h_saved, ldh, mul_mode, stream);
 }

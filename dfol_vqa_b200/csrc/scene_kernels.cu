@@ -258,13 +258,18 @@ __global__ void __launch_bounds__(256) table_layer_bwd_kernel(
 //   dZ[row, e] = (sum_j dz_j[l] W[wrow_j, e]) * act'(H[row, e])             written once, no read-modify-write
 //   dW[wrow_j, e] += sum_l dz_j[l] H[row, e];  db[wrow_j] += sum_l dz_j[l]  (atomics, one per block and e)
 // Rows of images without slices are written as zero, so dZ needs no memset.
-template <int SMAX>
+__device__ __forceinline__ float ld_as_float(const float* p) { return *p; }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st_from_float(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_from_float(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+template <int SMAX, typename HT>
 __global__ void __launch_bounds__(256) table_layer_bwd_fused_kernel(
     const float* __restrict__ g, const int32_t* __restrict__ slice_goff, const int32_t* __restrict__ slice_col,
     const int32_t* __restrict__ slice_wrow, const int32_t* __restrict__ img_slice, const float* __restrict__ ll,
     const int64_t* __restrict__ blk, const int32_t* __restrict__ stride, const int32_t* __restrict__ row0,
     const int32_t* __restrict__ img_rows, const float* __restrict__ W, long long ldw,
-    const float* __restrict__ hs, long long ldh, int E, int act, float* __restrict__ dZ, long long lddz,
+    const HT* __restrict__ hs, long long ldh, int E, int act, HT* __restrict__ dZ, long long lddz, int out_cols,
     float* __restrict__ dW, float* __restrict__ db) {
   constexpr int R = 64;
   __shared__ float dz_s[SMAX][R];
@@ -277,18 +282,23 @@ __global__ void __launch_bounds__(256) table_layer_bwd_fused_kernel(
   const long long r0 = (long long)row0[b] + c;
   const int j0 = img_slice[b];
   const int S = min(img_slice[b + 1] - j0, SMAX);
+  // columns E .. out_cols are the zero K-padding of the next (tensor-core) GEMM
+  for (int idx = threadIdx.x; idx < cn * (out_cols - E); idx += blockDim.x) {
+    const int l = idx / (out_cols - E), e = E + idx - l * (out_cols - E);
+    st_from_float(dZ + (r0 + l) * lddz + e, 0.0f);
+  }
   if (S == 0) {
     for (int idx = threadIdx.x; idx < cn * E; idx += blockDim.x) {
       const int l = idx / E, e = idx - l * E;
-      dZ[(r0 + l) * lddz + e] = 0.0f;
+      st_from_float(dZ + (r0 + l) * lddz + e, 0.0f);
     }
     return;
   }
   const int st = stride[b];
-  for (int idx = threadIdx.x; idx < S * R; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < SMAX * R; idx += blockDim.x) {  // unused slice rows must be zero (0 * garbage)
     const int j = idx / R, l = idx - j * R;
     float v = 0.0f;
-    if (l < cn) {
+    if (j < S && l < cn) {
       const float gv = g[slice_goff[j0 + j] + c + l];
       if (gv != 0.0f) v = gv * (1.0f - expf(ll[blk[b] + (long long)slice_col[j0 + j] * st + c + l]));
     }
@@ -310,7 +320,7 @@ __global__ void __launch_bounds__(256) table_layer_bwd_fused_kernel(
       dwj[j] = 0.0f;
     }
     for (int l = 0; l < cn; ++l) {
-      const float h = hs[(r0 + l) * ldh + e];
+      const float h = ld_as_float(hs + (r0 + l) * ldh + e);
       float out = 0.0f;
 #pragma unroll
       for (int j = 0; j < SMAX; ++j) {
@@ -318,7 +328,7 @@ __global__ void __launch_bounds__(256) table_layer_bwd_fused_kernel(
         out += dz * wj[j];
         dwj[j] += dz * h;
       }
-      dZ[(r0 + l) * lddz + e] = out * act_grad_from_output(h, act);
+      st_from_float(dZ + (r0 + l) * lddz + e, out * act_grad_from_output(h, act));
     }
 #pragma unroll
     for (int j = 0; j < SMAX; ++j)
@@ -342,6 +352,83 @@ __global__ void __launch_bounds__(256) table_grad_dense_kernel(
   for (int l = threadIdx.x & 31; l < rows; l += 32) {
     const float gv = gj[l];
     if (gv != 0.0f) atomicAdd(dZ + ((long long)row0[b] + l) * lddz + col, gv * (1.0f - expf(lj[l])));
+  }
+}
+
+
+// Backward of the pair hidden layer from bf16 dZ (activation derivative already applied by the dgrad epilogue).
+// One block per image, thread h owns hidden unit h: streams the image's N^2 rows (coalesced over h), keeps dU[s]
+// in a register, dV[o][h] in shared memory (thread-private column: no conflicts), dWg / db in registers.
+__global__ void __launch_bounds__(256) pair_hidden_bwd_bf16_kernel(
+    const __nv_bfloat16* __restrict__ dz, long long lddz, const float* __restrict__ pos, long long ldpos,
+    float* __restrict__ duv, long long lduv, float* __restrict__ dwg, long long ldw, float* __restrict__ dbias, int H,
+    const int32_t* __restrict__ pair_row, const int32_t* __restrict__ obj_row, const int32_t* __restrict__ img_n) {
+  extern __shared__ float dv_s[];  // [n][H]
+  const int b = blockIdx.x;
+  const int n = img_n[b];
+  const long long t0 = obj_row[b];
+  const long long p0 = pair_row[b];
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    for (int o = 0; o < n; ++o) dv_s[o * H + h] = 0.0f;
+    float dw0 = 0.f, dw1 = 0.f, dw2 = 0.f, dw3 = 0.f, dbh = 0.f;
+    for (int s = 0; s < n; ++s) {
+      float du = 0.f;
+      const __nv_bfloat16* row = dz + (p0 + (long long)s * n) * lddz + h;
+      const float* ps = pos + (t0 + s) * ldpos;
+      int o = 0;
+      for (; o + 4 <= n; o += 4) {  // four independent loads in flight
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __bfloat162float(row[(long long)(o + i) * lddz]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (o + i == s) continue;
+          float g[4];
+          pair_geometry(ps, pos + (t0 + o + i) * ldpos, g);
+          du += v[i];
+          dv_s[(o + i) * H + h] += v[i];
+          dw0 += v[i] * g[0]; dw1 += v[i] * g[1]; dw2 += v[i] * g[2]; dw3 += v[i] * g[3];
+        }
+      }
+      for (; o < n; ++o) {
+        if (o == s) continue;
+        const float v = __bfloat162float(row[(long long)o * lddz]);
+        float g[4];
+        pair_geometry(ps, pos + (t0 + o) * ldpos, g);
+        du += v;
+        dv_s[o * H + h] += v;
+        dw0 += v * g[0]; dw1 += v * g[1]; dw2 += v * g[2]; dw3 += v * g[3];
+      }
+      duv[(t0 + s) * lduv + h] = du;
+      dbh += du;
+    }
+    for (int o = 0; o < n; ++o) duv[(t0 + o) * lduv + H + h] = dv_s[o * H + h];
+    atomicAdd(dbias + h, dbh);
+    atomicAdd(dwg + h * ldw + 0, dw0);
+    atomicAdd(dwg + h * ldw + 1, dw1);
+    atomicAdd(dwg + h * ldw + 2, dw2);
+    atomicAdd(dwg + h * ldw + 3, dw3);
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ldx,
+                                                          long long M, int N, float* __restrict__ out,
+                                                          long long rows_per_block) {
+  __shared__ float part[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  float acc = 0.f;
+  if (col < N)
+    for (long long r = r0 + ry; r < r1; r += 8) acc += __bfloat162float(X[r * ldx + col]);
+  part[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][cx];
+    atomicAdd(out + col, t);
   }
 }
 
@@ -453,17 +540,24 @@ extern "C" int dfol_table_layer_bwd_fused(const float* g, const int32_t* slice_g
                                           const int32_t* slice_wrow, const int32_t* img_slice, int image_num,
                                           int max_rows, const float* ll, const int64_t* blk, const int32_t* stride,
                                           const int32_t* row0, const int32_t* img_rows, const float* W, int64_t ldw,
-                                          const float* h_saved, int64_t ldh, int E, int act, float* dZ, int64_t lddz,
-                                          float* dW, float* db, void* stream) {
+                                          const void* h_saved, int64_t ldh, int E, int act, void* dZ, int64_t lddz,
+                                          int out_cols, int bf16_io, float* dW, float* db, void* stream) {
   DFOL_REQUIRE(g && slice_goff && slice_col && slice_wrow && img_slice && ll && blk && stride && row0 && img_rows &&
                    W && h_saved && dZ && dW && db,
                "dfol_table_layer_bwd_fused: null pointer");
   if (image_num == 0 || max_rows == 0) return 0;
   dim3 grid((max_rows + 63) / 64, image_num);
   DFOL_REQUIRE(grid.y <= 65535, "dfol_table_layer_bwd_fused: too many images");
-  table_layer_bwd_fused_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(
-      g, slice_goff, slice_col, slice_wrow, img_slice, ll, blk, stride, row0, img_rows, W, ldw, h_saved, ldh, E, act,
-      dZ, lddz, dW, db);
+  DFOL_REQUIRE(out_cols >= E && out_cols <= lddz, "dfol_table_layer_bwd_fused: E <= out_cols <= lddz");
+  if (bf16_io)
+    table_layer_bwd_fused_kernel<8, __nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        g, slice_goff, slice_col, slice_wrow, img_slice, ll, blk, stride, row0, img_rows, W, ldw,
+        reinterpret_cast<const __nv_bfloat16*>(h_saved), ldh, E, act, reinterpret_cast<__nv_bfloat16*>(dZ), lddz,
+        out_cols, dW, db);
+  else
+    table_layer_bwd_fused_kernel<8, float><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        g, slice_goff, slice_col, slice_wrow, img_slice, ll, blk, stride, row0, img_rows, W, ldw,
+        reinterpret_cast<const float*>(h_saved), ldh, E, act, reinterpret_cast<float*>(dZ), lddz, out_cols, dW, db);
   return finish_launch("dfol_table_layer_bwd_fused");
 }
 
@@ -477,4 +571,30 @@ extern "C" int dfol_table_grad_dense(const float* g, const int32_t* slice_goff, 
   table_grad_dense_kernel<<<(slice_num + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
       g, slice_goff, slice_col, slice_img, slice_num, ll, blk, stride, row0, img_rows, dZ, lddz);
   return finish_launch("dfol_table_grad_dense");
+}
+
+extern "C" int dfol_pair_hidden_bwd_bf16(const void* dz, int64_t lddz, const float* obj_pos, int64_t ldpos, float* duv,
+                                         int64_t lduv, float* dwg, int64_t ldw, float* dbias, int H,
+                                         const int32_t* pair_row, const int32_t* obj_row, const int32_t* img_n,
+                                         int image_num, int max_n, void* stream) {
+  DFOL_REQUIRE(dz && obj_pos && duv && dwg && dbias && pair_row && obj_row && img_n,
+               "dfol_pair_hidden_bwd_bf16: null pointer");
+  if (image_num == 0) return 0;
+  const size_t smem = (size_t)max_n * H * sizeof(float);
+  DFOL_REQUIRE(smem <= 200 * 1024, "dfol_pair_hidden_bwd_bf16: N * H too large for shared memory");
+  cudaFuncSetAttribute(pair_hidden_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  pair_hidden_bwd_bf16_kernel<<<image_num, 256, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dz), lddz, obj_pos, ldpos, duv, lduv, dwg, ldw, dbias, H, pair_row,
+      obj_row, img_n);
+  return finish_launch("dfol_pair_hidden_bwd_bf16");
+}
+
+extern "C" int dfol_colsum_bf16(const void* X, int64_t ldx, int64_t M, int N, float* out, void* stream) {
+  DFOL_REQUIRE(X && out, "dfol_colsum_bf16: null pointer");
+  if (M == 0 || N == 0) return 0;
+  long long rows_per_block = 2048;
+  dim3 grid((N + 31) / 32, (unsigned)((M + rows_per_block - 1) / rows_per_block));
+  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(X), ldx, M, N, out,
+                                                            rows_per_block);
+  return finish_launch("dfol_colsum_bf16");
 }

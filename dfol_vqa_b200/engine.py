@@ -199,16 +199,20 @@ class ReasoningEngine(object):
         wa1 = self._cast16(w.attr[0].weight, Op, st)
         wa2 = self._cast16(w.attr[1].weight, Hap, st)
         we16 = self._cast16(w.emb.weight, Ep, st)
-        h1a = torch.empty(T, Hap, device=dev, dtype=torch.bfloat16)
-        self._tc(obj16, wa1, h1a, Ha, Op, w.attr[0].bias, K.ACT_ELU, st)
-        h2a = torch.empty(T, Ep, device=dev, dtype=torch.bfloat16)
-        self._tc(h1a, wa2, h2a, E, Hap, w.attr[1].bias, K.ACT_SIGMOID, st)
+        # object-sized activations are kept in fp32 (they are tiny and the fp32 backward kernels consume them);
+        # the tensor-core operands are bf16 copies
+        h1a32 = torch.empty(T, Ha, device=dev, dtype=torch.float32)
+        self._tc(obj16, wa1, h1a32, Ha, Op, w.attr[0].bias, K.ACT_ELU, st)
+        h1a = self._cast16(h1a32, Hap, st)
+        h2a32 = torch.empty(T, E, device=dev, dtype=torch.float32)
+        self._tc(h1a, wa2, h2a32, E, Hap, w.attr[1].bias, K.ACT_SIGMOID, st)
+        h2a = self._cast16(h2a32, Ep, st)
         attr_ll = torch.empty(layout.attr_size, device=dev, dtype=torch.float32)
         obj_table = {'row_img': layout.obj_img, 'img_row': layout.obj_row, 'img_blk': layout.attr_blk,
                      'img_stride': layout.attr_stride}
         self._tc(h2a, we16, attr_ll, w.emb.weight.shape[0], Ep, w.emb.bias, K.ACT_LOGSIGMOID, st, table=obj_table)
         sc.attr_ll = attr_ll
-        sc.attr_h = [h1a, h2a]
+        sc.attr_h = [h1a32, h2a32]
 
         # relation chain: U|V in one GEMM (N = 2H), pair hidden layer in bf16, two tensor-core layers over pairs
         first = w.rel[0]
@@ -367,9 +371,6 @@ class ReasoningEngine(object):
     def backward(self, cp, scene, tape, d_lp, grads):
         """d loss / d parameters given d loss / d lp.  ``grads``: dict param tensor id -> fp32 grad tensor of the
         parameter's shape (accumulated into; callers zero them)."""
-        if self.gemm_mode != 'fp32':
-            raise NotImplementedError('backward through the bf16 tensor-core scene build is not implemented yet; '
-                                      'train in gemm_mode="fp32"')
         w = self.w
         lay = scene.layout
         dev = scene.attr_ll.device
@@ -415,17 +416,20 @@ class ReasoningEngine(object):
             ridx = self.rel_index(dev)
             G(w.emb.weight).index_add_(0, ridx, dw_rel)
             G(w.emb.bias).index_add_(0, ridx, db_rel)
-            # dense layers above the pair hidden layer
-            d_h1 = self._mlp_backward(w.rel[1:], scene.rel_h, d_h, None, grads, st, first_layer_input_grad=False,
-                                      d_out_is_dz=is_dz and len(w.rel) > 1)
             first = w.rel[0]
             H = first.weight.shape[0]
-            duv = torch.zeros(T, 2 * H, device=dev, dtype=torch.float32)
             gw1 = G(first.weight)
-            act1 = K.ACT_ELU if len(w.rel) > 1 else K.ACT_SIGMOID
-            call('dfol_pair_hidden_bwd', ptr(d_h1), d_h1.stride(0), ptr(scene.rel_h[0]), scene.rel_h[0].stride(0),
-                 ptr(obj[:, F:]), ldo, ptr(duv), duv.stride(0), ptr(gw1[:, 2 * ldo:]), gw1.stride(0),
-                 ptr(G(first.bias)), H, act1, ptr(lay.pair_row), ptr(lay.obj_row), ptr(lay.img_n), lay.B, st)
+            if self.gemm_mode == 'bf16':
+                duv = self._rel_backward_bf16(scene, d_h, grads, st)
+            else:
+                # dense layers above the pair hidden layer
+                d_h1 = self._mlp_backward(w.rel[1:], scene.rel_h, d_h, None, grads, st, first_layer_input_grad=False,
+                                          d_out_is_dz=is_dz and len(w.rel) > 1)
+                duv = torch.zeros(T, 2 * H, device=dev, dtype=torch.float32)
+                act1 = K.ACT_ELU if len(w.rel) > 1 else K.ACT_SIGMOID
+                call('dfol_pair_hidden_bwd', ptr(d_h1), d_h1.stride(0), ptr(scene.rel_h[0]), scene.rel_h[0].stride(0),
+                     ptr(obj[:, F:]), ldo, ptr(duv), duv.stride(0), ptr(gw1[:, 2 * ldo:]), gw1.stride(0),
+                     ptr(G(first.bias)), H, act1, ptr(lay.pair_row), ptr(lay.obj_row), ptr(lay.img_n), lay.B, st)
             sk = _split_for(T)
             gemm_f32(duv[:, :H].t(), obj, gw1[:, :ldo], accumulate=(sk == 1), split_k=sk, stream=st)
             gemm_f32(duv[:, H:].t(), obj, gw1[:, ldo:2 * ldo], accumulate=(sk == 1), split_k=sk, stream=st)
@@ -439,6 +443,39 @@ class ReasoningEngine(object):
         sk = _split_for(T)
         gemm_f32(d_obj[:, :F].t(), scene.features[:, :D], G(w.feat.weight), accumulate=(sk == 1), split_k=sk, stream=st)
 
+    def _rel_backward_bf16(self, scene, dz2, grads, st):
+        """Relation chain backward on the tensor cores: dz2 = d loss / d (layer-2 pre-activation), bf16 (P, Ep).
+
+        db2 = colsum(dz2); dW2 += dz2^T . h1 (MN-major tcgen05 wgrad, split-K); dz1 = (dz2 . W2) * elu'(h1) (tcgen05
+        dgrad with the derivative in the epilogue); then the pair-hidden reduction to dU|dV, dWg, db1."""
+        w = self.w
+        lay = scene.layout
+        dev = dz2.device
+        first, second = w.rel[0], w.rel[1]
+        H, E = first.weight.shape[0], second.weight.shape[0]
+        h1 = scene.rel_h[0]
+        P, Hp = h1.shape
+        Ep = dz2.shape[1]
+        F = w.feat.weight.shape[0]
+        ldo = F + 4
+        call('dfol_colsum_bf16', ptr(dz2), Ep, P, E, ptr(grads[id(second.bias)]), st)
+        gw2 = grads[id(second.weight)]
+        if capi.trace is not None:
+            capi.next_meta = {'tag': 'gemm_bf16_tc_wgrad[%dx%dx%d]' % (E, H, P), 'flops': 2.0 * E * H * P}
+        call('dfol_gemm_bf16_tc_wgrad', ptr(dz2), Ep, ptr(h1), Hp, ptr(gw2), gw2.stride(0), E, H, P, st)
+        w2t = self._cast16(second.weight.detach().t().contiguous(), Ep, st)      # (H, Ep): B operand of the dgrad
+        dz1 = torch.empty(P, Hp, device=dev, dtype=torch.bfloat16)
+        if capi.trace is not None:
+            capi.next_meta = {'tag': 'gemm_bf16_tc_dgrad[%dx%dx%d]' % (P, H, Ep), 'flops': 2.0 * P * H * Ep}
+        call('dfol_gemm_bf16_tc_dgrad', ptr(dz2), Ep, ptr(w2t), Ep, ptr(dz1), Hp, P, H, Ep, ptr(h1), Hp,
+             K.MUL_ELU_GRAD, st)
+        duv = torch.empty(lay.T, 2 * H, device=dev, dtype=torch.float32)
+        gw1 = grads[id(first.weight)]
+        call('dfol_pair_hidden_bwd_bf16', ptr(dz1), Hp, ptr(scene.obj[:, F:]), ldo, ptr(duv), duv.stride(0),
+             ptr(gw1[:, 2 * ldo:]), gw1.stride(0), ptr(grads[id(first.bias)]), H, ptr(lay.pair_row), ptr(lay.obj_row),
+             ptr(lay.img_n), lay.B, lay.max_n, st)
+        return duv
+
     def _table_backward(self, g, tabs, ll, blk, stride, row0, img_rows, max_rows, rows_total, W, dW, db, h_last,
                         fuse_act, st):
         """Backward of a table layer LL = logsigmoid(h_last W^T + b) from the compact program gradient slices.
@@ -450,12 +487,22 @@ class ReasoningEngine(object):
         E = W.shape[1]
         if tabs['count'] == 0:
             return torch.zeros(rows_total, E, device=dev, dtype=torch.float32), False
+        if h_last.dtype == torch.bfloat16:
+            if tabs['max_per_image'] > 8:
+                raise NotImplementedError('bf16 backward: more than 8 relation columns per image')
+            cols = h_last.shape[1]  # padded width (zero K-padding of the next tensor-core GEMM)
+            d = torch.empty(rows_total, cols, device=dev, dtype=torch.bfloat16)
+            call('dfol_table_layer_bwd_fused', ptr(g), ptr(tabs['goff']), ptr(tabs['col']), ptr(tabs['col']),
+                 ptr(tabs['img_slice']), len(tabs['img_slice']) - 1, max_rows, ptr(ll), ptr(blk), ptr(stride),
+                 ptr(row0), ptr(img_rows), ptr(W), W.stride(0), ptr(h_last), h_last.stride(0), E, fuse_act, ptr(d),
+                 d.stride(0), cols, 1, ptr(dW), ptr(db), st)
+            return d, True
         if tabs['max_per_image'] <= 8:
             d = torch.empty(rows_total, E, device=dev, dtype=torch.float32)
             call('dfol_table_layer_bwd_fused', ptr(g), ptr(tabs['goff']), ptr(tabs['col']), ptr(tabs['col']),
                  ptr(tabs['img_slice']), len(tabs['img_slice']) - 1, max_rows, ptr(ll), ptr(blk), ptr(stride),
                  ptr(row0), ptr(img_rows), ptr(W), W.stride(0), ptr(h_last), h_last.stride(0), E, fuse_act, ptr(d),
-                 d.stride(0), ptr(dW), ptr(db), st)
+                 d.stride(0), E, 0, ptr(dW), ptr(db), st)
             return d, fuse_act != K.ACT_NONE
         C = W.shape[0]
         dz = torch.zeros(rows_total, C, device=dev, dtype=torch.float32)

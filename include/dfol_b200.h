@@ -79,6 +79,16 @@ int dfol_gemm_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, vo
                       const int32_t* row_img, const int32_t* img_row, const int64_t* img_blk,
                       const int32_t* img_stride, const int32_t* img_n, float diag_value, void* stream);
 
+/* Backward contractions of the tensor-core mode (bf16 operands, fp32 accumulation):
+ * dgrad: dX[M,N] (bf16, ld lddx) = (dZ[M,K] . Wt[N,K]^T) * act'(h_saved[m,n])  -- Wt is the TRANSPOSED weight,
+ *        mul_mode = DFOL_MUL_* evaluated from the saved bf16 activation output (epilogue multiplier);
+ * wgrad: C[M,N] (fp32) += A[K,M]^T . B[K,N] with the reduction over ROWS (K = pair / object rows): MN-major UMMA
+ *        operands straight from the row-major activations, split-K over CTAs, red.global.add.f32 epilogue. */
+int dfol_gemm_bf16_tc_dgrad(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX, int64_t lddx, int M,
+                            int N, int K, const void* h_saved, int64_t ldh, int mul_mode, void* stream);
+int dfol_gemm_bf16_tc_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
+                            int64_t K, void* stream);
+
 /* fp32 -> bf16 cast with row padding: dst[r*ldd + c] = bf16(src[r*lds + c]) for c < cols, 0 for cols <= c < ldd */
 int dfol_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 
@@ -104,6 +114,12 @@ int dfol_pair_hidden_bwd(const float* dh, int64_t lddh, const float* h_saved, in
                          int64_t ldpos, float* duv, int64_t lduv, float* dwg, int64_t ldw, float* dbias, int H,
                          int act, const int32_t* pair_row, const int32_t* obj_row, const int32_t* img_n,
                          int image_num, void* stream);
+
+/* bf16 variant: dz already carries the activation derivative (dgrad epilogue); duv is WRITTEN (no memset needed). */
+int dfol_pair_hidden_bwd_bf16(const void* dz, int64_t lddz, const float* obj_pos, int64_t ldpos, float* duv,
+                              int64_t lduv, float* dwg, int64_t ldw, float* dbias, int H, const int32_t* pair_row,
+                              const int32_t* obj_row, const int32_t* img_n, int image_num, int max_n, void* stream);
+int dfol_colsum_bf16(const void* X, int64_t ldx, int64_t M, int N, float* out, void* stream);
 
 /* in place dH[m,n] *= act'(.) evaluated from the saved activation output H[m,n] (act = DFOL_ACT_*) */
 int dfol_act_grad_mul(float* dH, int64_t lddh, const float* H, int64_t ldh, int64_t rows, int cols, int act,
@@ -195,13 +211,14 @@ int dfol_table_layer_bwd(const float* g, const int32_t* slice_goff, const int32_
 /* Fused variant for tables where an image touches at most 8 columns (the relation table): one pass over the rows
  * of every image, writes dZ = (sum_j dz_j W[wrow_j]) * act'(Hsaved) for ALL rows (zero where an image has no
  * slice: dZ needs no memset), accumulates dW / db with atomics.  max_rows = largest img_rows[b].
- * The caller guarantees img_slice[b+1] - img_slice[b] <= 8 for every image (otherwise use the general kernels). */
+ * The caller guarantees img_slice[b+1] - img_slice[b] <= 8 for every image (otherwise use the general kernels).
+ * bf16_io != 0: h_saved and dZ are bf16 (tensor-core mode); columns E <= e < out_cols of dZ are written as zero. */
 int dfol_table_layer_bwd_fused(const float* g, const int32_t* slice_goff, const int32_t* slice_col,
                                const int32_t* slice_wrow, const int32_t* img_slice, int image_num, int max_rows,
                                const float* ll, const int64_t* blk, const int32_t* stride, const int32_t* row0,
-                               const int32_t* img_rows, const float* W, int64_t ldw, const float* h_saved,
-                               int64_t ldh, int E, int act, float* dZ, int64_t lddz, float* dW, float* db,
-                               void* stream);
+                               const int32_t* img_rows, const float* W, int64_t ldw, const void* h_saved,
+                               int64_t ldh, int E, int act, void* dZ, int64_t lddz, int out_cols, int bf16_io,
+                               float* dW, float* db, void* stream);
 
 /* Dense variant for tables where images touch many columns (attribute options): scatters the slices into a zeroed
  * dense (rows x columns) matrix with logsigmoid' applied, dZ[row0[b] + l, col_j] += g_j[l] * (1 - exp(LL_j[l]));

@@ -221,3 +221,73 @@ def test_bf16_mode_answer_logits(terminal):
                 assert sorted(out['answer'][q]) == sorted(results[0]['answer'][q]), q
                 checked += 1
     assert checked > 0
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 64, 64), (300, 256, 5000), (512, 2048, 12288), (100, 516, 777), (300, 256, 589824)])
+def test_gemm_bf16_tcgen05_wgrad(M, N, K):
+    """MN-major split-K tcgen05 contraction C += A^T B (reduction over rows) vs fp64 on the same bf16 operands."""
+    from dfol_vqa_b200.capi import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(M + N)
+    lda, ldb = (M + 63) // 64 * 64, (N + 7) // 8 * 8
+    A = torch.zeros(K, lda, dtype=torch.bfloat16)
+    A[:, :M] = (torch.randn(K, M, generator=g) * 0.5).bfloat16()
+    B = torch.zeros(K, ldb, dtype=torch.bfloat16)
+    B[:, :N] = (torch.randn(K, N, generator=g) * 0.5).bfloat16()
+    Ad, Bd = A.cuda(), B.cuda()
+    C = torch.ones(M, N, device='cuda')
+    call('dfol_gemm_bf16_tc_wgrad', ptr(Ad), lda, ptr(Bd), ldb, ptr(C), N, M, N, K, stream_ptr())
+    torch.cuda.synchronize()
+    ref = Ad[:, :M].double().t() @ Bd[:, :N].double() + 1.0
+    err = (C.double() - ref).abs().max()
+    assert err <= 1e-3 * (K ** 0.5) * 0.25 + 1e-3, float(err)
+
+
+@pytest.mark.parametrize('M,N,K', [(1000, 256, 320), (4608, 256, 320), (300, 64, 64)])
+@pytest.mark.parametrize('mode', [0, 1, 2])
+def test_gemm_bf16_tcgen05_dgrad(M, N, K, mode):
+    from dfol_vqa_b200.capi import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(M + mode)
+    dZ = (torch.randn(M, K, generator=g)).cuda().bfloat16()
+    Wt = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
+    Hs = (torch.rand(M, N, generator=g) - 0.3).cuda().bfloat16()
+    dX = torch.full((M, N), float('nan'), device='cuda', dtype=torch.bfloat16)
+    call('dfol_gemm_bf16_tc_dgrad', ptr(dZ), K, ptr(Wt), K, ptr(dX), N, M, N, K, ptr(Hs), N, mode, stream_ptr())
+    torch.cuda.synchronize()
+    ref = dZ.double() @ Wt.double().t()
+    h = Hs.double()
+    if mode == 1:
+        ref = ref * h * (1 - h)
+    elif mode == 2:
+        ref = ref * torch.where(h > 0, torch.ones_like(h), h + 1)
+    assert torch.allclose(dX.double(), ref, rtol=1.5e-2, atol=1.5e-2), (dX.double() - ref).abs().max()
+
+
+@pytest.mark.parametrize('terminal', ['verify_rel', 'exist', 'and'])
+def test_bf16_mode_training_gradients(terminal):
+    """Training step in bf16 tensor-core mode: loss within 2e-2, gradients within a few percent of each tensor's
+    scale of the fp32 oracle (mixed precision: bf16 operands, fp32 accumulation / master weights)."""
+    from dfol_vqa_b200 import synth
+    from dfol_vqa_b200.ontology import synthetic_ontology
+    from dfol_vqa_b200.programs import ProgramCollater
+    from dfol_vqa_b200.interpreter import FusedTrainStep
+    dims = dict(box=2048, feat=512, hidden=256, emb=300)
+    ont = synthetic_ontology(400, 60, 6, 5, seed=3, embedding_dim=300)
+    interp = helpers.build_interpreter(ont, dims, seed=5, gemm_mode='bf16', emb_bias=-4.0)
+    questions = synth.make_questions(ont, 16, terminal, 1, 3, seed=31, relate_prob=0.6)
+    counts = synth.object_counts(16, 48, True, seed=32)
+    feats, bidx = synth.make_object_features(counts, 2048, seed=33)
+    pbs = ProgramCollater(1, lambda qs: (feats, bidx)).collate(questions)
+    params = helpers.oracle_params(interp, torch.float32, requires_grad=True)
+    results, loss_ref = orc.run_step(ont, params, ProgramCollater(1, lambda qs: (feats, bidx)).collate(
+        json.loads(json.dumps(questions))), is_training=True)
+    loss_ref.backward()
+    step = FusedTrainStep(interp)
+    loss = step.forward_backward(helpers.to_cuda(pbs))
+    assert abs(float(loss) - float(loss_ref)) <= 2e-2 * max(1.0, abs(float(loss_ref)))
+    keys = {id(p): k for k, p in interp.named_parameters()}
+    for p in interp.oracle_parameters():
+        k = keys[id(p)]
+        g_ref = params[k].grad if params[k].grad is not None else torch.zeros_like(params[k])
+        scale = float(g_ref.abs().max())
+        err = float((step.grads[id(p)].cpu() - g_ref).abs().max())
+        assert err <= 6e-2 * scale + 1e-6, (k, err, scale)
