@@ -17,7 +17,7 @@ _lib = None
 
 class K(object):
     """Constants of include/dfol_b200.h."""
-    ABI_VERSION = 1
+    ABI_VERSION = 2
     ACT_NONE, ACT_ELU, ACT_SIGMOID, ACT_LOGSIGMOID = 0, 1, 2, 3
     MUL_NONE, MUL_SIGMOID_GRAD, MUL_ELU_GRAD = 0, 1, 2
     INSTR_WORDS = 12
@@ -55,8 +55,17 @@ _SIGNATURES = {
                                      c_int64, P, P, P]),
     'dfol_table_layer_bwd_fused': (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, c_int64, P, c_int64, c_int,
                                            c_int, P, c_int64, c_int, c_int, P, P, P]),
-    'dfol_gemm_bf16_tc_dgrad': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, P, c_int64, c_int,
+    'dfol_gemm_bf16_tc_dgrad': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, c_int64,
+                                        c_int, P]),
+    'dfol_cast_jobs': (c_int, [P, c_int, c_int64, P]),
+    'dfol_cast_job_size': (c_int, []),
+    'dfol_obj_finish': (c_int, [P, c_int64, c_int, P, c_int64, c_int, P, c_int64, c_int64, P]),
+    'dfol_pair_hidden_fwd_tc': (c_int, [P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int, P, P, P, P, c_int,
+                                        c_int, P]),
+    'dfol_pair_hidden_bwd_tc': (c_int, [P, c_int64, P, P, P, c_int64, P, c_int64, P, c_int, P, P, P, c_int, c_int,
                                         P]),
+    'dfol_table_layer_bwd_tc': (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, c_int64, P, c_int64,
+                                        c_int, P, c_int64, c_int, P, P, P, P]),
     'dfol_gemm_bf16_tc_wgrad': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int64, P]),
     'dfol_pair_hidden_bwd_bf16': (c_int, [P, c_int64, P, c_int64, P, c_int64, P, c_int64, P, c_int, P, P, P, c_int,
                                           c_int, P]),

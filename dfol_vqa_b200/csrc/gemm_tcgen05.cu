@@ -246,7 +246,8 @@ using namespace dfol;
 static int launch_tc(const char* who, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                      const float* bias, int M, int N, int K, int act, int out_bf16, int store, const int32_t* row_img,
                      const int32_t* img_row, const int64_t* img_blk, const int32_t* img_stride, const int32_t* img_n,
-                     float diag_value, const void* mul_src, int64_t ld_mul, int mul_mode, void* stream) {
+                     float diag_value, const void* mul_src, int64_t ld_mul, int mul_mode, int store_cols,
+                     void* stream) {
   DFOL_REQUIRE(A && B && C, "%s: null pointer", who);
   DFOL_REQUIRE(M > 0 && N > 0 && K > 0 && (K % TC_BK) == 0, "%s: K must be a positive multiple of 64", who);
   DFOL_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && lda >= K && ldb >= K,
@@ -264,7 +265,8 @@ static int launch_tc(const char* who, const void* A, int64_t lda, const void* B,
   if (store == 0) {
     DFOL_REQUIRE(ldc >= N, "%s: ldc < N", who);
     DFOL_REQUIRE(!out_bf16 || (ldc % 8) == 0, "%s: bf16 output needs ldc %% 8 == 0", who);
-    n_store = (int)ldc;
+    n_store = store_cols > 0 ? store_cols : (int)ldc;
+    DFOL_REQUIRE(n_store >= N && n_store <= ldc, "%s: N <= store_cols <= ldc", who);
   }
   const int cover = (n_store + 15) / 16 * 16;
   const int n_tiles = (cover + 255) / 256;
@@ -303,12 +305,12 @@ extern "C" int dfol_gemm_bf16_tc(const void* A, int64_t lda, const void* B, int6
                                  const int32_t* row_img, const int32_t* img_row, const int64_t* img_blk,
                                  const int32_t* img_stride, const int32_t* img_n, float diag_value, void* stream) {
   return launch_tc("dfol_gemm_bf16_tc", A, lda, B, ldb, C, ldc, bias, M, N, K, act, out_bf16, store, row_img, img_row,
-                   img_blk, img_stride, img_n, diag_value, nullptr, 0, DFOL_MUL_NONE, stream);
+                   img_blk, img_stride, img_n, diag_value, nullptr, 0, DFOL_MUL_NONE, 0, stream);
 }
 
 extern "C" int dfol_gemm_bf16_tc_dgrad(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX,
-                                       int64_t lddx, int M, int N, int K, const void* h_saved, int64_t ldh,
-                                       int mul_mode, void* stream) {
+                                       int64_t lddx, int store_cols, int M, int N, int K, const void* h_saved,
+                                       int64_t ldh, int mul_mode, void* stream) {
   return launch_tc("dfol_gemm_bf16_tc_dgrad", dZ, lddz, Wt, ldwt, dX, lddx, nullptr, M, N, K, DFOL_ACT_NONE, 1, 0,
-                   nullptr, nullptr, nullptr, nullptr, nullptr, 0.0f, h_saved, ldh, mul_mode, stream);
+                   nullptr, nullptr, nullptr, nullptr, nullptr, 0.0f, h_saved, ldh, mul_mode, store_cols, stream);
 }

@@ -1,0 +1,504 @@
+// HBM-bound companions of the tensor-core (bf16) mode: operand preparation, the pair hidden layer (forward and
+// backward) and the backward of the table layer.  Every kernel here streams its big operand exactly once with
+// 128-byte warp transactions and keeps its reductions in registers / shared memory (see include/dfol_b200.h).
+#include <cuda_bf16.h>
+
+#include "dfol_common.cuh"
+
+namespace dfol {
+
+// ---------------------------------------------------------------------------------------------------------
+// Batched fp32 -> bf16 operand preparation: one launch casts (and optionally transposes) every weight matrix of
+// the step.  dst is [out_rows][ldd] with zero padding beyond the source extent.
+struct CastJob {
+  const float* src; long long lds; int rows, cols;       // source view [rows][cols]
+  __nv_bfloat16* dst; long long ldd; int out_rows;       // destination rows (>= rows, or >= cols if transposed)
+  int transpose;                                         // dst[c][r] = src[r][c]
+  int dcols;                                             // destination columns written per row (<= ldd)
+  int pad;
+};
+
+__global__ void __launch_bounds__(256) cast_jobs_kernel(const CastJob* __restrict__ jobs) {
+  const CastJob j = jobs[blockIdx.y];
+  const long long total = (long long)j.out_rows * j.dcols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / j.dcols;
+    const int c = (int)(i - r * j.dcols);
+    float v = 0.0f;
+    if (!j.transpose) {
+      if (r < j.rows && c < j.cols) v = j.src[r * j.lds + c];
+    } else {
+      if (c < j.rows && r < j.cols) v = j.src[(long long)c * j.lds + r];
+    }
+    j.dst[r * j.ldd + c] = __float2bfloat16(v);
+  }
+}
+
+// obj[t, F:F+4] = box position (batch_gqa_boxfeatures_pipeline.py:208-211) and obj16 = bf16(obj) with zero K-padding.
+__global__ void __launch_bounds__(256) obj_finish_kernel(const float* __restrict__ f, long long ldf, int D,
+                                                         float* __restrict__ obj, long long ldo, int F,
+                                                         __nv_bfloat16* __restrict__ obj16, long long ld16,
+                                                         long long rows) {
+  const long long total = rows * ld16;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / ld16;
+    const int c = (int)(i - t * ld16);
+    float v = 0.0f;
+    if (c < F) {
+      v = obj[t * ldo + c];
+    } else if (c < F + 4) {
+      const float* r = f + t * ldf + D;  // [W, H, x, y, w, h]
+      const int jj = c - F;
+      v = r[2 + jj] / fmaxf(r[jj & 1], 1.0f);
+      obj[t * ldo + c] = v;
+    }
+    obj16[i] = __float2bfloat16(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// geometry features of an ordered pair (s,o): dist, asin(dy/dist), sign(x_o-x_s), sign(y_o-y_s)
+// (batch_gqa_boxfeatures_pipeline.py:260-279)
+__device__ __forceinline__ float4 pair_geometry4(const float4 ps, const float4 po) {
+  const float dx = ps.x + ps.z / 2.0f - po.x - po.z / 2.0f;
+  const float dy = ps.y + ps.w / 2.0f - po.y - po.w / 2.0f;
+  const float dist = sqrtf(dx * dx + dy * dy);
+  float4 g;
+  g.x = dist;
+  g.y = asinf(dy / fmaxf(dist, 1e-10f));
+  const float sx = po.x - ps.x, sy = po.y - ps.y;
+  g.z = (sx > 0.0f) ? 1.0f : (sx < 0.0f ? -1.0f : 0.0f);
+  g.w = (sy > 0.0f) ? 1.0f : (sy < 0.0f ? -1.0f : 0.0f);
+  return g;
+}
+
+// Pair hidden layer (tensor-core mode): h[(s,o), :] = elu(U[s] + V[o] + Wg.geo(s,o) + b) in bf16, H = 256.
+// One block per (image, 32-object tile): the V rows of the tile live in shared memory for all subjects, warp w walks
+// the subjects s = w, w+8, ...; lane q owns hidden units 4q..4q+3 and 128+4q..; the geometry of (s, o0+lane) is
+// computed by lane `lane` and broadcast with shuffles (no barrier in the loop).  Also writes the geometry table
+// geo[pair] (float4) that the backward kernel re-uses.
+constexpr int PF_TO = 32;
+
+template <int G>  // G = H / 128 (float4 groups per lane)
+__global__ void __launch_bounds__(256) pair_hidden_fwd_tc_kernel(
+    const float* __restrict__ uv, long long lduv, const float* __restrict__ pos, long long ldpos,
+    const float* __restrict__ wg, long long ldw, const float* __restrict__ bias, __nv_bfloat16* __restrict__ hout,
+    long long ldh, float4* __restrict__ geo_out, const int32_t* __restrict__ pair_row,
+    const int32_t* __restrict__ obj_row, const int32_t* __restrict__ img_n) {
+  constexpr int H = 128 * G, H4 = H / 4;
+  extern __shared__ float4 vsm[];  // [PF_TO][H4]
+  const int b = blockIdx.y;
+  const int n = img_n[b];
+  const int o0 = blockIdx.x * PF_TO;
+  if (o0 >= n) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long t0 = obj_row[b];
+  const long long p0 = pair_row[b];
+  const int no = min(PF_TO, n - o0);
+  for (int idx = threadIdx.x; idx < no * H4; idx += 256) {
+    const int o = idx / H4, q = idx - o * H4;
+    vsm[o * H4 + q] = __ldg(reinterpret_cast<const float4*>(uv + (t0 + o0 + o) * lduv + H) + q);
+  }
+  float4 bz[G], w0[G], w1[G], w2[G], w3[G];
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    const int q = lane + 32 * i;
+    bz[i] = __ldg(reinterpret_cast<const float4*>(bias) + q);
+    const float* w = wg + (long long)(4 * q) * ldw;
+    w0[i] = make_float4(w[0], w[1], w[2], w[3]);
+    w1[i] = make_float4(w[ldw], w[ldw + 1], w[ldw + 2], w[ldw + 3]);
+    w2[i] = make_float4(w[2 * ldw], w[2 * ldw + 1], w[2 * ldw + 2], w[2 * ldw + 3]);
+    w3[i] = make_float4(w[3 * ldw], w[3 * ldw + 1], w[3 * ldw + 2], w[3 * ldw + 3]);
+  }
+  float4 po = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane < no) po = __ldg(reinterpret_cast<const float4*>(pos + (t0 + o0 + lane) * ldpos));
+  __syncthreads();
+  const int zero_cols = (int)ldh - H;
+  for (int s = warp; s < n; s += 8) {
+    const float4 ps = __ldg(reinterpret_cast<const float4*>(pos + (t0 + s) * ldpos));
+    float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < no && o0 + lane != s) gl = pair_geometry4(ps, po);
+    const long long prow = p0 + (long long)s * n + o0;
+    if (geo_out != nullptr && lane < no) geo_out[prow + lane] = gl;
+    float4 u[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      u[i] = __ldg(reinterpret_cast<const float4*>(uv + (t0 + s) * lduv) + lane + 32 * i);
+      u[i].x += bz[i].x; u[i].y += bz[i].y; u[i].z += bz[i].z; u[i].w += bz[i].w;
+    }
+    for (int oi = 0; oi < no; ++oi) {
+      float4 g;
+      g.x = __shfl_sync(0xffffffffu, gl.x, oi);
+      g.y = __shfl_sync(0xffffffffu, gl.y, oi);
+      g.z = __shfl_sync(0xffffffffu, gl.z, oi);
+      g.w = __shfl_sync(0xffffffffu, gl.w, oi);
+      __nv_bfloat16* dst = hout + (prow + oi) * ldh;
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int q = lane + 32 * i;
+        const float4 v = vsm[oi * H4 + q];
+        float a0 = u[i].x + v.x, a1 = u[i].y + v.y, a2 = u[i].z + v.z, a3 = u[i].w + v.w;
+        a0 = fmaf(w0[i].x, g.x, a0); a0 = fmaf(w0[i].y, g.y, a0); a0 = fmaf(w0[i].z, g.z, a0); a0 = fmaf(w0[i].w, g.w, a0);
+        a1 = fmaf(w1[i].x, g.x, a1); a1 = fmaf(w1[i].y, g.y, a1); a1 = fmaf(w1[i].z, g.z, a1); a1 = fmaf(w1[i].w, g.w, a1);
+        a2 = fmaf(w2[i].x, g.x, a2); a2 = fmaf(w2[i].y, g.y, a2); a2 = fmaf(w2[i].z, g.z, a2); a2 = fmaf(w2[i].w, g.w, a2);
+        a3 = fmaf(w3[i].x, g.x, a3); a3 = fmaf(w3[i].y, g.y, a3); a3 = fmaf(w3[i].z, g.z, a3); a3 = fmaf(w3[i].w, g.w, a3);
+        a0 = a0 > 0.0f ? a0 : __expf(a0) - 1.0f;
+        a1 = a1 > 0.0f ? a1 : __expf(a1) - 1.0f;
+        a2 = a2 > 0.0f ? a2 : __expf(a2) - 1.0f;
+        a3 = a3 > 0.0f ? a3 : __expf(a3) - 1.0f;
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
+        *reinterpret_cast<uint2*>(dst + 4 * q) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      }
+      for (int h = lane; h < zero_cols; h += 32) dst[H + h] = __float2bfloat16(0.0f);
+    }
+  }
+}
+
+// Backward of the pair hidden layer from bf16 dZ1 (activation derivative already applied by the dgrad epilogue).
+// One block per (image, 64 hidden units): thread (rg, lane) owns columns 2*lane, 2*lane+1 of the chunk and the objects
+// o = rg, rg+8, ...: for every subject s it loads its NI rows (s,o) (128-byte warp transactions), so
+//   dV[o][h] = sum_s dz   is thread-private (registers, written once at the end),
+//   dU[s][h] = sum_o dz   is reduced over the 8 row groups through a double-buffered shared tile (one barrier per s),
+//   dWg[h][k] = sum dz*geo_k and db[h] = sum dz stay in registers until the end (one atomic per block and column).
+// dU / dV are written as bf16 (operands of the next tensor-core GEMMs).
+template <int NI>
+__global__ void __launch_bounds__(256) pair_hidden_bwd_tc_kernel(
+    const __nv_bfloat16* __restrict__ dz, long long lddz, const float4* __restrict__ geo,
+    __nv_bfloat16* __restrict__ du_out, __nv_bfloat16* __restrict__ dv_out, long long ldo, float* __restrict__ dwg,
+    long long ldw, float* __restrict__ dbias, const int32_t* __restrict__ pair_row,
+    const int32_t* __restrict__ obj_row, const int32_t* __restrict__ img_n) {
+  __shared__ __align__(16) float red[2][8][64];
+  __shared__ __align__(16) float redw[8][4][64];
+  const int b = blockIdx.y;
+  const int n = img_n[b];
+  const long long t0 = obj_row[b];
+  const long long p0 = pair_row[b];
+  const int rg = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 64 + 2 * lane;
+  float dv[NI][2];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) dv[i][0] = dv[i][1] = 0.0f;
+  float dw[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  float dbv = 0.0f;  // threads < 64: column sum of dU
+  for (int s = 0; s < n; ++s) {
+    const long long prow = p0 + (long long)s * n;
+    float2 v[NI];
+    float4 g[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int o = rg + 8 * i;
+      v[i] = make_float2(0.f, 0.f);
+      g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (o < n && o != s) {
+        const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(dz + (prow + o) * lddz + c0);
+        v[i] = __bfloat1622float2(x);
+        g[i] = __ldg(geo + prow + o);
+      }
+    }
+    float du0 = 0.f, du1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      du0 += v[i].x; du1 += v[i].y;
+      dv[i][0] += v[i].x; dv[i][1] += v[i].y;
+      dw[0][0] = fmaf(v[i].x, g[i].x, dw[0][0]); dw[0][1] = fmaf(v[i].y, g[i].x, dw[0][1]);
+      dw[1][0] = fmaf(v[i].x, g[i].y, dw[1][0]); dw[1][1] = fmaf(v[i].y, g[i].y, dw[1][1]);
+      dw[2][0] = fmaf(v[i].x, g[i].z, dw[2][0]); dw[2][1] = fmaf(v[i].y, g[i].z, dw[2][1]);
+      dw[3][0] = fmaf(v[i].x, g[i].w, dw[3][0]); dw[3][1] = fmaf(v[i].y, g[i].w, dw[3][1]);
+    }
+    const int buf = s & 1;
+    *reinterpret_cast<float2*>(&red[buf][rg][2 * lane]) = make_float2(du0, du1);
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += red[buf][r][threadIdx.x];
+      du_out[(t0 + s) * ldo + blockIdx.x * 64 + threadIdx.x] = __float2bfloat16(t);
+      dbv += t;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int o = rg + 8 * i;
+    if (o < n) {
+      const __nv_bfloat162 x = __floats2bfloat162_rn(dv[i][0], dv[i][1]);
+      *reinterpret_cast<__nv_bfloat162*>(dv_out + (t0 + o) * ldo + c0) = x;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) *reinterpret_cast<float2*>(&redw[rg][k][2 * lane]) = make_float2(dw[k][0], dw[k][1]);
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int h = blockIdx.x * 64 + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += redw[r][k][threadIdx.x];
+      atomicAdd(dwg + (long long)h * ldw + k, t);
+    }
+    atomicAdd(dbias + h, dbv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Backward of the table layer LL = logsigmoid(H.W^T + b) in tensor-core mode (bf16 H in, bf16 dZ out) for up to
+// S table columns per image and launch (slices [j0 + first, j0 + first + S) of image b):
+//   dz_j[l]   = g_j[l] * (1 - exp(LL_j[l]))
+//   dZ[row,e] (+)= (sum_j dz_j[l] W[wrow_j, e]) * h(1-h)          (sigmoid' of the layer below, h = H[row,e])
+//   dW[wrow_j, e] += sum_l dz_j[l] h;  db[wrow_j] += sum_l dz_j[l];  dbelow[e] += sum_rows dZ[row,e]   (atomics)
+// One block per (128-row chunk, image); warp w streams rows w, w+8, ... of the chunk, lane owns the column pairs
+// 2*lane + 64*c (c < NC): every row is read and written with 128-byte warp transactions, exactly once.
+constexpr int TB_ROWS = 128;
+
+template <int S, int NC>
+__global__ void __launch_bounds__(256) table_layer_bwd_tc_kernel(
+    const float* __restrict__ g, const int32_t* __restrict__ slice_goff, const int32_t* __restrict__ slice_col,
+    const int32_t* __restrict__ slice_wrow, const int32_t* __restrict__ img_slice, int first, int accumulate,
+    const float* __restrict__ ll, const int64_t* __restrict__ blk, const int32_t* __restrict__ stride,
+    const int32_t* __restrict__ row0, const int32_t* __restrict__ img_rows, const float* __restrict__ W,
+    long long ldw, const __nv_bfloat16* __restrict__ hs, long long ldh, int E, __nv_bfloat16* __restrict__ dZ,
+    long long lddz, int out_cols, float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dbelow) {
+  __shared__ float dz_s[S][TB_ROWS];
+  __shared__ int wrow_s[S];
+  __shared__ __align__(16) float red_s[8][NC * 64];
+  const int b = blockIdx.y;
+  const int rows = img_rows[b];
+  const int c = blockIdx.x * TB_ROWS;
+  if (c >= rows) return;
+  const int cn = min(TB_ROWS, rows - c);
+  const long long r0 = (long long)row0[b] + c;
+  const int j0 = img_slice[b] + first;
+  const int Sb = max(0, min(img_slice[b + 1] - j0, S));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (Sb == 0) {
+    if (!accumulate) {  // rows of images without (more) slices are zero
+      for (int l = warp; l < cn; l += 8) {
+        __nv_bfloat16* drow = dZ + (r0 + l) * lddz;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          const int e = 2 * lane + 64 * k;
+          if (e < out_cols) *reinterpret_cast<uint32_t*>(drow + e) = 0u;
+        }
+      }
+    }
+    return;
+  }
+  const int st = stride[b];
+  for (int idx = threadIdx.x; idx < S * TB_ROWS; idx += 256) {
+    const int j = idx / TB_ROWS, l = idx - j * TB_ROWS;
+    float v = 0.0f;
+    if (j < Sb && l < cn) {
+      const float gv = g[slice_goff[j0 + j] + c + l];
+      if (gv != 0.0f) v = gv * (1.0f - __expf(ll[blk[b] + (long long)slice_col[j0 + j] * st + c + l]));
+    }
+    dz_s[j][l] = v;
+  }
+  if (threadIdx.x < S) wrow_s[threadIdx.x] = threadIdx.x < Sb ? slice_wrow[j0 + threadIdx.x] : 0;
+  __syncthreads();
+  if (warp < Sb) {  // db[wrow_j] += sum_l dz_j[l]
+    float t = 0.f;
+    for (int l = lane; l < cn; l += 32) t += dz_s[warp][l];
+    t = warp_sum(t);
+    if (lane == 0 && t != 0.0f) atomicAdd(db + wrow_s[warp], t);
+  }
+  float2 wj[S][NC], dwj[S][NC], colsum[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int e = 2 * lane + 64 * k;
+    colsum[k] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      dwj[j][k] = make_float2(0.f, 0.f);
+      wj[j][k] = (j < Sb && e < E) ? *reinterpret_cast<const float2*>(W + (long long)wrow_s[j] * ldw + e)
+                                   : make_float2(0.f, 0.f);
+    }
+  }
+  for (int l = warp; l < cn; l += 8) {
+    const __nv_bfloat16* hrow = hs + (r0 + l) * ldh;
+    __nv_bfloat16* drow = dZ + (r0 + l) * lddz;
+    float2 h[NC], prev[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int e = 2 * lane + 64 * k;
+      h[k] = make_float2(0.f, 0.f);
+      prev[k] = make_float2(0.f, 0.f);
+      if (e < E) h[k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hrow + e));
+      if (accumulate && e < E) prev[k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(drow + e));
+    }
+    float dzl[S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) dzl[j] = dz_s[j][l];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int e = 2 * lane + 64 * k;
+      float ox = 0.f, oy = 0.f;
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        ox = fmaf(dzl[j], wj[j][k].x, ox);
+        oy = fmaf(dzl[j], wj[j][k].y, oy);
+        dwj[j][k].x = fmaf(dzl[j], h[k].x, dwj[j][k].x);
+        dwj[j][k].y = fmaf(dzl[j], h[k].y, dwj[j][k].y);
+      }
+      ox *= h[k].x * (1.0f - h[k].x);
+      oy *= h[k].y * (1.0f - h[k].y);
+      colsum[k].x += ox;
+      colsum[k].y += oy;
+      if (e < out_cols) {  // columns E .. out_cols are the zero K-padding of the next GEMM (h = 0 there)
+        const __nv_bfloat162 o2 = __floats2bfloat162_rn(ox + prev[k].x, oy + prev[k].y);
+        *reinterpret_cast<__nv_bfloat162*>(drow + e) = o2;
+      }
+    }
+  }
+  // block reductions: dbelow (column sums of dZ) and dW rows, then one atomic per block and column
+#pragma unroll
+  for (int k = 0; k < NC; ++k) *reinterpret_cast<float2*>(&red_s[warp][64 * k + 2 * lane]) = colsum[k];
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red_s[w][e];
+    if (dbelow != nullptr && t != 0.0f) atomicAdd(dbelow + e, t);
+  }
+#pragma unroll
+  for (int j = 0; j < S; ++j) {
+    if (j >= Sb) break;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NC; ++k) *reinterpret_cast<float2*>(&red_s[warp][64 * k + 2 * lane]) = dwj[j][k];
+    __syncthreads();
+    for (int e = threadIdx.x; e < E; e += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red_s[w][e];
+      if (t != 0.0f) atomicAdd(dW + (long long)wrow_s[j] * ldw + e, t);
+    }
+  }
+}
+
+}  // namespace dfol
+
+using namespace dfol;
+
+extern "C" int dfol_cast_jobs(const void* jobs, int job_num, int64_t max_elements, void* stream) {
+  DFOL_REQUIRE(jobs && job_num > 0 && max_elements > 0, "dfol_cast_jobs: bad arguments");
+  long long bx = (max_elements + 255) / 256;
+  if (bx > 1024) bx = 1024;
+  dim3 grid((unsigned)bx, job_num);
+  cast_jobs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const CastJob*>(jobs));
+  return finish_launch("dfol_cast_jobs");
+}
+
+extern "C" int dfol_cast_job_size(void) { return (int)sizeof(CastJob); }
+
+extern "C" int dfol_obj_finish(const float* features, int64_t ldf, int feature_dim, float* obj, int64_t ldo, int F,
+                               void* obj16, int64_t ld16, int64_t rows, void* stream) {
+  DFOL_REQUIRE(features && obj && obj16 && ld16 >= F + 4 && ldo >= F + 4, "dfol_obj_finish: bad arguments");
+  if (rows == 0) return 0;
+  long long bx = (rows * ld16 + 255) / 256;
+  if (bx > 148 * 16) bx = 148 * 16;
+  obj_finish_kernel<<<(unsigned)bx, 256, 0, (cudaStream_t)stream>>>(features, ldf, feature_dim, obj, ldo, F,
+                                                                    reinterpret_cast<__nv_bfloat16*>(obj16), ld16, rows);
+  return finish_launch("dfol_obj_finish");
+}
+
+extern "C" int dfol_pair_hidden_fwd_tc(const float* uv, int64_t lduv, const float* obj_pos, int64_t ldpos,
+                                       const float* wg, int64_t ldw, const float* bias, void* h_out, int64_t ldh, int H,
+                                       void* geo_out, const int32_t* pair_row, const int32_t* obj_row,
+                                       const int32_t* img_n, int image_num, int max_n, void* stream) {
+  DFOL_REQUIRE(uv && obj_pos && wg && bias && h_out && pair_row && obj_row && img_n,
+               "dfol_pair_hidden_fwd_tc: null pointer");
+  if (image_num == 0) return 0;
+  DFOL_REQUIRE(H == 128 || H == 256 || H == 384 || H == 512, "dfol_pair_hidden_fwd_tc: H must be 128/256/384/512");
+  DFOL_REQUIRE((lduv % 4) == 0 && (ldh % 4) == 0 && ldh >= H && (ldpos % 4) == 0 &&
+                   (reinterpret_cast<uintptr_t>(uv) % 16) == 0 && (reinterpret_cast<uintptr_t>(h_out) % 16) == 0 &&
+                   (reinterpret_cast<uintptr_t>(obj_pos) % 16) == 0 && (reinterpret_cast<uintptr_t>(bias) % 16) == 0,
+               "dfol_pair_hidden_fwd_tc: strides must be multiples of 4 and buffers 16-byte aligned");
+  DFOL_REQUIRE(max_n >= 1, "dfol_pair_hidden_fwd_tc: empty batch");
+  dim3 grid((max_n + PF_TO - 1) / PF_TO, image_num);
+  const size_t smem = (size_t)PF_TO * (H / 4) * sizeof(float4);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(h_out);
+  float4* geo = reinterpret_cast<float4*>(geo_out);
+#define DFOL_PF_LAUNCH(G)                                                                                        \
+  {                                                                                                              \
+    auto kern = pair_hidden_fwd_tc_kernel<G>;                                                                    \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
+    kern<<<grid, 256, smem, st>>>(uv, lduv, obj_pos, ldpos, wg, ldw, bias, out, ldh, geo, pair_row, obj_row,    \
+                                  img_n);                                                                        \
+  }
+  switch (H / 128) {
+    case 1: DFOL_PF_LAUNCH(1) break;
+    case 2: DFOL_PF_LAUNCH(2) break;
+    case 3: DFOL_PF_LAUNCH(3) break;
+    default: DFOL_PF_LAUNCH(4) break;
+  }
+#undef DFOL_PF_LAUNCH
+  return finish_launch("dfol_pair_hidden_fwd_tc");
+}
+
+extern "C" int dfol_pair_hidden_bwd_tc(const void* dz, int64_t lddz, const void* geo, void* du_out, void* dv_out,
+                                       int64_t ldo, float* dwg, int64_t ldw, float* dbias, int H,
+                                       const int32_t* pair_row, const int32_t* obj_row, const int32_t* img_n,
+                                       int image_num, int max_n, void* stream) {
+  DFOL_REQUIRE(dz && geo && du_out && dv_out && dwg && dbias && pair_row && obj_row && img_n,
+               "dfol_pair_hidden_bwd_tc: null pointer");
+  if (image_num == 0) return 0;
+  DFOL_REQUIRE((H % 64) == 0 && (lddz % 2) == 0 && (ldo % 2) == 0 && max_n >= 1 && max_n <= 128,
+               "dfol_pair_hidden_bwd_tc: H %% 64 == 0, even strides, 1 <= max_n <= 128");
+  dim3 grid(H / 64, image_num);
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* dzp = reinterpret_cast<const __nv_bfloat16*>(dz);
+  const float4* gp = reinterpret_cast<const float4*>(geo);
+  __nv_bfloat16* dup = reinterpret_cast<__nv_bfloat16*>(du_out);
+  __nv_bfloat16* dvp = reinterpret_cast<__nv_bfloat16*>(dv_out);
+#define DFOL_PB_LAUNCH(NI)                                                                                        \
+  pair_hidden_bwd_tc_kernel<NI><<<grid, 256, 0, st>>>(dzp, lddz, gp, dup, dvp, ldo, dwg, ldw, dbias, pair_row,    \
+                                                      obj_row, img_n)
+  const int ni = (max_n + 7) / 8;
+  if (ni <= 4) DFOL_PB_LAUNCH(4);
+  else if (ni <= 6) DFOL_PB_LAUNCH(6);
+  else if (ni <= 8) DFOL_PB_LAUNCH(8);
+  else if (ni <= 13) DFOL_PB_LAUNCH(13);
+  else DFOL_PB_LAUNCH(16);
+#undef DFOL_PB_LAUNCH
+  return finish_launch("dfol_pair_hidden_bwd_tc");
+}
+
+extern "C" int dfol_table_layer_bwd_tc(const float* g, const int32_t* slice_goff, const int32_t* slice_col,
+                                       const int32_t* slice_wrow, const int32_t* img_slice, int image_num,
+                                       int max_rows, int max_slices, const float* ll, const int64_t* blk,
+                                       const int32_t* stride, const int32_t* row0, const int32_t* img_rows,
+                                       const float* W, int64_t ldw, const void* h_saved, int64_t ldh, int E, void* dZ,
+                                       int64_t lddz, int out_cols, float* dW, float* db, float* dbelow, void* stream) {
+  DFOL_REQUIRE(g && slice_goff && slice_col && slice_wrow && img_slice && ll && blk && stride && row0 && img_rows &&
+                   W && h_saved && dZ && dW && db,
+               "dfol_table_layer_bwd_tc: null pointer");
+  if (image_num == 0 || max_rows == 0) return 0;
+  DFOL_REQUIRE(out_cols >= E && out_cols <= lddz && out_cols <= 320 && (E % 2) == 0 && (out_cols % 2) == 0 &&
+                   (ldw % 2) == 0 && (ldh % 2) == 0 && (lddz % 2) == 0,
+               "dfol_table_layer_bwd_tc: E <= out_cols <= min(lddz, 320), even sizes and strides");
+  dim3 grid((max_rows + TB_ROWS - 1) / TB_ROWS, image_num);
+  DFOL_REQUIRE(grid.y <= 65535, "dfol_table_layer_bwd_tc: too many images");
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(h_saved);
+  __nv_bfloat16* dzp = reinterpret_cast<__nv_bfloat16*>(dZ);
+  // slices are consumed in groups of at most 4 per pass; later passes accumulate into dZ
+  int first = 0;
+  do {
+    const int left = max_slices - first;
+    const int acc = first > 0 ? 1 : 0;
+#define DFOL_TB_LAUNCH(S)                                                                                           \
+  table_layer_bwd_tc_kernel<S, 5><<<grid, 256, 0, st>>>(g, slice_goff, slice_col, slice_wrow, img_slice, first, acc, \
+                                                        ll, blk, stride, row0, img_rows, W, ldw, hp, ldh, E, dzp,    \
+                                                        lddz, out_cols, dW, db, dbelow)
+    if (left <= 1) DFOL_TB_LAUNCH(1);
+    else if (left == 2) DFOL_TB_LAUNCH(2);
+    else DFOL_TB_LAUNCH(4);
+#undef DFOL_TB_LAUNCH
+    first += 4;
+  } while (first < max_slices);
+  return finish_launch("dfol_table_layer_bwd_tc");
+}

@@ -131,6 +131,8 @@ class ReasoningEngine(object):
         self.gemm_mode = gemm_mode
         if gemm_mode not in ('fp32', 'bf16'):
             raise ValueError('gemm_mode must be fp32 or bf16')
+        from .engine_tc import TensorCorePath
+        self.tc = TensorCorePath(self)
 
     def rel_index(self, device):
         if self._rel_index is None or self._rel_index.device != device:
@@ -139,113 +141,10 @@ class ReasoningEngine(object):
 
     # ------------------------------------------------------------------------------------------ forward
 
-    # ------------------------------------------------------------------------------------------ bf16 forward
-
-    @staticmethod
-    def _cast16(src, ld, st, rows=None):
-        """bf16 copy of a 2-D fp32 view with rows padded to ``ld`` elements (zeros)."""
-        r, c = src.shape
-        out = torch.empty(r, ld, device=src.device, dtype=torch.bfloat16)
-        call('dfol_cast_bf16', ptr(src), src.stride(0), ptr(out), ld, r, c, st)
-        return out
-
-    @staticmethod
-    def _tc(A16, B16, C, N, Kp, bias, act, st, table=None):
-        """C = epilogue(A16[:, :Kp] @ B16[:N, :Kp]^T) on the tensor cores (dfol_gemm_bf16_tc)."""
-        M = A16.shape[0]
-        if table is None:
-            out_bf16 = int(C.dtype == torch.bfloat16)
-            ldc, store, maps, diag = C.stride(0), 0, (None, None, None, None, None), 0.0
-        else:
-            out_bf16, ldc, store = 0, 0, 1
-            maps = (ptr(table['row_img']), ptr(table['img_row']), ptr(table['img_blk']), ptr(table['img_stride']),
-                    ptr(table.get('img_n')))
-            diag = table.get('diag', DEFAULT_LL)
-        if capi.trace is not None:
-            capi.next_meta = {'tag': 'gemm_bf16_tc[%dx%dx%d]%s' % (M, N, Kp, ' table' if store else ''),
-                              'flops': 2.0 * M * N * Kp}
-        call('dfol_gemm_bf16_tc', ptr(A16), A16.stride(0), ptr(B16), B16.stride(0), ptr(C), ldc, ptr(bias), M, N, Kp,
-             act, out_bf16, store, maps[0], maps[1], maps[2], maps[3], maps[4], diag, st)
-
-    def build_scene_bf16(self, features, layout):
-        """Same tables as build_scene with every dense contraction on tcgen05 tensor cores (bf16 operands, fp32
-        accumulation in TMEM).  Forward only in this round: activations are kept in bf16."""
-        capi.lib()
-        w = self.w
-        dev = features.device
-        st = capi.stream_ptr(dev)
-        T, width = features.shape
-        D = width - 6
-        F = w.feat.weight.shape[0]
-        ldo = F + 4
-        assert len(w.attr) == 2 and len(w.rel) == 2, 'bf16 path: one hidden layer per network (reference configs)'
-        H, E = w.rel[0].weight.shape[0], w.rel[1].weight.shape[0]
-        Ha = w.attr[0].weight.shape[0]
-        sc = Scene()
-        sc.layout = layout
-        sc.features = features
-        Dp, Op, Hp, Hap, Ep = (_roundup(v, 64) for v in (D, ldo, H, Ha, E))
-
-        # featurizer (fp32 obj: the pair kernel and the position columns need it), then its bf16 copy
-        x16 = self._cast16(features[:, :D], Dp, st)
-        wf16 = self._cast16(w.feat.weight, Dp, st)
-        obj = torch.empty(T, ldo, device=dev, dtype=torch.float32)
-        self._tc(x16, wf16, obj, F, Dp, w.feat.bias, K.ACT_SIGMOID, st)
-        call('dfol_box_position', ptr(features), features.stride(0), D, ptr(obj), ldo, F, T, st)
-        obj16 = self._cast16(obj, Op, st)
-        sc.obj = obj
-
-        # attribute chain
-        wa1 = self._cast16(w.attr[0].weight, Op, st)
-        wa2 = self._cast16(w.attr[1].weight, Hap, st)
-        we16 = self._cast16(w.emb.weight, Ep, st)
-        # object-sized activations are kept in fp32 (they are tiny and the fp32 backward kernels consume them);
-        # the tensor-core operands are bf16 copies
-        h1a32 = torch.empty(T, Ha, device=dev, dtype=torch.float32)
-        self._tc(obj16, wa1, h1a32, Ha, Op, w.attr[0].bias, K.ACT_ELU, st)
-        h1a = self._cast16(h1a32, Hap, st)
-        h2a32 = torch.empty(T, E, device=dev, dtype=torch.float32)
-        self._tc(h1a, wa2, h2a32, E, Hap, w.attr[1].bias, K.ACT_SIGMOID, st)
-        h2a = self._cast16(h2a32, Ep, st)
-        attr_ll = torch.empty(layout.attr_size, device=dev, dtype=torch.float32)
-        obj_table = {'row_img': layout.obj_img, 'img_row': layout.obj_row, 'img_blk': layout.attr_blk,
-                     'img_stride': layout.attr_stride}
-        self._tc(h2a, we16, attr_ll, w.emb.weight.shape[0], Ep, w.emb.bias, K.ACT_LOGSIGMOID, st, table=obj_table)
-        sc.attr_ll = attr_ll
-        sc.attr_h = [h1a32, h2a32]
-
-        # relation chain: U|V in one GEMM (N = 2H), pair hidden layer in bf16, two tensor-core layers over pairs
-        first = w.rel[0]
-        wuv = torch.empty(2 * H, Op, device=dev, dtype=torch.bfloat16)
-        call('dfol_cast_bf16', ptr(first.weight[:, :ldo]), first.weight.stride(0), ptr(wuv), Op, H, ldo, st)
-        call('dfol_cast_bf16', ptr(first.weight[:, ldo:2 * ldo]), first.weight.stride(0), ptr(wuv[H:]), Op, H, ldo, st)
-        uv = torch.empty(T, 2 * H, device=dev, dtype=torch.float32)
-        self._tc(obj16, wuv, uv, 2 * H, Op, None, K.ACT_NONE, st)
-        wg = first.weight[:, 2 * ldo:]
-        h1r = torch.empty(layout.P, Hp, device=dev, dtype=torch.bfloat16)
-        call('dfol_pair_hidden_fwd', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo, ptr(wg), first.weight.stride(0),
-             ptr(first.bias), ptr(h1r), Hp, H, K.ACT_ELU, 1, ptr(layout.pair_row), ptr(layout.obj_row),
-             ptr(layout.img_n), layout.B, layout.max_n, st)
-        wr2 = self._cast16(w.rel[1].weight, Hp, st)
-        h2r = torch.empty(layout.P, Ep, device=dev, dtype=torch.bfloat16)
-        self._tc(h1r, wr2, h2r, E, Hp, w.rel[1].bias, K.ACT_SIGMOID, st)
-        ridx = self.rel_index(dev)
-        sc.w_rel = w.emb.weight.detach().index_select(0, ridx).contiguous()
-        sc.b_rel = w.emb.bias.detach().index_select(0, ridx).contiguous()
-        wrel16 = self._cast16(sc.w_rel, Ep, st)
-        rel_ll = torch.empty(layout.rel_size, device=dev, dtype=torch.float32)
-        pair_table = {'row_img': layout.pair_img, 'img_row': layout.pair_row, 'img_blk': layout.rel_blk,
-                      'img_stride': layout.rel_stride, 'img_n': layout.img_n, 'diag': DEFAULT_LL}
-        self._tc(h2r, wrel16, rel_ll, sc.w_rel.shape[0], Ep, sc.b_rel, K.ACT_LOGSIGMOID, st, table=pair_table)
-        sc.rel_ll = rel_ll
-        sc.rel_h = [h1r, h2r]
-        sc.uv = uv
-        return sc
-
     def build_scene(self, features, layout, keep_for_backward=True):
         """Featurizer + attribute / relation tables (K1-K6 of SURVEY.md §2.1)."""
         if self.gemm_mode == 'bf16':
-            return self.build_scene_bf16(features, layout)
+            return self.tc.build_scene(features, layout, keep_for_backward)
         capi.lib()
         w = self.w
         dev = features.device
@@ -363,15 +262,13 @@ class ReasoningEngine(object):
             return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
         pad = arr if arr.shape[0] else np.zeros((1, 3), dtype=np.int64)
         out = {'goff': dev(pad[:, 2].astype(np.int32)), 'col': dev(pad[:, 1].astype(np.int32)),
-               'img': dev(pad[:, 0].astype(np.int32)), 'img_slice': dev(img_slice), 'count': int(arr.shape[0]),
+               'wrow': dev(pad[:, 1].astype(np.int32)), 'img': dev(pad[:, 0].astype(np.int32)), 'img_slice': dev(img_slice), 'count': int(arr.shape[0]),
                'max_per_image': int(counts.max()) if counts.size else 0}
         cache[key] = out
         return out
 
-    def backward(self, cp, scene, tape, d_lp, grads):
-        """d loss / d parameters given d loss / d lp.  ``grads``: dict param tensor id -> fp32 grad tensor of the
-        parameter's shape (accumulated into; callers zero them)."""
-        w = self.w
+    def program_backward(self, cp, scene, tape, d_lp):
+        """Backward interpreter: compact gradient slices w.r.t. the raw attribute / relation table entries."""
         lay = scene.layout
         dev = scene.attr_ll.device
         st = capi.stream_ptr(dev)
@@ -379,9 +276,23 @@ class ReasoningEngine(object):
         stride = _roundup(lay.max_n, 4)
         g_attr = torch.zeros(cp.g_attr_size, device=dev, dtype=torch.float32)
         g_rel = torch.zeros(cp.g_rel_size, device=dev, dtype=torch.float32)
+        if capi.trace is not None:
+            capi.next_meta = {'tag': 'program_bwd', 'bytes': 2.0 * cp.alg_bytes}
         call('dfol_program_bwd', ptr(d['instr']), ptr(d['q_instr']), ptr(d['opts']), cp.question_num,
              ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride), ptr(scene.rel_ll), ptr(lay.rel_blk),
              ptr(lay.rel_stride), ptr(lay.img_n), ptr(d_lp), ptr(tape), stride, ptr(g_attr), ptr(g_rel), st)
+        return g_attr, g_rel
+
+    def backward(self, cp, scene, tape, d_lp, grads):
+        """d loss / d parameters given d loss / d lp.  ``grads``: dict param tensor id -> fp32 grad tensor of the
+        parameter's shape (accumulated into; callers zero them)."""
+        if self.gemm_mode == 'bf16':
+            return self.tc.backward(cp, scene, tape, d_lp, grads)
+        w = self.w
+        lay = scene.layout
+        dev = scene.attr_ll.device
+        st = capi.stream_ptr(dev)
+        g_attr, g_rel = self.program_backward(cp, scene, tape, d_lp)
 
         def G(p):
             return grads[id(p)]
@@ -419,17 +330,14 @@ class ReasoningEngine(object):
             first = w.rel[0]
             H = first.weight.shape[0]
             gw1 = G(first.weight)
-            if self.gemm_mode == 'bf16':
-                duv = self._rel_backward_bf16(scene, d_h, grads, st)
-            else:
-                # dense layers above the pair hidden layer
-                d_h1 = self._mlp_backward(w.rel[1:], scene.rel_h, d_h, None, grads, st, first_layer_input_grad=False,
-                                          d_out_is_dz=is_dz and len(w.rel) > 1)
-                duv = torch.zeros(T, 2 * H, device=dev, dtype=torch.float32)
-                act1 = K.ACT_ELU if len(w.rel) > 1 else K.ACT_SIGMOID
-                call('dfol_pair_hidden_bwd', ptr(d_h1), d_h1.stride(0), ptr(scene.rel_h[0]), scene.rel_h[0].stride(0),
-                     ptr(obj[:, F:]), ldo, ptr(duv), duv.stride(0), ptr(gw1[:, 2 * ldo:]), gw1.stride(0),
-                     ptr(G(first.bias)), H, act1, ptr(lay.pair_row), ptr(lay.obj_row), ptr(lay.img_n), lay.B, st)
+            # dense layers above the pair hidden layer
+            d_h1 = self._mlp_backward(w.rel[1:], scene.rel_h, d_h, None, grads, st, first_layer_input_grad=False,
+                                      d_out_is_dz=is_dz and len(w.rel) > 1)
+            duv = torch.zeros(T, 2 * H, device=dev, dtype=torch.float32)
+            act1 = K.ACT_ELU if len(w.rel) > 1 else K.ACT_SIGMOID
+            call('dfol_pair_hidden_bwd', ptr(d_h1), d_h1.stride(0), ptr(scene.rel_h[0]), scene.rel_h[0].stride(0),
+                 ptr(obj[:, F:]), ldo, ptr(duv), duv.stride(0), ptr(gw1[:, 2 * ldo:]), gw1.stride(0),
+                 ptr(G(first.bias)), H, act1, ptr(lay.pair_row), ptr(lay.obj_row), ptr(lay.img_n), lay.B, st)
             sk = _split_for(T)
             gemm_f32(duv[:, :H].t(), obj, gw1[:, :ldo], accumulate=(sk == 1), split_k=sk, stream=st)
             gemm_f32(duv[:, H:].t(), obj, gw1[:, ldo:2 * ldo], accumulate=(sk == 1), split_k=sk, stream=st)
@@ -443,39 +351,6 @@ class ReasoningEngine(object):
         sk = _split_for(T)
         gemm_f32(d_obj[:, :F].t(), scene.features[:, :D], G(w.feat.weight), accumulate=(sk == 1), split_k=sk, stream=st)
 
-    def _rel_backward_bf16(self, scene, dz2, grads, st):
-        """Relation chain backward on the tensor cores: dz2 = d loss / d (layer-2 pre-activation), bf16 (P, Ep).
-
-        db2 = colsum(dz2); dW2 += dz2^T . h1 (MN-major tcgen05 wgrad, split-K); dz1 = (dz2 . W2) * elu'(h1) (tcgen05
-        dgrad with the derivative in the epilogue); then the pair-hidden reduction to dU|dV, dWg, db1."""
-        w = self.w
-        lay = scene.layout
-        dev = dz2.device
-        first, second = w.rel[0], w.rel[1]
-        H, E = first.weight.shape[0], second.weight.shape[0]
-        h1 = scene.rel_h[0]
-        P, Hp = h1.shape
-        Ep = dz2.shape[1]
-        F = w.feat.weight.shape[0]
-        ldo = F + 4
-        call('dfol_colsum_bf16', ptr(dz2), Ep, P, E, ptr(grads[id(second.bias)]), st)
-        gw2 = grads[id(second.weight)]
-        if capi.trace is not None:
-            capi.next_meta = {'tag': 'gemm_bf16_tc_wgrad[%dx%dx%d]' % (E, H, P), 'flops': 2.0 * E * H * P}
-        call('dfol_gemm_bf16_tc_wgrad', ptr(dz2), Ep, ptr(h1), Hp, ptr(gw2), gw2.stride(0), E, H, P, st)
-        w2t = self._cast16(second.weight.detach().t().contiguous(), Ep, st)      # (H, Ep): B operand of the dgrad
-        dz1 = torch.empty(P, Hp, device=dev, dtype=torch.bfloat16)
-        if capi.trace is not None:
-            capi.next_meta = {'tag': 'gemm_bf16_tc_dgrad[%dx%dx%d]' % (P, H, Ep), 'flops': 2.0 * P * H * Ep}
-        call('dfol_gemm_bf16_tc_dgrad', ptr(dz2), Ep, ptr(w2t), Ep, ptr(dz1), Hp, P, H, Ep, ptr(h1), Hp,
-             K.MUL_ELU_GRAD, st)
-        duv = torch.empty(lay.T, 2 * H, device=dev, dtype=torch.float32)
-        gw1 = grads[id(first.weight)]
-        call('dfol_pair_hidden_bwd_bf16', ptr(dz1), Hp, ptr(scene.obj[:, F:]), ldo, ptr(duv), duv.stride(0),
-             ptr(gw1[:, 2 * ldo:]), gw1.stride(0), ptr(grads[id(first.bias)]), H, ptr(lay.pair_row), ptr(lay.obj_row),
-             ptr(lay.img_n), lay.B, lay.max_n, st)
-        return duv
-
     def _table_backward(self, g, tabs, ll, blk, stride, row0, img_rows, max_rows, rows_total, W, dW, db, h_last,
                         fuse_act, st):
         """Backward of a table layer LL = logsigmoid(h_last W^T + b) from the compact program gradient slices.
@@ -487,16 +362,6 @@ class ReasoningEngine(object):
         E = W.shape[1]
         if tabs['count'] == 0:
             return torch.zeros(rows_total, E, device=dev, dtype=torch.float32), False
-        if h_last.dtype == torch.bfloat16:
-            if tabs['max_per_image'] > 8:
-                raise NotImplementedError('bf16 backward: more than 8 relation columns per image')
-            cols = h_last.shape[1]  # padded width (zero K-padding of the next tensor-core GEMM)
-            d = torch.empty(rows_total, cols, device=dev, dtype=torch.bfloat16)
-            call('dfol_table_layer_bwd_fused', ptr(g), ptr(tabs['goff']), ptr(tabs['col']), ptr(tabs['col']),
-                 ptr(tabs['img_slice']), len(tabs['img_slice']) - 1, max_rows, ptr(ll), ptr(blk), ptr(stride),
-                 ptr(row0), ptr(img_rows), ptr(W), W.stride(0), ptr(h_last), h_last.stride(0), E, fuse_act, ptr(d),
-                 d.stride(0), cols, 1, ptr(dW), ptr(db), st)
-            return d, True
         if tabs['max_per_image'] <= 8:
             d = torch.empty(rows_total, E, device=dev, dtype=torch.float32)
             call('dfol_table_layer_bwd_fused', ptr(g), ptr(tabs['goff']), ptr(tabs['col']), ptr(tabs['col']),

@@ -1,0 +1,303 @@
+"""Tensor-core (bf16 operand, fp32 accumulate) scene build and backward of the reasoning path.
+
+Every dense contraction of the visual oracle -- forward, dgrad and wgrad -- runs on tcgen05 (dfol_gemm_bf16_tc*),
+the pair hidden layer and the table-layer backward run as single-pass HBM-bound kernels (csrc/tc_support.cu).
+Reference being replaced: featurize_scene (nsvqa/data/batch_gqa_boxfeatures_pipeline.py:199-281),
+ClassifierOracle.compute_all_log_likelihood_2 (nsvqa/nn/vision/classifier_oracle.py:145-156) and their autograd.
+
+Weights stay fp32 (master copy, optimiser state); their bf16 operand copies -- plain and transposed, K padded to 64
+-- are refreshed by ONE batched cast launch per step (dfol_cast_jobs).
+"""
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import K, call, ptr
+
+DEFAULT_LL = -30.0
+
+_JOB_DTYPE = np.dtype([('src', np.uint64), ('lds', np.int64), ('rows', np.int32), ('cols', np.int32),
+                       ('dst', np.uint64), ('ldd', np.int64), ('out_rows', np.int32), ('transpose', np.int32),
+                       ('dcols', np.int32), ('pad', np.int32)], align=True)
+
+
+def _roundup(x, m):
+    return (x + m - 1) // m * m
+
+
+class _Operands(object):
+    """bf16 operand copies of the 12 parameter tensors + the device job table that refreshes them."""
+
+    def __init__(self, w, device):
+        assert capi.lib().dfol_cast_job_size() == _JOB_DTYPE.itemsize
+        feat, a0, a1, r0, r1, emb = w.feat, w.attr[0], w.attr[1], w.rel[0], w.rel[1], w.emb
+        F, D = feat.weight.shape
+        ldo = F + 4
+        Ha, H, E, C = a0.weight.shape[0], r0.weight.shape[0], r1.weight.shape[0], emb.weight.shape[0]
+        assert a1.weight.shape[0] == E and emb.weight.shape[1] == E and r0.weight.shape[1] == 2 * ldo + 4
+        self.dims = dict(F=F, D=D, ldo=ldo, Ha=Ha, H=H, E=E, C=C)
+        Dp, Op, Hp, Hap, Ep = (_roundup(v, 64) for v in (D, ldo, H, Ha, E))
+        Kc = Hap + 2 * Hp
+        self.pad = dict(Dp=Dp, Op=Op, Hp=Hp, Hap=Hap, Ep=Ep, Kc=Kc)
+
+        def buf(rows, cols):
+            return torch.zeros(rows, cols, device=device, dtype=torch.bfloat16)
+
+        self.wf = buf(F, Dp)
+        self.wa1 = buf(Ha, Op)
+        self.wa2 = buf(E, Hap)
+        self.we = buf(C, Ep)
+        self.wuv = buf(2 * H, Op)
+        self.wr2 = buf(E, Hp)
+        self.wa2t = buf(Ha, Ep)     # dgrad operand of attribute layer 2: [in, out]
+        self.wr2t = buf(H, Ep)      # dgrad operand of relation layer 2
+        self.wcat_t = buf(F, Kc)    # dgrad operand of the three first layers that read obj: [F, Ha | H | H]
+        jobs = []
+
+        def job(src, rows, cols, dst, out_rows, dcols, transpose=0):
+            assert src.stride(1) == 1 and dst.stride(1) == 1
+            jobs.append((src.data_ptr(), src.stride(0), rows, cols, dst.data_ptr(), dst.stride(0), out_rows,
+                         transpose, dcols, 0))
+
+        fwd = [(feat.weight, self.wf), (a0.weight, self.wa1), (a1.weight, self.wa2), (emb.weight, self.we),
+               (r1.weight, self.wr2)]
+        for src, dst in fwd:
+            job(src, src.shape[0], src.shape[1], dst, dst.shape[0], dst.shape[1])
+        job(r0.weight[:, :ldo], H, ldo, self.wuv[:H], H, Op)
+        job(r0.weight[:, ldo:2 * ldo], H, ldo, self.wuv[H:], H, Op)
+        self.fwd_jobs = len(jobs)
+        job(a1.weight, E, Ha, self.wa2t, Ha, Ep, 1)
+        job(r1.weight, E, H, self.wr2t, H, Ep, 1)
+        job(a0.weight[:, :F], Ha, F, self.wcat_t[:, :Hap], F, Hap, 1)
+        job(r0.weight[:, :F], H, F, self.wcat_t[:, Hap:Hap + Hp], F, Hp, 1)
+        job(r0.weight[:, ldo:ldo + F], H, F, self.wcat_t[:, Hap + Hp:], F, Hp, 1)
+        arr = np.array(jobs, dtype=_JOB_DTYPE)
+        self.max_elems = int(max(int(j[6]) * int(j[8]) for j in jobs))
+        self.jobs = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+        self.n_jobs = len(jobs)
+        self.key = tuple(p.data_ptr() for p in w.parameters())
+
+    def refresh(self, st, training):
+        n = self.n_jobs if training else self.fwd_jobs
+        call('dfol_cast_jobs', ptr(self.jobs), n, self.max_elems, st)
+
+
+class TensorCorePath(object):
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.w = engine.w
+        self._ops = None
+
+    def operands(self, device):
+        key = tuple(p.data_ptr() for p in self.w.parameters())
+        if self._ops is None or self._ops.key != key:
+            w = self.w
+            assert len(w.attr) == 2 and len(w.rel) == 2, 'bf16 path: one hidden layer per network (reference configs)'
+            self._ops = _Operands(w, device)
+        return self._ops
+
+    @staticmethod
+    def _tc(A16, B16, C, N, Kp, bias, act, st, table=None):
+        """C = epilogue(A16[:, :Kp] @ B16[:N, :Kp]^T) on the tensor cores (dfol_gemm_bf16_tc)."""
+        M = A16.shape[0]
+        if table is None:
+            out_bf16 = int(C.dtype == torch.bfloat16)
+            ldc, store, maps, diag = C.stride(0), 0, (None, None, None, None, None), 0.0
+        else:
+            out_bf16, ldc, store = 0, 0, 1
+            maps = (ptr(table['row_img']), ptr(table['img_row']), ptr(table['img_blk']), ptr(table['img_stride']),
+                    ptr(table.get('img_n')))
+            diag = table.get('diag', DEFAULT_LL)
+        if capi.trace is not None:
+            capi.next_meta = {'tag': 'gemm_bf16_tc[%dx%dx%d]%s' % (M, N, Kp, ' table' if store else ''),
+                              'flops': 2.0 * M * N * Kp}
+        call('dfol_gemm_bf16_tc', ptr(A16), A16.stride(0), ptr(B16), B16.stride(0), ptr(C), ldc, ptr(bias), M, N, Kp,
+             act, out_bf16, store, maps[0], maps[1], maps[2], maps[3], maps[4], diag, st)
+
+    @staticmethod
+    def _dgrad(dZ, Wt, dX, N, Kp, h_saved, mul_mode, st):
+        """dX[:, :cols(dX)] = (dZ . Wt^T) * act'(h_saved); dX may be a column block of a wider buffer."""
+        M = dZ.shape[0]
+        if capi.trace is not None:
+            capi.next_meta = {'tag': 'gemm_bf16_tc_dgrad[%dx%dx%d]' % (M, N, Kp), 'flops': 2.0 * M * N * Kp}
+        call('dfol_gemm_bf16_tc_dgrad', ptr(dZ), dZ.stride(0), ptr(Wt), Wt.stride(0), ptr(dX), dX.stride(0), dX.shape[1], M,
+             N, Kp, ptr(h_saved), 0 if h_saved is None else h_saved.stride(0), mul_mode, st)
+
+    @staticmethod
+    def _wgrad(A, Mc, B, Nc, C, st):
+        """C[Mc, Nc] (fp32 view) += A[:, :Mc]^T . B[:, :Nc] (reduction over rows)."""
+        rows = A.shape[0]
+        if capi.trace is not None:
+            capi.next_meta = {'tag': 'gemm_bf16_tc_wgrad[%dx%dx%d]' % (Mc, Nc, rows), 'flops': 2.0 * Mc * Nc * rows}
+        call('dfol_gemm_bf16_tc_wgrad', ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(C), C.stride(0), Mc, Nc, rows,
+             st)
+
+    # -------------------------------------------------------------------------------------------- forward
+
+    def build_scene(self, features, layout, training):
+        from .engine import Scene
+        capi.lib()
+        w = self.w
+        dev = features.device
+        st = capi.stream_ptr(dev)
+        ops = self.operands(dev)
+        d, p = ops.dims, ops.pad
+        F, D, ldo, Ha, H, E, C = d['F'], d['D'], d['ldo'], d['Ha'], d['H'], d['E'], d['C']
+        T = features.shape[0]
+        assert T == layout.T and features.dtype == torch.float32 and features.stride(1) == 1
+        assert features.shape[1] == D + 6
+        ops.refresh(st, training)
+        sc = Scene()
+        sc.layout, sc.features, sc.tc = layout, features, True
+
+        def bf(rows, cols):
+            return torch.empty(rows, cols, device=dev, dtype=torch.bfloat16)
+
+        # featurizer: obj = [sigmoid(X Wf^T + b) | box position] (fp32 for the pair kernel) + bf16 operand copy
+        x16 = bf(T, p['Dp'])
+        call('dfol_cast_bf16', ptr(features), features.stride(0), ptr(x16), p['Dp'], T, D, st)
+        obj = torch.empty(T, ldo, device=dev, dtype=torch.float32)
+        self._tc(x16, ops.wf, obj, F, p['Dp'], w.feat.bias, K.ACT_SIGMOID, st)
+        obj16 = bf(T, p['Op'])
+        call('dfol_obj_finish', ptr(features), features.stride(0), D, ptr(obj), ldo, F, ptr(obj16), p['Op'], T, st)
+        sc.obj, sc.obj16, sc.x16 = obj, obj16, x16
+
+        # attribute chain (bf16 activations) -> attribute table (all C concept columns)
+        h1a = bf(T, p['Hap'])
+        self._tc(obj16, ops.wa1, h1a, Ha, p['Op'], w.attr[0].bias, K.ACT_ELU, st)
+        h2a = bf(T, p['Ep'])
+        self._tc(h1a, ops.wa2, h2a, E, p['Hap'], w.attr[1].bias, K.ACT_SIGMOID, st)
+        attr_ll = torch.empty(layout.attr_size, device=dev, dtype=torch.float32)
+        obj_table = {'row_img': layout.obj_img, 'img_row': layout.obj_row, 'img_blk': layout.attr_blk,
+                     'img_stride': layout.attr_stride}
+        self._tc(h2a, ops.we, attr_ll, C, p['Ep'], w.emb.bias, K.ACT_LOGSIGMOID, st, table=obj_table)
+        sc.attr_ll = attr_ll
+        sc.attr_h = [h1a, h2a]
+
+        # relation chain: U|V in one GEMM, pair hidden layer, layer 2, relation table
+        first = w.rel[0]
+        uv = torch.empty(T, 2 * H, device=dev, dtype=torch.float32)
+        self._tc(obj16, ops.wuv, uv, 2 * H, p['Op'], None, K.ACT_NONE, st)
+        h1r = bf(layout.P, p['Hp'])
+        geo = torch.empty(layout.P, 4, device=dev, dtype=torch.float32) if training else None
+        if capi.trace is not None:
+            capi.next_meta = {'tag': 'pair_hidden_fwd_tc', 'bytes': 2.0 * layout.P * p['Hp']}
+        call('dfol_pair_hidden_fwd_tc', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo, ptr(first.weight[:, 2 * ldo:]),
+             first.weight.stride(0), ptr(first.bias), ptr(h1r), p['Hp'], H, ptr(geo), ptr(layout.pair_row),
+             ptr(layout.obj_row), ptr(layout.img_n), layout.B, layout.max_n, st)
+        h2r = bf(layout.P, p['Ep'])
+        self._tc(h1r, ops.wr2, h2r, E, p['Hp'], w.rel[1].bias, K.ACT_SIGMOID, st)
+        ridx = self.engine.rel_index(dev)
+        sc.w_rel = w.emb.weight.detach().index_select(0, ridx).contiguous()
+        sc.b_rel = w.emb.bias.detach().index_select(0, ridx).contiguous()
+        wrel16 = bf(sc.w_rel.shape[0], p['Ep'])
+        call('dfol_cast_bf16', ptr(sc.w_rel), sc.w_rel.stride(0), ptr(wrel16), p['Ep'], sc.w_rel.shape[0], E, st)
+        rel_ll = torch.empty(layout.rel_size, device=dev, dtype=torch.float32)
+        pair_table = {'row_img': layout.pair_img, 'img_row': layout.pair_row, 'img_blk': layout.rel_blk,
+                      'img_stride': layout.rel_stride, 'img_n': layout.img_n, 'diag': DEFAULT_LL}
+        self._tc(h2r, wrel16, rel_ll, sc.w_rel.shape[0], p['Ep'], sc.b_rel, K.ACT_LOGSIGMOID, st, table=pair_table)
+        sc.rel_ll = rel_ll
+        sc.rel_h = [h1r, h2r]
+        sc.uv, sc.geo = uv, geo
+        return sc
+
+    # -------------------------------------------------------------------------------------------- backward
+
+    def _table_backward(self, g, tabs, ll, blk, stride, row0, img_rows, max_rows, rows_total, W, dW, db, h_last,
+                        d_below, st, tag):
+        """dZ (bf16, rows x padded width) of the layer below a table layer, from the compact gradient slices."""
+        dev = ll.device
+        E = W.shape[1]
+        cols = h_last.shape[1]
+        dz = torch.empty(rows_total, cols, device=dev, dtype=torch.bfloat16)
+        if tabs['max_per_image'] <= 12:
+            if capi.trace is not None:
+                passes = max(1, (tabs['max_per_image'] + 3) // 4)
+                capi.next_meta = {'tag': 'table_layer_bwd_tc[%s]' % tag, 'bytes': 4.0 * rows_total * cols * passes}
+            call('dfol_table_layer_bwd_tc', ptr(g), ptr(tabs['goff']), ptr(tabs['col']), ptr(tabs['wrow']),
+                 ptr(tabs['img_slice']), len(tabs['img_slice']) - 1, max_rows, tabs['max_per_image'], ptr(ll),
+                 ptr(blk), ptr(stride), ptr(row0), ptr(img_rows), ptr(W), W.stride(0), ptr(h_last),
+                 h_last.stride(0), E, ptr(dz), dz.stride(0), cols, ptr(dW), ptr(db), ptr(d_below), st)
+            return dz
+        # many columns per image (option lists of query-type programs): dense d logits + fp32 GEMMs
+        from .engine import gemm_f32, _split_for
+        Cn = dW.shape[0]
+        dl = torch.zeros(rows_total, Cn, device=dev, dtype=torch.float32)
+        call('dfol_table_grad_dense', ptr(g), ptr(tabs['goff']), ptr(tabs['col']), ptr(tabs['img']), tabs['count'],
+             ptr(ll), ptr(blk), ptr(stride), ptr(row0), ptr(img_rows), ptr(dl), Cn, st)
+        call('dfol_colsum', ptr(dl), Cn, rows_total, Cn, ptr(db), st)
+        h32 = h_last[:, :E].float()
+        sk = _split_for(rows_total)
+        gemm_f32(dl.t(), h32, dW, accumulate=(sk == 1), split_k=sk, stream=st)
+        d = torch.empty(rows_total, E, device=dev, dtype=torch.float32)
+        gemm_f32(dl, W, d, stream=st)
+        call('dfol_act_grad_mul', ptr(d), E, ptr(h32), E, rows_total, E, K.ACT_SIGMOID, st)
+        call('dfol_colsum', ptr(d), E, rows_total, E, ptr(d_below), st)
+        call('dfol_cast_bf16', ptr(d), E, ptr(dz), cols, rows_total, E, st)
+        return dz
+
+    def backward(self, cp, scene, tape, d_lp, grads):
+        eng = self.engine
+        w = self.w
+        lay = scene.layout
+        dev = scene.attr_ll.device
+        st = capi.stream_ptr(dev)
+        ops = self.operands(dev)
+        d, p = ops.dims, ops.pad
+        F, D, ldo, Ha, H, E = d['F'], d['D'], d['ldo'], d['Ha'], d['H'], d['E']
+        Hap, Hp, Ep, Kc = p['Hap'], p['Hp'], p['Ep'], p['Kc']
+        T, P = lay.T, lay.P
+        assert scene.geo is not None, 'scene was built without training buffers'
+
+        def G(prm):
+            return grads[id(prm)]
+
+        g_attr, g_rel = eng.program_backward(cp, scene, tape, d_lp)
+
+        # dcat = [dZ1 of the attribute chain | dU | dV]: the three first layers that read obj share one dgrad
+        dcat = torch.zeros(T, Kc, device=dev, dtype=torch.bfloat16)
+        a0, a1, r0, r1 = w.attr[0], w.attr[1], w.rel[0], w.rel[1]
+
+        # ---- attribute table layer -> layer 2 -> layer 1
+        sa = eng._slice_tables(cp.attr_slices, lay.B, dev, 'attr_slices', cp)
+        if sa['count']:
+            dz2a = self._table_backward(g_attr, sa, scene.attr_ll, lay.attr_blk, lay.attr_stride, lay.obj_row,
+                                        lay.img_n, lay.max_n, T, w.emb.weight, G(w.emb.weight), G(w.emb.bias),
+                                        scene.attr_h[1], G(a1.bias), st, 'attr')
+            self._wgrad(dz2a, E, scene.attr_h[0], Ha, G(a1.weight), st)
+            self._dgrad(dz2a, ops.wa2t, dcat[:, :Hap], Ha, Ep, scene.attr_h[0], K.MUL_ELU_GRAD, st)
+            call('dfol_colsum_bf16', ptr(dcat), Kc, T, Ha, ptr(G(a0.bias)), st)
+            self._wgrad(dcat, Ha, scene.obj16, ldo, G(a0.weight), st)
+
+        # ---- relation table layer -> layer 2 -> pair hidden layer
+        sr = eng._slice_tables(cp.rel_slices, lay.B, dev, 'rel_slices', cp)
+        if sr['count']:
+            nR = scene.w_rel.shape[0]
+            dw_rel = torch.zeros(nR, E, device=dev, dtype=torch.float32)
+            db_rel = torch.zeros(nR, device=dev, dtype=torch.float32)
+            dz2r = self._table_backward(g_rel, sr, scene.rel_ll, lay.rel_blk, lay.rel_stride, lay.pair_row,
+                                        lay.img_nn, lay.max_n ** 2, P, scene.w_rel, dw_rel, db_rel, scene.rel_h[1],
+                                        G(r1.bias), st, 'rel')
+            ridx = eng.rel_index(dev)
+            G(w.emb.weight).index_add_(0, ridx, dw_rel)
+            G(w.emb.bias).index_add_(0, ridx, db_rel)
+            h1r = scene.rel_h[0]
+            self._wgrad(dz2r, E, h1r, H, G(r1.weight), st)
+            dz1r = torch.empty(P, Hp, device=dev, dtype=torch.bfloat16)
+            self._dgrad(dz2r, ops.wr2t, dz1r, H, Ep, h1r, K.MUL_ELU_GRAD, st)
+            gw1 = G(r0.weight)
+            if capi.trace is not None:
+                capi.next_meta = {'tag': 'pair_hidden_bwd_tc', 'bytes': 2.0 * P * H + 16.0 * P}
+            call('dfol_pair_hidden_bwd_tc', ptr(dz1r), Hp, ptr(scene.geo), ptr(dcat[:, Hap:]), ptr(dcat[:, Hap + Hp:]),
+                 Kc, ptr(gw1[:, 2 * ldo:]), gw1.stride(0), ptr(G(r0.bias)), H, ptr(lay.pair_row), ptr(lay.obj_row),
+                 ptr(lay.img_n), lay.B, lay.max_n, st)
+            self._wgrad(dcat[:, Hap:], H, scene.obj16, ldo, gw1[:, :ldo], st)
+            self._wgrad(dcat[:, Hap + Hp:], H, scene.obj16, ldo, gw1[:, ldo:2 * ldo], st)
+
+        # ---- featurizer: d pre = (dcat . [Wa1 | Wu | Wv][:, :F]) * f (1 - f)
+        dpre = torch.empty(T, F, device=dev, dtype=torch.bfloat16)
+        self._dgrad(dcat, ops.wcat_t, dpre, F, Kc, scene.obj16, K.MUL_SIGMOID_GRAD, st)
+        call('dfol_colsum_bf16', ptr(dpre), F, T, F, ptr(G(w.feat.bias)), st)
+        self._wgrad(dpre, F, scene.x16, D, G(w.feat.weight), st)

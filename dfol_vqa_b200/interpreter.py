@@ -57,7 +57,7 @@ class _ReasoningFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, engine, cp, layout, features, need_grad, *params):
-        scene = engine.build_scene(features, layout)
+        scene = engine.build_scene(features, layout, keep_for_backward=need_grad)
         lp, tape = engine.run_programs(cp, scene, save_tape=need_grad)
         ctx.engine, ctx.cp, ctx.scene, ctx.tape, ctx.params = engine, cp, scene, tape, params
         return lp

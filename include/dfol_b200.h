@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFOL_ABI_VERSION 1
+#define DFOL_ABI_VERSION 2
 
 /* activation codes (RegularMLP / EmbeddingLayer, gqa_interpreter_experiments.py:28-33, :71-72) */
 #define DFOL_ACT_NONE 0
@@ -81,13 +81,24 @@ int dfol_gemm_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, vo
 
 /* Backward contractions of the tensor-core mode (bf16 operands, fp32 accumulation):
  * dgrad: dX[M,N] (bf16, ld lddx) = (dZ[M,K] . Wt[N,K]^T) * act'(h_saved[m,n])  -- Wt is the TRANSPOSED weight,
- *        mul_mode = DFOL_MUL_* evaluated from the saved bf16 activation output (epilogue multiplier);
+ *        mul_mode = DFOL_MUL_* evaluated from the saved bf16 activation output (epilogue multiplier); columns
+ *        N <= n < store_cols (0 = lddx) are written as zero, columns beyond store_cols are left untouched (dX may
+ *        be a column block of a wider concatenated operand);
  * wgrad: C[M,N] (fp32) += A[K,M]^T . B[K,N] with the reduction over ROWS (K = pair / object rows): MN-major UMMA
  *        operands straight from the row-major activations, split-K over CTAs, red.global.add.f32 epilogue. */
-int dfol_gemm_bf16_tc_dgrad(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX, int64_t lddx, int M,
-                            int N, int K, const void* h_saved, int64_t ldh, int mul_mode, void* stream);
+int dfol_gemm_bf16_tc_dgrad(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX, int64_t lddx,
+                            int store_cols, int M, int N, int K, const void* h_saved, int64_t ldh, int mul_mode,
+                            void* stream);
 int dfol_gemm_bf16_tc_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
                             int64_t K, void* stream);
+
+/* Batched operand preparation: job j casts (and, if transpose != 0, transposes) the fp32 view src[rows][cols]
+ * (row stride lds) into columns [0, dcols) of the bf16 rows dst[out_rows][ldd], zero beyond the source extent.
+ * `jobs` is a DEVICE array of job_num records of dfol_cast_job_size() bytes:
+ *   { const float* src; int64 lds; int32 rows, cols; bf16* dst; int64 ldd; int32 out_rows, transpose, dcols, pad }.
+ * max_elements = largest out_rows*dcols of the jobs (grid sizing).  One launch refreshes every weight operand. */
+int dfol_cast_jobs(const void* jobs, int job_num, int64_t max_elements, void* stream);
+int dfol_cast_job_size(void);
 
 /* fp32 -> bf16 cast with row padding: dst[r*ldd + c] = bf16(src[r*lds + c]) for c < cols, 0 for cols <= c < ldd */
 int dfol_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
@@ -114,6 +125,24 @@ int dfol_pair_hidden_bwd(const float* dh, int64_t lddh, const float* h_saved, in
                          int64_t ldpos, float* duv, int64_t lduv, float* dwg, int64_t ldw, float* dbias, int H,
                          int act, const int32_t* pair_row, const int32_t* obj_row, const int32_t* img_n,
                          int image_num, void* stream);
+
+/* Tensor-core mode (bf16 activations), single-pass HBM-bound kernels:
+ * dfol_obj_finish: writes the box position columns obj[t, F:F+4] (as dfol_box_position) and the bf16 operand copy
+ *   obj16[t, 0:ld16) = bf16(obj[t, :]) with zero K-padding.
+ * dfol_pair_hidden_fwd_tc: h = elu(U[s]+V[o]+Wg.geo+b) in bf16 (columns H..ldh zero) and, if geo_out != NULL, the
+ *   pair geometry table geo_out[pair] = float4(dist, asin, sign x, sign y) that the backward kernel re-uses.
+ * dfol_pair_hidden_bwd_tc: from dz (bf16, activation derivative already applied by the dgrad epilogue) and geo:
+ *   du_out[t, 0:H] = bf16(sum_o dz), dv_out[t, 0:H] = bf16(sum_s dz) (row stride ldo elements; WRITTEN),
+ *   dwg[h*ldw + k] += sum dz*geo_k, dbias[h] += sum dz (atomics; zeroed by the caller). */
+int dfol_obj_finish(const float* features, int64_t ldf, int feature_dim, float* obj, int64_t ldo, int F, void* obj16,
+                    int64_t ld16, int64_t rows, void* stream);
+int dfol_pair_hidden_fwd_tc(const float* uv, int64_t lduv, const float* obj_pos, int64_t ldpos, const float* wg,
+                            int64_t ldw, const float* bias, void* h_out, int64_t ldh, int H, void* geo_out,
+                            const int32_t* pair_row, const int32_t* obj_row, const int32_t* img_n, int image_num,
+                            int max_n, void* stream);
+int dfol_pair_hidden_bwd_tc(const void* dz, int64_t lddz, const void* geo, void* du_out, void* dv_out, int64_t ldo,
+                            float* dwg, int64_t ldw, float* dbias, int H, const int32_t* pair_row,
+                            const int32_t* obj_row, const int32_t* img_n, int image_num, int max_n, void* stream);
 
 /* bf16 variant: dz already carries the activation derivative (dgrad epilogue); duv is WRITTEN (no memset needed). */
 int dfol_pair_hidden_bwd_bf16(const void* dz, int64_t lddz, const float* obj_pos, int64_t ldpos, float* duv,
@@ -219,6 +248,18 @@ int dfol_table_layer_bwd_fused(const float* g, const int32_t* slice_goff, const 
                                const int32_t* img_rows, const float* W, int64_t ldw, const void* h_saved,
                                int64_t ldh, int E, int act, void* dZ, int64_t lddz, int out_cols, int bf16_io,
                                float* dW, float* db, void* stream);
+
+/* Tensor-core-mode variant (bf16 h_saved / dZ, sigmoid below the table layer): any number of slices per image
+ * (max_slices = largest img_slice[b+1]-img_slice[b]; consumed four per pass, later passes accumulate into dZ);
+ * slice_col = column inside the image's table block, slice_wrow = row of W / dW / db; additionally
+ * dbelow[e] += sum_rows dZ[row, e] (bias gradient of the layer below; NULL to skip).  Streams H and dZ once per pass
+ * with 128-byte warp transactions. */
+int dfol_table_layer_bwd_tc(const float* g, const int32_t* slice_goff, const int32_t* slice_col,
+                            const int32_t* slice_wrow, const int32_t* img_slice, int image_num, int max_rows,
+                            int max_slices, const float* ll, const int64_t* blk, const int32_t* stride,
+                            const int32_t* row0, const int32_t* img_rows, const float* W, int64_t ldw,
+                            const void* h_saved, int64_t ldh, int E, void* dZ, int64_t lddz, int out_cols, float* dW,
+                            float* db, float* dbelow, void* stream);
 
 /* Dense variant for tables where images touch many columns (attribute options): scatters the slices into a zeroed
  * dense (rows x columns) matrix with logsigmoid' applied, dZ[row0[b] + l, col_j] += g_j[l] * (1 - exp(LL_j[l]));

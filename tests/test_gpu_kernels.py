@@ -79,7 +79,8 @@ def test_gemm_f32_variants():
 @pytest.mark.parametrize('impl', ['f32', 'tc'])
 def test_gemm_table_store(pairs, impl):
     """Per-image transposed table store (+ -30 on self pairs) of both GEMM kernels."""
-    from dfol_vqa_b200.engine import gemm_f32, ReasoningEngine
+    from dfol_vqa_b200.engine import gemm_f32
+    from dfol_vqa_b200.engine_tc import TensorCorePath as ReasoningEngine
     counts = [5, 12, 3, 9, 16]
     ncols, Kd = 37, 128
     dev = torch.device('cuda')
@@ -113,7 +114,7 @@ def test_gemm_table_store(pairs, impl):
 @pytest.mark.parametrize('act,out16', [(0, False), (2, True), (1, True), (3, False)])
 def test_gemm_bf16_tcgen05(M, N, K, act, out16):
     """tcgen05/TMA GEMM vs an fp64 product of the same bf16 operands; padding columns of C must be zero."""
-    from dfol_vqa_b200.engine import ReasoningEngine
+    from dfol_vqa_b200.engine_tc import TensorCorePath as ReasoningEngine
     g = torch.Generator().manual_seed(M + N + K)
     A = (torch.randn(M, K, generator=g)).cuda().bfloat16()
     W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
@@ -251,7 +252,7 @@ def test_gemm_bf16_tcgen05_dgrad(M, N, K, mode):
     Wt = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
     Hs = (torch.rand(M, N, generator=g) - 0.3).cuda().bfloat16()
     dX = torch.full((M, N), float('nan'), device='cuda', dtype=torch.bfloat16)
-    call('dfol_gemm_bf16_tc_dgrad', ptr(dZ), K, ptr(Wt), K, ptr(dX), N, M, N, K, ptr(Hs), N, mode, stream_ptr())
+    call('dfol_gemm_bf16_tc_dgrad', ptr(dZ), K, ptr(Wt), K, ptr(dX), N, 0, M, N, K, ptr(Hs), N, mode, stream_ptr())
     torch.cuda.synchronize()
     ref = dZ.double() @ Wt.double().t()
     h = Hs.double()
