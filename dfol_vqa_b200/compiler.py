@@ -48,15 +48,21 @@ class CompiledPrograms(object):
 
     __slots__ = ('instr', 'q_instr', 'opts', 'lp_num', 'kind', 'options', 'seg', 'names', 'question_num',
                  'g_attr_size', 'g_rel_size', 'attr_slices', 'rel_slices', 'terminal', 'lp_owner', 'device_cache',
-                 'alg_bytes')
+                 'alg_bytes', 'slot_wrow', 'img_slot', 'slot_blk', 'rel_slot_size', 'max_slots')
 
 
 class ProgramCompiler(object):
 
-    def __init__(self, ontology, normalize=True, hard_mode=False):
+    def __init__(self, ontology, normalize=True, hard_mode=False, relation_slots=False):
+        """relation_slots: demand-driven relation table.  Instead of indexing a dense [nR] relation table, relate /
+        choose_rel operands are renumbered per image to *slots* 0..k_b-1 (the distinct relations the image's own
+        program uses); the scene build then evaluates only those k_b columns of ClassifierOracle.
+        compute_all_log_likelihood_2 (classifier_oracle.py:154 computes all and slices)."""
         self.ont = ontology
         self.normalize = normalize
         self.hard_mode = hard_mode
+        self.relation_slots = relation_slots
+        self._rel_concept = list(ontology._relation_index)
         self._a2i = ontology._vocabulary['arg_to_idx']
         self._rel_rev = ontology._relation_reveresed_index
         self._option_cache = {}
@@ -103,11 +109,25 @@ class ProgramCompiler(object):
             ga[0] += len(cols) * a_stride[q]
             return off
 
+        use_slots = self.relation_slots
+        slot_of = [dict() for _ in range(B)]  # per image: relation column -> slot
+
+        def rel_operand(q, col):
+            """Table column of relation ``col`` inside image q's block (its slot when demand-driven)."""
+            if not use_slots:
+                return col
+            d = slot_of[q]
+            if col not in d:
+                d[col] = len(d)
+            return d[col]
+
         def rel_slice(q, cols):
+            """Reserve gradient slices for relation columns ``cols``; records (image, table column, g offset, W row)."""
             cols = cols if isinstance(cols, (list, tuple)) else [cols]
             off = gr[0]
             for k, c in enumerate(cols):
-                rel_slices.append((q, c, off + k * r_stride[q]))
+                wrow = self._rel_concept[c] if use_slots else c
+                rel_slices.append((q, rel_operand(q, c), off + k * r_stride[q], wrow))
             gr[0] += len(cols) * r_stride[q]
             return off
 
@@ -134,7 +154,10 @@ class ProgramCompiler(object):
                 hit = (words, cols)
                 self._option_cache[key] = hit
             start = len(opts)
-            opts.extend(hit[0])
+            if kind == 'rel' and use_slots:
+                opts.extend(rel_operand(q, c) | (w & K.OPT_NEG) for w, c in zip(hit[0], hit[1]))
+            else:
+                opts.extend(hit[0])
             return start, len(hit[0]), hit[1]
 
         for i, slot in enumerate(slots):
@@ -183,8 +206,8 @@ class ProgramCompiler(object):
                         ncol, nfl = name_flags(nms[q], any_name_neg)
                         fl = (K.F_NEG if neg else 0) | (K.F_ROUNDTRIP if any_neg and not neg else 0) | nfl
                         fl |= K.F_SUBJECT if subj[q] else 0
-                        emit(q, K.OP_RELATE, fl, col, ncol, ga1=attr_slice(q, ncol) if ncol >= 0 else -1,
-                             grr=rel_slice(q, col))
+                        emit(q, K.OP_RELATE, fl, rel_operand(q, col), ncol,
+                             ga1=attr_slice(q, ncol) if ncol >= 0 else -1, grr=rel_slice(q, col))
                         names[q] = nms[q] if name_valid[q] else 'entity'
                 if name == 'verify_rel':
                     assert all(m > 0 for m in mask), 'one terminal operator per program batch'
@@ -305,6 +328,20 @@ class ProgramCompiler(object):
         cp.lp_owner = result['lp_owner']
         cp.device_cache = None
         # algorithmic bytes of one forward pass: every table slice read once + the log-probabilities written
-        cp.alg_bytes = 4.0 * (sum(object_counts[q] for q, _, _ in attr_slices) +
-                              sum(object_counts[q] ** 2 for q, _, _ in rel_slices) + lp_num)
+        cp.alg_bytes = 4.0 * (sum(object_counts[s[0]] for s in attr_slices) +
+                              sum(object_counts[s[0]] ** 2 for s in rel_slices) + lp_num)
+        if use_slots:
+            n_slots = np.asarray([len(d) for d in slot_of], dtype=np.int64)
+            cp.img_slot = np.concatenate([[0], np.cumsum(n_slots)]).astype(np.int32)
+            wrow = []
+            for d in slot_of:
+                wrow += [self._rel_concept[c] for c, _ in sorted(d.items(), key=lambda kv: kv[1])]
+            cp.slot_wrow = np.asarray(wrow if wrow else [0], dtype=np.int32)
+            blk = np.concatenate([[0], np.cumsum(n_slots * np.asarray(r_stride, dtype=np.int64))])
+            cp.slot_blk = blk[:-1].astype(np.int64)
+            cp.rel_slot_size = int(max(blk[-1], 1))
+            cp.max_slots = int(n_slots.max()) if B else 0
+        else:
+            cp.img_slot = cp.slot_wrow = cp.slot_blk = None
+            cp.rel_slot_size = cp.max_slots = 0
         return cp

@@ -378,6 +378,69 @@ __global__ void __launch_bounds__(256) table_layer_bwd_tc_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Demand-driven relation table (tensor-core mode): only the relation columns ("slots") the image's own program uses
+// are evaluated, LL[b][slot j][l] = logsigmoid(H2[row0[b] + l, :] . W[wrow_j, :] + bias[wrow_j]), self pairs = diag.
+// Same streaming structure as the table-layer backward: block = (128-row chunk, image), warp per row, lanes over
+// column pairs, one warp reduction per (row, slot); results are staged in shared memory and written coalesced.
+template <int S, int NC>
+__global__ void __launch_bounds__(256) rel_slots_fwd_kernel(
+    const __nv_bfloat16* __restrict__ hs, long long ldh, int E, const float* __restrict__ W, long long ldw,
+    const float* __restrict__ bias, const int32_t* __restrict__ slot_wrow, const int32_t* __restrict__ img_slot,
+    int first, const int64_t* __restrict__ slot_blk, const int32_t* __restrict__ stride,
+    const int32_t* __restrict__ row0, const int32_t* __restrict__ img_rows, const int32_t* __restrict__ img_n,
+    float diag, float* __restrict__ ll) {
+  __shared__ float zs[S][TB_ROWS];
+  const int b = blockIdx.y;
+  const int rows = img_rows[b];
+  const int c = blockIdx.x * TB_ROWS;
+  if (c >= rows) return;
+  const int j0 = img_slot[b] + first;
+  const int Sb = min(img_slot[b + 1] - j0, S);
+  if (Sb <= 0) return;
+  const int cn = min(TB_ROWS, rows - c);
+  const long long r0 = (long long)row0[b] + c;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2 wj[S][NC];
+#pragma unroll
+  for (int j = 0; j < S; ++j) {
+    const int wr = j < Sb ? slot_wrow[j0 + j] : 0;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int e = 2 * lane + 64 * k;
+      wj[j][k] = (j < Sb && e < E) ? *reinterpret_cast<const float2*>(W + (long long)wr * ldw + e)
+                                   : make_float2(0.f, 0.f);
+    }
+  }
+  for (int l = warp; l < cn; l += 8) {
+    const __nv_bfloat16* hrow = hs + (r0 + l) * ldh;
+    float2 h[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int e = 2 * lane + 64 * k;
+      h[k] = (e < E) ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hrow + e)) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      float z = 0.f;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) z = fmaf(h[k].x, wj[j][k].x, fmaf(h[k].y, wj[j][k].y, z));
+      z = warp_sum(z);
+      if (lane == 0) zs[j][l] = z;
+    }
+  }
+  __syncthreads();
+  const int n = img_n[b];
+  const long long base = slot_blk[b] + (long long)first * stride[b] + c;
+  for (int idx = threadIdx.x; idx < Sb * cn; idx += 256) {
+    const int j = idx / cn, l = idx - j * cn;
+    const int lg = c + l;
+    const float x = zs[j][l] + __ldg(bias + slot_wrow[j0 + j]);
+    const float v = fminf(x, 0.0f) - __logf(1.0f + __expf(-fabsf(x)));
+    ll[base + (long long)j * stride[b] + l] = ((lg / n) == (lg % n)) ? diag : v;
+  }
+}
+
 }  // namespace dfol
 
 using namespace dfol;
@@ -501,4 +564,31 @@ extern "C" int dfol_table_layer_bwd_tc(const float* g, const int32_t* slice_goff
     first += 4;
   } while (first < max_slices);
   return finish_launch("dfol_table_layer_bwd_tc");
+}
+
+extern "C" int dfol_rel_slots_fwd(const void* h_saved, int64_t ldh, int E, const float* W, int64_t ldw,
+                                  const float* bias, const int32_t* slot_wrow, const int32_t* img_slot, int max_slots,
+                                  const int64_t* slot_blk, const int32_t* stride, const int32_t* row0,
+                                  const int32_t* img_rows, const int32_t* img_n, int image_num, int max_rows,
+                                  float diag_value, float* ll, void* stream) {
+  DFOL_REQUIRE(h_saved && W && bias && slot_wrow && img_slot && slot_blk && stride && row0 && img_rows && img_n && ll,
+               "dfol_rel_slots_fwd: null pointer");
+  if (image_num == 0 || max_rows == 0 || max_slots == 0) return 0;
+  DFOL_REQUIRE(E <= 320 && (E % 2) == 0 && (ldw % 2) == 0 && (ldh % 2) == 0,
+               "dfol_rel_slots_fwd: E <= 320, even sizes and strides");
+  dim3 grid((max_rows + TB_ROWS - 1) / TB_ROWS, image_num);
+  DFOL_REQUIRE(grid.y <= 65535, "dfol_rel_slots_fwd: too many images");
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(h_saved);
+  for (int first = 0; first < max_slots; first += 4) {
+    const int left = max_slots - first;
+#define DFOL_RS_LAUNCH(S)                                                                                          \
+  rel_slots_fwd_kernel<S, 5><<<grid, 256, 0, st>>>(hp, ldh, E, W, ldw, bias, slot_wrow, img_slot, first, slot_blk,  \
+                                                   stride, row0, img_rows, img_n, diag_value, ll)
+    if (left <= 1) DFOL_RS_LAUNCH(1);
+    else if (left == 2) DFOL_RS_LAUNCH(2);
+    else DFOL_RS_LAUNCH(4);
+#undef DFOL_RS_LAUNCH
+  }
+  return finish_launch("dfol_rel_slots_fwd");
 }

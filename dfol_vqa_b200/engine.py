@@ -141,10 +141,11 @@ class ReasoningEngine(object):
 
     # ------------------------------------------------------------------------------------------ forward
 
-    def build_scene(self, features, layout, keep_for_backward=True):
-        """Featurizer + attribute / relation tables (K1-K6 of SURVEY.md §2.1)."""
+    def build_scene(self, features, layout, keep_for_backward=True, cp=None):
+        """Featurizer + attribute / relation tables (K1-K6 of SURVEY.md §2.1).  ``cp``: the compiled programs of the
+        batch; when they carry relation slots only those relation columns are evaluated (tensor-core mode)."""
         if self.gemm_mode == 'bf16':
-            return self.tc.build_scene(features, layout, keep_for_backward)
+            return self.tc.build_scene(features, layout, keep_for_backward, cp)
         capi.lib()
         w = self.w
         dev = features.device
@@ -210,6 +211,7 @@ class ReasoningEngine(object):
                       'img_stride': layout.rel_stride, 'img_n': layout.img_n, 'diag': DEFAULT_LL}
         gemm_f32(h, sc.w_rel.t(), rel_ll, sc.b_rel, K.ACT_LOGSIGMOID, table=pair_table, stream=st)
         sc.rel_ll = rel_ll
+        sc.rel_blk = layout.rel_blk
         return sc
 
     def upload_programs(self, cp, device):
@@ -220,6 +222,8 @@ class ReasoningEngine(object):
             cache = {'device': device, 'instr': dev(cp.instr), 'q_instr': dev(cp.q_instr), 'opts': dev(cp.opts)}
             if cp.seg is not None:
                 cache['seg'] = dev(cp.seg)
+            if cp.img_slot is not None:
+                cache.update(slot_wrow=dev(cp.slot_wrow), img_slot=dev(cp.img_slot), slot_blk=dev(cp.slot_blk))
             cp.device_cache = cache
         return cp.device_cache
 
@@ -237,7 +241,7 @@ class ReasoningEngine(object):
         if capi.trace is not None:
             capi.next_meta = {'tag': 'program_fwd', 'bytes': cp.alg_bytes}
         call('dfol_program_fwd', ptr(d['instr']), ptr(d['q_instr']), ptr(d['opts']), cp.question_num,
-             ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride), ptr(scene.rel_ll), ptr(lay.rel_blk),
+             ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride), ptr(scene.rel_ll), ptr(scene.rel_blk),
              ptr(lay.rel_stride), ptr(lay.img_n), ptr(lp), ptr(tape), stride, st)
         return lp[:cp.lp_num], tape
 
@@ -249,20 +253,21 @@ class ReasoningEngine(object):
         if key in cache:
             return cache[key]
         if slices:
-            arr = np.asarray(slices, dtype=np.int64)  # (question, column, g offset)
+            arr = np.asarray(slices, dtype=np.int64)  # (question, column, g offset[, W row])
             order = np.argsort(arr[:, 0], kind='stable')
             arr = arr[order]
             counts = np.bincount(arr[:, 0], minlength=B)
         else:
-            arr = np.zeros((0, 3), dtype=np.int64)
+            arr = np.zeros((0, 4), dtype=np.int64)
             counts = np.zeros(B, dtype=np.int64)
         img_slice = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
 
         def dev(a):
             return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
-        pad = arr if arr.shape[0] else np.zeros((1, 3), dtype=np.int64)
+        pad = arr if arr.shape[0] else np.zeros((1, 4), dtype=np.int64)
+        wrow = pad[:, 3] if pad.shape[1] > 3 else pad[:, 1]
         out = {'goff': dev(pad[:, 2].astype(np.int32)), 'col': dev(pad[:, 1].astype(np.int32)),
-               'wrow': dev(pad[:, 1].astype(np.int32)), 'img': dev(pad[:, 0].astype(np.int32)), 'img_slice': dev(img_slice), 'count': int(arr.shape[0]),
+               'wrow': dev(wrow.astype(np.int32)), 'img': dev(pad[:, 0].astype(np.int32)), 'img_slice': dev(img_slice), 'count': int(arr.shape[0]),
                'max_per_image': int(counts.max()) if counts.size else 0}
         cache[key] = out
         return out
@@ -279,7 +284,7 @@ class ReasoningEngine(object):
         if capi.trace is not None:
             capi.next_meta = {'tag': 'program_bwd', 'bytes': 2.0 * cp.alg_bytes}
         call('dfol_program_bwd', ptr(d['instr']), ptr(d['q_instr']), ptr(d['opts']), cp.question_num,
-             ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride), ptr(scene.rel_ll), ptr(lay.rel_blk),
+             ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride), ptr(scene.rel_ll), ptr(scene.rel_blk),
              ptr(lay.rel_stride), ptr(lay.img_n), ptr(d_lp), ptr(tape), stride, ptr(g_attr), ptr(g_rel), st)
         return g_attr, g_rel
 

@@ -136,7 +136,7 @@ class TensorCorePath(object):
 
     # -------------------------------------------------------------------------------------------- forward
 
-    def build_scene(self, features, layout, training):
+    def build_scene(self, features, layout, training, cp=None):
         from .engine import Scene
         capi.lib()
         w = self.w
@@ -189,15 +189,30 @@ class TensorCorePath(object):
              ptr(layout.obj_row), ptr(layout.img_n), layout.B, layout.max_n, st)
         h2r = bf(layout.P, p['Ep'])
         self._tc(h1r, ops.wr2, h2r, E, p['Hp'], w.rel[1].bias, K.ACT_SIGMOID, st)
-        ridx = self.engine.rel_index(dev)
-        sc.w_rel = w.emb.weight.detach().index_select(0, ridx).contiguous()
-        sc.b_rel = w.emb.bias.detach().index_select(0, ridx).contiguous()
-        wrel16 = bf(sc.w_rel.shape[0], p['Ep'])
-        call('dfol_cast_bf16', ptr(sc.w_rel), sc.w_rel.stride(0), ptr(wrel16), p['Ep'], sc.w_rel.shape[0], E, st)
-        rel_ll = torch.empty(layout.rel_size, device=dev, dtype=torch.float32)
-        pair_table = {'row_img': layout.pair_img, 'img_row': layout.pair_row, 'img_blk': layout.rel_blk,
-                      'img_stride': layout.rel_stride, 'img_n': layout.img_n, 'diag': DEFAULT_LL}
-        self._tc(h2r, wrel16, rel_ll, sc.w_rel.shape[0], p['Ep'], sc.b_rel, K.ACT_LOGSIGMOID, st, table=pair_table)
+        if cp is not None and cp.img_slot is not None:
+            # demand-driven: only the relation columns this batch's programs read, in the compact slot layout
+            dc = self.engine.upload_programs(cp, dev)
+            rel_ll = torch.empty(cp.rel_slot_size, device=dev, dtype=torch.float32)
+            if capi.trace is not None:
+                capi.next_meta = {'tag': 'rel_slots_fwd', 'bytes': 2.0 * layout.P * p['Ep'] * max(
+                    1, (cp.max_slots + 3) // 4) + 4.0 * cp.rel_slot_size}
+            call('dfol_rel_slots_fwd', ptr(h2r), p['Ep'], E, ptr(w.emb.weight), w.emb.weight.stride(0),
+                 ptr(w.emb.bias), ptr(dc['slot_wrow']), ptr(dc['img_slot']), cp.max_slots, ptr(dc['slot_blk']),
+                 ptr(layout.rel_stride), ptr(layout.pair_row), ptr(layout.img_nn), ptr(layout.img_n), layout.B,
+                 layout.max_n ** 2, DEFAULT_LL, ptr(rel_ll), st)
+            sc.rel_blk, sc.rel_slots = dc['slot_blk'], True
+        else:
+            ridx = self.engine.rel_index(dev)
+            sc.w_rel = w.emb.weight.detach().index_select(0, ridx).contiguous()
+            sc.b_rel = w.emb.bias.detach().index_select(0, ridx).contiguous()
+            wrel16 = bf(sc.w_rel.shape[0], p['Ep'])
+            call('dfol_cast_bf16', ptr(sc.w_rel), sc.w_rel.stride(0), ptr(wrel16), p['Ep'], sc.w_rel.shape[0], E, st)
+            rel_ll = torch.empty(layout.rel_size, device=dev, dtype=torch.float32)
+            pair_table = {'row_img': layout.pair_img, 'img_row': layout.pair_row, 'img_blk': layout.rel_blk,
+                          'img_stride': layout.rel_stride, 'img_n': layout.img_n, 'diag': DEFAULT_LL}
+            self._tc(h2r, wrel16, rel_ll, sc.w_rel.shape[0], p['Ep'], sc.b_rel, K.ACT_LOGSIGMOID, st,
+                     table=pair_table)
+            sc.rel_blk, sc.rel_slots = layout.rel_blk, False
         sc.rel_ll = rel_ll
         sc.rel_h = [h1r, h2r]
         sc.uv, sc.geo = uv, geo
@@ -274,15 +289,20 @@ class TensorCorePath(object):
         # ---- relation table layer -> layer 2 -> pair hidden layer
         sr = eng._slice_tables(cp.rel_slices, lay.B, dev, 'rel_slices', cp)
         if sr['count']:
-            nR = scene.w_rel.shape[0]
-            dw_rel = torch.zeros(nR, E, device=dev, dtype=torch.float32)
-            db_rel = torch.zeros(nR, device=dev, dtype=torch.float32)
-            dz2r = self._table_backward(g_rel, sr, scene.rel_ll, lay.rel_blk, lay.rel_stride, lay.pair_row,
-                                        lay.img_nn, lay.max_n ** 2, P, scene.w_rel, dw_rel, db_rel, scene.rel_h[1],
-                                        G(r1.bias), st, 'rel')
-            ridx = eng.rel_index(dev)
-            G(w.emb.weight).index_add_(0, ridx, dw_rel)
-            G(w.emb.bias).index_add_(0, ridx, db_rel)
+            if scene.rel_slots:
+                dz2r = self._table_backward(g_rel, sr, scene.rel_ll, scene.rel_blk, lay.rel_stride, lay.pair_row,
+                                            lay.img_nn, lay.max_n ** 2, P, w.emb.weight, G(w.emb.weight),
+                                            G(w.emb.bias), scene.rel_h[1], G(r1.bias), st, 'rel')
+            else:
+                nR = scene.w_rel.shape[0]
+                dw_rel = torch.zeros(nR, E, device=dev, dtype=torch.float32)
+                db_rel = torch.zeros(nR, device=dev, dtype=torch.float32)
+                dz2r = self._table_backward(g_rel, sr, scene.rel_ll, lay.rel_blk, lay.rel_stride, lay.pair_row,
+                                            lay.img_nn, lay.max_n ** 2, P, scene.w_rel, dw_rel, db_rel,
+                                            scene.rel_h[1], G(r1.bias), st, 'rel')
+                ridx = eng.rel_index(dev)
+                G(w.emb.weight).index_add_(0, ridx, dw_rel)
+                G(w.emb.bias).index_add_(0, ridx, db_rel)
             h1r = scene.rel_h[0]
             self._wgrad(dz2r, E, h1r, H, G(r1.weight), st)
             dz1r = torch.empty(P, Hp, device=dev, dtype=torch.bfloat16)

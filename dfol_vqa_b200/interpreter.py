@@ -57,7 +57,7 @@ class _ReasoningFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, engine, cp, layout, features, need_grad, *params):
-        scene = engine.build_scene(features, layout, keep_for_backward=need_grad)
+        scene = engine.build_scene(features, layout, keep_for_backward=need_grad, cp=cp)
         lp, tape = engine.run_programs(cp, scene, save_tape=need_grad)
         ctx.engine, ctx.cp, ctx.scene, ctx.tape, ctx.params = engine, cp, scene, tape, params
         return lp
@@ -108,7 +108,8 @@ class FastGQAInterpreter(nn.Module):
                                       linear_layers(oracle._relation_network),
                                       linear_layers(oracle._embedding_network)[0])
         self._engine = ReasoningEngine(self._weights, ontology._relation_index, self._gemm_mode)
-        self._compiler = ProgramCompiler(ontology, normalize=oracle._normalize, hard_mode=hard_mode)
+        self._compiler = ProgramCompiler(ontology, normalize=oracle._normalize, hard_mode=hard_mode,
+                                         relation_slots=(self._gemm_mode == 'bf16'))
 
     _dropout = 0.0
 
@@ -294,7 +295,7 @@ class FusedTrainStep(object):
             layout = SceneLayout.get(counts, interp._weights.emb.weight.shape[0],
                                      len(interp._ontology._relation_index), dev)
             cp = interp.compiled(pb, False)
-            scene = self.engine.build_scene(feats, layout)
+            scene = self.engine.build_scene(feats, layout, cp=cp)
             lp, tape = self.engine.run_programs(cp, scene, save_tape=True)
             target = self._targets(pb, cp, dev)
             d_lp = torch.empty_like(lp)

@@ -261,6 +261,16 @@ int dfol_table_layer_bwd_tc(const float* g, const int32_t* slice_goff, const int
                             const void* h_saved, int64_t ldh, int E, void* dZ, int64_t lddz, int out_cols, float* dW,
                             float* db, float* dbelow, void* stream);
 
+/* Demand-driven relation table (tensor-core mode; replaces computing all nR columns of
+ * ClassifierOracle.compute_all_log_likelihood_2, classifier_oracle.py:154, when the batch's programs are known):
+ * image b owns slots [img_slot[b], img_slot[b+1]); slot j evaluates row slot_wrow[j] of the embedding layer:
+ * ll[slot_blk[b] + k*stride[b] + l] = logsigmoid(H[row0[b]+l, :] . W[wrow, :] + bias[wrow]) for the k-th slot of
+ * the image, l < img_rows[b]; self pairs (l / img_n[b] == l %% img_n[b]) are written as diag_value. */
+int dfol_rel_slots_fwd(const void* h_saved, int64_t ldh, int E, const float* W, int64_t ldw, const float* bias,
+                       const int32_t* slot_wrow, const int32_t* img_slot, int max_slots, const int64_t* slot_blk,
+                       const int32_t* stride, const int32_t* row0, const int32_t* img_rows, const int32_t* img_n,
+                       int image_num, int max_rows, float diag_value, float* ll, void* stream);
+
 /* Dense variant for tables where images touch many columns (attribute options): scatters the slices into a zeroed
  * dense (rows x columns) matrix with logsigmoid' applied, dZ[row0[b] + l, col_j] += g_j[l] * (1 - exp(LL_j[l]));
  * the layer backward is then two ordinary GEMMs (dH = dZ.W, dW = dZ^T.H) and a column sum. */
