@@ -140,6 +140,9 @@ class FastGQAInterpreter(nn.Module):
         assert bool((host[1:] >= host[:-1]).all()), 'object rows must be grouped by image'
         counts = torch.bincount(host).tolist()
         pb._dfol_counts = counts
+        src = getattr(pb, '_dfol_host', None)
+        if src is not None:
+            src._dfol_counts = counts
         return counts
 
     def compiled(self, pb, give_answer):
@@ -147,6 +150,9 @@ class FastGQAInterpreter(nn.Module):
         if cache is None:
             cache = {}
             pb._dfol_compiled = cache
+            host = getattr(pb, '_dfol_host', None)
+            if host is not None:
+                host._dfol_compiled = cache
         key = bool(give_answer and self._hard_mode)
         if key not in cache:
             cache[key] = self._compiler.compile(pb, self._object_counts(pb), give_answer=give_answer)
@@ -274,6 +280,9 @@ class FusedTrainStep(object):
         if t is None or t.device != dev:
             t = torch.from_numpy(targets_of(cp, pb._answers)).to(dev, non_blocking=True)
             pb._dfol_targets = t
+            host = getattr(pb, '_dfol_host', None)
+            if host is not None:
+                host._dfol_targets = t
         return t
 
     def forward_backward(self, program_batch_list, global_question_num=None):

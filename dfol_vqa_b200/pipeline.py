@@ -1,0 +1,56 @@
+"""Host-side staging pipeline of the step: pinned host batches -> device, double buffered.
+
+The reference trainer moves every program batch to the GPU inside the step (VQATrainer._run_model ->
+ProgramBatch.to_cuda, reference src/nsvqa/train/trainer.py:90-97, data_pipeline.py:116-140) and reads the loss back
+with .item() right after (trainer.py:440-447), so copy, compute and read-back serialise.  Here the H2D copy of batch
+i+1 runs on a copy stream while batch i computes, and the result of step i is read back (pinned, asynchronous)
+after step i+1 has been enqueued; every step still pays its own H2D copy and its own D2H read.
+"""
+
+import torch
+
+
+class HostStepPipeline(object):
+
+    def __init__(self, step_fn, device):
+        """``step_fn(device_program_batch) -> device tensor`` (loss scalar or log-probabilities)."""
+        self.step_fn = step_fn
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self._host = [None, None]
+
+    def _stage(self, hb):
+        with torch.cuda.stream(self.copy_stream):
+            db = hb.to_cuda(self.device.index, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return db, ev
+
+    def run(self, host_batches):
+        """Runs the step over ``host_batches`` (a sequence); returns the list of results as CPU tensors."""
+        compute = torch.cuda.current_stream(self.device)
+        n = len(host_batches)
+        results, pending = [], None
+        nxt = self._stage(host_batches[0]) if n else None
+        for i in range(n):
+            db, ev = nxt
+            if i + 1 < n:
+                nxt = self._stage(host_batches[i + 1])
+            compute.wait_event(ev)
+            db._object_features.record_stream(compute)
+            db._object_batch_index.record_stream(compute)
+            out = self.step_fn(db).detach()
+            slot = i & 1
+            if self._host[slot] is None or self._host[slot].shape != out.shape or self._host[slot].dtype != out.dtype:
+                self._host[slot] = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            self._host[slot].copy_(out, non_blocking=True)
+            rev = torch.cuda.Event()
+            rev.record(compute)
+            if pending is not None:
+                pending[1].synchronize()
+                results.append(pending[0].clone())
+            pending = (self._host[slot], rev)
+        if pending is not None:
+            pending[1].synchronize()
+            results.append(pending[0].clone())
+        return results

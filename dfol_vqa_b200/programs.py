@@ -112,6 +112,11 @@ class ProgramBatch(object):
         bidx = self._object_batch_index.cuda(device, non_blocking=non_blocking)
         pb = ProgramBatch(torch.device('cuda', device) if isinstance(device, int) else device, self._op_batch_list,
                           self._dependencies, self._answers, feats, bidx, self._original_dicts, self._meta_data)
+        # collate-time products of the fused path (compiled bytecode, object counts, targets) travel with the batch
+        for key in ('_dfol_compiled', '_dfol_counts', '_dfol_targets'):
+            if hasattr(self, key):
+                setattr(pb, key, getattr(self, key))
+        pb._dfol_host = self
         return pb
 
 
