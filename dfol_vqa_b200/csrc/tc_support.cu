@@ -86,13 +86,15 @@ __global__ void __launch_bounds__(256) pair_hidden_fwd_tc_kernel(
     const float* __restrict__ uv, long long lduv, const float* __restrict__ pos, long long ldpos,
     const float* __restrict__ wg, long long ldw, const float* __restrict__ bias, __nv_bfloat16* __restrict__ hout,
     long long ldh, float4* __restrict__ geo_out, const int32_t* __restrict__ pair_row,
-    const int32_t* __restrict__ obj_row, const int32_t* __restrict__ img_n) {
+    const int32_t* __restrict__ obj_row, const int32_t* __restrict__ img_n, int subjects_per_block) {
   constexpr int H = 128 * G, H4 = H / 4;
   extern __shared__ float4 vsm[];  // [PF_TO][H4]
   const int b = blockIdx.y;
   const int n = img_n[b];
   const int o0 = blockIdx.x * PF_TO;
-  if (o0 >= n) return;
+  const int s_begin = blockIdx.z * subjects_per_block;
+  if (o0 >= n || s_begin >= n) return;
+  const int s_end = min(n, s_begin + subjects_per_block);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long t0 = obj_row[b];
   const long long p0 = pair_row[b];
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(256) pair_hidden_fwd_tc_kernel(
   if (lane < no) po = __ldg(reinterpret_cast<const float4*>(pos + (t0 + o0 + lane) * ldpos));
   __syncthreads();
   const int zero_cols = (int)ldh - H;
-  for (int s = warp; s < n; s += 8) {
+  for (int s = s_begin + warp; s < s_end; s += 8) {
     const float4 ps = __ldg(reinterpret_cast<const float4*>(pos + (t0 + s) * ldpos));
     float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane < no && o0 + lane != s) gl = pair_geometry4(ps, po);
@@ -164,14 +166,14 @@ __global__ void __launch_bounds__(256) pair_hidden_fwd_tc_kernel(
 //   dU[s][h] = sum_o dz   is reduced over the 8 row groups through a double-buffered shared tile (one barrier per s),
 //   dWg[h][k] = sum dz*geo_k and db[h] = sum dz stay in registers until the end (one atomic per block and column).
 // dU / dV are written as bf16 (operands of the next tensor-core GEMMs).
-template <int NI>
-__global__ void __launch_bounds__(256) pair_hidden_bwd_tc_kernel(
+template <int RG, int NI>
+__global__ void __launch_bounds__(32 * RG) pair_hidden_bwd_tc_kernel(
     const __nv_bfloat16* __restrict__ dz, long long lddz, const float4* __restrict__ geo,
     __nv_bfloat16* __restrict__ du_out, __nv_bfloat16* __restrict__ dv_out, long long ldo, float* __restrict__ dwg,
     long long ldw, float* __restrict__ dbias, const int32_t* __restrict__ pair_row,
     const int32_t* __restrict__ obj_row, const int32_t* __restrict__ img_n) {
-  __shared__ __align__(16) float red[2][8][64];
-  __shared__ __align__(16) float redw[8][4][64];
+  __shared__ __align__(16) float red[2][RG][64];
+  __shared__ __align__(16) float redw[RG][4][64];
   const int b = blockIdx.y;
   const int n = img_n[b];
   const long long t0 = obj_row[b];
@@ -183,30 +185,36 @@ __global__ void __launch_bounds__(256) pair_hidden_bwd_tc_kernel(
   for (int i = 0; i < NI; ++i) dv[i][0] = dv[i][1] = 0.0f;
   float dw[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
   float dbv = 0.0f;  // threads < 64: column sum of dU
+  constexpr int CH = (NI > 8) ? (NI + 1) / 2 : NI;  // rows in flight per thread (bounds the register footprint)
   for (int s = 0; s < n; ++s) {
     const long long prow = p0 + (long long)s * n;
-    float2 v[NI];
-    float4 g[NI];
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int o = rg + 8 * i;
-      v[i] = make_float2(0.f, 0.f);
-      g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (o < n && o != s) {
-        const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(dz + (prow + o) * lddz + c0);
-        v[i] = __bfloat1622float2(x);
-        g[i] = __ldg(geo + prow + o);
-      }
-    }
     float du0 = 0.f, du1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      du0 += v[i].x; du1 += v[i].y;
-      dv[i][0] += v[i].x; dv[i][1] += v[i].y;
-      dw[0][0] = fmaf(v[i].x, g[i].x, dw[0][0]); dw[0][1] = fmaf(v[i].y, g[i].x, dw[0][1]);
-      dw[1][0] = fmaf(v[i].x, g[i].y, dw[1][0]); dw[1][1] = fmaf(v[i].y, g[i].y, dw[1][1]);
-      dw[2][0] = fmaf(v[i].x, g[i].z, dw[2][0]); dw[2][1] = fmaf(v[i].y, g[i].z, dw[2][1]);
-      dw[3][0] = fmaf(v[i].x, g[i].w, dw[3][0]); dw[3][1] = fmaf(v[i].y, g[i].w, dw[3][1]);
+    for (int i0 = 0; i0 < NI; i0 += CH) {
+      float2 v[CH];
+      float4 g[CH];
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int o = rg + RG * (i0 + i);
+        v[i] = make_float2(0.f, 0.f);
+        g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i0 + i < NI && o < n && o != s) {
+          const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(dz + (prow + o) * lddz + c0);
+          v[i] = __bfloat1622float2(x);
+          g[i] = __ldg(geo + prow + o);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        if (i0 + i < NI) {
+          du0 += v[i].x; du1 += v[i].y;
+          dv[i0 + i][0] += v[i].x; dv[i0 + i][1] += v[i].y;
+          dw[0][0] = fmaf(v[i].x, g[i].x, dw[0][0]); dw[0][1] = fmaf(v[i].y, g[i].x, dw[0][1]);
+          dw[1][0] = fmaf(v[i].x, g[i].y, dw[1][0]); dw[1][1] = fmaf(v[i].y, g[i].y, dw[1][1]);
+          dw[2][0] = fmaf(v[i].x, g[i].z, dw[2][0]); dw[2][1] = fmaf(v[i].y, g[i].z, dw[2][1]);
+          dw[3][0] = fmaf(v[i].x, g[i].w, dw[3][0]); dw[3][1] = fmaf(v[i].y, g[i].w, dw[3][1]);
+        }
+      }
     }
     const int buf = s & 1;
     *reinterpret_cast<float2*>(&red[buf][rg][2 * lane]) = make_float2(du0, du1);
@@ -214,14 +222,14 @@ __global__ void __launch_bounds__(256) pair_hidden_bwd_tc_kernel(
     if (threadIdx.x < 64) {
       float t = 0.f;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) t += red[buf][r][threadIdx.x];
+      for (int r = 0; r < RG; ++r) t += red[buf][r][threadIdx.x];
       du_out[(t0 + s) * ldo + blockIdx.x * 64 + threadIdx.x] = __float2bfloat16(t);
       dbv += t;
     }
   }
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
-    const int o = rg + 8 * i;
+    const int o = rg + RG * i;
     if (o < n) {
       const __nv_bfloat162 x = __floats2bfloat162_rn(dv[i][0], dv[i][1]);
       *reinterpret_cast<__nv_bfloat162*>(dv_out + (t0 + o) * ldo + c0) = x;
@@ -236,7 +244,7 @@ __global__ void __launch_bounds__(256) pair_hidden_bwd_tc_kernel(
     for (int k = 0; k < 4; ++k) {
       float t = 0.f;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) t += redw[r][k][threadIdx.x];
+      for (int r = 0; r < RG; ++r) t += redw[r][k][threadIdx.x];
       atomicAdd(dwg + (long long)h * ldw + k, t);
     }
     atomicAdd(dbias + h, dbv);
@@ -252,18 +260,20 @@ __global__ void __launch_bounds__(256) pair_hidden_bwd_tc_kernel(
 // One block per (128-row chunk, image); warp w streams rows w, w+8, ... of the chunk, lane owns the column pairs
 // 2*lane + 64*c (c < NC): every row is read and written with 128-byte warp transactions, exactly once.
 constexpr int TB_ROWS = 128;
+constexpr int TB_RP = 2;  // row-parallel warps per column chunk
 
 template <int S, int NC>
-__global__ void __launch_bounds__(256) table_layer_bwd_tc_kernel(
+__global__ void __launch_bounds__(32 * NC * TB_RP) table_layer_bwd_tc_kernel(
     const float* __restrict__ g, const int32_t* __restrict__ slice_goff, const int32_t* __restrict__ slice_col,
     const int32_t* __restrict__ slice_wrow, const int32_t* __restrict__ img_slice, int first, int accumulate,
     const float* __restrict__ ll, const int64_t* __restrict__ blk, const int32_t* __restrict__ stride,
     const int32_t* __restrict__ row0, const int32_t* __restrict__ img_rows, const float* __restrict__ W,
     long long ldw, const __nv_bfloat16* __restrict__ hs, long long ldh, int E, __nv_bfloat16* __restrict__ dZ,
     long long lddz, int out_cols, float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dbelow) {
+  constexpr int THREADS = 32 * NC * TB_RP;
   __shared__ float dz_s[S][TB_ROWS];
   __shared__ int wrow_s[S];
-  __shared__ __align__(16) float red_s[8][NC * 64];
+  __shared__ __align__(16) float red_s[TB_RP][NC * 64];
   const int b = blockIdx.y;
   const int rows = img_rows[b];
   const int c = blockIdx.x * TB_ROWS;
@@ -273,21 +283,15 @@ __global__ void __launch_bounds__(256) table_layer_bwd_tc_kernel(
   const int j0 = img_slice[b] + first;
   const int Sb = max(0, min(img_slice[b + 1] - j0, S));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = warp % NC, rp = warp / NC;   // column chunk of this warp, row phase
+  const int e = 64 * k + 2 * lane;           // column pair of this thread
   if (Sb == 0) {
-    if (!accumulate) {  // rows of images without (more) slices are zero
-      for (int l = warp; l < cn; l += 8) {
-        __nv_bfloat16* drow = dZ + (r0 + l) * lddz;
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-          const int e = 2 * lane + 64 * k;
-          if (e < out_cols) *reinterpret_cast<uint32_t*>(drow + e) = 0u;
-        }
-      }
-    }
+    if (!accumulate && e < out_cols)  // rows of images without (more) slices are zero
+      for (int l = rp; l < cn; l += TB_RP) *reinterpret_cast<uint32_t*>(dZ + (r0 + l) * lddz + e) = 0u;
     return;
   }
   const int st = stride[b];
-  for (int idx = threadIdx.x; idx < S * TB_ROWS; idx += 256) {
+  for (int idx = threadIdx.x; idx < S * TB_ROWS; idx += THREADS) {
     const int j = idx / TB_ROWS, l = idx - j * TB_ROWS;
     float v = 0.0f;
     if (j < Sb && l < cn) {
@@ -304,76 +308,71 @@ __global__ void __launch_bounds__(256) table_layer_bwd_tc_kernel(
     t = warp_sum(t);
     if (lane == 0 && t != 0.0f) atomicAdd(db + wrow_s[warp], t);
   }
-  float2 wj[S][NC], dwj[S][NC], colsum[NC];
+  const bool e_ok = e < E, st_ok = e < out_cols;
+  float2 wj[S], dwj[S], colsum = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int k = 0; k < NC; ++k) {
-    const int e = 2 * lane + 64 * k;
-    colsum[k] = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < S; ++j) {
-      dwj[j][k] = make_float2(0.f, 0.f);
-      wj[j][k] = (j < Sb && e < E) ? *reinterpret_cast<const float2*>(W + (long long)wrow_s[j] * ldw + e)
-                                   : make_float2(0.f, 0.f);
-    }
+  for (int j = 0; j < S; ++j) {
+    dwj[j] = make_float2(0.f, 0.f);
+    wj[j] = (j < Sb && e_ok) ? *reinterpret_cast<const float2*>(W + (long long)wrow_s[j] * ldw + e)
+                             : make_float2(0.f, 0.f);
   }
-  for (int l = warp; l < cn; l += 8) {
-    const __nv_bfloat16* hrow = hs + (r0 + l) * ldh;
-    __nv_bfloat16* drow = dZ + (r0 + l) * lddz;
-    float2 h[NC], prev[NC];
+  constexpr int UN = 4;  // rows in flight per warp
+  for (int l0 = rp; l0 < cn; l0 += TB_RP * UN) {
+    float2 h[UN], prev[UN];
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      const int e = 2 * lane + 64 * k;
-      h[k] = make_float2(0.f, 0.f);
-      prev[k] = make_float2(0.f, 0.f);
-      if (e < E) h[k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hrow + e));
-      if (accumulate && e < E) prev[k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(drow + e));
-    }
-    float dzl[S];
-#pragma unroll
-    for (int j = 0; j < S; ++j) dzl[j] = dz_s[j][l];
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      const int e = 2 * lane + 64 * k;
-      float ox = 0.f, oy = 0.f;
-#pragma unroll
-      for (int j = 0; j < S; ++j) {
-        ox = fmaf(dzl[j], wj[j][k].x, ox);
-        oy = fmaf(dzl[j], wj[j][k].y, oy);
-        dwj[j][k].x = fmaf(dzl[j], h[k].x, dwj[j][k].x);
-        dwj[j][k].y = fmaf(dzl[j], h[k].y, dwj[j][k].y);
+    for (int u = 0; u < UN; ++u) {
+      const int l = l0 + TB_RP * u;
+      h[u] = make_float2(0.f, 0.f);
+      prev[u] = make_float2(0.f, 0.f);
+      if (l < cn && e_ok) {
+        h[u] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hs + (r0 + l) * ldh + e));
+        if (accumulate) prev[u] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dZ + (r0 + l) * lddz + e));
       }
-      ox *= h[k].x * (1.0f - h[k].x);
-      oy *= h[k].y * (1.0f - h[k].y);
-      colsum[k].x += ox;
-      colsum[k].y += oy;
-      if (e < out_cols) {  // columns E .. out_cols are the zero K-padding of the next GEMM (h = 0 there)
-        const __nv_bfloat162 o2 = __floats2bfloat162_rn(ox + prev[k].x, oy + prev[k].y);
-        *reinterpret_cast<__nv_bfloat162*>(drow + e) = o2;
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int l = l0 + TB_RP * u;
+      if (l < cn) {
+        float ox = 0.f, oy = 0.f;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          const float dzl = dz_s[j][l];
+          ox = fmaf(dzl, wj[j].x, ox);
+          oy = fmaf(dzl, wj[j].y, oy);
+          dwj[j].x = fmaf(dzl, h[u].x, dwj[j].x);
+          dwj[j].y = fmaf(dzl, h[u].y, dwj[j].y);
+        }
+        ox *= h[u].x * (1.0f - h[u].x);
+        oy *= h[u].y * (1.0f - h[u].y);
+        colsum.x += ox;
+        colsum.y += oy;
+        if (st_ok) {  // columns E .. out_cols are the zero K-padding of the next GEMM (h = 0 there)
+          const __nv_bfloat162 o2 = __floats2bfloat162_rn(ox + prev[u].x, oy + prev[u].y);
+          *reinterpret_cast<__nv_bfloat162*>(dZ + (r0 + l) * lddz + e) = o2;
+        }
       }
     }
   }
-  // block reductions: dbelow (column sums of dZ) and dW rows, then one atomic per block and column
-#pragma unroll
-  for (int k = 0; k < NC; ++k) *reinterpret_cast<float2*>(&red_s[warp][64 * k + 2 * lane]) = colsum[k];
+  // block reductions over the row phases: dbelow (column sums of dZ) and the dW rows, one atomic per column
+  *reinterpret_cast<float2*>(&red_s[rp][e]) = colsum;
   __syncthreads();
-  for (int e = threadIdx.x; e < E; e += 256) {
+  for (int x = threadIdx.x; x < E; x += THREADS) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red_s[w][e];
-    if (dbelow != nullptr && t != 0.0f) atomicAdd(dbelow + e, t);
+    for (int r = 0; r < TB_RP; ++r) t += red_s[r][x];
+    if (dbelow != nullptr && t != 0.0f) atomicAdd(dbelow + x, t);
   }
 #pragma unroll
   for (int j = 0; j < S; ++j) {
     if (j >= Sb) break;
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < NC; ++k) *reinterpret_cast<float2*>(&red_s[warp][64 * k + 2 * lane]) = dwj[j][k];
+    *reinterpret_cast<float2*>(&red_s[rp][e]) = dwj[j];
     __syncthreads();
-    for (int e = threadIdx.x; e < E; e += 256) {
+    for (int x = threadIdx.x; x < E; x += THREADS) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += red_s[w][e];
-      if (t != 0.0f) atomicAdd(dW + (long long)wrow_s[j] * ldw + e, t);
+      for (int r = 0; r < TB_RP; ++r) t += red_s[r][x];
+      if (t != 0.0f) atomicAdd(dW + (long long)wrow_s[j] * ldw + x, t);
     }
   }
 }
@@ -480,7 +479,9 @@ extern "C" int dfol_pair_hidden_fwd_tc(const float* uv, int64_t lduv, const floa
                    (reinterpret_cast<uintptr_t>(obj_pos) % 16) == 0 && (reinterpret_cast<uintptr_t>(bias) % 16) == 0,
                "dfol_pair_hidden_fwd_tc: strides must be multiples of 4 and buffers 16-byte aligned");
   DFOL_REQUIRE(max_n >= 1, "dfol_pair_hidden_fwd_tc: empty batch");
-  dim3 grid((max_n + PF_TO - 1) / PF_TO, image_num);
+  // small work items (8 subjects x 32 objects) so that the grid is many waves deep: no tail on 148 SMs
+  const int ts = 8;
+  dim3 grid((max_n + PF_TO - 1) / PF_TO, image_num, (max_n + ts - 1) / ts);
   const size_t smem = (size_t)PF_TO * (H / 4) * sizeof(float4);
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(h_out);
@@ -490,7 +491,7 @@ extern "C" int dfol_pair_hidden_fwd_tc(const float* uv, int64_t lduv, const floa
     auto kern = pair_hidden_fwd_tc_kernel<G>;                                                                    \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
     kern<<<grid, 256, smem, st>>>(uv, lduv, obj_pos, ldpos, wg, ldw, bias, out, ldh, geo, pair_row, obj_row,    \
-                                  img_n);                                                                        \
+                                  img_n, ts);                                                                    \
   }
   switch (H / 128) {
     case 1: DFOL_PF_LAUNCH(1) break;
@@ -517,15 +518,15 @@ extern "C" int dfol_pair_hidden_bwd_tc(const void* dz, int64_t lddz, const void*
   const float4* gp = reinterpret_cast<const float4*>(geo);
   __nv_bfloat16* dup = reinterpret_cast<__nv_bfloat16*>(du_out);
   __nv_bfloat16* dvp = reinterpret_cast<__nv_bfloat16*>(dv_out);
-#define DFOL_PB_LAUNCH(NI)                                                                                        \
-  pair_hidden_bwd_tc_kernel<NI><<<grid, 256, 0, st>>>(dzp, lddz, gp, dup, dvp, ldo, dwg, ldw, dbias, pair_row,    \
-                                                      obj_row, img_n)
-  const int ni = (max_n + 7) / 8;
-  if (ni <= 4) DFOL_PB_LAUNCH(4);
-  else if (ni <= 6) DFOL_PB_LAUNCH(6);
-  else if (ni <= 8) DFOL_PB_LAUNCH(8);
-  else if (ni <= 13) DFOL_PB_LAUNCH(13);
-  else DFOL_PB_LAUNCH(16);
+#define DFOL_PB_LAUNCH(RG, NI)                                                                                \
+  pair_hidden_bwd_tc_kernel<RG, NI><<<grid, 32 * RG, 0, st>>>(dzp, lddz, gp, dup, dvp, ldo, dwg, ldw, dbias,   \
+                                                              pair_row, obj_row, img_n)
+  // 4 row groups (128 threads) for small images: H/64 * B blocks of 128 threads fit the GPU in one wave
+  if (max_n <= 32) DFOL_PB_LAUNCH(4, 8);
+  else if (max_n <= 48) DFOL_PB_LAUNCH(4, 12);
+  else if (max_n <= 64) DFOL_PB_LAUNCH(8, 8);
+  else if (max_n <= 104) DFOL_PB_LAUNCH(8, 13);
+  else DFOL_PB_LAUNCH(8, 16);
 #undef DFOL_PB_LAUNCH
   return finish_launch("dfol_pair_hidden_bwd_tc");
 }
@@ -554,7 +555,7 @@ extern "C" int dfol_table_layer_bwd_tc(const float* g, const int32_t* slice_goff
     const int left = max_slices - first;
     const int acc = first > 0 ? 1 : 0;
 #define DFOL_TB_LAUNCH(S)                                                                                           \
-  table_layer_bwd_tc_kernel<S, 5><<<grid, 256, 0, st>>>(g, slice_goff, slice_col, slice_wrow, img_slice, first, acc, \
+  table_layer_bwd_tc_kernel<S, 5><<<grid, 320, 0, st>>>(g, slice_goff, slice_col, slice_wrow, img_slice, first, acc, \
                                                         ll, blk, stride, row0, img_rows, W, ldw, hp, ldh, E, dzp,    \
                                                         lddz, out_cols, dW, db, dbelow)
     if (left <= 1) DFOL_TB_LAUNCH(1);
