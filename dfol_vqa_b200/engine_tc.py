@@ -187,21 +187,37 @@ class TensorCorePath(object):
         call('dfol_pair_hidden_fwd_tc', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo, ptr(first.weight[:, 2 * ldo:]),
              first.weight.stride(0), ptr(first.bias), ptr(h1r), p['Hp'], H, ptr(geo), ptr(layout.pair_row),
              ptr(layout.obj_row), ptr(layout.img_n), layout.B, layout.max_n, st)
-        h2r = bf(layout.P, p['Ep'])
-        self._tc(h1r, ops.wr2, h2r, E, p['Hp'], w.rel[1].bias, K.ACT_SIGMOID, st)
-        if cp is not None and cp.img_slot is not None:
-            # demand-driven: only the relation columns this batch's programs read, in the compact slot layout
+        # the activation of layer 2 is only materialised when the backward pass (or the dense table) needs it
+        slots = cp is not None and cp.img_slot is not None
+        h2r = bf(layout.P, p['Ep']) if (training or not slots) else None
+        if slots:
             dc = self.engine.upload_programs(cp, dev)
             rel_ll = torch.empty(cp.rel_slot_size, device=dev, dtype=torch.float32)
-            if capi.trace is not None:
-                capi.next_meta = {'tag': 'rel_slots_fwd', 'bytes': 2.0 * layout.P * p['Ep'] * max(
-                    1, (cp.max_slots + 3) // 4) + 4.0 * cp.rel_slot_size}
-            call('dfol_rel_slots_fwd', ptr(h2r), p['Ep'], E, ptr(w.emb.weight), w.emb.weight.stride(0),
-                 ptr(w.emb.bias), ptr(dc['slot_wrow']), ptr(dc['img_slot']), cp.max_slots, ptr(dc['slot_blk']),
-                 ptr(layout.rel_stride), ptr(layout.pair_row), ptr(layout.img_nn), ptr(layout.img_n), layout.B,
-                 layout.max_n ** 2, DEFAULT_LL, ptr(rel_ll), st)
+            if training:
+                # the backward pass needs the layer-2 activation: GEMM with bf16 store, then the demand-driven
+                # relation columns from the stored activation
+                self._tc(h1r, ops.wr2, h2r, E, p['Hp'], w.rel[1].bias, K.ACT_SIGMOID, st)
+                if capi.trace is not None:
+                    capi.next_meta = {'tag': 'rel_slots_fwd', 'bytes': 2.0 * layout.P * p['Ep'] * max(
+                        1, (cp.max_slots + 3) // 4) + 4.0 * cp.rel_slot_size}
+                call('dfol_rel_slots_fwd', ptr(h2r), p['Ep'], E, ptr(w.emb.weight), w.emb.weight.stride(0),
+                     ptr(w.emb.bias), ptr(dc['slot_wrow']), ptr(dc['img_slot']), cp.max_slots, ptr(dc['slot_blk']),
+                     ptr(layout.rel_stride), ptr(layout.pair_row), ptr(layout.img_nn), ptr(layout.img_n), layout.B,
+                     layout.max_n ** 2, DEFAULT_LL, ptr(rel_ll), st)
+            else:
+                # inference: layer 2 + relation columns in one persistent tcgen05 kernel; the P x E activation is
+                # consumed in registers and never written
+                if capi.trace is not None:
+                    capi.next_meta = {'tag': 'pair_layer_fwd_tc[%dx%dx%d]+slots' % (layout.P, E, p['Hp']),
+                                      'flops': 2.0 * layout.P * E * p['Hp']}
+                call('dfol_pair_layer_fwd_tc', ptr(h1r), p['Hp'], ptr(ops.wr2), p['Hp'], None, p['Ep'], p['Ep'],
+                     ptr(w.rel[1].bias), layout.P, E, p['Hp'], K.ACT_SIGMOID, ptr(w.emb.weight),
+                     w.emb.weight.stride(0), ptr(w.emb.bias), ptr(dc['slot_wrow']), ptr(dc['img_slot']),
+                     cp.max_slots, ptr(dc['slot_blk']), ptr(layout.rel_stride), ptr(layout.pair_img),
+                     ptr(layout.pair_row), ptr(layout.img_n), DEFAULT_LL, ptr(rel_ll), st)
             sc.rel_blk, sc.rel_slots = dc['slot_blk'], True
         else:
+            self._tc(h1r, ops.wr2, h2r, E, p['Hp'], w.rel[1].bias, K.ACT_SIGMOID, st)
             ridx = self.engine.rel_index(dev)
             sc.w_rel = w.emb.weight.detach().index_select(0, ridx).contiguous()
             sc.b_rel = w.emb.bias.detach().index_select(0, ridx).contiguous()
@@ -306,7 +322,10 @@ class TensorCorePath(object):
             h1r = scene.rel_h[0]
             self._wgrad(dz2r, E, h1r, H, G(r1.weight), st)
             dz1r = torch.empty(P, Hp, device=dev, dtype=torch.bfloat16)
-            self._dgrad(dz2r, ops.wr2t, dz1r, H, Ep, h1r, K.MUL_ELU_GRAD, st)
+            if capi.trace is not None:
+                capi.next_meta = {'tag': 'pair_layer_dgrad_tc[%dx%dx%d]' % (P, H, Ep), 'flops': 2.0 * P * H * Ep}
+            call('dfol_pair_layer_dgrad_tc', ptr(dz2r), Ep, ptr(ops.wr2t), Ep, ptr(dz1r), Hp, Hp, P, H, Ep, ptr(h1r),
+                 Hp, K.MUL_ELU_GRAD, st)
             gw1 = G(r0.weight)
             if capi.trace is not None:
                 capi.next_meta = {'tag': 'pair_hidden_bwd_tc', 'bytes': 2.0 * P * H + 16.0 * P}

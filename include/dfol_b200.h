@@ -100,6 +100,25 @@ int dfol_gemm_bf16_tc_wgrad(const void* A, int64_t lda, const void* B, int64_t l
 int dfol_cast_jobs(const void* jobs, int job_num, int64_t max_elements, void* stream);
 int dfol_cast_job_size(void);
 
+/* Persistent, weights-resident tensor-core GEMM for the pair-level layers of the relation network
+ * (RegularMLP over the (P, .) pair matrix, gqa_interpreter_experiments.py:167; classifier_oracle.py:150-154).
+ * One CTA per SM keeps the whole weight matrix B[N,K] (N <= 320, K <= 320) in shared memory and streams the 128-row
+ * tiles of A through a TMA ring; accumulators live in TMEM (double buffered when N <= 256).
+ * dfol_pair_layer_fwd_tc: C = act(A.B^T + bias) stored as bf16 (C == NULL: not stored), columns N <= n < store_cols
+ *   zero.  If slot_wrow != NULL (act must be sigmoid) the epilogue also evaluates the demand-driven relation
+ *   columns of dfol_rel_slots_fwd from the fp32 activations while they are in registers:
+ *   ll[slot_blk[b] + k*rel_stride[b] + l] = logsigmoid(C[m,:] . W_emb[wrow,:] + b_emb[wrow]), b = row_img[m],
+ *   l = m - img_row[b], self pairs = diag_value.
+ * dfol_pair_layer_dgrad_tc: same contract as dfol_gemm_bf16_tc_dgrad. */
+int dfol_pair_layer_fwd_tc(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int store_cols,
+                           const float* bias, int M, int N, int K, int act, const float* W_emb, int64_t ldw,
+                           const float* b_emb, const int32_t* slot_wrow, const int32_t* img_slot, int max_slots,
+                           const int64_t* slot_blk, const int32_t* rel_stride, const int32_t* row_img,
+                           const int32_t* img_row, const int32_t* img_n, float diag_value, float* ll, void* stream);
+int dfol_pair_layer_dgrad_tc(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX, int64_t lddx,
+                             int store_cols, int M, int N, int K, const void* h_saved, int64_t ldh, int mul_mode,
+                             void* stream);
+
 /* fp32 -> bf16 cast with row padding: dst[r*ldd + c] = bf16(src[r*lds + c]) for c < cols, 0 for cols <= c < ldd */
 int dfol_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 

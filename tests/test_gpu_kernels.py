@@ -292,3 +292,101 @@ def test_bf16_mode_training_gradients(terminal):
         scale = float(g_ref.abs().max())
         err = float((step.grads[id(p)].cpu() - g_ref).abs().max())
         assert err <= 6e-2 * scale + 1e-6, (k, err, scale)
+
+
+@pytest.mark.parametrize('M,N,K,act', [(1000, 300, 256, 2), (4608 + 77, 300, 256, 2), (300, 256, 320, 1), (129, 64, 64, 0)])
+def test_pair_layer_fwd_resident_gemm(M, N, K, act):
+    """Persistent weights-resident tcgen05 GEMM (no slots): bf16 output with zero K-padding vs fp64."""
+    from dfol_vqa_b200.capi import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
+    b = torch.randn(N, generator=g).cuda()
+    ldc = (N + 63) // 64 * 64
+    C = torch.full((M, ldc), float('nan'), device='cuda', dtype=torch.bfloat16)
+    call('dfol_pair_layer_fwd_tc', ptr(A), K, ptr(W), K, ptr(C), ldc, ldc, ptr(b), M, N, K, act, None, 0, None, None,
+         None, 0, None, None, None, None, None, 0.0, None, stream_ptr())
+    torch.cuda.synchronize()
+    z = A.double() @ W.double().t() + b.double()
+    ref = {0: z, 1: torch.nn.functional.elu(z), 2: torch.sigmoid(z)}[act]
+    assert torch.allclose(C[:, :N].double(), ref, rtol=1.5e-2, atol=1.5e-2), (C[:, :N].double() - ref).abs().max()
+    assert bool((C[:, N:] == 0).all())
+
+
+@pytest.mark.parametrize('counts,slots_per_image', [([5, 12, 3, 9, 16], [1, 0, 2, 4, 3]), ([48] * 6, [2, 1, 9, 0, 5, 4])])
+@pytest.mark.parametrize('store', [True, False])
+def test_pair_layer_fwd_slot_epilogue(counts, slots_per_image, store):
+    """Layer-2 GEMM + demand-driven relation columns in the epilogue vs an fp64 evaluation from the same bf16
+    operands; also checks the stand-alone dfol_rel_slots_fwd kernel on the stored activation."""
+    from dfol_vqa_b200.capi import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(sum(counts))
+    K, E, C = 256, 300, 500
+    n = torch.tensor(counts)
+    P = int((n * n).sum())
+    A = (torch.randn(P, K, generator=g) * 0.5).cuda().bfloat16()
+    W2 = (torch.randn(E, K, generator=g) / K ** 0.5).cuda().bfloat16()
+    b2 = torch.randn(E, generator=g).cuda()
+    We = (torch.randn(C, E, generator=g) * 0.3).cuda()
+    be = torch.randn(C, generator=g).cuda()
+    stride = (n * n + 3) // 4 * 4
+    img_slot = torch.tensor([0] + list(torch.tensor(slots_per_image).cumsum(0)), dtype=torch.int32)
+    total_slots = int(img_slot[-1])
+    slot_wrow = torch.randint(0, C, (max(total_slots, 1),), generator=g, dtype=torch.int32)
+    blk = torch.tensor([0] + list((torch.tensor(slots_per_image) * stride).cumsum(0)), dtype=torch.int64)
+    size = int(blk[-1])
+    pair_row = torch.tensor([0] + list((n * n).cumsum(0)), dtype=torch.int32)
+    row_img = torch.repeat_interleave(torch.arange(len(counts), dtype=torch.int32), n * n)
+    dev = lambda t: t.cuda()
+    d = dict(slot_wrow=dev(slot_wrow), img_slot=dev(img_slot), blk=dev(blk[:-1].contiguous()),
+             stride=dev(stride.int()), row_img=dev(row_img), pair_row=dev(pair_row), img_n=dev(n.int()),
+             img_nn=dev((n * n).int()))
+    ldc = 320
+    H2 = torch.full((P, ldc), float('nan'), device='cuda', dtype=torch.bfloat16) if store else None
+    ll = torch.full((max(size, 1),), float('nan'), device='cuda')
+    call('dfol_pair_layer_fwd_tc', ptr(A), K, ptr(W2), K, ptr(H2), ldc, ldc, ptr(b2), P, E, K, 2, ptr(We), E, ptr(be),
+         ptr(d['slot_wrow']), ptr(d['img_slot']), max(slots_per_image), ptr(d['blk']), ptr(d['stride']),
+         ptr(d['row_img']), ptr(d['pair_row']), ptr(d['img_n']), -30.0, ptr(ll), stream_ptr())
+    torch.cuda.synchronize()
+    h2 = torch.sigmoid(A.double() @ W2.double().t() + b2.double())
+    ref = torch.full((max(size, 1),), float('nan'), dtype=torch.float64)
+    h2c = h2.cpu()
+    for b_i, nb in enumerate(counts):
+        rows = h2c[int(pair_row[b_i]):int(pair_row[b_i + 1])]
+        for k in range(slots_per_image[b_i]):
+            wr = int(slot_wrow[int(img_slot[b_i]) + k])
+            z = torch.nn.functional.logsigmoid(rows @ We[wr].double().cpu() + be[wr].double().cpu())
+            z = z.view(nb, nb).clone()
+            z.fill_diagonal_(-30.0)
+            o = int(blk[b_i]) + k * int(stride[b_i])
+            ref[o:o + nb * nb] = z.reshape(-1)
+    mask = ~torch.isnan(ref)
+    got = ll.double().cpu()
+    assert torch.allclose(got[mask], ref[mask], rtol=2e-2, atol=2e-2), (got[mask] - ref[mask]).abs().max()
+    if store:
+        assert torch.allclose(H2[:, :E].double(), h2, rtol=1.5e-2, atol=1.5e-2)
+        assert bool((H2[:, E:] == 0).all())
+        ll2 = torch.full_like(ll, float('nan'))
+        call('dfol_rel_slots_fwd', ptr(H2), ldc, E, ptr(We), E, ptr(be), ptr(d['slot_wrow']), ptr(d['img_slot']),
+             max(slots_per_image), ptr(d['blk']), ptr(d['stride']), ptr(d['pair_row']), ptr(d['img_nn']),
+             ptr(d['img_n']), len(counts), max(counts) ** 2, -30.0, ptr(ll2), stream_ptr())
+        torch.cuda.synchronize()
+        got2 = ll2.double().cpu()
+        assert torch.allclose(got2[mask], ref[mask], rtol=2e-2, atol=2e-2), (got2[mask] - ref[mask]).abs().max()
+
+
+@pytest.mark.parametrize('M,N,K', [(1000, 256, 320), (4608 + 5, 256, 320), (300, 64, 64)])
+@pytest.mark.parametrize('mode', [0, 2])
+def test_pair_layer_dgrad_resident_gemm(M, N, K, mode):
+    from dfol_vqa_b200.capi import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(M + mode)
+    dZ = (torch.randn(M, K, generator=g)).cuda().bfloat16()
+    Wt = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
+    Hs = (torch.rand(M, N, generator=g) - 0.3).cuda().bfloat16()
+    dX = torch.full((M, N), float('nan'), device='cuda', dtype=torch.bfloat16)
+    call('dfol_pair_layer_dgrad_tc', ptr(dZ), K, ptr(Wt), K, ptr(dX), N, 0, M, N, K, ptr(Hs), N, mode, stream_ptr())
+    torch.cuda.synchronize()
+    ref = dZ.double() @ Wt.double().t()
+    h = Hs.double()
+    if mode == 2:
+        ref = ref * torch.where(h > 0, torch.ones_like(h), h + 1)
+    assert torch.allclose(dX.double(), ref, rtol=1.5e-2, atol=1.5e-2), (dX.double() - ref).abs().max()
