@@ -50,6 +50,8 @@ _SIGNATURES = {
     'dfol_act_grad_mul': (c_int, [P, c_int64, P, c_int64, c_int64, c_int, c_int, P]),
     'dfol_program_fwd': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_int, P]),
     'dfol_program_bwd': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_int, P, P, P]),
+    'dfol_program_fwd_fast': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_int, P]),
+    'dfol_program_bwd_fast': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_int, P, P, P]),
     'dfol_loss_fwd_bwd': (c_int, [P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
     'dfol_table_layer_bwd': (c_int, [P, P, P, P, P, c_int, P, P, P, P, P, P, c_int64, P, c_int64, c_int, P,
                                      c_int64, P, P, P]),

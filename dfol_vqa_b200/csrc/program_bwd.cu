@@ -32,7 +32,7 @@ __device__ __forceinline__ void bwd_option_denominators(const Image& im, const i
 #pragma unroll
     for (int j = 0; j < NCHUNK; ++j) {
       const int t = lane + 32 * j;
-      if (t < im.n) acc[j] += expf(attr_raw(im, col, t));
+      if (t < im.n) acc[j] += DFOL_EXPF(attr_raw(im, col, t));
     }
   }
   reduce_columns(acc, im.n, den, sc, false);
@@ -58,7 +58,7 @@ __device__ __forceinline__ void attr_softmax_correction(const Image& im, const i
       if (t < im.n) {
         const float d = den[t];
         const float inv = (d >= kLogEps) ? 1.0f / d : 0.0f;
-        gslice[(long long)k * im.astride + t] -= tot[t] * expf(attr_raw(im, col, t)) * inv;
+        gslice[(long long)k * im.astride + t] -= tot[t] * DFOL_EXPF(attr_raw(im, col, t)) * inv;
       }
     }
   }
@@ -110,13 +110,17 @@ __device__ __forceinline__ void relate_backward(int n, const LL& L, const float*
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
+static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
     const int32_t* __restrict__ instr, const int32_t* __restrict__ q_instr, const int32_t* __restrict__ opts,
     const float* __restrict__ attr_ll, const int64_t* __restrict__ attr_blk, const int32_t* __restrict__ attr_stride,
     const float* __restrict__ rel_ll, const int64_t* __restrict__ rel_blk, const int32_t* __restrict__ rel_stride,
     const int32_t* __restrict__ img_n, const float* __restrict__ d_lp, const float* __restrict__ tape,
-    int tape_stride, float* __restrict__ g_attr, float* __restrict__ g_rel) {
-  __shared__ BwdShared sm;
+    int tape_stride, float* __restrict__ g_attr, float* __restrict__ g_rel
+#ifdef DFOL_PROGRAM_FAST
+    , int ring_nbuf, int ring_tile_floats
+#endif
+    ) {
+  __shared__ __align__(16) BwdShared sm;
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Image im;
@@ -129,6 +133,36 @@ __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
   const int ip0 = q_instr[q], ip1 = q_instr[q + 1];
 
   if (tid < MAXN) { sm.g[tid] = 0.f; sm.gs[tid] = 0.f; sm.saved[tid] = 0.f; sm.cur[tid] = 0.f; }
+#ifdef DFOL_PROGRAM_FAST
+  // relate tiles of this program, streamed through the shared-memory ring in REVERSE execution order
+  extern __shared__ __align__(128) float ring_mem[];
+  __shared__ __align__(8) uint64_t ring_full[8];
+  __shared__ int rel_ip[MAX_REL];
+  __shared__ int rel_count;
+  TileRing ring{ring_mem, ring_nbuf, ring_tile_floats, ring_full};
+  auto issue_tile = [&](int j) {  // elected thread: tile of the j-th relate counted from the END -> slot j % nbuf
+    const int col = instr[(long long)rel_ip[rel_count - 1 - j] * DFOL_INSTR_WORDS + DFOL_I_A0];
+    const int b = j % ring.nbuf;
+    const uint32_t bytes = (uint32_t)im.rstride * 4u;
+    mbar_expect_tx(&ring.full[b], bytes);
+    bulk_load(ring.buf + (size_t)b * ring.tile_floats, im.rel + (long long)col * im.rstride, bytes, &ring.full[b]);
+  };
+  if (tid == 0) {
+    int c = 0;
+    for (int ip = ip0; ip < ip1 && c < MAX_REL; ++ip)
+      if (instr[(long long)ip * DFOL_INSTR_WORDS + DFOL_I_OP] == DFOL_OP_RELATE) rel_ip[c++] = ip;
+    rel_count = c;
+    for (int b = 0; b < ring.nbuf; ++b) mbar_init(&ring.full[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int j = 0; j < c && j < ring.nbuf; ++j) issue_tile(j);
+  }
+  __syncthreads();
+  // relates beyond the ring capacity (the LAST ones in execution order, met first here) use direct loads
+  int total_rel = 0;
+  for (int ip = ip0; ip < ip1; ++ip)
+    total_rel += instr[(long long)ip * DFOL_INSTR_WORDS + DFOL_I_OP] == DFOL_OP_RELATE;
+  int rel_seen = 0;  // relates met so far walking backwards
+#endif
   // the first branch's final attention is the tape row of the PUSH instruction
   for (int ip = ip0; ip < ip1; ++ip)
     if (instr[(long long)ip * DFOL_INSTR_WORDS + DFOL_I_OP] == DFOL_OP_PUSH && tid < n)
@@ -165,12 +199,27 @@ __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
           sm.tmp[tid] = 0.f;
         }
         __syncthreads();
-        RelOption L{&im, nullptr, 1, 0, false, rt, I.a0, neg};
         const bool subj = I.flags & DFOL_F_SUBJECT;
         const float* a_s = subj ? sm.nw : sm.cur;
         const float* a_o = subj ? sm.cur : sm.nw;
-        relate_forward(n, L, a_s, a_o, subj, sm.res, sm.inner, sm.sc);
-        relate_backward(n, L, a_s, a_o, subj, sm.dres, sm.inner, sm.tmp, g_rel + I.gr, sm.sc);
+#ifdef DFOL_PROGRAM_FAST
+        const int j = rel_seen - (total_rel - rel_count);  // position among the ring-served relates, from the end
+        ++rel_seen;
+        if (j >= 0) {
+          const int b = j % ring.nbuf;
+          mbar_wait(&ring.full[b], (uint32_t)(j / ring.nbuf) & 1u);
+          const float* tile = ring.buf + (size_t)b * ring.tile_floats;
+          relate_forward_tile(n, tile, neg, rt, a_s, a_o, subj, sm.res, sm.inner, sm.den, sm.sc);
+          relate_backward_tile(n, tile, neg, rt, a_s, subj, sm.dres, sm.inner, sm.den, sm.tot, sm.tmp, g_rel + I.gr,
+                               sm.sc);
+          if (tid == 0 && j + ring.nbuf < rel_count) issue_tile(j + ring.nbuf);
+        } else
+#endif
+        {
+          RelOption L{&im, nullptr, 1, 0, false, rt, I.a0, neg};
+          relate_forward(n, L, a_s, a_o, subj, sm.res, sm.inner, sm.sc);
+          relate_backward(n, L, a_s, a_o, subj, sm.dres, sm.inner, sm.tmp, g_rel + I.gr, sm.sc);
+        }
         if (tid < n) {
           // the kept role's own prior is the new object: its gradient feeds the name select
           if (I.a1 >= 0) g_attr[I.ga1 + tid] = sm.dres[tid] * post_ll_grad(attr_raw(im, I.a1, tid), nneg, nrt);
@@ -195,7 +244,7 @@ __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
         const float dlp = d_lp[I.out];
         float de1 = dlp, de2 = dlp;
         if (I.op == DFOL_OP_OR) {
-          const float E1 = expf(e1), E2 = expf(e2);
+          const float E1 = DFOL_EXPF(e1), E2 = DFOL_EXPF(e2);
           const float v = 1.0f - (1.0f - E1) * (1.0f - E2);
           const float dv = (v >= kLogEps) ? dlp / v : 0.0f;
           de1 = dv * (1.0f - E2) * E1;
@@ -358,15 +407,15 @@ __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
         const float e1 = exists_block(sm.res, n, false, sm.sc, &S1);
         const float e2 = exists_block(sm.nw, n, false, sm.sc, &S2);
         const float mx = fmaxf(e1, e2);
-        const float lse = logf(expf(e1 - mx) + expf(e2 - mx));
+        const float lse = DFOL_LOGF(DFOL_EXPF(e1 - mx) + DFOL_EXPF(e2 - mx));
         const float z1 = e1 - mx - lse, z2 = e2 - mx - lse;
         const float alpha = (I.flags & DFOL_F_IS_LESS) ? 1.0f : 0.0f;
         const float c = 1.0f - 2.0f * alpha;
-        const float v1 = alpha + c * expf(z1), v2 = alpha + c * expf(z2);
-        const float dz1 = (v1 >= kLogEps) ? d_lp[I.out] * c * expf(z1) / v1 : 0.0f;
-        const float dz2 = (v2 >= kLogEps) ? d_lp[I.out + 1] * c * expf(z2) / v2 : 0.0f;
-        const float de1 = dz1 - expf(z1) * (dz1 + dz2);
-        const float de2 = dz2 - expf(z2) * (dz1 + dz2);
+        const float v1 = alpha + c * DFOL_EXPF(z1), v2 = alpha + c * DFOL_EXPF(z2);
+        const float dz1 = (v1 >= kLogEps) ? d_lp[I.out] * c * DFOL_EXPF(z1) / v1 : 0.0f;
+        const float dz2 = (v2 >= kLogEps) ? d_lp[I.out + 1] * c * DFOL_EXPF(z2) / v2 : 0.0f;
+        const float de1 = dz1 - DFOL_EXPF(z1) * (dz1 + dz2);
+        const float de2 = dz2 - DFOL_EXPF(z2) * (dz1 + dz2);
         if (tid < n) {
           const float dx1 = de1 * lnot_grad(S1) * lnot_grad(sm.res[tid]);
           const float dx2 = de2 * lnot_grad(S2) * lnot_grad(sm.nw[tid]);
@@ -411,12 +460,12 @@ __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
             if (s == o) continue;
             float den = 0.f, tot = 0.f;
             for (int j = 0; j < I.a1; ++j) {
-              den += expf(rel_raw(im, op[j] & ~DFOL_OPT_NEG, s, o));
+              den += DFOL_EXPF(rel_raw(im, op[j] & ~DFOL_OPT_NEG, s, o));
               tot += gs[(long long)j * im.rstride + e];
             }
             const float inv = (den >= kLogEps) ? 1.0f / den : 0.0f;
             for (int j = 0; j < I.a1; ++j)
-              gs[(long long)j * im.rstride + e] -= tot * expf(rel_raw(im, op[j] & ~DFOL_OPT_NEG, s, o)) * inv;
+              gs[(long long)j * im.rstride + e] -= tot * DFOL_EXPF(rel_raw(im, op[j] & ~DFOL_OPT_NEG, s, o)) * inv;
           }
         }
         __syncthreads();
@@ -437,17 +486,36 @@ __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
 
 using namespace dfol;
 
-extern "C" int dfol_program_bwd(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
-                                const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
-                                const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride,
-                                const int32_t* img_n, const float* d_lp, const float* tape, int tape_stride,
-                                float* g_attr, float* g_rel, void* stream) {
+#ifdef DFOL_PROGRAM_FAST
+#define DFOL_PROGRAM_BWD_ENTRY dfol_program_bwd_fast
+#else
+#define DFOL_PROGRAM_BWD_ENTRY dfol_program_bwd
+#endif
+
+extern "C" int DFOL_PROGRAM_BWD_ENTRY(const int32_t* instr, const int32_t* q_instr, const int32_t* opts,
+                                      int question_num, const float* attr_ll, const int64_t* attr_blk,
+                                      const int32_t* attr_stride, const float* rel_ll, const int64_t* rel_blk,
+                                      const int32_t* rel_stride, const int32_t* img_n, const float* d_lp,
+                                      const float* tape, int tape_stride, float* g_attr, float* g_rel, void* stream) {
   DFOL_REQUIRE(instr && q_instr && attr_ll && attr_blk && attr_stride && rel_ll && rel_blk && rel_stride && img_n &&
                    d_lp && tape && g_attr && g_rel,
                "dfol_program_bwd: null pointer");
   if (question_num == 0) return 0;
+#ifdef DFOL_PROGRAM_FAST
+  DFOL_REQUIRE(tape_stride >= 1 && tape_stride <= MAXN, "dfol_program_bwd_fast: tape_stride = max objects rounded to 4");
+  const int tile_floats = (tape_stride * tape_stride + 31) / 32 * 32;
+  int nbuf = (96 * 1024) / (tile_floats * 4);
+  nbuf = nbuf < 1 ? 1 : (nbuf > 4 ? 4 : nbuf);
+  const size_t smem = (size_t)nbuf * tile_floats * 4;
+  cudaFuncSetAttribute(program_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  program_bwd_kernel<<<question_num, PROG_THREADS, smem, (cudaStream_t)stream>>>(
+      instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, d_lp, tape,
+      tape_stride, g_attr, g_rel, nbuf, tile_floats);
+  return finish_launch("dfol_program_bwd_fast");
+#else
   program_bwd_kernel<<<question_num, PROG_THREADS, 0, (cudaStream_t)stream>>>(
       instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, d_lp, tape,
       tape_stride, g_attr, g_rel);
   return finish_launch("dfol_program_bwd");
+#endif
 }

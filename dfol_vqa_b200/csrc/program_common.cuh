@@ -14,7 +14,7 @@ struct Instr {
   int op, flags, a0, a1, a2, out, ga0, ga1, gr;
 };
 
-__device__ __forceinline__ Instr load_instr(const int32_t* __restrict__ instr, int ip) {
+__device__ __forceinline__ Instr load_instr(const int32_t* instr, int ip) {
   const int32_t* w = instr + (long long)ip * DFOL_INSTR_WORDS;
   Instr I;
   I.op = w[DFOL_I_OP]; I.flags = w[DFOL_I_FLAGS]; I.a0 = w[DFOL_I_A0]; I.a1 = w[DFOL_I_A1]; I.a2 = w[DFOL_I_A2];
@@ -56,7 +56,7 @@ __device__ __forceinline__ float post_ll_grad(float raw, bool neg, bool rt) {
 
 struct BlockScratch {
   float red[PROG_WARPS];
-  float colacc[PROG_WARPS][MAXN];
+  __align__(16) float colacc[PROG_WARPS][MAXN];
 };
 
 // Sum over all threads of the block; every thread gets the result. Deterministic order.
@@ -125,7 +125,7 @@ struct RelOption {
     const float r = rel_raw(*im, opts[k] & ~DFOL_OPT_NEG, s, o);
     if (!normalise) return r;
     float den = 0.f;
-    for (int j = 0; j < count; ++j) den += expf(rel_raw(*im, opts[j] & ~DFOL_OPT_NEG, s, o));
+    for (int j = 0; j < count; ++j) den += DFOL_EXPF(rel_raw(*im, opts[j] & ~DFOL_OPT_NEG, s, o));
     return r - slog(den);
   }
   __device__ __forceinline__ bool neg() const {
@@ -169,5 +169,265 @@ __device__ __forceinline__ void relate_forward(int n, const LL& L, const float* 
   }
   __syncthreads();
 }
+
+#ifdef DFOL_PROGRAM_FAST
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-core-mode interpreter: the N x N relation tile of every relate hop is streamed into shared memory by a
+// bulk-async copy (one elected thread, mbarrier completion) through a ring of tile buffers, so the tile of hop h+1 ..
+// h+nbuf-1 is in flight while hop h computes: the table loads never sit on the dependent chain of the attention
+// vector.  The hop itself is evaluated in probability space,
+//   res[s] = a[s] + slog(1 - prod_{o != s} max(1 - e^{ll[s,o]} e^{a'[o]}, eps))
+// (one MUFU.EX2 per pair instead of an exp and a log; identical to sum_o slog(1 - e^{ll+a'}) up to fp32 rounding).
+constexpr int MAX_CODE = 48;  // instructions per program staged in shared memory
+constexpr int MAX_REL = 64;  // relate hops per program served by the ring (longer programs fall back to direct loads)
+
+struct TileRing {
+  float* buf;
+  int nbuf, tile_floats;
+  uint64_t* full;
+};
+
+// post-processed likelihood of a raw tile entry and its derivative w.r.t. the raw entry
+__device__ __forceinline__ float tile_post(float raw, bool neg, bool rt) {
+  const float c = fminf(raw, 0.0f);
+  return neg ? lnot(c) : (rt ? roundtrip(c) : c);
+}
+
+// t = max(1 - e^{post(raw)} * e_other, eps) for the four pairs of one float4 of a tile row
+__device__ __forceinline__ float4 tile_terms(float4 r, float4 eo, bool neg, bool rt) {
+  float4 t;
+  t.x = fmaxf(1.0f - __expf(tile_post(r.x, neg, rt)) * eo.x, kLogEps);
+  t.y = fmaxf(1.0f - __expf(tile_post(r.y, neg, rt)) * eo.y, kLogEps);
+  t.z = fmaxf(1.0f - __expf(tile_post(r.z, neg, rt)) * eo.z, kLogEps);
+  t.w = fmaxf(1.0f - __expf(tile_post(r.w, neg, rt)) * eo.w, kLogEps);
+  return t;
+}
+
+// inner[] receives the products Q (NOT their logarithm); ea[] (n floats of scratch) the exponentials of the other
+// role's attention, both re-used by relate_backward_tile.
+// Fast path (n % 4 == 0): a warp owns a row, lane l the four objects 4l..4l+3 (one LDS.128 per row and lane); the
+// self pair needs no test unless the relation is negated: its raw entry is -30, so 1 - e^{-30} e^{a} == 1.0f.
+__device__ __forceinline__ void relate_forward_tile(int n, const float* __restrict__ tile, bool neg, bool rt,
+                                                    const float* a_subj, const float* a_obj, bool subject_role,
+                                                    float* res, float* inner, float* ea, BlockScratch& sc) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x < n) ea[threadIdx.x] = __expf(subject_role ? a_obj[threadIdx.x] : a_subj[threadIdx.x]);
+  __syncthreads();
+  if ((n & 3) == 0) {
+    const int o4 = 4 * lane;
+    const bool act = o4 < n;
+    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 eo = (act && subject_role) ? *reinterpret_cast<const float4*>(ea + o4) : one;
+    float4 acc = one;
+    if (!neg && !rt) {
+      // plain relation (the common case): raw <= 0 (log-sigmoid) so t = 1 - e^raw * e_other needs no clamp in
+      // the product (a zero factor gives slog(1 - 0) = 0 exactly as the clamped one does)
+      constexpr float kLog2e = 1.4426950408889634f;
+      for (int s = w; s < n; s += PROG_WARPS) {
+        float4 t = one;
+        if (act) {
+          const float4 r = *reinterpret_cast<const float4*>(tile + s * n + o4);
+          const float es = ea[s];
+          const float4 e = subject_role ? eo : make_float4(es, es, es, es);
+          t.x = fmaf(-exp2f(fminf(r.x, 0.f) * kLog2e), e.x, 1.0f);
+          t.y = fmaf(-exp2f(fminf(r.y, 0.f) * kLog2e), e.y, 1.0f);
+          t.z = fmaf(-exp2f(fminf(r.z, 0.f) * kLog2e), e.z, 1.0f);
+          t.w = fmaf(-exp2f(fminf(r.w, 0.f) * kLog2e), e.w, 1.0f);
+        }
+        if (subject_role) {
+          const float q = warp_prod((t.x * t.y) * (t.z * t.w));
+          if (lane == 0) { inner[s] = q; res[s] = a_subj[s] + slog(1.0f - q); }
+        } else {
+          acc.x *= t.x; acc.y *= t.y; acc.z *= t.z; acc.w *= t.w;
+        }
+      }
+    } else {
+      for (int s = w; s < n; s += PROG_WARPS) {
+        float4 t = one;
+        if (act) {
+          const float4 r = *reinterpret_cast<const float4*>(tile + s * n + o4);
+          const float es = ea[s];
+          t = tile_terms(r, subject_role ? eo : make_float4(es, es, es, es), neg, rt);
+          if (neg && (s >> 2) == lane) {  // negated relation: the self pair must be skipped explicitly
+            const int d = s & 3;
+            if (d == 0) t.x = 1.f; else if (d == 1) t.y = 1.f; else if (d == 2) t.z = 1.f; else t.w = 1.f;
+          }
+        }
+        if (subject_role) {
+          const float q = warp_prod((t.x * t.y) * (t.z * t.w));
+          if (lane == 0) { inner[s] = q; res[s] = a_subj[s] + slog(1.0f - q); }
+        } else {
+          acc.x *= t.x; acc.y *= t.y; acc.z *= t.z; acc.w *= t.w;
+        }
+      }
+    }
+    if (!subject_role) {
+      __syncthreads();
+      *reinterpret_cast<float4*>(&sc.colacc[w][o4]) = acc;
+      __syncthreads();
+      if (threadIdx.x < n) {
+        float q = 1.f;
+#pragma unroll
+        for (int i = 0; i < PROG_WARPS; ++i) q *= sc.colacc[i][threadIdx.x];
+        inner[threadIdx.x] = q;
+        res[threadIdx.x] = a_obj[threadIdx.x] + slog(1.0f - q);
+      }
+    }
+    __syncthreads();
+    return;
+  }
+  float acc[NCHUNK];
+#pragma unroll
+  for (int j = 0; j < NCHUNK; ++j) acc[j] = 1.f;
+  for (int s = w; s < n; s += PROG_WARPS) {
+    const float es = ea[s];
+    const float* row = tile + s * n;
+    float rowprod = 1.f;
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) {
+      const int o = lane + 32 * j;
+      if (o < n && o != s) {
+        const float p = __expf(tile_post(row[o], neg, rt)) * (subject_role ? ea[o] : es);
+        const float t = fmaxf(1.0f - p, kLogEps);
+        if (subject_role) rowprod *= t;
+        else acc[j] *= t;
+      }
+    }
+    if (subject_role) {
+      rowprod = warp_prod(rowprod);
+      if (lane == 0) { inner[s] = rowprod; res[s] = a_subj[s] + slog(1.0f - rowprod); }
+    }
+  }
+  if (!subject_role) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) sc.colacc[w][lane + 32 * j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < n) {
+      float q = 1.f;
+#pragma unroll
+      for (int i = 0; i < PROG_WARPS; ++i) q *= sc.colacc[i][threadIdx.x];
+      inner[threadIdx.x] = q;
+      res[threadIdx.x] = a_obj[threadIdx.x] + slog(1.0f - q);
+    }
+  }
+  __syncthreads();
+}
+
+// d slog(1 - Q) / d log Q given the product Q
+__device__ __forceinline__ float lnot_grad_q(float q) {
+  const float u = 1.0f - q;
+  return (u >= kLogEps) ? __fdividef(-q, u) : 0.0f;
+}
+
+// du/d(l+a) factor -p/(1-p) (zero where the clamp is active) of one pair, p = e^{post(raw)} * e_other
+__device__ __forceinline__ float tile_lgrad(float raw, float eo, bool neg, bool rt) {
+  const float p = __expf(tile_post(raw, neg, rt)) * eo;
+  const float u = 1.0f - p;
+  return (u >= kLogEps) ? __fdividef(-p, u) : 0.0f;
+}
+
+// Backward of relate_forward_tile (same contract as relate_backward); dq[] is n floats of scratch.
+__device__ __forceinline__ void relate_backward_tile(int n, const float* __restrict__ tile, bool neg, bool rt,
+                                                     const float* a_subj, bool subject_role, const float* dres,
+                                                     const float* inner, const float* ea, float* dq, float* g_other,
+                                                     float* __restrict__ gslice, BlockScratch& sc) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x < n) dq[threadIdx.x] = dres[threadIdx.x] * lnot_grad_q(inner[threadIdx.x]);
+  __syncthreads();
+  if ((n & 3) == 0) {
+    const int o4 = 4 * lane;
+    const bool act = o4 < n;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 eo = (act && subject_role) ? *reinterpret_cast<const float4*>(ea + o4) : zero;
+    const float4 dqo = (act && !subject_role) ? *reinterpret_cast<const float4*>(dq + o4) : zero;
+    float4 acc = zero;
+    for (int s = w; s < n; s += PROG_WARPS) {
+      float rowsum = 0.f;
+      if (act) {
+        const float4 r = *reinterpret_cast<const float4*>(tile + s * n + o4);
+        const float es = ea[s], dS_row = dq[s];
+        float4 du;
+        if (subject_role) {
+          du.x = dS_row * tile_lgrad(r.x, eo.x, neg, rt);
+          du.y = dS_row * tile_lgrad(r.y, eo.y, neg, rt);
+          du.z = dS_row * tile_lgrad(r.z, eo.z, neg, rt);
+          du.w = dS_row * tile_lgrad(r.w, eo.w, neg, rt);
+        } else {
+          du.x = dqo.x * tile_lgrad(r.x, es, neg, rt);
+          du.y = dqo.y * tile_lgrad(r.y, es, neg, rt);
+          du.z = dqo.z * tile_lgrad(r.z, es, neg, rt);
+          du.w = dqo.w * tile_lgrad(r.w, es, neg, rt);
+        }
+        if ((s >> 2) == lane) {  // self pair: no gradient
+          const int d = s & 3;
+          if (d == 0) du.x = 0.f; else if (d == 1) du.y = 0.f; else if (d == 2) du.z = 0.f; else du.w = 0.f;
+        }
+        if (subject_role) { acc.x += du.x; acc.y += du.y; acc.z += du.z; acc.w += du.w; }
+        else rowsum = (du.x + du.y) + (du.z + du.w);
+        float4 dn;
+        dn.x = du.x * post_ll_grad(r.x, neg, rt);
+        dn.y = du.y * post_ll_grad(r.y, neg, rt);
+        dn.z = du.z * post_ll_grad(r.z, neg, rt);
+        dn.w = du.w * post_ll_grad(r.w, neg, rt);
+        *reinterpret_cast<float4*>(gslice + s * n + o4) = dn;
+      }
+      if (!subject_role) {
+        rowsum = warp_sum(rowsum);
+        if (lane == 0) g_other[s] += rowsum;
+      }
+    }
+    if (subject_role) {
+      __syncthreads();
+      *reinterpret_cast<float4*>(&sc.colacc[w][o4]) = acc;
+      __syncthreads();
+      if (threadIdx.x < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < PROG_WARPS; ++i) t += sc.colacc[i][threadIdx.x];
+        g_other[threadIdx.x] += t;
+      }
+    }
+    __syncthreads();
+    return;
+  }
+  float acc[NCHUNK];
+#pragma unroll
+  for (int j = 0; j < NCHUNK; ++j) acc[j] = 0.f;
+  for (int s = w; s < n; s += PROG_WARPS) {
+    const float es = ea[s];
+    const float dS_row = dq[s];
+    const float* row = tile + s * n;
+    float rowsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) {
+      const int o = lane + 32 * j;
+      if (o < n) {
+        float dn = 0.0f;
+        if (o != s) {
+          const float raw = row[o];
+          const float lg = tile_lgrad(raw, subject_role ? ea[o] : es, neg, rt);
+          float du;
+          if (subject_role) {
+            du = dS_row * lg;
+            acc[j] += du;
+          } else {
+            du = dq[o] * lg;
+            rowsum += du;
+          }
+          dn = du * post_ll_grad(raw, neg, rt);
+        }
+        gslice[s * n + o] = dn;
+      }
+    }
+    if (!subject_role) {
+      rowsum = warp_sum(rowsum);
+      if (lane == 0) g_other[s] += rowsum;
+    }
+  }
+  if (subject_role) reduce_columns(acc, n, g_other, sc, true);
+  __syncthreads();
+}
+#endif  // DFOL_PROGRAM_FAST
 
 }  // namespace dfol

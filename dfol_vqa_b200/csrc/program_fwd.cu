@@ -35,7 +35,7 @@ __device__ __forceinline__ void option_denominators(const Image& im, const int32
 #pragma unroll
     for (int j = 0; j < NCHUNK; ++j) {
       const int t = lane + 32 * j;
-      if (t < im.n) acc[j] += expf(attr_raw(im, col, t));
+      if (t < im.n) acc[j] += DFOL_EXPF(attr_raw(im, col, t));
     }
   }
   reduce_columns(acc, im.n, den, sc, false);
@@ -67,12 +67,16 @@ __device__ __forceinline__ float warp_exists(const float x[NCHUNK], int n, bool 
   return lnot(s);
 }
 
-__global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
+static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
     const int32_t* __restrict__ instr, const int32_t* __restrict__ q_instr, const int32_t* __restrict__ opts,
     const float* __restrict__ attr_ll, const int64_t* __restrict__ attr_blk, const int32_t* __restrict__ attr_stride,
     const float* __restrict__ rel_ll, const int64_t* __restrict__ rel_blk, const int32_t* __restrict__ rel_stride,
-    const int32_t* __restrict__ img_n, float* __restrict__ lp_out, float* __restrict__ tape, int tape_stride) {
-  __shared__ FwdShared sm;
+    const int32_t* __restrict__ img_n, float* __restrict__ lp_out, float* __restrict__ tape, int tape_stride
+#ifdef DFOL_PROGRAM_FAST
+    , int ring_nbuf, int ring_tile_floats
+#endif
+    ) {
+  __shared__ __align__(16) FwdShared sm;
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Image im;
@@ -84,10 +88,45 @@ __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
   const int n = im.n;
 
   if (tid < MAXN) { sm.cur[tid] = 0.f; sm.saved[tid] = 0.f; }
+#ifdef DFOL_PROGRAM_FAST
+  // relate tiles of this program, in execution order, streamed through the shared-memory ring
+  extern __shared__ __align__(128) float ring_mem[];
+  __shared__ __align__(8) uint64_t ring_full[8];
+  __shared__ int rel_ip[MAX_REL];
+  __shared__ int rel_count;
+  TileRing ring{ring_mem, ring_nbuf, ring_tile_floats, ring_full};
+  auto issue_tile = [&](int k) {  // elected thread: tile of the k-th relate -> ring slot k % nbuf
+    const int col = instr[(long long)rel_ip[k] * DFOL_INSTR_WORDS + DFOL_I_A0];
+    const int b = k % ring.nbuf;
+    const uint32_t bytes = (uint32_t)im.rstride * 4u;
+    mbar_expect_tx(&ring.full[b], bytes);
+    bulk_load(ring.buf + (size_t)b * ring.tile_floats, im.rel + (long long)col * im.rstride, bytes, &ring.full[b]);
+  };
+  if (tid == 0) {
+    int c = 0;
+    for (int ip = q_instr[q]; ip < q_instr[q + 1] && c < MAX_REL; ++ip)
+      if (instr[(long long)ip * DFOL_INSTR_WORDS + DFOL_I_OP] == DFOL_OP_RELATE) rel_ip[c++] = ip;
+    rel_count = c;
+    for (int b = 0; b < ring.nbuf; ++b) mbar_init(&ring.full[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int k = 0; k < c && k < ring.nbuf; ++k) issue_tile(k);
+  }
+  int krel = 0;
+  // the question's bytecode is read once into shared memory: no global load on the per-instruction critical path
+  __shared__ int32_t code_s[MAX_CODE * DFOL_INSTR_WORDS];
+  const int ip_first = q_instr[q];
+  const int code_n = min(q_instr[q + 1] - ip_first, MAX_CODE);
+  for (int i = tid; i < code_n * DFOL_INSTR_WORDS; i += PROG_THREADS)
+    code_s[i] = instr[(long long)ip_first * DFOL_INSTR_WORDS + i];
+#endif
   __syncthreads();
 
   for (int ip = q_instr[q]; ip < q_instr[q + 1]; ++ip) {
+#ifdef DFOL_PROGRAM_FAST
+    const Instr I = (ip - ip_first < MAX_CODE) ? load_instr(code_s, ip - ip_first) : load_instr(instr, ip);
+#else
     const Instr I = load_instr(instr, ip);
+#endif
     const bool neg = I.flags & DFOL_F_NEG, rt = I.flags & DFOL_F_ROUNDTRIP;
     const bool hard = I.flags & DFOL_F_HARD, normalise = I.flags & DFOL_F_NORMALISE;
     if (tape != nullptr && tid < n) tape[(long long)ip * tape_stride + tid] = sm.cur[tid];
@@ -109,9 +148,24 @@ __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
 
       case DFOL_OP_RELATE: {
         select_into(sm.nw, im, I.a1, I.flags & DFOL_F_NAME_NEG, I.flags & DFOL_F_NAME_ROUNDTRIP);
-        RelOption L{&im, nullptr, 1, 0, false, rt, I.a0, neg};
         const bool subj = I.flags & DFOL_F_SUBJECT;
-        relate_forward(n, L, subj ? sm.nw : sm.cur, subj ? sm.cur : sm.nw, subj, sm.res, sm.inner, sm.sc);
+#ifdef DFOL_PROGRAM_FAST
+        if (krel < MAX_REL) {
+          const int b = krel % ring.nbuf;
+          mbar_wait(&ring.full[b], (uint32_t)(krel / ring.nbuf) & 1u);
+          relate_forward_tile(n, ring.buf + (size_t)b * ring.tile_floats, neg, rt, subj ? sm.nw : sm.cur,
+                              subj ? sm.cur : sm.nw, subj, sm.res, sm.inner, sm.den, sm.sc);
+          // every thread is past its last read of the slot: refill it with the tile nbuf hops ahead
+          if (tid == 0 && krel + ring.nbuf < rel_count) issue_tile(krel + ring.nbuf);
+        } else
+#endif
+        {
+          RelOption L{&im, nullptr, 1, 0, false, rt, I.a0, neg};
+          relate_forward(n, L, subj ? sm.nw : sm.cur, subj ? sm.cur : sm.nw, subj, sm.res, sm.inner, sm.sc);
+        }
+#ifdef DFOL_PROGRAM_FAST
+        ++krel;
+#endif
         if (tid < n) sm.cur[tid] = sm.res[tid];
         __syncthreads();
         break;
@@ -128,7 +182,7 @@ __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
         const float e1 = exists_block(sm.saved, n, hard, sm.sc, nullptr);
         const float e2 = exists_block(sm.cur, n, hard, sm.sc, nullptr);
         if (tid == 0)
-          lp_out[I.out] = (I.op == DFOL_OP_AND) ? e1 + e2 : slog(1.0f - (1.0f - expf(e1)) * (1.0f - expf(e2)));
+          lp_out[I.out] = (I.op == DFOL_OP_AND) ? e1 + e2 : slog(1.0f - (1.0f - DFOL_EXPF(e1)) * (1.0f - DFOL_EXPF(e2)));
         break;
       }
 
@@ -233,11 +287,11 @@ __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
         const float e2 = exists_block(sm.nw, n, hard, sm.sc, nullptr);
         if (tid == 0) {
           const float mx = fmaxf(e1, e2);
-          const float lse = logf(expf(e1 - mx) + expf(e2 - mx));
+          const float lse = DFOL_LOGF(DFOL_EXPF(e1 - mx) + DFOL_EXPF(e2 - mx));
           const float z1 = e1 - mx - lse, z2 = e2 - mx - lse;
           const float alpha = (I.flags & DFOL_F_IS_LESS) ? 1.0f : 0.0f;
-          lp_out[I.out] = slog(alpha + (1.0f - 2.0f * alpha) * expf(z1));
-          lp_out[I.out + 1] = slog(alpha + (1.0f - 2.0f * alpha) * expf(z2));
+          lp_out[I.out] = slog(alpha + (1.0f - 2.0f * alpha) * DFOL_EXPF(z1));
+          lp_out[I.out + 1] = slog(alpha + (1.0f - 2.0f * alpha) * DFOL_EXPF(z2));
         }
         break;
       }
@@ -265,17 +319,38 @@ __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
 
 using namespace dfol;
 
-extern "C" int dfol_program_fwd(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
-                                const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
-                                const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride,
-                                const int32_t* img_n, float* lp_out, float* tape, int tape_stride, void* stream) {
+#ifdef DFOL_PROGRAM_FAST
+#define DFOL_PROGRAM_FWD_ENTRY dfol_program_fwd_fast
+#else
+#define DFOL_PROGRAM_FWD_ENTRY dfol_program_fwd
+#endif
+
+extern "C" int DFOL_PROGRAM_FWD_ENTRY(const int32_t* instr, const int32_t* q_instr, const int32_t* opts,
+                                      int question_num, const float* attr_ll, const int64_t* attr_blk,
+                                      const int32_t* attr_stride, const float* rel_ll, const int64_t* rel_blk,
+                                      const int32_t* rel_stride, const int32_t* img_n, float* lp_out, float* tape,
+                                      int tape_stride, void* stream) {
   DFOL_REQUIRE(instr && q_instr && attr_ll && attr_blk && attr_stride && rel_ll && rel_blk && rel_stride && img_n &&
                    lp_out,
                "dfol_program_fwd: null pointer");
   DFOL_REQUIRE(tape == nullptr || tape_stride >= 1, "dfol_program_fwd: bad tape stride");
   if (question_num == 0) return 0;
+#ifdef DFOL_PROGRAM_FAST
+  // ring of relation-tile buffers: as many (up to 4) as fit in ~96 KB so that two blocks share an SM
+  DFOL_REQUIRE(tape_stride >= 1 && tape_stride <= MAXN, "dfol_program_fwd_fast: tape_stride = max objects rounded to 4");
+  const int tile_floats = (tape_stride * tape_stride + 31) / 32 * 32;
+  int nbuf = (96 * 1024) / (tile_floats * 4);
+  nbuf = nbuf < 1 ? 1 : (nbuf > 4 ? 4 : nbuf);
+  const size_t smem = (size_t)nbuf * tile_floats * 4;
+  cudaFuncSetAttribute(program_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  program_fwd_kernel<<<question_num, PROG_THREADS, smem, (cudaStream_t)stream>>>(
+      instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, lp_out, tape,
+      tape_stride, nbuf, tile_floats);
+  return finish_launch("dfol_program_fwd_fast");
+#else
   program_fwd_kernel<<<question_num, PROG_THREADS, 0, (cudaStream_t)stream>>>(
       instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, lp_out, tape,
       tape_stride);
   return finish_launch("dfol_program_fwd");
+#endif
 }

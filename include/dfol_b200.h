@@ -237,6 +237,21 @@ int dfol_program_bwd(const int32_t* instr, const int32_t* q_instr, const int32_t
                      const float* d_lp, const float* tape, int tape_stride, float* g_attr, float* g_rel,
                      void* stream);
 
+/* Tensor-core-mode builds of the two interpreter kernels (same contract, tape_stride = largest object count rounded
+ * up to 4): MUFU exp/log approximations; the N x N tile of every relate hop is fetched with a bulk-async copy into a
+ * ring of shared-memory buffers ahead of the hop that reads it, and the hop is evaluated in probability space (one
+ * exponential per pair).  Results agree with the exact kernels to fp32 rounding of the approximations (bf16-mode
+ * tolerance of the answer logits: 2e-2). */
+int dfol_program_fwd_fast(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
+                          const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
+                          const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride,
+                          const int32_t* img_n, float* lp_out, float* tape, int tape_stride, void* stream);
+int dfol_program_bwd_fast(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
+                          const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
+                          const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride,
+                          const int32_t* img_n, const float* d_lp, const float* tape, int tape_stride, float* g_attr,
+                          float* g_rel, void* stream);
+
 /* Loss of VQATrainer._compute_loss (nsvqa/train/trainer.py:181-262) and its derivative w.r.t. lp.
  * kind 0 BINARY: BCE(exp(lp), target) summed; 1 QUERY: sum_q slog(sum_{k in q} e^{lp_k}) - sum_k target_k lp_k
  * (seg[q]..seg[q+1] are question q's predicates); 2 STATEMENT: -sum lp.  loss_out[0] += scale * loss,
