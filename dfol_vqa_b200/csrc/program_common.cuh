@@ -5,7 +5,11 @@
 
 namespace dfol {
 
+#ifdef DFOL_PROGRAM_FAST
+constexpr int PROG_THREADS = 512;  // 16 warps per question: twice the rows of a relation tile in flight
+#else
 constexpr int PROG_THREADS = 256;
+#endif
 constexpr int PROG_WARPS = PROG_THREADS / 32;
 constexpr int MAXN = 128;  // objects per image supported by the interpreter kernels (GQA: <= 100)
 constexpr int NCHUNK = MAXN / 32;
@@ -193,6 +197,12 @@ __device__ __forceinline__ float tile_post(float raw, bool neg, bool rt) {
   return neg ? lnot(c) : (rt ? roundtrip(c) : c);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // t = max(1 - e^{post(raw)} * e_other, eps) for the four pairs of one float4 of a tile row
 __device__ __forceinline__ float4 tile_terms(float4 r, float4 eo, bool neg, bool rt) {
   float4 t;
@@ -201,6 +211,99 @@ __device__ __forceinline__ float4 tile_terms(float4 r, float4 eo, bool neg, bool
   t.z = fmaxf(1.0f - __expf(tile_post(r.z, neg, rt)) * eo.z, kLogEps);
   t.w = fmaxf(1.0f - __expf(tile_post(r.w, neg, rt)) * eo.w, kLogEps);
   return t;
+}
+
+// Lean forward hop: the products Q_x = prod_{y != x} max(1 - e^{post(ll)} e^{a_other[y]}, eps) of the kept role, left
+// in inner[] (subject role) or as per-warp partial products in sc.colacc (object role: relate_kept_q multiplies
+// them).  ea[] = e^{a_other} must be visible to the block; ONE barrier, at the end.
+__device__ __forceinline__ void relate_tile_products(int n, const float* __restrict__ tile, bool neg, bool rt,
+                                                     const float* ea, bool subject_role, float* inner,
+                                                     BlockScratch& sc) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if ((n & 3) == 0 && !neg && !rt) {
+    constexpr float kLog2e = 1.4426950408889634f;
+    const int o4 = 4 * lane;
+    const bool act = o4 < n;
+    const float* rowp = tile + w * n + o4;
+    const int step = PROG_WARPS * n;
+    if (subject_role) {
+      const float4 eo = act ? *reinterpret_cast<const float4*>(ea + o4) : make_float4(1.f, 1.f, 1.f, 1.f);
+      for (int s = w; s < n; s += 2 * PROG_WARPS, rowp += 2 * step) {
+        const bool two = s + PROG_WARPS < n;
+        float q0 = 1.f, q1 = 1.f;
+        if (act) {
+          const float4 r0 = *reinterpret_cast<const float4*>(rowp);
+          const float4 r1 = two ? *reinterpret_cast<const float4*>(rowp + step)
+                                : make_float4(-100.f, -100.f, -100.f, -100.f);
+          q0 = (fmaf(-ex2_approx(fminf(r0.x, 0.f) * kLog2e), eo.x, 1.0f) *
+                fmaf(-ex2_approx(fminf(r0.y, 0.f) * kLog2e), eo.y, 1.0f)) *
+               (fmaf(-ex2_approx(fminf(r0.z, 0.f) * kLog2e), eo.z, 1.0f) *
+                fmaf(-ex2_approx(fminf(r0.w, 0.f) * kLog2e), eo.w, 1.0f));
+          q1 = (fmaf(-ex2_approx(fminf(r1.x, 0.f) * kLog2e), eo.x, 1.0f) *
+                fmaf(-ex2_approx(fminf(r1.y, 0.f) * kLog2e), eo.y, 1.0f)) *
+               (fmaf(-ex2_approx(fminf(r1.z, 0.f) * kLog2e), eo.z, 1.0f) *
+                fmaf(-ex2_approx(fminf(r1.w, 0.f) * kLog2e), eo.w, 1.0f));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          q0 *= __shfl_xor_sync(0xffffffffu, q0, o);
+          q1 *= __shfl_xor_sync(0xffffffffu, q1, o);
+        }
+        if (lane == 0) {
+          inner[s] = q0;
+          if (two) inner[s + PROG_WARPS] = q1;
+        }
+      }
+    } else {
+      float4 acc = make_float4(1.f, 1.f, 1.f, 1.f);
+      for (int s = w; s < n; s += PROG_WARPS, rowp += step) {
+        if (act) {
+          const float4 r = *reinterpret_cast<const float4*>(rowp);
+          const float es = ea[s];
+          acc.x *= fmaf(-ex2_approx(fminf(r.x, 0.f) * kLog2e), es, 1.0f);
+          acc.y *= fmaf(-ex2_approx(fminf(r.y, 0.f) * kLog2e), es, 1.0f);
+          acc.z *= fmaf(-ex2_approx(fminf(r.z, 0.f) * kLog2e), es, 1.0f);
+          acc.w *= fmaf(-ex2_approx(fminf(r.w, 0.f) * kLog2e), es, 1.0f);
+        }
+      }
+      if (o4 < MAXN) *reinterpret_cast<float4*>(&sc.colacc[w][o4]) = acc;
+    }
+  } else {
+    float acc[NCHUNK];
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) acc[j] = 1.f;
+    for (int s = w; s < n; s += PROG_WARPS) {
+      const float es = ea[s];
+      const float* row = tile + s * n;
+      float rowprod = 1.f;
+#pragma unroll
+      for (int j = 0; j < NCHUNK; ++j) {
+        const int o = lane + 32 * j;
+        if (o < n && o != s) {
+          const float t = fmaxf(1.0f - __expf(tile_post(row[o], neg, rt)) * (subject_role ? ea[o] : es), kLogEps);
+          if (subject_role) rowprod *= t;
+          else acc[j] *= t;
+        }
+      }
+      if (subject_role) {
+        rowprod = warp_prod(rowprod);
+        if (lane == 0) inner[s] = rowprod;
+      }
+    }
+    if (!subject_role) {
+#pragma unroll
+      for (int j = 0; j < NCHUNK; ++j) sc.colacc[w][lane + 32 * j] = acc[j];
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float relate_kept_q(int x, bool subject_role, const float* inner, const BlockScratch& sc) {
+  if (subject_role) return inner[x];
+  float q = 1.f;
+#pragma unroll
+  for (int i = 0; i < PROG_WARPS; ++i) q *= sc.colacc[i][x];
+  return q;
 }
 
 // inner[] receives the products Q (NOT their logarithm); ea[] (n floats of scratch) the exponentials of the other
@@ -221,24 +324,50 @@ __device__ __forceinline__ void relate_forward_tile(int n, const float* __restri
     float4 acc = one;
     if (!neg && !rt) {
       // plain relation (the common case): raw <= 0 (log-sigmoid) so t = 1 - e^raw * e_other needs no clamp in
-      // the product (a zero factor gives slog(1 - 0) = 0 exactly as the clamped one does)
+      // the product (a zero factor gives slog(1 - 0) = 0 exactly as the clamped one does).  Two rows per iteration
+      // for instruction-level parallelism; res[] is finished for all rows at once after the loop.
       constexpr float kLog2e = 1.4426950408889634f;
-      for (int s = w; s < n; s += PROG_WARPS) {
-        float4 t = one;
-        if (act) {
-          const float4 r = *reinterpret_cast<const float4*>(tile + s * n + o4);
-          const float es = ea[s];
-          const float4 e = subject_role ? eo : make_float4(es, es, es, es);
-          t.x = fmaf(-exp2f(fminf(r.x, 0.f) * kLog2e), e.x, 1.0f);
-          t.y = fmaf(-exp2f(fminf(r.y, 0.f) * kLog2e), e.y, 1.0f);
-          t.z = fmaf(-exp2f(fminf(r.z, 0.f) * kLog2e), e.z, 1.0f);
-          t.w = fmaf(-exp2f(fminf(r.w, 0.f) * kLog2e), e.w, 1.0f);
+      const float* rowp = tile + w * n + o4;
+      const int step = PROG_WARPS * n;
+      if (subject_role) {
+        for (int s = w; s < n; s += 2 * PROG_WARPS, rowp += 2 * step) {
+          const bool two = s + PROG_WARPS < n;
+          float q0 = 1.f, q1 = 1.f;
+          if (act) {
+            const float4 r0 = *reinterpret_cast<const float4*>(rowp);
+            const float4 r1 = two ? *reinterpret_cast<const float4*>(rowp + step) : make_float4(-100.f, -100.f, -100.f, -100.f);
+            q0 = (fmaf(-ex2_approx(fminf(r0.x, 0.f) * kLog2e), eo.x, 1.0f) *
+                  fmaf(-ex2_approx(fminf(r0.y, 0.f) * kLog2e), eo.y, 1.0f)) *
+                 (fmaf(-ex2_approx(fminf(r0.z, 0.f) * kLog2e), eo.z, 1.0f) *
+                  fmaf(-ex2_approx(fminf(r0.w, 0.f) * kLog2e), eo.w, 1.0f));
+            q1 = (fmaf(-ex2_approx(fminf(r1.x, 0.f) * kLog2e), eo.x, 1.0f) *
+                  fmaf(-ex2_approx(fminf(r1.y, 0.f) * kLog2e), eo.y, 1.0f)) *
+                 (fmaf(-ex2_approx(fminf(r1.z, 0.f) * kLog2e), eo.z, 1.0f) *
+                  fmaf(-ex2_approx(fminf(r1.w, 0.f) * kLog2e), eo.w, 1.0f));
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            q0 *= __shfl_xor_sync(0xffffffffu, q0, o);
+            q1 *= __shfl_xor_sync(0xffffffffu, q1, o);
+          }
+          if (lane == 0) {
+            inner[s] = q0;
+            if (two) inner[s + PROG_WARPS] = q1;
+          }
         }
-        if (subject_role) {
-          const float q = warp_prod((t.x * t.y) * (t.z * t.w));
-          if (lane == 0) { inner[s] = q; res[s] = a_subj[s] + slog(1.0f - q); }
-        } else {
-          acc.x *= t.x; acc.y *= t.y; acc.z *= t.z; acc.w *= t.w;
+        __syncthreads();
+        if (threadIdx.x < n) res[threadIdx.x] = a_subj[threadIdx.x] + slog(1.0f - inner[threadIdx.x]);
+        __syncthreads();
+        return;
+      }
+      for (int s = w; s < n; s += PROG_WARPS, rowp += step) {
+        if (act) {
+          const float4 r = *reinterpret_cast<const float4*>(rowp);
+          const float es = ea[s];
+          acc.x *= fmaf(-ex2_approx(fminf(r.x, 0.f) * kLog2e), es, 1.0f);
+          acc.y *= fmaf(-ex2_approx(fminf(r.y, 0.f) * kLog2e), es, 1.0f);
+          acc.z *= fmaf(-ex2_approx(fminf(r.z, 0.f) * kLog2e), es, 1.0f);
+          acc.w *= fmaf(-ex2_approx(fminf(r.w, 0.f) * kLog2e), es, 1.0f);
         }
       }
     } else {

@@ -100,7 +100,11 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
     const int b = k % ring.nbuf;
     const uint32_t bytes = (uint32_t)im.rstride * 4u;
     mbar_expect_tx(&ring.full[b], bytes);
-    bulk_load(ring.buf + (size_t)b * ring.tile_floats, im.rel + (long long)col * im.rstride, bytes, &ring.full[b]);
+    // several bulk copies per tile: more requests in flight than one long copy
+    const char* src = reinterpret_cast<const char*>(im.rel + (long long)col * im.rstride);
+    char* dst = reinterpret_cast<char*>(ring.buf + (size_t)b * ring.tile_floats);
+    for (uint32_t off = 0; off < bytes; off += 4096u)
+      bulk_load(dst + off, src + off, min(4096u, bytes - off), &ring.full[b]);
   };
   if (tid == 0) {
     int c = 0;
@@ -121,9 +125,34 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
 #endif
   __syncthreads();
 
+#ifdef DFOL_PROGRAM_FAST
+  // software prefetch of the single attribute row the NEXT instruction reads (select / filter / relate name):
+  // the load is issued one instruction early, so its latency hides behind the current instruction
+  auto operand_col = [](const Instr& J) -> int {
+    if (J.op == DFOL_OP_SELECT || J.op == DFOL_OP_FILTER) return J.a0;
+    if (J.op == DFOL_OP_RELATE) return J.a1;
+    return -1;
+  };
+  auto fetch_instr = [&](int ip) -> Instr {
+    return (ip - ip_first < MAX_CODE) ? load_instr(code_s, ip - ip_first) : load_instr(instr, ip);
+  };
+  float pre_raw = 0.f;
+  {
+    const int ip = q_instr[q];
+    if (ip < q_instr[q + 1]) {
+      const int col = operand_col(fetch_instr(ip));
+      if (col >= 0 && tid < n) pre_raw = attr_raw(im, col, tid);
+    }
+  }
+#endif
   for (int ip = q_instr[q]; ip < q_instr[q + 1]; ++ip) {
 #ifdef DFOL_PROGRAM_FAST
-    const Instr I = (ip - ip_first < MAX_CODE) ? load_instr(code_s, ip - ip_first) : load_instr(instr, ip);
+    const Instr I = fetch_instr(ip);
+    const float cur_raw = pre_raw;  // operand row of THIS instruction (valid where operand_col(I) >= 0)
+    if (ip + 1 < q_instr[q + 1]) {
+      const int col = operand_col(fetch_instr(ip + 1));
+      if (col >= 0 && tid < n) pre_raw = attr_raw(im, col, tid);
+    }
 #else
     const Instr I = load_instr(instr, ip);
 #endif
@@ -133,11 +162,20 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
 
     switch (I.op) {
       case DFOL_OP_SELECT:
+#ifdef DFOL_PROGRAM_FAST
+        if (tid < n) sm.cur[tid] = (I.a0 >= 0) ? post_ll(cur_raw, neg, rt) : 0.0f;
+        __syncthreads();
+#else
         select_into(sm.cur, im, I.a0, neg, rt);
+#endif
         break;
 
       case DFOL_OP_FILTER:  // a'[t] = a[t] + ll[t]  (_forward_core arity 1)
+#ifdef DFOL_PROGRAM_FAST
+        if (tid < n) sm.cur[tid] += post_ll(cur_raw, neg, rt);
+#else
         if (tid < n) sm.cur[tid] += post_ll(attr_raw(im, I.a0, tid), neg, rt);
+#endif
         __syncthreads();
         break;
 
@@ -147,25 +185,39 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
         break;
 
       case DFOL_OP_RELATE: {
-        select_into(sm.nw, im, I.a1, I.flags & DFOL_F_NAME_NEG, I.flags & DFOL_F_NAME_ROUNDTRIP);
         const bool subj = I.flags & DFOL_F_SUBJECT;
 #ifdef DFOL_PROGRAM_FAST
         if (krel < MAX_REL) {
+          // phase A (thread-local): prior of the new object from the prefetched name row, e^{cur} of the other role
+          float nwv = 0.0f;
+          if (tid < n) {
+            if (I.a1 >= 0) nwv = post_ll(cur_raw, I.flags & DFOL_F_NAME_NEG, I.flags & DFOL_F_NAME_ROUNDTRIP);
+            sm.den[tid] = __expf(sm.cur[tid]);
+          }
           const int b = krel % ring.nbuf;
           mbar_wait(&ring.full[b], (uint32_t)(krel / ring.nbuf) & 1u);
-          relate_forward_tile(n, ring.buf + (size_t)b * ring.tile_floats, neg, rt, subj ? sm.nw : sm.cur,
-                              subj ? sm.cur : sm.nw, subj, sm.res, sm.inner, sm.den, sm.sc);
+          __syncthreads();
+          // phase B: products over the tile (one barrier at its end)
+          relate_tile_products(n, ring.buf + (size_t)b * ring.tile_floats, neg, rt, sm.den, subj, sm.inner, sm.sc);
           // every thread is past its last read of the slot: refill it with the tile nbuf hops ahead
           if (tid == 0 && krel + ring.nbuf < rel_count) issue_tile(krel + ring.nbuf);
-        } else
+          // phase C (thread-local): posterior of the kept role replaces the attention
+          if (tid < n) sm.cur[tid] = nwv + slog(1.0f - relate_kept_q(tid, subj, sm.inner, sm.sc));
+          __syncthreads();
+          ++krel;
+          break;
+        }
+        ++krel;
+        if (tid < n)
+          sm.nw[tid] = (I.a1 >= 0) ? post_ll(cur_raw, I.flags & DFOL_F_NAME_NEG, I.flags & DFOL_F_NAME_ROUNDTRIP) : 0.0f;
+        __syncthreads();
+#else
+        select_into(sm.nw, im, I.a1, I.flags & DFOL_F_NAME_NEG, I.flags & DFOL_F_NAME_ROUNDTRIP);
 #endif
         {
           RelOption L{&im, nullptr, 1, 0, false, rt, I.a0, neg};
           relate_forward(n, L, subj ? sm.nw : sm.cur, subj ? sm.cur : sm.nw, subj, sm.res, sm.inner, sm.sc);
         }
-#ifdef DFOL_PROGRAM_FAST
-        ++krel;
-#endif
         if (tid < n) sm.cur[tid] = sm.res[tid];
         __syncthreads();
         break;

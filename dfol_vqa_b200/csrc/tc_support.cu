@@ -581,14 +581,15 @@ extern "C" int dfol_rel_slots_fwd(const void* h_saved, int64_t ldh, int E, const
   DFOL_REQUIRE(grid.y <= 65535, "dfol_rel_slots_fwd: too many images");
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(h_saved);
-  for (int first = 0; first < max_slots; first += 4) {
+  for (int first = 0; first < max_slots;) {
     const int left = max_slots - first;
 #define DFOL_RS_LAUNCH(S)                                                                                          \
   rel_slots_fwd_kernel<S, 5><<<grid, 256, 0, st>>>(hp, ldh, E, W, ldw, bias, slot_wrow, img_slot, first, slot_blk,  \
                                                    stride, row0, img_rows, img_n, diag_value, ll)
-    if (left <= 1) DFOL_RS_LAUNCH(1);
-    else if (left == 2) DFOL_RS_LAUNCH(2);
-    else DFOL_RS_LAUNCH(4);
+    if (left <= 1) { DFOL_RS_LAUNCH(1); first += 1; }
+    else if (left == 2) { DFOL_RS_LAUNCH(2); first += 2; }
+    else if (left <= 4) { DFOL_RS_LAUNCH(4); first += 4; }
+    else { DFOL_RS_LAUNCH(8); first += 8; }
 #undef DFOL_RS_LAUNCH
   }
   return finish_launch("dfol_rel_slots_fwd");

@@ -189,17 +189,19 @@ class TensorCorePath(object):
              ptr(layout.obj_row), ptr(layout.img_n), layout.B, layout.max_n, st)
         # the activation of layer 2 is only materialised when the backward pass (or the dense table) needs it
         slots = cp is not None and cp.img_slot is not None
-        h2r = bf(layout.P, p['Ep']) if (training or not slots) else None
+        # inference with few relation columns per image: layer 2 and the columns in one kernel, no activation store
+        fused = slots and not training and cp.max_slots <= 4
+        h2r = None if fused else bf(layout.P, p['Ep'])
         if slots:
             dc = self.engine.upload_programs(cp, dev)
             rel_ll = torch.empty(cp.rel_slot_size, device=dev, dtype=torch.float32)
-            if training:
-                # the backward pass needs the layer-2 activation: GEMM with bf16 store, then the demand-driven
-                # relation columns from the stored activation
+            if not fused:
+                # the backward pass needs the layer-2 activation (or the image uses many relations): GEMM with bf16
+                # store, then the demand-driven relation columns from the stored activation
                 self._tc(h1r, ops.wr2, h2r, E, p['Hp'], w.rel[1].bias, K.ACT_SIGMOID, st)
                 if capi.trace is not None:
                     capi.next_meta = {'tag': 'rel_slots_fwd', 'bytes': 2.0 * layout.P * p['Ep'] * max(
-                        1, (cp.max_slots + 3) // 4) + 4.0 * cp.rel_slot_size}
+                        1, (cp.max_slots + 7) // 8) + 4.0 * cp.rel_slot_size}
                 call('dfol_rel_slots_fwd', ptr(h2r), p['Ep'], E, ptr(w.emb.weight), w.emb.weight.stride(0),
                      ptr(w.emb.bias), ptr(dc['slot_wrow']), ptr(dc['img_slot']), cp.max_slots, ptr(dc['slot_blk']),
                      ptr(layout.rel_stride), ptr(layout.pair_row), ptr(layout.img_nn), ptr(layout.img_n), layout.B,
