@@ -96,3 +96,47 @@ def test_shard_ranges_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_compiler_relation_slots_are_consistent():
+    """Demand-driven relation slots: per image the slot numbering is dense, every relate / choose_rel operand and its
+    gradient slice point at the slot of the relation the dense compilation names, and W rows are concept rows."""
+    import numpy as np
+    from dfol_vqa_b200 import synth
+    from dfol_vqa_b200.capi import K
+    from dfol_vqa_b200.compiler import ProgramCompiler
+    from dfol_vqa_b200.ontology import synthetic_ontology
+    from dfol_vqa_b200.programs import ProgramCollater
+    ont = synthetic_ontology(160, 24, 5, 4, seed=1, embedding_dim=16)
+    for terminal in ('verify_rel', 'choose_rel', 'exist'):
+        questions = synth.make_questions(ont, 12, terminal, 1, 3, seed=7, relate_prob=0.7)
+        counts = synth.object_counts(12, 9, True, seed=8)
+        pb = ProgramCollater(1, lambda qs: (None, None)).collate(questions)[0]
+        dense = ProgramCompiler(ont, relation_slots=False).compile(pb, counts)
+        slot = ProgramCompiler(ont, relation_slots=True).compile(pb, counts)
+        assert dense.img_slot is None and slot.img_slot is not None
+        assert dense.instr.shape == slot.instr.shape and dense.lp_num == slot.lp_num
+        n_slots = np.diff(slot.img_slot)
+        rel_index = list(ont._relation_index)
+        for q in range(12):
+            seen = {}
+            for ip in range(dense.q_instr[q], dense.q_instr[q + 1]):
+                d, s = dense.instr[ip], slot.instr[ip]
+                assert d[0] == s[0]
+                if d[0] == K.OP_RELATE:
+                    seen.setdefault(int(d[2]), int(s[2]))
+                    assert seen[int(d[2])] == int(s[2])
+                elif d[0] == K.OP_CHOOSE_REL:
+                    for k in range(int(d[3])):
+                        dw, sw = int(dense.opts[d[2] + k]), int(slot.opts[s[2] + k])
+                        assert (dw & K.OPT_NEG) == (sw & K.OPT_NEG)
+                        seen.setdefault(dw & ~K.OPT_NEG, sw & ~K.OPT_NEG)
+                        assert seen[dw & ~K.OPT_NEG] == sw & ~K.OPT_NEG
+            assert sorted(seen.values()) == list(range(int(n_slots[q])))
+            for col, sl in seen.items():
+                assert int(slot.slot_wrow[slot.img_slot[q] + sl]) == rel_index[col]
+        assert len(dense.rel_slices) == len(slot.rel_slices)
+        for a, b in zip(dense.rel_slices, slot.rel_slices):
+            assert a[0] == b[0] and a[2] == b[2] and b[3] == rel_index[a[1]]
+        stride = [(c * c + 3) // 4 * 4 for c in counts]
+        assert slot.rel_slot_size == max(1, int(sum(k * s for k, s in zip(n_slots, stride))))
