@@ -349,7 +349,7 @@ def main():
     kernels = {k: {'ms_per_step': v['ms'] / args.steps, 'launches_per_step': v['n'] / args.steps,
                    'tflops': (v['flops'] / (v['ms'] * 1e-3) / 1e12) if v['flops'] and v['ms'] else None,
                    'gbs': (v['bytes'] / (v['ms'] * 1e-3) / 1e9) if v['bytes'] and v['ms'] else None}
-               for k, v in sorted(per.items(), key=lambda kv: -kv[1]['ms'])[:12]}
+               for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])[:40]}
 
     value = global_q * args.steps / (ms * 1e-3)
     e2e_value = global_q * args.steps / (ms_e2e * 1e-3)
@@ -370,6 +370,7 @@ def main():
         'gpu_launches': launches,
         'roofline': roof,
         'kernels': kernels,
+        'kernel_ms_per_step': total_kernel_ms / args.steps,
         'scene_fwd_gflop_per_step': fwd_flops / 1e9,
     }
     if not args.no_cpu_baseline and world >= 1:

@@ -65,6 +65,10 @@ _SIGNATURES = {
                                        c_int64, P, P, P, c_int, P, P, P, P, P, c_float, P, P]),
     'dfol_pair_layer_dgrad_tc': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, c_int64,
                                          c_int, P]),
+    'dfol_pair_layer_fwd_cluster': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, P, c_int, c_int, c_int, c_int,
+                                            P]),
+    'dfol_pair_layer_dgrad_cluster': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P,
+                                              c_int64, c_int, P]),
     'dfol_cast_jobs': (c_int, [P, c_int, c_int64, P]),
     'dfol_cast_job_size': (c_int, []),
     'dfol_obj_finish': (c_int, [P, c_int64, c_int, P, c_int64, c_int, P, c_int64, c_int64, P]),

@@ -1,0 +1,381 @@
+// Cluster-of-two, weights-resident bf16 tensor-core GEMM for the pair-level layers (sm_100a):
+//   C[M, N] = epilogue(A[M, K] . B[N, K]^T),  M ~ 10^5..10^6 pair rows, small weight matrix (N <= 384, K <= 320).
+//
+// Two CTAs on two SMs form a thread-block cluster and split N: CTA r keeps rows [r*BNh, (r+1)*BNh) of B resident in
+// shared memory (<= 96 KB instead of the whole matrix), which leaves room for a deep A ring and for TMA-staged
+// epilogue tiles.  Per CTA:
+//   warp 0 (one lane) : TMA producer.  Every 128 x 64 A block is fetched ONCE per cluster: CTA r loads rows
+//                       [64r, 64r+64) with .multicast::cluster into both CTAs' rings; the epilogue operand tile
+//                       (saved activation of the dgrad) is a plain TMA load of this CTA's columns.
+//   warp 1 (one lane) : tcgen05.mma issuer, 128 x BNh x 16, fp32 accumulators double buffered in TMEM;
+//                       tcgen05.commit.multicast releases a ring stage in BOTH CTAs.
+//   warps 2..9        : epilogue: tcgen05.ld, bias + activation or activation-derivative multiplier (operand read from
+//                       the 128B-swizzled shared tile, conflict free), bf16 result written to a swizzled shared tile
+//                       and stored with cp.async.bulk.tensor (full 128-byte lines) -- no per-thread global access.
+// Every mbarrier wait is bounded (trap instead of hanging the GPU).
+#include "tc_common.cuh"
+
+namespace dfol {
+
+constexpr int CL_BM = 128;
+constexpr int CL_BK = 64;
+constexpr int CL_THREADS = 64 + 256;
+constexpr int CL_MAX_STAGES = 8;
+constexpr int CL_MAX_KB = 5;
+constexpr int CL_MAX_CH = 6;      // 16-column chunks per epilogue warp (192 / 2 / 16)
+
+struct ClParams {
+  const float* bias;
+  int M, N, K;
+  int BNh;              // columns per CTA (multiple of 64)
+  int stages;
+  int act, mul_mode;    // mul_mode != NONE: epilogue operand tile (bf16, same shape as C) is loaded through tmap_e
+  int store_boxes[2];   // 64-column boxes of C this CTA stores (boxes entirely beyond the stored width are skipped)
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  // non-.aligned forms: the single-lane producer / MMA roles leave their warps diverged
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void cl_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cl_named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+
+// byte offset of the 16-byte piece `piece` (0..7) of row `row` inside a [rows][64] bf16 box with 128-byte swizzle
+__device__ __forceinline__ uint32_t swz128(int row, int piece) {
+  return (uint32_t)(row * 128 + ((piece ^ (row & 7)) << 4));
+}
+
+template <int ACT>
+__device__ __forceinline__ float cl_act(float x) {
+  if (ACT == DFOL_ACT_ELU) return x > 0.0f ? x : __expf(x) - 1.0f;
+  if (ACT == DFOL_ACT_SIGMOID) {  // 0.5 tanh(x/2) + 0.5: one MUFU op instead of exp + reciprocal
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+  }
+  return x;
+}
+
+template <int ACT, bool HAS_E>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
+    gemm_bf16_tc_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_e,
+                                ClParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t b_full;
+  __shared__ __align__(8) uint64_t a_full[CL_MAX_STAGES];
+  __shared__ __align__(8) uint64_t a_empty[CL_MAX_STAGES];
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
+  __shared__ __align__(8) uint64_t e_full[2];
+  __shared__ __align__(8) uint64_t e_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float bias_s[192];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_kb = p.K / CL_BK;
+  const int num_tiles = (p.M + CL_BM - 1) / CL_BM;
+  const int BNh = p.BNh;
+  const int nbox = BNh / 64;                                // 64-column boxes of the C / E tiles of this CTA
+  const int n0 = (int)rank * BNh;                           // first column of this CTA
+  const uint32_t a_bytes = CL_BM * CL_BK * 2;               // 16 KB per stage
+  const uint32_t b_kb_bytes = (uint32_t)BNh * CL_BK * 2;
+  const uint32_t box_bytes = CL_BM * 128;                   // one 128 x 64 bf16 box
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* b_tiles = base;
+  uint8_t* a_tiles = b_tiles + (size_t)num_kb * b_kb_bytes;
+  // staging tiles: one result tile (forward), or two tiles that first receive the epilogue operand by TMA and are
+  // then overwritten IN PLACE with the result (dgrad: double buffered so the next operand load overlaps)
+  uint8_t* c_tile = a_tiles + (size_t)p.stages * a_bytes;
+  const uint32_t ec_bytes = (uint32_t)nbox * box_bytes;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&b_full, 1);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  for (int i = threadIdx.x; i < 192; i += CL_THREADS)
+    bias_s[i] = (p.bias != nullptr && i < BNh && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any multicast load / remote arrival
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+      mbar_expect_tx(&b_full, (uint32_t)num_kb * b_kb_bytes);
+      for (int kb = 0; kb < num_kb; ++kb)
+        tma_load_2d(&tmap_b, &b_full, b_tiles + (size_t)kb * b_kb_bytes, kb * CL_BK, n0);
+      int it = 0, local = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+        if (HAS_E) {
+          const int eb = local & 1;
+          mbar_wait(&e_empty[eb], (uint32_t)((local >> 1) & 1) ^ 1u);  // the store that used this buffer has read it
+          mbar_expect_tx(&e_full[eb], ec_bytes);
+          for (int j = 0; j < nbox; ++j)
+            tma_load_2d(&tmap_e, &e_full[eb], c_tile + (size_t)eb * ec_bytes + (size_t)j * box_bytes, n0 + 64 * j,
+                        tile * CL_BM);
+        }
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t phase = (it / p.stages) & 1;
+          mbar_wait(&a_empty[s], phase ^ 1);  // released by the MMAs of BOTH CTAs
+          mbar_expect_tx(&a_full[s], a_bytes);
+          // this CTA fetches rows [64 rank, 64 rank + 64) of the block for both CTAs
+          tma_load_2d_mc(&tmap_a, &a_full[s], a_tiles + (size_t)s * a_bytes + rank * (a_bytes / 2), kb * CL_BK,
+                         tile * CL_BM + (int)rank * 64, (uint16_t)3);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNh >> 3) << 17) |
+                             ((uint32_t)(CL_BM >> 4) << 24);
+      mbar_wait(&b_full, 0);
+      int it = 0, local = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+        const int buf = local & 1;
+        const uint32_t use = (uint32_t)(local >> 1);
+        mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t phase = (it / p.stages) & 1;
+          mbar_wait(&a_full[s], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_smem_desc(smem_u32(a_tiles + (size_t)s * a_bytes));
+          const uint64_t db = make_smem_desc(smem_u32(b_tiles + (size_t)kb * b_kb_bytes));
+#pragma unroll
+          for (int k = 0; k < CL_BK / 16; ++k)
+            umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_mc(&a_empty[s], (uint16_t)3);  // the stage is free in both CTAs once these MMAs have read it
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ---------------- epilogue: warps 2..9; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 ----------------
+    const int quad = warp & 3;
+    const int ch = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int cw = BNh / 2;
+    const int cbeg = ch * cw;
+    const int nchunks = cw / 16;
+    const bool issuer = (warp == 2 && lane == 0);
+    int local = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+      const int buf = local & 1;
+      const uint32_t use = (uint32_t)(local >> 1);
+      mbar_wait(&acc_full[buf], use & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint8_t* stage = c_tile + (HAS_E ? (size_t)(local & 1) * ec_bytes : 0);
+      if (HAS_E) {
+        // the previous tile's store has had a whole MMA phase to read its buffer: hand that buffer back to the
+        // producer now, a full tile before it is needed again
+        if (issuer && local >= 1) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          cl_mbar_arrive(&e_empty[(local - 1) & 1]);
+        }
+        mbar_wait(&e_full[local & 1], (uint32_t)((local >> 1) & 1));
+      } else {
+        // the previous tile's TMA store must have finished READING the staging tile before it is overwritten
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        cl_named_bar(1, 256);
+      }
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + cbeg);
+      uint32_t r[2][16];
+      tmem_ld16(trow, r[0]);
+#pragma unroll
+      for (int c = 0; c < CL_MAX_CH; ++c) {
+        if (c >= nchunks) break;
+        const int c0 = cbeg + 16 * c;  // column inside this CTA's half
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c + 1 < nchunks) tmem_ld16(trow + (uint32_t)(16 * (c + 1)), r[(c + 1) & 1]);
+        const int box = c0 >> 6, piece = (c0 & 63) >> 3;  // 16-byte piece index of the chunk's first 8 columns
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = cl_act<ACT>(__uint_as_float(r[c & 1][j]) + bias_s[c0 + j]);
+        if (HAS_E) {
+          const uint8_t* eb = stage + (size_t)box * box_bytes;
+          const uint4 h0 = *reinterpret_cast<const uint4*>(eb + swz128(row, piece));
+          const uint4 h1 = *reinterpret_cast<const uint4*>(eb + swz128(row, piece + 1));
+          const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
+            if (p.mul_mode == DFOL_MUL_SIGMOID_GRAD) {
+              v[2 * j] *= h.x * (1.0f - h.x);
+              v[2 * j + 1] *= h.y * (1.0f - h.y);
+            } else {
+              v[2 * j] *= (h.x > 0.0f ? 1.0f : h.x + 1.0f);
+              v[2 * j + 1] *= (h.y > 0.0f ? 1.0f : h.y + 1.0f);
+            }
+          }
+        }
+        if (n0 + c0 + 16 > p.N) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j >= p.N) v[j] = 0.0f;  // K padding of the next layer
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        uint8_t* cb = stage + (size_t)box * box_bytes;
+        *reinterpret_cast<uint4*>(cb + swz128(row, piece)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(cb + swz128(row, piece + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      // accumulator buffer and operand tile are free again
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) cl_mbar_arrive(&acc_empty[buf]);
+      // staging tile complete -> one thread stores it with TMA (rows beyond M / columns beyond the map are clipped)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      cl_named_bar(1, 256);
+      if (issuer) {
+        for (int j = 0; j < p.store_boxes[rank]; ++j)
+          tma_store_2d(&tmap_c, stage + (size_t)j * box_bytes, n0 + 64 * j, tile * CL_BM);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // the peer may still multicast into this CTA's ring / arrive on its barriers until it is done
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+typedef void (*ClKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, ClParams);
+
+}  // namespace dfol
+
+using namespace dfol;
+
+static int launch_cluster(const char* who, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                          int store_cols, const float* bias, int M, int N, int K, int act, const void* E, int64_t lde,
+                          int mul_mode, void* stream) {
+  DFOL_REQUIRE(A && B && C, "%s: null pointer", who);
+  DFOL_REQUIRE(M > 0 && N > 0 && K > 0 && (K % CL_BK) == 0 && K <= CL_BK * CL_MAX_KB,
+               "%s: K must be a multiple of 64, at most %d", who, CL_BK * CL_MAX_KB);
+  DFOL_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && (ldc % 8) == 0 && lda >= K && ldb >= K,
+               "%s: strides must be multiples of 8 elements, lda/ldb >= K", who);
+  DFOL_REQUIRE((reinterpret_cast<uintptr_t>(A) % 16) == 0 && (reinterpret_cast<uintptr_t>(B) % 16) == 0 &&
+                   (reinterpret_cast<uintptr_t>(C) % 16) == 0,
+               "%s: operands must be 16-byte aligned", who);
+  const int n_store = store_cols > 0 ? store_cols : (int)ldc;
+  DFOL_REQUIRE(n_store >= N && n_store <= ldc && (n_store % 8) == 0, "%s: N <= store_cols <= ldc, multiple of 8", who);
+  const bool has_e = mul_mode != DFOL_MUL_NONE;
+  DFOL_REQUIRE(!has_e || (E && (lde % 8) == 0 && (reinterpret_cast<uintptr_t>(E) % 16) == 0 && lde >= N),
+               "%s: multiplier operand must be 16-byte aligned with ld %% 8 == 0", who);
+  ClParams p;
+  p.bias = bias; p.M = M; p.N = N; p.K = K; p.act = act; p.mul_mode = mul_mode;
+  p.BNh = ((n_store + 1) / 2 + 63) / 64 * 64;  // half of the stored width, rounded up to whole 64-column boxes
+  DFOL_REQUIRE(p.BNh <= 192, "%s: at most 384 output columns", who);
+  for (int r = 0; r < 2; ++r) {
+    int cols = n_store - r * p.BNh;
+    cols = cols < 0 ? 0 : (cols > p.BNh ? p.BNh : cols);
+    p.store_boxes[r] = (cols + 63) / 64;
+  }
+  const int num_kb = K / CL_BK;
+  const size_t b_bytes = (size_t)num_kb * p.BNh * CL_BK * 2;
+  const size_t box = (size_t)CL_BM * 128;
+  const size_t tiles_bytes = (size_t)(p.BNh / 64) * box * (has_e ? 2 : 1);  // dgrad: two in-place operand/result tiles
+  const size_t a_stage = (size_t)CL_BM * CL_BK * 2;
+  const size_t budget = 224 * 1024;  // + ~2 KB static (barriers, bias) <= 227 KB
+  DFOL_REQUIRE(b_bytes + tiles_bytes + 2 * a_stage + 1024 <= budget, "%s: does not fit in shared memory", who);
+  int stages = (int)((budget - 1024 - b_bytes - tiles_bytes) / a_stage);
+  if (stages > CL_MAX_STAGES) stages = CL_MAX_STAGES;
+  p.stages = stages;
+  const size_t smem = b_bytes + tiles_bytes + (size_t)stages * a_stage + 1024;
+  ClKernel kernel;
+  if (has_e) kernel = gemm_bf16_tc_cluster_kernel<DFOL_ACT_NONE, true>;
+  else if (act == DFOL_ACT_SIGMOID) kernel = gemm_bf16_tc_cluster_kernel<DFOL_ACT_SIGMOID, false>;
+  else if (act == DFOL_ACT_ELU) kernel = gemm_bf16_tc_cluster_kernel<DFOL_ACT_ELU, false>;
+  else kernel = gemm_bf16_tc_cluster_kernel<DFOL_ACT_NONE, false>;
+  DFOL_REQUIRE(!has_e || act == DFOL_ACT_NONE, "%s: the multiplier epilogue has no activation", who);
+  {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return (int)e; }
+  }
+  alignas(64) CUtensorMap ma, mb, mc, me;
+  int rc = encode_map_bf16(&ma, A, M, K, lda, 64);
+  if (rc != 0) return rc;
+  rc = encode_map_bf16(&mb, B, N, K, ldb, p.BNh);
+  if (rc != 0) return rc;
+  rc = encode_map_bf16(&mc, C, M, n_store, ldc, CL_BM);
+  if (rc != 0) return rc;
+  rc = encode_map_bf16(&me, has_e ? E : C, M, has_e ? N : n_store, has_e ? lde : ldc, CL_BM);
+  if (rc != 0) return rc;
+  int sms = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int tiles = (M + CL_BM - 1) / CL_BM;
+  int clusters = sms / 2;
+  if (clusters > tiles) clusters = tiles;
+  kernel<<<2 * clusters, CL_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, mc, me, p);
+  return finish_launch(who);
+}
+
+extern "C" int dfol_pair_layer_fwd_cluster(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                                           int store_cols, const float* bias, int M, int N, int K, int act,
+                                           void* stream) {
+  return launch_cluster("dfol_pair_layer_fwd_cluster", A, lda, B, ldb, C, ldc, store_cols, bias, M, N, K, act, nullptr,
+                        0, DFOL_MUL_NONE, stream);
+}
+
+extern "C" int dfol_pair_layer_dgrad_cluster(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX,
+                                             int64_t lddx, int store_cols, int M, int N, int K, const void* h_saved,
+                                             int64_t ldh, int mul_mode, void* stream) {
+  return launch_cluster("dfol_pair_layer_dgrad_cluster", dZ, lddz, Wt, ldwt, dX, lddx, store_cols, nullptr, M, N, K,
+                        DFOL_ACT_NONE, h_saved, ldh, mul_mode, stream);
+}

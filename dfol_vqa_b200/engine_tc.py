@@ -198,7 +198,11 @@ class TensorCorePath(object):
             if not fused:
                 # the backward pass needs the layer-2 activation (or the image uses many relations): GEMM with bf16
                 # store, then the demand-driven relation columns from the stored activation
-                self._tc(h1r, ops.wr2, h2r, E, p['Hp'], w.rel[1].bias, K.ACT_SIGMOID, st)
+                if capi.trace is not None:
+                    capi.next_meta = {'tag': 'pair_layer_fwd_cluster[%dx%dx%d]' % (layout.P, E, p['Hp']),
+                                      'flops': 2.0 * layout.P * E * p['Hp']}
+                call('dfol_pair_layer_fwd_cluster', ptr(h1r), p['Hp'], ptr(ops.wr2), p['Hp'], ptr(h2r), p['Ep'],
+                     p['Ep'], ptr(w.rel[1].bias), layout.P, E, p['Hp'], K.ACT_SIGMOID, st)
                 if capi.trace is not None:
                     capi.next_meta = {'tag': 'rel_slots_fwd', 'bytes': 2.0 * layout.P * p['Ep'] * max(
                         1, (cp.max_slots + 7) // 8) + 4.0 * cp.rel_slot_size}
@@ -325,9 +329,9 @@ class TensorCorePath(object):
             self._wgrad(dz2r, E, h1r, H, G(r1.weight), st)
             dz1r = torch.empty(P, Hp, device=dev, dtype=torch.bfloat16)
             if capi.trace is not None:
-                capi.next_meta = {'tag': 'pair_layer_dgrad_tc[%dx%dx%d]' % (P, H, Ep), 'flops': 2.0 * P * H * Ep}
-            call('dfol_pair_layer_dgrad_tc', ptr(dz2r), Ep, ptr(ops.wr2t), Ep, ptr(dz1r), Hp, Hp, P, H, Ep, ptr(h1r),
-                 Hp, K.MUL_ELU_GRAD, st)
+                capi.next_meta = {'tag': 'pair_layer_dgrad_cluster[%dx%dx%d]' % (P, H, Ep), 'flops': 2.0 * P * H * Ep}
+            call('dfol_pair_layer_dgrad_cluster', ptr(dz2r), Ep, ptr(ops.wr2t), Ep, ptr(dz1r), Hp, Hp, P, H, Ep,
+                 ptr(h1r), Hp, K.MUL_ELU_GRAD, st)
             gw1 = G(r0.weight)
             if capi.trace is not None:
                 capi.next_meta = {'tag': 'pair_hidden_bwd_tc', 'bytes': 2.0 * P * H + 16.0 * P}

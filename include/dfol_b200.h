@@ -119,6 +119,17 @@ int dfol_pair_layer_dgrad_tc(const void* dZ, int64_t lddz, const void* Wt, int64
                              int store_cols, int M, int N, int K, const void* h_saved, int64_t ldh, int mul_mode,
                              void* stream);
 
+/* Cluster-of-two variant of the pair-layer GEMMs (same arithmetic contract, bf16 row-major C, N <= 384): two CTAs on
+ * two SMs split the output columns, each keeps half of B resident; every A block is fetched once per cluster
+ * (TMA .multicast::cluster), accumulators are double buffered in TMEM, and the epilogue moves its operand
+ * (h_saved of the dgrad) and its result through 128B-swizzled shared tiles with TMA loads / stores, so global
+ * memory only ever sees full-line bulk transfers.  store_cols (0 = ldc) columns are written, zero beyond N. */
+int dfol_pair_layer_fwd_cluster(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                                int store_cols, const float* bias, int M, int N, int K, int act, void* stream);
+int dfol_pair_layer_dgrad_cluster(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX, int64_t lddx,
+                                  int store_cols, int M, int N, int K, const void* h_saved, int64_t ldh, int mul_mode,
+                                  void* stream);
+
 /* fp32 -> bf16 cast with row padding: dst[r*ldd + c] = bf16(src[r*lds + c]) for c < cols, 0 for cols <= c < ldd */
 int dfol_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 

@@ -294,9 +294,12 @@ def test_bf16_mode_training_gradients(terminal):
         assert err <= 6e-2 * scale + 1e-6, (k, err, scale)
 
 
-@pytest.mark.parametrize('M,N,K,act', [(1000, 300, 256, 2), (4608 + 77, 300, 256, 2), (300, 256, 320, 1), (129, 64, 64, 0)])
-def test_pair_layer_fwd_resident_gemm(M, N, K, act):
-    """Persistent weights-resident tcgen05 GEMM (no slots): bf16 output with zero K-padding vs fp64."""
+@pytest.mark.parametrize('M,N,K,act', [(1000, 300, 256, 2), (4608 + 77, 300, 256, 2), (300, 256, 320, 1), (129, 64, 64, 0),
+                                       (40000, 300, 256, 2)])
+@pytest.mark.parametrize('impl', ['resident', 'cluster'])
+def test_pair_layer_fwd_resident_gemm(M, N, K, act, impl):
+    """Persistent weights-resident tcgen05 GEMMs (single CTA and cluster-of-two): bf16 output with zero K-padding
+    vs fp64."""
     from dfol_vqa_b200.capi import call, ptr, stream_ptr
     g = torch.Generator().manual_seed(M + N + K)
     A = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
@@ -304,8 +307,11 @@ def test_pair_layer_fwd_resident_gemm(M, N, K, act):
     b = torch.randn(N, generator=g).cuda()
     ldc = (N + 63) // 64 * 64
     C = torch.full((M, ldc), float('nan'), device='cuda', dtype=torch.bfloat16)
-    call('dfol_pair_layer_fwd_tc', ptr(A), K, ptr(W), K, ptr(C), ldc, ldc, ptr(b), M, N, K, act, None, 0, None, None,
-         None, 0, None, None, None, None, None, 0.0, None, stream_ptr())
+    if impl == 'cluster':
+        call('dfol_pair_layer_fwd_cluster', ptr(A), K, ptr(W), K, ptr(C), ldc, ldc, ptr(b), M, N, K, act, stream_ptr())
+    else:
+        call('dfol_pair_layer_fwd_tc', ptr(A), K, ptr(W), K, ptr(C), ldc, ldc, ptr(b), M, N, K, act, None, 0, None,
+             None, None, 0, None, None, None, None, None, 0.0, None, stream_ptr())
     torch.cuda.synchronize()
     z = A.double() @ W.double().t() + b.double()
     ref = {0: z, 1: torch.nn.functional.elu(z), 2: torch.sigmoid(z)}[act]
@@ -374,16 +380,18 @@ def test_pair_layer_fwd_slot_epilogue(counts, slots_per_image, store):
         assert torch.allclose(got2[mask], ref[mask], rtol=2e-2, atol=2e-2), (got2[mask] - ref[mask]).abs().max()
 
 
-@pytest.mark.parametrize('M,N,K', [(1000, 256, 320), (4608 + 5, 256, 320), (300, 64, 64)])
+@pytest.mark.parametrize('M,N,K', [(1000, 256, 320), (4608 + 5, 256, 320), (300, 64, 64), (40000, 256, 320)])
 @pytest.mark.parametrize('mode', [0, 2])
-def test_pair_layer_dgrad_resident_gemm(M, N, K, mode):
+@pytest.mark.parametrize('impl', ['resident', 'cluster'])
+def test_pair_layer_dgrad_resident_gemm(M, N, K, mode, impl):
     from dfol_vqa_b200.capi import call, ptr, stream_ptr
     g = torch.Generator().manual_seed(M + mode)
     dZ = (torch.randn(M, K, generator=g)).cuda().bfloat16()
     Wt = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
     Hs = (torch.rand(M, N, generator=g) - 0.3).cuda().bfloat16()
     dX = torch.full((M, N), float('nan'), device='cuda', dtype=torch.bfloat16)
-    call('dfol_pair_layer_dgrad_tc', ptr(dZ), K, ptr(Wt), K, ptr(dX), N, 0, M, N, K, ptr(Hs), N, mode, stream_ptr())
+    entry = 'dfol_pair_layer_dgrad_cluster' if impl == 'cluster' else 'dfol_pair_layer_dgrad_tc'
+    call(entry, ptr(dZ), K, ptr(Wt), K, ptr(dX), N, 0, M, N, K, ptr(Hs), N, mode, stream_ptr())
     torch.cuda.synchronize()
     ref = dZ.double() @ Wt.double().t()
     h = Hs.double()

@@ -36,5 +36,15 @@ def dgrad():
     call('dfol_pair_layer_dgrad_tc', ptr(dZ), 320, ptr(Wt), 320, ptr(dX), 256, 0, P, 256, 320, ptr(A), 256, 2, stream_ptr())
 
 
+def fwd_cluster():
+    call('dfol_pair_layer_fwd_cluster', ptr(A), K, ptr(W2), K, ptr(H2), 320, 320, ptr(b2), P, E, K, 2, stream_ptr())
+
+
+def dgrad_cluster():
+    call('dfol_pair_layer_dgrad_cluster', ptr(dZ), 320, ptr(Wt), 320, ptr(dX), 256, 0, P, 256, 320, ptr(A), 256, 2,
+         stream_ptr())
+
+
+print('cluster: fwd %.3f ms  dgrad %.3f ms' % (timeit(fwd_cluster), timeit(dgrad_cluster)))
 print('(DFOL_RS_DEBUG needs a -DDFOL_RS_EXPERIMENTS build) DFOL_RS_DEBUG=%s fwd %.3f ms  dgrad %.3f ms' % (
     os.environ.get('DFOL_RS_DEBUG', '0'), timeit(fwd), timeit(dgrad)))
