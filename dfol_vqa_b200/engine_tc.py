@@ -130,7 +130,8 @@ class TensorCorePath(object):
         """C[Mc, Nc] (fp32 view) += A[:, :Mc]^T . B[:, :Nc] (reduction over rows)."""
         rows = A.shape[0]
         if capi.trace is not None:
-            capi.next_meta = {'tag': 'gemm_bf16_tc_wgrad[%dx%dx%d]' % (Mc, Nc, rows), 'flops': 2.0 * Mc * Nc * rows}
+            capi.next_meta = {'tag': 'gemm_bf16_tc_wgrad[%dx%dx%d]' % (Mc, Nc, rows), 'flops': 2.0 * Mc * Nc * rows,
+                              'bytes': 2.0 * rows * (A.stride(0) + B.stride(0)) if rows > 100000 else 0.0}
         call('dfol_gemm_bf16_tc_wgrad', ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(C), C.stride(0), Mc, Nc, rows,
              st)
 
@@ -200,7 +201,8 @@ class TensorCorePath(object):
                 # store, then the demand-driven relation columns from the stored activation
                 if capi.trace is not None:
                     capi.next_meta = {'tag': 'pair_layer_fwd_cluster[%dx%dx%d]' % (layout.P, E, p['Hp']),
-                                      'flops': 2.0 * layout.P * E * p['Hp']}
+                                      'flops': 2.0 * layout.P * E * p['Hp'],
+                                      'bytes': 2.0 * layout.P * (p['Hp'] + p['Ep'])}
                 call('dfol_pair_layer_fwd_cluster', ptr(h1r), p['Hp'], ptr(ops.wr2), p['Hp'], ptr(h2r), p['Ep'],
                      p['Ep'], ptr(w.rel[1].bias), layout.P, E, p['Hp'], K.ACT_SIGMOID, st)
                 if capi.trace is not None:
@@ -329,7 +331,8 @@ class TensorCorePath(object):
             self._wgrad(dz2r, E, h1r, H, G(r1.weight), st)
             dz1r = torch.empty(P, Hp, device=dev, dtype=torch.bfloat16)
             if capi.trace is not None:
-                capi.next_meta = {'tag': 'pair_layer_dgrad_cluster[%dx%dx%d]' % (P, H, Ep), 'flops': 2.0 * P * H * Ep}
+                capi.next_meta = {'tag': 'pair_layer_dgrad_cluster[%dx%dx%d]' % (P, H, Ep), 'flops': 2.0 * P * H * Ep,
+                                  'bytes': 2.0 * P * (Ep + 2 * Hp)}
             call('dfol_pair_layer_dgrad_cluster', ptr(dz2r), Ep, ptr(ops.wr2t), Ep, ptr(dz1r), Hp, Hp, P, H, Ep,
                  ptr(h1r), Hp, K.MUL_ELU_GRAD, st)
             gw1 = G(r0.weight)
