@@ -185,35 +185,32 @@ __global__ void __launch_bounds__(32 * RG) pair_hidden_bwd_tc_kernel(
   for (int i = 0; i < NI; ++i) dv[i][0] = dv[i][1] = 0.0f;
   float dw[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
   float dbv = 0.0f;  // threads < 64: column sum of dU
-  constexpr int CH = (NI > 8) ? (NI + 1) / 2 : NI;  // rows in flight per thread (bounds the register footprint)
-  for (int s = 0; s < n; ++s) {
-    const long long prow = p0 + (long long)s * n;
+  // all NI row loads of a subject are issued before the first use (raw bf16x2 words: one register each); row
+  // addresses are a per-subject base plus 32-bit offsets
+  const long long srow = (long long)n * lddz;
+  const __nv_bfloat16* sbase = dz + p0 * lddz + c0;
+  const float4* gbase = geo + p0;
+  for (int s = 0; s < n; ++s, sbase += srow, gbase += n) {
+    uint32_t raw[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int o = rg + RG * i;
+      raw[i] = 0u;
+      if (o < n && o != s) raw[i] = *reinterpret_cast<const uint32_t*>(sbase + o * (int)lddz);
+    }
     float du0 = 0.f, du1 = 0.f;
 #pragma unroll
-    for (int i0 = 0; i0 < NI; i0 += CH) {
-      float2 v[CH];
-      float4 g[CH];
-#pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        const int o = rg + RG * (i0 + i);
-        v[i] = make_float2(0.f, 0.f);
-        g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i0 + i < NI && o < n && o != s) {
-          const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(dz + (prow + o) * lddz + c0);
-          v[i] = __bfloat1622float2(x);
-          g[i] = __ldg(geo + prow + o);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        if (i0 + i < NI) {
-          du0 += v[i].x; du1 += v[i].y;
-          dv[i0 + i][0] += v[i].x; dv[i0 + i][1] += v[i].y;
-          dw[0][0] = fmaf(v[i].x, g[i].x, dw[0][0]); dw[0][1] = fmaf(v[i].y, g[i].x, dw[0][1]);
-          dw[1][0] = fmaf(v[i].x, g[i].y, dw[1][0]); dw[1][1] = fmaf(v[i].y, g[i].y, dw[1][1]);
-          dw[2][0] = fmaf(v[i].x, g[i].z, dw[2][0]); dw[2][1] = fmaf(v[i].y, g[i].z, dw[2][1]);
-          dw[3][0] = fmaf(v[i].x, g[i].w, dw[3][0]); dw[3][1] = fmaf(v[i].y, g[i].w, dw[3][1]);
-        }
+    for (int i = 0; i < NI; ++i) {
+      const int o = rg + RG * i;
+      if (o < n && o != s) {
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[i]));
+        const float4 g = __ldg(gbase + o);
+        du0 += v.x; du1 += v.y;
+        dv[i][0] += v.x; dv[i][1] += v.y;
+        dw[0][0] = fmaf(v.x, g.x, dw[0][0]); dw[0][1] = fmaf(v.y, g.x, dw[0][1]);
+        dw[1][0] = fmaf(v.x, g.y, dw[1][0]); dw[1][1] = fmaf(v.y, g.y, dw[1][1]);
+        dw[2][0] = fmaf(v.x, g.z, dw[2][0]); dw[2][1] = fmaf(v.y, g.z, dw[2][1]);
+        dw[3][0] = fmaf(v.x, g.w, dw[3][0]); dw[3][1] = fmaf(v.y, g.w, dw[3][1]);
       }
     }
     const int buf = s & 1;
@@ -316,39 +313,45 @@ __global__ void __launch_bounds__(32 * NC * TB_RP) table_layer_bwd_tc_kernel(
     wj[j] = (j < Sb && e_ok) ? *reinterpret_cast<const float2*>(W + (long long)wrow_s[j] * ldw + e)
                              : make_float2(0.f, 0.f);
   }
-  constexpr int UN = 4;  // rows in flight per warp
-  for (int l0 = rp; l0 < cn; l0 += TB_RP * UN) {
-    float2 h[UN], prev[UN];
+  constexpr int UN = 8;  // rows in flight per warp
+  // row pointers advance by a fixed stride: no 64-bit multiply per access
+  const __nv_bfloat16* hp = hs + (r0 + rp) * ldh + e;
+  __nv_bfloat16* zp = dZ + (r0 + rp) * lddz + e;
+  const long long hstep = (long long)TB_RP * ldh, zstep = (long long)TB_RP * lddz;
+  for (int l0 = rp; l0 < cn; l0 += TB_RP * UN, hp += UN * hstep, zp += UN * zstep) {
+    uint32_t hraw[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-      const int l = l0 + TB_RP * u;
-      h[u] = make_float2(0.f, 0.f);
-      prev[u] = make_float2(0.f, 0.f);
-      if (l < cn && e_ok) {
-        h[u] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hs + (r0 + l) * ldh + e));
-        if (accumulate) prev[u] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dZ + (r0 + l) * lddz + e));
-      }
+      hraw[u] = 0u;
+      if (l0 + TB_RP * u < cn && e_ok) hraw[u] = *reinterpret_cast<const uint32_t*>(hp + u * hstep);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const int l = l0 + TB_RP * u;
       if (l < cn) {
+        const float2 hv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hraw[u]));
         float ox = 0.f, oy = 0.f;
 #pragma unroll
         for (int j = 0; j < S; ++j) {
-          const float dzl = dz_s[j][l];
-          ox = fmaf(dzl, wj[j].x, ox);
-          oy = fmaf(dzl, wj[j].y, oy);
-          dwj[j].x = fmaf(dzl, h[u].x, dwj[j].x);
-          dwj[j].y = fmaf(dzl, h[u].y, dwj[j].y);
+          if (j < Sb) {  // block-uniform: images that use fewer slices than the batch maximum skip the rest
+            const float dzl = dz_s[j][l];
+            ox = fmaf(dzl, wj[j].x, ox);
+            oy = fmaf(dzl, wj[j].y, oy);
+            dwj[j].x = fmaf(dzl, hv.x, dwj[j].x);
+            dwj[j].y = fmaf(dzl, hv.y, dwj[j].y);
+          }
         }
-        ox *= h[u].x * (1.0f - h[u].x);
-        oy *= h[u].y * (1.0f - h[u].y);
+        ox *= hv.x * (1.0f - hv.x);
+        oy *= hv.y * (1.0f - hv.y);
         colsum.x += ox;
         colsum.y += oy;
         if (st_ok) {  // columns E .. out_cols are the zero K-padding of the next GEMM (h = 0 there)
-          const __nv_bfloat162 o2 = __floats2bfloat162_rn(ox + prev[u].x, oy + prev[u].y);
-          *reinterpret_cast<__nv_bfloat162*>(dZ + (r0 + l) * lddz + e) = o2;
+          if (accumulate && e_ok) {
+            const float2 pv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zp + u * zstep));
+            ox += pv.x;
+            oy += pv.y;
+          }
+          *reinterpret_cast<__nv_bfloat162*>(zp + u * zstep) = __floats2bfloat162_rn(ox, oy);
         }
       }
     }
