@@ -196,6 +196,36 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, long long lds, _
   dst[i] = __float2bfloat16(c < cols ? src[r * lds + c] : 0.0f);
 }
 
+// Same cast, 8 elements per thread (four 8-byte loads, one 16-byte store): ldd a multiple of 8, lds even, src 8-byte
+// and dst 16-byte aligned.  Grid-stride over (row, 8-column group).
+__global__ void __launch_bounds__(256) cast_bf16_vec8_kernel(const float* __restrict__ src, long long lds,
+                                                             __nv_bfloat16* __restrict__ dst, long long ldd,
+                                                             long long rows, int cols) {
+  const int groups = (int)(ldd >> 3);
+  const long long total = rows * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups;
+    const int c = (int)(i - r * groups) << 3;
+    float v[8];
+    if (c + 8 <= cols) {  // 8-byte loads: box-feature rows are (D + 6) floats long, i.e. only 8-byte aligned
+      const float2* q = reinterpret_cast<const float2*>(src + r * lds + c);
+      const float2 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 2), e = __ldg(q + 3);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = d.x; v[5] = d.y; v[6] = e.x; v[7] = e.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c + j < cols) ? src[r * lds + c + j] : 0.0f;
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(dst + r * ldd + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Backward of the table layer LL = logsigmoid(H.W^T + b) for the compact gradient slices of the programs.
 // One block per image: for each slice (column c of the table), dz[l] = g[l]*(1-exp(LL[l])).
@@ -411,24 +441,45 @@ __global__ void __launch_bounds__(256) pair_hidden_bwd_bf16_kernel(
   }
 }
 
+// out[n] += sum_m X[m, n] for bf16 X: block = 64 columns (bf16x2 per lane) x 8 row groups, rows_per_block rows;
+// four rows in flight per thread.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ldx,
                                                           long long M, int N, float* __restrict__ out,
                                                           long long rows_per_block) {
-  __shared__ float part[8][33];
+  __shared__ float part[8][64];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + cx;
+  const int col = blockIdx.x * 64 + 2 * cx;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = min(M, r0 + rows_per_block);
-  float acc = 0.f;
-  if (col < N)
-    for (long long r = r0 + ry; r < r1; r += 8) acc += __bfloat162float(X[r * ldx + col]);
-  part[ry][cx] = acc;
+  float ax = 0.f, ay = 0.f;
+  if (col + 1 < N || (col < N && (N & 1) == 0)) {
+    const __nv_bfloat16* p = X + (r0 + ry) * ldx + col;
+    const long long step = 8 * ldx;
+    long long r = r0 + ry;
+    for (; r + 24 < r1; r += 32, p += 4 * step) {
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + step));
+      const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + 2 * step));
+      const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + 3 * step));
+      ax += (a.x + b.x) + (c.x + d.x);
+      ay += (a.y + b.y) + (c.y + d.y);
+    }
+    for (; r < r1; r += 8, p += step) {
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+      ax += a.x;
+      ay += a.y;
+    }
+  } else if (col < N) {  // odd trailing column
+    for (long long r = r0 + ry; r < r1; r += 8) ax += __bfloat162float(X[r * ldx + col]);
+  }
+  part[ry][2 * cx] = ax;
+  part[ry][2 * cx + 1] = ay;
   __syncthreads();
-  if (ry == 0 && col < N) {
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < N) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += part[i][cx];
-    atomicAdd(out + col, t);
+    for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+    atomicAdd(out + blockIdx.x * 64 + threadIdx.x, t);
   }
 }
 
@@ -515,8 +566,17 @@ extern "C" int dfol_cast_bf16(const float* src, int64_t lds, void* dst, int64_t 
   DFOL_REQUIRE(src && dst && ldd >= cols, "dfol_cast_bf16: bad arguments");
   long long n = rows * ldd;
   if (n == 0) return 0;
-  cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
+  const bool vec = (ldd % 8) == 0 && (lds % 2) == 0 && (reinterpret_cast<uintptr_t>(src) % 8) == 0 &&
+                   (reinterpret_cast<uintptr_t>(dst) % 16) == 0;
+  if (vec) {
+    long long blocks = (n / 8 + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    cast_bf16_vec8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
+  } else {
+    cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
+  }
   return finish_launch("dfol_cast_bf16");
 }
 
@@ -592,8 +652,9 @@ extern "C" int dfol_pair_hidden_bwd_bf16(const void* dz, int64_t lddz, const flo
 extern "C" int dfol_colsum_bf16(const void* X, int64_t ldx, int64_t M, int N, float* out, void* stream) {
   DFOL_REQUIRE(X && out, "dfol_colsum_bf16: null pointer");
   if (M == 0 || N == 0) return 0;
-  long long rows_per_block = 2048;
-  dim3 grid((N + 31) / 32, (unsigned)((M + rows_per_block - 1) / rows_per_block));
+  DFOL_REQUIRE((ldx % 2) == 0 && (reinterpret_cast<uintptr_t>(X) % 4) == 0, "dfol_colsum_bf16: ldx must be even");
+  long long rows_per_block = 256;
+  dim3 grid((N + 63) / 64, (unsigned)((M + rows_per_block - 1) / rows_per_block));
   colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(X), ldx, M, N, out,
                                                             rows_per_block);
   return finish_launch("dfol_colsum_bf16");
