@@ -79,6 +79,8 @@ _SIGNATURES = {
     'dfol_table_layer_bwd_tc': (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, c_int64, P, c_int64,
                                         c_int, P, c_int64, c_int, P, P, P, P]),
     'dfol_gemm_bf16_tc_wgrad': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int64, P]),
+    'dfol_gemm_bf16_tc_wgrad_seg': (c_int, [P, c_int64, P, c_int64, P, c_int64, P, c_int64, P, c_int64, c_int, c_int,
+                                            c_int, c_int64, P]),
     'dfol_pair_hidden_bwd_bf16': (c_int, [P, c_int64, P, c_int64, P, c_int64, P, c_int64, P, c_int, P, P, P, c_int,
                                           c_int, P]),
     'dfol_colsum_bf16': (c_int, [P, c_int64, c_int64, c_int, P, P]),

@@ -16,6 +16,8 @@ constexpr int WG_BM = 128, WG_BK = 64, WG_THREADS = 192, WG_MAX_STAGES = 4;
 
 struct WgParams {
   float* C; long long ldc;
+  // optional row segments of the output: rows [i*seg_rows, (i+1)*seg_rows) go to Cseg[i] (seg_rows = 0: single C)
+  float* Cseg[4]; long long ldcseg[4]; int seg_rows;
   int M, N, K;
   int BN, stages;
   int kb_per_split;  // 64-row blocks per split
@@ -116,7 +118,16 @@ __global__ void __launch_bounds__(WG_THREADS) gemm_bf16_tc_wgrad_kernel(const __
         tmem_ld16(trow + (uint32_t)c0, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (m < p.M) {
-          float* dst = p.C + (long long)m * p.ldc + n0 + c0;
+          float* dst;
+          if (p.seg_rows > 0) {
+            // (no dynamic indexing of the parameter arrays: that would spill them to local memory)
+            const int sg = m / p.seg_rows;
+            float* cb = sg == 0 ? p.Cseg[0] : (sg == 1 ? p.Cseg[1] : p.Cseg[2]);
+            const long long cl = sg == 0 ? p.ldcseg[0] : (sg == 1 ? p.ldcseg[1] : p.ldcseg[2]);
+            dst = cb + (long long)(m - sg * p.seg_rows) * cl + n0 + c0;
+          } else {
+            dst = p.C + (long long)m * p.ldc + n0 + c0;
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (n0 + c0 + j < p.N) atomicAdd(dst + j, __uint_as_float(r[j]));
@@ -136,9 +147,9 @@ __global__ void __launch_bounds__(WG_THREADS) gemm_bf16_tc_wgrad_kernel(const __
 
 using namespace dfol;
 
-extern "C" int dfol_gemm_bf16_tc_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
-                                       int M, int N, int64_t K, void* stream) {
-  DFOL_REQUIRE(A && B && C, "dfol_gemm_bf16_tc_wgrad: null pointer");
+static int launch_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
+                        int64_t K, float* const* Cseg, const int64_t* ldcseg, int seg_rows, void* stream) {
+  DFOL_REQUIRE(A && B && (C || seg_rows > 0), "dfol_gemm_bf16_tc_wgrad: null pointer");
   DFOL_REQUIRE(M > 0 && N > 0 && K > 0 && K < (1ll << 31), "dfol_gemm_bf16_tc_wgrad: bad sizes");
   DFOL_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && lda >= M && ldb >= N,
                "dfol_gemm_bf16_tc_wgrad: lda >= M, ldb >= N, both multiples of 8 elements");
@@ -146,6 +157,11 @@ extern "C" int dfol_gemm_bf16_tc_wgrad(const void* A, int64_t lda, const void* B
                "dfol_gemm_bf16_tc_wgrad: operands must be 16-byte aligned");
   WgParams p;
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = (int)K;
+  p.seg_rows = seg_rows;
+  for (int i = 0; i < 4; ++i) {
+    p.Cseg[i] = (seg_rows > 0 && i * seg_rows < M) ? Cseg[i] : nullptr;
+    p.ldcseg[i] = (seg_rows > 0 && i * seg_rows < M) ? ldcseg[i] : 0;
+  }
   const int n64 = (N + 63) / 64;
   const int n_tiles = (n64 + 3) / 4;
   p.BN = ((n64 + n_tiles - 1) / n_tiles) * 64;
@@ -176,4 +192,20 @@ extern "C" int dfol_gemm_bf16_tc_wgrad(const void* A, int64_t lda, const void* B
   dim3 grid(n_tiles, m_tiles, splits);
   gemm_bf16_tc_wgrad_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, p);
   return finish_launch("dfol_gemm_bf16_tc_wgrad");
+}
+
+extern "C" int dfol_gemm_bf16_tc_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                                       int M, int N, int64_t K, void* stream) {
+  return launch_wgrad(A, lda, B, ldb, C, ldc, M, N, K, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int dfol_gemm_bf16_tc_wgrad_seg(const void* A, int64_t lda, const void* B, int64_t ldb, float* C0, int64_t ldc0,
+                                           float* C1, int64_t ldc1, float* C2, int64_t ldc2, int seg_rows, int M, int N,
+                                           int64_t K, void* stream) {
+  DFOL_REQUIRE(seg_rows > 0 && (seg_rows % 128) == 0 && M <= 3 * seg_rows && C0 && (M <= seg_rows || C1) &&
+                   (M <= 2 * seg_rows || C2),
+               "dfol_gemm_bf16_tc_wgrad_seg: up to three segments of seg_rows (multiple of 128) rows each");
+  float* cs[4] = {C0, C1, C2, nullptr};
+  const int64_t ls[4] = {ldc0, ldc1, ldc2, 0};
+  return launch_wgrad(A, lda, B, ldb, nullptr, 0, M, N, K, cs, ls, seg_rows, stream);
 }

@@ -295,8 +295,10 @@ class TensorCorePath(object):
 
         g_attr, g_rel = eng.program_backward(cp, scene, tape, d_lp)
 
-        # dcat = [dZ1 of the attribute chain | dU | dV]: the three first layers that read obj share one dgrad
+        # dcat = [dZ1 of the attribute chain | dU | dV]: the three first layers that read obj share one dgrad and
+        # (when their widths are equal multiples of 128) one segmented wgrad
         dcat = torch.zeros(T, Kc, device=dev, dtype=torch.bfloat16)
+        merged = Ha == Hap == Hp == H and Hp % 128 == 0
         a0, a1, r0, r1 = w.attr[0], w.attr[1], w.rel[0], w.rel[1]
 
         # ---- attribute table layer -> layer 2 -> layer 1
@@ -308,7 +310,8 @@ class TensorCorePath(object):
             self._wgrad(dz2a, E, scene.attr_h[0], Ha, G(a1.weight), st)
             self._dgrad(dz2a, ops.wa2t, dcat[:, :Hap], Ha, Ep, scene.attr_h[0], K.MUL_ELU_GRAD, st)
             call('dfol_colsum_bf16', ptr(dcat), Kc, T, Ha, ptr(G(a0.bias)), st)
-            self._wgrad(dcat, Ha, scene.obj16, ldo, G(a0.weight), st)
+            if not merged:
+                self._wgrad(dcat, Ha, scene.obj16, ldo, G(a0.weight), st)
 
         # ---- relation table layer -> layer 2 -> pair hidden layer
         sr = eng._slice_tables(cp.rel_slices, lay.B, dev, 'rel_slices', cp)
@@ -341,8 +344,17 @@ class TensorCorePath(object):
             call('dfol_pair_hidden_bwd_tc', ptr(dz1r), Hp, ptr(scene.geo), ptr(dcat[:, Hap:]), ptr(dcat[:, Hap + Hp:]),
                  Kc, ptr(gw1[:, 2 * ldo:]), gw1.stride(0), ptr(G(r0.bias)), H, ptr(lay.pair_row), ptr(lay.obj_row),
                  ptr(lay.img_n), lay.B, lay.max_n, st)
-            self._wgrad(dcat[:, Hap:], H, scene.obj16, ldo, gw1[:, :ldo], st)
-            self._wgrad(dcat[:, Hap + Hp:], H, scene.obj16, ldo, gw1[:, ldo:2 * ldo], st)
+            if not merged:
+                self._wgrad(dcat[:, Hap:], H, scene.obj16, ldo, gw1[:, :ldo], st)
+                self._wgrad(dcat[:, Hap + Hp:], H, scene.obj16, ldo, gw1[:, ldo:2 * ldo], st)
+
+        if merged:
+            gw1 = G(r0.weight)
+            if capi.trace is not None:
+                capi.next_meta = {'tag': 'gemm_bf16_tc_wgrad_seg[%dx%dx%d]' % (Kc, ldo, T), 'flops': 2.0 * Kc * ldo * T}
+            call('dfol_gemm_bf16_tc_wgrad_seg', ptr(dcat), Kc, ptr(scene.obj16), scene.obj16.stride(0),
+                 ptr(G(a0.weight)), G(a0.weight).stride(0), ptr(gw1[:, :ldo]), gw1.stride(0),
+                 ptr(gw1[:, ldo:2 * ldo]), gw1.stride(0), Hp, Kc, ldo, T, st)
 
         # ---- featurizer: d pre = (dcat . [Wa1 | Wu | Wv][:, :F]) * f (1 - f)
         dpre = torch.empty(T, F, device=dev, dtype=torch.bfloat16)

@@ -91,6 +91,12 @@ int dfol_gemm_bf16_tc_dgrad(const void* dZ, int64_t lddz, const void* Wt, int64_
                             void* stream);
 int dfol_gemm_bf16_tc_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
                             int64_t K, void* stream);
+/* same contraction with the M rows of the result split into up to three segments of seg_rows rows (multiple of 128)
+ * that accumulate into different gradient tensors: one launch for the weight gradients of all first layers that read
+ * the object features (A = [dZ1_attr | dU | dV], B = obj). */
+int dfol_gemm_bf16_tc_wgrad_seg(const void* A, int64_t lda, const void* B, int64_t ldb, float* C0, int64_t ldc0,
+                                float* C1, int64_t ldc1, float* C2, int64_t ldc2, int seg_rows, int M, int N, int64_t K,
+                                void* stream);
 
 /* Batched operand preparation: job j casts (and, if transpose != 0, transposes) the fp32 view src[rows][cols]
  * (row stride lds) into columns [0, dcols) of the bf16 rows dst[out_rows][ldd], zero beyond the source extent.
