@@ -22,6 +22,7 @@ constexpr int CL_BK = 64;
 constexpr int CL_THREADS = 64 + 256;
 constexpr int CL_MAX_STAGES = 8;
 constexpr int CL_MAX_KB = 5;
+constexpr int CL_EC = 3;          // in-place operand/result tiles of the dgrad (operand prefetched two tiles ahead)
 constexpr int CL_MAX_CH = 6;      // 16-column chunks per epilogue warp (192 / 2 / 16)
 
 struct ClParams {
@@ -96,8 +97,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
   __shared__ __align__(8) uint64_t a_empty[CL_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2];
   __shared__ __align__(8) uint64_t acc_empty[2];
-  __shared__ __align__(8) uint64_t e_full[2];
-  __shared__ __align__(8) uint64_t e_empty[2];
+  __shared__ __align__(8) uint64_t e_full[CL_EC];
+  __shared__ __align__(8) uint64_t e_empty[CL_EC];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float bias_s[192];
 
@@ -124,7 +125,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
     mbar_init(&b_full, 1);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 2); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 1); }
+    for (int i = 0; i < CL_EC; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -150,8 +151,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
       int it = 0, local = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
         if (HAS_E) {
-          const int eb = local & 1;
-          mbar_wait(&e_empty[eb], (uint32_t)((local >> 1) & 1) ^ 1u);  // the store that used this buffer has read it
+          const int eb = local % CL_EC;
+          mbar_wait(&e_empty[eb], (uint32_t)((local / CL_EC) & 1) ^ 1u);  // the store that used this buffer has read it
           mbar_expect_tx(&e_full[eb], ec_bytes);
           for (int j = 0; j < nbox; ++j)
             tma_load_2d(&tmap_e, &e_full[eb], c_tile + (size_t)eb * ec_bytes + (size_t)j * box_bytes, n0 + 64 * j,
@@ -210,15 +211,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
       const uint32_t use = (uint32_t)(local >> 1);
       mbar_wait(&acc_full[buf], use & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint8_t* stage = c_tile + (HAS_E ? (size_t)(local & 1) * ec_bytes : 0);
+      uint8_t* stage = c_tile + (HAS_E ? (size_t)(local % CL_EC) * ec_bytes : 0);
       if (HAS_E) {
         // the previous tile's store has had a whole MMA phase to read its buffer: hand that buffer back to the
         // producer now, a full tile before it is needed again
         if (issuer && local >= 1) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          cl_mbar_arrive(&e_empty[(local - 1) & 1]);
+          cl_mbar_arrive(&e_empty[(local - 1) % CL_EC]);
         }
-        mbar_wait(&e_full[local & 1], (uint32_t)((local >> 1) & 1));
+        mbar_wait(&e_full[local % CL_EC], (uint32_t)((local / CL_EC) & 1));
       } else {
         // the previous tile's TMA store must have finished READING the staging tile before it is overwritten
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -277,7 +278,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       cl_named_bar(1, 256);
       if (issuer) {
-        for (int j = 0; j < p.store_boxes[rank]; ++j)
+        const int my_boxes = rank == 0 ? p.store_boxes[0] : p.store_boxes[1];  // (no dynamic param indexing)
+        for (int j = 0; j < my_boxes; ++j)
           tma_store_2d(&tmap_c, stage + (size_t)j * box_bytes, n0 + 64 * j, tile * CL_BM);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
@@ -327,7 +329,7 @@ static int launch_cluster(const char* who, const void* A, int64_t lda, const voi
   const int num_kb = K / CL_BK;
   const size_t b_bytes = (size_t)num_kb * p.BNh * CL_BK * 2;
   const size_t box = (size_t)CL_BM * 128;
-  const size_t tiles_bytes = (size_t)(p.BNh / 64) * box * (has_e ? 2 : 1);  // dgrad: two in-place operand/result tiles
+  const size_t tiles_bytes = (size_t)(p.BNh / 64) * box * (has_e ? CL_EC : 1);  // dgrad: in-place operand/result tiles
   const size_t a_stage = (size_t)CL_BM * CL_BK * 2;
   const size_t budget = 224 * 1024;  // + ~2 KB static (barriers, bias) <= 227 KB
   DFOL_REQUIRE(b_bytes + tiles_bytes + 2 * a_stage + 1024 <= budget, "%s: does not fit in shared memory", who);
