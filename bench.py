@@ -227,7 +227,8 @@ def main():
     args = ap.parse_args()
     if args.gemm is None:
         args.gemm = 'bf16'  # tensor-core mode (bf16 operands, fp32 accumulation); --gemm fp32 = parity mode
-    args.warmup = max(args.warmup, 3)
+    # every distinct batch of the pool is stepped once before timing (allocator growth, per-batch device tables)
+    args.warmup = max(args.warmup, 3, args.pool)
     if args.impl == 'reference':
         return run_reference(args)
 

@@ -299,11 +299,11 @@ __global__ void __launch_bounds__(32 * NC * TB_RP) table_layer_bwd_tc_kernel(
   }
   if (threadIdx.x < S) wrow_s[threadIdx.x] = threadIdx.x < Sb ? slice_wrow[j0 + threadIdx.x] : 0;
   __syncthreads();
-  if (warp < Sb) {  // db[wrow_j] += sum_l dz_j[l]
+  for (int j = warp; j < Sb; j += THREADS / 32) {  // db[wrow_j] += sum_l dz_j[l]
     float t = 0.f;
-    for (int l = lane; l < cn; l += 32) t += dz_s[warp][l];
+    for (int l = lane; l < cn; l += 32) t += dz_s[j][l];
     t = warp_sum(t);
-    if (lane == 0 && t != 0.0f) atomicAdd(db + wrow_s[warp], t);
+    if (lane == 0 && t != 0.0f) atomicAdd(db + wrow_s[j], t);
   }
   const bool e_ok = e < E, st_ok = e < out_cols;
   float2 wj[S], dwj[S], colsum = make_float2(0.f, 0.f);
@@ -552,7 +552,7 @@ extern "C" int dfol_table_layer_bwd_tc(const float* g, const int32_t* slice_goff
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(h_saved);
   __nv_bfloat16* dzp = reinterpret_cast<__nv_bfloat16*>(dZ);
-  // slices are consumed in groups of at most 4 per pass; later passes accumulate into dZ
+  // slices are consumed in groups of at most 12 per pass; later passes accumulate into dZ
   int first = 0;
   do {
     const int left = max_slices - first;
@@ -561,11 +561,12 @@ extern "C" int dfol_table_layer_bwd_tc(const float* g, const int32_t* slice_goff
   table_layer_bwd_tc_kernel<S, 5><<<grid, 320, 0, st>>>(g, slice_goff, slice_col, slice_wrow, img_slice, first, acc, \
                                                         ll, blk, stride, row0, img_rows, W, ldw, hp, ldh, E, dzp,    \
                                                         lddz, out_cols, dW, db, dbelow)
-    if (left <= 1) DFOL_TB_LAUNCH(1);
-    else if (left == 2) DFOL_TB_LAUNCH(2);
-    else DFOL_TB_LAUNCH(4);
+    if (left <= 1) { DFOL_TB_LAUNCH(1); first += 1; }
+    else if (left == 2) { DFOL_TB_LAUNCH(2); first += 2; }
+    else if (left <= 4) { DFOL_TB_LAUNCH(4); first += 4; }
+    else if (left <= 8) { DFOL_TB_LAUNCH(8); first += 8; }
+    else { DFOL_TB_LAUNCH(12); first += 12; }
 #undef DFOL_TB_LAUNCH
-    first += 4;
   } while (first < max_slices);
   return finish_launch("dfol_table_layer_bwd_tc");
 }

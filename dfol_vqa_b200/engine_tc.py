@@ -251,9 +251,9 @@ class TensorCorePath(object):
         E = W.shape[1]
         cols = h_last.shape[1]
         dz = torch.empty(rows_total, cols, device=dev, dtype=torch.bfloat16)
-        if tabs['max_per_image'] <= 12:
+        if tabs['max_per_image'] <= 24:
             if capi.trace is not None:
-                passes = max(1, (tabs['max_per_image'] + 3) // 4)
+                passes = max(1, (tabs['max_per_image'] + 11) // 12)
                 capi.next_meta = {'tag': 'table_layer_bwd_tc[%s]' % tag, 'bytes': 4.0 * rows_total * cols * passes}
             call('dfol_table_layer_bwd_tc', ptr(g), ptr(tabs['goff']), ptr(tabs['col']), ptr(tabs['wrow']),
                  ptr(tabs['img_slice']), len(tabs['img_slice']) - 1, max_rows, tabs['max_per_image'], ptr(ll),
