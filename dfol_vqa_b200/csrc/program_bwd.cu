@@ -145,11 +145,7 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
     const int b = j % ring.nbuf;
     const uint32_t bytes = (uint32_t)im.rstride * 4u;
     mbar_expect_tx(&ring.full[b], bytes);
-    // several bulk copies per tile: more requests in flight than one long copy
-    const char* src = reinterpret_cast<const char*>(im.rel + (long long)col * im.rstride);
-    char* dst = reinterpret_cast<char*>(ring.buf + (size_t)b * ring.tile_floats);
-    for (uint32_t off = 0; off < bytes; off += 4096u)
-      bulk_load(dst + off, src + off, min(4096u, bytes - off), &ring.full[b]);
+    bulk_load(ring.buf + (size_t)b * ring.tile_floats, im.rel + (long long)col * im.rstride, bytes, &ring.full[b]);
   };
   if (tid == 0) {
     int c = 0;

@@ -235,14 +235,14 @@ __device__ __forceinline__ void relate_tile_products(int n, const float* __restr
           const float4 r0 = *reinterpret_cast<const float4*>(rowp);
           const float4 r1 = two ? *reinterpret_cast<const float4*>(rowp + step)
                                 : make_float4(-100.f, -100.f, -100.f, -100.f);
-          q0 = (fmaf(-ex2_approx(fminf(r0.x, 0.f) * kLog2e), eo.x, 1.0f) *
-                fmaf(-ex2_approx(fminf(r0.y, 0.f) * kLog2e), eo.y, 1.0f)) *
-               (fmaf(-ex2_approx(fminf(r0.z, 0.f) * kLog2e), eo.z, 1.0f) *
-                fmaf(-ex2_approx(fminf(r0.w, 0.f) * kLog2e), eo.w, 1.0f));
-          q1 = (fmaf(-ex2_approx(fminf(r1.x, 0.f) * kLog2e), eo.x, 1.0f) *
-                fmaf(-ex2_approx(fminf(r1.y, 0.f) * kLog2e), eo.y, 1.0f)) *
-               (fmaf(-ex2_approx(fminf(r1.z, 0.f) * kLog2e), eo.z, 1.0f) *
-                fmaf(-ex2_approx(fminf(r1.w, 0.f) * kLog2e), eo.w, 1.0f));
+          q0 = (fmaf(-ex2_approx(r0.x * kLog2e), eo.x, 1.0f) *
+                fmaf(-ex2_approx(r0.y * kLog2e), eo.y, 1.0f)) *
+               (fmaf(-ex2_approx(r0.z * kLog2e), eo.z, 1.0f) *
+                fmaf(-ex2_approx(r0.w * kLog2e), eo.w, 1.0f));
+          q1 = (fmaf(-ex2_approx(r1.x * kLog2e), eo.x, 1.0f) *
+                fmaf(-ex2_approx(r1.y * kLog2e), eo.y, 1.0f)) *
+               (fmaf(-ex2_approx(r1.z * kLog2e), eo.z, 1.0f) *
+                fmaf(-ex2_approx(r1.w * kLog2e), eo.w, 1.0f));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -260,10 +260,10 @@ __device__ __forceinline__ void relate_tile_products(int n, const float* __restr
         if (act) {
           const float4 r = *reinterpret_cast<const float4*>(rowp);
           const float es = ea[s];
-          acc.x *= fmaf(-ex2_approx(fminf(r.x, 0.f) * kLog2e), es, 1.0f);
-          acc.y *= fmaf(-ex2_approx(fminf(r.y, 0.f) * kLog2e), es, 1.0f);
-          acc.z *= fmaf(-ex2_approx(fminf(r.z, 0.f) * kLog2e), es, 1.0f);
-          acc.w *= fmaf(-ex2_approx(fminf(r.w, 0.f) * kLog2e), es, 1.0f);
+          acc.x *= fmaf(-ex2_approx(r.x * kLog2e), es, 1.0f);
+          acc.y *= fmaf(-ex2_approx(r.y * kLog2e), es, 1.0f);
+          acc.z *= fmaf(-ex2_approx(r.z * kLog2e), es, 1.0f);
+          acc.w *= fmaf(-ex2_approx(r.w * kLog2e), es, 1.0f);
         }
       }
       if (o4 < MAXN) *reinterpret_cast<float4*>(&sc.colacc[w][o4]) = acc;
@@ -323,7 +323,8 @@ __device__ __forceinline__ void relate_forward_tile(int n, const float* __restri
     const float4 eo = (act && subject_role) ? *reinterpret_cast<const float4*>(ea + o4) : one;
     float4 acc = one;
     if (!neg && !rt) {
-      // plain relation (the common case): raw <= 0 (log-sigmoid) so t = 1 - e^raw * e_other needs no clamp in
+      // plain relation (the common case): raw <= 0 by construction (log-sigmoid table entries, -30 on self pairs), so
+      // min(raw, 0) is the identity and t = 1 - e^raw * e_other needs no clamp in
       // the product (a zero factor gives slog(1 - 0) = 0 exactly as the clamped one does).  Two rows per iteration
       // for instruction-level parallelism; res[] is finished for all rows at once after the loop.
       constexpr float kLog2e = 1.4426950408889634f;
@@ -336,14 +337,14 @@ __device__ __forceinline__ void relate_forward_tile(int n, const float* __restri
           if (act) {
             const float4 r0 = *reinterpret_cast<const float4*>(rowp);
             const float4 r1 = two ? *reinterpret_cast<const float4*>(rowp + step) : make_float4(-100.f, -100.f, -100.f, -100.f);
-            q0 = (fmaf(-ex2_approx(fminf(r0.x, 0.f) * kLog2e), eo.x, 1.0f) *
-                  fmaf(-ex2_approx(fminf(r0.y, 0.f) * kLog2e), eo.y, 1.0f)) *
-                 (fmaf(-ex2_approx(fminf(r0.z, 0.f) * kLog2e), eo.z, 1.0f) *
-                  fmaf(-ex2_approx(fminf(r0.w, 0.f) * kLog2e), eo.w, 1.0f));
-            q1 = (fmaf(-ex2_approx(fminf(r1.x, 0.f) * kLog2e), eo.x, 1.0f) *
-                  fmaf(-ex2_approx(fminf(r1.y, 0.f) * kLog2e), eo.y, 1.0f)) *
-                 (fmaf(-ex2_approx(fminf(r1.z, 0.f) * kLog2e), eo.z, 1.0f) *
-                  fmaf(-ex2_approx(fminf(r1.w, 0.f) * kLog2e), eo.w, 1.0f));
+            q0 = (fmaf(-ex2_approx(r0.x * kLog2e), eo.x, 1.0f) *
+                  fmaf(-ex2_approx(r0.y * kLog2e), eo.y, 1.0f)) *
+                 (fmaf(-ex2_approx(r0.z * kLog2e), eo.z, 1.0f) *
+                  fmaf(-ex2_approx(r0.w * kLog2e), eo.w, 1.0f));
+            q1 = (fmaf(-ex2_approx(r1.x * kLog2e), eo.x, 1.0f) *
+                  fmaf(-ex2_approx(r1.y * kLog2e), eo.y, 1.0f)) *
+                 (fmaf(-ex2_approx(r1.z * kLog2e), eo.z, 1.0f) *
+                  fmaf(-ex2_approx(r1.w * kLog2e), eo.w, 1.0f));
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
@@ -364,10 +365,10 @@ __device__ __forceinline__ void relate_forward_tile(int n, const float* __restri
         if (act) {
           const float4 r = *reinterpret_cast<const float4*>(rowp);
           const float es = ea[s];
-          acc.x *= fmaf(-ex2_approx(fminf(r.x, 0.f) * kLog2e), es, 1.0f);
-          acc.y *= fmaf(-ex2_approx(fminf(r.y, 0.f) * kLog2e), es, 1.0f);
-          acc.z *= fmaf(-ex2_approx(fminf(r.z, 0.f) * kLog2e), es, 1.0f);
-          acc.w *= fmaf(-ex2_approx(fminf(r.w, 0.f) * kLog2e), es, 1.0f);
+          acc.x *= fmaf(-ex2_approx(r.x * kLog2e), es, 1.0f);
+          acc.y *= fmaf(-ex2_approx(r.y * kLog2e), es, 1.0f);
+          acc.z *= fmaf(-ex2_approx(r.z * kLog2e), es, 1.0f);
+          acc.w *= fmaf(-ex2_approx(r.w * kLog2e), es, 1.0f);
         }
       }
     } else {

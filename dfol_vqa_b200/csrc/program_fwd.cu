@@ -3,6 +3,14 @@
 // per-image contiguous block (see include/dfol_b200.h for the contract and reference citations).
 #include "program_common.cuh"
 
+#ifdef DFOL_PROG_TIMING  // timing experiment only: per-phase clock64 stamps of block 0 / thread 0 of the relate hops
+__device__ long long dfol_tstamps[64 * 8];
+__device__ int dfol_tcount;
+#define DFOL_TSTAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && krel < 64) dfol_tstamps[krel * 8 + (i)] = clock64(); } while (0)
+#else
+#define DFOL_TSTAMP(i) do { } while (0)
+#endif
+
 namespace dfol {
 
 struct FwdShared {
@@ -77,6 +85,9 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
 #endif
     ) {
   __shared__ __align__(16) FwdShared sm;
+#ifdef DFOL_PROG_TIMING
+  if (blockIdx.x == 0 && threadIdx.x == 0) dfol_tstamps[6] = clock64();
+#endif
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Image im;
@@ -95,62 +106,91 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
   __shared__ int rel_ip[MAX_REL];
   __shared__ int rel_count;
   TileRing ring{ring_mem, ring_nbuf, ring_tile_floats, ring_full};
+  // the question's bytecode is read once into shared memory (no global load on the per-instruction critical path),
+  // together with the attribute column each instruction will want prefetched and the list of its relate hops
+  __shared__ int32_t code_s[MAX_CODE * DFOL_INSTR_WORDS];
+  __shared__ int pre_col_s[MAX_CODE];
+  const int ip_first = q_instr[q];
+  const int ip_last = q_instr[q + 1];
+  const int code_n = min(ip_last - ip_first, MAX_CODE);
+  for (int i = tid; i < code_n * DFOL_INSTR_WORDS; i += PROG_THREADS)
+    code_s[i] = instr[(long long)ip_first * DFOL_INSTR_WORDS + i];
+  if (tid == 0) {
+    for (int b = 0; b < ring.nbuf; ++b) mbar_init(&ring.full[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   auto issue_tile = [&](int k) {  // elected thread: tile of the k-th relate -> ring slot k % nbuf
-    const int col = instr[(long long)rel_ip[k] * DFOL_INSTR_WORDS + DFOL_I_A0];
+    const int col = code_s[(rel_ip[k] - ip_first) * DFOL_INSTR_WORDS + DFOL_I_A0];
     const int b = k % ring.nbuf;
     const uint32_t bytes = (uint32_t)im.rstride * 4u;
     mbar_expect_tx(&ring.full[b], bytes);
-    // several bulk copies per tile: more requests in flight than one long copy
-    const char* src = reinterpret_cast<const char*>(im.rel + (long long)col * im.rstride);
-    char* dst = reinterpret_cast<char*>(ring.buf + (size_t)b * ring.tile_floats);
-    for (uint32_t off = 0; off < bytes; off += 4096u)
-      bulk_load(dst + off, src + off, min(4096u, bytes - off), &ring.full[b]);
+    bulk_load(ring.buf + (size_t)b * ring.tile_floats, im.rel + (long long)col * im.rstride, bytes, &ring.full[b]);
   };
-  if (tid == 0) {
-    int c = 0;
-    for (int ip = q_instr[q]; ip < q_instr[q + 1] && c < MAX_REL; ++ip)
-      if (instr[(long long)ip * DFOL_INSTR_WORDS + DFOL_I_OP] == DFOL_OP_RELATE) rel_ip[c++] = ip;
-    rel_count = c;
-    for (int b = 0; b < ring.nbuf; ++b) mbar_init(&ring.full[b], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int k = 0; k < c && k < ring.nbuf; ++k) issue_tile(k);
+  if (tid < code_n) {
+    const int op = code_s[tid * DFOL_INSTR_WORDS + DFOL_I_OP];
+    pre_col_s[tid] = (op == DFOL_OP_SELECT || op == DFOL_OP_FILTER) ? code_s[tid * DFOL_INSTR_WORDS + DFOL_I_A0]
+                     : (op == DFOL_OP_RELATE ? code_s[tid * DFOL_INSTR_WORDS + DFOL_I_A1] : -1);
+  }
+  if (w == 0) {  // warp 0 compacts the relate hops of the staged instructions (ballot + prefix popcount)
+    int base = 0;
+    for (int c0 = 0; c0 < code_n; c0 += 32) {
+      const int idx = c0 + lane;
+      const bool is_rel = idx < code_n && code_s[idx * DFOL_INSTR_WORDS + DFOL_I_OP] == DFOL_OP_RELATE;
+      const unsigned m = __ballot_sync(0xffffffffu, is_rel);
+      if (is_rel) rel_ip[base + __popc(m & ((1u << lane) - 1u))] = ip_first + idx;
+      base += __popc(m);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      rel_count = base;
+      for (int k = 0; k < base && k < ring.nbuf; ++k) issue_tile(k);
+    }
   }
   int krel = 0;
-  // the question's bytecode is read once into shared memory: no global load on the per-instruction critical path
-  __shared__ int32_t code_s[MAX_CODE * DFOL_INSTR_WORDS];
-  const int ip_first = q_instr[q];
-  const int code_n = min(q_instr[q + 1] - ip_first, MAX_CODE);
-  for (int i = tid; i < code_n * DFOL_INSTR_WORDS; i += PROG_THREADS)
-    code_s[i] = instr[(long long)ip_first * DFOL_INSTR_WORDS + i];
 #endif
   __syncthreads();
 
 #ifdef DFOL_PROGRAM_FAST
   // software prefetch of the single attribute row the NEXT instruction reads (select / filter / relate name):
   // the load is issued one instruction early, so its latency hides behind the current instruction
-  auto operand_col = [](const Instr& J) -> int {
-    if (J.op == DFOL_OP_SELECT || J.op == DFOL_OP_FILTER) return J.a0;
-    if (J.op == DFOL_OP_RELATE) return J.a1;
-    return -1;
-  };
   auto fetch_instr = [&](int ip) -> Instr {
-    return (ip - ip_first < MAX_CODE) ? load_instr(code_s, ip - ip_first) : load_instr(instr, ip);
+    if (ip - ip_first < MAX_CODE) {  // shared-memory copy, indexed directly (LDS); the forward pass needs six words
+      const int o = (ip - ip_first) * DFOL_INSTR_WORDS;
+      Instr J;
+      J.op = code_s[o + DFOL_I_OP]; J.flags = code_s[o + DFOL_I_FLAGS]; J.a0 = code_s[o + DFOL_I_A0];
+      J.a1 = code_s[o + DFOL_I_A1]; J.a2 = code_s[o + DFOL_I_A2]; J.out = code_s[o + DFOL_I_OUT];
+      J.ga0 = J.ga1 = J.gr = -1;
+      return J;
+    }
+    return load_instr(instr, ip);
+  };
+  auto operand_col_at = [&](int ip) -> int {
+    if (ip - ip_first < MAX_CODE) return pre_col_s[ip - ip_first];
+    const Instr J = load_instr(instr, ip);
+    if (J.op == DFOL_OP_SELECT || J.op == DFOL_OP_FILTER) return J.a0;
+    return J.op == DFOL_OP_RELATE ? J.a1 : -1;
   };
   float pre_raw = 0.f;
-  {
-    const int ip = q_instr[q];
-    if (ip < q_instr[q + 1]) {
-      const int col = operand_col(fetch_instr(ip));
-      if (col >= 0 && tid < n) pre_raw = attr_raw(im, col, tid);
-    }
+  if (ip_first < ip_last) {
+    const int col = operand_col_at(ip_first);
+    if (col >= 0 && tid < n) pre_raw = attr_raw(im, col, tid);
   }
 #endif
-  for (int ip = q_instr[q]; ip < q_instr[q + 1]; ++ip) {
+#ifdef DFOL_PROGRAM_FAST
+  const int ip_begin = ip_first, ip_end = ip_last;
+#else
+  const int ip_begin = q_instr[q], ip_end = q_instr[q + 1];
+#endif
+#ifdef DFOL_PROG_TIMING
+  if (blockIdx.x == 0 && threadIdx.x == 0) dfol_tstamps[7] = clock64();
+#endif
+  for (int ip = ip_begin; ip < ip_end; ++ip) {
 #ifdef DFOL_PROGRAM_FAST
     const Instr I = fetch_instr(ip);
     const float cur_raw = pre_raw;  // operand row of THIS instruction (valid where operand_col(I) >= 0)
-    if (ip + 1 < q_instr[q + 1]) {
-      const int col = operand_col(fetch_instr(ip + 1));
+    if (ip + 1 < ip_end) {
+      const int col = operand_col_at(ip + 1);
       if (col >= 0 && tid < n) pre_raw = attr_raw(im, col, tid);
     }
 #else
@@ -187,23 +227,29 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
       case DFOL_OP_RELATE: {
         const bool subj = I.flags & DFOL_F_SUBJECT;
 #ifdef DFOL_PROGRAM_FAST
-        if (krel < MAX_REL) {
+        if (krel < rel_count) {
           // phase A (thread-local): prior of the new object from the prefetched name row, e^{cur} of the other role
           float nwv = 0.0f;
+          DFOL_TSTAMP(0);
           if (tid < n) {
             if (I.a1 >= 0) nwv = post_ll(cur_raw, I.flags & DFOL_F_NAME_NEG, I.flags & DFOL_F_NAME_ROUNDTRIP);
             sm.den[tid] = __expf(sm.cur[tid]);
           }
           const int b = krel % ring.nbuf;
+          DFOL_TSTAMP(1);
           mbar_wait(&ring.full[b], (uint32_t)(krel / ring.nbuf) & 1u);
+          DFOL_TSTAMP(2);
           __syncthreads();
+          DFOL_TSTAMP(3);
           // phase B: products over the tile (one barrier at its end)
           relate_tile_products(n, ring.buf + (size_t)b * ring.tile_floats, neg, rt, sm.den, subj, sm.inner, sm.sc);
+          DFOL_TSTAMP(4);
           // every thread is past its last read of the slot: refill it with the tile nbuf hops ahead
           if (tid == 0 && krel + ring.nbuf < rel_count) issue_tile(krel + ring.nbuf);
           // phase C (thread-local): posterior of the kept role replaces the attention
           if (tid < n) sm.cur[tid] = nwv + slog(1.0f - relate_kept_q(tid, subj, sm.inner, sm.sc));
           __syncthreads();
+          DFOL_TSTAMP(5);
           ++krel;
           break;
         }
@@ -365,6 +411,9 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
         break;
     }
   }
+#ifdef DFOL_PROG_TIMING
+  if (blockIdx.x == 0 && threadIdx.x == 0) dfol_tstamps[8 + 6] = clock64();
+#endif
 }
 
 }  // namespace dfol
@@ -375,6 +424,12 @@ using namespace dfol;
 #define DFOL_PROGRAM_FWD_ENTRY dfol_program_fwd_fast
 #else
 #define DFOL_PROGRAM_FWD_ENTRY dfol_program_fwd
+#endif
+
+#ifdef DFOL_PROG_TIMING
+extern "C" int dfol_prog_timing_read(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, dfol_tstamps, sizeof(long long) * n);
+}
 #endif
 
 extern "C" int DFOL_PROGRAM_FWD_ENTRY(const int32_t* instr, const int32_t* q_instr, const int32_t* opts,

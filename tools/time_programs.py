@@ -10,8 +10,9 @@ import bench
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--workload', default='c3')
+ap.add_argument('--batch', type=int, default=0)
 a = ap.parse_args()
-args = argparse.Namespace(workload=a.workload, gemm='bf16', local_batch=0, pool=1, mode='infer')
+args = argparse.Namespace(workload=a.workload, gemm='bf16', local_batch=a.batch, pool=1, mode='infer')
 dev = torch.device('cuda', 0)
 ont, interp, host_batches, B = bench.build_world(args, 0, dev)
 pb = host_batches[0].to_cuda(0)
