@@ -89,6 +89,16 @@ class TensorCorePath(object):
         self.engine = engine
         self.w = engine.w
         self._ops = None
+        self._side = {}
+
+    def side_stream(self, device):
+        """Second stream for the attribute chain: its object-level GEMMs (T rows, < 148 tiles) leave most SMs idle, so
+        they run beside the pair-level kernels of the relation chain; joined with events before the interpreter (forward)
+        and before the shared first-layer gradients (backward)."""
+        key = str(device)
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device)
+        return self._side[key]
 
     def operands(self, device):
         key = tuple(p.data_ptr() for p in self.w.parameters())
@@ -165,15 +175,25 @@ class TensorCorePath(object):
         call('dfol_obj_finish', ptr(features), features.stride(0), D, ptr(obj), ldo, F, ptr(obj16), p['Op'], T, st)
         sc.obj, sc.obj16, sc.x16 = obj, obj16, x16
 
-        # attribute chain (bf16 activations) -> attribute table (all C concept columns)
-        h1a = bf(T, p['Hap'])
-        self._tc(obj16, ops.wa1, h1a, Ha, p['Op'], w.attr[0].bias, K.ACT_ELU, st)
-        h2a = bf(T, p['Ep'])
-        self._tc(h1a, ops.wa2, h2a, E, p['Hap'], w.attr[1].bias, K.ACT_SIGMOID, st)
-        attr_ll = torch.empty(layout.attr_size, device=dev, dtype=torch.float32)
-        obj_table = {'row_img': layout.obj_img, 'img_row': layout.obj_row, 'img_blk': layout.attr_blk,
-                     'img_stride': layout.attr_stride}
-        self._tc(h2a, ops.we, attr_ll, C, p['Ep'], w.emb.bias, K.ACT_LOGSIGMOID, st, table=obj_table)
+        # attribute chain (bf16 activations) -> attribute table (all C concept columns), on the side stream
+        main = torch.cuda.current_stream(dev)
+        # (per-kernel tracing keeps everything on one stream so that the CUDA-event table shows isolated kernel times)
+        side = main if capi.trace is not None else self.side_stream(dev)
+        ev_obj = torch.cuda.Event()
+        ev_obj.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ev_obj)
+            st2 = side.cuda_stream
+            h1a = bf(T, p['Hap'])
+            self._tc(obj16, ops.wa1, h1a, Ha, p['Op'], w.attr[0].bias, K.ACT_ELU, st2)
+            h2a = bf(T, p['Ep'])
+            self._tc(h1a, ops.wa2, h2a, E, p['Hap'], w.attr[1].bias, K.ACT_SIGMOID, st2)
+            attr_ll = torch.empty(layout.attr_size, device=dev, dtype=torch.float32)
+            obj_table = {'row_img': layout.obj_img, 'img_row': layout.obj_row, 'img_blk': layout.attr_blk,
+                         'img_stride': layout.attr_stride}
+            self._tc(h2a, ops.we, attr_ll, C, p['Ep'], w.emb.bias, K.ACT_LOGSIGMOID, st2, table=obj_table)
+            ev_attr = torch.cuda.Event()
+            ev_attr.record(side)
         sc.attr_ll = attr_ll
         sc.attr_h = [h1a, h2a]
 
@@ -240,6 +260,7 @@ class TensorCorePath(object):
         sc.rel_ll = rel_ll
         sc.rel_h = [h1r, h2r]
         sc.uv, sc.geo = uv, geo
+        main.wait_event(ev_attr)  # the interpreter reads both tables
         return sc
 
     # -------------------------------------------------------------------------------------------- backward
@@ -301,17 +322,26 @@ class TensorCorePath(object):
         merged = Ha == Hap == Hp == H and Hp % 128 == 0
         a0, a1, r0, r1 = w.attr[0], w.attr[1], w.rel[0], w.rel[1]
 
-        # ---- attribute table layer -> layer 2 -> layer 1
-        sa = eng._slice_tables(cp.attr_slices, lay.B, dev, 'attr_slices', cp)
-        if sa['count']:
-            dz2a = self._table_backward(g_attr, sa, scene.attr_ll, lay.attr_blk, lay.attr_stride, lay.obj_row,
-                                        lay.img_n, lay.max_n, T, w.emb.weight, G(w.emb.weight), G(w.emb.bias),
-                                        scene.attr_h[1], G(a1.bias), st, 'attr')
-            self._wgrad(dz2a, E, scene.attr_h[0], Ha, G(a1.weight), st)
-            self._dgrad(dz2a, ops.wa2t, dcat[:, :Hap], Ha, Ep, scene.attr_h[0], K.MUL_ELU_GRAD, st)
-            call('dfol_colsum_bf16', ptr(dcat), Kc, T, Ha, ptr(G(a0.bias)), st)
-            if not merged:
-                self._wgrad(dcat, Ha, scene.obj16, ldo, G(a0.weight), st)
+        # ---- attribute table layer -> layer 2 -> layer 1 (side stream, beside the relation chain)
+        main = torch.cuda.current_stream(dev)
+        side = main if capi.trace is not None else self.side_stream(dev)
+        sa = eng._slice_tables(cp.attr_slices, lay.B, dev, 'attr_slices', cp)  # (first use uploads on `main`)
+        ev_pb = torch.cuda.Event()
+        ev_pb.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ev_pb)
+            st2 = side.cuda_stream
+            if sa['count']:
+                dz2a = self._table_backward(g_attr, sa, scene.attr_ll, lay.attr_blk, lay.attr_stride, lay.obj_row,
+                                            lay.img_n, lay.max_n, T, w.emb.weight, G(w.emb.weight), G(w.emb.bias),
+                                            scene.attr_h[1], G(a1.bias), st2, 'attr')
+                self._wgrad(dz2a, E, scene.attr_h[0], Ha, G(a1.weight), st2)
+                self._dgrad(dz2a, ops.wa2t, dcat[:, :Hap], Ha, Ep, scene.attr_h[0], K.MUL_ELU_GRAD, st2)
+                call('dfol_colsum_bf16', ptr(dcat), Kc, T, Ha, ptr(G(a0.bias)), st2)
+                if not merged:
+                    self._wgrad(dcat, Ha, scene.obj16, ldo, G(a0.weight), st2)
+            ev_attr = torch.cuda.Event()
+            ev_attr.record(side)
 
         # ---- relation table layer -> layer 2 -> pair hidden layer
         sr = eng._slice_tables(cp.rel_slices, lay.B, dev, 'rel_slices', cp)
@@ -348,6 +378,7 @@ class TensorCorePath(object):
                 self._wgrad(dcat[:, Hap:], H, scene.obj16, ldo, gw1[:, :ldo], st)
                 self._wgrad(dcat[:, Hap + Hp:], H, scene.obj16, ldo, gw1[:, ldo:2 * ldo], st)
 
+        main.wait_event(ev_attr)  # dcat[:, :Hap] and the attribute-side gradients are complete
         if merged:
             gw1 = G(r0.weight)
             if capi.trace is not None:
