@@ -414,21 +414,43 @@ __global__ void __launch_bounds__(256) rel_slots_fwd_kernel(
                                    : make_float2(0.f, 0.f);
     }
   }
-  for (int l = warp; l < cn; l += 8) {
-    const __nv_bfloat16* hrow = hs + (r0 + l) * ldh;
-    float2 h[NC];
+  // two rows per warp iteration (10 row loads in flight per lane), pointer-increment addressing
+  const __nv_bfloat16* hp = hs + (r0 + warp) * ldh + 2 * lane;
+  const long long step = 8 * ldh;
+  for (int l = warp; l < cn; l += 16, hp += 2 * step) {
+    const bool two = l + 8 < cn;
+    uint32_t raw0[NC], raw1[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-      const int e = 2 * lane + 64 * k;
-      h[k] = (e < E) ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hrow + e)) : make_float2(0.f, 0.f);
+      const bool ok = 2 * lane + 64 * k < E;
+      raw0[k] = ok ? *reinterpret_cast<const uint32_t*>(hp + 64 * k) : 0u;
+      raw1[k] = (ok && two) ? *reinterpret_cast<const uint32_t*>(hp + step + 64 * k) : 0u;
+    }
+    float2 h0[NC], h1[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      h0[k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw0[k]));
+      h1[k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw1[k]));
     }
 #pragma unroll
     for (int j = 0; j < S; ++j) {
-      float z = 0.f;
+      if (j < Sb) {  // block-uniform
+        float z0 = 0.f, z1 = 0.f;
 #pragma unroll
-      for (int k = 0; k < NC; ++k) z = fmaf(h[k].x, wj[j][k].x, fmaf(h[k].y, wj[j][k].y, z));
-      z = warp_sum(z);
-      if (lane == 0) zs[j][l] = z;
+        for (int k = 0; k < NC; ++k) {
+          z0 = fmaf(h0[k].x, wj[j][k].x, fmaf(h0[k].y, wj[j][k].y, z0));
+          z1 = fmaf(h1[k].x, wj[j][k].x, fmaf(h1[k].y, wj[j][k].y, z1));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          z0 += __shfl_xor_sync(0xffffffffu, z0, o);
+          z1 += __shfl_xor_sync(0xffffffffu, z1, o);
+        }
+        if (lane == 0) {
+          zs[j][l] = z0;
+          if (two) zs[j][l + 8] = z1;
+        }
+      }
     }
   }
   __syncthreads();
