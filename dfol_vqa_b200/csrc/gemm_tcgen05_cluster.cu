@@ -1,14 +1,15 @@
-// Cluster-of-two, weights-resident bf16 tensor-core GEMM for the pair-level layers (sm_100a):
+// Cluster-split, weights-resident bf16 tensor-core GEMM for the pair-level layers (sm_100a):
 //   C[M, N] = epilogue(A[M, K] . B[N, K]^T),  M ~ 10^5..10^6 pair rows, small weight matrix (N <= 384, K <= 320).
 //
-// Two CTAs on two SMs form a thread-block cluster and split N: CTA r keeps rows [r*BNh, (r+1)*BNh) of B resident in
-// shared memory (<= 96 KB instead of the whole matrix), which leaves room for a deep A ring and for TMA-staged
-// epilogue tiles.  Per CTA:
-//   warp 0 (one lane) : TMA producer.  Every 128 x 64 A block is fetched ONCE per cluster: CTA r loads rows
-//                       [64r, 64r+64) with .multicast::cluster into both CTAs' rings; the epilogue operand tile
-//                       (saved activation of the dgrad) is a plain TMA load of this CTA's columns.
+// The CTAs of a thread-block cluster (two in practice; the code handles 1-4) sit on different SMs and split N: CTA r
+// keeps rows [r*BNh, (r+1)*BNh) of B resident in shared memory (<= 96 KB instead of the whole matrix), which leaves
+// room for the A ring and for TMA-staged epilogue tiles.  Per CTA:
+//   warp 0 (one lane) : TMA producer.  Every 128 x 64 A block is fetched ONCE per cluster: its two 64-row boxes are
+//                       dealt round-robin to the CTAs, each loaded with .multicast::cluster into all rings; the
+//                       epilogue operand tile (saved activation of the dgrad) is a plain TMA load of this CTA's
+//                       columns.
 //   warp 1 (one lane) : tcgen05.mma issuer, 128 x BNh x 16, fp32 accumulators double buffered in TMEM;
-//                       tcgen05.commit.multicast releases a ring stage in BOTH CTAs.
+//                       tcgen05.commit.multicast releases a ring stage in ALL CTAs of the cluster.
 //   warps 2..9        : epilogue: tcgen05.ld, bias + activation or activation-derivative multiplier (operand read from
 //                       the 128B-swizzled shared tile, conflict free), bf16 result written to a swizzled shared tile
 //                       and stored with cp.async.bulk.tensor (full 128-byte lines) -- no per-thread global access.
@@ -22,6 +23,7 @@ constexpr int CL_BK = 64;
 constexpr int CL_THREADS = 64 + 256;
 constexpr int CL_MAX_STAGES = 8;
 constexpr int CL_MAX_KB = 5;
+constexpr int CL_ABOX = 2;        // row boxes per A block, dealt round-robin to the CTAs of the cluster
 constexpr int CL_EC = 3;          // in-place operand/result tiles of the dgrad (operand prefetched two tiles ahead)
 constexpr int CL_MAX_CH = 6;      // 16-column chunks per epilogue warp (192 / 2 / 16)
 
@@ -31,12 +33,18 @@ struct ClParams {
   int BNh;              // columns per CTA (multiple of 64)
   int stages;
   int act, mul_mode;    // mul_mode != NONE: epilogue operand tile (bf16, same shape as C) is loaded through tmap_e
-  int store_boxes[2];   // 64-column boxes of C this CTA stores (boxes entirely beyond the stored width are skipped)
+  int cluster_size;     // CTAs per cluster (the launch attribute)
+  int n_store;          // stored width of C (64-column boxes entirely beyond it are skipped)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
   return r;
 }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -87,7 +95,7 @@ __device__ __forceinline__ float cl_act(float x) {
 }
 
 template <int ACT, bool HAS_E>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
+__global__ void __launch_bounds__(CL_THREADS, 1)
     gemm_bf16_tc_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_e,
                                 ClParams p) {
@@ -103,8 +111,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
   __shared__ float bias_s[192];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const uint32_t rank = cluster_ctarank(), CS = (uint32_t)p.cluster_size;
+  const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
+  const int cluster_id = blockIdx.x / (int)CS, num_clusters = gridDim.x / (int)CS;
   const int num_kb = p.K / CL_BK;
   const int num_tiles = (p.M + CL_BM - 1) / CL_BM;
   const int BNh = p.BNh;
@@ -123,7 +132,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
 
   if (threadIdx.x == 0) {
     mbar_init(&b_full, 1);
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 2); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], CS); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     for (int i = 0; i < CL_EC; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -161,11 +170,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t phase = (it / p.stages) & 1;
-          mbar_wait(&a_empty[s], phase ^ 1);  // released by the MMAs of BOTH CTAs
+          mbar_wait(&a_empty[s], phase ^ 1);  // released by the MMAs of ALL CTAs of the cluster
           mbar_expect_tx(&a_full[s], a_bytes);
-          // this CTA fetches rows [64 rank, 64 rank + 64) of the block for both CTAs
-          tma_load_2d_mc(&tmap_a, &a_full[s], a_tiles + (size_t)s * a_bytes + rank * (a_bytes / 2), kb * CL_BK,
-                         tile * CL_BM + (int)rank * 64, (uint16_t)3);
+          // the row boxes of the block are dealt round-robin to the CTAs; each is multicast to every ring
+          for (uint32_t j = rank; j < CL_ABOX; j += CS)
+            tma_load_2d_mc(&tmap_a, &a_full[s], a_tiles + (size_t)s * a_bytes + j * (a_bytes / CL_ABOX), kb * CL_BK,
+                           tile * CL_BM + (int)j * (CL_BM / CL_ABOX), cmask);
         }
       }
     }
@@ -191,7 +201,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < CL_BK / 16; ++k)
             umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit_mc(&a_empty[s], (uint16_t)3);  // the stage is free in both CTAs once these MMAs have read it
+          umma_commit_mc(&a_empty[s], cmask);  // the stage is free everywhere once every CTA's MMAs have read it
         }
         umma_commit(&acc_full[buf]);
       }
@@ -278,7 +288,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       cl_named_bar(1, 256);
       if (issuer) {
-        const int my_boxes = rank == 0 ? p.store_boxes[0] : p.store_boxes[1];  // (no dynamic param indexing)
+        const int my_cols = min(max(p.n_store - n0, 0), BNh);
+        const int my_boxes = (my_cols + 63) / 64;
         for (int j = 0; j < my_boxes; ++j)
           tma_store_2d(&tmap_c, stage + (size_t)j * box_bytes, n0 + 64 * j, tile * CL_BM);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -319,13 +330,14 @@ static int launch_cluster(const char* who, const void* A, int64_t lda, const voi
                "%s: multiplier operand must be 16-byte aligned with ld %% 8 == 0", who);
   ClParams p;
   p.bias = bias; p.M = M; p.N = N; p.K = K; p.act = act; p.mul_mode = mul_mode;
-  p.BNh = ((n_store + 1) / 2 + 63) / 64 * 64;  // half of the stored width, rounded up to whole 64-column boxes
+  // columns per CTA and cluster size.  Two CTAs (half of the stored width each, whole 64-column boxes) measured best:
+  // clusters of 3-4 CTAs leave room for a 7-8 stage A ring but run 2x slower (every ring stage is released by a
+  // commit from every CTA of the cluster, and the lockstep of 3-4 SMs costs more than the deeper ring gains).
+  p.BNh = ((n_store + 1) / 2 + 63) / 64 * 64;
   DFOL_REQUIRE(p.BNh <= 192, "%s: at most 384 output columns", who);
-  for (int r = 0; r < 2; ++r) {
-    int cols = n_store - r * p.BNh;
-    cols = cols < 0 ? 0 : (cols > p.BNh ? p.BNh : cols);
-    p.store_boxes[r] = (cols + 63) / 64;
-  }
+  const int CS = (n_store + p.BNh - 1) / p.BNh;
+  p.n_store = n_store;
+  p.cluster_size = CS;
   const int num_kb = K / CL_BK;
   const size_t b_bytes = (size_t)num_kb * p.BNh * CL_BK * 2;
   const size_t box = (size_t)CL_BM * 128;
@@ -362,9 +374,24 @@ static int launch_cluster(const char* who, const void* A, int64_t lda, const voi
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int tiles = (M + CL_BM - 1) / CL_BM;
-  int clusters = sms / 2;
+  int clusters = sms / CS;
   if (clusters > tiles) clusters = tiles;
-  kernel<<<2 * clusters, CL_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, mc, me, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CS * clusters, 1, 1);
+  cfg.blockDim = dim3(CL_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  {
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ma, mb, mc, me, p);
+    if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return (int)e; }
+  }
   return finish_launch(who);
 }
 
