@@ -248,3 +248,58 @@ def test_host_step_pipeline_matches_direct_steps():
     assert len(piped) == len(direct)
     for a, b in zip(piped, direct):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('workload,batch,n,mode', [('c1', 256, 48, 'bf16'), ('c1', 256, 48, 'fp32'), ('c3', 256, 100, 'bf16')])
+def test_full_size_question_independence(workload, batch, n, mode):
+    """Size-independent property at BASELINE.json's full sizes: every question only depends on its own image, so the
+    log-probabilities of the first questions of the full batch are BIT-identical to running those questions alone
+    (forward kernels have no cross-question reductions), and finite everywhere."""
+    from dfol_vqa_b200 import synth
+    from dfol_vqa_b200.ontology import synthetic_ontology
+    from dfol_vqa_b200.programs import ProgramCollater
+    dims = dict(box=2048, feat=512, hidden=256, emb=300)
+    ont = synthetic_ontology(seed=1, embedding_dim=300, concept_num=2335, relation_num=333, category_num=31, class_num=53)
+    interp = helpers.build_interpreter(ont, dims, seed=0, gemm_mode=mode, emb_bias=-4.0)
+    if workload == 'c3':
+        questions = synth.make_relation_chain_questions(ont, batch, 9, seed=5)
+    else:
+        questions = synth.make_questions(ont, batch, 'verify_rel', 1, 3, seed=5, relate_prob=0.35)
+    feats, bidx = synth.make_object_features([n] * batch, 2048, seed=6)
+    sub = 16
+    full = ProgramCollater(1, lambda qs: (feats, bidx)).collate(questions)[0].to_cuda(0)
+    part = ProgramCollater(1, lambda qs: (feats[:sub * n].clone(), bidx[:sub * n].clone())).collate(
+        json.loads(json.dumps(questions[:sub])))[0].to_cuda(0)
+    with torch.no_grad():
+        lp_full = interp([full], True)['log_probability'].clone()
+        lp_part = interp([part], True)['log_probability'].clone()
+    assert lp_full.numel() == batch and bool(torch.isfinite(lp_full).all())
+    assert bool((lp_full <= 1e-6).all())
+    assert torch.equal(lp_full[:sub], lp_part), (lp_full[:sub] - lp_part).abs().max()
+
+
+def test_full_size_gradient_additivity():
+    """Size-independent property of the training step at the full c1 size: loss and gradients of the whole batch equal
+    the accumulation over two sub-batches (the reference's split_num semantics, trainer.py:429-442)."""
+    from dfol_vqa_b200 import synth
+    from dfol_vqa_b200.interpreter import FusedTrainStep
+    from dfol_vqa_b200.ontology import synthetic_ontology
+    from dfol_vqa_b200.programs import ProgramCollater
+    dims = dict(box=2048, feat=512, hidden=256, emb=300)
+    batch, n = 256, 48
+    ont = synthetic_ontology(seed=1, embedding_dim=300, concept_num=2335, relation_num=333, category_num=31, class_num=53)
+    interp = helpers.build_interpreter(ont, dims, seed=0, gemm_mode='bf16', emb_bias=-4.0)
+    questions = synth.make_questions(ont, batch, 'verify_rel', 1, 3, seed=15, relate_prob=0.35)
+    feats, bidx = synth.make_object_features([n] * batch, 2048, seed=16)
+    full = ProgramCollater(1, lambda qs: (feats, bidx)).collate(json.loads(json.dumps(questions)))
+    halves = ProgramCollater(2, helpers.slicing_source(feats, bidx)).collate(json.loads(json.dumps(questions)))
+    assert len(halves) == 2
+    step = FusedTrainStep(interp)
+    loss_full = float(step.forward_backward(helpers.to_cuda(full), global_question_num=batch))
+    g_full = step.flat_grad.clone()
+    loss_split = float(step.forward_backward(helpers.to_cuda(halves), global_question_num=batch))
+    g_split = step.flat_grad.clone()
+    assert abs(loss_full - loss_split) <= 1e-4 * max(1.0, abs(loss_full))
+    scale = float(g_full.abs().max())
+    assert scale > 0 and bool(torch.isfinite(g_full).all())
+    assert float((g_full - g_split).abs().max()) <= 2e-3 * scale
