@@ -28,11 +28,18 @@ BINARY, QUERY, STATEMENT = 0, 1, 2
 K = capi.K  # constants mirrored from include/dfol_b200.h
 
 
+_SPLIT_CACHE = {}
+
+
 def _split_neg(token):
-    t = token.strip()
-    if _NEG_RE.match(t) is not None:
-        return True, t[4:-1]
-    return False, t
+    """(negated, bare token) of a predicate token; ``not(x)`` detection as util.detect_negations (util.py:68-85)."""
+    hit = _SPLIT_CACHE.get(token)
+    if hit is None:
+        t = token.strip()
+        hit = (True, t[4:-1]) if (t.startswith('not(') and _NEG_RE.match(t) is not None) else (False, t)
+        if len(_SPLIT_CACHE) < 100000:
+            _SPLIT_CACHE[token] = hit
+    return hit
 
 
 def _blank(tok):
@@ -66,14 +73,22 @@ class ProgramCompiler(object):
         self._a2i = ontology._vocabulary['arg_to_idx']
         self._rel_rev = ontology._relation_reveresed_index
         self._option_cache = {}
+        self._attr_cache = {}
+        self._rel_cache = {}
 
     def _attr_word(self, tok):
-        neg, t = _split_neg(tok)
-        return (self._a2i[t] - 1), neg
+        hit = self._attr_cache.get(tok)
+        if hit is None:
+            neg, t = _split_neg(tok)
+            hit = self._attr_cache[tok] = ((self._a2i[t] - 1), neg)
+        return hit
 
     def _rel_word(self, tok):
-        neg, t = _split_neg(tok)
-        return self._rel_rev[self._a2i[t] - 1], neg
+        hit = self._rel_cache.get(tok)
+        if hit is None:
+            neg, t = _split_neg(tok)
+            hit = self._rel_cache[tok] = (self._rel_rev[self._a2i[t] - 1], neg)
+        return hit
 
     def _query(self, category, name):
         key = category if category not in ('name', 'type') else name
@@ -164,7 +179,10 @@ class ProgramCompiler(object):
             name = slot._op_name
             args = slot._arguments
             mask = slot._mask
-            mask = [1.0] * B if mask is None else [float(m) for m in mask]
+            if mask is None:
+                mask = [1.0] * B
+            else:
+                mask = mask.tolist() if hasattr(mask, 'tolist') else [float(m) for m in mask]
             terminal = getattr(slot, '_is_terminal', False) or name in capi.TERMINAL_NAMES
             if not terminal and name == 'select':
                 if branch_count >= 1:

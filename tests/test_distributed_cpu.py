@@ -140,3 +140,24 @@ def test_compiler_relation_slots_are_consistent():
             assert a[0] == b[0] and a[2] == b[2] and b[3] == rel_index[a[1]]
         stride = [(c * c + 3) // 4 * 4 for c in counts]
         assert slot.rel_slot_size == max(1, int(sum(k * s for k, s in zip(n_slots, stride))))
+
+
+def test_collater_attaches_compiled_programs():
+    """ProgramCollater(compiler=...) lowers the programs at collate time (DataLoader worker) and the result pickles."""
+    import pickle
+    from dfol_vqa_b200 import synth
+    from dfol_vqa_b200.compiler import ProgramCompiler
+    from dfol_vqa_b200.ontology import synthetic_ontology
+    from dfol_vqa_b200.programs import ProgramCollater
+    ont = synthetic_ontology(160, 24, 5, 4, seed=1, embedding_dim=16)
+    questions = synth.make_questions(ont, 10, 'verify_rel', 1, 3, seed=7, relate_prob=0.7)
+    counts = synth.object_counts(10, 9, True, seed=8)
+    feats, bidx = synth.make_object_features(counts, 32, seed=9)
+    comp = ProgramCompiler(ont, relation_slots=True)
+    pb = ProgramCollater(1, lambda qs: (feats, bidx), compiler=comp).collate(questions)[0]
+    assert pb._dfol_counts == counts
+    cp = pb._dfol_compiled[False]
+    ref = comp.compile(pb, counts)
+    assert (cp.instr == ref.instr).all() and (cp.q_instr == ref.q_instr).all() and cp.rel_slices == ref.rel_slices
+    clone = pickle.loads(pickle.dumps(pb))
+    assert (clone._dfol_compiled[False].instr == cp.instr).all()
