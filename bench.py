@@ -247,8 +247,20 @@ def main():
     device = torch.device('cuda', local_rank)
     group = None
     if world > 1:
-        dist.init_process_group('nccl', device_id=device)
-        group = dist.group.WORLD
+        # NCCL prints its version banner on fd 1 when the communicator is created: keep stdout to the ONE JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=device)
+            group = dist.group.WORLD
+            warm = torch.zeros(1, device=device)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     ont, interp, host_batches, B = build_world(args, rank, device)
     wl = WORKLOADS[args.workload]

@@ -2,7 +2,7 @@
 import json
 import sys
 
-d = json.load(open(sys.argv[1]))
+d = json.loads([l for l in open(sys.argv[1]) if l.startswith('{')][-1])
 print('value %.0f q/s  %.3f ms/step | e2e %.0f q/s %.3f ms | launches %d' % (
     d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['gpu_launches']))
 r = d['roofline']
