@@ -55,13 +55,19 @@ class CompiledPrograms(object):
 
     __slots__ = ('instr', 'q_instr', 'opts', 'lp_num', 'kind', 'options', 'seg', 'names', 'question_num',
                  'g_attr_size', 'g_rel_size', 'attr_slices', 'rel_slices', 'terminal', 'lp_owner', 'device_cache',
-                 'alg_bytes', 'slot_wrow', 'img_slot', 'slot_blk', 'rel_slot_size', 'max_slots')
+                 'alg_bytes', 'slot_wrow', 'img_slot', 'slot_blk', 'rel_slot_size', 'max_slots', 'mod_plan',
+                 'mod_descs', 'mod_rows')
 
 
 class ProgramCompiler(object):
 
-    def __init__(self, ontology, normalize=True, hard_mode=False, relation_slots=False):
-        """relation_slots: demand-driven relation table.  Instead of indexing a dense [nR] relation table, relate /
+    def __init__(self, ontology, normalize=True, hard_mode=False, relation_slots=False, modulated=False):
+        """modulated: attention-transfer modulations are active (FastGQAInterpreter built with the three attention
+        networks): every filter-like / relate-like sub-operator of a slot that has at least one non-blank predicate gets
+        one row of (alpha, beta, c, d) per predicate (FilterBatch.forward / RelateBatch.forward apply_modulations,
+        batch_base_ops.py:400-402, :588-594); the instruction words MOD / MOD2 index those rows.
+
+        relation_slots: demand-driven relation table.  Instead of indexing a dense [nR] relation table, relate /
         choose_rel operands are renumbered per image to *slots* 0..k_b-1 (the distinct relations the image's own
         program uses); the scene build then evaluates only those k_b columns of ClassifierOracle.
         compute_all_log_likelihood_2 (classifier_oracle.py:154 computes all and slices)."""
@@ -69,6 +75,7 @@ class ProgramCompiler(object):
         self.normalize = normalize
         self.hard_mode = hard_mode
         self.relation_slots = relation_slots
+        self.modulated = modulated
         self._rel_concept = list(ontology._relation_index)
         self._a2i = ontology._vocabulary['arg_to_idx']
         self._rel_rev = ontology._relation_reveresed_index
@@ -146,8 +153,35 @@ class ProgramCompiler(object):
             gr[0] += len(cols) * r_stride[q]
             return off
 
-        def emit(q, op, flags=0, a0=-1, a1=-1, a2=-1, out=-1, ga0=-1, ga1=-1, grr=-1):
-            prog[q].append((op, flags | hard if op >= K.OP_EXIST else flags, a0, a1, a2, out, ga0, ga1, grr, 0, 0, 0))
+        def emit(q, op, flags=0, a0=-1, a1=-1, a2=-1, out=-1, ga0=-1, ga1=-1, grr=-1, mod=-1, mod2=-1):
+            prog[q].append((op, flags | hard if op >= K.OP_EXIST else flags, a0, a1, a2, out, ga0, ga1, grr, mod, mod2,
+                            0))
+
+        modulated = self.modulated
+        mod_plan = []                        # (slot, key, rows, base row), in row order
+        mod_descs = []                       # per slot: what the attention-transfer state passes need
+        mod_rows = [0]
+
+        def alloc(slot_i, key, rows):
+            """Reserve ``rows`` modulation rows for sub-operator ``key`` of slot ``slot_i``; -1 when modulations are off."""
+            if not modulated:
+                return -1
+            base = mod_rows[0]
+            mod_plan.append((slot_i, key, rows, base))
+            mod_rows[0] += rows
+            return base
+
+        def at(base, off):
+            return base + off if base >= 0 else -1
+
+        def flat_rows(lists):
+            """(flattened tokens, owner question per row, first row of every question) of per-question option lists."""
+            flat, owner, start = [], [], []
+            for q, l in enumerate(lists):
+                start.append(len(flat))
+                flat += list(l)
+                owner += [q] * len(l)
+            return flat, owner, start
 
         def name_flags(name_tok, roundtrip):
             """(column, flags) of the name select of a relate-like op."""
@@ -194,30 +228,48 @@ class ProgramCompiler(object):
                 toks = args[0] if args else [None] * B
                 blank = [t is None or t.lower() in ('_', 'scene') for t in toks]
                 any_neg = any(_split_neg(t)[0] for t, b in zip(toks, blank) if not b)
+                sel_toks = [None if b else t for t, b in zip(toks, blank)]
+                base = alloc(i, 'select', B) if not all(blank) else -1
+                mod_descs.append({'op': name, 'select': sel_toks if not all(blank) else None})
                 for q in range(B):
                     if blank[q]:
                         names[q] = 'entity'
-                        emit(q, K.OP_SELECT, 0, -1)
+                        emit(q, K.OP_SELECT, 0, -1, mod=at(base, q))
                     else:
                         names[q] = toks[q]
                         col, neg = self._attr_word(toks[q])
                         fl = (K.F_NEG if neg else 0) | (K.F_ROUNDTRIP if any_neg and not neg else 0)
-                        emit(q, K.OP_SELECT, fl, col, ga0=attr_slice(q, col))
+                        emit(q, K.OP_SELECT, fl, col, ga0=attr_slice(q, col), mod=at(base, q))
             elif not terminal and name == 'filter':
                 toks = args[0]
                 valid = [mask[q] > 0 and not _blank(toks[q]) for q in range(B)]
                 # negation detection spans every non-blank predicate of the slot (mask-0 questions carry None)
                 any_neg = any(_split_neg(t)[0] for t in toks if not _blank(t))
+                fil_toks = [None if _blank(t) else t for t in toks]
+                has = any(t is not None for t in fil_toks)
+                base = alloc(i, 'filter', B) if has else -1
+                mod_descs.append({'op': name, 'filter': (fil_toks, None) if has else None})
                 for q in range(B):
                     if valid[q]:
                         col, neg = self._attr_word(toks[q])
                         fl = (K.F_NEG if neg else 0) | (K.F_ROUNDTRIP if any_neg and not neg else 0)
-                        emit(q, K.OP_FILTER, fl, col, ga0=attr_slice(q, col))
+                        emit(q, K.OP_FILTER, fl, col, ga0=attr_slice(q, col), mod=at(base, q))
+                    elif mask[q] > 0 and base >= 0:
+                        # blank predicate of a participating question in a slot that has predicates: the reference
+                        # passes the attention through and still applies the row's modulation (batch_base_ops.py:385-402)
+                        emit(q, K.OP_FILTER, 0, -1, mod=at(base, q))
             elif name in ('relate', 'verify_rel'):
                 rels, subj, nms = args[0], args[1], args[2]
                 any_neg = any(_split_neg(t)[0] for t in rels if not _blank(t))
                 name_valid = [not (t is None or t.lower() in ('_', 'scene')) for t in nms]
                 any_name_neg = any(_split_neg(t)[0] for t, v in zip(nms, name_valid) if v)
+                sel_toks = [t if v else None for t, v in zip(nms, name_valid)]
+                rel_toks = [None if _blank(t) else t for t in rels]
+                has_sel, has_rel = any(name_valid), any(t is not None for t in rel_toks)
+                base_sel = alloc(i, 'select', B) if has_sel else -1
+                base_rel = alloc(i, 'relate', B) if has_rel else -1
+                mod_descs.append({'op': name, 'select': sel_toks if has_sel else None,
+                                  'relate': (rel_toks, None, [1.0 if f else 0.0 for f in subj]) if has_rel else None})
                 for q in range(B):
                     if mask[q] > 0 and not _blank(rels[q]):
                         col, neg = self._rel_word(rels[q])
@@ -225,8 +277,11 @@ class ProgramCompiler(object):
                         fl = (K.F_NEG if neg else 0) | (K.F_ROUNDTRIP if any_neg and not neg else 0) | nfl
                         fl |= K.F_SUBJECT if subj[q] else 0
                         emit(q, K.OP_RELATE, fl, rel_operand(q, col), ncol,
-                             ga1=attr_slice(q, ncol) if ncol >= 0 else -1, grr=rel_slice(q, col))
+                             ga1=attr_slice(q, ncol) if ncol >= 0 else -1, grr=rel_slice(q, col),
+                             mod=at(base_rel, q), mod2=at(base_sel, q))
                         names[q] = nms[q] if name_valid[q] else 'entity'
+                    elif mask[q] > 0 and modulated and (has_sel or has_rel):
+                        raise NotImplementedError('blank relation of a participating question with attention transfer')
                 if name == 'verify_rel':
                     assert all(m > 0 for m in mask), 'one terminal operator per program batch'
                     for q in range(B):
@@ -243,13 +298,17 @@ class ProgramCompiler(object):
                         emit(q, op, out=q)
                     lp_num = B
                     result.update(kind=STATEMENT if name == 'end' else BINARY, lp_owner=list(range(B)))
+                    mod_descs.append({'op': name})
                 elif name == 'verify_attrs':
                     lists = args[0]
                     any_neg = any(_split_neg(t)[0] for l in lists for t in l)
+                    flat, owner, first = flat_rows(lists)
+                    base = alloc(i, 'filter', len(flat))
+                    mod_descs.append({'op': name, 'filter': (flat, owner)})
                     for q in range(B):
                         start, cnt, cols = option_words(q, lists[q], 'attr')
                         emit(q, K.OP_VERIFY_ATTRS, K.F_ROUNDTRIP if any_neg else 0, start, cnt, out=q,
-                             ga0=attr_slice(q, cols))
+                             ga0=attr_slice(q, cols), mod=at(base, first[q]))
                     lp_num = B
                     result.update(kind=BINARY, lp_owner=list(range(B)))
                 elif name in ('choose_attr', 'query_attr', 'all_same', 'all_different', 'two_same', 'two_different'):
@@ -261,12 +320,17 @@ class ProgramCompiler(object):
                     any_neg = any(_split_neg(t)[0] for l in lists for t in l)
                     norm = self.normalize and any(len(l) > 1 for l in lists)
                     fl = (K.F_ROUNDTRIP if any_neg else 0) | (K.F_NORMALISE if norm else 0)
+                    flat, flat_owner, first = flat_rows(lists)
+                    two = name in ('two_same', 'two_different')
+                    base = alloc(i, 'filter0' if two else 'filter', len(flat))
+                    base2 = alloc(i, 'filter1', len(flat)) if two else -1
+                    mod_descs.append({'op': name, 'filter': (flat, flat_owner), 'two': two})
                     if name in ('choose_attr', 'query_attr'):
                         seg, owner = [0], []
                         for q in range(B):
                             start, cnt, cols = option_words(q, lists[q], 'attr')
                             emit(q, K.OP_CHOOSE_ATTR, fl, start, cnt, out=lp_num,
-                                 ga0=attr_slice(q, cols))
+                                 ga0=attr_slice(q, cols), mod=at(base, first[q]))
                             lp_num += cnt
                             seg.append(lp_num)
                             owner += [q] * cnt
@@ -278,7 +342,7 @@ class ProgramCompiler(object):
                         for q in range(B):
                             start, cnt, cols = option_words(q, lists[q], 'attr')
                             emit(q, op, fl, start, cnt, out=q,
-                                 ga0=attr_slice(q, cols))
+                                 ga0=attr_slice(q, cols), mod=at(base, first[q]), mod2=at(base2, first[q]))
                         lp_num = B
                         result.update(kind=BINARY, lp_owner=list(range(B)))
                 elif name == 'choose_rel':
@@ -288,6 +352,12 @@ class ProgramCompiler(object):
                     name_valid = [not (t is None or t.lower() in ('_', 'scene')) for t in nms]
                     any_name_neg = any(_split_neg(t)[0] for t, v in zip(nms, name_valid) if v)
                     seg, owner = [0], []
+                    flat, flat_owner, first = flat_rows(lists)
+                    sel_toks = [t if v else None for t, v in zip(nms, name_valid)]
+                    base_sel = alloc(i, 'select', B) if any(name_valid) else -1
+                    base_rel = alloc(i, 'relate', len(flat))
+                    mod_descs.append({'op': name, 'select': sel_toks if any(name_valid) else None,
+                                      'relate': (flat, flat_owner, [1.0 if f else 0.0 for f in subj])})
                     for q in range(B):
                         start, cnt, cols = option_words(q, lists[q], 'rel')
                         ncol, nfl = name_flags(nms[q], any_name_neg)
@@ -295,7 +365,7 @@ class ProgramCompiler(object):
                         fl |= K.F_SUBJECT if subj[q] else 0
                         emit(q, K.OP_CHOOSE_REL, fl, start, cnt, ncol, out=lp_num,
                              ga1=attr_slice(q, ncol) if ncol >= 0 else -1,
-                             grr=rel_slice(q, cols))
+                             grr=rel_slice(q, cols), mod=at(base_rel, first[q]), mod2=at(base_sel, q))
                         lp_num += cnt
                         seg.append(lp_num)
                         owner += [q] * cnt
@@ -303,14 +373,20 @@ class ProgramCompiler(object):
                 elif name == 'compare':
                     toks, less = args[0], args[1]
                     any_neg = any(_split_neg(t)[0] for t in toks if not _blank(t))
+                    cmp_toks = [None if _blank(t) else t for t in toks]
+                    has = any(t is not None for t in cmp_toks)
+                    base = alloc(i, 'filter0', B) if has else -1
+                    base2 = alloc(i, 'filter1', B) if has else -1
+                    mod_descs.append({'op': name, 'filter': (cmp_toks, None) if has else None, 'two': True})
                     for q in range(B):
                         fl = K.F_IS_LESS if less[q] else 0
                         if _blank(toks[q]):
-                            emit(q, K.OP_COMPARE, fl, -1, out=2 * q)
+                            emit(q, K.OP_COMPARE, fl, -1, out=2 * q, mod=at(base, q), mod2=at(base2, q))
                         else:
                             col, neg = self._attr_word(toks[q])
                             fl |= (K.F_NEG if neg else 0) | (K.F_ROUNDTRIP if any_neg and not neg else 0)
-                            emit(q, K.OP_COMPARE, fl, col, out=2 * q, ga0=attr_slice(q, col))
+                            emit(q, K.OP_COMPARE, fl, col, out=2 * q, ga0=attr_slice(q, col), mod=at(base, q),
+                                 mod2=at(base2, q))
                     lp_num = 2 * B
                     result.update(kind=QUERY, options=list(zip(branch_names[0], names)),
                                   seg=list(range(0, 2 * B + 1, 2)), lp_owner=[q for q in range(B) for _ in (0, 1)])
@@ -324,6 +400,11 @@ class ProgramCompiler(object):
                 emit(q, K.OP_EXIST, out=q)
             lp_num = B
             result.update(kind=STATEMENT, terminal='end', lp_owner=list(range(B)))
+
+        for i, d in enumerate(mod_descs):  # state-pass wiring of the slots that were compiled
+            d['deps'] = list(deps[i])
+            m = slots[i]._mask
+            d['mask'] = None if m is None else [float(v) for v in (m.tolist() if hasattr(m, 'tolist') else m)]
 
         cp = CompiledPrograms()
         q_instr = np.zeros(B + 1, dtype=np.int32)
@@ -345,6 +426,9 @@ class ProgramCompiler(object):
         cp.terminal = result['terminal']
         cp.lp_owner = result['lp_owner']
         cp.device_cache = None
+        cp.mod_plan = mod_plan
+        cp.mod_descs = mod_descs
+        cp.mod_rows = mod_rows[0]
         # algorithmic bytes of one forward pass: every table slice read once + the log-probabilities written
         cp.alg_bytes = 4.0 * (sum(object_counts[s[0]] for s in attr_slices) +
                               sum(object_counts[s[0]] ** 2 for s in rel_slices) + lp_num)

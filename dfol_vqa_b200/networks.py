@@ -83,5 +83,30 @@ def build_networks(config, ontology):
                       ('freeze_relation_network', relation), ('freeze_embedding_network', embedding)):
         if config.get(flag, False):
             net.requires_grad_(False)
-    return {'featurizer_network': featurizer, 'attribute_network': attribute, 'relation_network': relation,
-            'embedding_network': embedding}
+    nets = {'featurizer_network': featurizer, 'attribute_network': attribute, 'relation_network': relation,
+            'embedding_network': embedding, 'forward_attention_network': None, 'backward_attention_network': None,
+            'attention_output_network': None}
+    if config.get('activate_attention_transfer', False):
+        nets.update(build_attention_networks(config['word_embedding_dim'], config['attention_transfer_state_dim'],
+                                             config.get('freeze_attention_network', False)))
+    return nets
+
+
+def build_attention_networks(word_embedding_dim, state_dim, freeze=False):
+    """The attention-transfer networks of GQAObjectBoxExperiment.build_neural_modules (reference :112-135): two
+    LSTMCells over [17 operator classes | attribute/relation flag | word embedding] and a 4-output Linear+Sigmoid whose
+    initial bias makes every modulation the identity (alpha = beta = c = 1, d = 0.5)."""
+    import math
+    output_dim, max_activation = 4, 10.0
+    forward = nn.LSTMCell(word_embedding_dim + 1 + 17, state_dim)
+    backward = nn.LSTMCell(word_embedding_dim + 1 + 17, state_dim)
+    output = nn.Sequential(nn.Linear(2 * state_dim, output_dim), nn.Sigmoid())
+    output[0].weight = nn.Parameter(torch.zeros(output_dim, 2 * state_dim))
+    bias = -math.log(max_activation - 1) * torch.ones(output_dim)
+    bias[3] = 0
+    output[0].bias = nn.Parameter(bias)
+    if freeze:
+        for net in (forward, backward, output):
+            net.requires_grad_(False)
+    return {'forward_attention_network': forward, 'backward_attention_network': backward,
+            'attention_output_network': output}

@@ -75,6 +75,14 @@ def is_blank(tok):
     return tok is None or tok.strip() in ('', '_')
 
 
+def apply_modulations(log_attention, m):
+    """BatchVariableSet.apply_modulations (batch_base_types.py:170-187) for one predicate: ``m`` = the 4 raw outputs
+    (alpha, beta, c, d) of the attention output network (gqa_interpreter_experiments.py:119-131; no gate column)."""
+    alpha, beta, c, d = m[0] * 10, m[1] * 10, m[2] * 10, m[3]
+    temp = alpha * log_attention + safe_log(c) + safe_log(d)
+    return temp - safe_log((beta * log_not(log_attention) + safe_log(1.0 - d)).exp() + temp.exp())
+
+
 # ------------------------------------------------------------------ scene (featurizer + visual oracle)
 
 def scene_tables(params, features, batch_index, relation_index):
@@ -194,25 +202,27 @@ class OracleInterpreter(object):
 
     # ---- ops
 
-    def _filter_slot(self, attr, atts, tokens):
-        """Plain FilterBatch over one slot (batch_base_ops.py:311-405): one optional token per question."""
+    def _filter_slot(self, attr, atts, tokens, mod=None):
+        """Plain FilterBatch over one slot (batch_base_ops.py:311-405): one optional token per question.  ``mod``:
+        (B, 4) attention-transfer modulations of the slot (:400-402), applied to EVERY row when the slot has at least
+        one predicate -- blank rows included."""
         roundtrip = self._any_negated([[t] for t in tokens if t is not None])
+        if all(is_blank(t) for t in tokens):
+            return list(atts)
         out = []
         for q, (a, t) in enumerate(zip(atts, tokens)):
-            if is_blank(t):
-                out.append(a)
-            else:
-                out.append(a + self._predicate_ll(attr[q], 'attr', [t], False, roundtrip)[0])
+            x = a if is_blank(t) else a + self._predicate_ll(attr[q], 'attr', [t], False, roundtrip)[0]
+            out.append(x if mod is None else apply_modulations(x, mod[q]))
         return out
 
-    def _select_slot(self, attr, names):
+    def _select_slot(self, attr, names, mod=None):
         # GQASelectBatch, batch_gqa_ops.py:168-183
         blank = [n is None or n.lower() in ('_', 'scene') for n in names]
         zeros = [torch.zeros(a.shape[0], dtype=a.dtype) for a in attr]
         out_names = ['entity' if b else n for b, n in zip(blank, names)]
         if all(blank):
             return zeros, out_names
-        return self._filter_slot(attr, zeros, [None if b else n for b, n in zip(blank, names)]), out_names
+        return self._filter_slot(attr, zeros, [None if b else n for b, n in zip(blank, names)], mod), out_names
 
     @staticmethod
     def _relate_core(ll, a_subj, a_obj):
@@ -226,9 +236,10 @@ class OracleInterpreter(object):
         out_obj = a_obj + log_not(inner_o.sum(0))
         return out_subj, out_obj
 
-    def _relate_slot(self, attr, rel, atts, names_in, relations, is_subject, names):
-        # GQARelateBatch, batch_gqa_ops.py:364-371 + RelateBatch.forward, batch_base_ops.py:483-596
-        new, new_names = self._select_slot(attr, [n for n in names])
+    def _relate_slot(self, attr, rel, atts, names_in, relations, is_subject, names, mod_sel=None, mod_rel=None):
+        # GQARelateBatch, batch_gqa_ops.py:364-371 + RelateBatch.forward, batch_base_ops.py:483-596 (the kept role's
+        # posterior carries that role's modulation, :588-594)
+        new, new_names = self._select_slot(attr, [n for n in names], mod_sel)
         roundtrip = self._any_negated([[r] for r in relations if r is not None])
         out, out_names = [], []
         for q in range(len(atts)):
@@ -241,7 +252,7 @@ class OracleInterpreter(object):
                 res = self._relate_core(ll, new[q], atts[q])[0]
             else:
                 res = self._relate_core(ll, atts[q], new[q])[1]
-            out.append(res)
+            out.append(res if mod_rel is None else apply_modulations(res, mod_rel[q]))
             out_names.append(new_names[q])
         return out, out_names
 
@@ -249,20 +260,31 @@ class OracleInterpreter(object):
         # batch_gqa_ops.py:305, :583, :655
         return [self.ont.query(c if c not in ('name', 'type') else n) for c, n in zip(categories, names)]
 
-    def _option_filter(self, attr, atts, option_lists, normalized_probability=True):
-        """FilterBatch with a predicate->question map: per question list of a + ll_k."""
+    def _option_filter(self, attr, atts, option_lists, normalized_probability=True, mod=None):
+        """FilterBatch with a predicate->question map: per question list of a + ll_k (modulation row = the flattened
+        predicate index)."""
         normalise = self.normalize and normalized_probability and any(len(o) > 1 for o in option_lists)
         roundtrip = self._any_negated(option_lists)
-        return [[atts[q] + ll for ll in self._predicate_ll(attr[q], 'attr', opts, normalise, roundtrip)]
-                for q, opts in enumerate(option_lists)]
+        out, row = [], 0
+        for q, opts in enumerate(option_lists):
+            xs = []
+            for ll in self._predicate_ll(attr[q], 'attr', opts, normalise, roundtrip):
+                x = atts[q] + ll
+                xs.append(x if mod is None else apply_modulations(x, mod[row]))
+                row += 1
+            out.append(xs)
+        return out
 
     def _agg(self, att, give_answer):
         return exists_hard(att) if (give_answer and self.hard_mode) else exists(att)
 
     # ---- the program loop
 
-    def run(self, program_batch, is_training=True, tables=None):
+    def run(self, program_batch, is_training=True, tables=None, modulations=None):
+        """modulations: None, or {(slot index, sub-operator key): (rows, 4) tensor} of attention-transfer modulations
+        (keys 'select' / 'filter' / 'relate' / 'filter0' / 'filter1'; rows = questions, or flattened options)."""
         pb = program_batch
+        mods = modulations or {}
         feats = pb._object_features
         bidx = pb._object_batch_index.to(torch.int64)
         attr, rel = tables if tables is not None else scene_tables(self.params, feats, bidx, self.rel_index)
@@ -278,14 +300,16 @@ class OracleInterpreter(object):
             mask = None if slot._mask is None else [float(m) for m in slot._mask]
             name = slot._op_name
             if name == 'select':
-                x = self._select_slot(attr, args[0] if args else [None] * B)
+                x = self._select_slot(attr, args[0] if args else [None] * B, mods.get((i, 'select')))
             elif name == 'filter':
-                x = (self._filter_slot(attr, inputs[0][0], args[0]), list(inputs[0][1]))
+                x = (self._filter_slot(attr, inputs[0][0], args[0], mods.get((i, 'filter'))), list(inputs[0][1]))
             elif name == 'relate':
-                x = self._relate_slot(attr, rel, inputs[0][0], inputs[0][1], args[0], args[1], args[2])
+                x = self._relate_slot(attr, rel, inputs[0][0], inputs[0][1], args[0], args[1], args[2],
+                                      mods.get((i, 'select')), mods.get((i, 'relate')))
             else:
                 assert mask is None or all(m > 0 for m in mask), 'one terminal operator per program batch'
-                result = self._terminal(name, attr, rel, inputs, args, give_answer, B)
+                result = self._terminal(name, attr, rel, inputs, args, give_answer, B,
+                                        {k[1]: v for k, v in mods.items() if k[0] == i})
                 trace.append(None)
                 break
             if inputs and mask is not None:  # gate the unaffected questions (batch_base_interpreter.py:166-167)
@@ -316,8 +340,9 @@ class OracleInterpreter(object):
             out.append([o for o, k in zip(opts, keep.tolist()) if k])
         return out
 
-    def _terminal(self, name, attr, rel, inputs, args, give_answer, B):
+    def _terminal(self, name, attr, rel, inputs, args, give_answer, B, mods=None):
         agg = lambda a: self._agg(a, give_answer)
+        mods = mods or {}
         if name in ('exist', 'end'):
             atts, names = inputs[0]
             lp = torch.stack([agg(a) for a in atts])
@@ -338,7 +363,7 @@ class OracleInterpreter(object):
         if name == 'verify_attrs':
             # GQAVerifyAttrsBatch, batch_gqa_ops.py:452-473: un-normalised, prior counted once per attribute
             atts, _ = inputs[0]
-            per_q = self._option_filter(attr, atts, args[0], normalized_probability=False)
+            per_q = self._option_filter(attr, atts, args[0], normalized_probability=False, mod=mods.get('filter'))
             lp = torch.stack([agg(torch.stack(x).sum(0)) for x in per_q])
             return {'log_probability': lp, 'type': BINARY, 'options': ['no', 'yes'],
                     'answer': self._binary_answer(lp, give_answer)}
@@ -346,7 +371,8 @@ class OracleInterpreter(object):
         if name == 'verify_rel':
             # GQAVerifyRelBatch, batch_gqa_ops.py:489-501
             atts, names = inputs[0]
-            out, _ = self._relate_slot(attr, rel, atts, names, args[0], args[1], args[2])
+            out, _ = self._relate_slot(attr, rel, atts, names, args[0], args[1], args[2], mods.get('select'),
+                                       mods.get('relate'))
             lp = torch.stack([agg(a) for a in out])
             return {'log_probability': lp, 'type': BINARY, 'options': ['no', 'yes'],
                     'answer': self._binary_answer(lp, give_answer)}
@@ -355,7 +381,7 @@ class OracleInterpreter(object):
             # GQAChooseAttrBatch :215-228, GQAQueryAttrBatch :304-306
             atts, names = inputs[0]
             option_lists = args[0] if name == 'choose_attr' else self._options(args[0], names)
-            per_q = self._option_filter(attr, atts, option_lists)
+            per_q = self._option_filter(attr, atts, option_lists, mod=mods.get('filter'))
             lp_lists = [[agg(x) for x in xs] for xs in per_q]
             lp = torch.stack([v for l in lp_lists for v in l])
             return {'log_probability': lp, 'type': QUERY, 'options': [list(o) for o in option_lists],
@@ -365,10 +391,11 @@ class OracleInterpreter(object):
             # GQAChooseRelBatch, batch_gqa_ops.py:246-267
             atts, names_in = inputs[0]
             option_lists, is_subject, names = args[0], args[1], args[2]
-            new, _ = self._select_slot(attr, list(names))
+            new, _ = self._select_slot(attr, list(names), mods.get('select'))
             normalise = self.normalize and any(len(o) > 1 for o in option_lists)
             roundtrip = self._any_negated(option_lists)
             lp_lists = []
+            mod_rel, prow = mods.get('relate'), 0
             for q, opts in enumerate(option_lists):
                 lls = self._predicate_ll(rel[q], 'rel', opts, normalise, roundtrip)
                 row = []
@@ -377,6 +404,9 @@ class OracleInterpreter(object):
                         res = self._relate_core(ll, new[q], atts[q])[0]
                     else:
                         res = self._relate_core(ll, atts[q], new[q])[1]
+                    if mod_rel is not None:
+                        res = apply_modulations(res, mod_rel[prow])
+                    prow += 1
                     row.append(agg(res))
                 lp_lists.append(row)
             lp = torch.stack([v for l in lp_lists for v in l])
@@ -387,7 +417,7 @@ class OracleInterpreter(object):
             # GQAAllSameBatch :582-608, GQAAllDifferentBatch :627-639
             atts, names = inputs[0]
             option_lists = self._options(args[0], names)
-            per_q = self._option_filter(attr, atts, option_lists)
+            per_q = self._option_filter(attr, atts, option_lists, mod=mods.get('filter'))
             lps = []
             for q, xs in enumerate(per_q):
                 qk = [for_all(log_not(atts[q] + log_not(x))) for x in xs]
@@ -402,8 +432,8 @@ class OracleInterpreter(object):
             # GQATwoSameBatch :654-681, GQATwoDifferentBatch :702-714
             (atts1, names1), (atts2, _) = inputs[0], inputs[1]
             option_lists = self._options(args[0], names1)
-            x1 = self._option_filter(attr, atts1, option_lists)
-            x2 = self._option_filter(attr, atts2, option_lists)
+            x1 = self._option_filter(attr, atts1, option_lists, mod=mods.get('filter0'))
+            x2 = self._option_filter(attr, atts2, option_lists, mod=mods.get('filter1'))
             lps = []
             for q in range(B):
                 both = torch.stack([agg(a) + agg(b) for a, b in zip(x1[q], x2[q])])
@@ -417,8 +447,8 @@ class OracleInterpreter(object):
         if name == 'compare':
             # GQACompareBatch, batch_gqa_ops.py:730-758
             (atts1, names1), (atts2, names2) = inputs[0], inputs[1]
-            x1 = self._filter_slot(attr, atts1, args[0])
-            x2 = self._filter_slot(attr, atts2, args[0])
+            x1 = self._filter_slot(attr, atts1, args[0], mods.get('filter0'))
+            x2 = self._filter_slot(attr, atts2, args[0], mods.get('filter1'))
             z = torch.stack([torch.stack([agg(a) for a in x1]), torch.stack([agg(a) for a in x2])], dim=1)
             z = F.log_softmax(z, dim=1)
             alpha = torch.tensor([1.0 if f else 0.0 for f in args[1]], dtype=z.dtype)[:, None]
@@ -461,10 +491,12 @@ def compute_loss(results, answer_lists):
 
 
 def run_step(ontology, params, program_batches, is_training=True, normalize=True, hard_mode=False,
-             likelihood_threshold=0.0):
-    """Forward over a list of program batches + loss/B (what VQATrainer._train_batch differentiates)."""
+             likelihood_threshold=0.0, modulations=None):
+    """Forward over a list of program batches + loss/B (what VQATrainer._train_batch differentiates).
+    ``modulations``: optional list (one dict per program batch, see OracleInterpreter.run)."""
     interp = OracleInterpreter(ontology, params, normalize, likelihood_threshold, hard_mode)
-    results = [interp.run(pb, is_training) for pb in program_batches]
+    results = [interp.run(pb, is_training, modulations=None if modulations is None else modulations[k])
+               for k, pb in enumerate(program_batches)]
     total = sum(pb.batch_size() for pb in program_batches)
     loss = compute_loss(results, [pb._answers for pb in program_batches]) / total
     return results, loss

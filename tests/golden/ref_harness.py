@@ -113,6 +113,7 @@ class ReferenceRun(object):
         counts = torch.bincount(batch_index, minlength=n).tolist()
         starts = np.concatenate([[0], np.cumsum(counts)]).tolist()
         cursor = {'q': 0}
+        emb_dim = self.config['word_embedding_dim'] if self.config['activate_attention_transfer'] else 0
 
         class C(self._Collater):
             def collate_object_features(inner, qs):
@@ -122,7 +123,11 @@ class ReferenceRun(object):
                 return features[lo:hi].clone(), (batch_index[lo:hi] - q0).clone()
 
             def collate_meta_data(inner, qs):
-                return {}
+                if not emb_dim:
+                    return {}
+                # attention-transfer runs read world.word_embedding_dim() from the meta data; an empty index sends
+                # every token lookup to ontology.get_embeddings (base_oracle.py:45-55)
+                return {'index': {}, 'embedding': torch.zeros(1, emb_dim)}
 
         pbs = C('select', 'relate', 'filter', split_num).collate(copy.deepcopy(questions))
         for pb in pbs:

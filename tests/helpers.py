@@ -19,6 +19,27 @@ def golden_files():
     return sorted(glob.glob(os.path.join(GOLDEN_DIR, 'golden_*.pt')))
 
 
+def golden_mod_files():
+    """Fixtures recorded with the attention-transfer calibrator on (tests/golden/make_golden_mod.py)."""
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, 'goldenmod_*.pt')))
+
+
+ATTENTION_NETS = ('_forward_attention_network', '_backward_attention_network', '_attention_output_network')
+
+
+def attention_networks_of(case, device='cpu'):
+    """The three attention-transfer networks of a goldenmod fixture (same initial values as the reference run)."""
+    from dfol_vqa_b200.networks import build_attention_networks
+    nets = build_attention_networks(case['dims']['emb'], case['state_dim'])
+    out = []
+    for key, name in zip(('forward_attention_network', 'backward_attention_network', 'attention_output_network'),
+                         ATTENTION_NETS):
+        net = nets[key]
+        net.load_state_dict({k[len(name) + 1:]: v for k, v in case['attention_state'].items() if k.startswith(name)})
+        out.append(net.to(device))
+    return out
+
+
 def load_golden(path):
     return torch.load(path, weights_only=False)
 
