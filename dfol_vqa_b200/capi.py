@@ -17,7 +17,7 @@ _lib = None
 
 class K(object):
     """Constants of include/dfol_b200.h."""
-    ABI_VERSION = 2
+    ABI_VERSION = 3
     ACT_NONE, ACT_ELU, ACT_SIGMOID, ACT_LOGSIGMOID = 0, 1, 2, 3
     MUL_NONE, MUL_SIGMOID_GRAD, MUL_ELU_GRAD = 0, 1, 2
     INSTR_WORDS = 12
@@ -48,10 +48,10 @@ _SIGNATURES = {
                                      P, P, P, c_int, P]),
     'dfol_colsum': (c_int, [P, c_int64, c_int64, c_int, P, P]),
     'dfol_act_grad_mul': (c_int, [P, c_int64, P, c_int64, c_int64, c_int, c_int, P]),
-    'dfol_program_fwd': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_int, P]),
-    'dfol_program_bwd': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_int, P, P, P]),
-    'dfol_program_fwd_fast': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_int, P]),
-    'dfol_program_bwd_fast': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_int, P, P, P]),
+    'dfol_program_fwd': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, c_int, P]),
+    'dfol_program_bwd': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, c_int, P, P, P, P]),
+    'dfol_program_fwd_fast': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, c_int, P]),
+    'dfol_program_bwd_fast': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, c_int, P, P, P, P]),
     'dfol_loss_fwd_bwd': (c_int, [P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
     'dfol_table_layer_bwd': (c_int, [P, P, P, P, P, c_int, P, P, P, P, P, P, c_int64, P, c_int64, c_int, P,
                                      c_int64, P, P, P]),

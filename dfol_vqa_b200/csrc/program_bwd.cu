@@ -6,6 +6,9 @@
 
 namespace dfol {
 
+// modulation row, compiled out of the unmodulated instantiation
+#define DFOL_LOAD_MOD(row) (MOD ? load_mod(mods, (row)) : load_mod(nullptr, -1))
+
 struct BwdShared {
   float cur[MAXN];    // attention before the current instruction (tape)
   float saved[MAXN];  // final attention of the first branch
@@ -65,6 +68,16 @@ __device__ __forceinline__ void attr_softmax_correction(const Image& im, const i
   __syncthreads();
 }
 
+// d loss / d modulation row: block-wide (every thread calls) or warp-wide sum of the per-thread partials; one writer.
+__device__ __forceinline__ void block_write_dm(const float dm[4], float* __restrict__ d_mods, int row, BlockScratch& sc) {
+  const float r0 = block_sum(dm[0], sc), r1 = block_sum(dm[1], sc), r2 = block_sum(dm[2], sc), r3 = block_sum(dm[3], sc);
+  if (threadIdx.x == 0 && d_mods != nullptr) reinterpret_cast<float4*>(d_mods)[row] = make_float4(r0, r1, r2, r3);
+}
+__device__ __forceinline__ void warp_write_dm(const float dm[4], float* __restrict__ d_mods, int row) {
+  const float r0 = warp_sum(dm[0]), r1 = warp_sum(dm[1]), r2 = warp_sum(dm[2]), r3 = warp_sum(dm[3]);
+  if ((threadIdx.x & 31) == 0 && d_mods != nullptr) reinterpret_cast<float4*>(d_mods)[row] = make_float4(r0, r1, r2, r3);
+}
+
 // Backward of relate_forward for the kept role. dres = d loss / d res. Adds the gradient of the OTHER role's
 // prior into g_other (accumulating) and writes d loss / d nrm[s,o] into gslice (n x n tile, diagonal zero).
 template <class LL>
@@ -110,12 +123,14 @@ __device__ __forceinline__ void relate_backward(int n, const LL& L, const float*
   __syncthreads();
 }
 
+template <bool MOD>
 static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
     const int32_t* __restrict__ instr, const int32_t* __restrict__ q_instr, const int32_t* __restrict__ opts,
     const float* __restrict__ attr_ll, const int64_t* __restrict__ attr_blk, const int32_t* __restrict__ attr_stride,
     const float* __restrict__ rel_ll, const int64_t* __restrict__ rel_blk, const int32_t* __restrict__ rel_stride,
-    const int32_t* __restrict__ img_n, const float* __restrict__ d_lp, const float* __restrict__ tape,
-    int tape_stride, float* __restrict__ g_attr, float* __restrict__ g_rel
+    const int32_t* __restrict__ img_n, const float* __restrict__ mods, const float* __restrict__ d_lp,
+    const float* __restrict__ tape, int tape_stride, float* __restrict__ g_attr, float* __restrict__ g_rel,
+    float* __restrict__ d_mods
 #ifdef DFOL_PROGRAM_FAST
     , int ring_nbuf, int ring_tile_floats
 #endif
@@ -179,13 +194,21 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
 
     switch (I.op) {
       case DFOL_OP_SELECT:
-        if (I.a0 >= 0 && tid < n) g_attr[I.ga0 + tid] = sm.g[tid] * post_ll_grad(attr_raw(im, I.a0, tid), neg, rt);
-        if (tid < n) sm.g[tid] = 0.f;
+      case DFOL_OP_FILTER: {
+        // x = (filter: cur +) post(ll); out = M(x)
+        const Mod m = DFOL_LOAD_MOD(I.mod);
+        float dm[4] = {0.f, 0.f, 0.f, 0.f};
+        if (tid < n) {
+          const float raw = (I.a0 >= 0) ? attr_raw(im, I.a0, tid) : 0.0f;
+          const float l = (I.a0 >= 0) ? post_ll(raw, neg, rt) : 0.0f;
+          const float x = (I.op == DFOL_OP_FILTER) ? sm.cur[tid] + l : l;
+          const float dx = mod_grad(m, x, sm.g[tid], dm);
+          if (I.a0 >= 0) g_attr[I.ga0 + tid] = dx * post_ll_grad(raw, neg, rt);
+          sm.g[tid] = (I.op == DFOL_OP_FILTER) ? dx : 0.f;
+        }
+        if (m.on) block_write_dm(dm, d_mods, I.mod, sm.sc);
         break;
-
-      case DFOL_OP_FILTER:
-        if (tid < n) g_attr[I.ga0 + tid] = sm.g[tid] * post_ll_grad(attr_raw(im, I.a0, tid), neg, rt);
-        break;
+      }
 
       case DFOL_OP_PUSH:
         if (tid < n) { sm.g[tid] = sm.gs[tid]; sm.gs[tid] = 0.f; }
@@ -193,8 +216,11 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
 
       case DFOL_OP_RELATE: {
         const bool nneg = I.flags & DFOL_F_NAME_NEG, nrt = I.flags & DFOL_F_NAME_ROUNDTRIP;
+        const Mod mr = DFOL_LOAD_MOD(I.mod), ms = DFOL_LOAD_MOD(I.mod2);
+        float nw0 = 0.0f;  // prior of the new object before its modulation
         if (tid < n) {
-          sm.nw[tid] = (I.a1 >= 0) ? post_ll(attr_raw(im, I.a1, tid), nneg, nrt) : 0.0f;
+          nw0 = (I.a1 >= 0) ? post_ll(attr_raw(im, I.a1, tid), nneg, nrt) : 0.0f;
+          sm.nw[tid] = mod_apply(ms, nw0);
           sm.dres[tid] = sm.g[tid];
           sm.tmp[tid] = 0.f;
         }
@@ -210,6 +236,11 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
           mbar_wait(&ring.full[b], (uint32_t)(j / ring.nbuf) & 1u);
           const float* tile = ring.buf + (size_t)b * ring.tile_floats;
           relate_forward_tile(n, tile, neg, rt, a_s, a_o, subj, sm.res, sm.inner, sm.den, sm.sc);
+          if (mr.on) {  // gradient through the modulation of the posterior: sm.g (d out) -> sm.dres (d res)
+            float dm[4] = {0.f, 0.f, 0.f, 0.f};
+            if (tid < n) sm.dres[tid] = mod_grad(mr, sm.res[tid], sm.g[tid], dm);
+            block_write_dm(dm, d_mods, I.mod, sm.sc);
+          }
           relate_backward_tile(n, tile, neg, rt, a_s, subj, sm.dres, sm.inner, sm.den, sm.tot, sm.tmp, g_rel + I.gr,
                                sm.sc);
           if (tid == 0 && j + ring.nbuf < rel_count) issue_tile(j + ring.nbuf);
@@ -218,12 +249,22 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
         {
           RelOption L{&im, nullptr, 1, 0, false, rt, I.a0, neg};
           relate_forward(n, L, a_s, a_o, subj, sm.res, sm.inner, sm.sc);
+          if (mr.on) {
+            float dm[4] = {0.f, 0.f, 0.f, 0.f};
+            if (tid < n) sm.dres[tid] = mod_grad(mr, sm.res[tid], sm.g[tid], dm);
+            block_write_dm(dm, d_mods, I.mod, sm.sc);
+          }
           relate_backward(n, L, a_s, a_o, subj, sm.dres, sm.inner, sm.tmp, g_rel + I.gr, sm.sc);
         }
-        if (tid < n) {
-          // the kept role's own prior is the new object: its gradient feeds the name select
-          if (I.a1 >= 0) g_attr[I.ga1 + tid] = sm.dres[tid] * post_ll_grad(attr_raw(im, I.a1, tid), nneg, nrt);
-          sm.g[tid] = sm.tmp[tid];
+        {
+          float dm[4] = {0.f, 0.f, 0.f, 0.f};
+          if (tid < n) {
+            // the kept role's own prior is the (modulated) new object: its gradient feeds the name select
+            const float dnw0 = mod_grad(ms, nw0, sm.dres[tid], dm);
+            if (I.a1 >= 0) g_attr[I.ga1 + tid] = dnw0 * post_ll_grad(attr_raw(im, I.a1, tid), nneg, nrt);
+            sm.g[tid] = sm.tmp[tid];
+          }
+          if (ms.on) block_write_dm(dm, d_mods, I.mod2, sm.sc);
         }
         break;
       }
@@ -262,11 +303,14 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
         float acc[NCHUNK];
 #pragma unroll
         for (int j = 0; j < NCHUNK; ++j) acc[j] = 0.f;
+        const bool modulated = MOD && I.mod >= 0;
         for (int k = w; k < I.a1; k += PROG_WARPS) {
+          const Mod mk = DFOL_LOAD_MOD(modulated ? I.mod + k : -1);
 #pragma unroll
           for (int j = 0; j < NCHUNK; ++j) {
             const int t = lane + 32 * j;
-            if (t < n) acc[j] += sm.cur[t] + post_ll(attr_raw(im, op[k] & ~DFOL_OPT_NEG, t), op[k] & DFOL_OPT_NEG, rt);
+            if (t < n)
+              acc[j] += mod_apply(mk, sm.cur[t] + post_ll(attr_raw(im, op[k] & ~DFOL_OPT_NEG, t), op[k] & DFOL_OPT_NEG, rt));
           }
         }
         reduce_columns(acc, n, sm.res, sm.sc, false);
@@ -279,15 +323,24 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
           sm.tmp[tid] = datt;
         }
         __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NCHUNK; ++j) acc[j] = 0.f;
         for (int k = w; k < I.a1; k += PROG_WARPS) {
+          const Mod mk = DFOL_LOAD_MOD(modulated ? I.mod + k : -1);
+          float dm[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int j = 0; j < NCHUNK; ++j) {
             const int t = lane + 32 * j;
-            if (t < n)
-              g_attr[I.ga0 + (long long)k * im.astride + t] =
-                  sm.tmp[t] * post_ll_grad(attr_raw(im, op[k] & ~DFOL_OPT_NEG, t), op[k] & DFOL_OPT_NEG, rt);
+            if (t < n) {
+              const float raw = attr_raw(im, op[k] & ~DFOL_OPT_NEG, t);
+              const float dx = mod_grad(mk, sm.cur[t] + post_ll(raw, op[k] & DFOL_OPT_NEG, rt), sm.tmp[t], dm);
+              acc[j] += dx;
+              g_attr[I.ga0 + (long long)k * im.astride + t] = dx * post_ll_grad(raw, op[k] & DFOL_OPT_NEG, rt);
+            }
           }
+          if (mk.on) warp_write_dm(dm, d_mods, I.mod + k);
         }
+        if (modulated) reduce_columns(acc, n, sm.g, sm.sc, false);  // d cur = sum_k dx_k (unmodulated: a1 * datt, above)
         break;
       }
 
@@ -303,6 +356,7 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
           float part = 0.f;
           for (int k = w; k < I.a1; k += PROG_WARPS) {
             const bool kneg = op[k] & DFOL_OPT_NEG;
+            const Mod m1 = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1), m2 = DFOL_LOAD_MOD(I.mod2 >= 0 ? I.mod2 + k : -1);
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
             for (int j = 0; j < NCHUNK; ++j) {
@@ -311,10 +365,10 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
                 const float l = post_ll(option_nrm(im, op[k], t, normalise, sm.den), kneg, rt);
                 if (I.op == DFOL_OP_ALL_SAME) {
                   const float a = sm.cur[t];
-                  s1 += roundtrip(lnot(a + lnot(a + l)));
+                  s1 += roundtrip(lnot(a + lnot(mod_apply(m1, a + l))));
                 } else {
-                  s1 += lnot(sm.saved[t] + l);
-                  s2 += lnot(sm.cur[t] + l);
+                  s1 += lnot(mod_apply(m1, sm.saved[t] + l));
+                  s2 += lnot(mod_apply(m2, sm.cur[t] + l));
                 }
               }
             }
@@ -332,18 +386,28 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
         for (int j = 0; j < NCHUNK; ++j) { acc_g[j] = 0.f; acc_gs[j] = 0.f; acc_tot[j] = 0.f; }
         for (int k = w; k < I.a1; k += PROG_WARPS) {
           const bool kneg = op[k] & DFOL_OPT_NEG;
-          float nrm[NCHUNK], l[NCHUNK];
+          const Mod m1 = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1), m2 = DFOL_LOAD_MOD(I.mod2 >= 0 ? I.mod2 + k : -1);
+          float dm1[4] = {0.f, 0.f, 0.f, 0.f}, dm2[4] = {0.f, 0.f, 0.f, 0.f};
+          float nrm[NCHUNK], l[NCHUNK], xm1[NCHUNK], xm2[NCHUNK];  // xm: modulated filter outputs
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
           for (int j = 0; j < NCHUNK; ++j) {
             const int t = lane + 32 * j;
-            nrm[j] = 0.f; l[j] = 0.f;
+            nrm[j] = 0.f; l[j] = 0.f; xm1[j] = 0.f; xm2[j] = 0.f;
             if (t < n) {
               nrm[j] = option_nrm(im, op[k], t, normalise, sm.den);
               l[j] = post_ll(nrm[j], kneg, rt);
-              if (I.op == DFOL_OP_CHOOSE_ATTR) s1 += lnot(sm.cur[t] + l[j]);
-              else if (I.op == DFOL_OP_ALL_SAME) { const float a = sm.cur[t]; s1 += roundtrip(lnot(a + lnot(a + l[j]))); }
-              else { s1 += lnot(sm.saved[t] + l[j]); s2 += lnot(sm.cur[t] + l[j]); }
+              if (I.op == DFOL_OP_CHOOSE_ATTR) { xm1[j] = mod_apply(m1, sm.cur[t] + l[j]); s1 += lnot(xm1[j]); }
+              else if (I.op == DFOL_OP_ALL_SAME) {
+                const float a = sm.cur[t];
+                xm1[j] = mod_apply(m1, a + l[j]);
+                s1 += roundtrip(lnot(a + lnot(xm1[j])));
+              } else {
+                xm1[j] = mod_apply(m1, sm.saved[t] + l[j]);
+                xm2[j] = mod_apply(m2, sm.cur[t] + l[j]);
+                s1 += lnot(xm1[j]);
+                s2 += lnot(xm2[j]);
+              }
             }
           }
           s1 = warp_sum(s1);
@@ -362,21 +426,20 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
             if (t < n) {
               float dl;
               if (I.op == DFOL_OP_CHOOSE_ATTR) {
-                const float dx = d1 * lnot_grad(sm.cur[t] + l[j]);
+                const float dx = mod_grad(m1, sm.cur[t] + l[j], d1 * lnot_grad(xm1[j]), dm1);
                 acc_g[j] += dx;
                 dl = dx;
               } else if (I.op == DFOL_OP_ALL_SAME) {
                 const float a = sm.cur[t];
-                const float x = a + l[j];
-                const float wv = a + lnot(x);
+                const float wv = a + lnot(xm1[j]);
                 const float y = lnot(wv);
                 const float dw = d1 * roundtrip_grad(y) * lnot_grad(wv);
-                const float dx = dw * lnot_grad(x);
+                const float dx = mod_grad(m1, a + l[j], dw * lnot_grad(xm1[j]), dm1);
                 acc_g[j] += dw + dx;
                 dl = dx;
               } else {
-                const float dx1 = d1 * lnot_grad(sm.saved[t] + l[j]);
-                const float dx2 = d2 * lnot_grad(sm.cur[t] + l[j]);
+                const float dx1 = mod_grad(m1, sm.saved[t] + l[j], d1 * lnot_grad(xm1[j]), dm1);
+                const float dx2 = mod_grad(m2, sm.cur[t] + l[j], d2 * lnot_grad(xm2[j]), dm2);
                 acc_gs[j] += dx1;
                 acc_g[j] += dx2;
                 dl = dx1 + dx2;
@@ -386,6 +449,8 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
               gslice[(long long)k * im.astride + t] = dn;
             }
           }
+          if (m1.on) warp_write_dm(dm1, d_mods, I.mod + k);
+          if (m2.on) warp_write_dm(dm2, d_mods, I.mod2 + k);
         }
         reduce_columns(acc_g, n, sm.g, sm.sc, false);
         if (I.op == DFOL_OP_TWO_SAME) reduce_columns(acc_gs, n, sm.gs, sm.sc, false);
@@ -397,10 +462,11 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
       }
 
       case DFOL_OP_COMPARE: {
+        const Mod m1 = DFOL_LOAD_MOD(I.mod), m2 = DFOL_LOAD_MOD(I.mod2);
         if (tid < n) {
           const float l = (I.a0 >= 0) ? post_ll(attr_raw(im, I.a0, tid), neg, rt) : 0.0f;
-          sm.res[tid] = sm.saved[tid] + l;
-          sm.nw[tid] = sm.cur[tid] + l;
+          sm.res[tid] = mod_apply(m1, sm.saved[tid] + l);
+          sm.nw[tid] = mod_apply(m2, sm.cur[tid] + l);
         }
         __syncthreads();
         float S1, S2;
@@ -416,22 +482,30 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
         const float dz2 = (v2 >= kLogEps) ? d_lp[I.out + 1] * c * DFOL_EXPF(z2) / v2 : 0.0f;
         const float de1 = dz1 - DFOL_EXPF(z1) * (dz1 + dz2);
         const float de2 = dz2 - DFOL_EXPF(z2) * (dz1 + dz2);
+        float dm1[4] = {0.f, 0.f, 0.f, 0.f}, dm2[4] = {0.f, 0.f, 0.f, 0.f};
         if (tid < n) {
-          const float dx1 = de1 * lnot_grad(S1) * lnot_grad(sm.res[tid]);
-          const float dx2 = de2 * lnot_grad(S2) * lnot_grad(sm.nw[tid]);
+          const float raw = (I.a0 >= 0) ? attr_raw(im, I.a0, tid) : 0.0f;
+          const float l = (I.a0 >= 0) ? post_ll(raw, neg, rt) : 0.0f;
+          const float dx1 = mod_grad(m1, sm.saved[tid] + l, de1 * lnot_grad(S1) * lnot_grad(sm.res[tid]), dm1);
+          const float dx2 = mod_grad(m2, sm.cur[tid] + l, de2 * lnot_grad(S2) * lnot_grad(sm.nw[tid]), dm2);
           sm.gs[tid] = dx1;
           sm.g[tid] = dx2;
-          if (I.a0 >= 0) g_attr[I.ga0 + tid] = (dx1 + dx2) * post_ll_grad(attr_raw(im, I.a0, tid), neg, rt);
+          if (I.a0 >= 0) g_attr[I.ga0 + tid] = (dx1 + dx2) * post_ll_grad(raw, neg, rt);
         }
+        if (m1.on) block_write_dm(dm1, d_mods, I.mod, sm.sc);
+        if (m2.on) block_write_dm(dm2, d_mods, I.mod2, sm.sc);
         break;
       }
 
       case DFOL_OP_CHOOSE_REL: {
         const bool nneg = I.flags & DFOL_F_NAME_NEG, nrt = I.flags & DFOL_F_NAME_ROUNDTRIP;
+        const Mod ms = DFOL_LOAD_MOD(I.mod2);
+        float nw0 = 0.0f;
         if (tid < n) {
-          sm.nw[tid] = (I.a2 >= 0) ? post_ll(attr_raw(im, I.a2, tid), nneg, nrt) : 0.0f;
+          nw0 = (I.a2 >= 0) ? post_ll(attr_raw(im, I.a2, tid), nneg, nrt) : 0.0f;
+          sm.nw[tid] = mod_apply(ms, nw0);
           sm.tmp[tid] = 0.f;  // gradient of the incoming attention
-          sm.tot[tid] = 0.f;  // gradient of the new object's prior
+          sm.tot[tid] = 0.f;  // gradient of the new object's (modulated) prior
         }
         __syncthreads();
         const bool subj = I.flags & DFOL_F_SUBJECT;
@@ -440,13 +514,18 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
         for (int k = 0; k < I.a1; ++k) {
           RelOption L{&im, opts + I.a0, I.a1, k, normalise, rt, -1, false};
           relate_forward(n, L, a_s, a_o, subj, sm.res, sm.inner, sm.sc);
+          const Mod mk = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1);
+          if (tid < n) sm.den[tid] = mod_apply(mk, sm.res[tid]);  // modulated posterior of option k
+          __syncthreads();
           float S;
-          exists_block(sm.res, n, false, sm.sc, &S);
+          exists_block(sm.den, n, false, sm.sc, &S);
           const float d = d_lp[I.out + k] * lnot_grad(S);
+          float dm[4] = {0.f, 0.f, 0.f, 0.f};
           if (tid < n) {
-            sm.dres[tid] = d * lnot_grad(sm.res[tid]);
+            sm.dres[tid] = mod_grad(mk, sm.res[tid], d * lnot_grad(sm.den[tid]), dm);
             sm.tot[tid] += sm.dres[tid];
           }
+          if (mk.on) block_write_dm(dm, d_mods, I.mod + k, sm.sc);
           __syncthreads();
           relate_backward(n, L, a_s, a_o, subj, sm.dres, sm.inner, sm.tmp, g_rel + I.gr + (long long)k * im.rstride,
                           sm.sc);
@@ -469,9 +548,14 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
           }
         }
         __syncthreads();
-        if (tid < n) {
-          if (I.a2 >= 0) g_attr[I.ga1 + tid] = sm.tot[tid] * post_ll_grad(attr_raw(im, I.a2, tid), nneg, nrt);
-          sm.g[tid] = sm.tmp[tid];
+        {
+          float dm[4] = {0.f, 0.f, 0.f, 0.f};
+          if (tid < n) {
+            const float dnw0 = mod_grad(ms, nw0, sm.tot[tid], dm);
+            if (I.a2 >= 0) g_attr[I.ga1 + tid] = dnw0 * post_ll_grad(attr_raw(im, I.a2, tid), nneg, nrt);
+            sm.g[tid] = sm.tmp[tid];
+          }
+          if (ms.on) block_write_dm(dm, d_mods, I.mod2, sm.sc);
         }
         break;
       }
@@ -495,11 +579,13 @@ using namespace dfol;
 extern "C" int DFOL_PROGRAM_BWD_ENTRY(const int32_t* instr, const int32_t* q_instr, const int32_t* opts,
                                       int question_num, const float* attr_ll, const int64_t* attr_blk,
                                       const int32_t* attr_stride, const float* rel_ll, const int64_t* rel_blk,
-                                      const int32_t* rel_stride, const int32_t* img_n, const float* d_lp,
-                                      const float* tape, int tape_stride, float* g_attr, float* g_rel, void* stream) {
+                                      const int32_t* rel_stride, const int32_t* img_n, const float* mods,
+                                      const float* d_lp, const float* tape, int tape_stride, float* g_attr,
+                                      float* g_rel, float* d_mods, void* stream) {
   DFOL_REQUIRE(instr && q_instr && attr_ll && attr_blk && attr_stride && rel_ll && rel_blk && rel_stride && img_n &&
                    d_lp && tape && g_attr && g_rel,
                "dfol_program_bwd: null pointer");
+  DFOL_REQUIRE((mods == nullptr) == (d_mods == nullptr), "dfol_program_bwd: mods and d_mods go together");
   if (question_num == 0) return 0;
 #ifdef DFOL_PROGRAM_FAST
   DFOL_REQUIRE(tape_stride >= 1 && tape_stride <= MAXN, "dfol_program_bwd_fast: tape_stride = max objects rounded to 4");
@@ -507,15 +593,15 @@ extern "C" int DFOL_PROGRAM_BWD_ENTRY(const int32_t* instr, const int32_t* q_ins
   int nbuf = (96 * 1024) / (tile_floats * 4);
   nbuf = nbuf < 1 ? 1 : (nbuf > 4 ? 4 : nbuf);
   const size_t smem = (size_t)nbuf * tile_floats * 4;
-  cudaFuncSetAttribute(program_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  program_bwd_kernel<<<question_num, PROG_THREADS, smem, (cudaStream_t)stream>>>(
-      instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, d_lp, tape,
-      tape_stride, g_attr, g_rel, nbuf, tile_floats);
+  cudaFuncSetAttribute(mods ? program_bwd_kernel<true> : program_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  (mods ? program_bwd_kernel<true> : program_bwd_kernel<false>)<<<question_num, PROG_THREADS, smem, (cudaStream_t)stream>>>(
+      instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, mods, d_lp, tape,
+      tape_stride, g_attr, g_rel, d_mods, nbuf, tile_floats);
   return finish_launch("dfol_program_bwd_fast");
 #else
-  program_bwd_kernel<<<question_num, PROG_THREADS, 0, (cudaStream_t)stream>>>(
-      instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, d_lp, tape,
-      tape_stride, g_attr, g_rel);
+  (mods ? program_bwd_kernel<true> : program_bwd_kernel<false>)<<<question_num, PROG_THREADS, 0, (cudaStream_t)stream>>>(
+      instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, mods, d_lp, tape,
+      tape_stride, g_attr, g_rel, d_mods);
   return finish_launch("dfol_program_bwd");
 #endif
 }

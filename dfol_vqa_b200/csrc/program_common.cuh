@@ -15,7 +15,7 @@ constexpr int MAXN = 128;  // objects per image supported by the interpreter ker
 constexpr int NCHUNK = MAXN / 32;
 
 struct Instr {
-  int op, flags, a0, a1, a2, out, ga0, ga1, gr;
+  int op, flags, a0, a1, a2, out, ga0, ga1, gr, mod, mod2;
 };
 
 __device__ __forceinline__ Instr load_instr(const int32_t* instr, int ip) {
@@ -23,7 +23,65 @@ __device__ __forceinline__ Instr load_instr(const int32_t* instr, int ip) {
   Instr I;
   I.op = w[DFOL_I_OP]; I.flags = w[DFOL_I_FLAGS]; I.a0 = w[DFOL_I_A0]; I.a1 = w[DFOL_I_A1]; I.a2 = w[DFOL_I_A2];
   I.out = w[DFOL_I_OUT]; I.ga0 = w[DFOL_I_GA0]; I.ga1 = w[DFOL_I_GA1]; I.gr = w[DFOL_I_GR];
+  I.mod = w[DFOL_I_MOD]; I.mod2 = w[DFOL_I_MOD2];
   return I;
+}
+
+// Attention-transfer modulation of one predicate row (BatchVariableSet.apply_modulations, batch_base_types.py:170-187):
+//   out = temp - slog(e^{beta * lnot(L) + slog(1 - d)} + e^{temp}),   temp = alpha * L + slog(c) + slog(d)
+// with (alpha, beta, c) = 10 * raw[0..2] and d = raw[3] (the 4-output network of gqa_interpreter_experiments.py:119-131).
+struct Mod {
+  float alpha, beta, c, d;  // scaled
+  float lcd, l1d;           // slog(c) + slog(d), slog(1 - d)
+  bool on;
+};
+__device__ __forceinline__ Mod load_mod(const float* __restrict__ mods, int row) {
+  Mod m;
+  m.on = (mods != nullptr) && (row >= 0);
+  m.alpha = m.beta = m.c = 1.0f; m.d = 0.5f; m.lcd = m.l1d = 0.0f;
+  if (m.on) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(mods) + row);
+    m.alpha = 10.0f * r.x; m.beta = 10.0f * r.y; m.c = 10.0f * r.z; m.d = r.w;
+    m.lcd = slog(m.c) + slog(m.d);
+    m.l1d = slog(1.0f - m.d);
+  }
+  return m;
+}
+// log(1 + t) for t >= 0 without the cancellation of log(1.0f + t) for small t
+__device__ __forceinline__ float mod_log1p(float t) {
+#ifdef DFOL_PROGRAM_FAST
+  if (t < 0.03125f) return t * (1.0f + t * (-0.5f + t * (0.33333334f + t * (-0.25f + t * 0.2f))));
+  return __logf(1.0f + t);
+#else
+  return log1pf(t);
+#endif
+}
+// out = temp - log(e^u + e^temp) = -log(1 + e^{u - temp}): evaluated in this form, which has no cancellation when the
+// result is close to 0 (the reference's fp32 form loses ~6e-8 absolute there, which log(1 - e^x) then amplifies)
+__device__ __forceinline__ float mod_apply(const Mod& m, float L) {
+  if (!m.on) return L;
+  const float temp = m.alpha * L + m.lcd;
+  const float u = m.beta * lnot(L) + m.l1d;
+  const float z = u - temp;
+  if (z > 30.0f) return (u < kLnLogEps && temp < kLnLogEps) ? temp - kLnLogEps : -z;
+  return -mod_log1p(DFOL_EXPF(z));
+}
+// Backward of mod_apply: returns d loss / d L given g = d loss / d out and adds g * d out / d raw[i] to dm[i].
+__device__ __forceinline__ float mod_grad(const Mod& m, float L, float g, float dm[4]) {
+  if (!m.on) return g;
+  const float nl = lnot(L);
+  const float temp = m.alpha * L + m.lcd;
+  const float u = m.beta * nl + m.l1d;
+  // d out / d temp = sigmoid(u - temp) = -d out / d u
+  const float z = u - temp;
+  const float wu = (z > 30.0f) ? 1.0f : DFOL_DIVF(1.0f, 1.0f + DFOL_EXPF(-z));
+  const float dtemp = g * wu;
+  const float du = -dtemp;
+  dm[0] += 10.0f * dtemp * L;
+  dm[1] += 10.0f * du * nl;
+  dm[2] += (m.c >= kLogEps) ? 10.0f * dtemp / m.c : 0.0f;
+  dm[3] += ((m.d >= kLogEps) ? dtemp / m.d : 0.0f) - ((1.0f - m.d >= kLogEps) ? du / (1.0f - m.d) : 0.0f);
+  return dtemp * m.alpha + du * m.beta * lnot_grad(L);
 }
 
 // One question's image: table slices of its own image only.

@@ -13,6 +13,9 @@ __device__ int dfol_tcount;
 
 namespace dfol {
 
+// modulation row, compiled out of the unmodulated instantiation
+#define DFOL_LOAD_MOD(row) (MOD ? load_mod(mods, (row)) : load_mod(nullptr, -1))
+
 struct FwdShared {
   float cur[MAXN];
   float saved[MAXN];
@@ -75,11 +78,13 @@ __device__ __forceinline__ float warp_exists(const float x[NCHUNK], int n, bool 
   return lnot(s);
 }
 
+template <bool MOD>
 static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
     const int32_t* __restrict__ instr, const int32_t* __restrict__ q_instr, const int32_t* __restrict__ opts,
     const float* __restrict__ attr_ll, const int64_t* __restrict__ attr_blk, const int32_t* __restrict__ attr_stride,
     const float* __restrict__ rel_ll, const int64_t* __restrict__ rel_blk, const int32_t* __restrict__ rel_stride,
-    const int32_t* __restrict__ img_n, float* __restrict__ lp_out, float* __restrict__ tape, int tape_stride
+    const int32_t* __restrict__ img_n, const float* __restrict__ mods, float* __restrict__ lp_out,
+    float* __restrict__ tape, int tape_stride
 #ifdef DFOL_PROGRAM_FAST
     , int ring_nbuf, int ring_tile_floats
 #endif
@@ -161,6 +166,7 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
       J.op = code_s[o + DFOL_I_OP]; J.flags = code_s[o + DFOL_I_FLAGS]; J.a0 = code_s[o + DFOL_I_A0];
       J.a1 = code_s[o + DFOL_I_A1]; J.a2 = code_s[o + DFOL_I_A2]; J.out = code_s[o + DFOL_I_OUT];
       J.ga0 = J.ga1 = J.gr = -1;
+      J.mod = code_s[o + DFOL_I_MOD]; J.mod2 = code_s[o + DFOL_I_MOD2];
       return J;
     }
     return load_instr(instr, ip);
@@ -201,23 +207,32 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
     if (tape != nullptr && tid < n) tape[(long long)ip * tape_stride + tid] = sm.cur[tid];
 
     switch (I.op) {
-      case DFOL_OP_SELECT:
+      case DFOL_OP_SELECT: {
+        const Mod m = DFOL_LOAD_MOD(I.mod);
 #ifdef DFOL_PROGRAM_FAST
-        if (tid < n) sm.cur[tid] = (I.a0 >= 0) ? post_ll(cur_raw, neg, rt) : 0.0f;
+        if (tid < n) sm.cur[tid] = mod_apply(m, (I.a0 >= 0) ? post_ll(cur_raw, neg, rt) : 0.0f);
         __syncthreads();
 #else
         select_into(sm.cur, im, I.a0, neg, rt);
+        if (m.on) {
+          if (tid < n) sm.cur[tid] = mod_apply(m, sm.cur[tid]);
+          __syncthreads();
+        }
 #endif
         break;
+      }
 
-      case DFOL_OP_FILTER:  // a'[t] = a[t] + ll[t]  (_forward_core arity 1)
+      case DFOL_OP_FILTER: {  // a'[t] = a[t] + ll[t]  (_forward_core arity 1); a0 < 0: modulated pass-through
+        const Mod m = DFOL_LOAD_MOD(I.mod);
 #ifdef DFOL_PROGRAM_FAST
-        if (tid < n) sm.cur[tid] += post_ll(cur_raw, neg, rt);
+        if (tid < n) sm.cur[tid] = mod_apply(m, sm.cur[tid] + ((I.a0 >= 0) ? post_ll(cur_raw, neg, rt) : 0.0f));
 #else
-        if (tid < n) sm.cur[tid] += post_ll(attr_raw(im, I.a0, tid), neg, rt);
+        if (tid < n)
+          sm.cur[tid] = mod_apply(m, sm.cur[tid] + ((I.a0 >= 0) ? post_ll(attr_raw(im, I.a0, tid), neg, rt) : 0.0f));
 #endif
         __syncthreads();
         break;
+      }
 
       case DFOL_OP_PUSH:
         if (tid < n) sm.saved[tid] = sm.cur[tid];
@@ -231,8 +246,10 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
           // phase A (thread-local): prior of the new object from the prefetched name row, e^{cur} of the other role
           float nwv = 0.0f;
           DFOL_TSTAMP(0);
+          const Mod mr = DFOL_LOAD_MOD(I.mod), ms = DFOL_LOAD_MOD(I.mod2);
           if (tid < n) {
             if (I.a1 >= 0) nwv = post_ll(cur_raw, I.flags & DFOL_F_NAME_NEG, I.flags & DFOL_F_NAME_ROUNDTRIP);
+            nwv = mod_apply(ms, nwv);
             sm.den[tid] = __expf(sm.cur[tid]);
           }
           const int b = krel % ring.nbuf;
@@ -247,7 +264,7 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
           // every thread is past its last read of the slot: refill it with the tile nbuf hops ahead
           if (tid == 0 && krel + ring.nbuf < rel_count) issue_tile(krel + ring.nbuf);
           // phase C (thread-local): posterior of the kept role replaces the attention
-          if (tid < n) sm.cur[tid] = nwv + slog(1.0f - relate_kept_q(tid, subj, sm.inner, sm.sc));
+          if (tid < n) sm.cur[tid] = mod_apply(mr, nwv + slog(1.0f - relate_kept_q(tid, subj, sm.inner, sm.sc)));
           __syncthreads();
           DFOL_TSTAMP(5);
           ++krel;
@@ -255,16 +272,24 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
         }
         ++krel;
         if (tid < n)
-          sm.nw[tid] = (I.a1 >= 0) ? post_ll(cur_raw, I.flags & DFOL_F_NAME_NEG, I.flags & DFOL_F_NAME_ROUNDTRIP) : 0.0f;
+          sm.nw[tid] = mod_apply(DFOL_LOAD_MOD(I.mod2), (I.a1 >= 0) ? post_ll(cur_raw, I.flags & DFOL_F_NAME_NEG,
+                                                                               I.flags & DFOL_F_NAME_ROUNDTRIP) : 0.0f);
         __syncthreads();
 #else
         select_into(sm.nw, im, I.a1, I.flags & DFOL_F_NAME_NEG, I.flags & DFOL_F_NAME_ROUNDTRIP);
+        {
+          const Mod ms = DFOL_LOAD_MOD(I.mod2);
+          if (ms.on) {
+            if (tid < n) sm.nw[tid] = mod_apply(ms, sm.nw[tid]);
+            __syncthreads();
+          }
+        }
 #endif
         {
           RelOption L{&im, nullptr, 1, 0, false, rt, I.a0, neg};
           relate_forward(n, L, subj ? sm.nw : sm.cur, subj ? sm.cur : sm.nw, subj, sm.res, sm.inner, sm.sc);
         }
-        if (tid < n) sm.cur[tid] = sm.res[tid];
+        if (tid < n) sm.cur[tid] = mod_apply(DFOL_LOAD_MOD(I.mod), sm.res[tid]);
         __syncthreads();
         break;
       }
@@ -291,10 +316,11 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
 #pragma unroll
         for (int j = 0; j < NCHUNK; ++j) acc[j] = 0.f;
         for (int k = w; k < I.a1; k += PROG_WARPS) {
+          const Mod mk = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1);
 #pragma unroll
           for (int j = 0; j < NCHUNK; ++j) {
             const int t = lane + 32 * j;
-            if (t < n) acc[j] += sm.cur[t] + option_ll(im, op[k], t, false, rt, nullptr);
+            if (t < n) acc[j] += mod_apply(mk, sm.cur[t] + option_ll(im, op[k], t, false, rt, nullptr));
           }
         }
         reduce_columns(acc, n, sm.res, sm.sc, false);
@@ -307,11 +333,12 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
         const int32_t* op = opts + I.a0;
         if (normalise) option_denominators(im, op, I.a1, sm.den, sm.sc);
         for (int k = w; k < I.a1; k += PROG_WARPS) {
+          const Mod mk = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1);
           float x[NCHUNK];
 #pragma unroll
           for (int j = 0; j < NCHUNK; ++j) {
             const int t = lane + 32 * j;
-            x[j] = (t < n) ? sm.cur[t] + option_ll(im, op[k], t, normalise, rt, sm.den) : 0.f;
+            x[j] = (t < n) ? mod_apply(mk, sm.cur[t] + option_ll(im, op[k], t, normalise, rt, sm.den)) : 0.f;
           }
           const float lp = warp_exists(x, n, hard, nullptr);
           if (lane == 0) lp_out[I.out + k] = lp;
@@ -326,6 +353,7 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
         if (normalise) option_denominators(im, op, I.a1, sm.den, sm.sc);
         float part = 0.f;
         for (int k = w; k < I.a1; k += PROG_WARPS) {
+          const Mod mk = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1);
           float s = 0.f;
           bool first = true;
 #pragma unroll
@@ -333,7 +361,7 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
             const int t = lane + 32 * j;
             if (t < n) {
               const float a = sm.cur[t];
-              const float y = lnot(a + lnot(a + option_ll(im, op[k], t, normalise, rt, sm.den)));
+              const float y = lnot(a + lnot(mod_apply(mk, a + option_ll(im, op[k], t, normalise, rt, sm.den))));
               const float r = roundtrip(y);
               if (hard) { s = first ? r : fminf(s, r); first = false; }
               else s += r;
@@ -354,13 +382,14 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
         if (normalise) option_denominators(im, op, I.a1, sm.den, sm.sc);
         float part = 0.f;
         for (int k = w; k < I.a1; k += PROG_WARPS) {
+          const Mod m1 = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1), m2 = DFOL_LOAD_MOD(I.mod2 >= 0 ? I.mod2 + k : -1);
           float x1[NCHUNK], x2[NCHUNK];
 #pragma unroll
           for (int j = 0; j < NCHUNK; ++j) {
             const int t = lane + 32 * j;
             const float l = (t < n) ? option_ll(im, op[k], t, normalise, rt, sm.den) : 0.f;
-            x1[j] = (t < n) ? sm.saved[t] + l : 0.f;
-            x2[j] = (t < n) ? sm.cur[t] + l : 0.f;
+            x1[j] = (t < n) ? mod_apply(m1, sm.saved[t] + l) : 0.f;
+            x2[j] = (t < n) ? mod_apply(m2, sm.cur[t] + l) : 0.f;
           }
           const float e1 = warp_exists(x1, n, hard, nullptr);
           const float e2 = warp_exists(x2, n, hard, nullptr);
@@ -377,8 +406,8 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
         // filter both branches by the attribute, exists, log-softmax over the two, flip by is_less (:730-738)
         if (tid < n) {
           const float l = (I.a0 >= 0) ? post_ll(attr_raw(im, I.a0, tid), neg, rt) : 0.0f;
-          sm.res[tid] = sm.saved[tid] + l;
-          sm.nw[tid] = sm.cur[tid] + l;
+          sm.res[tid] = mod_apply(DFOL_LOAD_MOD(I.mod), sm.saved[tid] + l);
+          sm.nw[tid] = mod_apply(DFOL_LOAD_MOD(I.mod2), sm.cur[tid] + l);
         }
         __syncthreads();
         const float e1 = exists_block(sm.res, n, hard, sm.sc, nullptr);
@@ -396,10 +425,22 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
 
       case DFOL_OP_CHOOSE_REL: {
         select_into(sm.nw, im, I.a2, I.flags & DFOL_F_NAME_NEG, I.flags & DFOL_F_NAME_ROUNDTRIP);
+        {
+          const Mod ms = DFOL_LOAD_MOD(I.mod2);
+          if (ms.on) {
+            if (tid < n) sm.nw[tid] = mod_apply(ms, sm.nw[tid]);
+            __syncthreads();
+          }
+        }
         const bool subj = I.flags & DFOL_F_SUBJECT;
         for (int k = 0; k < I.a1; ++k) {
           RelOption L{&im, opts + I.a0, I.a1, k, normalise, rt, -1, false};
           relate_forward(n, L, subj ? sm.nw : sm.cur, subj ? sm.cur : sm.nw, subj, sm.res, sm.inner, sm.sc);
+          const Mod mk = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1);
+          if (mk.on) {
+            if (tid < n) sm.res[tid] = mod_apply(mk, sm.res[tid]);
+            __syncthreads();
+          }
           const float lp = exists_block(sm.res, n, hard, sm.sc, nullptr);
           if (tid == 0) lp_out[I.out + k] = lp;
           __syncthreads();
@@ -435,8 +476,8 @@ extern "C" int dfol_prog_timing_read(long long* host, int n) {
 extern "C" int DFOL_PROGRAM_FWD_ENTRY(const int32_t* instr, const int32_t* q_instr, const int32_t* opts,
                                       int question_num, const float* attr_ll, const int64_t* attr_blk,
                                       const int32_t* attr_stride, const float* rel_ll, const int64_t* rel_blk,
-                                      const int32_t* rel_stride, const int32_t* img_n, float* lp_out, float* tape,
-                                      int tape_stride, void* stream) {
+                                      const int32_t* rel_stride, const int32_t* img_n, const float* mods,
+                                      float* lp_out, float* tape, int tape_stride, void* stream) {
   DFOL_REQUIRE(instr && q_instr && attr_ll && attr_blk && attr_stride && rel_ll && rel_blk && rel_stride && img_n &&
                    lp_out,
                "dfol_program_fwd: null pointer");
@@ -449,14 +490,14 @@ extern "C" int DFOL_PROGRAM_FWD_ENTRY(const int32_t* instr, const int32_t* q_ins
   int nbuf = (96 * 1024) / (tile_floats * 4);
   nbuf = nbuf < 1 ? 1 : (nbuf > 4 ? 4 : nbuf);
   const size_t smem = (size_t)nbuf * tile_floats * 4;
-  cudaFuncSetAttribute(program_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  program_fwd_kernel<<<question_num, PROG_THREADS, smem, (cudaStream_t)stream>>>(
-      instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, lp_out, tape,
+  cudaFuncSetAttribute(mods ? program_fwd_kernel<true> : program_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  (mods ? program_fwd_kernel<true> : program_fwd_kernel<false>)<<<question_num, PROG_THREADS, smem, (cudaStream_t)stream>>>(
+      instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, mods, lp_out, tape,
       tape_stride, nbuf, tile_floats);
   return finish_launch("dfol_program_fwd_fast");
 #else
-  program_fwd_kernel<<<question_num, PROG_THREADS, 0, (cudaStream_t)stream>>>(
-      instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, lp_out, tape,
+  (mods ? program_fwd_kernel<true> : program_fwd_kernel<false>)<<<question_num, PROG_THREADS, 0, (cudaStream_t)stream>>>(
+      instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, mods, lp_out, tape,
       tape_stride);
   return finish_launch("dfol_program_fwd");
 #endif

@@ -228,7 +228,8 @@ class ReasoningEngine(object):
         return cp.device_cache
 
     def run_programs(self, cp, scene, save_tape=True):
-        """Executes the compiled programs; returns lp (cp.lp_num,) and the tape (or None)."""
+        """Executes the compiled programs; returns lp (cp.lp_num,) and the tape (or None).  ``scene.mods`` (optional,
+        (cp.mod_rows, 4) fp32): attention-transfer modulations; program_backward then fills ``scene.d_mods``."""
         lay = scene.layout
         dev = scene.attr_ll.device
         st = capi.stream_ptr(dev)
@@ -243,7 +244,7 @@ class ReasoningEngine(object):
         entry = 'dfol_program_fwd_fast' if self.gemm_mode == 'bf16' else 'dfol_program_fwd'
         call(entry, ptr(d['instr']), ptr(d['q_instr']), ptr(d['opts']), cp.question_num,
              ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride), ptr(scene.rel_ll), ptr(scene.rel_blk),
-             ptr(lay.rel_stride), ptr(lay.img_n), ptr(lp), ptr(tape), stride, st)
+             ptr(lay.rel_stride), ptr(lay.img_n), ptr(getattr(scene, 'mods', None)), ptr(lp), ptr(tape), stride, st)
         return lp[:cp.lp_num], tape
 
     # ------------------------------------------------------------------------------------------ backward
@@ -287,7 +288,8 @@ class ReasoningEngine(object):
         entry = 'dfol_program_bwd_fast' if self.gemm_mode == 'bf16' else 'dfol_program_bwd'
         call(entry, ptr(d['instr']), ptr(d['q_instr']), ptr(d['opts']), cp.question_num,
              ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride), ptr(scene.rel_ll), ptr(scene.rel_blk),
-             ptr(lay.rel_stride), ptr(lay.img_n), ptr(d_lp), ptr(tape), stride, ptr(g_attr), ptr(g_rel), st)
+             ptr(lay.rel_stride), ptr(lay.img_n), ptr(getattr(scene, 'mods', None)), ptr(d_lp), ptr(tape), stride,
+             ptr(g_attr), ptr(g_rel), ptr(getattr(scene, 'd_mods', None)), st)
         return g_attr, g_rel
 
     def backward(self, cp, scene, tape, d_lp, grads):

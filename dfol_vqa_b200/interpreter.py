@@ -24,6 +24,7 @@ from . import capi
 from .capi import K, call, ptr
 from .compiler import BINARY, QUERY, STATEMENT, ProgramCompiler
 from .engine import OracleWeights, ReasoningEngine, SceneLayout
+from .modulator import AttentionTransfer
 from .networks import dropout_p, linear_layers
 from .parallel import FlatBucket
 
@@ -53,22 +54,46 @@ class FastClassifierOracle(nn.Module):
 
 
 class _ReasoningFunction(torch.autograd.Function):
-    """features + oracle parameters -> log-probabilities of one program batch."""
+    """features + oracle parameters (+ attention-transfer modulations) -> log-probabilities of one program batch."""
 
     @staticmethod
-    def forward(ctx, engine, cp, layout, features, need_grad, *params):
-        scene = engine.build_scene(features, layout, keep_for_backward=need_grad, cp=cp)
+    def forward(ctx, engine, cp, layout, features, need_grad, mods, *params):
+        oracle_grad = need_grad and any(p.requires_grad for p in params)
+        scene = engine.build_scene(features, layout, keep_for_backward=oracle_grad, cp=cp)
+        if mods is not None:
+            scene.mods = mods.detach().float().contiguous()
         lp, tape = engine.run_programs(cp, scene, save_tape=need_grad)
         ctx.engine, ctx.cp, ctx.scene, ctx.tape, ctx.params = engine, cp, scene, tape, params
+        ctx.oracle_grad, ctx.mod_dtype = oracle_grad, (None if mods is None else mods.dtype)
         return lp
 
     @staticmethod
     def backward(ctx, d_lp):
-        params = ctx.params
-        grads = {id(p): torch.zeros_like(p, dtype=torch.float32) for p in params}
-        ctx.engine.backward(ctx.cp, ctx.scene, ctx.tape, d_lp.contiguous().float(), grads)
+        params, scene = ctx.params, ctx.scene
+        d_lp = d_lp.contiguous().float()
+        if ctx.mod_dtype is not None:
+            scene.d_mods = torch.zeros_like(scene.mods)
+        if ctx.oracle_grad:
+            grads = {id(p): torch.zeros_like(p, dtype=torch.float32) for p in params}
+            ctx.engine.backward(ctx.cp, scene, ctx.tape, d_lp, grads)
+        else:
+            # frozen oracle (sample_config.yaml: only the attention networks train): the backward interpreter alone
+            # yields d loss / d modulations; the scene's backward pass is skipped
+            grads = {}
+            ctx.engine.program_backward(ctx.cp, scene, ctx.tape, d_lp)
+        d_mods = None if ctx.mod_dtype is None else scene.d_mods.to(ctx.mod_dtype)
         ctx.scene = ctx.tape = None
-        return (None, None, None, None, None) + tuple(grads[id(p)] if p.requires_grad else None for p in params)
+        return (None, None, None, None, None, d_mods) + tuple(
+            grads[id(p)] if (p.requires_grad and ctx.oracle_grad) else None for p in params)
+
+
+class _Holder(nn.Module):
+    """Registers shared sub-modules under the reference's attribute path (state-dict key compatibility)."""
+
+    def __init__(self, **children):
+        super(_Holder, self).__init__()
+        for k, v in children.items():
+            setattr(self, k, v)
 
 
 class FastGQAInterpreter(nn.Module):
@@ -81,9 +106,12 @@ class FastGQAInterpreter(nn.Module):
         super(FastGQAInterpreter, self).__init__()
         if trainable_module_type is not None or trainable_gate or feature_dim != 1:
             raise NotImplementedError('trainable logic gates / operator MLPs are outside the hot path (SURVEY.md §2)')
-        if forward_attention_network is not None or backward_attention_network is not None or \
-                attention_output_network is not None:
-            raise NotImplementedError('attention-transfer calibrator: SURVEY.md §8(f) row 1 (next)')
+        attention_nets = (forward_attention_network, backward_attention_network, attention_output_network)
+        if any(n is not None for n in attention_nets) and not all(n is not None for n in attention_nets):
+            raise ValueError('the attention-transfer calibrator needs all three attention networks')
+        if not apply_modulation_everywhere and attention_nets[0] is not None:
+            raise NotImplementedError('apply_modulation_everywhere=False (the reference itself fails on it: '
+                                      'batch_base_interpreter.py:90-92 sets an attribute on a list)')
         if visual_rule_learner is not None or calibrator is not None:
             raise NotImplementedError('visual rule learner / calibrator are not part of the reference hot path')
         if featurizer is None:
@@ -95,7 +123,8 @@ class FastGQAInterpreter(nn.Module):
         self._likelihood_threshold = likelihood_threshold
         self._hard_mode = hard_mode
         self._global_step = nn.Parameter(torch.tensor([0], dtype=torch.float), requires_grad=False)
-        self._has_modulator = False
+        self._has_modulator = attention_nets[0] is not None
+        self._attention_transfer_state_dim = attention_transfer_state_dim
         self._cached = cached
         self._gemm_mode = gemm_mode or os.environ.get('DFOL_GEMM_MODE', 'fp32')
 
@@ -109,7 +138,28 @@ class FastGQAInterpreter(nn.Module):
                                       linear_layers(oracle._embedding_network)[0])
         self._engine = ReasoningEngine(self._weights, ontology._relation_index, self._gemm_mode)
         self._compiler = ProgramCompiler(ontology, normalize=oracle._normalize, hard_mode=hard_mode,
-                                         relation_slots=(self._gemm_mode == 'bf16'))
+                                         relation_slots=(self._gemm_mode == 'bf16'), modulated=self._has_modulator)
+        self._attention = None
+        if self._has_modulator:
+            # the reference registers the SAME three networks under every operator module; the first registration
+            # (_ops.select._filter.*) names the parameters, the remaining paths are kept so that checkpoints written by
+            # either side load into the other (load_state_dict(strict=False), batch_base_interpreter.py:42-43)
+            def flt():
+                return _Holder(_forward_attention_network=forward_attention_network,
+                               _backward_attention_network=backward_attention_network,
+                               _attention_output_network=attention_output_network)
+            def sel():
+                return _Holder(_filter=flt())
+            def rel():
+                return _Holder(_gqa_select=sel(), _relate=flt())
+            self._ops = nn.ModuleDict({
+                'select': sel(), 'filter': sel(), 'relate': rel(), 'query_attr': _Holder(_gqa_choose_attr=sel()),
+                'choose_attr': sel(), 'verify_attrs': sel(), 'choose_rel': rel(),
+                'verify_rel': _Holder(_gqa_relate=rel()), 'all_same': sel(),
+                'all_different': _Holder(_gqa_all_same=sel()), 'two_same': sel(),
+                'two_different': _Holder(_gqa_two_same=sel()), 'compare': sel()})
+            self._attention = AttentionTransfer(forward_attention_network, backward_attention_network,
+                                                attention_output_network, ontology)
 
     _dropout = 0.0
 
@@ -126,6 +176,15 @@ class FastGQAInterpreter(nn.Module):
 
     def oracle_parameters(self):
         return self._weights.parameters()
+
+    def attention_parameters(self):
+        return [] if self._attention is None else self._attention.parameters()
+
+    def modulations(self, cp, modulator_switch=True):
+        """(cp.mod_rows, 4) autograd-attached modulations of a compiled batch, or None (no calibrator / switched off)."""
+        if self._attention is None or not modulator_switch or cp.mod_rows == 0:
+            return None
+        return self._attention.modulations(cp)
 
     # ---- helpers -----------------------------------------------------------------------------------------
 
@@ -169,7 +228,8 @@ class FastGQAInterpreter(nn.Module):
         self._check_mode(is_training)
         give_answer = not is_training
         params = self._weights.parameters()
-        need_grad = is_training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need_grad = is_training and torch.is_grad_enabled() and any(
+            p.requires_grad for p in params + (self.attention_parameters() if modulator_switch else []))
         lps, metas, traces = [], [], []
         for pb in program_batch_list:
             feats = pb._object_features
@@ -181,7 +241,8 @@ class FastGQAInterpreter(nn.Module):
             layout = SceneLayout.get(counts, self._weights.emb.weight.shape[0], len(self._ontology._relation_index),
                                      feats.device)
             cp = self.compiled(pb, give_answer)
-            lp = _ReasoningFunction.apply(self._engine, cp, layout, feats, need_grad, *params)
+            mods = self.modulations(cp, modulator_switch)
+            lp = _ReasoningFunction.apply(self._engine, cp, layout, feats, need_grad, mods, *params)
             lps.append(lp)
             metas.append(cp)
             traces.append([])
@@ -265,11 +326,22 @@ class FusedTrainStep(object):
         self.betas, self.eps = betas, eps
         self.group = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
-        params = interpreter.oracle_parameters()
+        oracle_params = interpreter.oracle_parameters()
+        # the optimizer sees the trainable parameters only (VQATrainer.get_parameter_list); frozen oracle tensors
+        # (sample_config.yaml freezes all four networks) stay out of the bucket and get scratch gradient buffers
+        self.attention_params = [p for p in interpreter.attention_parameters() if p.requires_grad]
+        params = [p for p in oracle_params if p.requires_grad] + self.attention_params
+        assert params, 'nothing to train'
         self.params = params
+        self.oracle_trainable = any(p.requires_grad for p in oracle_params)
         dev = params[0].device
         self.bucket = FlatBucket(params)
-        self.flat, self.flat_grad, self.grads = self.bucket.flat, self.bucket.flat_grad, self.bucket.grads
+        self.flat, self.flat_grad, self.grads = self.bucket.flat, self.bucket.flat_grad, dict(self.bucket.grads)
+        for p in oracle_params:
+            if not p.requires_grad and self.oracle_trainable:
+                self.grads[id(p)] = torch.zeros_like(p, dtype=torch.float32)
+        for p in self.attention_params:
+            p.grad = self.bucket.grads[id(p)]  # autograd accumulates the modulator's gradients straight into the bucket
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
         self.step_count = 0
@@ -304,14 +376,23 @@ class FusedTrainStep(object):
             layout = SceneLayout.get(counts, interp._weights.emb.weight.shape[0],
                                      len(interp._ontology._relation_index), dev)
             cp = interp.compiled(pb, False)
-            scene = self.engine.build_scene(feats, layout, cp=cp)
+            scene = self.engine.build_scene(feats, layout, keep_for_backward=self.oracle_trainable, cp=cp)
+            mods = interp.modulations(cp)
+            if mods is not None:
+                scene.mods = mods.detach().float().contiguous()
+                scene.d_mods = torch.zeros_like(scene.mods)
             lp, tape = self.engine.run_programs(cp, scene, save_tape=True)
             target = self._targets(pb, cp, dev)
             d_lp = torch.empty_like(lp)
             seg = self.engine.upload_programs(cp, dev).get('seg')
             call('dfol_loss_fwd_bwd', ptr(lp), ptr(target), ptr(seg), cp.question_num, cp.lp_num, cp.kind, scale,
                  ptr(self.scalars), ptr(d_lp), st)
-            self.engine.backward(cp, scene, tape, d_lp, self.grads)
+            if self.oracle_trainable:
+                self.engine.backward(cp, scene, tape, d_lp, self.grads)
+            else:
+                self.engine.program_backward(cp, scene, tape, d_lp)
+            if mods is not None and self.attention_params:
+                mods.backward(scene.d_mods.to(mods.dtype))
         return self.scalars[0]
 
     def optimizer_step(self):

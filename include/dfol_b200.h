@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFOL_ABI_VERSION 2
+#define DFOL_ABI_VERSION 3
 
 /* activation codes (RegularMLP / EmbeddingLayer, gqa_interpreter_experiments.py:28-33, :71-72) */
 #define DFOL_ACT_NONE 0
@@ -207,6 +207,10 @@ int dfol_colsum(const float* X, int64_t ldx, int64_t M, int N, float* out, void*
  * Backward: d_lp (same indexing as lp_out) -> g_attr / g_rel: compact gradient slices w.r.t. the RAW table
  * entries each instruction read (offsets in instr words GA0/GA1/GR; slices of one option list are consecutive
  * with stride attr_stride[b] / rel_stride[b]); buffers must be zeroed by the caller.
+ * mods (optional, may be NULL): float[rows][4] raw attention-transfer modulations (alpha/10, beta/10, c/10, d), one row
+ * per predicate of every modulated sub-operator (BatchVariableSet.apply_modulations, batch_base_types.py:170-187;
+ * rows indexed by the instruction words MOD / MOD2, +k per option); backward writes d loss / d mods into d_mods (same
+ * shape, zeroed by the caller; every row has exactly one writer).
  */
 #define DFOL_INSTR_WORDS 12
 #define DFOL_I_OP 0
@@ -218,6 +222,8 @@ int dfol_colsum(const float* X, int64_t ldx, int64_t M, int N, float* out, void*
 #define DFOL_I_GA0 6  /* g_attr offset of the primary attribute operand (or of option 0) */
 #define DFOL_I_GA1 7  /* g_attr offset of the name operand of relate / choose_rel */
 #define DFOL_I_GR 8   /* g_rel offset of the relation operand (or of option 0) */
+#define DFOL_I_MOD 9  /* attention-transfer modulation row of the primary sub-operator (of option 0), -1 = none */
+#define DFOL_I_MOD2 10 /* ... of the name select of relate / choose_rel, or of the second branch (two_same, compare) */
 
 #define DFOL_OP_SELECT 1
 #define DFOL_OP_FILTER 2
@@ -247,12 +253,12 @@ int dfol_colsum(const float* X, int64_t ldx, int64_t M, int N, float* out, void*
 int dfol_program_fwd(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
                      const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
                      const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride, const int32_t* img_n,
-                     float* lp_out, float* tape, int tape_stride, void* stream);
+                     const float* mods, float* lp_out, float* tape, int tape_stride, void* stream);
 int dfol_program_bwd(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
                      const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
                      const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride, const int32_t* img_n,
-                     const float* d_lp, const float* tape, int tape_stride, float* g_attr, float* g_rel,
-                     void* stream);
+                     const float* mods, const float* d_lp, const float* tape, int tape_stride, float* g_attr,
+                     float* g_rel, float* d_mods, void* stream);
 
 /* Tensor-core-mode builds of the two interpreter kernels (same contract, tape_stride = largest object count rounded
  * up to 4): MUFU exp/log approximations; the N x N tile of every relate hop is fetched with a bulk-async copy into a
@@ -262,12 +268,13 @@ int dfol_program_bwd(const int32_t* instr, const int32_t* q_instr, const int32_t
 int dfol_program_fwd_fast(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
                           const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
                           const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride,
-                          const int32_t* img_n, float* lp_out, float* tape, int tape_stride, void* stream);
+                          const int32_t* img_n, const float* mods, float* lp_out, float* tape, int tape_stride,
+                          void* stream);
 int dfol_program_bwd_fast(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
                           const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
                           const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride,
-                          const int32_t* img_n, const float* d_lp, const float* tape, int tape_stride, float* g_attr,
-                          float* g_rel, void* stream);
+                          const int32_t* img_n, const float* mods, const float* d_lp, const float* tape,
+                          int tape_stride, float* g_attr, float* g_rel, float* d_mods, void* stream);
 
 /* Loss of VQATrainer._compute_loss (nsvqa/train/trainer.py:181-262) and its derivative w.r.t. lp.
  * kind 0 BINARY: BCE(exp(lp), target) summed; 1 QUERY: sum_q slog(sum_{k in q} e^{lp_k}) - sum_k target_k lp_k

@@ -97,7 +97,8 @@ def model_config(dims, dropout=0.0):
             'relation_network_layers_config': [dims['hidden']], 'dropout': dropout}
 
 
-def build_interpreter(ont, dims, state=None, device='cuda', gemm_mode='fp32', seed=0, emb_bias=None):
+def build_interpreter(ont, dims, state=None, device='cuda', gemm_mode='fp32', seed=0, emb_bias=None,
+                      attention_nets=None, freeze_oracle=False):
     """FastGQAInterpreter over freshly initialised (or fixture) oracle networks."""
     from dfol_vqa_b200.interpreter import FastBoxFeaturizer, FastClassifierOracle, FastGQAInterpreter
     from dfol_vqa_b200.networks import build_networks
@@ -110,7 +111,14 @@ def build_interpreter(ont, dims, state=None, device='cuda', gemm_mode='fp32', se
     featurizer = FastBoxFeaturizer(nets['featurizer_network'])
     oracle = FastClassifierOracle(ont, nets['attribute_network'], nets['relation_network'], nets['embedding_network'],
                                   normalize=True, cached=True)
-    interp = FastGQAInterpreter('model', oracle, ont, featurizer, gemm_mode=gemm_mode)
+    if freeze_oracle:
+        for key in ('featurizer_network', 'attribute_network', 'relation_network', 'embedding_network'):
+            nets[key].requires_grad_(False)
+    fwd, bwd, out = attention_nets if attention_nets is not None else (None, None, None)
+    interp = FastGQAInterpreter('model', oracle, ont, featurizer, gemm_mode=gemm_mode,
+                                attention_transfer_state_dim=0 if fwd is None else fwd.hidden_size,
+                                forward_attention_network=fwd, backward_attention_network=bwd,
+                                attention_output_network=out)
     if state is not None:
         missing, unexpected = interp.load_state_dict(state, strict=False)
         assert not unexpected, unexpected
