@@ -6,7 +6,7 @@ been built (``python -c 'import __graft_entry__ as g; g.build()'`` or ``python -
 
 import ctypes
 import os
-from ctypes import c_float, c_int, c_int64, c_void_p
+from ctypes import c_float, c_int, c_int64, c_uint64, c_void_p
 
 import torch
 
@@ -70,6 +70,9 @@ _SIGNATURES = {
     'dfol_pair_layer_dgrad_cluster': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P,
                                               c_int64, c_int, P]),
     'dfol_cast_jobs': (c_int, [P, c_int, c_int64, P]),
+    'dfol_dropout_scale': (c_int, [P, c_int64, c_int64, c_int, c_int, c_uint64, c_int, c_float, P]),
+    'dfol_pair_features_dropout': (c_int, [P, c_int64, c_int, c_int, P, c_int64, c_int, c_int, P, P, P, P, c_int64,
+                                           c_uint64, c_int, c_float, P]),
     'dfol_cast_job_size': (c_int, []),
     'dfol_obj_finish': (c_int, [P, c_int64, c_int, P, c_int64, c_int, P, c_int64, c_int64, P]),
     'dfol_pair_hidden_fwd_tc': (c_int, [P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int, P, P, P, P, c_int,

@@ -56,7 +56,7 @@ class CompiledPrograms(object):
     __slots__ = ('instr', 'q_instr', 'opts', 'lp_num', 'kind', 'options', 'seg', 'names', 'question_num',
                  'g_attr_size', 'g_rel_size', 'attr_slices', 'rel_slices', 'terminal', 'lp_owner', 'device_cache',
                  'alg_bytes', 'slot_wrow', 'img_slot', 'slot_blk', 'rel_slot_size', 'max_slots', 'mod_plan',
-                 'mod_descs', 'mod_rows')
+                 'mod_descs', 'mod_rows', 'slot_after', 'slot_names')
 
 
 class ProgramCompiler(object):
@@ -209,7 +209,16 @@ class ProgramCompiler(object):
                 opts.extend(hit[0])
             return start, len(hit[0]), hit[1]
 
+        slot_after = []                      # per non-terminal slot: instructions each question has executed after it
+        slot_names = []                      # ... and the variable names at that point
+
+        def close_slot():
+            slot_after.append([len(p) for p in prog])
+            slot_names.append(list(names))
+
         for i, slot in enumerate(slots):
+            if i > 0:
+                close_slot()
             name = slot._op_name
             args = slot._arguments
             mask = slot._mask
@@ -396,6 +405,7 @@ class ProgramCompiler(object):
 
         if result['kind'] is None:
             # last slot is not terminal: implicit 'end' (batch_gqa_interpreter.py:75-76)
+            close_slot()
             for q in range(B):
                 emit(q, K.OP_EXIST, out=q)
             lp_num = B
@@ -426,6 +436,8 @@ class ProgramCompiler(object):
         cp.terminal = result['terminal']
         cp.lp_owner = result['lp_owner']
         cp.device_cache = None
+        cp.slot_after = np.asarray(slot_after, dtype=np.int64).reshape(len(slot_after), B)
+        cp.slot_names = slot_names
         cp.mod_plan = mod_plan
         cp.mod_descs = mod_descs
         cp.mod_rows = mod_rows[0]

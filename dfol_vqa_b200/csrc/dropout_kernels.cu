@@ -1,0 +1,186 @@
+// Training-mode dropout of the visual oracle's networks (nn.Dropout in front of every Linear of RegularMLP /
+// EmbeddingLayer: nsvqa/nn/vision/regular_mlp.py:29-32, embedding_layer.py:73; sample_config.yaml: dropout 0.1).
+//
+// The keep/drop decision of element (row, col) of dropout site `site` is a pure function of (seed, site, row, col):
+// Philox4x32-10 keyed by the seed, counter = (group of 8 consecutive columns of the row, site), 16 bits per element,
+// keep iff bits >= round(p * 65536); kept elements are scaled by 1 / (1 - p) like torch.nn.functional.dropout.
+// Nothing is stored: every kernel that needs a mask recomputes it, and the parity tests export the very same masks
+// (dfol_dropout_scale on a tensor of ones) for the CPU oracle -- the reference's own RNG stream cannot be matched.
+#include <cuda_bf16.h>
+
+#include "dfol_common.cuh"
+
+namespace dfol {
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+struct DropSite {
+  uint2 key;
+  uint32_t site, thresh;
+  long long groups_per_row;
+  float scale;
+};
+
+// scale factors (0 or 1/(1-p)) of the 8 elements of column group `g8` of `row`
+__device__ __forceinline__ void drop_scales8(const DropSite& d, long long row, long long g8, float s[8]) {
+  const unsigned long long g = (unsigned long long)row * (unsigned long long)d.groups_per_row + (unsigned long long)g8;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), d.site, 0u), d.key);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s[2 * i] = ((w[i] & 0xffffu) >= d.thresh) ? d.scale : 0.0f;
+    s[2 * i + 1] = ((w[i] >> 16) >= d.thresh) ? d.scale : 0.0f;
+  }
+}
+
+static DropSite make_site(unsigned long long seed, int site, float p, long long cols) {
+  DropSite d;
+  d.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  d.site = (uint32_t)site;
+  long long t = (long long)(p * 65536.0 + 0.5);
+  d.thresh = (uint32_t)(t < 0 ? 0 : (t > 65536 ? 65536 : t));
+  d.groups_per_row = (cols + 7) / 8;
+  d.scale = 1.0f / (1.0f - p);
+  return d;
+}
+
+// x[row, col] *= scale(row, col), in place; one thread per group of 8 columns
+template <class T>
+__global__ void __launch_bounds__(256) dropout_scale_kernel(T* __restrict__ x, long long ld, long long rows, int cols,
+                                                            DropSite d) {
+  const long long total = rows * d.groups_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / d.groups_per_row, g8 = i - row * d.groups_per_row;
+    float s[8];
+    drop_scales8(d, row, g8, s);
+    T* p = x + row * ld + g8 * 8;
+    const int m = min(8, cols - (int)(g8 * 8));
+    if (sizeof(T) == 2 && m == 8 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      uint4 v = *reinterpret_cast<uint4*>(p);
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(h[j]);
+        h[j] = __floats2bfloat162_rn(f.x * s[2 * j], f.y * s[2 * j + 1]);
+      }
+      *reinterpret_cast<uint4*>(p) = v;
+    } else {
+      for (int j = 0; j < m; ++j) p[j] = (T)((float)p[j] * s[j]);
+    }
+  }
+}
+
+// geometry features of an ordered pair (s,o): dist, asin(dy/dist), sign(x_o-x_s), sign(y_o-y_s)
+// (batch_gqa_boxfeatures_pipeline.py:260-279; same arithmetic as scene_kernels.cu pair_geometry)
+__device__ __forceinline__ void drop_pair_geometry(const float* ps, const float* po, float g[4]) {
+  const float x1 = ps[0], y1 = ps[1], w1 = ps[2], h1 = ps[3];
+  const float x2 = po[0], y2 = po[1], w2 = po[2], h2 = po[3];
+  const float dx = x1 + w1 / 2.0f - x2 - w2 / 2.0f;
+  const float dy = y1 + h1 / 2.0f - y2 - h2 / 2.0f;
+  const float dist = sqrtf(dx * dx + dy * dy);
+  g[0] = dist;
+  g[1] = asinf(dy / fmaxf(dist, 1e-10f));
+  const float sx = x2 - x1, sy = y2 - y1;
+  g[2] = (sx > 0.0f) ? 1.0f : (sx < 0.0f ? -1.0f : 0.0f);
+  g[3] = (sy > 0.0f) ? 1.0f : (sy < 0.0f ? -1.0f : 0.0f);
+}
+
+// Masked relation-network input rows: out[(b,s,o), :] = mask .* [obj_s | obj_o | geo(s,o)], zero beyond 2*ldo+4.
+// With an independent mask per pair element the first layer no longer factors into U[s] + V[o], so the training-mode
+// dropout path evaluates it as the reference does, on the materialised pair matrix.  One warp per pair row.
+template <class T>
+__global__ void __launch_bounds__(256) pair_features_dropout_kernel(
+    const float* __restrict__ obj, long long ldobj, int width, int pos_col, T* __restrict__ out, long long ldout,
+    int out_cols, const int32_t* __restrict__ pair_row, const int32_t* __restrict__ obj_row,
+    const int32_t* __restrict__ img_n, const int32_t* __restrict__ pair_img, long long pairs, DropSite d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int in_cols = 2 * width + 4;
+  for (long long r = warp; r < pairs; r += nwarps) {
+    const int b = pair_img[r];
+    const int n = img_n[b];
+    const int local = (int)(r - pair_row[b]);
+    const int s = local / n, o = local - s * n;
+    const float* os = obj + (long long)(obj_row[b] + s) * ldobj;
+    const float* oo = obj + (long long)(obj_row[b] + o) * ldobj;
+    float geo[4];
+    drop_pair_geometry(os + pos_col, oo + pos_col, geo);
+    T* dst = out + r * ldout;
+    for (int g8 = lane; g8 * 8 < out_cols; g8 += 32) {
+      float sc[8];
+      drop_scales8(d, r, g8, sc);
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = g8 * 8 + j;
+        float x = 0.0f;
+        if (c < width) x = os[c];
+        else if (c < 2 * width) x = oo[c - width];
+        else if (c < in_cols) x = geo[c - 2 * width];
+        v[j] = x * sc[j];
+      }
+      T* p8 = dst + g8 * 8;
+      if (sizeof(T) == 2 && g8 * 8 + 8 <= out_cols && (reinterpret_cast<uintptr_t>(p8) & 15) == 0) {
+        uint4 pk;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        *reinterpret_cast<uint4*>(p8) = pk;
+      } else {
+        for (int j = 0; j < 8 && g8 * 8 + j < out_cols; ++j) p8[j] = (T)v[j];
+      }
+    }
+  }
+}
+
+}  // namespace dfol
+
+using namespace dfol;
+
+extern "C" int dfol_dropout_scale(void* x, int64_t ld, int64_t rows, int cols, int is_bf16, uint64_t seed, int site,
+                                  float p, void* stream) {
+  DFOL_REQUIRE(x != nullptr && rows >= 0 && cols > 0 && ld >= cols, "dfol_dropout_scale: bad arguments");
+  DFOL_REQUIRE(p >= 0.0f && p < 1.0f, "dfol_dropout_scale: p must be in [0, 1)");
+  if (rows == 0) return 0;
+  const DropSite d = make_site(seed, site, p, cols);
+  const long long total = rows * d.groups_per_row;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  if (is_bf16)
+    dropout_scale_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x, ld, rows, cols, d);
+  else
+    dropout_scale_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)x, ld, rows, cols, d);
+  return finish_launch("dfol_dropout_scale");
+}
+
+extern "C" int dfol_pair_features_dropout(const float* obj, int64_t ldobj, int width, int pos_col, void* out,
+                                          int64_t ldout, int out_cols, int is_bf16, const int32_t* pair_row,
+                                          const int32_t* obj_row, const int32_t* img_n, const int32_t* pair_img,
+                                          int64_t pairs, uint64_t seed, int site, float p, void* stream) {
+  DFOL_REQUIRE(obj && out && pair_row && obj_row && img_n && pair_img, "dfol_pair_features_dropout: null pointer");
+  DFOL_REQUIRE(width >= 4 && pos_col + 4 <= width && out_cols >= 2 * width + 4 && ldout >= out_cols,
+               "dfol_pair_features_dropout: bad shape");
+  DFOL_REQUIRE(p >= 0.0f && p < 1.0f, "dfol_pair_features_dropout: p must be in [0, 1)");
+  if (pairs == 0) return 0;
+  const DropSite d = make_site(seed, site, p, 2 * width + 4);
+  const long long warps = pairs;
+  const int blocks = (int)((warps + 7) / 8 < 148 * 16 ? (warps + 7) / 8 : 148 * 16);
+  if (is_bf16)
+    pair_features_dropout_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        obj, ldobj, width, pos_col, (__nv_bfloat16*)out, ldout, out_cols, pair_row, obj_row, img_n, pair_img, pairs, d);
+  else
+    pair_features_dropout_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        obj, ldobj, width, pos_col, (float*)out, ldout, out_cols, pair_row, obj_row, img_n, pair_img, pairs, d);
+  return finish_launch("dfol_pair_features_dropout");
+}

@@ -13,6 +13,8 @@ from . import capi
 from .capi import K, call, ptr
 
 DEFAULT_LL = -30.0
+# dropout sites (one independent mask each; rows x logical columns)
+DROP_FEATURES, DROP_ATTR_IN, DROP_ATTR_HIDDEN, DROP_REL_IN, DROP_REL_HIDDEN, DROP_EMB_ATTR, DROP_EMB_REL = range(7)
 
 
 def _roundup(x, m):
@@ -141,11 +143,15 @@ class ReasoningEngine(object):
 
     # ------------------------------------------------------------------------------------------ forward
 
-    def build_scene(self, features, layout, keep_for_backward=True, cp=None):
+    def build_scene(self, features, layout, keep_for_backward=True, cp=None, dropout=None):
         """Featurizer + attribute / relation tables (K1-K6 of SURVEY.md §2.1).  ``cp``: the compiled programs of the
-        batch; when they carry relation slots only those relation columns are evaluated (tensor-core mode)."""
+        batch; when they carry relation slots only those relation columns are evaluated (tensor-core mode).
+        ``dropout``: None, or (p, seed) -- training-mode dropout in front of every Linear (forward only: the oracle
+        networks must be frozen, as in sample_config.yaml); see csrc/dropout_kernels.cu."""
+        if dropout is not None:
+            assert not keep_for_backward, 'dropout is implemented for frozen oracle networks (forward only)'
         if self.gemm_mode == 'bf16':
-            return self.tc.build_scene(features, layout, keep_for_backward, cp)
+            return self.tc.build_scene(features, layout, keep_for_backward, cp, dropout)
         capi.lib()
         w = self.w
         dev = features.device
@@ -159,21 +165,30 @@ class ReasoningEngine(object):
         sc.layout = layout
         sc.features = features
 
+        def drop(x, cols, site):
+            """x[:, :cols] *= mask of dropout site ``site`` (in place); no-op without dropout."""
+            if dropout is not None:
+                call('dfol_dropout_scale', ptr(x), x.stride(0), x.shape[0], cols, int(x.dtype == torch.bfloat16),
+                     int(dropout[1]), site, float(dropout[0]), st)
+            return x
+
         # featurizer: obj = [sigmoid(X Wf^T + b) | box position]
         obj = torch.empty(T, ldo, device=dev, dtype=torch.float32)
-        gemm_f32(features[:, :D], w.feat.weight.t(), obj[:, :F], w.feat.bias, K.ACT_SIGMOID, stream=st)
+        x_in = features[:, :D] if dropout is None else drop(features[:, :D].contiguous(), D, DROP_FEATURES)
+        gemm_f32(x_in, w.feat.weight.t(), obj[:, :F], w.feat.bias, K.ACT_SIGMOID, stream=st)
         call('dfol_box_position', ptr(features), features.stride(0), D, ptr(obj), ldo, F, T, st)
         sc.obj = obj
 
         # attribute chain -> attribute table (all C concept columns)
-        h = obj
+        h = obj if dropout is None else drop(obj.clone(), ldo, DROP_ATTR_IN)
         sc.attr_h = []
         for i, layer in enumerate(w.attr):
+            assert dropout is None or len(w.attr) == 2, 'dropout: one hidden layer per network (reference configs)'
             out = torch.empty(T, layer.weight.shape[0], device=dev, dtype=torch.float32)
             gemm_f32(h, layer.weight.t(), out, layer.bias, K.ACT_ELU if i < len(w.attr) - 1 else K.ACT_SIGMOID,
                      stream=st)
             sc.attr_h.append(out)
-            h = out
+            h = drop(out, out.shape[1], DROP_ATTR_HIDDEN if i == 0 else DROP_EMB_ATTR)
         C = w.emb.weight.shape[0]
         attr_ll = torch.empty(layout.attr_size, device=dev, dtype=torch.float32)
         obj_table = {'row_img': layout.obj_img, 'img_row': layout.obj_row, 'img_blk': layout.attr_blk,
@@ -192,9 +207,22 @@ class ReasoningEngine(object):
         wg = first.weight[:, 2 * ldo:]
         h1 = torch.empty(layout.P, H, device=dev, dtype=torch.float32)
         act1 = K.ACT_ELU if len(w.rel) > 1 else K.ACT_SIGMOID
-        call('dfol_pair_hidden_fwd', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo, ptr(wg), first.weight.stride(0),
-             ptr(first.bias), ptr(h1), H, H, act1, 0, ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_n),
-             layout.B, layout.max_n, st)
+        if dropout is None:
+            call('dfol_pair_hidden_fwd', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo, ptr(wg), first.weight.stride(0),
+                 ptr(first.bias), ptr(h1), H, H, act1, 0, ptr(layout.pair_row), ptr(layout.obj_row),
+                 ptr(layout.img_n), layout.B, layout.max_n, st)
+        else:
+            # an independent mask per pair element breaks the U[s] + V[o] factorisation: the first layer runs on the
+            # materialised, masked pair matrix as in the reference (batch_gqa_boxfeatures_pipeline.py:260-281)
+            assert len(w.rel) == 2, 'dropout: one hidden layer per network (reference configs)'
+            width = 2 * ldo + 4
+            pm = torch.empty(layout.P, width, device=dev, dtype=torch.float32)
+            call('dfol_pair_features_dropout', ptr(obj), ldo, ldo, F, ptr(pm), width, width, 0, ptr(layout.pair_row),
+                 ptr(layout.obj_row), ptr(layout.img_n), ptr(layout.pair_img), layout.P, int(dropout[1]),
+                 DROP_REL_IN, float(dropout[0]), st)
+            gemm_f32(pm, first.weight.t(), h1, first.bias, act1, stream=st)
+            del pm
+            drop(h1, H, DROP_REL_HIDDEN)
         sc.rel_h = [h1]
         h = h1
         for i, layer in enumerate(w.rel[1:], start=1):
@@ -202,7 +230,7 @@ class ReasoningEngine(object):
             gemm_f32(h, layer.weight.t(), out, layer.bias, K.ACT_ELU if i < len(w.rel) - 1 else K.ACT_SIGMOID,
                      stream=st)
             sc.rel_h.append(out)
-            h = out
+            h = drop(out, out.shape[1], DROP_EMB_REL)
         ridx = self.rel_index(dev)
         sc.w_rel = w.emb.weight.detach().index_select(0, ridx).contiguous()
         sc.b_rel = w.emb.bias.detach().index_select(0, ridx).contiguous()

@@ -147,8 +147,9 @@ class TensorCorePath(object):
 
     # -------------------------------------------------------------------------------------------- forward
 
-    def build_scene(self, features, layout, training, cp=None):
-        from .engine import Scene
+    def build_scene(self, features, layout, training, cp=None, dropout=None):
+        from .engine import (Scene, DROP_FEATURES, DROP_ATTR_IN, DROP_ATTR_HIDDEN, DROP_REL_IN, DROP_REL_HIDDEN,
+                             DROP_EMB_ATTR, DROP_EMB_REL)
         capi.lib()
         w = self.w
         dev = features.device
@@ -166,9 +167,17 @@ class TensorCorePath(object):
         def bf(rows, cols):
             return torch.empty(rows, cols, device=dev, dtype=torch.bfloat16)
 
+        def drop(x, cols, site, stream=None):
+            """x[:, :cols] *= mask of dropout site ``site`` (in place); no-op without dropout."""
+            if dropout is not None:
+                call('dfol_dropout_scale', ptr(x), x.stride(0), x.shape[0], cols, int(x.dtype == torch.bfloat16),
+                     int(dropout[1]), site, float(dropout[0]), st if stream is None else stream)
+            return x
+
         # featurizer: obj = [sigmoid(X Wf^T + b) | box position] (fp32 for the pair kernel) + bf16 operand copy
         x16 = bf(T, p['Dp'])
         call('dfol_cast_bf16', ptr(features), features.stride(0), ptr(x16), p['Dp'], T, D, st)
+        drop(x16, D, DROP_FEATURES)
         obj = torch.empty(T, ldo, device=dev, dtype=torch.float32)
         self._tc(x16, ops.wf, obj, F, p['Dp'], w.feat.bias, K.ACT_SIGMOID, st)
         obj16 = bf(T, p['Op'])
@@ -185,9 +194,12 @@ class TensorCorePath(object):
             side.wait_event(ev_obj)
             st2 = side.cuda_stream
             h1a = bf(T, p['Hap'])
-            self._tc(obj16, ops.wa1, h1a, Ha, p['Op'], w.attr[0].bias, K.ACT_ELU, st2)
+            obj16a = obj16 if dropout is None else drop(obj16.clone(), ldo, DROP_ATTR_IN, st2)
+            self._tc(obj16a, ops.wa1, h1a, Ha, p['Op'], w.attr[0].bias, K.ACT_ELU, st2)
+            drop(h1a, Ha, DROP_ATTR_HIDDEN, st2)
             h2a = bf(T, p['Ep'])
             self._tc(h1a, ops.wa2, h2a, E, p['Hap'], w.attr[1].bias, K.ACT_SIGMOID, st2)
+            drop(h2a, E, DROP_EMB_ATTR, st2)
             attr_ll = torch.empty(layout.attr_size, device=dev, dtype=torch.float32)
             obj_table = {'row_img': layout.obj_img, 'img_row': layout.obj_row, 'img_blk': layout.attr_blk,
                          'img_stride': layout.attr_stride}
@@ -199,19 +211,40 @@ class TensorCorePath(object):
 
         # relation chain: U|V in one GEMM, pair hidden layer, layer 2, relation table
         first = w.rel[0]
-        uv = torch.empty(T, 2 * H, device=dev, dtype=torch.float32)
-        self._tc(obj16, ops.wuv, uv, 2 * H, p['Op'], None, K.ACT_NONE, st)
         h1r = bf(layout.P, p['Hp'])
-        geo = torch.empty(layout.P, 4, device=dev, dtype=torch.float32) if training else None
-        if capi.trace is not None:
-            capi.next_meta = {'tag': 'pair_hidden_fwd_tc', 'bytes': 2.0 * layout.P * p['Hp']}
-        call('dfol_pair_hidden_fwd_tc', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo, ptr(first.weight[:, 2 * ldo:]),
-             first.weight.stride(0), ptr(first.bias), ptr(h1r), p['Hp'], H, ptr(geo), ptr(layout.pair_row),
-             ptr(layout.obj_row), ptr(layout.img_n), layout.B, layout.max_n, st)
+        if dropout is None:
+            uv = torch.empty(T, 2 * H, device=dev, dtype=torch.float32)
+            self._tc(obj16, ops.wuv, uv, 2 * H, p['Op'], None, K.ACT_NONE, st)
+            geo = torch.empty(layout.P, 4, device=dev, dtype=torch.float32) if training else None
+            if capi.trace is not None:
+                capi.next_meta = {'tag': 'pair_hidden_fwd_tc', 'bytes': 2.0 * layout.P * p['Hp']}
+            call('dfol_pair_hidden_fwd_tc', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo,
+                 ptr(first.weight[:, 2 * ldo:]), first.weight.stride(0), ptr(first.bias), ptr(h1r), p['Hp'], H,
+                 ptr(geo), ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_n), layout.B, layout.max_n, st)
+        else:
+            # an independent mask per pair element breaks the U[s] + V[o] factorisation: the first layer runs as one
+            # tcgen05 GEMM over the materialised, masked pair matrix (the reference's formulation,
+            # batch_gqa_boxfeatures_pipeline.py:260-281)
+            uv = geo = None
+            width = 2 * ldo + 4
+            Kp = _roundup(width, 64)
+            pm = bf(layout.P, Kp)
+            if capi.trace is not None:
+                capi.next_meta = {'tag': 'pair_features_dropout', 'bytes': 2.0 * layout.P * Kp}
+            call('dfol_pair_features_dropout', ptr(obj), ldo, ldo, F, ptr(pm), Kp, Kp, 1, ptr(layout.pair_row),
+                 ptr(layout.obj_row), ptr(layout.img_n), ptr(layout.pair_img), layout.P, int(dropout[1]),
+                 DROP_REL_IN, float(dropout[0]), st)
+            w1 = torch.zeros(H, Kp, device=dev, dtype=torch.bfloat16)
+            call('dfol_cast_bf16', ptr(first.weight), first.weight.stride(0), ptr(w1), Kp, H, width, st)
+            if p['Hp'] > H:
+                h1r.zero_()
+            self._tc(pm, w1, h1r, H, Kp, first.bias, K.ACT_ELU, st)
+            del pm
+            drop(h1r, H, DROP_REL_HIDDEN)
         # the activation of layer 2 is only materialised when the backward pass (or the dense table) needs it
         slots = cp is not None and cp.img_slot is not None
         # inference with few relation columns per image: layer 2 and the columns in one kernel, no activation store
-        fused = slots and not training and cp.max_slots <= 4
+        fused = slots and not training and cp.max_slots <= 4 and dropout is None
         h2r = None if fused else bf(layout.P, p['Ep'])
         if slots:
             dc = self.engine.upload_programs(cp, dev)
@@ -225,6 +258,7 @@ class TensorCorePath(object):
                                       'bytes': 2.0 * layout.P * (p['Hp'] + p['Ep'])}
                 call('dfol_pair_layer_fwd_cluster', ptr(h1r), p['Hp'], ptr(ops.wr2), p['Hp'], ptr(h2r), p['Ep'],
                      p['Ep'], ptr(w.rel[1].bias), layout.P, E, p['Hp'], K.ACT_SIGMOID, st)
+                drop(h2r, E, DROP_EMB_REL)
                 if capi.trace is not None:
                     capi.next_meta = {'tag': 'rel_slots_fwd', 'bytes': 2.0 * layout.P * p['Ep'] * max(
                         1, (cp.max_slots + 7) // 8) + 4.0 * cp.rel_slot_size}
@@ -246,6 +280,7 @@ class TensorCorePath(object):
             sc.rel_blk, sc.rel_slots = dc['slot_blk'], True
         else:
             self._tc(h1r, ops.wr2, h2r, E, p['Hp'], w.rel[1].bias, K.ACT_SIGMOID, st)
+            drop(h2r, E, DROP_EMB_REL)
             ridx = self.engine.rel_index(dev)
             sc.w_rel = w.emb.weight.detach().index_select(0, ridx).contiguous()
             sc.b_rel = w.emb.bias.detach().index_select(0, ridx).contiguous()

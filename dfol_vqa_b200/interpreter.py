@@ -57,12 +57,14 @@ class _ReasoningFunction(torch.autograd.Function):
     """features + oracle parameters (+ attention-transfer modulations) -> log-probabilities of one program batch."""
 
     @staticmethod
-    def forward(ctx, engine, cp, layout, features, need_grad, mods, *params):
+    def forward(ctx, engine, cp, layout, features, need_grad, mods, sink, dropout, *params):
         oracle_grad = need_grad and any(p.requires_grad for p in params)
-        scene = engine.build_scene(features, layout, keep_for_backward=oracle_grad, cp=cp)
+        scene = engine.build_scene(features, layout, keep_for_backward=oracle_grad, cp=cp, dropout=dropout)
         if mods is not None:
             scene.mods = mods.detach().float().contiguous()
-        lp, tape = engine.run_programs(cp, scene, save_tape=need_grad)
+        lp, tape = engine.run_programs(cp, scene, save_tape=need_grad or sink is not None)
+        if sink is not None:
+            sink['tape'] = tape
         ctx.engine, ctx.cp, ctx.scene, ctx.tape, ctx.params = engine, cp, scene, tape, params
         ctx.oracle_grad, ctx.mod_dtype = oracle_grad, (None if mods is None else mods.dtype)
         return lp
@@ -83,8 +85,19 @@ class _ReasoningFunction(torch.autograd.Function):
             ctx.engine.program_backward(ctx.cp, scene, ctx.tape, d_lp)
         d_mods = None if ctx.mod_dtype is None else scene.d_mods.to(ctx.mod_dtype)
         ctx.scene = ctx.tape = None
-        return (None, None, None, None, None, d_mods) + tuple(
+        return (None, None, None, None, None, d_mods, None, None) + tuple(
             grads[id(p)] if (p.requires_grad and ctx.oracle_grad) else None for p in params)
+
+
+class _TraceEntry(object):
+    """What the reference's trace consumers read of a BatchVariableSet (batch_base_types.py:34-100)."""
+
+    def __init__(self, log_attention, names):
+        self._log_attention = log_attention
+        self._name = names
+
+    def get_attention(self):
+        return self._log_attention.exp()
 
 
 class _Holder(nn.Module):
@@ -217,21 +230,38 @@ class FastGQAInterpreter(nn.Module):
             cache[key] = self._compiler.compile(pb, self._object_counts(pb), give_answer=give_answer)
         return cache[key]
 
-    def _check_mode(self, is_training):
-        if is_training and self.training and self._dropout > 0:
-            raise NotImplementedError('dropout > 0 in training mode is not implemented in the fused path yet '
-                                      '(set dropout: 0.0); SURVEY.md §7 hard parts')
+    def _dropout_for(self, is_training):
+        """None, or (p, seed) of this forward pass: nn.Dropout is active when the module is in train() mode and the
+        networks were built with dropout > 0 (sample_config.yaml: 0.1).  Implemented for FROZEN oracle networks (the
+        sample configuration: only the attention networks train), i.e. forward only; a fresh seed per call is drawn from
+        torch's CPU generator (reproducible under torch.manual_seed).  The reference's own RNG stream cannot be matched;
+        the masks are a pure function of the seed (csrc/dropout_kernels.cu) and the tests export them for the oracle."""
+        if not (is_training and self.training and self._dropout > 0):
+            return None
+        if any(p.requires_grad for p in self._weights.parameters()):
+            raise NotImplementedError('dropout > 0 with TRAINABLE oracle networks is not implemented (the backward pass '
+                                      'of the masked layers): freeze the four oracle networks as sample_config.yaml '
+                                      'does, or set dropout: 0.0')
+        seed = self._fixed_dropout_seed
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        self._last_dropout_seed = seed
+        return (float(self._dropout), seed)
+
+    _fixed_dropout_seed = None
+    _last_dropout_seed = None
 
     # ---- forward -----------------------------------------------------------------------------------------
 
     def forward(self, program_batch_list, is_training, return_trace=False, modulator_switch=True):
-        self._check_mode(is_training)
+        dropout = self._dropout_for(is_training)
         give_answer = not is_training
         params = self._weights.parameters()
         need_grad = is_training and torch.is_grad_enabled() and any(
             p.requires_grad for p in params + (self.attention_parameters() if modulator_switch else []))
         lps, metas, traces = [], [], []
-        for pb in program_batch_list:
+        for k, pb in enumerate(program_batch_list):
+            drop_k = None if dropout is None else (dropout[0], dropout[1] + k)  # independent masks per sub-batch
             feats = pb._object_features
             if not feats.is_cuda:
                 raise RuntimeError('dfol_vqa_b200 runs on CUDA only (no CPU fallback): move the program batch to the '
@@ -242,14 +272,37 @@ class FastGQAInterpreter(nn.Module):
                                      feats.device)
             cp = self.compiled(pb, give_answer)
             mods = self.modulations(cp, modulator_switch)
-            lp = _ReasoningFunction.apply(self._engine, cp, layout, feats, need_grad, mods, *params)
+            sink = {} if return_trace else None
+            lp = _ReasoningFunction.apply(self._engine, cp, layout, feats, need_grad, mods, sink, drop_k, *params)
             lps.append(lp)
             metas.append(cp)
-            traces.append([])
+            traces.append(self._trace(cp, layout, sink['tape']) if return_trace else [])
         result = self._gather(lps, metas, give_answer)
         if return_trace:
             return result, traces
         return result
+
+    def _trace(self, cp, layout, tape):
+        """Per-slot attention states for ``return_trace=True`` (VQATrainer._visualize_batch reads
+        ``trace[k][i]._log_attention[j, :]``, trainer.py:548, :591): entry i holds the (questions, T) log-attention after
+        op slot i, rebuilt from the interpreter's attention tape.  Objects of other images -- which the reference fills
+        with by-products that no output depends on -- are set to log(1e-20).  The terminal slot has no entry."""
+        B, T, dev = layout.B, layout.T, tape.device
+        stride = tape.numel() // max(cp.instr.shape[0], 1)
+        rows = tape.view(-1, stride)
+        q_first = torch.from_numpy(cp.q_instr[:-1].astype(np.int64)).to(dev)
+        n = layout.img_n.long()
+        col = torch.arange(stride, device=dev)[None, :].expand(B, stride)
+        valid = col < n[:, None]
+        dst = (layout.obj_row[:-1].long()[:, None] + col)[valid]
+        qi = torch.arange(B, device=dev)[:, None].expand(B, stride)[valid]
+        out = []
+        for i in range(cp.slot_after.shape[0]):
+            ip = q_first + torch.from_numpy(cp.slot_after[i]).to(dev)
+            att = torch.full((B, T), math.log(1e-20), device=dev, dtype=torch.float32)
+            att[qi, dst] = rows[ip][valid]
+            out.append(_TraceEntry(att, cp.slot_names[i]))
+        return out
 
     def _gather(self, lps, metas, give_answer):
         """gather_results (reference: nsvqa/nn/interpreter/data_parallel.py:15-50) + host-side answers."""
@@ -361,12 +414,13 @@ class FusedTrainStep(object):
         """Accumulates gradients of loss / global_question_num into the flat bucket; returns the device loss scalar
         (local share)."""
         interp = self.interp
-        interp._check_mode(True)
+        dropout = interp._dropout_for(True)
         total = global_question_num or sum(pb.batch_size() for pb in program_batch_list)
         scale = 1.0 / float(total)
         self.flat_grad.zero_()
         self.scalars.zero_()
-        for pb in program_batch_list:
+        for k, pb in enumerate(program_batch_list):
+            drop_k = None if dropout is None else (dropout[0], dropout[1] + k)
             feats = pb._object_features
             if not feats.is_cuda:
                 raise RuntimeError('dfol_vqa_b200 runs on CUDA only (no CPU fallback)')
@@ -376,7 +430,8 @@ class FusedTrainStep(object):
             layout = SceneLayout.get(counts, interp._weights.emb.weight.shape[0],
                                      len(interp._ontology._relation_index), dev)
             cp = interp.compiled(pb, False)
-            scene = self.engine.build_scene(feats, layout, keep_for_backward=self.oracle_trainable, cp=cp)
+            scene = self.engine.build_scene(feats, layout, keep_for_backward=self.oracle_trainable, cp=cp,
+                                            dropout=drop_k)
             mods = interp.modulations(cp)
             if mods is not None:
                 scene.mods = mods.detach().float().contiguous()

@@ -276,6 +276,21 @@ int dfol_program_bwd_fast(const int32_t* instr, const int32_t* q_instr, const in
                           const int32_t* img_n, const float* mods, const float* d_lp, const float* tape,
                           int tape_stride, float* g_attr, float* g_rel, float* d_mods, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Training-mode dropout of the oracle networks (nn.Dropout in front of every Linear: nsvqa/nn/vision/regular_mlp.py:
+ * 29-32, embedding_layer.py:73; sample_config.yaml: dropout 0.1).  The keep/drop decision of element (row, col) of
+ * dropout site `site` is a pure function of (seed, site, row, col) (Philox4x32-10, 16 bits per element); kept elements
+ * are scaled by 1/(1-p).  dfol_dropout_scale multiplies a row-major matrix in place (run it on a tensor of ones to
+ * export a mask); dfol_pair_features_dropout writes the masked relation-network input rows
+ * mask .* [obj_s | obj_o | geo(s,o)] of all pairs (batch_gqa_boxfeatures_pipeline.py:260-281), zero beyond 2*width+4.
+ */
+int dfol_dropout_scale(void* x, int64_t ld, int64_t rows, int cols, int is_bf16, uint64_t seed, int site, float p,
+                       void* stream);
+int dfol_pair_features_dropout(const float* obj, int64_t ldobj, int width, int pos_col, void* out, int64_t ldout,
+                               int out_cols, int is_bf16, const int32_t* pair_row, const int32_t* obj_row,
+                               const int32_t* img_n, const int32_t* pair_img, int64_t pairs, uint64_t seed, int site,
+                               float p, void* stream);
+
 /* Loss of VQATrainer._compute_loss (nsvqa/train/trainer.py:181-262) and its derivative w.r.t. lp.
  * kind 0 BINARY: BCE(exp(lp), target) summed; 1 QUERY: sum_q slog(sum_{k in q} e^{lp_k}) - sum_k target_k lp_k
  * (seg[q]..seg[q+1] are question q's predicates); 2 STATEMENT: -sum lp.  loss_out[0] += scale * loss,

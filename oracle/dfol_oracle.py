@@ -85,8 +85,16 @@ def apply_modulations(log_attention, m):
 
 # ------------------------------------------------------------------ scene (featurizer + visual oracle)
 
-def scene_tables(params, features, batch_index, relation_index):
+DROP_FEATURES, DROP_ATTR_IN, DROP_ATTR_HIDDEN, DROP_REL_IN, DROP_REL_HIDDEN, DROP_EMB_ATTR, DROP_EMB_REL = range(7)
+
+
+def scene_tables(params, features, batch_index, relation_index, masks=None):
     """Per-image attribute and relation log-likelihood tables.
+
+    ``masks`` (training-mode dropout, nn.Dropout in front of every Linear: regular_mlp.py:29-32, embedding_layer.py:73):
+    None, or {site: (rows, cols) tensor of 0 / 1/(1-p) scale factors}; pair-level sites hold n_b^2 rows per image in
+    (image, subject, object) order, self pairs included.  The reference draws its masks from torch's RNG; parity runs
+    feed both sides the masks the CUDA path generates.
 
     featurize_scene: nsvqa/data/batch_gqa_boxfeatures_pipeline.py:199-281 (featurizer = Linear+Sigmoid,
     gqa_interpreter_experiments.py:28-33 with an empty hidden list); tables: ClassifierOracle.
@@ -94,22 +102,33 @@ def scene_tables(params, features, batch_index, relation_index):
     Returns lists over images: attr[b] (N_b, C), rel[b] (N_b, N_b, nR) with rel[b][s, s, :] = -30.
     """
     x = features
-    f = torch.sigmoid(F.linear(x[:, :-6], params[P_FEAT_W], params[P_FEAT_B]))
+    m = masks or {}
+
+    def drop(t, site, rows=None):
+        if site not in m:
+            return t
+        k = m[site].to(t.dtype)
+        return t * (k if rows is None else k[rows])
+
+    f = torch.sigmoid(F.linear(drop(x[:, :-6], DROP_FEATURES), params[P_FEAT_W], params[P_FEAT_B]))
     size = torch.stack([x[:, -6], x[:, -5], x[:, -6], x[:, -5]], dim=1).clamp(min=1)
     pos = x[:, -4:] / size
     obj = torch.cat([f, pos], dim=1)
 
-    def head(h, w1, b1, w2, b2):
-        h = F.elu(F.linear(h, params[w1], params[b1]))
-        return torch.sigmoid(F.linear(h, params[w2], params[b2]))
+    def head(h, w1, b1, w2, b2, sites, rows=None):
+        h = F.elu(F.linear(drop(h, sites[0], rows), params[w1], params[b1]))
+        h = torch.sigmoid(F.linear(drop(h, sites[1], rows), params[w2], params[b2]))
+        return drop(h, sites[2], rows)
 
-    attr_all = F.logsigmoid(F.linear(head(obj, P_ATTR_W1, P_ATTR_B1, P_ATTR_W2, P_ATTR_B2), params[P_EMB_W],
+    attr_all = F.logsigmoid(F.linear(head(obj, P_ATTR_W1, P_ATTR_B1, P_ATTR_W2, P_ATTR_B2,
+                                          (DROP_ATTR_IN, DROP_ATTR_HIDDEN, DROP_EMB_ATTR)), params[P_EMB_W],
                                      params[P_EMB_B]))
     rel_w = params[P_EMB_W][relation_index]
     rel_b = params[P_EMB_B][relation_index]
 
     image_num = int(batch_index.max().item()) + 1
     attr, rel = [], []
+    pair_start = 0
     for b in range(image_num):
         rows = (batch_index == b).nonzero().flatten()
         n = rows.numel()
@@ -127,7 +146,10 @@ def scene_tables(params, features, batch_index, relation_index):
         ang = torch.asin(dy / dist.clamp(min=1e-10))
         pair = torch.cat([o[s_idx], o[o_idx], dist[:, None], ang[:, None], (x2 - x1).sign()[:, None],
                           (y2 - y1).sign()[:, None]], dim=1)
-        ll = F.logsigmoid(F.linear(head(pair, P_REL_W1, P_REL_B1, P_REL_W2, P_REL_B2), rel_w, rel_b))
+        pair_rows = slice(pair_start, pair_start + n * n)
+        pair_start += n * n
+        ll = F.logsigmoid(F.linear(head(pair, P_REL_W1, P_REL_B1, P_REL_W2, P_REL_B2,
+                                        (DROP_REL_IN, DROP_REL_HIDDEN, DROP_EMB_REL), pair_rows), rel_w, rel_b))
         ll = torch.where(off[:, None], ll, torch.full_like(ll, DEFAULT_LL))
         rel.append(ll.view(n, n, -1))
     return attr, rel
@@ -280,14 +302,14 @@ class OracleInterpreter(object):
 
     # ---- the program loop
 
-    def run(self, program_batch, is_training=True, tables=None, modulations=None):
+    def run(self, program_batch, is_training=True, tables=None, modulations=None, masks=None):
         """modulations: None, or {(slot index, sub-operator key): (rows, 4) tensor} of attention-transfer modulations
         (keys 'select' / 'filter' / 'relate' / 'filter0' / 'filter1'; rows = questions, or flattened options)."""
         pb = program_batch
         mods = modulations or {}
         feats = pb._object_features
         bidx = pb._object_batch_index.to(torch.int64)
-        attr, rel = tables if tables is not None else scene_tables(self.params, feats, bidx, self.rel_index)
+        attr, rel = tables if tables is not None else scene_tables(self.params, feats, bidx, self.rel_index, masks)
         B = len(attr)
         give_answer = not is_training
         trace = []  # per slot: (attentions, names)

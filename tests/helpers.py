@@ -98,12 +98,12 @@ def model_config(dims, dropout=0.0):
 
 
 def build_interpreter(ont, dims, state=None, device='cuda', gemm_mode='fp32', seed=0, emb_bias=None,
-                      attention_nets=None, freeze_oracle=False):
+                      attention_nets=None, freeze_oracle=False, dropout=0.0):
     """FastGQAInterpreter over freshly initialised (or fixture) oracle networks."""
     from dfol_vqa_b200.interpreter import FastBoxFeaturizer, FastClassifierOracle, FastGQAInterpreter
     from dfol_vqa_b200.networks import build_networks
     torch.manual_seed(seed)
-    nets = build_networks(model_config(dims), ont)
+    nets = build_networks(model_config(dims, dropout), ont)
     if emb_bias is not None:
         # a trained-like operating point: concept probabilities near 0 for most objects, so that the exists-
         # quantifier over ~50 objects does not saturate at p = 1 (random-init logits are ~N(0, 3^2); SURVEY.md App. A)

@@ -1,0 +1,177 @@
+"""Training-mode dropout of the (frozen) oracle networks -- the arrangement of the reference's sample_config.yaml
+(dropout 0.1, all four oracle networks frozen, attention networks training).  The reference's torch RNG stream cannot
+be matched, so parity is: the CUDA path exports the masks it uses (a pure function of seed / site / row / column) and
+the CPU oracle applies the very same masks in front of every Linear.  Needs a GPU."""
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import dfol_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def export_mask(rows, cols, seed, site, p, dtype=torch.float32):
+    from dfol_vqa_b200.capi import call, ptr, stream_ptr
+    m = torch.ones(rows, cols, device='cuda', dtype=dtype)
+    call('dfol_dropout_scale', ptr(m), cols, rows, cols, int(dtype == torch.bfloat16), seed, site, p,
+         stream_ptr(m.device))
+    return m
+
+
+def oracle_masks(interp, counts, seed, p):
+    w = interp._weights
+    F, D = w.feat.weight.shape
+    ldo, Ha, H, E = F + 4, w.attr[0].weight.shape[0], w.rel[0].weight.shape[0], w.emb.weight.shape[1]
+    T, P = sum(counts), sum(c * c for c in counts)
+    shapes = {orc.DROP_FEATURES: (T, D), orc.DROP_ATTR_IN: (T, ldo), orc.DROP_ATTR_HIDDEN: (T, Ha),
+              orc.DROP_REL_IN: (P, 2 * ldo + 4), orc.DROP_REL_HIDDEN: (P, H), orc.DROP_EMB_ATTR: (T, E),
+              orc.DROP_EMB_REL: (P, E)}
+    return {site: export_mask(r, c, seed, site, p).cpu() for site, (r, c) in shapes.items()}
+
+
+@pytest.mark.parametrize('p', [0.1, 0.5])
+def test_mask_statistics_and_determinism(p):
+    rows, cols = 4096, 523
+    a = export_mask(rows, cols, 1234, 3, p)
+    vals = torch.unique(a)
+    assert vals.numel() == 2 and float(vals[0]) == 0.0 and abs(float(vals[1]) - 1.0 / (1.0 - p)) < 1e-6
+    keep = float((a > 0).float().mean())
+    sigma = (p * (1 - p) / (rows * cols)) ** 0.5
+    assert abs(keep - (1.0 - p)) < 5 * sigma + 2e-5, keep      # 16-bit threshold: |p_eff - p| <= 8e-6
+    assert torch.equal(a, export_mask(rows, cols, 1234, 3, p))
+    assert not torch.equal(a, export_mask(rows, cols, 1235, 3, p))
+    assert not torch.equal(a, export_mask(rows, cols, 1234, 4, p))
+    # no visible correlation between neighbouring columns / rows
+    k = (a > 0).float() - (1.0 - p)
+    assert abs(float((k[:, 1:] * k[:, :-1]).mean())) < 5 * p * (1 - p) / (rows * cols) ** 0.5
+    assert abs(float((k[1:] * k[:-1]).mean())) < 5 * p * (1 - p) / (rows * cols) ** 0.5
+    # the bf16 variant takes the same decisions
+    b = export_mask(rows, cols, 1234, 3, p, torch.bfloat16)
+    assert torch.equal(b > 0, a > 0)
+
+
+def test_pair_features_dropout_matches_torch():
+    from dfol_vqa_b200.capi import call, ptr, stream_ptr
+    from dfol_vqa_b200.engine import SceneLayout
+    counts = [5, 9, 3, 7]
+    width, F = 36, 32
+    T, P = sum(counts), sum(c * c for c in counts)
+    torch.manual_seed(0)
+    obj = torch.rand(T, width, device='cuda')
+    layout = SceneLayout.get(counts, 10, 4, torch.device('cuda', 0))
+    cols = 2 * width + 4
+    out = torch.full((P, cols + 4), float('nan'), device='cuda')
+    call('dfol_pair_features_dropout', ptr(obj), width, width, F, ptr(out), cols + 4, cols + 4, 0,
+         ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_n), ptr(layout.pair_img), P, 77, 3, 0.3,
+         stream_ptr(obj.device))
+    mask = export_mask(P, cols, 77, 3, 0.3)
+    rows, start = [], 0
+    for n in counts:
+        o = obj[start:start + n]
+        s_idx, o_idx = torch.arange(n).repeat_interleave(n), torch.arange(n).repeat(n)
+        p1, p2 = o[s_idx, F:], o[o_idx, F:]
+        dy = p1[:, 1] + p1[:, 3] / 2 - p2[:, 1] - p2[:, 3] / 2
+        dist = torch.sqrt((p1[:, 0] + p1[:, 2] / 2 - p2[:, 0] - p2[:, 2] / 2) ** 2 + dy ** 2)
+        ang = torch.asin(dy / dist.clamp(min=1e-10))
+        rows.append(torch.cat([o[s_idx], o[o_idx], dist[:, None], ang[:, None], (p2[:, 0] - p1[:, 0]).sign()[:, None],
+                               (p2[:, 1] - p1[:, 1]).sign()[:, None]], dim=1))
+        start += n
+    ref = torch.cat(rows) * mask
+    off = torch.cat([(torch.arange(n * n) // n != torch.arange(n * n) % n) for n in counts]).cuda()
+    assert torch.allclose(out[off][:, :cols], ref[off], rtol=1e-6, atol=1e-6)
+    assert bool((out[:, cols:] == 0).all())
+
+
+@pytest.mark.parametrize('name', ['verify_rel', 'query_attr', 'choose_rel', 'and'])
+def test_dropout_forward_and_attention_gradients_match_oracle(name):
+    """fp32 mode, frozen oracle + calibrator (sample_config.yaml's arrangement) with dropout 0.25: log-probabilities and
+    the attention networks' gradients against the oracle fed with the exported masks."""
+    from dfol_vqa_b200.compiler import ProgramCompiler
+    from dfol_vqa_b200.modulator import AttentionTransfer
+    path = [f for f in helpers.golden_mod_files() if name in f][0]
+    case = helpers.load_golden(path)
+    ont = helpers.ontology_of(case)
+    p, seed = 0.25, 4242
+    nets = helpers.attention_networks_of(case)
+    interp = helpers.build_interpreter(ont, case['dims'], case['state'], attention_nets=nets, freeze_oracle=True,
+                                       dropout=p)
+    interp._fixed_dropout_seed = seed
+    host = helpers.program_batches_of(case)
+    pbs = helpers.to_cuda(host)
+    answers = [a for pb in pbs for a in pb._answers]
+    interp.train()
+    result = interp(pbs, True)
+    lp = result['log_probability']
+    loss = orc.compute_loss([{'log_probability': lp, 'type': result['type'], 'options': result['options']}],
+                            [answers]) / len(answers)
+    loss.backward()
+
+    # oracle with the same masks (and the same modulator network on the CPU)
+    masks = oracle_masks(interp, case['counts'], seed, p)
+    cpu_nets = helpers.attention_networks_of(case)
+    at = AttentionTransfer(cpu_nets[0], cpu_nets[1], cpu_nets[2], ont)
+    cp = ProgramCompiler(ont, normalize=True, modulated=True).compile(host[0], case['counts'])
+    rows = at.modulations(cp)
+    mods = {(s, k): rows[b:b + r] for s, k, r, b in cp.mod_plan}
+    params = {k: v.clone() for k, v in case['state'].items()}
+    ref = orc.OracleInterpreter(ont, params).run(host[0], True, modulations=mods, masks=masks)
+    ref_lp = ref['log_probability']
+    mine = lp.detach().cpu()
+    if ref['type'] == 1 and case['terminal'] != 'compare':
+        perm, start = [], 0
+        for a, b in zip(result['options'], ref['options']):
+            perm += [start + b.index(x) for x in a]
+            start += len(b)
+        ref_lp = ref_lp[perm]
+    sat = (mine.exp() - ref_lp.detach().exp()).abs() <= 5e-7
+    assert bool((((mine - ref_lp.detach()).abs() <= 3e-5 * ref_lp.detach().abs() + 3e-6) | sat).all()), (mine, ref_lp)
+    # ... and it really is a dropout run
+    interp.eval()
+    with torch.no_grad():
+        clean = interp(pbs, True)['log_probability'].cpu()
+    assert not torch.allclose(clean, mine, rtol=1e-3, atol=1e-4)
+    ref_loss = orc.compute_loss([ref], [answers]) / len(answers)
+    ref_loss.backward()
+    for net, cnet in zip(nets, cpu_nets):
+        for (pn, pp), (_, cpar) in zip(net.named_parameters(), cnet.named_parameters()):
+            g = cpar.grad if cpar.grad is not None else torch.zeros_like(cpar)
+            mine_g = pp.grad.cpu() if pp.grad is not None else torch.zeros_like(g)
+            assert (mine_g - g).abs().max() <= 2e-4 * g.abs().max() + 2e-7, (pn, float((mine_g - g).abs().max()))
+
+
+def test_dropout_bf16_mode_uses_the_same_masks():
+    """Tensor-core mode at the reference's real dimensions: the dropout run of the bf16 engine (masked pair matrix ->
+    tcgen05 GEMM) against the fp32 engine with the same seed; answer logits within the bf16-mode bar."""
+    from test_gpu_tc_kernels import _programs_world
+    ont, dims, pbs = _programs_world('verify_rel', 10, 20, True, seed=71)
+    out = {}
+    for mode in ('fp32', 'bf16'):
+        interp = helpers.build_interpreter(ont, dims, seed=5, gemm_mode=mode, emb_bias=-4.0, freeze_oracle=True,
+                                           dropout=0.1)
+        interp._fixed_dropout_seed = 99
+        interp.train()
+        with torch.no_grad():
+            out[mode] = interp([pbs[0].to_cuda(0)], True)['log_probability'].cpu()
+            if mode == 'fp32':
+                interp._fixed_dropout_seed = 100
+                other = interp([pbs[0].to_cuda(0)], True)['log_probability'].cpu()
+    a, b = out['bf16'], out['fp32']
+    sat = (a.exp() - b.exp()).abs() <= 1e-6
+    assert bool((((a - b).abs() <= 2e-2 * b.abs() + 2e-2) | sat).all()), (a, b)
+    assert not torch.allclose(other, b, rtol=1e-3, atol=1e-3)   # a different seed gives a different draw
+
+
+def test_dropout_with_trainable_oracle_raises():
+    case = helpers.load_golden(helpers.golden_files()[0])
+    ont = helpers.ontology_of(case)
+    interp = helpers.build_interpreter(ont, case['dims'], case['state'], dropout=0.1)
+    pbs = helpers.to_cuda(helpers.program_batches_of(case))
+    interp.train()
+    with pytest.raises(NotImplementedError):
+        interp(pbs, True)
+    interp.eval()          # eval mode: nn.Dropout is the identity, nothing to refuse
+    with torch.no_grad():
+        interp(pbs, False)

@@ -169,3 +169,29 @@ def test_cuda_matches_oracle_at_reference_dims(terminal, batch, n_max, ragged):
         err = (step.grads[id(p)].cpu().double() - g32[k].double()).abs().max()
         noise = (g32[k].double() - g64[k]).abs().max()
         assert err <= 1e-5 * scale + 4 * noise + 1e-9, (k, float(err), float(scale), float(noise))
+
+
+@pytest.mark.parametrize('terminal', ['exist', 'and', 'query_attr', 'verify_rel'])
+def test_return_trace_matches_oracle(terminal):
+    """return_trace=True (what VQATrainer._visualize_batch consumes, trainer.py:548-591): the per-slot log-attention
+    rebuilt from the attention tape against the oracle's per-image trace."""
+    path = [p for p in helpers.golden_files() if ('golden_%s_s1' % terminal) in p][0]
+    case = helpers.load_golden(path)
+    ont = helpers.ontology_of(case)
+    interp = helpers.build_interpreter(ont, case['dims'], case['state'])
+    host = helpers.program_batches_of(case)
+    pbs = helpers.to_cuda(host)
+    interp.eval()
+    with torch.no_grad():
+        result, traces = interp(pbs, False, return_trace=True)
+    params = {k: v.clone() for k, v in case['state'].items()}
+    ref = orc.OracleInterpreter(ont, params).run(host[0], is_training=False)
+    starts = np.concatenate([[0], np.cumsum(case['counts'])])
+    slots = [t for t in ref['trace'] if t is not None]
+    assert len(traces) == 1 and len(traces[0]) == len(slots) >= 1
+    for entry, (atts, names) in zip(traces[0], slots):
+        assert entry._log_attention.shape == (len(case['counts']), int(starts[-1]))
+        assert list(entry._name) == list(names)
+        for q, a in enumerate(atts):
+            mine = entry._log_attention[q, starts[q]:starts[q + 1]].cpu()
+            assert torch.allclose(mine, a, rtol=1e-5, atol=1e-5), (q, mine, a)
