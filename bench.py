@@ -58,7 +58,20 @@ def build_world(args, rank, device):
     ont = synthetic_ontology(seed=1, embedding_dim=DIMS['emb'], **VOCAB)
     interp = None
     if device is not None:
-        interp = helpers.build_interpreter(ont, DIMS, seed=0, device=device, gemm_mode=args.gemm, emb_bias=EMB_BIAS)
+        extra = {}
+        if args.calibrate:
+            # sample_config.yaml's arrangement: the four oracle networks frozen, dropout 0.1, the attention-transfer
+            # calibrator (two LSTMCells + output layer, state 50) training
+            from dfol_vqa_b200.networks import build_attention_networks
+            nets = build_attention_networks(DIMS['emb'], 50)
+            torch.manual_seed(3)
+            with torch.no_grad():  # away from the identity initialisation, as after some training
+                nets['attention_output_network'][0].weight.normal_(0.0, 0.05)
+            extra = dict(attention_nets=[nets[k] for k in ('forward_attention_network', 'backward_attention_network',
+                                                           'attention_output_network')],
+                         freeze_oracle=True, dropout=args.dropout)
+        interp = helpers.build_interpreter(ont, DIMS, seed=0, device=device, gemm_mode=args.gemm, emb_bias=EMB_BIAS,
+                                           **extra)
     B = args.local_batch or wl['batch']
     batches = []
     for i in range(args.pool):
@@ -224,6 +237,10 @@ def main():
     ap.add_argument('--pool', type=int, default=5, help='distinct pre-collated batches cycled through the steps')
     ap.add_argument('--cpu-sample', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--calibrate', action='store_true',
+                    help="sample_config.yaml's training arrangement: frozen oracle networks with dropout, the "
+                         'attention-transfer calibrator trains (not the default headline workload)')
+    ap.add_argument('--dropout', type=float, default=0.1)
     args = ap.parse_args()
     if args.gemm is None:
         args.gemm = 'bf16'  # tensor-core mode (bf16 operands, fp32 accumulation); --gemm fp32 = parity mode
@@ -379,7 +396,9 @@ def main():
         'metric': 'questions/sec', 'value': value, 'unit': 'questions/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32' if args.gemm == 'fp32' else 'bf16', 'data': 'synthetic',
-        'config': {'workload': '%s: %s' % (args.workload, wl['desc']), 'step': args.mode, 'gemm_mode': args.gemm,
+        'config': {'workload': '%s: %s' % (args.workload, wl['desc']),
+                   'step': args.mode + (' (calibrator only: frozen oracle, dropout %.2f)' % args.dropout
+                                        if args.calibrate else ''), 'gemm_mode': args.gemm,
                    'global_batch': global_q, 'objects_per_image': wl['n'], 'box_feature_dim': DIMS['box'],
                    'concepts': C, 'relations': nR, 'parallelism': 'dp%d (questions sharded by rank)' % world,
                    'l2': 'inputs larger than L2: per-step tables + activations %.1f GB >> 126 MB; %d distinct '

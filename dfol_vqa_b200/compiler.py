@@ -56,7 +56,7 @@ class CompiledPrograms(object):
     __slots__ = ('instr', 'q_instr', 'opts', 'lp_num', 'kind', 'options', 'seg', 'names', 'question_num',
                  'g_attr_size', 'g_rel_size', 'attr_slices', 'rel_slices', 'terminal', 'lp_owner', 'device_cache',
                  'alg_bytes', 'slot_wrow', 'img_slot', 'slot_blk', 'rel_slot_size', 'max_slots', 'mod_plan',
-                 'mod_descs', 'mod_rows', 'slot_after', 'slot_names')
+                 'mod_descs', 'mod_rows', 'slot_after', 'slot_names', 'mod_cache')
 
 
 class ProgramCompiler(object):
@@ -438,6 +438,7 @@ class ProgramCompiler(object):
         cp.device_cache = None
         cp.slot_after = np.asarray(slot_after, dtype=np.int64).reshape(len(slot_after), B)
         cp.slot_names = slot_names
+        cp.mod_cache = {}
         cp.mod_plan = mod_plan
         cp.mod_descs = mod_descs
         cp.mod_rows = mod_rows[0]

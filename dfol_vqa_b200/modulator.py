@@ -32,9 +32,10 @@ def _strip_negation(tok):
 
 
 def _gate(x, y, g):
-    """BatchAttentionState.gate: x where g == 1, y where g == 0 (rows)."""
-    g = g.unsqueeze(1)
-    return (x[0] * g + y[0] * (1.0 - g), x[1] * g + y[1] * (1.0 - g))
+    """BatchAttentionState.gate (x * g + y * (1 - g) rowwise, batch_base_types.py:283-290) for flags in {0, 1}: x where
+    g == 1, y where g == 0 -- one select per tensor instead of four arithmetic launches."""
+    keep = (g > 0).unsqueeze(1)
+    return (torch.where(keep, x[0], y[0]), torch.where(keep, x[1], y[1]))
 
 
 class AttentionTransfer(object):
@@ -56,7 +57,28 @@ class AttentionTransfer(object):
             hit = self._emb[tok] = np.asarray(self.ont.get_embeddings([tok]), dtype=np.float32)[0]
         return hit
 
+    def _cached(self, key, build):
+        """Program-only tensors (feature matrices, row owners, masks, subject flags) are built once per compiled batch
+        and device and kept on the CompiledPrograms object (collate-time products, like the bytecode)."""
+        hit = self._cache.get(key)
+        if hit is None:
+            hit = self._cache[key] = build()
+        return hit
+
     def _features(self, op_name, tokens, rel_flag, ref):
+        key = ('feat', op_name, rel_flag, id(tokens), str(ref.device), ref.dtype)
+        return self._cached(key, lambda: self._build_features(op_name, tokens, rel_flag, ref))
+
+    def _index(self, owner, ref):
+        if owner is None:
+            return None
+        return self._cached(('own', id(owner), str(ref.device)), lambda: torch.as_tensor(owner, device=ref.device))
+
+    def _vector(self, values, ref):
+        return self._cached(('vec', id(values), str(ref.device), ref.dtype),
+                            lambda: torch.tensor(values, device=ref.device, dtype=ref.dtype))
+
+    def _build_features(self, op_name, tokens, rel_flag, ref):
         f = np.zeros((len(tokens), self.fwd.input_size), dtype=np.float32)
         col = OPS_INDEX[op_name]
         for r, t in enumerate(tokens):
@@ -97,32 +119,30 @@ class AttentionTransfer(object):
         B = self._B
         if rel is None:
             raise NotImplementedError('relate slot without any relation predicate')
-        tokens, owner, is_subject = rel
-        subj_q = torch.tensor(is_subject, device=ref.device, dtype=ref.dtype)
-        own = None if owner is None else torch.as_tensor(owner, device=ref.device)
-        subj_p = subj_q if own is None else subj_q[own]
+        tokens, owner, _is_subject = rel   # the subject flags cancel out of both passes (see below)
+        own = self._index(owner, ref)
         if is_forward:
             x = self._zeros(ref, B)
             if sel is not None:
                 x = self._filter((i, 'select'), True, x, d['op'], sel, None, mods, store)
-            s_set, o_set = _gate(x, state, subj_q), _gate(state, x, subj_q)
+            # subject set = x where is_subject else the incoming state, object set the other way round (:376-377): the
+            # LSTM sees their SUM, which is x + state whatever the flag
+            agg = (x[0] + state[0], x[1] + state[1])
             if own is not None:
-                s_set, o_set = (s_set[0][own], s_set[1][own]), (o_set[0][own], o_set[1][own])
+                agg = (agg[0][own], agg[1][own])
             feats = self._features(d['op'], tokens, 1.0, ref)
-            new = self.fwd(feats, (s_set[0] + o_set[0], s_set[1] + o_set[1]))
+            new = self.fwd(feats, agg)
             store[(i, 'relate')] = new
             return new  # subject and object states are the same tensor values; the gate of the two is the identity
-        zero = (torch.zeros_like(state[0]), torch.zeros_like(state[1]))
-        o_set, s_set = _gate(zero, state, subj_p), _gate(state, zero, subj_p)
+        # backward pass (:383-390): subject set = the incoming state where is_subject else zero, object set the other way
+        # round.  The execution pass keeps the subject posterior where is_subject and the object posterior elsewhere
+        # (batch_gqa_ops.py:371 / :254-257), i.e. exactly the role whose backward state is the incoming state: the
+        # modulation row that is used is out([forward h | incoming h]) for every flag, and the LSTM sees the sum of the
+        # two sets, which is the incoming state.
         fwd_state = store.pop((i, 'relate'))
-        # the kept role's modulation (subject rows where is_subject, object rows elsewhere: the row that is used by
-        # the execution pass, batch_gqa_ops.py:371 / :254-257)
-        m_subj = self._modulation(fwd_state, s_set)
-        m_obj = self._modulation(fwd_state, o_set)
-        g = subj_p.unsqueeze(1)
-        mods[(i, 'relate')] = m_subj * g + m_obj * (1.0 - g)
+        mods[(i, 'relate')] = self._modulation(fwd_state, state)
         feats = self._features(d['op'], tokens, 1.0, ref)
-        new = self.bwd(feats, (s_set[0] + o_set[0], s_set[1] + o_set[1]))
+        new = self.bwd(feats, state)
         if own is not None:
             new = tuple(torch.zeros(B, v.shape[1], device=v.device, dtype=v.dtype).index_add_(0, own, v) for v in new)
         if sel is not None:
@@ -149,13 +169,13 @@ class AttentionTransfer(object):
         if d.get('two'):
             if fil is None:
                 return (inputs[0], inputs[1])
-            own = None if fil[1] is None else torch.as_tensor(fil[1], device=ref.device)
+            own = self._index(fil[1], ref)
             x1 = self._filter((i, 'filter0'), is_forward, inputs[0], op, fil[0], own, mods, store)
             x2 = self._filter((i, 'filter1'), is_forward, inputs[1], op, fil[0], own, mods, store)
             return (x1, x2)
         if fil is None:
             return inputs[0]
-        own = None if fil[1] is None else torch.as_tensor(fil[1], device=ref.device)
+        own = self._index(fil[1], ref)
         return self._filter((i, 'filter'), is_forward, inputs[0], op, fil[0], own, mods, store)
 
     # ---- the two passes
@@ -166,10 +186,11 @@ class AttentionTransfer(object):
         n = len(descs)
         ref = self.fwd.weight_ih
         self._B = cp.question_num
+        self._cache = cp.mod_cache
         mods, store = {}, {}
 
         def mask_of(d):
-            return None if d['mask'] is None else torch.tensor(d['mask'], device=ref.device, dtype=ref.dtype)
+            return None if d['mask'] is None else self._vector(d['mask'], ref)
 
         trace = []
         for i, d in enumerate(descs):
