@@ -24,7 +24,7 @@ from . import capi
 from .capi import K, call, ptr
 from .compiler import BINARY, QUERY, STATEMENT, ProgramCompiler
 from .engine import OracleWeights, ReasoningEngine, SceneLayout
-from .modulator import AttentionTransfer
+from .modulator_cuda import NativeAttentionTransfer
 from .networks import dropout_p, linear_layers
 from .parallel import FlatBucket
 
@@ -54,39 +54,47 @@ class FastClassifierOracle(nn.Module):
 
 
 class _ReasoningFunction(torch.autograd.Function):
-    """features + oracle parameters (+ attention-transfer modulations) -> log-probabilities of one program batch."""
+    """features + oracle parameters (+ attention-network parameters) -> log-probabilities of one program batch."""
 
     @staticmethod
-    def forward(ctx, engine, cp, layout, features, need_grad, mods, sink, dropout, *params):
-        oracle_grad = need_grad and any(p.requires_grad for p in params)
+    def forward(ctx, engine, cp, layout, features, need_grad, attention, sink, dropout, n_oracle, *params):
+        oracle_params = params[:n_oracle]
+        oracle_grad = need_grad and any(p.requires_grad for p in oracle_params)
         scene = engine.build_scene(features, layout, keep_for_backward=oracle_grad, cp=cp, dropout=dropout)
-        if mods is not None:
-            scene.mods = mods.detach().float().contiguous()
+        mod_ctx = None
+        if attention is not None:
+            # token-side LSTM passes of the calibrator (libdfol_b200 kernels, modulator_cuda.py) -> one row of
+            # (alpha, beta, c, d) per predicate, consumed by the interpreter kernels
+            scene.mods, mod_ctx = attention.forward(cp)
         lp, tape = engine.run_programs(cp, scene, save_tape=need_grad or sink is not None)
         if sink is not None:
             sink['tape'] = tape
         ctx.engine, ctx.cp, ctx.scene, ctx.tape, ctx.params = engine, cp, scene, tape, params
-        ctx.oracle_grad, ctx.mod_dtype = oracle_grad, (None if mods is None else mods.dtype)
+        ctx.oracle_grad, ctx.n_oracle, ctx.attention, ctx.mod_ctx = oracle_grad, n_oracle, attention, mod_ctx
         return lp
 
     @staticmethod
     def backward(ctx, d_lp):
-        params, scene = ctx.params, ctx.scene
+        params, scene, n_oracle = ctx.params, ctx.scene, ctx.n_oracle
         d_lp = d_lp.contiguous().float()
-        if ctx.mod_dtype is not None:
+        if ctx.mod_ctx is not None:
             scene.d_mods = torch.zeros_like(scene.mods)
+        grads = {id(p): torch.zeros_like(p, dtype=torch.float32)
+                 for k, p in enumerate(params) if (ctx.oracle_grad if k < n_oracle else ctx.mod_ctx is not None)}
         if ctx.oracle_grad:
-            grads = {id(p): torch.zeros_like(p, dtype=torch.float32) for p in params}
             ctx.engine.backward(ctx.cp, scene, ctx.tape, d_lp, grads)
         else:
             # frozen oracle (sample_config.yaml: only the attention networks train): the backward interpreter alone
             # yields d loss / d modulations; the scene's backward pass is skipped
-            grads = {}
             ctx.engine.program_backward(ctx.cp, scene, ctx.tape, d_lp)
-        d_mods = None if ctx.mod_dtype is None else scene.d_mods.to(ctx.mod_dtype)
-        ctx.scene = ctx.tape = None
-        return (None, None, None, None, None, d_mods, None, None) + tuple(
-            grads[id(p)] if (p.requires_grad and ctx.oracle_grad) else None for p in params)
+        if ctx.mod_ctx is not None and any(p.requires_grad for p in params[n_oracle:]):
+            ctx.attention.backward(ctx.mod_ctx, scene.d_mods, grads)
+        ctx.scene = ctx.tape = ctx.mod_ctx = None
+        out = []
+        for k, p in enumerate(params):
+            live = p.requires_grad and (ctx.oracle_grad if k < n_oracle else ctx.attention is not None)
+            out.append(grads[id(p)] if live else None)
+        return (None, None, None, None, None, None, None, None, None) + tuple(out)
 
 
 class _TraceEntry(object):
@@ -171,8 +179,8 @@ class FastGQAInterpreter(nn.Module):
                 'verify_rel': _Holder(_gqa_relate=rel()), 'all_same': sel(),
                 'all_different': _Holder(_gqa_all_same=sel()), 'two_same': sel(),
                 'two_different': _Holder(_gqa_two_same=sel()), 'compare': sel()})
-            self._attention = AttentionTransfer(forward_attention_network, backward_attention_network,
-                                                attention_output_network, ontology)
+            self._attention = NativeAttentionTransfer(forward_attention_network, backward_attention_network,
+                                                      attention_output_network, ontology)
 
     _dropout = 0.0
 
@@ -193,11 +201,16 @@ class FastGQAInterpreter(nn.Module):
     def attention_parameters(self):
         return [] if self._attention is None else self._attention.parameters()
 
-    def modulations(self, cp, modulator_switch=True):
-        """(cp.mod_rows, 4) autograd-attached modulations of a compiled batch, or None (no calibrator / switched off)."""
+    def modulator(self, cp, modulator_switch=True):
+        """The calibrator to run for a compiled batch, or None (no calibrator / switched off / nothing to modulate)."""
         if self._attention is None or not modulator_switch or cp.mod_rows == 0:
             return None
-        return self._attention.modulations(cp)
+        return self._attention
+
+    def modulations(self, cp, modulator_switch=True):
+        """(cp.mod_rows, 4) modulations of a compiled batch (no autograd), or None."""
+        att = self.modulator(cp, modulator_switch)
+        return None if att is None else att.forward(cp)[0]
 
     # ---- helpers -----------------------------------------------------------------------------------------
 
@@ -271,9 +284,10 @@ class FastGQAInterpreter(nn.Module):
             layout = SceneLayout.get(counts, self._weights.emb.weight.shape[0], len(self._ontology._relation_index),
                                      feats.device)
             cp = self.compiled(pb, give_answer)
-            mods = self.modulations(cp, modulator_switch)
+            att = self.modulator(cp, modulator_switch)
             sink = {} if return_trace else None
-            lp = _ReasoningFunction.apply(self._engine, cp, layout, feats, need_grad, mods, sink, drop_k, *params)
+            lp = _ReasoningFunction.apply(self._engine, cp, layout, feats, need_grad, att, sink, drop_k, len(params),
+                                          *(params + (self.attention_parameters() if att is not None else [])))
             lps.append(lp)
             metas.append(cp)
             traces.append(self._trace(cp, layout, sink['tape']) if return_trace else [])
@@ -393,8 +407,9 @@ class FusedTrainStep(object):
         for p in oracle_params:
             if not p.requires_grad and self.oracle_trainable:
                 self.grads[id(p)] = torch.zeros_like(p, dtype=torch.float32)
-        for p in self.attention_params:
-            p.grad = self.bucket.grads[id(p)]  # autograd accumulates the modulator's gradients straight into the bucket
+        for p in interpreter.attention_parameters():
+            if not p.requires_grad:  # frozen attention networks: scratch buffers for the backward reductions
+                self.grads[id(p)] = torch.zeros_like(p, dtype=torch.float32)
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
         self.step_count = 0
@@ -432,9 +447,10 @@ class FusedTrainStep(object):
             cp = interp.compiled(pb, False)
             scene = self.engine.build_scene(feats, layout, keep_for_backward=self.oracle_trainable, cp=cp,
                                             dropout=drop_k)
-            mods = interp.modulations(cp)
-            if mods is not None:
-                scene.mods = mods.detach().float().contiguous()
+            att = interp.modulator(cp)
+            mod_ctx = None
+            if att is not None:
+                scene.mods, mod_ctx = att.forward(cp)
                 scene.d_mods = torch.zeros_like(scene.mods)
             lp, tape = self.engine.run_programs(cp, scene, save_tape=True)
             target = self._targets(pb, cp, dev)
@@ -446,8 +462,8 @@ class FusedTrainStep(object):
                 self.engine.backward(cp, scene, tape, d_lp, self.grads)
             else:
                 self.engine.program_backward(cp, scene, tape, d_lp)
-            if mods is not None and self.attention_params:
-                mods.backward(scene.d_mods.to(mods.dtype))
+            if mod_ctx is not None and self.attention_params:
+                att.backward(mod_ctx, scene.d_mods, self.grads)
         return self.scalars[0]
 
     def optimizer_step(self):

@@ -291,6 +291,30 @@ int dfol_pair_features_dropout(const float* obj, int64_t ldobj, int width, int p
                                const int32_t* img_n, const int32_t* pair_img, int64_t pairs, uint64_t seed, int site,
                                float p, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Attention-transfer calibrator, token side (BatchInterpreterBase.forward modulator loops, batch_base_interpreter.py:
+ * 87-140; transform_attention of FilterBatch / RelateBatch, batch_base_ops.py:407-467, :598-684; _compute_attention_
+ * modulations :275-286).  One LSTMCell evaluation over `rows` predicate rows, recurrent part only:
+ *   pre = xproj[row] + b_hh + W_hh . (h_in[src] (+ h_add[src])),  src = owner ? owner[row] : row   (gates i, f, g, o)
+ * xproj = features . W_ih^T + b_ih of ALL cells of the batch is one dfol_gemm_f32 by the caller.  mask (optional, 0/1 per
+ * row): rows with 0 output the fallback state fb.  saved: [rows][7 S] (gates, c_in, tanh(c'), total h_in) for backward.
+ * Backward writes d pre (rows x 4S), accumulates (+=) into the input / added / fallback state gradients; dW_ih, dW_hh and
+ * the bias gradients are GEMM-shaped reductions over all cell rows done by the caller.  dfol_mod_out_*: the modulation
+ * output layer sigmoid(W_out . [fh | bh] + b_out), its input kept in `cat`, and its backward (dzo = d pre-sigmoid).
+ */
+int dfol_lstm_cell_fwd(const float* xproj, int64_t ldx, const float* b_hh, const float* w_hh, int S, const float* h_in,
+                       const float* c_in, const float* h_add, const float* c_add, const int64_t* owner,
+                       const float* mask, const float* fb_h, const float* fb_c, float* h_out, float* c_out,
+                       float* saved, int rows, void* stream);
+int dfol_lstm_cell_bwd(const float* d_h_out, const float* d_c_out, const float* w_hh, int S, const float* saved,
+                       const int64_t* owner, const float* mask, float* dpre, int64_t lddp, float* d_h_in,
+                       float* d_c_in, float* d_h_add, float* d_c_add, float* d_fb_h, float* d_fb_c, int rows,
+                       void* stream);
+int dfol_mod_out_fwd(const float* fh, const float* bh, const int64_t* owner, const float* w_out, const float* b_out,
+                     int S, int n_out, float* mods, float* cat, int rows, void* stream);
+int dfol_mod_out_bwd(const float* d_mods, const float* mods, const int64_t* owner, const float* w_out, int S, int n_out,
+                     float* dzo, float* d_fh, float* d_bh, int rows, void* stream);
+
 /* Loss of VQATrainer._compute_loss (nsvqa/train/trainer.py:181-262) and its derivative w.r.t. lp.
  * kind 0 BINARY: BCE(exp(lp), target) summed; 1 QUERY: sum_q slog(sum_{k in q} e^{lp_k}) - sum_k target_k lp_k
  * (seg[q]..seg[q+1] are question q's predicates); 2 STATEMENT: -sum lp.  loss_out[0] += scale * loss,

@@ -229,6 +229,52 @@ def test_fast_interpreter_with_modulations_matches_exact(terminal, n_max, ragged
             assert float((a - b).abs().max()) <= 2e-2 * scale + 1e-6, float((a - b).abs().max()) / (scale + 1e-9)
 
 
+@pytest.mark.parametrize('terminal,n_max', [('verify_rel', 20), ('query_attr', 12), ('choose_rel', 16),
+                                            ('two_same', 10), ('compare', 14), ('and', 18)])
+def test_native_modulator_matches_torch_statement(terminal, n_max):
+    """modulator_cuda.NativeAttentionTransfer (hand-written LSTM-cell / output-layer kernels, hand-derived backward)
+    against modulator.AttentionTransfer (torch ops + autograd; held to the recorded reference runs by the CPU tests) at
+    the reference's real dimensions (318-wide features, state 50): modulation rows and all 10 parameter gradients."""
+    from test_gpu_tc_kernels import _programs_world
+    from dfol_vqa_b200.compiler import ProgramCompiler
+    from dfol_vqa_b200.modulator import AttentionTransfer
+    from dfol_vqa_b200.modulator_cuda import NativeAttentionTransfer
+    from dfol_vqa_b200.networks import build_attention_networks
+    ont, dims, pbs = _programs_world(terminal, 24, n_max, True, seed=77)
+    torch.manual_seed(11)
+    nets = build_attention_networks(dims['emb'], 50)
+    with torch.no_grad():
+        nets['attention_output_network'][0].weight.normal_(0.0, 0.3)
+    fwd, bwd, out = (nets[k].cuda() for k in ('forward_attention_network', 'backward_attention_network',
+                                              'attention_output_network'))
+    cp = ProgramCompiler(ont, normalize=True, modulated=True).compile(pbs[0], [n_max] * 24)
+    ref = AttentionTransfer(fwd, bwd, out, ont)
+    rows = ref.modulations(cp)
+    # rows of questions that do not execute a slot (mask 0) are computed by the reference but never read: the
+    # interpreter gates those questions back to their input (batch_base_interpreter.py:166-167), no instruction
+    # carries their row, their d_mods is zero.  The native pass does not reproduce them (it keeps the gated state).
+    live = torch.ones(rows.shape[0], dtype=torch.bool)
+    for slot, key, n, base in cp.mod_plan:
+        m = cp.mod_descs[slot]['mask']
+        if m is not None and n == len(m):
+            live[base:base + n] = torch.tensor(m) > 0
+    live = live.cuda()
+    assert float(live.float().mean()) < 1.0
+    w = torch.randn(rows.shape, device='cuda', generator=torch.Generator('cuda').manual_seed(5)) * live[:, None]
+    rows.backward(w)
+    params = ref.parameters()
+    ref_grads = [p.grad.clone() for p in params]
+    native = NativeAttentionTransfer(fwd, bwd, out, ont)
+    mods, ctx = native.forward(cp)
+    assert mods.shape == rows.shape
+    assert torch.allclose(mods[live], rows.detach()[live], rtol=1e-5, atol=1e-6), (mods - rows.detach()).abs().max()
+    grads = {id(p): torch.zeros_like(p) for p in params}
+    native.backward(ctx, w, grads)
+    for p, g in zip(params, ref_grads):
+        err = (grads[id(p)] - g).abs().max()
+        assert err <= 2e-4 * g.abs().max() + 1e-6, (tuple(p.shape), float(err), float(g.abs().max()))
+
+
 def test_modulated_eval_answers_match_reference_golden():
     for path in FILES:
         case = helpers.load_golden(path)

@@ -23,11 +23,16 @@ cps = [interp.compiled(pb, False) for pb in pbs]
 print('slots', [len(cp.mod_descs) for cp in cps], 'rows', [cp.mod_rows for cp in cps])
 print('full step            %.2f ms' % t(lambda i: step.step([pbs[i % 3]])))
 def fwd_only(i):
-    with torch.no_grad(): interp.modulations(cps[i % 3])
-print('modulator fwd no-grad %.2f ms' % t(fwd_only))
+    interp._attention.forward(cps[i % 3])
+print('native modulator fwd      %.2f ms' % t(fwd_only))
+grads = {id(p): torch.zeros_like(p) for p in interp.attention_parameters()}
 def fwd_bwd(i):
-    m = interp.modulations(cps[i % 3]); m.backward(torch.ones_like(m))
-print('modulator fwd+bwd     %.2f ms' % t(fwd_bwd))
+    m, c = interp._attention.forward(cps[i % 3]); interp._attention.backward(c, torch.ones_like(m), grads)
+print('native modulator fwd+bwd  %.2f ms' % t(fwd_bwd))
+tm = interp._attention._torch
+def torch_fwd_bwd(i):
+    m = tm.modulations(cps[i % 3]); m.backward(torch.ones_like(m))
+print('torch modulator fwd+bwd   %.2f ms' % t(torch_fwd_bwd))
 interp._attention = None; interp._has_modulator = False
 step2 = step
 def no_mod(i):
