@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(256) pair_features_dropout_kernel(
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int in_cols = 2 * width + 4;
+  const bool vec4 = (width % 4) == 0 && (ldobj % 4) == 0 && (reinterpret_cast<uintptr_t>(obj) & 15) == 0;
   for (long long r = warp; r < pairs; r += nwarps) {
     const int b = pair_img[r];
     const int n = img_n[b];
@@ -122,14 +123,28 @@ __global__ void __launch_bounds__(256) pair_features_dropout_kernel(
       float sc[8];
       drop_scales8(d, r, g8, sc);
       float v[8];
+      if (vec4) {
+        // width % 4 == 0 and 16-byte aligned object rows: each half of the group lies inside ONE segment
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = g8 * 8 + j;
-        float x = 0.0f;
-        if (c < width) x = os[c];
-        else if (c < 2 * width) x = oo[c - width];
-        else if (c < in_cols) x = geo[c - 2 * width];
-        v[j] = x * sc[j];
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          const int c = g8 * 8 + 4 * hlf;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < width) x = *reinterpret_cast<const float4*>(os + c);
+          else if (c < 2 * width) x = *reinterpret_cast<const float4*>(oo + (c - width));
+          else if (c < in_cols) x = make_float4(geo[0], geo[1], geo[2], geo[3]);
+          v[4 * hlf] = x.x * sc[4 * hlf]; v[4 * hlf + 1] = x.y * sc[4 * hlf + 1];
+          v[4 * hlf + 2] = x.z * sc[4 * hlf + 2]; v[4 * hlf + 3] = x.w * sc[4 * hlf + 3];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = g8 * 8 + j;
+          float x = 0.0f;
+          if (c < width) x = os[c];
+          else if (c < 2 * width) x = oo[c - width];
+          else if (c < in_cols) x = geo[c - 2 * width];
+          v[j] = x * sc[j];
+        }
       }
       T* p8 = dst + g8 * 8;
       if (sizeof(T) == 2 && g8 * 8 + 8 <= out_cols && (reinterpret_cast<uintptr_t>(p8) & 15) == 0) {

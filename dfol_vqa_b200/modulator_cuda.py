@@ -242,10 +242,23 @@ class NativeAttentionTransfer(object):
         dzo = torch.zeros(R, n_out, device=dev, dtype=torch.float32)
         w_hh = {'f': self.fwd.weight_hh, 'b': self.bwd.weight_hh}
 
+        # gradient buffers of every state on the tape: ONE zero-filled pool, sliced (instead of ~100 tiny memsets)
+        states = {}
+        for rec in ctx['tape']:
+            for obj in rec[1:]:
+                if isinstance(obj, _State) and obj.h is not None:
+                    states[id(obj)] = obj
+        total = sum(o.h.shape[0] for o in states.values())
+        pool = torch.zeros(2, max(total, 1), S, device=dev, dtype=torch.float32)
+        off = 0
+        for o in states.values():
+            n = o.h.shape[0]
+            o.dh, o.dc = pool[0, off:off + n], pool[1, off:off + n]
+            off += n
+        touched = set()
+
         def need(state, rows):
-            if state.dh is None:
-                state.dh = torch.zeros(rows, S, device=dev, dtype=torch.float32)
-                state.dc = torch.zeros(rows, S, device=dev, dtype=torch.float32)
+            touched.add(id(state))
             return state
 
         for rec in reversed(ctx['tape']):
@@ -260,7 +273,7 @@ class NativeAttentionTransfer(object):
                      ptr(dzo[base:]), ptr(fstate.dh), ptr(bstate.dh if has_b else None), rows, st)
             elif kind == 'cell':
                 _, net, base, rows, state, add, owner, mask, fb, out = rec
-                if out.dh is None:
+                if id(out) not in touched:
                     continue  # nothing downstream depends on this cell
                 has_in = state.h is not None
                 if has_in:
@@ -276,14 +289,14 @@ class NativeAttentionTransfer(object):
                      ptr(None if fb is None else fb.dc), rows, st)
             elif kind == 'squeeze':
                 _, state, owner, out = rec
-                if out.dh is None:
+                if id(out) not in touched:
                     continue
                 need(state, state.h.shape[0])
                 state.dh += out.dh[owner]
                 state.dc += out.dc[owner]
             elif kind == 'gate':
                 _, new, old, keep, out = rec
-                if out.dh is None:
+                if id(out) not in touched:
                     continue
                 need(new, new.h.shape[0])
                 need(old, old.h.shape[0])
@@ -303,5 +316,6 @@ class NativeAttentionTransfer(object):
             gemm_f32(dp.t(), saved[net][:, 6 * S:7 * S], G(mod.weight_hh), accumulate=(sk == 1), split_k=sk, stream=st)
             call('dfol_colsum', ptr(dp), dp.stride(0), R, 4 * S, ptr(G(mod.bias_ih)), st)
             call('dfol_colsum', ptr(dp), dp.stride(0), R, 4 * S, ptr(G(mod.bias_hh)), st)
-        gemm_f32(dzo.t(), cat, G(self.lin.weight), accumulate=True, stream=st)
+        sk = max(1, min(16, R // 512))
+        gemm_f32(dzo.t(), cat, G(self.lin.weight), accumulate=(sk == 1), split_k=sk, stream=st)
         call('dfol_colsum', ptr(dzo), dzo.stride(0), R, n_out, ptr(G(self.lin.bias)), st)

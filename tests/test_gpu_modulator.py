@@ -275,6 +275,64 @@ def test_native_modulator_matches_torch_statement(terminal, n_max):
         assert err <= 2e-4 * g.abs().max() + 1e-6, (tuple(p.shape), float(err), float(g.abs().max()))
 
 
+def test_full_size_calibrator_question_independence_and_additivity():
+    """Size-independent properties of the calibrator arrangement at the full c1 size (B=256, N=48, real dimensions,
+    frozen oracle, randomised attention networks): a question's log-probability does not depend on which other
+    questions share its batch -- although the slot alignment, the masks and therefore every LSTM launch differ -- and
+    the attention-network gradients of the whole batch equal the accumulation over two sub-batches."""
+    import json
+    from dfol_vqa_b200 import synth
+    from dfol_vqa_b200.interpreter import FusedTrainStep
+    from dfol_vqa_b200.networks import build_attention_networks
+    from dfol_vqa_b200.ontology import synthetic_ontology
+    from dfol_vqa_b200.programs import ProgramCollater
+    dims = dict(box=2048, feat=512, hidden=256, emb=300)
+    batch, n, sub = 256, 48, 16
+    ont = synthetic_ontology(seed=1, embedding_dim=300, concept_num=2335, relation_num=333, category_num=31, class_num=53)
+    torch.manual_seed(21)
+    nets = build_attention_networks(300, 50)
+    with torch.no_grad():
+        nets['attention_output_network'][0].weight.normal_(0.0, 0.1)
+    interp = helpers.build_interpreter(ont, dims, seed=0, gemm_mode='bf16', emb_bias=-4.0, freeze_oracle=True,
+                                       attention_nets=[nets[k] for k in ('forward_attention_network',
+                                                                         'backward_attention_network',
+                                                                         'attention_output_network')])
+    questions = synth.make_questions(ont, batch, 'verify_rel', 1, 3, seed=15, relate_prob=0.35)
+    feats, bidx = synth.make_object_features([n] * batch, 2048, seed=16)
+    full = ProgramCollater(1, lambda qs: (feats, bidx)).collate(json.loads(json.dumps(questions)))
+    part = ProgramCollater(1, lambda qs: (feats[:sub * n].clone(), bidx[:sub * n].clone())).collate(
+        json.loads(json.dumps(questions[:sub])))
+    halves = ProgramCollater(2, helpers.slicing_source(feats, bidx)).collate(json.loads(json.dumps(questions)))
+    interp.train()
+    with torch.no_grad():
+        lp_full = interp(helpers.to_cuda(full), True)['log_probability'].clone()
+        lp_part = interp(helpers.to_cuda(part), True)['log_probability'].clone()
+        lp_off = interp(helpers.to_cuda(full), True, modulator_switch=False)['log_probability'].clone()
+    assert bool(torch.isfinite(lp_full).all()) and not torch.allclose(lp_full, lp_off, rtol=1e-3, atol=1e-4)
+    # One batch-composition dependence is the reference's own: a blank predicate ('_' name of a relate, say) is
+    # modulated iff SOME question of the batch has a predicate in that slot (FilterBatch returns early otherwise,
+    # batch_base_ops.py:315-317).  Questions whose modulated sub-operators differ between the two batches are excluded.
+    cf, cpart = interp.compiled(helpers.to_cuda(full)[0], False), interp.compiled(helpers.to_cuda(part)[0], False)
+
+    def coverage(cp, q):
+        rows = cp.instr[cp.q_instr[q]:cp.q_instr[q + 1]]
+        return [(int(r[0]), int(r[9]) >= 0, int(r[10]) >= 0) for r in rows]
+    same = torch.tensor([coverage(cf, q) == coverage(cpart, q) for q in range(sub)], device='cuda')
+    assert int(same.sum()) >= sub - 4
+    sat = (lp_full[:sub].exp() - lp_part.exp()).abs() <= 1e-6
+    ok = ((lp_full[:sub] - lp_part).abs() <= 1e-4 * lp_part.abs() + 1e-5) | sat
+    assert bool(ok[same].all()), (lp_full[:sub] - lp_part).abs()
+    step = FusedTrainStep(interp)
+    loss_full = float(step.forward_backward(helpers.to_cuda(full), global_question_num=batch))
+    g_full = step.flat_grad.clone()
+    loss_split = float(step.forward_backward(helpers.to_cuda(halves), global_question_num=batch))
+    g_split = step.flat_grad.clone()
+    assert abs(loss_full - loss_split) <= 1e-4 * max(1.0, abs(loss_full))
+    scale = float(g_full.abs().max())
+    assert scale > 0 and bool(torch.isfinite(g_full).all())
+    assert float((g_full - g_split).abs().max()) <= 2e-3 * scale, float((g_full - g_split).abs().max()) / scale
+
+
 def test_modulated_eval_answers_match_reference_golden():
     for path in FILES:
         case = helpers.load_golden(path)
