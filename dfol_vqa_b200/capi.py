@@ -75,6 +75,7 @@ _SIGNATURES = {
     'dfol_mod_out_fwd': (c_int, [P, P, P, P, P, c_int, c_int, P, P, c_int, P]),
     'dfol_mod_out_bwd': (c_int, [P, P, P, P, c_int, c_int, P, P, P, c_int, P]),
     'dfol_dropout_scale': (c_int, [P, c_int64, c_int64, c_int, c_int, c_uint64, c_int, c_float, P]),
+    'dfol_pair_features_bwd': (c_int, [P, c_int64, c_int, P, c_int64, P, P, P, P, c_int64, P]),
     'dfol_pair_features_dropout': (c_int, [P, c_int64, c_int, c_int, P, c_int64, c_int, c_int, P, P, P, P, c_int64,
                                            c_uint64, c_int, c_float, P]),
     'dfol_cast_job_size': (c_int, []),

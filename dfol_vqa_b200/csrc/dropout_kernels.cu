@@ -160,9 +160,41 @@ __global__ void __launch_bounds__(256) pair_features_dropout_kernel(
   }
 }
 
+// Backward of the pair-feature gather: d_obj[t, c] += sum_o dpm[(t,o), c] + sum_s dpm[(s,t), width + c]
+// (the geometry columns carry no parameter gradient).  One block per object row, threads over columns.
+__global__ void __launch_bounds__(256) pair_features_bwd_kernel(const float* __restrict__ dpm, long long ld, int width,
+                                                                float* __restrict__ d_obj, long long ldobj,
+                                                                const int32_t* __restrict__ pair_row,
+                                                                const int32_t* __restrict__ obj_row,
+                                                                const int32_t* __restrict__ img_n,
+                                                                const int32_t* __restrict__ obj_img) {
+  const long long t = blockIdx.x;
+  const int b = obj_img[t];
+  const int n = img_n[b];
+  const int i = (int)(t - obj_row[b]);
+  const float* base = dpm + (long long)pair_row[b] * ld;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    float acc = 0.f;
+    for (int o = 0; o < n; ++o) acc += base[(long long)(i * n + o) * ld + c];
+    for (int s2 = 0; s2 < n; ++s2) acc += base[(long long)(s2 * n + i) * ld + width + c];
+    d_obj[t * ldobj + c] += acc;
+  }
+}
+
 }  // namespace dfol
 
 using namespace dfol;
+
+extern "C" int dfol_pair_features_bwd(const float* dpm, int64_t ld, int width, float* d_obj, int64_t ldobj,
+                                      const int32_t* pair_row, const int32_t* obj_row, const int32_t* img_n,
+                                      const int32_t* obj_img, int64_t objects, void* stream) {
+  DFOL_REQUIRE(dpm && d_obj && pair_row && obj_row && img_n && obj_img, "dfol_pair_features_bwd: null pointer");
+  DFOL_REQUIRE(width >= 1 && ld >= 2 * width && ldobj >= width, "dfol_pair_features_bwd: bad shape");
+  if (objects == 0) return 0;
+  pair_features_bwd_kernel<<<(unsigned)objects, 256, 0, (cudaStream_t)stream>>>(dpm, ld, width, d_obj, ldobj, pair_row,
+                                                                               obj_row, img_n, obj_img);
+  return finish_launch("dfol_pair_features_bwd");
+}
 
 extern "C" int dfol_dropout_scale(void* x, int64_t ld, int64_t rows, int cols, int is_bf16, uint64_t seed, int site,
                                   float p, void* stream) {

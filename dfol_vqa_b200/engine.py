@@ -148,8 +148,9 @@ class ReasoningEngine(object):
         batch; when they carry relation slots only those relation columns are evaluated (tensor-core mode).
         ``dropout``: None, or (p, seed) -- training-mode dropout in front of every Linear (forward only: the oracle
         networks must be frozen, as in sample_config.yaml); see csrc/dropout_kernels.cu."""
-        if dropout is not None:
-            assert not keep_for_backward, 'dropout is implemented for frozen oracle networks (forward only)'
+        if dropout is not None and keep_for_backward and self.gemm_mode == 'bf16':
+            raise NotImplementedError('dropout > 0 with TRAINABLE oracle networks is implemented in fp32 mode only: the '
+                                      'tensor-core backward kernels read act\'(h) from the saved activations')
         if self.gemm_mode == 'bf16':
             return self.tc.build_scene(features, layout, keep_for_backward, cp, dropout)
         capi.lib()
@@ -176,19 +177,25 @@ class ReasoningEngine(object):
         obj = torch.empty(T, ldo, device=dev, dtype=torch.float32)
         x_in = features[:, :D] if dropout is None else drop(features[:, :D].contiguous(), D, DROP_FEATURES)
         gemm_f32(x_in, w.feat.weight.t(), obj[:, :F], w.feat.bias, K.ACT_SIGMOID, stream=st)
+        sc.dropout = dropout
+        sc.feat_in = x_in          # what the featurizer GEMM read (masked under dropout): operand of its wgrad
+        keep = dropout is not None and keep_for_backward
         call('dfol_box_position', ptr(features), features.stride(0), D, ptr(obj), ldo, F, T, st)
         sc.obj = obj
 
         # attribute chain -> attribute table (all C concept columns)
+        # under dropout every Linear reads a MASKED copy of the previous output: the unmasked outputs (attr_h) give
+        # act'(h) in the backward pass, the masked inputs (attr_in) are the wgrad operands
         h = obj if dropout is None else drop(obj.clone(), ldo, DROP_ATTR_IN)
-        sc.attr_h = []
+        sc.attr_h, sc.attr_in = [], [h]
         for i, layer in enumerate(w.attr):
             assert dropout is None or len(w.attr) == 2, 'dropout: one hidden layer per network (reference configs)'
             out = torch.empty(T, layer.weight.shape[0], device=dev, dtype=torch.float32)
             gemm_f32(h, layer.weight.t(), out, layer.bias, K.ACT_ELU if i < len(w.attr) - 1 else K.ACT_SIGMOID,
                      stream=st)
             sc.attr_h.append(out)
-            h = drop(out, out.shape[1], DROP_ATTR_HIDDEN if i == 0 else DROP_EMB_ATTR)
+            h = drop(out.clone() if keep else out, out.shape[1], DROP_ATTR_HIDDEN if i == 0 else DROP_EMB_ATTR)
+            sc.attr_in.append(h)
         C = w.emb.weight.shape[0]
         attr_ll = torch.empty(layout.attr_size, device=dev, dtype=torch.float32)
         obj_table = {'row_img': layout.obj_img, 'img_row': layout.obj_row, 'img_blk': layout.attr_blk,
@@ -221,16 +228,20 @@ class ReasoningEngine(object):
                  ptr(layout.obj_row), ptr(layout.img_n), ptr(layout.pair_img), layout.P, int(dropout[1]),
                  DROP_REL_IN, float(dropout[0]), st)
             gemm_f32(pm, first.weight.t(), h1, first.bias, act1, stream=st)
+            sc.rel_in = [pm if keep else None]
             del pm
-            drop(h1, H, DROP_REL_HIDDEN)
         sc.rel_h = [h1]
-        h = h1
+        h = h1 if dropout is None else drop(h1.clone() if keep else h1, H, DROP_REL_HIDDEN)
+        if dropout is not None:
+            sc.rel_in.append(h)
         for i, layer in enumerate(w.rel[1:], start=1):
             out = torch.empty(layout.P, layer.weight.shape[0], device=dev, dtype=torch.float32)
             gemm_f32(h, layer.weight.t(), out, layer.bias, K.ACT_ELU if i < len(w.rel) - 1 else K.ACT_SIGMOID,
                      stream=st)
             sc.rel_h.append(out)
-            h = drop(out, out.shape[1], DROP_EMB_REL)
+            h = drop(out.clone() if keep else out, out.shape[1], DROP_EMB_REL)
+            if dropout is not None:
+                sc.rel_in.append(h)
         ridx = self.rel_index(dev)
         sc.w_rel = w.emb.weight.detach().index_select(0, ridx).contiguous()
         sc.b_rel = w.emb.bias.detach().index_select(0, ridx).contiguous()
@@ -341,14 +352,32 @@ class ReasoningEngine(object):
         E = w.emb.weight.shape[1]
         d_obj = torch.zeros(T, ldo, device=dev, dtype=torch.float32)
 
+        dropout = getattr(scene, 'dropout', None)
+
+        def drop(x, cols, site):
+            """gradient w.r.t. a masked tensor -> gradient w.r.t. the unmasked one: the same mask again (in place)"""
+            call('dfol_dropout_scale', ptr(x), x.stride(0), x.shape[0], cols, 0, int(dropout[1]), site,
+                 float(dropout[0]), st)
+            return x
+
         # ---- attribute table layer (sparse slices) -> dense chain backward
         sa = self._slice_tables(cp.attr_slices, lay.B, dev, 'attr_slices', cp)
-        h_last = scene.attr_h[-1]
-        d_h, is_dz = self._table_backward(
-            g_attr, sa, scene.attr_ll, lay.attr_blk, lay.attr_stride, lay.obj_row, lay.img_n, lay.max_n, T,
-            w.emb.weight, G(w.emb.weight), G(w.emb.bias), h_last, K.ACT_SIGMOID, st)
-        self._mlp_backward(w.attr, [obj] + scene.attr_h, d_h, d_obj, grads, st, first_layer_input_grad=True,
-                           d_out_is_dz=is_dz)
+        if dropout is None:
+            h_last = scene.attr_h[-1]
+            d_h, is_dz = self._table_backward(
+                g_attr, sa, scene.attr_ll, lay.attr_blk, lay.attr_stride, lay.obj_row, lay.img_n, lay.max_n, T,
+                w.emb.weight, G(w.emb.weight), G(w.emb.bias), h_last, K.ACT_SIGMOID, st)
+            self._mlp_backward(w.attr, [obj] + scene.attr_h, d_h, d_obj, grads, st, first_layer_input_grad=True,
+                               d_out_is_dz=is_dz)
+        else:
+            # the table layer read the MASKED last activation: un-fused (no act'), mask the gradient, then the chain
+            d_h, _ = self._table_backward(
+                g_attr, sa, scene.attr_ll, lay.attr_blk, lay.attr_stride, lay.obj_row, lay.img_n, lay.max_n, T,
+                w.emb.weight, G(w.emb.weight), G(w.emb.bias), scene.attr_in[-1], K.ACT_NONE, st)
+            drop(d_h, E, DROP_EMB_ATTR)
+            self._mlp_backward(w.attr, [obj] + scene.attr_h, d_h, d_obj, grads, st, first_layer_input_grad=True,
+                               ins=scene.attr_in, mask=lambda x, i: drop(x, x.shape[1],
+                                                                         (DROP_ATTR_IN, DROP_ATTR_HIDDEN)[i]))
 
         # ---- relation table layer -> dense layers -> pair hidden layer
         sr = self._slice_tables(cp.rel_slices, lay.B, dev, 'rel_slices', cp)
@@ -357,7 +386,9 @@ class ReasoningEngine(object):
             h_last = scene.rel_h[-1]
             dw_rel = torch.zeros(nR, E, device=dev, dtype=torch.float32)
             db_rel = torch.zeros(nR, device=dev, dtype=torch.float32)
-            fuse = K.ACT_SIGMOID if len(w.rel) > 1 else K.ACT_NONE
+            fuse = K.ACT_SIGMOID if (len(w.rel) > 1 and dropout is None) else K.ACT_NONE
+            if dropout is not None:
+                h_last = scene.rel_in[-1]   # the table layer read the masked activation
             d_h, is_dz = self._table_backward(
                 g_rel, sr, scene.rel_ll, lay.rel_blk, lay.rel_stride, lay.pair_row, lay.img_nn, lay.max_n ** 2, P,
                 scene.w_rel, dw_rel, db_rel, h_last, fuse, st)
@@ -367,6 +398,23 @@ class ReasoningEngine(object):
             first = w.rel[0]
             H = first.weight.shape[0]
             gw1 = G(first.weight)
+            if dropout is not None:
+                # masked layers: layer 2 on the masked h1, layer 1 on the materialised masked pair matrix
+                drop(d_h, E, DROP_EMB_REL)
+                d_h1 = self._mlp_backward(w.rel[1:], scene.rel_h, d_h, None, grads, st, first_layer_input_grad=False,
+                                          ins=scene.rel_in[1:], mask=lambda x, i: drop(x, x.shape[1], DROP_REL_HIDDEN))
+                h1, pm = scene.rel_h[0], scene.rel_in[0]
+                call('dfol_act_grad_mul', ptr(d_h1), d_h1.stride(0), ptr(h1), h1.stride(0), P, H, K.ACT_ELU, st)
+                call('dfol_colsum', ptr(d_h1), d_h1.stride(0), P, H, ptr(G(first.bias)), st)
+                sk = _split_for(P)
+                gemm_f32(d_h1.t(), pm, gw1, accumulate=(sk == 1), split_k=sk, stream=st)
+                d_pm = torch.empty(P, pm.shape[1], device=dev, dtype=torch.float32)
+                gemm_f32(d_h1, first.weight, d_pm, stream=st)
+                drop(d_pm, pm.shape[1], DROP_REL_IN)
+                call('dfol_pair_features_bwd', ptr(d_pm), d_pm.stride(0), ldo, ptr(d_obj), ldo, ptr(lay.pair_row),
+                     ptr(lay.obj_row), ptr(lay.img_n), ptr(lay.obj_img), T, st)
+                sr = {'count': 0}  # the factored first-layer backward below is skipped
+        if sr['count']:
             # dense layers above the pair hidden layer
             d_h1 = self._mlp_backward(w.rel[1:], scene.rel_h, d_h, None, grads, st, first_layer_input_grad=False,
                                       d_out_is_dz=is_dz and len(w.rel) > 1)
@@ -386,7 +434,8 @@ class ReasoningEngine(object):
         call('dfol_colsum', ptr(d_obj), ldo, T, F, ptr(G(w.feat.bias)), st)
         D = scene.features.shape[1] - 6
         sk = _split_for(T)
-        gemm_f32(d_obj[:, :F].t(), scene.features[:, :D], G(w.feat.weight), accumulate=(sk == 1), split_k=sk, stream=st)
+        x_in = scene.features[:, :D] if dropout is None else scene.feat_in
+        gemm_f32(d_obj[:, :F].t(), x_in, G(w.feat.weight), accumulate=(sk == 1), split_k=sk, stream=st)
 
     def _table_backward(self, g, tabs, ll, blk, stride, row0, img_rows, max_rows, rows_total, W, dW, db, h_last,
                         fuse_act, st):
@@ -417,11 +466,14 @@ class ReasoningEngine(object):
         gemm_f32(dz, W, d, stream=st)
         return d, False
 
-    def _mlp_backward(self, layers, acts, d_out, d_in_accum, grads, st, first_layer_input_grad, d_out_is_dz=False):
+    def _mlp_backward(self, layers, acts, d_out, d_in_accum, grads, st, first_layer_input_grad, d_out_is_dz=False,
+                      ins=None, mask=None):
         """Backward through [Linear+act]* given d loss / d (last activation OUTPUT).
 
         ``acts`` = [input, h_1, ..., h_L] (saved outputs), ``layers`` the L Linear modules. Returns d loss / d input
         (accumulated into ``d_in_accum`` if given, else a fresh tensor) -- or d_out itself when L == 0.
+        Dropout: ``ins[i]`` is what Linear i really read (the masked copy of acts[i]) and ``mask(x, i)`` multiplies the
+        gradient w.r.t. that masked input by the same mask in place.
         """
         L = len(layers)
         if L == 0:
@@ -430,7 +482,7 @@ class ReasoningEngine(object):
         d_h = d_out
         for i in range(L - 1, -1, -1):
             layer = layers[i]
-            h_out, h_in = acts[i + 1], acts[i]
+            h_out, h_in = acts[i + 1], (acts[i] if ins is None else ins[i])
             rows, width = h_out.shape
             act = K.ACT_SIGMOID if i == L - 1 else K.ACT_ELU
             # dZ = dH * act'(h) in place (already applied by the fused table-layer kernel for the last layer)
@@ -440,11 +492,16 @@ class ReasoningEngine(object):
             sk = _split_for(rows)
             gemm_f32(d_h.t(), h_in, grads[id(layer.weight)], accumulate=(sk == 1), split_k=sk, stream=st)
             if i > 0 or first_layer_input_grad or d_in_accum is None:
-                if i == 0 and d_in_accum is not None:
+                if i == 0 and d_in_accum is not None and mask is None:
                     gemm_f32(d_h, layer.weight, d_in_accum, accumulate=True, stream=st)
                     d_h = d_in_accum
                 else:
                     nxt = torch.empty(rows, h_in.shape[1], device=d_h.device, dtype=torch.float32)
                     gemm_f32(d_h, layer.weight, nxt, stream=st)
+                    if mask is not None:
+                        mask(nxt, i)
+                    if i == 0 and d_in_accum is not None:
+                        d_in_accum += nxt
+                        nxt = d_in_accum
                     d_h = nxt
         return d_h

@@ -245,16 +245,17 @@ class FastGQAInterpreter(nn.Module):
 
     def _dropout_for(self, is_training):
         """None, or (p, seed) of this forward pass: nn.Dropout is active when the module is in train() mode and the
-        networks were built with dropout > 0 (sample_config.yaml: 0.1).  Implemented for FROZEN oracle networks (the
-        sample configuration: only the attention networks train), i.e. forward only; a fresh seed per call is drawn from
-        torch's CPU generator (reproducible under torch.manual_seed).  The reference's own RNG stream cannot be matched;
+        networks were built with dropout > 0 (sample_config.yaml: 0.1).  Tensor-core mode implements it for FROZEN oracle
+        networks (the sample configuration: only the attention networks train), i.e. forward only; fp32 mode also runs
+        the backward pass of the masked layers.  A fresh seed per call is drawn from torch's CPU generator (reproducible
+        under torch.manual_seed).  The reference's own RNG stream cannot be matched;
         the masks are a pure function of the seed (csrc/dropout_kernels.cu) and the tests export them for the oracle."""
         if not (is_training and self.training and self._dropout > 0):
             return None
-        if any(p.requires_grad for p in self._weights.parameters()):
-            raise NotImplementedError('dropout > 0 with TRAINABLE oracle networks is not implemented (the backward pass '
-                                      'of the masked layers): freeze the four oracle networks as sample_config.yaml '
-                                      'does, or set dropout: 0.0')
+        if self._gemm_mode == 'bf16' and any(p.requires_grad for p in self._weights.parameters()):
+            raise NotImplementedError('dropout > 0 with TRAINABLE oracle networks is implemented in fp32 mode only '
+                                      '(gemm_mode="fp32"); in tensor-core mode freeze the four oracle networks as '
+                                      'sample_config.yaml does, or set dropout: 0.0')
         seed = self._fixed_dropout_seed
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())

@@ -286,6 +286,10 @@ int dfol_program_bwd_fast(const int32_t* instr, const int32_t* q_instr, const in
  */
 int dfol_dropout_scale(void* x, int64_t ld, int64_t rows, int cols, int is_bf16, uint64_t seed, int site, float p,
                        void* stream);
+/* backward of the gather: d_obj[t, c] += sum_o dpm[(t,o), c] + sum_s dpm[(s,t), width + c] (dpm already masked) */
+int dfol_pair_features_bwd(const float* dpm, int64_t ld, int width, float* d_obj, int64_t ldobj,
+                           const int32_t* pair_row, const int32_t* obj_row, const int32_t* img_n,
+                           const int32_t* obj_img, int64_t objects, void* stream);
 int dfol_pair_features_dropout(const float* obj, int64_t ldobj, int width, int pos_col, void* out, int64_t ldout,
                                int out_cols, int is_bf16, const int32_t* pair_row, const int32_t* obj_row,
                                const int32_t* img_n, const int32_t* pair_img, int64_t pairs, uint64_t seed, int site,

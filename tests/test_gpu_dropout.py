@@ -164,14 +164,56 @@ def test_dropout_bf16_mode_uses_the_same_masks():
     assert not torch.allclose(other, b, rtol=1e-3, atol=1e-3)   # a different seed gives a different draw
 
 
-def test_dropout_with_trainable_oracle_raises():
-    case = helpers.load_golden(helpers.golden_files()[0])
+@pytest.mark.parametrize('name', ['verify_rel', 'query_attr', 'choose_rel', 'two_same', 'exist'])
+def test_dropout_with_trainable_oracle_fp32_gradients_match_oracle(name):
+    """fp32 mode, TRAINABLE oracle networks with dropout 0.2: loss and all 12 parameter gradients (both surfaces) against
+    autograd through the oracle fed with the exported masks -- the backward pass of the masked layers, including the
+    materialised pair matrix of the first relation layer."""
+    from dfol_vqa_b200.interpreter import FusedTrainStep
+    path = [f for f in helpers.golden_files() if ('golden_%s_s1' % name) in f][0]
+    case = helpers.load_golden(path)
     ont = helpers.ontology_of(case)
-    interp = helpers.build_interpreter(ont, case['dims'], case['state'], dropout=0.1)
-    pbs = helpers.to_cuda(helpers.program_batches_of(case))
+    p, seed = 0.2, 777
+    interp = helpers.build_interpreter(ont, case['dims'], case['state'], dropout=p)
+    interp._fixed_dropout_seed = seed
+    host = helpers.program_batches_of(case)
+    pbs = helpers.to_cuda(host)
+    answers = [a for pb in pbs for a in pb._answers]
+    interp.train()
+    result = interp(pbs, True)
+    lp = result['log_probability']
+    loss = orc.compute_loss([{'log_probability': lp, 'type': result['type'], 'options': result['options']}],
+                            [answers]) / len(answers)
+    loss.backward()
+
+    masks = oracle_masks(interp, case['counts'], seed, p)
+    params = {k: v.clone().requires_grad_(True) for k, v in case['state'].items()}
+    ref = orc.OracleInterpreter(ont, params).run(host[0], True, masks=masks)
+    ref_loss = orc.compute_loss([ref], [answers]) / len(answers)
+    ref_loss.backward()
+    assert abs(float(loss) - float(ref_loss)) <= 3e-5 * max(1.0, abs(float(ref_loss)))
+    sd_keys = {id(q): k for k, q in interp.named_parameters()}
+    for q in interp.oracle_parameters():
+        g = params[sd_keys[id(q)]].grad
+        err = (q.grad.cpu() - g).abs().max()
+        assert err <= 2e-4 * g.abs().max() + 1e-7, (sd_keys[id(q)], float(err), float(g.abs().max()))
+    interp.zero_grad()
+    step = FusedTrainStep(interp)
+    loss2 = step.forward_backward(pbs)
+    assert abs(float(loss2) - float(ref_loss)) <= 3e-5 * max(1.0, abs(float(ref_loss)))
+    for q in interp.oracle_parameters():
+        g = params[sd_keys[id(q)]].grad
+        err = (step.grads[id(q)].cpu() - g).abs().max()
+        assert err <= 2e-4 * g.abs().max() + 1e-7, ('fused', sd_keys[id(q)], float(err), float(g.abs().max()))
+
+
+def test_dropout_with_trainable_oracle_raises_in_tensor_core_mode():
+    from test_gpu_tc_kernels import _programs_world
+    ont, dims, pbs = _programs_world('exist', 4, 8, True, seed=3)
+    interp = helpers.build_interpreter(ont, dims, seed=5, gemm_mode='bf16', dropout=0.1)
     interp.train()
     with pytest.raises(NotImplementedError):
-        interp(pbs, True)
+        interp([pbs[0].to_cuda(0)], True)
     interp.eval()          # eval mode: nn.Dropout is the identity, nothing to refuse
     with torch.no_grad():
-        interp(pbs, False)
+        interp([pbs[0].to_cuda(0)], False)

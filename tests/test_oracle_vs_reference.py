@@ -86,3 +86,61 @@ def test_drop_in_construction_with_reference_objects():
         assert a.kind == b.kind and a.lp_num == b.lp_num
         # 'entity' option order follows the ontology object that is passed in (the reference's is hash-ordered)
         assert [sorted(map(str, o)) for o in a.options] == [sorted(map(str, o)) for o in b.options]
+
+
+def test_drop_in_construction_with_attention_transfer():
+    """sample_config.yaml's arrangement built from the REFERENCE's own modules (activate_attention_transfer: True,
+    frozen oracle networks): our interpreter registers the three attention networks under the reference's parameter
+    names, every `_ops.*` path we expose exists in the reference's state dict, a checkpoint of one loads into the other,
+    and the compiler plan + token-side modulator (torch statement) reproduce the reference's log-probabilities live."""
+    from ref_harness import ReferenceRun, synthetic_metadata
+    from dfol_vqa_b200 import synth
+    from dfol_vqa_b200.interpreter import FastBoxFeaturizer, FastClassifierOracle, FastGQAInterpreter
+    from dfol_vqa_b200.modulator import AttentionTransfer
+    dims = dict(box=40, feat=24, hidden=16, emb=20)
+    md = synthetic_metadata(96, 12, 4, 3, seed=0)
+    run = ReferenceRun(md, dims, seed=0, config_overrides={
+        'activate_attention_transfer': True, 'freeze_attention_network': False, 'attention_transfer_state_dim': 8,
+        'freeze_featurizer': True, 'freeze_attribute_network': True, 'freeze_relation_network': True,
+        'freeze_embedding_network': True})
+    ref_model = run.model
+    flt = ref_model._ops['filter']._filter
+    torch.manual_seed(4)
+    with torch.no_grad():
+        flt._attention_output_network[0].weight.normal_(0.0, 0.5)
+    featurizer = FastBoxFeaturizer(featurizer_network=ref_model._featurizer._featurizer_network)
+    ref_oracle = ref_model._oracle
+    oracle = FastClassifierOracle(run.ontology, ref_oracle._attribute_network, ref_oracle._relation_network,
+                                  ref_oracle._embedding_network, normalize=True, cached=True)
+    interp = FastGQAInterpreter('golden', oracle, run.ontology, featurizer, trainable_gate=False, likelihood_threshold=0,
+                                hard_mode=False, attention_transfer_state_dim=8,
+                                forward_attention_network=flt._forward_attention_network,
+                                backward_attention_network=flt._backward_attention_network,
+                                attention_output_network=flt._attention_output_network,
+                                apply_modulation_everywhere=True, cached=True)
+    assert interp._has_modulator
+    mine, theirs = interp.state_dict(), ref_model.state_dict()
+    ours_ops = {k for k in mine if k.startswith('_ops.')}
+    assert ours_ops and ours_ops <= set(theirs), sorted(ours_ops - set(theirs))[:5]
+    assert {k for k, _ in interp.named_parameters() if 'attention' in k} == \
+        {k for k, _ in ref_model.named_parameters() if 'attention' in k}
+    assert interp.parameter_count() == ref_model.parameter_count()
+    missing, unexpected = interp.load_state_dict(theirs, strict=False)
+    assert not missing
+    assert all(k.startswith('_ops.') for k in unexpected)   # the reference repeats the oracle under every operator
+
+    questions = synth.make_questions(helpers.ontology_of({'metadata': md, 'dims': dims}), 6, 'verify_rel', 0, 4, seed=8)
+    counts = synth.object_counts(6, 7, True, seed=2)
+    feats, bidx = synth.make_object_features(counts, dims['box'], seed=3)
+    ref_pb = run.collate(questions, feats, bidx)
+    ref_lp = run.forward(ref_pb, is_training=True)['log_probability'].detach()
+    cp = interp._compiler.compile(ref_pb[0], counts)
+    at = AttentionTransfer(flt._forward_attention_network, flt._backward_attention_network,
+                           flt._attention_output_network, run.ontology)
+    rows = at.modulations(cp)
+    mods = {(s, k): rows[b:b + r] for s, k, r, b in cp.mod_plan}
+    sd = run.state_dict()
+    params = {k: sd[k] for k in orc.PARAM_KEYS}
+    with torch.no_grad():
+        mine_lp = orc.OracleInterpreter(run.ontology, params).run(ref_pb[0], True, modulations=mods)['log_probability']
+    assert torch.allclose(mine_lp, ref_lp, rtol=2e-5, atol=2e-6), (mine_lp - ref_lp).abs().max()
