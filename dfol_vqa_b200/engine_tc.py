@@ -152,14 +152,22 @@ class TensorCorePath(object):
                              DROP_EMB_ATTR, DROP_EMB_REL)
         capi.lib()
         w = self.w
-        dev = features.device
+        staged = features if isinstance(features, tuple) else None   # (bf16 features (T, D), fp32 geometry (T, 6))
+        dev = staged[1].device if staged is not None else features.device
         st = capi.stream_ptr(dev)
         ops = self.operands(dev)
         d, p = ops.dims, ops.pad
         F, D, ldo, Ha, H, E, C = d['F'], d['D'], d['ldo'], d['Ha'], d['H'], d['E'], d['C']
-        T = features.shape[0]
-        assert T == layout.T and features.dtype == torch.float32 and features.stride(1) == 1
-        assert features.shape[1] == D + 6
+        if staged is not None:
+            x16_in, geometry = staged
+            T = geometry.shape[0]
+            assert D == p['Dp'] and x16_in.shape == (T, D) and x16_in.dtype == torch.bfloat16 and x16_in.stride(1) == 1
+            assert geometry.shape == (T, 6) and geometry.dtype == torch.float32 and geometry.is_contiguous()
+            features = None
+        else:
+            T = features.shape[0]
+            assert features.dtype == torch.float32 and features.stride(1) == 1 and features.shape[1] == D + 6
+        assert T == layout.T
         ops.refresh(st, training)
         sc = Scene()
         sc.layout, sc.features, sc.tc = layout, features, True
@@ -175,13 +183,19 @@ class TensorCorePath(object):
             return x
 
         # featurizer: obj = [sigmoid(X Wf^T + b) | box position] (fp32 for the pair kernel) + bf16 operand copy
-        x16 = bf(T, p['Dp'])
-        call('dfol_cast_bf16', ptr(features), features.stride(0), ptr(x16), p['Dp'], T, D, st)
+        if staged is not None:
+            # the host already holds the features as bf16 (ProgramBatch.stage_bf16): same bits as the cast below
+            x16 = x16_in if dropout is None else x16_in.clone()
+            box, ldbox, box_col = geometry, 6, 0
+        else:
+            x16 = bf(T, p['Dp'])
+            call('dfol_cast_bf16', ptr(features), features.stride(0), ptr(x16), p['Dp'], T, D, st)
+            box, ldbox, box_col = features, features.stride(0), D
         drop(x16, D, DROP_FEATURES)
         obj = torch.empty(T, ldo, device=dev, dtype=torch.float32)
         self._tc(x16, ops.wf, obj, F, p['Dp'], w.feat.bias, K.ACT_SIGMOID, st)
         obj16 = bf(T, p['Op'])
-        call('dfol_obj_finish', ptr(features), features.stride(0), D, ptr(obj), ldo, F, ptr(obj16), p['Op'], T, st)
+        call('dfol_obj_finish', ptr(box), ldbox, box_col, ptr(obj), ldo, F, ptr(obj16), p['Op'], T, st)
         sc.obj, sc.obj16, sc.x16 = obj, obj16, x16
 
         # attribute chain (bf16 activations) -> attribute table (all C concept columns), on the side stream

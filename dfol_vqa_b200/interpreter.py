@@ -243,6 +243,23 @@ class FastGQAInterpreter(nn.Module):
             cache[key] = self._compiler.compile(pb, self._object_counts(pb), give_answer=give_answer)
         return cache[key]
 
+    def _features_of(self, pb):
+        """The box features of a program batch on the device: the reference's (T, D+6) fp32 tensor, or -- when the batch
+        was staged with ProgramBatch.stage_bf16 -- the pair (bf16 features (T, D), fp32 geometry (T, 6))."""
+        staged = getattr(pb, '_staged', None)
+        if staged is not None and pb._object_features is None:
+            if self._gemm_mode != 'bf16':
+                raise RuntimeError('bf16-staged program batches need the tensor-core mode (gemm_mode="bf16")')
+            if not staged[0].is_cuda:
+                raise RuntimeError('dfol_vqa_b200 runs on CUDA only (no CPU fallback): move the program batch to the '
+                                   'GPU first (ProgramBatch.to_cuda)')
+            return staged
+        feats = pb._object_features
+        if not feats.is_cuda:
+            raise RuntimeError('dfol_vqa_b200 runs on CUDA only (no CPU fallback): move the program batch to the '
+                               'GPU first (ProgramBatch.to_cuda)')
+        return feats.float().contiguous()
+
     def _dropout_for(self, is_training):
         """None, or (p, seed) of this forward pass: nn.Dropout is active when the module is in train() mode and the
         networks were built with dropout > 0 (sample_config.yaml: 0.1).  Tensor-core mode implements it for FROZEN oracle
@@ -276,14 +293,10 @@ class FastGQAInterpreter(nn.Module):
         lps, metas, traces = [], [], []
         for k, pb in enumerate(program_batch_list):
             drop_k = None if dropout is None else (dropout[0], dropout[1] + k)  # independent masks per sub-batch
-            feats = pb._object_features
-            if not feats.is_cuda:
-                raise RuntimeError('dfol_vqa_b200 runs on CUDA only (no CPU fallback): move the program batch to the '
-                                   'GPU first (ProgramBatch.to_cuda)')
-            feats = feats.float().contiguous()
+            feats = self._features_of(pb)
             counts = self._object_counts(pb)
             layout = SceneLayout.get(counts, self._weights.emb.weight.shape[0], len(self._ontology._relation_index),
-                                     feats.device)
+                                     feats[1].device if isinstance(feats, tuple) else feats.device)
             cp = self.compiled(pb, give_answer)
             att = self.modulator(cp, modulator_switch)
             sink = {} if return_trace else None
@@ -437,10 +450,8 @@ class FusedTrainStep(object):
         self.scalars.zero_()
         for k, pb in enumerate(program_batch_list):
             drop_k = None if dropout is None else (dropout[0], dropout[1] + k)
-            feats = pb._object_features
-            if not feats.is_cuda:
-                raise RuntimeError('dfol_vqa_b200 runs on CUDA only (no CPU fallback)')
-            dev = feats.device
+            feats = interp._features_of(pb)
+            dev = feats[1].device if isinstance(feats, tuple) else feats.device
             st = capi.stream_ptr(dev)
             counts = interp._object_counts(pb)
             layout = SceneLayout.get(counts, interp._weights.emb.weight.shape[0],

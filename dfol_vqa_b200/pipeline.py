@@ -37,8 +37,9 @@ class HostStepPipeline(object):
             if i + 1 < n:
                 nxt = self._stage(host_batches[i + 1])
             compute.wait_event(ev)
-            db._object_features.record_stream(compute)
-            db._object_batch_index.record_stream(compute)
+            for t in (db._object_features, db._object_batch_index) + tuple(getattr(db, '_staged', None) or ()):
+                if t is not None:
+                    t.record_stream(compute)
             out = self.step_fn(db).detach()
             slot = i & 1
             if self._host[slot] is None or self._host[slot].shape != out.shape or self._host[slot].dtype != out.dtype:

@@ -303,3 +303,35 @@ def test_full_size_gradient_additivity():
     scale = float(g_full.abs().max())
     assert scale > 0 and bool(torch.isfinite(g_full).all())
     assert float((g_full - g_split).abs().max()) <= 2e-3 * scale
+
+
+def test_bf16_staged_features_are_bit_identical():
+    """ProgramBatch.stage_bf16 (bf16 box features + fp32 geometry on the host, half the H2D bytes): the tensor-core scene
+    build casts the fp32 features to bf16 as its first step, so log-probabilities and loss are BIT-identical (gradients up to the order of their atomic reductions)."""
+    import copy
+    from dfol_vqa_b200.interpreter import FusedTrainStep
+    ont, dims, pbs = _programs_world('verify_rel', 12, 24, True, seed=91)
+    interp = helpers.build_interpreter(ont, dims, seed=5, gemm_mode='bf16', emb_bias=-4.0)
+    plain = pbs[0]
+    staged = copy.copy(plain).stage_bf16(drop_fp32=True)
+    assert staged._object_features is None and plain._object_features is not None
+    h2d_plain = plain._object_features.numel() * 4
+    h2d_staged = sum(t.numel() * t.element_size() for t in staged._staged)
+    assert h2d_staged < 0.51 * h2d_plain
+    step = FusedTrainStep(interp)
+    interp.train()
+    out = []
+    for pb in (plain, staged):
+        dev_pb = pb.pin_memory().to_cuda(0)
+        with torch.no_grad():
+            lp = interp([dev_pb], True)['log_probability'].clone()
+        loss = step.forward_backward([dev_pb]).clone()
+        out.append((lp, loss, step.flat_grad.clone()))
+    assert torch.equal(out[0][0], out[1][0])
+    assert torch.equal(out[0][1], out[1][1])
+    # (the weight gradients are split-K reductions with atomic adds: equal up to summation order)
+    scale = float(out[0][2].abs().max())
+    assert float((out[0][2] - out[1][2]).abs().max()) <= 1e-5 * scale
+    fp32 = helpers.build_interpreter(ont, dims, seed=5, gemm_mode='fp32', emb_bias=-4.0)
+    with pytest.raises(RuntimeError):
+        fp32([staged.to_cuda(0)], True)
