@@ -17,7 +17,7 @@ _lib = None
 
 class K(object):
     """Constants of include/dfol_b200.h."""
-    ABI_VERSION = 3
+    ABI_VERSION = 4
     ACT_NONE, ACT_ELU, ACT_SIGMOID, ACT_LOGSIGMOID = 0, 1, 2, 3
     MUL_NONE, MUL_SIGMOID_GRAD, MUL_ELU_GRAD = 0, 1, 2
     INSTR_WORDS = 12
@@ -58,7 +58,7 @@ _SIGNATURES = {
     'dfol_table_layer_bwd_fused': (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, c_int64, P, c_int64, c_int,
                                            c_int, P, c_int64, c_int, c_int, P, P, P]),
     'dfol_gemm_bf16_tc_dgrad': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, c_int64,
-                                        c_int, P]),
+                                        c_int, c_float, P]),
     'dfol_rel_slots_fwd': (c_int, [P, c_int64, c_int, P, c_int64, P, P, P, c_int, P, P, P, P, P, c_int, c_int,
                                    c_float, P, P]),
     'dfol_pair_layer_fwd_tc': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, P, c_int, c_int, c_int, c_int, P,
@@ -68,14 +68,14 @@ _SIGNATURES = {
     'dfol_pair_layer_fwd_cluster': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, P, c_int, c_int, c_int, c_int,
                                             P]),
     'dfol_pair_layer_dgrad_cluster': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P,
-                                              c_int64, c_int, P]),
+                                              c_int64, c_int, c_float, P]),
     'dfol_cast_jobs': (c_int, [P, c_int, c_int64, P]),
     'dfol_lstm_cell_fwd': (c_int, [P, c_int64, P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int, P]),
     'dfol_lstm_cell_bwd': (c_int, [P, P, P, c_int, P, P, P, P, c_int64, P, P, P, P, P, P, c_int, P]),
     'dfol_mod_out_fwd': (c_int, [P, P, P, P, P, c_int, c_int, P, P, c_int, P]),
     'dfol_mod_out_bwd': (c_int, [P, P, P, P, c_int, c_int, P, P, P, c_int, P]),
     'dfol_dropout_scale': (c_int, [P, c_int64, c_int64, c_int, c_int, c_uint64, c_int, c_float, P]),
-    'dfol_pair_features_bwd': (c_int, [P, c_int64, c_int, P, c_int64, P, P, P, P, c_int64, P]),
+    'dfol_pair_features_bwd': (c_int, [P, c_int64, c_int, c_int, P, c_int64, P, c_int64, P, P, P, P, c_int64, P]),
     'dfol_pair_features_dropout': (c_int, [P, c_int64, c_int, c_int, P, c_int64, c_int, c_int, P, P, P, P, c_int64,
                                            c_uint64, c_int, c_float, P]),
     'dfol_cast_job_size': (c_int, []),
@@ -85,7 +85,7 @@ _SIGNATURES = {
     'dfol_pair_hidden_bwd_tc': (c_int, [P, c_int64, P, P, P, c_int64, P, c_int64, P, c_int, P, P, P, c_int, c_int,
                                         P]),
     'dfol_table_layer_bwd_tc': (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, c_int64, P, c_int64,
-                                        c_int, P, c_int64, c_int, P, P, P, P]),
+                                        c_int, P, c_int64, c_int, P, P, P, c_float, P]),
     'dfol_gemm_bf16_tc_wgrad': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int64, P]),
     'dfol_gemm_bf16_tc_wgrad_seg': (c_int, [P, c_int64, P, c_int64, P, c_int64, P, c_int64, P, c_int64, c_int, c_int,
                                             c_int, c_int64, P]),

@@ -160,11 +160,13 @@ __global__ void __launch_bounds__(256) pair_features_dropout_kernel(
   }
 }
 
-// Backward of the pair-feature gather: d_obj[t, c] += sum_o dpm[(t,o), c] + sum_s dpm[(s,t), width + c]
+// Backward of the pair-feature gather: d_obj[t, c] += sum_o dpm[(t,o), c] + sum_s dpm[(s,t), width + c] (+ addend[t, c])
 // (the geometry columns carry no parameter gradient).  One block per object row, threads over columns.
-__global__ void __launch_bounds__(256) pair_features_bwd_kernel(const float* __restrict__ dpm, long long ld, int width,
+template <class T>
+__global__ void __launch_bounds__(256) pair_features_bwd_kernel(const T* __restrict__ dpm, long long ld, int width,
                                                                 float* __restrict__ d_obj, long long ldobj,
-                                                                const int32_t* __restrict__ pair_row,
+                                                                const __nv_bfloat16* __restrict__ addend,
+                                                                long long ld_add, const int32_t* __restrict__ pair_row,
                                                                 const int32_t* __restrict__ obj_row,
                                                                 const int32_t* __restrict__ img_n,
                                                                 const int32_t* __restrict__ obj_img) {
@@ -172,11 +174,11 @@ __global__ void __launch_bounds__(256) pair_features_bwd_kernel(const float* __r
   const int b = obj_img[t];
   const int n = img_n[b];
   const int i = (int)(t - obj_row[b]);
-  const float* base = dpm + (long long)pair_row[b] * ld;
+  const T* base = dpm + (long long)pair_row[b] * ld;
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
-    float acc = 0.f;
-    for (int o = 0; o < n; ++o) acc += base[(long long)(i * n + o) * ld + c];
-    for (int s2 = 0; s2 < n; ++s2) acc += base[(long long)(s2 * n + i) * ld + width + c];
+    float acc = addend ? __bfloat162float(addend[t * ld_add + c]) : 0.f;
+    for (int o = 0; o < n; ++o) acc += (float)base[(long long)(i * n + o) * ld + c];
+    for (int s2 = 0; s2 < n; ++s2) acc += (float)base[(long long)(s2 * n + i) * ld + width + c];
     d_obj[t * ldobj + c] += acc;
   }
 }
@@ -185,14 +187,22 @@ __global__ void __launch_bounds__(256) pair_features_bwd_kernel(const float* __r
 
 using namespace dfol;
 
-extern "C" int dfol_pair_features_bwd(const float* dpm, int64_t ld, int width, float* d_obj, int64_t ldobj,
-                                      const int32_t* pair_row, const int32_t* obj_row, const int32_t* img_n,
-                                      const int32_t* obj_img, int64_t objects, void* stream) {
+extern "C" int dfol_pair_features_bwd(const void* dpm, int64_t ld, int is_bf16, int width, float* d_obj, int64_t ldobj,
+                                      const void* addend_bf16, int64_t ld_add, const int32_t* pair_row,
+                                      const int32_t* obj_row, const int32_t* img_n, const int32_t* obj_img,
+                                      int64_t objects, void* stream) {
   DFOL_REQUIRE(dpm && d_obj && pair_row && obj_row && img_n && obj_img, "dfol_pair_features_bwd: null pointer");
-  DFOL_REQUIRE(width >= 1 && ld >= 2 * width && ldobj >= width, "dfol_pair_features_bwd: bad shape");
+  DFOL_REQUIRE(width >= 1 && ld >= 2 * width && ldobj >= width && (addend_bf16 == nullptr || ld_add >= width),
+               "dfol_pair_features_bwd: bad shape");
   if (objects == 0) return 0;
-  pair_features_bwd_kernel<<<(unsigned)objects, 256, 0, (cudaStream_t)stream>>>(dpm, ld, width, d_obj, ldobj, pair_row,
-                                                                               obj_row, img_n, obj_img);
+  const __nv_bfloat16* add = reinterpret_cast<const __nv_bfloat16*>(addend_bf16);
+  if (is_bf16)
+    pair_features_bwd_kernel<__nv_bfloat16><<<(unsigned)objects, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dpm), ld, width, d_obj, ldobj, add, ld_add, pair_row, obj_row, img_n,
+        obj_img);
+  else
+    pair_features_bwd_kernel<float><<<(unsigned)objects, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float*>(dpm), ld, width, d_obj, ldobj, add, ld_add, pair_row, obj_row, img_n, obj_img);
   return finish_launch("dfol_pair_features_bwd");
 }
 

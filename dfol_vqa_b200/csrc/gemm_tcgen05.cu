@@ -30,6 +30,7 @@ struct TcParams {
   const int32_t* img_n; float diag_value;
   // optional epilogue multiplier (backward): v *= act'(h) with h = mul_src[m * ld_mul + n] (bf16), DFOL_MUL_*
   const __nv_bfloat16* mul_src; long long ld_mul; int mul_mode;
+  float keep;  // < 1: mul_src holds post-dropout activations (0 / h / keep): act' at h = src * keep, factor (src != 0) / keep
 };
 
 template <int ACT>
@@ -157,7 +158,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc_kernel(const __grid_c
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
-          if (p.mul_mode == DFOL_MUL_SIGMOID_GRAD) {
+          if (p.keep < 1.0f) {
+            const float ik = 1.0f / p.keep, hx = h.x * p.keep, hy = h.y * p.keep;
+            const float gx = (p.mul_mode == DFOL_MUL_SIGMOID_GRAD) ? hx * (1.0f - hx) : (hx > 0.0f ? 1.0f : hx + 1.0f);
+            const float gy = (p.mul_mode == DFOL_MUL_SIGMOID_GRAD) ? hy * (1.0f - hy) : (hy > 0.0f ? 1.0f : hy + 1.0f);
+            v[2 * j] *= (h.x != 0.0f ? ik : 0.0f) * gx;
+            v[2 * j + 1] *= (h.y != 0.0f ? ik : 0.0f) * gy;
+          } else if (p.mul_mode == DFOL_MUL_SIGMOID_GRAD) {
             v[2 * j] *= h.x * (1.0f - h.x);
             v[2 * j + 1] *= h.y * (1.0f - h.y);
           } else {
@@ -247,7 +254,8 @@ static int launch_tc(const char* who, const void* A, int64_t lda, const void* B,
                      const float* bias, int M, int N, int K, int act, int out_bf16, int store, const int32_t* row_img,
                      const int32_t* img_row, const int64_t* img_blk, const int32_t* img_stride, const int32_t* img_n,
                      float diag_value, const void* mul_src, int64_t ld_mul, int mul_mode, int store_cols,
-                     void* stream) {
+                     void* stream, float keep = 1.0f) {
+  DFOL_REQUIRE(keep > 0.0f && keep <= 1.0f, "%s: keep = 1 - dropout p must be in (0, 1]", who);
   DFOL_REQUIRE(A && B && C, "%s: null pointer", who);
   DFOL_REQUIRE(M > 0 && N > 0 && K > 0 && (K % TC_BK) == 0, "%s: K must be a positive multiple of 64", who);
   DFOL_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && lda >= K && ldb >= K,
@@ -277,6 +285,7 @@ static int launch_tc(const char* who, const void* A, int64_t lda, const void* B,
   p.row_img = row_img; p.img_row = img_row; p.img_blk = img_blk; p.img_stride = img_stride; p.img_n = img_n;
   p.diag_value = diag_value;
   p.mul_src = reinterpret_cast<const __nv_bfloat16*>(mul_src); p.ld_mul = ld_mul; p.mul_mode = mul_mode;
+  p.keep = keep;
   const int stage_bytes = (TC_BM + BN) * TC_BK * 2;
   int stages = (110 * 1024) / stage_bytes;  // two CTAs per SM
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -310,7 +319,7 @@ extern "C" int dfol_gemm_bf16_tc(const void* A, int64_t lda, const void* B, int6
 
 extern "C" int dfol_gemm_bf16_tc_dgrad(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX,
                                        int64_t lddx, int store_cols, int M, int N, int K, const void* h_saved,
-                                       int64_t ldh, int mul_mode, void* stream) {
+                                       int64_t ldh, int mul_mode, float keep, void* stream) {
   return launch_tc("dfol_gemm_bf16_tc_dgrad", dZ, lddz, Wt, ldwt, dX, lddx, nullptr, M, N, K, DFOL_ACT_NONE, 1, 0,
-                   nullptr, nullptr, nullptr, nullptr, nullptr, 0.0f, h_saved, ldh, mul_mode, store_cols, stream);
+                   nullptr, nullptr, nullptr, nullptr, nullptr, 0.0f, h_saved, ldh, mul_mode, store_cols, stream, keep);
 }

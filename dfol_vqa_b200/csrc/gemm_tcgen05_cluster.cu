@@ -35,6 +35,7 @@ struct ClParams {
   int act, mul_mode;    // mul_mode != NONE: epilogue operand tile (bf16, same shape as C) is loaded through tmap_e
   int cluster_size;     // CTAs per cluster (the launch attribute)
   int n_store;          // stored width of C (64-column boxes entirely beyond it are skipped)
+  float keep;           // < 1: the multiplier operand holds post-dropout activations (0 / h / keep)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -256,7 +257,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
-            if (p.mul_mode == DFOL_MUL_SIGMOID_GRAD) {
+            if (p.keep < 1.0f) {  // act' at h = operand * keep, mask factor (operand != 0) / keep
+              const float ik = 1.0f / p.keep, hx = h.x * p.keep, hy = h.y * p.keep;
+              const float gx = (p.mul_mode == DFOL_MUL_SIGMOID_GRAD) ? hx * (1.0f - hx) : (hx > 0.0f ? 1.0f : hx + 1.0f);
+              const float gy = (p.mul_mode == DFOL_MUL_SIGMOID_GRAD) ? hy * (1.0f - hy) : (hy > 0.0f ? 1.0f : hy + 1.0f);
+              v[2 * j] *= (h.x != 0.0f ? ik : 0.0f) * gx;
+              v[2 * j + 1] *= (h.y != 0.0f ? ik : 0.0f) * gy;
+            } else if (p.mul_mode == DFOL_MUL_SIGMOID_GRAD) {
               v[2 * j] *= h.x * (1.0f - h.x);
               v[2 * j + 1] *= h.y * (1.0f - h.y);
             } else {
@@ -314,8 +321,9 @@ using namespace dfol;
 
 static int launch_cluster(const char* who, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                           int store_cols, const float* bias, int M, int N, int K, int act, const void* E, int64_t lde,
-                          int mul_mode, void* stream) {
+                          int mul_mode, void* stream, float keep = 1.0f) {
   DFOL_REQUIRE(A && B && C, "%s: null pointer", who);
+  DFOL_REQUIRE(keep > 0.0f && keep <= 1.0f, "%s: keep = 1 - dropout p must be in (0, 1]", who);
   DFOL_REQUIRE(M > 0 && N > 0 && K > 0 && (K % CL_BK) == 0 && K <= CL_BK * CL_MAX_KB,
                "%s: K must be a multiple of 64, at most %d", who, CL_BK * CL_MAX_KB);
   DFOL_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && (ldc % 8) == 0 && lda >= K && ldb >= K,
@@ -329,7 +337,7 @@ static int launch_cluster(const char* who, const void* A, int64_t lda, const voi
   DFOL_REQUIRE(!has_e || (E && (lde % 8) == 0 && (reinterpret_cast<uintptr_t>(E) % 16) == 0 && lde >= N),
                "%s: multiplier operand must be 16-byte aligned with ld %% 8 == 0", who);
   ClParams p;
-  p.bias = bias; p.M = M; p.N = N; p.K = K; p.act = act; p.mul_mode = mul_mode;
+  p.bias = bias; p.M = M; p.N = N; p.K = K; p.act = act; p.mul_mode = mul_mode; p.keep = keep;
   // columns per CTA and cluster size.  Two CTAs (half of the stored width each, whole 64-column boxes) measured best:
   // clusters of 3-4 CTAs leave room for a 7-8 stage A ring but run 2x slower (every ring stage is released by a
   // commit from every CTA of the cluster, and the lockstep of 3-4 SMs costs more than the deeper ring gains).
@@ -404,7 +412,7 @@ extern "C" int dfol_pair_layer_fwd_cluster(const void* A, int64_t lda, const voi
 
 extern "C" int dfol_pair_layer_dgrad_cluster(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX,
                                              int64_t lddx, int store_cols, int M, int N, int K, const void* h_saved,
-                                             int64_t ldh, int mul_mode, void* stream) {
+                                             int64_t ldh, int mul_mode, float keep, void* stream) {
   return launch_cluster("dfol_pair_layer_dgrad_cluster", dZ, lddz, Wt, ldwt, dX, lddx, store_cols, nullptr, M, N, K,
-                        DFOL_ACT_NONE, h_saved, ldh, mul_mode, stream);
+                        DFOL_ACT_NONE, h_saved, ldh, mul_mode, stream, keep);
 }

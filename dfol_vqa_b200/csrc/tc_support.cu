@@ -259,15 +259,20 @@ __global__ void __launch_bounds__(32 * RG) pair_hidden_bwd_tc_kernel(
 constexpr int TB_ROWS = 128;
 constexpr int TB_RP = 2;  // row-parallel warps per column chunk
 
-template <int S, int NC>
+template <int S, int NC, bool DROP>
 __global__ void __launch_bounds__(32 * NC * TB_RP) table_layer_bwd_tc_kernel(
     const float* __restrict__ g, const int32_t* __restrict__ slice_goff, const int32_t* __restrict__ slice_col,
     const int32_t* __restrict__ slice_wrow, const int32_t* __restrict__ img_slice, int first, int accumulate,
     const float* __restrict__ ll, const int64_t* __restrict__ blk, const int32_t* __restrict__ stride,
     const int32_t* __restrict__ row0, const int32_t* __restrict__ img_rows, const float* __restrict__ W,
     long long ldw, const __nv_bfloat16* __restrict__ hs, long long ldh, int E, __nv_bfloat16* __restrict__ dZ,
-    long long lddz, int out_cols, float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dbelow) {
+    long long lddz, int out_cols, float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dbelow,
+    float keep) {
   constexpr int THREADS = 32 * NC * TB_RP;
+  // keep < 1: hs holds the activation AFTER dropout (0 where dropped, h / keep where kept): it is the operand of the dW
+  // rows as it stands, sigmoid' is taken at h = hs * keep and the gradient carries the mask factor (hs != 0) / keep
+  // (DROP is a template parameter: the instantiation without dropout is the kernel it was before)
+  const float inv_keep = DROP ? 1.0f / keep : 1.0f;
   __shared__ float dz_s[S][TB_ROWS];
   __shared__ int wrow_s[S];
   __shared__ __align__(16) float red_s[TB_RP][NC * 64];
@@ -341,8 +346,14 @@ __global__ void __launch_bounds__(32 * NC * TB_RP) table_layer_bwd_tc_kernel(
             dwj[j].y = fmaf(dzl, hv.y, dwj[j].y);
           }
         }
-        ox *= hv.x * (1.0f - hv.x);
-        oy *= hv.y * (1.0f - hv.y);
+        if (DROP) {
+          const float hx = hv.x * keep, hy = hv.y * keep;
+          ox *= (hv.x != 0.0f ? inv_keep : 0.0f) * hx * (1.0f - hx);
+          oy *= (hv.y != 0.0f ? inv_keep : 0.0f) * hy * (1.0f - hy);
+        } else {
+          ox *= hv.x * (1.0f - hv.x);
+          oy *= hv.y * (1.0f - hv.y);
+        }
         colsum.x += ox;
         colsum.y += oy;
         if (st_ok) {  // columns E .. out_cols are the zero K-padding of the next GEMM (h = 0 there)
@@ -561,10 +572,12 @@ extern "C" int dfol_table_layer_bwd_tc(const float* g, const int32_t* slice_goff
                                        int max_rows, int max_slices, const float* ll, const int64_t* blk,
                                        const int32_t* stride, const int32_t* row0, const int32_t* img_rows,
                                        const float* W, int64_t ldw, const void* h_saved, int64_t ldh, int E, void* dZ,
-                                       int64_t lddz, int out_cols, float* dW, float* db, float* dbelow, void* stream) {
+                                       int64_t lddz, int out_cols, float* dW, float* db, float* dbelow, float keep,
+                                       void* stream) {
   DFOL_REQUIRE(g && slice_goff && slice_col && slice_wrow && img_slice && ll && blk && stride && row0 && img_rows &&
                    W && h_saved && dZ && dW && db,
                "dfol_table_layer_bwd_tc: null pointer");
+  DFOL_REQUIRE(keep > 0.0f && keep <= 1.0f, "dfol_table_layer_bwd_tc: keep = 1 - dropout p must be in (0, 1]");
   if (image_num == 0 || max_rows == 0) return 0;
   DFOL_REQUIRE(out_cols >= E && out_cols <= lddz && out_cols <= 320 && (E % 2) == 0 && (out_cols % 2) == 0 &&
                    (ldw % 2) == 0 && (ldh % 2) == 0 && (lddz % 2) == 0,
@@ -579,16 +592,20 @@ extern "C" int dfol_table_layer_bwd_tc(const float* g, const int32_t* slice_goff
   do {
     const int left = max_slices - first;
     const int acc = first > 0 ? 1 : 0;
-#define DFOL_TB_LAUNCH(S)                                                                                           \
-  table_layer_bwd_tc_kernel<S, 5><<<grid, 320, 0, st>>>(g, slice_goff, slice_col, slice_wrow, img_slice, first, acc, \
-                                                        ll, blk, stride, row0, img_rows, W, ldw, hp, ldh, E, dzp,    \
-                                                        lddz, out_cols, dW, db, dbelow)
+#define DFOL_TB_ARGS g, slice_goff, slice_col, slice_wrow, img_slice, first, acc, ll, blk, stride, row0, img_rows, W, ldw, \
+                     hp, ldh, E, dzp, lddz, out_cols, dW, db, dbelow, keep
+#define DFOL_TB_LAUNCH(S)                                                                        \
+  do {                                                                                           \
+    if (keep < 1.0f) table_layer_bwd_tc_kernel<S, 5, true><<<grid, 320, 0, st>>>(DFOL_TB_ARGS);  \
+    else table_layer_bwd_tc_kernel<S, 5, false><<<grid, 320, 0, st>>>(DFOL_TB_ARGS);             \
+  } while (0)
     if (left <= 1) { DFOL_TB_LAUNCH(1); first += 1; }
     else if (left == 2) { DFOL_TB_LAUNCH(2); first += 2; }
     else if (left <= 4) { DFOL_TB_LAUNCH(4); first += 4; }
     else if (left <= 8) { DFOL_TB_LAUNCH(8); first += 8; }
     else { DFOL_TB_LAUNCH(12); first += 12; }
 #undef DFOL_TB_LAUNCH
+#undef DFOL_TB_ARGS
   } while (first < max_slices);
   return finish_launch("dfol_table_layer_bwd_tc");
 }

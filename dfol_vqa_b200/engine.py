@@ -148,9 +148,6 @@ class ReasoningEngine(object):
         batch; when they carry relation slots only those relation columns are evaluated (tensor-core mode).
         ``dropout``: None, or (p, seed) -- training-mode dropout in front of every Linear (forward only: the oracle
         networks must be frozen, as in sample_config.yaml); see csrc/dropout_kernels.cu."""
-        if dropout is not None and keep_for_backward and self.gemm_mode == 'bf16':
-            raise NotImplementedError('dropout > 0 with TRAINABLE oracle networks is implemented in fp32 mode only: the '
-                                      'tensor-core backward kernels read act\'(h) from the saved activations')
         if self.gemm_mode == 'bf16':
             return self.tc.build_scene(features, layout, keep_for_backward, cp, dropout)
         capi.lib()
@@ -411,8 +408,8 @@ class ReasoningEngine(object):
                 d_pm = torch.empty(P, pm.shape[1], device=dev, dtype=torch.float32)
                 gemm_f32(d_h1, first.weight, d_pm, stream=st)
                 drop(d_pm, pm.shape[1], DROP_REL_IN)
-                call('dfol_pair_features_bwd', ptr(d_pm), d_pm.stride(0), ldo, ptr(d_obj), ldo, ptr(lay.pair_row),
-                     ptr(lay.obj_row), ptr(lay.img_n), ptr(lay.obj_img), T, st)
+                call('dfol_pair_features_bwd', ptr(d_pm), d_pm.stride(0), 0, ldo, ptr(d_obj), ldo, None, 0,
+                     ptr(lay.pair_row), ptr(lay.obj_row), ptr(lay.img_n), ptr(lay.obj_img), T, st)
                 sr = {'count': 0}  # the factored first-layer backward below is skipped
         if sr['count']:
             # dense layers above the pair hidden layer

@@ -127,13 +127,13 @@ class TensorCorePath(object):
              act, out_bf16, store, maps[0], maps[1], maps[2], maps[3], maps[4], diag, st)
 
     @staticmethod
-    def _dgrad(dZ, Wt, dX, N, Kp, h_saved, mul_mode, st):
+    def _dgrad(dZ, Wt, dX, N, Kp, h_saved, mul_mode, st, keep=1.0):
         """dX[:, :cols(dX)] = (dZ . Wt^T) * act'(h_saved); dX may be a column block of a wider buffer."""
         M = dZ.shape[0]
         if capi.trace is not None:
             capi.next_meta = {'tag': 'gemm_bf16_tc_dgrad[%dx%dx%d]' % (M, N, Kp), 'flops': 2.0 * M * N * Kp}
         call('dfol_gemm_bf16_tc_dgrad', ptr(dZ), dZ.stride(0), ptr(Wt), Wt.stride(0), ptr(dX), dX.stride(0), dX.shape[1], M,
-             N, Kp, ptr(h_saved), 0 if h_saved is None else h_saved.stride(0), mul_mode, st)
+             N, Kp, ptr(h_saved), 0 if h_saved is None else h_saved.stride(0), mul_mode, float(keep), st)
 
     @staticmethod
     def _wgrad(A, Mc, B, Nc, C, st):
@@ -170,7 +170,7 @@ class TensorCorePath(object):
         assert T == layout.T
         ops.refresh(st, training)
         sc = Scene()
-        sc.layout, sc.features, sc.tc = layout, features, True
+        sc.layout, sc.features, sc.tc, sc.dropout = layout, features, True, dropout
 
         def bf(rows, cols):
             return torch.empty(rows, cols, device=dev, dtype=torch.bfloat16)
@@ -209,6 +209,7 @@ class TensorCorePath(object):
             st2 = side.cuda_stream
             h1a = bf(T, p['Hap'])
             obj16a = obj16 if dropout is None else drop(obj16.clone(), ldo, DROP_ATTR_IN, st2)
+            sc.obj16a = obj16a
             self._tc(obj16a, ops.wa1, h1a, Ha, p['Op'], w.attr[0].bias, K.ACT_ELU, st2)
             drop(h1a, Ha, DROP_ATTR_HIDDEN, st2)
             h2a = bf(T, p['Ep'])
@@ -253,6 +254,7 @@ class TensorCorePath(object):
             if p['Hp'] > H:
                 h1r.zero_()
             self._tc(pm, w1, h1r, H, Kp, first.bias, K.ACT_ELU, st)
+            sc.pm, sc.w1_16 = (pm, w1) if training else (None, None)
             del pm
             drop(h1r, H, DROP_REL_HIDDEN)
         # the activation of layer 2 is only materialised when the backward pass (or the dense table) needs it
@@ -315,7 +317,7 @@ class TensorCorePath(object):
     # -------------------------------------------------------------------------------------------- backward
 
     def _table_backward(self, g, tabs, ll, blk, stride, row0, img_rows, max_rows, rows_total, W, dW, db, h_last,
-                        d_below, st, tag):
+                        d_below, st, tag, keep=1.0, remask=None):
         """dZ (bf16, rows x padded width) of the layer below a table layer, from the compact gradient slices."""
         dev = ll.device
         E = W.shape[1]
@@ -328,8 +330,9 @@ class TensorCorePath(object):
             call('dfol_table_layer_bwd_tc', ptr(g), ptr(tabs['goff']), ptr(tabs['col']), ptr(tabs['wrow']),
                  ptr(tabs['img_slice']), len(tabs['img_slice']) - 1, max_rows, tabs['max_per_image'], ptr(ll),
                  ptr(blk), ptr(stride), ptr(row0), ptr(img_rows), ptr(W), W.stride(0), ptr(h_last),
-                 h_last.stride(0), E, ptr(dz), dz.stride(0), cols, ptr(dW), ptr(db), ptr(d_below), st)
+                 h_last.stride(0), E, ptr(dz), dz.stride(0), cols, ptr(dW), ptr(db), ptr(d_below), float(keep), st)
             return dz
+        assert keep == 1.0 or rows_total < (1 << 22), 'dropout: the dense table backward is meant for object rows'
         # many columns per image (option lists of query-type programs): dense d logits + fp32 GEMMs
         from .engine import gemm_f32, _split_for
         Cn = dW.shape[0]
@@ -342,6 +345,9 @@ class TensorCorePath(object):
         gemm_f32(dl.t(), h32, dW, accumulate=(sk == 1), split_k=sk, stream=st)
         d = torch.empty(rows_total, E, device=dev, dtype=torch.float32)
         gemm_f32(dl, W, d, stream=st)
+        if keep < 1.0:  # h_last is the post-dropout activation: re-mask the gradient, sigmoid' at h = saved * keep
+            remask(d, E)
+            h32 = h32 * keep
         call('dfol_act_grad_mul', ptr(d), E, ptr(h32), E, rows_total, E, K.ACT_SIGMOID, st)
         call('dfol_colsum', ptr(d), E, rows_total, E, ptr(d_below), st)
         call('dfol_cast_bf16', ptr(d), E, ptr(dz), cols, rows_total, E, st)
@@ -358,6 +364,8 @@ class TensorCorePath(object):
         F, D, ldo, Ha, H, E = d['F'], d['D'], d['ldo'], d['Ha'], d['H'], d['E']
         Hap, Hp, Ep, Kc = p['Hap'], p['Hp'], p['Ep'], p['Kc']
         T, P = lay.T, lay.P
+        if getattr(scene, 'dropout', None) is not None:
+            return self._backward_dropout(cp, scene, tape, d_lp, grads)
         assert scene.geo is not None, 'scene was built without training buffers'
 
         def G(prm):
@@ -416,7 +424,7 @@ class TensorCorePath(object):
                 capi.next_meta = {'tag': 'pair_layer_dgrad_cluster[%dx%dx%d]' % (P, H, Ep), 'flops': 2.0 * P * H * Ep,
                                   'bytes': 2.0 * P * (Ep + 2 * Hp)}
             call('dfol_pair_layer_dgrad_cluster', ptr(dz2r), Ep, ptr(ops.wr2t), Ep, ptr(dz1r), Hp, Hp, P, H, Ep,
-                 ptr(h1r), Hp, K.MUL_ELU_GRAD, st)
+                 ptr(h1r), Hp, K.MUL_ELU_GRAD, 1.0, st)
             gw1 = G(r0.weight)
             if capi.trace is not None:
                 capi.next_meta = {'tag': 'pair_hidden_bwd_tc', 'bytes': 2.0 * P * H + 16.0 * P}
@@ -440,4 +448,90 @@ class TensorCorePath(object):
         dpre = torch.empty(T, F, device=dev, dtype=torch.bfloat16)
         self._dgrad(dcat, ops.wcat_t, dpre, F, Kc, scene.obj16, K.MUL_SIGMOID_GRAD, st)
         call('dfol_colsum_bf16', ptr(dpre), F, T, F, ptr(G(w.feat.bias)), st)
+        self._wgrad(dpre, F, scene.x16, D, G(w.feat.weight), st)
+
+    def _backward_dropout(self, cp, scene, tape, d_lp, grads):
+        """Backward pass of a scene built with training-mode dropout.  Every saved activation is the tensor AFTER its
+        dropout mask (the real operand of the next GEMM, hence of its wgrad); the kernels that need act'(h) recover h
+        and the mask from it (``keep`` = 1 - p: h = saved * keep, mask factor (saved != 0) / keep), the masks of the
+        two network inputs are recomputed (dfol_dropout_scale on the gradient).  The first relation layer runs on the
+        materialised masked pair matrix, so its weight gradient is one tcgen05 wgrad and its input gradient one dgrad +
+        mask + reduction over pairs (dfol_pair_features_bwd) instead of the factored pair-hidden backward."""
+        from .engine import DROP_ATTR_IN, DROP_REL_IN, DROP_EMB_ATTR
+        eng = self.engine
+        w = self.w
+        lay = scene.layout
+        dev = scene.attr_ll.device
+        st = capi.stream_ptr(dev)
+        ops = self.operands(dev)
+        d, p = ops.dims, ops.pad
+        F, D, ldo, Ha, H, E = d['F'], d['D'], d['ldo'], d['Ha'], d['H'], d['E']
+        Hap, Hp, Ep, Op = p['Hap'], p['Hp'], p['Ep'], p['Op']
+        T, P = lay.T, lay.P
+        prob, seed = float(scene.dropout[0]), int(scene.dropout[1])
+        keep = 1.0 - prob
+        assert scene.pm is not None, 'scene was built without training buffers'
+
+        def G(prm):
+            return grads[id(prm)]
+
+        def remask(x, cols, site):
+            call('dfol_dropout_scale', ptr(x), x.stride(0), x.shape[0], cols, int(x.dtype == torch.bfloat16), seed, site,
+                 prob, st)
+
+        a0, a1, r0, r1 = w.attr[0], w.attr[1], w.rel[0], w.rel[1]
+        g_attr, g_rel = eng.program_backward(cp, scene, tape, d_lp)
+
+        # ---- attribute chain
+        d_obj_a = torch.zeros(T, Op, device=dev, dtype=torch.bfloat16)   # its share of d obj (masked input gradient)
+        sa = eng._slice_tables(cp.attr_slices, lay.B, dev, 'attr_slices', cp)
+        if sa['count']:
+            h1a, h2a = scene.attr_h
+            dz2a = self._table_backward(g_attr, sa, scene.attr_ll, lay.attr_blk, lay.attr_stride, lay.obj_row,
+                                        lay.img_n, lay.max_n, T, w.emb.weight, G(w.emb.weight), G(w.emb.bias), h2a,
+                                        G(a1.bias), st, 'attr', keep, lambda x, c: remask(x, c, DROP_EMB_ATTR))
+            self._wgrad(dz2a, E, h1a, Ha, G(a1.weight), st)
+            dz1a = torch.zeros(T, Hap, device=dev, dtype=torch.bfloat16)
+            self._dgrad(dz2a, ops.wa2t, dz1a, Ha, Ep, h1a, K.MUL_ELU_GRAD, st, keep)
+            call('dfol_colsum_bf16', ptr(dz1a), Hap, T, Ha, ptr(G(a0.bias)), st)
+            self._wgrad(dz1a, Ha, scene.obj16a, ldo, G(a0.weight), st)
+            self._dgrad(dz1a, ops.wcat_t[:, :Hap], d_obj_a, F, Hap, None, K.MUL_NONE, st)
+            remask(d_obj_a, ldo, DROP_ATTR_IN)
+
+        # ---- relation chain
+        d_obj = torch.zeros(T, ldo, device=dev, dtype=torch.float32)
+        sr = eng._slice_tables(cp.rel_slices, lay.B, dev, 'rel_slices', cp)
+        if sr['count']:
+            assert scene.rel_slots, 'dropout with trainable oracle networks needs the demand-driven relation table'
+            h1r, h2r = scene.rel_h
+            dz2r = self._table_backward(g_rel, sr, scene.rel_ll, scene.rel_blk, lay.rel_stride, lay.pair_row,
+                                        lay.img_nn, lay.max_n ** 2, P, w.emb.weight, G(w.emb.weight), G(w.emb.bias),
+                                        h2r, G(r1.bias), st, 'rel', keep)
+            self._wgrad(dz2r, E, h1r, H, G(r1.weight), st)
+            dz1r = torch.empty(P, Hp, device=dev, dtype=torch.bfloat16)
+            call('dfol_pair_layer_dgrad_cluster', ptr(dz2r), Ep, ptr(ops.wr2t), Ep, ptr(dz1r), Hp, Hp, P, H, Ep,
+                 ptr(h1r), Hp, K.MUL_ELU_GRAD, keep, st)
+            del dz2r
+            call('dfol_colsum_bf16', ptr(dz1r), Hp, P, H, ptr(G(r0.bias)), st)
+            pm, w1 = scene.pm, scene.w1_16
+            width = 2 * ldo + 4
+            Kp = pm.shape[1]
+            self._wgrad(dz1r, H, pm, width, G(r0.weight), st)
+            # d pm = dZ1 . W1 (all pair columns), re-masked, reduced over pairs back to the objects
+            w1t = w1.t().contiguous()   # [Kp, H]: dgrad operand (in x out)
+            if Hp > H:
+                w1t = torch.nn.functional.pad(w1t, (0, Hp - H))
+            d_pm = torch.empty(P, Kp, device=dev, dtype=torch.bfloat16)
+            self._dgrad(dz1r, w1t, d_pm, Kp, Hp, None, K.MUL_NONE, st)
+            remask(d_pm, width, DROP_REL_IN)
+            call('dfol_pair_features_bwd', ptr(d_pm), Kp, 1, ldo, ptr(d_obj), ldo, ptr(d_obj_a), Op,
+                 ptr(lay.pair_row), ptr(lay.obj_row), ptr(lay.img_n), ptr(lay.obj_img), T, st)
+        else:
+            d_obj[:, :F] = d_obj_a[:, :F].float()
+
+        # ---- featurizer: d pre = d obj[:, :F] * f (1 - f) (obj itself is not masked: the masks sit on its copies)
+        call('dfol_act_grad_mul', ptr(d_obj), ldo, ptr(scene.obj), ldo, T, F, K.ACT_SIGMOID, st)
+        call('dfol_colsum', ptr(d_obj), ldo, T, F, ptr(G(w.feat.bias)), st)
+        dpre = torch.empty(T, F, device=dev, dtype=torch.bfloat16)
+        call('dfol_cast_bf16', ptr(d_obj), ldo, ptr(dpre), F, T, F, st)
         self._wgrad(dpre, F, scene.x16, D, G(w.feat.weight), st)

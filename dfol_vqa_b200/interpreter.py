@@ -238,7 +238,8 @@ class FastGQAInterpreter(nn.Module):
             host = getattr(pb, '_dfol_host', None)
             if host is not None:
                 host._dfol_compiled = cache
-        key = bool(give_answer and self._hard_mode)
+        # (the bytecode depends on the compiler's table layout and on whether modulation rows are assigned)
+        key = (bool(give_answer and self._hard_mode), self._compiler.relation_slots, self._compiler.modulated)
         if key not in cache:
             cache[key] = self._compiler.compile(pb, self._object_counts(pb), give_answer=give_answer)
         return cache[key]
@@ -262,17 +263,13 @@ class FastGQAInterpreter(nn.Module):
 
     def _dropout_for(self, is_training):
         """None, or (p, seed) of this forward pass: nn.Dropout is active when the module is in train() mode and the
-        networks were built with dropout > 0 (sample_config.yaml: 0.1).  Tensor-core mode implements it for FROZEN oracle
-        networks (the sample configuration: only the attention networks train), i.e. forward only; fp32 mode also runs
-        the backward pass of the masked layers.  A fresh seed per call is drawn from torch's CPU generator (reproducible
-        under torch.manual_seed).  The reference's own RNG stream cannot be matched;
+        networks were built with dropout > 0 (sample_config.yaml: 0.1).  With frozen oracle networks (the sample
+        configuration: only the attention networks train) only the forward pass is masked; with trainable ones both
+        modes also run the backward pass of the masked layers.  A fresh seed per call is drawn from torch's CPU generator
+        (reproducible under torch.manual_seed).  The reference's own RNG stream cannot be matched;
         the masks are a pure function of the seed (csrc/dropout_kernels.cu) and the tests export them for the oracle."""
         if not (is_training and self.training and self._dropout > 0):
             return None
-        if self._gemm_mode == 'bf16' and any(p.requires_grad for p in self._weights.parameters()):
-            raise NotImplementedError('dropout > 0 with TRAINABLE oracle networks is implemented in fp32 mode only '
-                                      '(gemm_mode="fp32"); in tensor-core mode freeze the four oracle networks as '
-                                      'sample_config.yaml does, or set dropout: 0.0')
         seed = self._fixed_dropout_seed
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())

@@ -231,5 +231,6 @@ def attach_compiled(program_batch, compiler, give_answer=False):
     cache = getattr(program_batch, '_dfol_compiled', None)
     if cache is None:
         cache = program_batch._dfol_compiled = {}
-    cache[bool(give_answer and compiler.hard_mode)] = compiler.compile(program_batch, counts, give_answer=give_answer)
+    key = (bool(give_answer and compiler.hard_mode), compiler.relation_slots, compiler.modulated)
+    cache[key] = compiler.compile(program_batch, counts, give_answer=give_answer)
     return program_batch

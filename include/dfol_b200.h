@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFOL_ABI_VERSION 3
+#define DFOL_ABI_VERSION 4
 
 /* activation codes (RegularMLP / EmbeddingLayer, gqa_interpreter_experiments.py:28-33, :71-72) */
 #define DFOL_ACT_NONE 0
@@ -88,7 +88,10 @@ int dfol_gemm_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, vo
  *        operands straight from the row-major activations, split-K over CTAs, red.global.add.f32 epilogue. */
 int dfol_gemm_bf16_tc_dgrad(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX, int64_t lddx,
                             int store_cols, int M, int N, int K, const void* h_saved, int64_t ldh, int mul_mode,
-                            void* stream);
+                            float keep, void* stream);
+/* keep (here, in dfol_pair_layer_dgrad_cluster and in dfol_table_layer_bwd_tc) = 1 - dropout p of the layer whose saved
+ * activation is passed: 1 = no dropout; < 1 = the saved tensor holds the activation AFTER dropout (0 where dropped,
+ * h / keep where kept), so act' is taken at saved * keep and the gradient carries the mask factor (saved != 0) / keep. */
 int dfol_gemm_bf16_tc_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
                             int64_t K, void* stream);
 /* same contraction with the M rows of the result split into up to three segments of seg_rows rows (multiple of 128)
@@ -134,7 +137,7 @@ int dfol_pair_layer_fwd_cluster(const void* A, int64_t lda, const void* B, int64
                                 int store_cols, const float* bias, int M, int N, int K, int act, void* stream);
 int dfol_pair_layer_dgrad_cluster(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX, int64_t lddx,
                                   int store_cols, int M, int N, int K, const void* h_saved, int64_t ldh, int mul_mode,
-                                  void* stream);
+                                  float keep, void* stream);
 
 /* fp32 -> bf16 cast with row padding: dst[r*ldd + c] = bf16(src[r*lds + c]) for c < cols, 0 for cols <= c < ldd */
 int dfol_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
@@ -286,10 +289,11 @@ int dfol_program_bwd_fast(const int32_t* instr, const int32_t* q_instr, const in
  */
 int dfol_dropout_scale(void* x, int64_t ld, int64_t rows, int cols, int is_bf16, uint64_t seed, int site, float p,
                        void* stream);
-/* backward of the gather: d_obj[t, c] += sum_o dpm[(t,o), c] + sum_s dpm[(s,t), width + c] (dpm already masked) */
-int dfol_pair_features_bwd(const float* dpm, int64_t ld, int width, float* d_obj, int64_t ldobj,
-                           const int32_t* pair_row, const int32_t* obj_row, const int32_t* img_n,
-                           const int32_t* obj_img, int64_t objects, void* stream);
+/* backward of the gather: d_obj[t, c] += sum_o dpm[(t,o), c] + sum_s dpm[(s,t), width + c] (dpm already masked; fp32 or
+ * bf16) + addend_bf16[t, c] (optional: the attribute chain's share of d obj in tensor-core mode) */
+int dfol_pair_features_bwd(const void* dpm, int64_t ld, int is_bf16, int width, float* d_obj, int64_t ldobj,
+                           const void* addend_bf16, int64_t ld_add, const int32_t* pair_row, const int32_t* obj_row,
+                           const int32_t* img_n, const int32_t* obj_img, int64_t objects, void* stream);
 int dfol_pair_features_dropout(const float* obj, int64_t ldobj, int width, int pos_col, void* out, int64_t ldout,
                                int out_cols, int is_bf16, const int32_t* pair_row, const int32_t* obj_row,
                                const int32_t* img_n, const int32_t* pair_img, int64_t pairs, uint64_t seed, int site,
@@ -360,7 +364,7 @@ int dfol_table_layer_bwd_tc(const float* g, const int32_t* slice_goff, const int
                             int max_slices, const float* ll, const int64_t* blk, const int32_t* stride,
                             const int32_t* row0, const int32_t* img_rows, const float* W, int64_t ldw,
                             const void* h_saved, int64_t ldh, int E, void* dZ, int64_t lddz, int out_cols, float* dW,
-                            float* db, float* dbelow, void* stream);
+                            float* db, float* dbelow, float keep, void* stream);
 
 /* Demand-driven relation table (tensor-core mode; replaces computing all nR columns of
  * ClassifierOracle.compute_all_log_likelihood_2, classifier_oracle.py:154, when the batch's programs are known):

@@ -156,8 +156,8 @@ def test_collater_attaches_compiled_programs():
     comp = ProgramCompiler(ont, relation_slots=True)
     pb = ProgramCollater(1, lambda qs: (feats, bidx), compiler=comp).collate(questions)[0]
     assert pb._dfol_counts == counts
-    cp = pb._dfol_compiled[False]
+    cp = next(iter(pb._dfol_compiled.values()))
     ref = comp.compile(pb, counts)
     assert (cp.instr == ref.instr).all() and (cp.q_instr == ref.q_instr).all() and cp.rel_slices == ref.rel_slices
     clone = pickle.loads(pickle.dumps(pb))
-    assert (clone._dfol_compiled[False].instr == cp.instr).all()
+    assert (next(iter(clone._dfol_compiled.values())).instr == cp.instr).all()

@@ -207,13 +207,31 @@ def test_dropout_with_trainable_oracle_fp32_gradients_match_oracle(name):
         assert err <= 2e-4 * g.abs().max() + 1e-7, ('fused', sd_keys[id(q)], float(err), float(g.abs().max()))
 
 
-def test_dropout_with_trainable_oracle_raises_in_tensor_core_mode():
+@pytest.mark.parametrize('terminal,n_max', [('and', 16), ('exist', 20), ('choose_rel', 14), ('two_same', 12),
+                                            ('verify_attrs', 16)])
+def test_dropout_with_trainable_oracle_tensor_core_matches_fp32_mode(terminal, n_max):
+    """Tensor-core mode, TRAINABLE oracle networks with dropout 0.1 at the reference's real dimensions: loss and all 12
+    parameter gradients against the fp32 engine run with the SAME seed (same masks; the fp32 engine is held to the
+    oracle above), within the bf16-mode gradient bar.  (Batches whose questions sit at probabilities of ~1e-6 are left
+    out: there fp32 log(1 - e^x) itself is only good to ~10 %, SURVEY.md §7, and the two engines -- and the oracle --
+    disagree by that much in the gradients; tools/dbg_tc_dropout2.py.)"""
     from test_gpu_tc_kernels import _programs_world
-    ont, dims, pbs = _programs_world('exist', 4, 8, True, seed=3)
-    interp = helpers.build_interpreter(ont, dims, seed=5, gemm_mode='bf16', dropout=0.1)
-    interp.train()
-    with pytest.raises(NotImplementedError):
-        interp([pbs[0].to_cuda(0)], True)
-    interp.eval()          # eval mode: nn.Dropout is the identity, nothing to refuse
-    with torch.no_grad():
-        interp([pbs[0].to_cuda(0)], False)
+    from dfol_vqa_b200.interpreter import FusedTrainStep
+    ont, dims, pbs = _programs_world(terminal, 12, n_max, True, seed=83)
+    out = {}
+    for mode in ('fp32', 'bf16'):
+        interp = helpers.build_interpreter(ont, dims, seed=5, gemm_mode=mode, emb_bias=-4.0, dropout=0.1)
+        interp._fixed_dropout_seed = 1717
+        interp.train()
+        step = FusedTrainStep(interp)
+        loss = float(step.forward_backward([pbs[0].to_cuda(0)]))
+        out[mode] = (loss, {k: step.grads[id(q)].clone() for k, q in zip(orc.PARAM_KEYS, interp.oracle_parameters())})
+    (l32, g32), (l16, g16) = out['fp32'], out['bf16']
+    assert abs(l16 - l32) <= 2e-2 * max(1.0, abs(l32)), (l16, l32)
+    for k in orc.PARAM_KEYS:
+        a, b = g16[k], g32[k]
+        scale = float(b.abs().max())
+        assert scale > 0 or float(a.abs().max()) == 0, k
+        # relative error of the whole tensor (bf16 operands, fp32 accumulation)
+        err = float((a - b).norm() / (b.norm() + 1e-20))
+        assert err <= 3e-2, (k, err, scale)

@@ -252,7 +252,7 @@ def test_gemm_bf16_tcgen05_dgrad(M, N, K, mode):
     Wt = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
     Hs = (torch.rand(M, N, generator=g) - 0.3).cuda().bfloat16()
     dX = torch.full((M, N), float('nan'), device='cuda', dtype=torch.bfloat16)
-    call('dfol_gemm_bf16_tc_dgrad', ptr(dZ), K, ptr(Wt), K, ptr(dX), N, 0, M, N, K, ptr(Hs), N, mode, stream_ptr())
+    call('dfol_gemm_bf16_tc_dgrad', ptr(dZ), K, ptr(Wt), K, ptr(dX), N, 0, M, N, K, ptr(Hs), N, mode, 1.0, stream_ptr())
     torch.cuda.synchronize()
     ref = dZ.double() @ Wt.double().t()
     h = Hs.double()
@@ -391,7 +391,8 @@ def test_pair_layer_dgrad_resident_gemm(M, N, K, mode, impl):
     Hs = (torch.rand(M, N, generator=g) - 0.3).cuda().bfloat16()
     dX = torch.full((M, N), float('nan'), device='cuda', dtype=torch.bfloat16)
     entry = 'dfol_pair_layer_dgrad_cluster' if impl == 'cluster' else 'dfol_pair_layer_dgrad_tc'
-    call(entry, ptr(dZ), K, ptr(Wt), K, ptr(dX), N, 0, M, N, K, ptr(Hs), N, mode, stream_ptr())
+    keep = (1.0,) if impl == 'cluster' else ()   # (the cluster entry point takes the dropout keep factor)
+    call(entry, ptr(dZ), K, ptr(Wt), K, ptr(dX), N, 0, M, N, K, ptr(Hs), N, mode, *keep, stream_ptr())
     torch.cuda.synchronize()
     ref = dZ.double() @ Wt.double().t()
     h = Hs.double()

@@ -127,7 +127,7 @@ def test_table_layer_bwd_tc(counts, slices_per_image):
              rows=i32(rows), W=W.cuda(), H2=H2.cuda())
     call('dfol_table_layer_bwd_tc', ptr(d['g']), ptr(d['goff']), ptr(d['cols']), ptr(d['wrow']), ptr(d['img_slice']),
          len(counts), max(rows), max(slices_per_image), ptr(d['ll']), ptr(d['blk']), ptr(d['stride']), ptr(d['row0']),
-         ptr(d['rows']), ptr(d['W']), E, ptr(d['H2']), ld, E, ptr(dZ), ld, ld, ptr(dW), ptr(db), ptr(dbelow),
+         ptr(d['rows']), ptr(d['W']), E, ptr(d['H2']), ld, E, ptr(dZ), ld, ld, ptr(dW), ptr(db), ptr(dbelow), 1.0,
          stream_ptr())
     torch.cuda.synchronize()
     h = H2[:, :E].double()

@@ -41,7 +41,7 @@ def fwd_cluster():
 
 
 def dgrad_cluster():
-    call('dfol_pair_layer_dgrad_cluster', ptr(dZ), 320, ptr(Wt), 320, ptr(dX), 256, 0, P, 256, 320, ptr(A), 256, 2,
+    call('dfol_pair_layer_dgrad_cluster', ptr(dZ), 320, ptr(Wt), 320, ptr(dX), 256, 0, P, 256, 320, ptr(A), 256, 2, 1.0,
          stream_ptr())
 
 
