@@ -70,6 +70,8 @@ def build_world(args, rank, device):
             extra = dict(attention_nets=[nets[k] for k in ('forward_attention_network', 'backward_attention_network',
                                                            'attention_output_network')],
                          freeze_oracle=True, dropout=args.dropout)
+        if args.train_dropout > 0 and not args.calibrate:
+            extra = dict(dropout=args.train_dropout)   # trainable oracle networks under dropout (both passes masked)
         interp = helpers.build_interpreter(ont, DIMS, seed=0, device=device, gemm_mode=args.gemm, emb_bias=EMB_BIAS,
                                            **extra)
     B = args.local_batch or wl['batch']
@@ -241,6 +243,8 @@ def main():
                     help="sample_config.yaml's training arrangement: frozen oracle networks with dropout, the "
                          'attention-transfer calibrator trains (not the default headline workload)')
     ap.add_argument('--dropout', type=float, default=0.1)
+    ap.add_argument('--train-dropout', type=float, default=0.0,
+                    help='train the oracle networks with this dropout probability (not the default headline workload)')
     args = ap.parse_args()
     if args.gemm is None:
         args.gemm = 'bf16'  # tensor-core mode (bf16 operands, fp32 accumulation); --gemm fp32 = parity mode
@@ -408,7 +412,9 @@ def main():
         'vs_baseline': None, 'dtype': 'f32' if args.gemm == 'fp32' else 'bf16', 'data': 'synthetic',
         'config': {'workload': '%s: %s' % (args.workload, wl['desc']),
                    'step': args.mode + (' (calibrator only: frozen oracle, dropout %.2f)' % args.dropout
-                                        if args.calibrate else ''), 'gemm_mode': args.gemm,
+                                        if args.calibrate else '') +
+                           (' (oracle networks trained under dropout %.2f)' % args.train_dropout
+                            if args.train_dropout > 0 and not args.calibrate else ''), 'gemm_mode': args.gemm,
                    'global_batch': global_q, 'objects_per_image': wl['n'], 'box_feature_dim': DIMS['box'],
                    'concepts': C, 'relations': nR, 'parallelism': 'dp%d (questions sharded by rank)' % world,
                    'l2': 'inputs larger than L2: per-step tables + activations %.1f GB >> 126 MB; %d distinct '
