@@ -153,9 +153,11 @@ class ProgramCompiler(object):
             gr[0] += len(cols) * r_stride[q]
             return off
 
-        def emit(q, op, flags=0, a0=-1, a1=-1, a2=-1, out=-1, ga0=-1, ga1=-1, grr=-1, mod=-1, mod2=-1):
-            prog[q].append((op, flags | hard if op >= K.OP_EXIST else flags, a0, a1, a2, out, ga0, ga1, grr, mod, mod2,
-                            0))
+        def emit(q, op, flags=0, a0=-1, a1=-1, a2=-1, out=-1, ga0=-1, ga1=-1, grr=-1, mod=-1, mod2=-1, soft=False):
+            # soft: query_attr, all_different and two_different call their inner operator WITHOUT forwarding hard_mode
+            # (batch_gqa_ops.py:306, :628, :703), so their quantifiers stay soft even under `hard_mode: True`
+            h = hard if (op >= K.OP_EXIST and not soft) else 0
+            prog[q].append((op, flags | h, a0, a1, a2, out, ga0, ga1, grr, mod, mod2, 0))
 
         modulated = self.modulated
         mod_plan = []                        # (slot, key, rows, base row), in row order
@@ -339,7 +341,7 @@ class ProgramCompiler(object):
                         for q in range(B):
                             start, cnt, cols = option_words(q, lists[q], 'attr')
                             emit(q, K.OP_CHOOSE_ATTR, fl, start, cnt, out=lp_num,
-                                 ga0=attr_slice(q, cols), mod=at(base, first[q]))
+                                 ga0=attr_slice(q, cols), mod=at(base, first[q]), soft=(name == 'query_attr'))
                             lp_num += cnt
                             seg.append(lp_num)
                             owner += [q] * cnt
@@ -351,7 +353,8 @@ class ProgramCompiler(object):
                         for q in range(B):
                             start, cnt, cols = option_words(q, lists[q], 'attr')
                             emit(q, op, fl, start, cnt, out=q,
-                                 ga0=attr_slice(q, cols), mod=at(base, first[q]), mod2=at(base2, first[q]))
+                                 ga0=attr_slice(q, cols), mod=at(base, first[q]), mod2=at(base2, first[q]),
+                                 soft=name.endswith('different'))
                         lp_num = B
                         result.update(kind=BINARY, lp_owner=list(range(B)))
                 elif name == 'choose_rel':

@@ -172,6 +172,11 @@ def exists_hard(att):
     return log_not(log_not(att).min(-1)[0])
 
 
+def for_all_hard(att):
+    # batch_base_types.py:104-112 with quantifier FOR_ALL: log_parametric_not(x, 0, 1) = safe_log(exp(x)) on both sides
+    return safe_log(safe_log(att.exp()).min(-1)[0].exp())
+
+
 # ------------------------------------------------------------------ the interpreter
 
 class OracleInterpreter(object):
@@ -363,7 +368,10 @@ class OracleInterpreter(object):
         return out
 
     def _terminal(self, name, attr, rel, inputs, args, give_answer, B, mods=None):
-        agg = lambda a: self._agg(a, give_answer)
+        # query_attr, all_different and two_different call their inner operator without forwarding hard_mode
+        # (batch_gqa_ops.py:306, :628, :703): their quantifiers stay soft under `hard_mode: True`
+        hard_ok = name not in ('query_attr', 'all_different', 'two_different')
+        agg = lambda a: self._agg(a, give_answer and hard_ok)
         mods = mods or {}
         if name in ('exist', 'end'):
             atts, names = inputs[0]
@@ -442,7 +450,8 @@ class OracleInterpreter(object):
             per_q = self._option_filter(attr, atts, option_lists, mod=mods.get('filter'))
             lps = []
             for q, xs in enumerate(per_q):
-                qk = [for_all(log_not(atts[q] + log_not(x))) for x in xs]
+                fa = for_all_hard if (give_answer and self.hard_mode and hard_ok) else for_all
+                qk = [fa(log_not(atts[q] + log_not(x))) for x in xs]
                 lps.append(log_not(log_not(torch.stack(qk)).sum()))
             lp = torch.stack(lps)
             if name == 'all_different':

@@ -98,7 +98,7 @@ def model_config(dims, dropout=0.0):
 
 
 def build_interpreter(ont, dims, state=None, device='cuda', gemm_mode='fp32', seed=0, emb_bias=None,
-                      attention_nets=None, freeze_oracle=False, dropout=0.0):
+                      attention_nets=None, freeze_oracle=False, dropout=0.0, hard_mode=False):
     """FastGQAInterpreter over freshly initialised (or fixture) oracle networks."""
     from dfol_vqa_b200.interpreter import FastBoxFeaturizer, FastClassifierOracle, FastGQAInterpreter
     from dfol_vqa_b200.networks import build_networks
@@ -115,7 +115,7 @@ def build_interpreter(ont, dims, state=None, device='cuda', gemm_mode='fp32', se
         for key in ('featurizer_network', 'attribute_network', 'relation_network', 'embedding_network'):
             nets[key].requires_grad_(False)
     fwd, bwd, out = attention_nets if attention_nets is not None else (None, None, None)
-    interp = FastGQAInterpreter('model', oracle, ont, featurizer, gemm_mode=gemm_mode,
+    interp = FastGQAInterpreter('model', oracle, ont, featurizer, gemm_mode=gemm_mode, hard_mode=hard_mode,
                                 attention_transfer_state_dim=0 if fwd is None else fwd.hidden_size,
                                 forward_attention_network=fwd, backward_attention_network=bwd,
                                 attention_output_network=out)

@@ -195,3 +195,44 @@ def test_return_trace_matches_oracle(terminal):
         for q, a in enumerate(atts):
             mine = entry._log_attention[q, starts[q]:starts[q + 1]].cpu()
             assert torch.allclose(mine, a, rtol=1e-5, atol=1e-5), (q, mine, a)
+
+
+@pytest.mark.parametrize('terminal', ['exist', 'and', 'verify_rel', 'query_attr', 'choose_rel', 'two_same', 'all_same',
+                                      'compare', 'all_different', 'two_different', 'verify_attrs', 'choose_attr', 'or'])
+def test_hard_mode_eval_matches_oracle(terminal):
+    """hard_mode (config `hard_mode: True`; min instead of sum in the quantifiers when answers are given,
+    batch_base_types.py:104-112): eval-mode log-probabilities and answers against the oracle; training-mode passes of the
+    same interpreter stay soft."""
+    path = [p for p in helpers.golden_files() if ('golden_%s_s1' % terminal) in p][0]
+    case = helpers.load_golden(path)
+    ont = helpers.ontology_of(case)
+    interp = helpers.build_interpreter(ont, case['dims'], case['state'], hard_mode=True)
+    host = helpers.program_batches_of(case)
+    pbs = helpers.to_cuda(host)
+    interp.eval()
+    with torch.no_grad():
+        result = interp(pbs, False)
+        soft = interp(pbs, True)['log_probability'].cpu()
+    params = {k: v.clone() for k, v in case['state'].items()}
+    ref = orc.OracleInterpreter(ont, params, hard_mode=True).run(host[0], is_training=False)
+    ref_lp = ref['log_probability']
+    lp = result['log_probability'].cpu()
+    if ref['type'] == 1 and terminal != 'compare':
+        ref_lp = _align(result['options'], ref['options'], ref_lp)
+    sat = (lp.exp() - ref_lp.exp()).abs() <= 5e-7
+    assert bool((((lp - ref_lp).abs() <= 2e-5 * ref_lp.abs() + 2e-6) | sat).all()), (lp, ref_lp)
+    assert [sorted(a) for a in result['answer']] == [sorted(a) for a in ref['answer']]
+    import os
+    rec = torch.load(os.path.join(helpers.GOLDEN_DIR, 'hard_eval_golden.pt'), weights_only=False)[os.path.basename(path)]
+    assert [sorted(a) for a in result['answer']] == [sorted(a) for a in rec['answer']]   # the reference's own run
+    ok, _ = helpers.close_to_reference(soft, case['ref32']['log_probability'] if ref['type'] != 1 or terminal == 'compare'
+                                       else _align(result['options'], case['ref32']['options'],
+                                                   case['ref32']['log_probability']),
+                                       case['ref64']['log_probability'] if ref['type'] != 1 or terminal == 'compare'
+                                       else _align(result['options'], case['ref32']['options'],
+                                                   case['ref64']['log_probability']))
+    assert ok
+    if terminal in ('exist', 'verify_rel', 'choose_attr'):
+        assert not torch.allclose(lp, soft, rtol=1e-4, atol=1e-5)   # hard and soft quantifiers really differ
+    if terminal in ('query_attr', 'all_different', 'two_different'):
+        assert torch.allclose(lp, soft, rtol=1e-6, atol=1e-7)       # ... except where the reference drops hard_mode

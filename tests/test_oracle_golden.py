@@ -88,3 +88,28 @@ def test_oracle_scene_tables():
     for b, r in enumerate(rel):
         n = r.shape[0]
         assert bool((r[torch.arange(n), torch.arange(n)] == -30.0).all())
+
+
+def test_oracle_hard_mode_matches_reference_golden():
+    """`hard_mode: True` eval runs of the reference (tests/golden/make_golden_hard.py): min-quantifiers, including the
+    operators that do NOT forward hard_mode to their inner operator (query_attr, all_different, two_different stay soft,
+    batch_gqa_ops.py:306, :628, :703)."""
+    import os
+    hard = torch.load(os.path.join(helpers.GOLDEN_DIR, 'hard_eval_golden.pt'), weights_only=False)
+    assert len(hard) >= 13
+    for name, rec in hard.items():
+        case = helpers.load_golden(os.path.join(helpers.GOLDEN_DIR, name))
+        ont = helpers.ontology_of(case)
+        pbs = helpers.program_batches_of(case)
+        params = {k: v.clone() for k, v in case['state'].items()}
+        with torch.no_grad():
+            res = orc.OracleInterpreter(ont, params, hard_mode=True).run(pbs[0], is_training=False)
+        ref_lp = rec['log_probability']
+        if rec['type'] == 1 and case['terminal'] != 'compare':
+            perm, start = [], 0
+            for mine, theirs in zip(res['options'], rec['options']):
+                perm += [start + theirs.index(m) for m in mine]
+                start += len(theirs)
+            ref_lp = ref_lp[perm]
+        assert torch.allclose(res['log_probability'], ref_lp, rtol=1e-5, atol=2e-6), (name, res['log_probability'], ref_lp)
+        assert [sorted(a) for a in res['answer']] == [sorted(a) for a in rec['answer']], name
