@@ -98,7 +98,8 @@ def model_config(dims, dropout=0.0):
 
 
 def build_interpreter(ont, dims, state=None, device='cuda', gemm_mode='fp32', seed=0, emb_bias=None,
-                      attention_nets=None, freeze_oracle=False, dropout=0.0, hard_mode=False):
+                      attention_nets=None, freeze_oracle=False, dropout=0.0, hard_mode=False, normalize=True,
+                      likelihood_threshold=0):
     """FastGQAInterpreter over freshly initialised (or fixture) oracle networks."""
     from dfol_vqa_b200.interpreter import FastBoxFeaturizer, FastClassifierOracle, FastGQAInterpreter
     from dfol_vqa_b200.networks import build_networks
@@ -110,12 +111,13 @@ def build_interpreter(ont, dims, state=None, device='cuda', gemm_mode='fp32', se
         nets['embedding_network']._network[1].bias.data.fill_(emb_bias)
     featurizer = FastBoxFeaturizer(nets['featurizer_network'])
     oracle = FastClassifierOracle(ont, nets['attribute_network'], nets['relation_network'], nets['embedding_network'],
-                                  normalize=True, cached=True)
+                                  normalize=normalize, cached=True)
     if freeze_oracle:
         for key in ('featurizer_network', 'attribute_network', 'relation_network', 'embedding_network'):
             nets[key].requires_grad_(False)
     fwd, bwd, out = attention_nets if attention_nets is not None else (None, None, None)
     interp = FastGQAInterpreter('model', oracle, ont, featurizer, gemm_mode=gemm_mode, hard_mode=hard_mode,
+                                likelihood_threshold=likelihood_threshold,
                                 attention_transfer_state_dim=0 if fwd is None else fwd.hidden_size,
                                 forward_attention_network=fwd, backward_attention_network=bwd,
                                 attention_output_network=out)

@@ -236,3 +236,45 @@ def test_hard_mode_eval_matches_oracle(terminal):
         assert not torch.allclose(lp, soft, rtol=1e-4, atol=1e-5)   # hard and soft quantifiers really differ
     if terminal in ('query_attr', 'all_different', 'two_different'):
         assert torch.allclose(lp, soft, rtol=1e-6, atol=1e-7)       # ... except where the reference drops hard_mode
+
+
+@pytest.mark.parametrize('terminal', ['choose_attr', 'query_attr', 'choose_rel', 'all_same', 'two_same'])
+def test_unnormalised_oracle_and_likelihood_threshold(terminal):
+    """`normalize_oracle: False` (no softmax over a question's options, classifier_oracle.py:22-42) and a non-zero
+    `likelihood_threshold` (answers need p > threshold, util.find_max_ind): training-mode log-probabilities + gradients
+    and eval answers against the oracle (which a live run holds to the reference with the same settings)."""
+    path = [p for p in helpers.golden_files() if ('golden_%s_s1' % terminal) in p][0]
+    case = helpers.load_golden(path)
+    ont = helpers.ontology_of(case)
+    interp = helpers.build_interpreter(ont, case['dims'], case['state'], normalize=False, likelihood_threshold=0.3)
+    host = helpers.program_batches_of(case)
+    pbs = helpers.to_cuda(host)
+    answers = [a for pb in pbs for a in pb._answers]
+    params = {k: v.clone().requires_grad_(True) for k, v in case['state'].items()}
+    oi = orc.OracleInterpreter(ont, params, normalize=False, likelihood_threshold=0.3)
+    ref = oi.run(host[0], is_training=True)
+    interp.train()
+    result = interp(pbs, True)
+    lp, ref_lp = result['log_probability'], ref['log_probability']
+    if ref['type'] == 1:
+        ref_lp = _align(result['options'], ref['options'], ref_lp)
+    sat = (lp.detach().cpu().exp() - ref_lp.detach().exp()).abs() <= 5e-7
+    assert bool((((lp.detach().cpu() - ref_lp.detach()).abs() <= 2e-5 * ref_lp.detach().abs() + 2e-6) | sat).all())
+    unnorm_differs = not torch.allclose(lp.detach().cpu(), case['ref32']['log_probability'] if ref['type'] != 1 else
+                                        _align(result['options'], case['ref32']['options'],
+                                               case['ref32']['log_probability']), rtol=1e-3, atol=1e-4)
+    assert unnorm_differs or terminal == 'two_same'
+    loss = orc.compute_loss([{'log_probability': lp, 'type': result['type'], 'options': result['options']}],
+                            [answers]) / len(answers)
+    loss.backward()
+    (orc.compute_loss([ref], [answers]) / len(answers)).backward()
+    keys = {id(p): k for k, p in interp.named_parameters()}
+    for p in interp.oracle_parameters():
+        g = params[keys[id(p)]].grad
+        g = g if g is not None else torch.zeros_like(params[keys[id(p)]])
+        assert (p.grad.cpu() - g).abs().max() <= 2e-4 * g.abs().max() + 1e-7, keys[id(p)]
+    interp.eval()
+    with torch.no_grad():
+        ev = interp(pbs, False)
+        ref_ev = oi.run(host[0], is_training=False)
+    assert [sorted(a) for a in ev['answer']] == [sorted(a) for a in ref_ev['answer']]

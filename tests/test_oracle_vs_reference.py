@@ -144,3 +144,39 @@ def test_drop_in_construction_with_attention_transfer():
     with torch.no_grad():
         mine_lp = orc.OracleInterpreter(run.ontology, params).run(ref_pb[0], True, modulations=mods)['log_probability']
     assert torch.allclose(mine_lp, ref_lp, rtol=2e-5, atol=2e-6), (mine_lp - ref_lp).abs().max()
+
+
+@pytest.mark.parametrize('overrides', [{'hard_mode': True}, {'normalize_oracle': False, 'likelihood_threshold': 0.3}],
+                         ids=['hard_mode', 'unnormalised_threshold'])
+def test_oracle_eval_options_match_reference_live(overrides):
+    """Config switches that the recorded training fixtures do not exercise -- `hard_mode`, `normalize_oracle: False`,
+    `likelihood_threshold` -- checked live: eval-mode log-probabilities and answers of every terminal operator."""
+    from ref_harness import ReferenceRun, synthetic_metadata
+    from dfol_vqa_b200 import synth
+    from dfol_vqa_b200.programs import ProgramCollater
+    dims = dict(box=40, feat=24, hidden=16, emb=20)
+    md = synthetic_metadata(96, 12, 4, 3, seed=0)
+    ont = helpers.ontology_of({'metadata': md, 'dims': dims})
+    for terminal in ('exist', 'and', 'or', 'verify_attrs', 'verify_rel', 'choose_attr', 'choose_rel', 'query_attr',
+                     'all_same', 'all_different', 'two_same', 'two_different', 'compare'):
+        questions = synth.make_questions(ont, 6, terminal, 0, 4, seed=21)
+        counts = synth.object_counts(6, 7, True, seed=21)
+        feats, bidx = synth.make_object_features(counts, dims['box'], seed=22)
+        run = ReferenceRun(md, dims, seed=21, config_overrides=overrides)
+        ev = run.forward(run.collate(questions, feats, bidx), is_training=False)
+        mine = ProgramCollater(1, helpers.slicing_source(feats, bidx)).collate(json.loads(json.dumps(questions)))
+        sd = run.state_dict()
+        params = {k: sd[k].clone() for k in orc.PARAM_KEYS}
+        with torch.no_grad():
+            res = orc.OracleInterpreter(ont, params, normalize=overrides.get('normalize_oracle', True),
+                                        likelihood_threshold=overrides.get('likelihood_threshold', 0.0),
+                                        hard_mode=overrides.get('hard_mode', False)).run(mine[0], is_training=False)
+        a, b = res['log_probability'], ev['log_probability']
+        if res['type'] == 1 and terminal != 'compare':
+            perm, start = [], 0
+            for x, y in zip(res['options'], ev['options']):
+                perm += [start + list(y).index(m) for m in x]
+                start += len(y)
+            b = b[perm]
+        assert torch.allclose(a, b, rtol=1e-5, atol=2e-6), (terminal, a, b)
+        assert [sorted(x) for x in res['answer']] == [sorted(x) for x in ev['answer']], terminal
