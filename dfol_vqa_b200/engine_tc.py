@@ -109,6 +109,12 @@ class TensorCorePath(object):
         return self._ops
 
     @staticmethod
+    def _slots_on_tensor_cores(cp):
+        import os
+        thr = int(os.environ.get('DFOL_SLOTS_TC_MIN', '1'))   # measured faster for every slot count (c1: 0.11 -> 0.07 ms)
+        return cp.max_slots >= thr
+
+    @staticmethod
     def _tc(A16, B16, C, N, Kp, bias, act, st, table=None):
         """C = epilogue(A16[:, :Kp] @ B16[:N, :Kp]^T) on the tensor cores (dfol_gemm_bf16_tc)."""
         M = A16.shape[0]
@@ -260,7 +266,11 @@ class TensorCorePath(object):
         # the activation of layer 2 is only materialised when the backward pass (or the dense table) needs it
         slots = cp is not None and cp.img_slot is not None
         # inference with few relation columns per image: layer 2 and the columns in one kernel, no activation store
-        fused = slots and not training and cp.max_slots <= 4 and dropout is None
+        # (opt-in: it saves the 377 MB H2 store of c1 but measures 0.38 ms against 0.19 + 0.11 ms for the cluster GEMM
+        # followed by the slot columns -- the slot FMAs sit on its TMEM-drain path)
+        import os
+        fused = (slots and not training and cp.max_slots <= 4 and dropout is None
+                 and os.environ.get('DFOL_FUSED_INFERENCE', '0') == '1')
         h2r = None if fused else bf(layout.P, p['Ep'])
         if slots:
             dc = self.engine.upload_programs(cp, dev)
@@ -278,10 +288,22 @@ class TensorCorePath(object):
                 if capi.trace is not None:
                     capi.next_meta = {'tag': 'rel_slots_fwd', 'bytes': 2.0 * layout.P * p['Ep'] * max(
                         1, (cp.max_slots + 7) // 8) + 4.0 * cp.rel_slot_size}
-                call('dfol_rel_slots_fwd', ptr(h2r), p['Ep'], E, ptr(w.emb.weight), w.emb.weight.stride(0),
-                     ptr(w.emb.bias), ptr(dc['slot_wrow']), ptr(dc['img_slot']), cp.max_slots, ptr(dc['slot_blk']),
-                     ptr(layout.rel_stride), ptr(layout.pair_row), ptr(layout.img_nn), ptr(layout.img_n), layout.B,
-                     layout.max_n ** 2, DEFAULT_LL, ptr(rel_ll), st)
+                if self._slots_on_tensor_cores(cp):
+                    # grouped tcgen05 GEMM: the activation is read once whatever the number of slots
+                    if capi.trace is not None:
+                        capi.next_meta = {'tag': 'rel_slots_fwd_tc', 'bytes': 2.0 * layout.P * p['Ep'] * max(
+                            1, (cp.max_slots + 15) // 16) + 4.0 * cp.rel_slot_size}
+                    wb = bf(16 * layout.B, p['Ep'])
+                    call('dfol_rel_slots_fwd_tc', ptr(h2r), p['Ep'], layout.P, E, p['Ep'], ptr(w.emb.weight),
+                         w.emb.weight.stride(0), ptr(w.emb.bias), ptr(dc['slot_wrow']), ptr(dc['img_slot']),
+                         cp.max_slots, ptr(dc['slot_blk']), ptr(layout.rel_stride), ptr(layout.pair_row),
+                         ptr(layout.img_nn), ptr(layout.img_n), layout.B, layout.max_n ** 2, DEFAULT_LL, ptr(wb),
+                         ptr(rel_ll), st)
+                else:
+                    call('dfol_rel_slots_fwd', ptr(h2r), p['Ep'], E, ptr(w.emb.weight), w.emb.weight.stride(0),
+                         ptr(w.emb.bias), ptr(dc['slot_wrow']), ptr(dc['img_slot']), cp.max_slots,
+                         ptr(dc['slot_blk']), ptr(layout.rel_stride), ptr(layout.pair_row), ptr(layout.img_nn),
+                         ptr(layout.img_n), layout.B, layout.max_n ** 2, DEFAULT_LL, ptr(rel_ll), st)
             else:
                 # inference: layer 2 + relation columns in one persistent tcgen05 kernel; the P x E activation is
                 # consumed in registers and never written

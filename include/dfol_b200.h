@@ -323,6 +323,15 @@ int dfol_mod_out_fwd(const float* fh, const float* bh, const int64_t* owner, con
 int dfol_mod_out_bwd(const float* d_mods, const float* mods, const int64_t* owner, const float* w_out, int S, int n_out,
                      float* dzo, float* d_fh, float* d_bh, int rows, void* stream);
 
+/* dfol_rel_slots_fwd on the tensor cores: a grouped GEMM, image b multiplies its activation rows by its own <= 16 slot
+ * rows of W (gathered to bf16 into wb_workspace, 16 * image_num * K bf16) per pass; the activation (bf16, total_rows x K
+ * valid columns, zero K padding) is read once whatever the number of slots.  Same tables and layout as dfol_rel_slots_fwd. */
+int dfol_rel_slots_fwd_tc(const void* h_saved, int64_t ldh, int64_t total_rows, int E, int K, const float* W, int64_t ldw,
+                          const float* bias, const int32_t* slot_wrow, const int32_t* img_slot, int max_slots,
+                          const int64_t* slot_blk, const int32_t* stride, const int32_t* row0, const int32_t* img_rows,
+                          const int32_t* img_n, int image_num, int max_rows, float diag_value, void* wb_workspace,
+                          float* ll, void* stream);
+
 /* Loss of VQATrainer._compute_loss (nsvqa/train/trainer.py:181-262) and its derivative w.r.t. lp.
  * kind 0 BINARY: BCE(exp(lp), target) summed; 1 QUERY: sum_q slog(sum_{k in q} e^{lp_k}) - sum_k target_k lp_k
  * (seg[q]..seg[q+1] are question q's predicates); 2 STATEMENT: -sum lp.  loss_out[0] += scale * loss,

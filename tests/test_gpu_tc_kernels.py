@@ -335,3 +335,37 @@ def test_bf16_staged_features_are_bit_identical():
     fp32 = helpers.build_interpreter(ont, dims, seed=5, gemm_mode='fp32', emb_bias=-4.0)
     with pytest.raises(RuntimeError):
         fp32([staged.to_cuda(0)], True)
+
+
+@pytest.mark.parametrize('terminal,n_max,ragged', [('chain', 48, False), ('chain', 37, True), ('verify_rel', 100, False),
+                                                   ('choose_rel', 5, True)])
+def test_rel_slots_tensor_core_kernel_matches_simt(terminal, n_max, ragged, monkeypatch):
+    """dfol_rel_slots_fwd_tc (grouped tcgen05 GEMM: every image against its own slot rows, bf16 weights) against
+    dfol_rel_slots_fwd (fp32 weights, SIMT dot products) on the same stored activation: the compact relation tables."""
+    from dfol_vqa_b200.engine import SceneLayout
+    ont, dims, pbs = _programs_world(terminal, 12, n_max, ragged, seed=43)
+    interp = helpers.build_interpreter(ont, dims, seed=5, gemm_mode='bf16', emb_bias=-4.0)
+    pb = pbs[0].to_cuda(0)
+    cp = interp.compiled(pb, False)
+    counts = interp._object_counts(pb)
+    layout = SceneLayout.get(counts, interp._weights.emb.weight.shape[0], len(ont._relation_index), torch.device('cuda', 0))
+    tables = {}
+    for name, thr in (('tc', '1'), ('simt', '99')):
+        monkeypatch.setenv('DFOL_SLOTS_TC_MIN', thr)
+        with torch.no_grad():
+            scene = interp._engine.build_scene(pb._object_features.float(), layout, keep_for_backward=True, cp=cp)
+        torch.cuda.synchronize()
+        tables[name] = scene.rel_ll.clone()
+    # valid entries: n_b^2 per slot (slices are padded to a multiple of 4 floats; the padding is never read)
+    valid = torch.zeros(tables['tc'].numel(), dtype=torch.bool)
+    for b, n in enumerate(counts):
+        stride = int(layout.r_stride_host[b])
+        for j in range(int(cp.img_slot[b + 1] - cp.img_slot[b])):
+            off = int(cp.slot_blk[b]) + j * stride
+            valid[off:off + n * n] = True
+    valid = valid.cuda()
+    a, b = tables['tc'][valid], tables['simt'][valid]
+    assert a.numel() > 0 and bool(torch.isfinite(a).all())
+    off_diag = b != -30.0
+    assert bool(((a == -30.0) == (b == -30.0)).all())   # self pairs agree exactly
+    assert float((a - b)[off_diag].abs().max()) <= 2e-2 + 2e-2 * float(b[off_diag].abs().max())
