@@ -70,6 +70,8 @@ _SIGNATURES = {
     'dfol_pair_layer_dgrad_cluster': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P,
                                               c_int64, c_int, c_float, P]),
     'dfol_cast_jobs': (c_int, [P, c_int, c_int64, P]),
+    'dfol_pair_hidden_fwd_mma': (c_int, [P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int, P, P, P, P, c_int,
+                                         c_int, P, P]),
     'dfol_rel_slots_fwd_tc': (c_int, [P, c_int64, c_int64, c_int, c_int, P, c_int64, P, P, P, c_int, P, P, P, P, P, c_int,
                                       c_int, c_float, P, P, P]),
     'dfol_lstm_cell_fwd': (c_int, [P, c_int64, P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int, P]),

@@ -237,11 +237,26 @@ class TensorCorePath(object):
             uv = torch.empty(T, 2 * H, device=dev, dtype=torch.float32)
             self._tc(obj16, ops.wuv, uv, 2 * H, p['Op'], None, K.ACT_NONE, st)
             geo = torch.empty(layout.P, 4, device=dev, dtype=torch.float32) if training else None
-            if capi.trace is not None:
-                capi.next_meta = {'tag': 'pair_hidden_fwd_tc', 'bytes': 2.0 * layout.P * p['Hp']}
-            call('dfol_pair_hidden_fwd_tc', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo,
-                 ptr(first.weight[:, 2 * ldo:]), first.weight.stride(0), ptr(first.bias), ptr(h1r), p['Hp'], H,
-                 ptr(geo), ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_n), layout.B, layout.max_n, st)
+            import os
+            if 2 * layout.max_n + 5 <= 256 and H <= 256 and os.environ.get('DFOL_PAIR_HIDDEN_MMA', '0') == '1':
+                # one-hot grouped GEMM on the tensor cores (pair_hidden_mma.cu).  Opt-in: correct, but its first version
+                # (one tile per CTA, row-per-lane 32-byte stores) measures 0.181 ms against 0.163 ms for the SIMT kernel at
+                # c1 and 1.13 against 0.63 ms at c3 (192 KB of shared memory: one CTA per SM, no overlap of its phases)
+                if capi.trace is not None:
+                    capi.next_meta = {'tag': 'pair_hidden_fwd_mma', 'bytes': 2.0 * layout.P * p['Hp']}
+                Kp1 = _roundup(2 * layout.max_n + 5, 64)
+                bm = bf(layout.B * H, Kp1)
+                call('dfol_pair_hidden_fwd_mma', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo,
+                     ptr(first.weight[:, 2 * ldo:]), first.weight.stride(0), ptr(first.bias), ptr(h1r), p['Hp'], H,
+                     ptr(geo), ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_n), layout.B, layout.max_n,
+                     ptr(bm), st)
+            else:
+                if capi.trace is not None:
+                    capi.next_meta = {'tag': 'pair_hidden_fwd_tc', 'bytes': 2.0 * layout.P * p['Hp']}
+                call('dfol_pair_hidden_fwd_tc', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo,
+                     ptr(first.weight[:, 2 * ldo:]), first.weight.stride(0), ptr(first.bias), ptr(h1r), p['Hp'], H,
+                     ptr(geo), ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_n), layout.B, layout.max_n,
+                     st)
         else:
             # an independent mask per pair element breaks the U[s] + V[o] factorisation: the first layer runs as one
             # tcgen05 GEMM over the materialised, masked pair matrix (the reference's formulation,

@@ -323,6 +323,13 @@ int dfol_mod_out_fwd(const float* fh, const float* bh, const int64_t* owner, con
 int dfol_mod_out_bwd(const float* d_mods, const float* mods, const int64_t* owner, const float* w_out, int S, int n_out,
                      float* dzo, float* d_fh, float* d_bh, int rows, void* stream);
 
+/* dfol_pair_hidden_fwd_tc on the tensor cores: per 128-row tile the one-hot operand [e_s | e_o | geo | 1] is generated in
+ * shared memory and multiplied by the image's own operand [U_b; V_b; Wg; bias] (gathered to bf16 into operand_workspace,
+ * image_num * H * roundup(2 max_n + 5, 64) bf16), then ELU and the bf16 store.  max_n <= 125, H <= 256 (H % 16 == 0). */
+int dfol_pair_hidden_fwd_mma(const float* uv, int64_t lduv, const float* obj_pos, int64_t ldpos, const float* wg,
+                             int64_t ldw, const float* bias, void* h_out, int64_t ldh, int H, void* geo_out,
+                             const int32_t* pair_row, const int32_t* obj_row, const int32_t* img_n, int image_num,
+                             int max_n, void* operand_workspace, void* stream);
 /* dfol_rel_slots_fwd on the tensor cores: a grouped GEMM, image b multiplies its activation rows by its own <= 16 slot
  * rows of W (gathered to bf16 into wb_workspace, 16 * image_num * K bf16) per pass; the activation (bf16, total_rows x K
  * valid columns, zero K padding) is read once whatever the number of slots.  Same tables and layout as dfol_rel_slots_fwd. */

@@ -369,3 +369,38 @@ def test_rel_slots_tensor_core_kernel_matches_simt(terminal, n_max, ragged, monk
     off_diag = b != -30.0
     assert bool(((a == -30.0) == (b == -30.0)).all())   # self pairs agree exactly
     assert float((a - b)[off_diag].abs().max()) <= 2e-2 + 2e-2 * float(b[off_diag].abs().max())
+
+
+@pytest.mark.parametrize('counts', [[48] * 6, [5, 9, 3, 7, 1, 2], [100, 37, 125], [64, 63, 65]])
+def test_pair_hidden_mma_matches_simt(counts):
+    """dfol_pair_hidden_fwd_mma (one-hot grouped tcgen05 GEMM: U, V, Wg and the bias as bf16 operands) against
+    dfol_pair_hidden_fwd_tc (fp32 sums, one bf16 rounding) on the same U|V: the bf16 hidden layer and the geometry table."""
+    from dfol_vqa_b200.capi import call, ptr, stream_ptr
+    from dfol_vqa_b200.engine import SceneLayout
+    H, F = 256, 32
+    T, P = sum(counts), sum(c * c for c in counts)
+    g = torch.Generator().manual_seed(sum(counts))
+    uv = (torch.randn(T, 2 * H, generator=g) * 0.7).cuda()
+    obj = torch.rand(T, F + 4, generator=g).cuda()
+    wg = (torch.randn(H, 4, generator=g) * 0.5).cuda()
+    bias = (torch.randn(H, generator=g) * 0.3).cuda()
+    layout = SceneLayout.get(counts, 10, 4, torch.device('cuda', 0))
+    outs = {}
+    for name in ('simt', 'mma'):
+        h = torch.full((P, H), float('nan'), device='cuda', dtype=torch.bfloat16)
+        geo = torch.full((P, 4), float('nan'), device='cuda')
+        args = (ptr(uv), 2 * H, ptr(obj[:, F:]), F + 4, ptr(wg), 4, ptr(bias), ptr(h), H, H, ptr(geo),
+                ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_n), len(counts), max(counts))
+        if name == 'mma':
+            ws = torch.empty(len(counts) * H, (2 * max(counts) + 5 + 63) // 64 * 64, device='cuda', dtype=torch.bfloat16)
+            call('dfol_pair_hidden_fwd_mma', *args, ptr(ws), stream_ptr())
+        else:
+            call('dfol_pair_hidden_fwd_tc', *args, stream_ptr())
+        torch.cuda.synchronize()
+        outs[name] = (h.float(), geo)
+    (ha, ga), (hb, gb) = outs['mma'], outs['simt']
+    assert bool(torch.isfinite(ha).all())
+    assert torch.equal(ga, gb)
+    # operands rounded to bf16 before the sum (|U|, |V| ~ 2): a few bf16 ulps of the operands
+    assert float((ha - hb).abs().max()) <= 4e-2, float((ha - hb).abs().max())
+    assert float((ha - hb).abs().mean()) <= 4e-3
