@@ -56,7 +56,7 @@ class CompiledPrograms(object):
     __slots__ = ('instr', 'q_instr', 'opts', 'lp_num', 'kind', 'options', 'seg', 'names', 'question_num',
                  'g_attr_size', 'g_rel_size', 'attr_slices', 'rel_slices', 'terminal', 'lp_owner', 'device_cache',
                  'alg_bytes', 'slot_wrow', 'img_slot', 'slot_blk', 'rel_slot_size', 'max_slots', 'mod_plan',
-                 'mod_descs', 'mod_rows', 'slot_after', 'slot_names', 'mod_cache')
+                 'mod_descs', 'mod_rows', 'slot_after', 'slot_names', 'mod_cache', 'mod_tok', 'mod_opcol', 'mod_relflag')
 
 
 class ProgramCompiler(object):
@@ -442,6 +442,23 @@ class ProgramCompiler(object):
         cp.slot_after = np.asarray(slot_after, dtype=np.int64).reshape(len(slot_after), B)
         cp.slot_names = slot_names
         cp.mod_cache = {}
+        # per modulation row: vocabulary index of its predicate token (-1 = blank), operator class and attribute /
+        # relation flag -- what the calibrator's feature rows are made of (BatchOperatorBase._get_features,
+        # batch_base_ops.py:265-273); built here so that it is collate-time work like the bytecode
+        from .modulator import OPS_INDEX
+        tok = np.full(max(mod_rows[0], 1), -1, dtype=np.int64)
+        opcol = np.zeros(max(mod_rows[0], 1), dtype=np.int64)
+        relflag = np.zeros(max(mod_rows[0], 1), dtype=np.float32)
+        for slot_i, key, rows, base in mod_plan:
+            d = mod_descs[slot_i]
+            tokens = d['select'] if key == 'select' else (d['relate'][0] if key == 'relate' else d['filter'][0])
+            opcol[base:base + rows] = OPS_INDEX[d['op']]
+            relflag[base:base + rows] = 1.0 if key == 'relate' else 0.0
+            ids = tok[base:base + rows]
+            for r, t in enumerate(tokens):
+                if t is not None:
+                    ids[r] = self._attr_word(t)[0]   # (vocabulary index of the bare token; relations included)
+        cp.mod_tok, cp.mod_opcol, cp.mod_relflag = tok, opcol, relflag
         cp.mod_plan = mod_plan
         cp.mod_descs = mod_descs
         cp.mod_rows = mod_rows[0]

@@ -20,7 +20,7 @@ import torch
 from . import capi
 from .capi import call, ptr
 from .engine import gemm_f32
-from .modulator import AttentionTransfer
+from .modulator import OPS_NUM, AttentionTransfer
 
 
 class _State(object):
@@ -41,9 +41,21 @@ class NativeAttentionTransfer(object):
         self.n_out = self.lin.weight.shape[0]
         assert self.S <= 64, 'attention_transfer_state_dim must be <= 64'
         self._torch = AttentionTransfer(forward_network, backward_network, output_network, ontology)
+        self._tables = {}
 
     def parameters(self):
         return self._torch.parameters()
+
+    def _embedding_table(self, dev):
+        """(vocabulary, E) word-embedding table on the device (ontology.get_embeddings of every vocabulary entry: what
+        ClassifierOracle.get_embedding returns per token, base_oracle.py:45-55)."""
+        key = str(dev)
+        hit = self._tables.get(key)
+        if hit is None:
+            ont = self._torch.ont
+            emb = np.asarray(ont.get_embeddings(ont._vocabulary['idx_to_arg']), dtype=np.float32)
+            hit = self._tables[key] = torch.from_numpy(emb).to(dev)
+        return hit
 
     # ---- program-only data of a compiled batch (cached with the bytecode)
 
@@ -52,21 +64,19 @@ class NativeAttentionTransfer(object):
         hit = cp.mod_cache.get(key)
         if hit is not None:
             return hit
+        # feature rows [one-hot operator | attribute/relation flag | word embedding] assembled on the device from the
+        # compiler's per-row indices and the vocabulary embedding table (index plumbing; blank rows stay all-zero)
         I = self.fwd.input_size
-        feats = np.zeros((max(cp.mod_rows, 1), I), dtype=np.float32)
-        base_of = {}
-        ref = torch.zeros(1)
-        for slot_i, skey, rows, base in cp.mod_plan:
-            d = cp.mod_descs[slot_i]
-            if skey == 'select':
-                tokens, flag = d['select'], 0.0
-            elif skey == 'relate':
-                tokens, flag = d['relate'][0], 1.0
-            else:
-                tokens, flag = d['filter'][0], 0.0
-            assert len(tokens) == rows
-            feats[base:base + rows] = self._torch._build_features(d['op'], tokens, flag, ref).numpy()
-            base_of[(slot_i, skey)] = (base, rows)
+        table = self._embedding_table(dev)
+        tok = torch.from_numpy(cp.mod_tok).to(dev)
+        live = tok >= 0
+        R = tok.shape[0]
+        feats = torch.zeros(R, I, device=dev, dtype=torch.float32)
+        rows = live.nonzero().flatten()
+        feats[rows, torch.from_numpy(cp.mod_opcol).to(dev)[rows]] = 1.0
+        feats[rows, OPS_NUM] = torch.from_numpy(cp.mod_relflag).to(dev)[rows]
+        feats[rows, OPS_NUM + 1:] = table[tok[rows]]
+        base_of = {(slot_i, skey): (base, n) for slot_i, skey, n, base in cp.mod_plan}
 
         def to_dev(a, dtype):
             return torch.as_tensor(np.asarray(a, dtype=dtype)).to(dev)
@@ -79,7 +89,7 @@ class NativeAttentionTransfer(object):
                     owners[(i, k)] = to_dev(v[1], np.int64)
             if d['mask'] is not None and any(m <= 0 for m in d['mask']):
                 masks[i] = to_dev(d['mask'], np.float32)
-        hit = {'feats': torch.from_numpy(feats).to(dev), 'base': base_of, 'owners': owners, 'masks': masks}
+        hit = {'feats': feats, 'base': base_of, 'owners': owners, 'masks': masks}
         cp.mod_cache[key] = hit
         return hit
 
