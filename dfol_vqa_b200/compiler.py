@@ -53,10 +53,88 @@ def _roundup4(x):
 class CompiledPrograms(object):
     """Bytecode + result metadata of one program batch."""
 
+    def pack_tables(self):
+        _pack_tables(self)
+
     __slots__ = ('instr', 'q_instr', 'opts', 'lp_num', 'kind', 'options', 'seg', 'names', 'question_num',
                  'g_attr_size', 'g_rel_size', 'attr_slices', 'rel_slices', 'terminal', 'lp_owner', 'device_cache',
                  'alg_bytes', 'slot_wrow', 'img_slot', 'slot_blk', 'rel_slot_size', 'max_slots', 'mod_plan',
-                 'mod_descs', 'mod_rows', 'slot_after', 'slot_names', 'mod_cache', 'mod_tok', 'mod_opcol', 'mod_relflag')
+                 'mod_descs', 'mod_rows', 'slot_after', 'slot_names', 'mod_cache', 'mod_tok', 'mod_opcol', 'mod_relflag', 'blob', 'blob_layout', 'slice_meta')
+
+
+def _slice_table(slices, B):
+    """Per-image grouped slice tables of dfol_table_layer_bwd* from (question, column, g offset[, W row]) tuples."""
+    if slices:
+        arr = np.asarray(slices, dtype=np.int64)
+        arr = arr[np.argsort(arr[:, 0], kind='stable')]
+        counts = np.bincount(arr[:, 0], minlength=B)
+    else:
+        arr = np.zeros((0, 4), dtype=np.int64)
+        counts = np.zeros(B, dtype=np.int64)
+    img_slice = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    pad = arr if arr.shape[0] else np.zeros((1, 4), dtype=np.int64)
+    wrow = pad[:, 3] if pad.shape[1] > 3 else pad[:, 1]
+    tables = {'goff': pad[:, 2].astype(np.int32), 'col': pad[:, 1].astype(np.int32), 'wrow': wrow.astype(np.int32),
+              'img': pad[:, 0].astype(np.int32), 'img_slice': img_slice}
+    meta = {'count': int(arr.shape[0]), 'max_per_image': int(counts.max()) if counts.size else 0}
+    return tables, meta
+
+
+def _pack_tables(cp):
+    """Everything the kernels read of a compiled batch -- bytecode, option words, result segments, relation-slot tables,
+    the per-image slice tables of the table-layer backward -- in ONE byte blob (16-byte aligned sections): one
+    host->device copy per batch instead of ~20 small ones.  Built at compile (= collate) time."""
+    B = cp.question_num
+    arrays = {'instr': cp.instr, 'q_instr': cp.q_instr, 'opts': cp.opts}
+    if cp.seg is not None:
+        arrays['seg'] = cp.seg
+    if cp.img_slot is not None:
+        arrays.update(slot_wrow=cp.slot_wrow, img_slot=cp.img_slot, slot_blk=cp.slot_blk)
+    cp.slice_meta = {}
+    for key, slices in (('attr_slices', cp.attr_slices), ('rel_slices', cp.rel_slices)):
+        tables, meta = _slice_table(slices, B)
+        cp.slice_meta[key] = meta
+        for name, a in tables.items():
+            arrays[key + '.' + name] = a
+    if cp.mod_rows > 0:  # calibrator: per-row token / operator / flag indices, option owners and slot masks
+        arrays.update({'mod_tok': cp.mod_tok, 'mod_opcol': cp.mod_opcol, 'mod_relflag': cp.mod_relflag})
+        for i, d in enumerate(cp.mod_descs):
+            for k in ('filter', 'relate'):
+                v = d.get(k)
+                if v is not None and v[1] is not None:
+                    arrays['mod_owner:%d:%s' % (i, k)] = np.asarray(v[1], dtype=np.int64)
+            if d['mask'] is not None and any(m <= 0 for m in d['mask']):
+                arrays['mod_mask:%d' % i] = np.asarray(d['mask'], dtype=np.float32)
+    layout, off = {}, 0
+    for name, a in arrays.items():
+        a = np.ascontiguousarray(a)
+        arrays[name] = a
+        layout[name] = (off, a.nbytes, a.dtype, a.shape)
+        off += (a.nbytes + 15) // 16 * 16
+    blob = np.zeros(max(off, 16), dtype=np.uint8)
+    for name, a in arrays.items():
+        o, nb = layout[name][0], layout[name][1]
+        blob[o:o + nb] = a.view(np.uint8).reshape(-1)
+    cp.blob, cp.blob_layout = blob, layout
+
+
+def upload_tables(cp, device):
+    """Device copies of the tables of a CompiledPrograms (cached on the object): ONE copy of the packed blob (pinned when
+    the batch was pinned; issued on the current stream), then typed views."""
+    import torch
+    if cp.device_cache is None or cp.device_cache['device'] != device:
+        host = cp.blob if isinstance(cp.blob, torch.Tensor) else torch.from_numpy(cp.blob)
+        blob = host.to(device, non_blocking=True)
+        cache = {'device': device, 'blob': blob}
+        for name, (off, nbytes, dtype, shape) in cp.blob_layout.items():
+            view = blob[off:off + nbytes].view(getattr(torch, np.dtype(dtype).name)).view(*shape)
+            if '.' in name:
+                key, sub = name.split('.')
+                cache.setdefault(key, dict(cp.slice_meta[key]))[sub] = view
+            else:
+                cache[name] = view
+        cp.device_cache = cache
+    return cp.device_cache
 
 
 class ProgramCompiler(object):
@@ -479,4 +557,5 @@ class ProgramCompiler(object):
         else:
             cp.img_slot = cp.slot_wrow = cp.slot_blk = None
             cp.rel_slot_size = cp.max_slots = 0
+        cp.pack_tables()
         return cp

@@ -251,17 +251,9 @@ class ReasoningEngine(object):
         return sc
 
     def upload_programs(self, cp, device):
-        """Device copies of the bytecode of a CompiledPrograms (cached on the object)."""
-        if cp.device_cache is None or cp.device_cache['device'] != device:
-            def dev(a):
-                return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
-            cache = {'device': device, 'instr': dev(cp.instr), 'q_instr': dev(cp.q_instr), 'opts': dev(cp.opts)}
-            if cp.seg is not None:
-                cache['seg'] = dev(cp.seg)
-            if cp.img_slot is not None:
-                cache.update(slot_wrow=dev(cp.slot_wrow), img_slot=dev(cp.img_slot), slot_blk=dev(cp.slot_blk))
-            cp.device_cache = cache
-        return cp.device_cache
+        """Device copies of the tables of a CompiledPrograms (compiler.upload_tables: one packed copy, cached)."""
+        from .compiler import upload_tables
+        return upload_tables(cp, device)
 
     def run_programs(self, cp, scene, save_tape=True):
         """Executes the compiled programs; returns lp (cp.lp_num,) and the tape (or None).  ``scene.mods`` (optional,
@@ -286,29 +278,8 @@ class ReasoningEngine(object):
     # ------------------------------------------------------------------------------------------ backward
 
     def _slice_tables(self, slices, B, device, key, cp):
-        """Per-image grouped slice tables for dfol_table_layer_bwd."""
-        cache = cp.device_cache
-        if key in cache:
-            return cache[key]
-        if slices:
-            arr = np.asarray(slices, dtype=np.int64)  # (question, column, g offset[, W row])
-            order = np.argsort(arr[:, 0], kind='stable')
-            arr = arr[order]
-            counts = np.bincount(arr[:, 0], minlength=B)
-        else:
-            arr = np.zeros((0, 4), dtype=np.int64)
-            counts = np.zeros(B, dtype=np.int64)
-        img_slice = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
-
-        def dev(a):
-            return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
-        pad = arr if arr.shape[0] else np.zeros((1, 4), dtype=np.int64)
-        wrow = pad[:, 3] if pad.shape[1] > 3 else pad[:, 1]
-        out = {'goff': dev(pad[:, 2].astype(np.int32)), 'col': dev(pad[:, 1].astype(np.int32)),
-               'wrow': dev(wrow.astype(np.int32)), 'img': dev(pad[:, 0].astype(np.int32)), 'img_slice': dev(img_slice), 'count': int(arr.shape[0]),
-               'max_per_image': int(counts.max()) if counts.size else 0}
-        cache[key] = out
-        return out
+        """Per-image grouped slice tables for dfol_table_layer_bwd* (packed at compile time, uploaded with the bytecode)."""
+        return self.upload_programs(cp, device)[key]
 
     def program_backward(self, cp, scene, tape, d_lp):
         """Backward interpreter: compact gradient slices w.r.t. the raw attribute / relation table entries."""

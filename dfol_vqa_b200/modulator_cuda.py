@@ -66,29 +66,25 @@ class NativeAttentionTransfer(object):
             return hit
         # feature rows [one-hot operator | attribute/relation flag | word embedding] assembled on the device from the
         # compiler's per-row indices and the vocabulary embedding table (index plumbing; blank rows stay all-zero)
+        from .compiler import upload_tables
         I = self.fwd.input_size
         table = self._embedding_table(dev)
-        tok = torch.from_numpy(cp.mod_tok).to(dev)
-        live = tok >= 0
+        tabs = upload_tables(cp, dev)   # (already on the device when the batch was staged with its features)
+        tok = tabs['mod_tok']
         R = tok.shape[0]
+        live = (tok >= 0).to(torch.float32)           # (no nonzero(): nothing here synchronises with the host)
         feats = torch.zeros(R, I, device=dev, dtype=torch.float32)
-        rows = live.nonzero().flatten()
-        feats[rows, torch.from_numpy(cp.mod_opcol).to(dev)[rows]] = 1.0
-        feats[rows, OPS_NUM] = torch.from_numpy(cp.mod_relflag).to(dev)[rows]
-        feats[rows, OPS_NUM + 1:] = table[tok[rows]]
+        feats[torch.arange(R, device=dev), tabs['mod_opcol']] = live
+        feats[:, OPS_NUM] = tabs['mod_relflag'] * live
+        feats[:, OPS_NUM + 1:] = table[tok.clamp(min=0)] * live[:, None]
         base_of = {(slot_i, skey): (base, n) for slot_i, skey, n, base in cp.mod_plan}
-
-        def to_dev(a, dtype):
-            return torch.as_tensor(np.asarray(a, dtype=dtype)).to(dev)
-
         owners, masks = {}, {}
-        for i, d in enumerate(cp.mod_descs):
-            for k in ('filter', 'relate'):
-                v = d.get(k)
-                if v is not None and v[1] is not None:
-                    owners[(i, k)] = to_dev(v[1], np.int64)
-            if d['mask'] is not None and any(m <= 0 for m in d['mask']):
-                masks[i] = to_dev(d['mask'], np.float32)
+        for name, view in tabs.items():
+            if name.startswith('mod_owner:'):
+                _, i, k = name.split(':')
+                owners[(int(i), k)] = view
+            elif name.startswith('mod_mask:'):
+                masks[int(name.split(':')[1])] = view
         hit = {'feats': feats, 'base': base_of, 'owners': owners, 'masks': masks}
         cp.mod_cache[key] = hit
         return hit

@@ -12,14 +12,23 @@ import torch
 
 class HostStepPipeline(object):
 
-    def __init__(self, step_fn, device):
-        """``step_fn(device_program_batch) -> device tensor`` (loss scalar or log-probabilities)."""
+    def __init__(self, step_fn, device, cold=False):
+        """``step_fn(device_program_batch) -> device tensor`` (loss scalar or log-probabilities).  ``cold``: forget the
+        device copies of a batch's program tables / targets before staging it, as if every batch were new (a benchmark
+        that cycles through a small pool of batches would otherwise find them cached on the device)."""
         self.step_fn = step_fn
+        self.cold = cold
         self.device = torch.device(device)
         self.copy_stream = torch.cuda.Stream(self.device)
         self._host = [None, None]
 
     def _stage(self, hb):
+        if self.cold:
+            for cp in getattr(hb, '_dfol_compiled', {}).values():
+                cp.device_cache = None
+                cp.mod_cache.clear()
+            if hasattr(hb, '_dfol_targets'):
+                del hb._dfol_targets
         with torch.cuda.stream(self.copy_stream):
             db = hb.to_cuda(self.device.index, non_blocking=True)
             ev = torch.cuda.Event()
@@ -37,7 +46,9 @@ class HostStepPipeline(object):
             if i + 1 < n:
                 nxt = self._stage(host_batches[i + 1])
             compute.wait_event(ev)
-            for t in (db._object_features, db._object_batch_index) + tuple(getattr(db, '_staged', None) or ()):
+            tables = tuple(cp.device_cache['blob'] for cp in getattr(db, '_dfol_compiled', {}).values()
+                           if cp.device_cache is not None)
+            for t in (db._object_features, db._object_batch_index) + tuple(getattr(db, '_staged', None) or ()) + tables:
                 if t is not None:
                     t.record_stream(compute)
             out = self.step_fn(db).detach()

@@ -107,6 +107,14 @@ class ProgramBatch(object):
             self._object_batch_index = self._object_batch_index.pin_memory()
         if self._staged is not None:
             self._staged = tuple(t.pin_memory() for t in self._staged)
+        compiled = getattr(self, '_dfol_compiled', {})
+        for cp in compiled.values():  # packed program tables: one async copy per batch
+            if not isinstance(cp.blob, torch.Tensor):
+                cp.blob = torch.from_numpy(cp.blob).pin_memory()
+        if compiled and self._answers is not None and not hasattr(self, '_dfol_targets_host'):
+            from .interpreter import targets_of   # loss targets (trainer.py:185-230): collate-time, pinned
+            self._dfol_targets_host = torch.from_numpy(
+                targets_of(next(iter(compiled.values())), self._answers)).pin_memory()
         return self
 
     _staged = None
@@ -139,6 +147,15 @@ class ProgramBatch(object):
         for key in ('_dfol_compiled', '_dfol_counts', '_dfol_targets'):
             if hasattr(self, key):
                 setattr(pb, key, getattr(self, key))
+        # the packed program tables travel with the features (same stream, one small copy per compiled variant)
+        if hasattr(self, '_dfol_compiled'):
+            from .compiler import upload_tables
+            dev = pb._device if isinstance(pb._device, torch.device) else torch.device('cuda', device)
+            for cp in self._dfol_compiled.values():
+                upload_tables(cp, dev)
+            answers_t = getattr(self, '_dfol_targets_host', None)
+            if answers_t is not None:
+                pb._dfol_targets = answers_t.cuda(device, non_blocking=non_blocking)
         pb._dfol_host = self
         return pb
 
