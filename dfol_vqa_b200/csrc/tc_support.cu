@@ -79,10 +79,38 @@ __device__ __forceinline__ float4 pair_geometry4(const float4 ps, const float4 p
 // the subjects s = w, w+8, ...; lane q owns hidden units 4q..4q+3 and 128+4q..; the geometry of (s, o0+lane) is
 // computed by lane `lane` and broadcast with shuffles (no barrier in the loop).  Also writes the geometry table
 // geo[pair] (float4) that the backward kernel re-uses.
+// Packed fp32 pair arithmetic (sm_100a FFMA2 / FADD2): both halves are IEEE round-to-nearest, i.e. bit-identical to the
+// scalar fmaf / add they replace, at half the issue slots.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// ELU with one MUFU: ex2.approx.ftz(a * log2 e) - 1 on the negative side.  Differs from __expf only where e^a is
+// subnormal (a < -87), where both give -1 after the subtraction.
+__device__ __forceinline__ float elu_fast(float a) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * 1.4426950408889634f));
+  return a > 0.0f ? a : e - 1.0f;
+}
+
 constexpr int PF_TO = 32;
 
 template <int G>  // G = H / 128 (float4 groups per lane)
-__global__ void __launch_bounds__(256) pair_hidden_fwd_tc_kernel(
+__global__ void __launch_bounds__(256, G <= 2 ? 3 : 1) pair_hidden_fwd_tc_kernel(
     const float* __restrict__ uv, long long lduv, const float* __restrict__ pos, long long ldpos,
     const float* __restrict__ wg, long long ldw, const float* __restrict__ bias, __nv_bfloat16* __restrict__ hout,
     long long ldh, float4* __restrict__ geo_out, const int32_t* __restrict__ pair_row,
@@ -103,16 +131,20 @@ __global__ void __launch_bounds__(256) pair_hidden_fwd_tc_kernel(
     const int o = idx / H4, q = idx - o * H4;
     vsm[o * H4 + q] = __ldg(reinterpret_cast<const float4*>(uv + (t0 + o0 + o) * lduv + H) + q);
   }
-  float4 bz[G], w0[G], w1[G], w2[G], w3[G];
+  // packed fp32 pairs (FFMA2 / FADD2 on sm_100a: two IEEE fma per issue slot): elements (4q, 4q+1) and (4q+2, 4q+3)
+  // of a lane's float4 group; wk[i][c][h] = geometry weights of component c for pair h
+  uint64_t bz[G][2], wk[G][4][2];
 #pragma unroll
   for (int i = 0; i < G; ++i) {
     const int q = lane + 32 * i;
-    bz[i] = __ldg(reinterpret_cast<const float4*>(bias) + q);
+    const float4 bq = __ldg(reinterpret_cast<const float4*>(bias) + q);
+    bz[i][0] = pack2(bq.x, bq.y); bz[i][1] = pack2(bq.z, bq.w);
     const float* w = wg + (long long)(4 * q) * ldw;
-    w0[i] = make_float4(w[0], w[1], w[2], w[3]);
-    w1[i] = make_float4(w[ldw], w[ldw + 1], w[ldw + 2], w[ldw + 3]);
-    w2[i] = make_float4(w[2 * ldw], w[2 * ldw + 1], w[2 * ldw + 2], w[2 * ldw + 3]);
-    w3[i] = make_float4(w[3 * ldw], w[3 * ldw + 1], w[3 * ldw + 2], w[3 * ldw + 3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      wk[i][c][0] = pack2(w[c], w[ldw + c]);
+      wk[i][c][1] = pack2(w[2 * ldw + c], w[3 * ldw + c]);
+    }
   }
   float4 po = make_float4(0.f, 0.f, 0.f, 0.f);
   if (lane < no) po = __ldg(reinterpret_cast<const float4*>(pos + (t0 + o0 + lane) * ldpos));
@@ -124,32 +156,35 @@ __global__ void __launch_bounds__(256) pair_hidden_fwd_tc_kernel(
     if (lane < no && o0 + lane != s) gl = pair_geometry4(ps, po);
     const long long prow = p0 + (long long)s * n + o0;
     if (geo_out != nullptr && lane < no) geo_out[prow + lane] = gl;
-    float4 u[G];
+    uint64_t u[G][2];
 #pragma unroll
     for (int i = 0; i < G; ++i) {
-      u[i] = __ldg(reinterpret_cast<const float4*>(uv + (t0 + s) * lduv) + lane + 32 * i);
-      u[i].x += bz[i].x; u[i].y += bz[i].y; u[i].z += bz[i].z; u[i].w += bz[i].w;
+      const float4 uq = __ldg(reinterpret_cast<const float4*>(uv + (t0 + s) * lduv) + lane + 32 * i);
+      u[i][0] = add2(pack2(uq.x, uq.y), bz[i][0]);
+      u[i][1] = add2(pack2(uq.z, uq.w), bz[i][1]);
     }
     for (int oi = 0; oi < no; ++oi) {
-      float4 g;
-      g.x = __shfl_sync(0xffffffffu, gl.x, oi);
-      g.y = __shfl_sync(0xffffffffu, gl.y, oi);
-      g.z = __shfl_sync(0xffffffffu, gl.z, oi);
-      g.w = __shfl_sync(0xffffffffu, gl.w, oi);
+      uint64_t g[4];
+      {
+        const float gx = __shfl_sync(0xffffffffu, gl.x, oi), gy = __shfl_sync(0xffffffffu, gl.y, oi);
+        const float gz = __shfl_sync(0xffffffffu, gl.z, oi), gw = __shfl_sync(0xffffffffu, gl.w, oi);
+        g[0] = pack2(gx, gx); g[1] = pack2(gy, gy); g[2] = pack2(gz, gz); g[3] = pack2(gw, gw);
+      }
       __nv_bfloat16* dst = hout + (prow + oi) * ldh;
 #pragma unroll
       for (int i = 0; i < G; ++i) {
         const int q = lane + 32 * i;
         const float4 v = vsm[oi * H4 + q];
-        float a0 = u[i].x + v.x, a1 = u[i].y + v.y, a2 = u[i].z + v.z, a3 = u[i].w + v.w;
-        a0 = fmaf(w0[i].x, g.x, a0); a0 = fmaf(w0[i].y, g.y, a0); a0 = fmaf(w0[i].z, g.z, a0); a0 = fmaf(w0[i].w, g.w, a0);
-        a1 = fmaf(w1[i].x, g.x, a1); a1 = fmaf(w1[i].y, g.y, a1); a1 = fmaf(w1[i].z, g.z, a1); a1 = fmaf(w1[i].w, g.w, a1);
-        a2 = fmaf(w2[i].x, g.x, a2); a2 = fmaf(w2[i].y, g.y, a2); a2 = fmaf(w2[i].z, g.z, a2); a2 = fmaf(w2[i].w, g.w, a2);
-        a3 = fmaf(w3[i].x, g.x, a3); a3 = fmaf(w3[i].y, g.y, a3); a3 = fmaf(w3[i].z, g.z, a3); a3 = fmaf(w3[i].w, g.w, a3);
-        a0 = a0 > 0.0f ? a0 : __expf(a0) - 1.0f;
-        a1 = a1 > 0.0f ? a1 : __expf(a1) - 1.0f;
-        a2 = a2 > 0.0f ? a2 : __expf(a2) - 1.0f;
-        a3 = a3 > 0.0f ? a3 : __expf(a3) - 1.0f;
+        uint64_t a01 = add2(u[i][0], pack2(v.x, v.y)), a23 = add2(u[i][1], pack2(v.z, v.w));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          a01 = fma2(wk[i][c][0], g[c], a01);
+          a23 = fma2(wk[i][c][1], g[c], a23);
+        }
+        float a0, a1, a2, a3;
+        unpack2(a01, a0, a1);
+        unpack2(a23, a2, a3);
+        a0 = elu_fast(a0); a1 = elu_fast(a1); a2 = elu_fast(a2); a3 = elu_fast(a3);
         const __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
         *reinterpret_cast<uint2*>(dst + 4 * q) =
             make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
@@ -167,13 +202,14 @@ __global__ void __launch_bounds__(256) pair_hidden_fwd_tc_kernel(
 //   dWg[h][k] = sum dz*geo_k and db[h] = sum dz stay in registers until the end (one atomic per block and column).
 // dU / dV are written as bf16 (operands of the next tensor-core GEMMs).
 template <int RG, int NI>
-__global__ void __launch_bounds__(32 * RG) pair_hidden_bwd_tc_kernel(
+__global__ void __launch_bounds__(32 * RG, RG == 4 ? 5 : 2) pair_hidden_bwd_tc_kernel(
     const __nv_bfloat16* __restrict__ dz, long long lddz, const float4* __restrict__ geo,
     __nv_bfloat16* __restrict__ du_out, __nv_bfloat16* __restrict__ dv_out, long long ldo, float* __restrict__ dwg,
     long long ldw, float* __restrict__ dbias, const int32_t* __restrict__ pair_row,
     const int32_t* __restrict__ obj_row, const int32_t* __restrict__ img_n) {
   __shared__ __align__(16) float red[2][RG][64];
   __shared__ __align__(16) float redw[RG][4][64];
+  __shared__ float4 gsm[2][RG * NI];
   const int b = blockIdx.y;
   const int n = img_n[b];
   const long long t0 = obj_row[b];
@@ -187,24 +223,41 @@ __global__ void __launch_bounds__(32 * RG) pair_hidden_bwd_tc_kernel(
   float dbv = 0.0f;  // threads < 64: column sum of dU
   // all NI row loads of a subject are issued before the first use (raw bf16x2 words: one register each); row
   // addresses are a per-subject base plus 32-bit offsets
+  // software pipeline: the NI row loads and the geometry row of subject s + 1 are issued before subject s is reduced, so
+  // that loads stay in flight across the per-subject barrier; the geometry row goes through a double-buffered shared
+  // tile (one float4 per object, broadcast reads) instead of 32 identical global loads per warp
   const long long srow = (long long)n * lddz;
   const __nv_bfloat16* sbase = dz + p0 * lddz + c0;
   const float4* gbase = geo + p0;
-  for (int s = 0; s < n; ++s, sbase += srow, gbase += n) {
-    uint32_t raw[NI];
+  uint32_t raw[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int o = rg + RG * i;
+    raw[i] = 0u;
+    if (o < n && o != 0) raw[i] = *reinterpret_cast<const uint32_t*>(sbase + o * (int)lddz);
+  }
+  if ((int)threadIdx.x < n) gsm[0][threadIdx.x] = __ldg(gbase + threadIdx.x);
+  __syncthreads();
+  for (int s = 0; s < n; ++s) {
+    uint32_t nxt[NI];
+    float4 gn = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool more = s + 1 < n;
+    sbase += srow; gbase += n;
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
       const int o = rg + RG * i;
-      raw[i] = 0u;
-      if (o < n && o != s) raw[i] = *reinterpret_cast<const uint32_t*>(sbase + o * (int)lddz);
+      nxt[i] = 0u;
+      if (more && o < n && o != s + 1) nxt[i] = *reinterpret_cast<const uint32_t*>(sbase + o * (int)lddz);
     }
+    if (more && (int)threadIdx.x < n) gn = __ldg(gbase + threadIdx.x);
+    const float4* gs = gsm[s & 1];
     float du0 = 0.f, du1 = 0.f;
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
       const int o = rg + RG * i;
       if (o < n && o != s) {
         const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[i]));
-        const float4 g = __ldg(gbase + o);
+        const float4 g = gs[o];
         du0 += v.x; du1 += v.y;
         dv[i][0] += v.x; dv[i][1] += v.y;
         dw[0][0] = fmaf(v.x, g.x, dw[0][0]); dw[0][1] = fmaf(v.y, g.x, dw[0][1]);
@@ -213,6 +266,9 @@ __global__ void __launch_bounds__(32 * RG) pair_hidden_bwd_tc_kernel(
         dw[3][0] = fmaf(v.x, g.w, dw[3][0]); dw[3][1] = fmaf(v.y, g.w, dw[3][1]);
       }
     }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) raw[i] = nxt[i];
+    if (more && (int)threadIdx.x < n) gsm[(s + 1) & 1][threadIdx.x] = gn;
     const int buf = s & 1;
     *reinterpret_cast<float2*>(&red[buf][rg][2 * lane]) = make_float2(du0, du1);
     __syncthreads();
