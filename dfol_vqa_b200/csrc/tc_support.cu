@@ -1,6 +1,7 @@
 // HBM-bound companions of the tensor-core (bf16) mode: operand preparation, the pair hidden layer (forward and
 // backward) and the backward of the table layer.  Every kernel here streams its big operand exactly once with
 // 128-byte warp transactions and keeps its reductions in registers / shared memory (see include/dfol_b200.h).
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "dfol_common.cuh"
@@ -195,44 +196,46 @@ __global__ void __launch_bounds__(256, G <= 2 ? 3 : 1) pair_hidden_fwd_tc_kernel
 }
 
 // Backward of the pair hidden layer from bf16 dZ1 (activation derivative already applied by the dgrad epilogue).
-// One block per (image, 64 hidden units): thread (rg, lane) owns columns 2*lane, 2*lane+1 of the chunk and the objects
-// o = rg, rg+8, ...: for every subject s it loads its NI rows (s,o) (128-byte warp transactions), so
+// One block per (image, CW hidden units), CW = 64 or 32: CW/2 consecutive threads form a row group that reads one row
+// (s,o) of the chunk (thread l owns columns 2l, 2l+1); row group rg owns the objects o = rg, rg + NRG, ...  For every
+// subject s a thread loads its NI rows, so
 //   dV[o][h] = sum_s dz   is thread-private (registers, written once at the end),
-//   dU[s][h] = sum_o dz   is reduced over the 8 row groups through a double-buffered shared tile (one barrier per s),
+//   dU[s][h] = sum_o dz   is reduced over the row groups through a double-buffered shared tile (one barrier per s),
 //   dWg[h][k] = sum dz*geo_k and db[h] = sum dz stay in registers until the end (one atomic per block and column).
-// dU / dV are written as bf16 (operands of the next tensor-core GEMMs).
-template <int RG, int NI>
-__global__ void __launch_bounds__(32 * RG, RG == 4 ? 5 : 2) pair_hidden_bwd_tc_kernel(
+// dU / dV are written as bf16 (operands of the next tensor-core GEMMs).  CW = 32 halves the per-thread state (more
+// resident blocks) and doubles the number of blocks: several waves instead of 1.4 on 148 SMs.
+template <int THREADS, int NI, int CW, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) pair_hidden_bwd_tc_kernel(
     const __nv_bfloat16* __restrict__ dz, long long lddz, const float4* __restrict__ geo,
     __nv_bfloat16* __restrict__ du_out, __nv_bfloat16* __restrict__ dv_out, long long ldo, float* __restrict__ dwg,
     long long ldw, float* __restrict__ dbias, const int32_t* __restrict__ pair_row,
     const int32_t* __restrict__ obj_row, const int32_t* __restrict__ img_n) {
-  __shared__ __align__(16) float red[2][RG][64];
-  __shared__ __align__(16) float redw[RG][4][64];
-  __shared__ float4 gsm[2][RG * NI];
+  constexpr int LPR = CW / 2;          // lanes per row
+  constexpr int NRG = THREADS / LPR;   // row groups
+  __shared__ __align__(16) float red[2][NRG][CW];
+  __shared__ __align__(16) float redw[NRG][4][CW];
+  __shared__ float4 gsm[2][NRG * NI];
   const int b = blockIdx.y;
   const int n = img_n[b];
   const long long t0 = obj_row[b];
   const long long p0 = pair_row[b];
-  const int rg = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c0 = blockIdx.x * 64 + 2 * lane;
+  const int rg = threadIdx.x / LPR, l = threadIdx.x % LPR;
+  const int c0 = blockIdx.x * CW + 2 * l;
   float dv[NI][2];
 #pragma unroll
   for (int i = 0; i < NI; ++i) dv[i][0] = dv[i][1] = 0.0f;
   float dw[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-  float dbv = 0.0f;  // threads < 64: column sum of dU
-  // all NI row loads of a subject are issued before the first use (raw bf16x2 words: one register each); row
-  // addresses are a per-subject base plus 32-bit offsets
+  float dbv = 0.0f;  // threads < CW: column sum of dU
   // software pipeline: the NI row loads and the geometry row of subject s + 1 are issued before subject s is reduced, so
-  // that loads stay in flight across the per-subject barrier; the geometry row goes through a double-buffered shared
-  // tile (one float4 per object, broadcast reads) instead of 32 identical global loads per warp
+  // that loads stay in flight across the per-subject barrier (raw bf16x2 words: one register each); the geometry row
+  // goes through a double-buffered shared tile (one float4 per object, broadcast reads)
   const long long srow = (long long)n * lddz;
   const __nv_bfloat16* sbase = dz + p0 * lddz + c0;
   const float4* gbase = geo + p0;
   uint32_t raw[NI];
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
-    const int o = rg + RG * i;
+    const int o = rg + NRG * i;
     raw[i] = 0u;
     if (o < n && o != 0) raw[i] = *reinterpret_cast<const uint32_t*>(sbase + o * (int)lddz);
   }
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(32 * RG, RG == 4 ? 5 : 2) pair_hidden_bwd_tc_k
     sbase += srow; gbase += n;
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-      const int o = rg + RG * i;
+      const int o = rg + NRG * i;
       nxt[i] = 0u;
       if (more && o < n && o != s + 1) nxt[i] = *reinterpret_cast<const uint32_t*>(sbase + o * (int)lddz);
     }
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(32 * RG, RG == 4 ? 5 : 2) pair_hidden_bwd_tc_k
     float du0 = 0.f, du1 = 0.f;
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-      const int o = rg + RG * i;
+      const int o = rg + NRG * i;
       if (o < n && o != s) {
         const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[i]));
         const float4 g = gs[o];
@@ -270,16 +273,126 @@ __global__ void __launch_bounds__(32 * RG, RG == 4 ? 5 : 2) pair_hidden_bwd_tc_k
     for (int i = 0; i < NI; ++i) raw[i] = nxt[i];
     if (more && (int)threadIdx.x < n) gsm[(s + 1) & 1][threadIdx.x] = gn;
     const int buf = s & 1;
-    *reinterpret_cast<float2*>(&red[buf][rg][2 * lane]) = make_float2(du0, du1);
+    *reinterpret_cast<float2*>(&red[buf][rg][2 * l]) = make_float2(du0, du1);
     __syncthreads();
-    if (threadIdx.x < 64) {
+    if (threadIdx.x < CW) {
       float t = 0.f;
 #pragma unroll
-      for (int r = 0; r < RG; ++r) t += red[buf][r][threadIdx.x];
-      du_out[(t0 + s) * ldo + blockIdx.x * 64 + threadIdx.x] = __float2bfloat16(t);
+      for (int r = 0; r < NRG; ++r) t += red[buf][r][threadIdx.x];
+      du_out[(t0 + s) * ldo + blockIdx.x * CW + threadIdx.x] = __float2bfloat16(t);
       dbv += t;
     }
   }
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int o = rg + NRG * i;
+    if (o < n) {
+      const __nv_bfloat162 x = __floats2bfloat162_rn(dv[i][0], dv[i][1]);
+      *reinterpret_cast<__nv_bfloat162*>(dv_out + (t0 + o) * ldo + c0) = x;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) *reinterpret_cast<float2*>(&redw[rg][k][2 * l]) = make_float2(dw[k][0], dw[k][1]);
+  __syncthreads();
+  if (threadIdx.x < CW) {
+    const int h = blockIdx.x * CW + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < NRG; ++r) t += redw[r][k][threadIdx.x];
+      atomicAdd(dwg + (long long)h * ldw + k, t);
+    }
+    atomicAdd(dbias + h, dbv);
+  }
+}
+
+// The same backward with the rows staged through shared memory by cp.async (16-byte LDGSTS, no registers held by
+// loads in flight): a ring of STAGES subject tiles (n rows x 128 B of the block's 64 columns + the n geometry float4) is
+// kept in flight per block, so HBM latency is covered by bytes in flight rather than by resident warps.  One barrier per
+// subject: it publishes the tile of subject s, frees the slot of subject s - 1 for the next copy, and separates the
+// dU partial sums of s - 1 (reduced by the first 64 threads while everybody works on s) from those of s + 1.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+
+template <int THREADS, int NI, int STAGES>
+__global__ void __launch_bounds__(THREADS) pair_hidden_bwd_async_kernel(
+    const __nv_bfloat16* __restrict__ dz, long long lddz, const float4* __restrict__ geo,
+    __nv_bfloat16* __restrict__ du_out, __nv_bfloat16* __restrict__ dv_out, long long ldo, float* __restrict__ dwg,
+    long long ldw, float* __restrict__ dbias, const int32_t* __restrict__ pair_row,
+    const int32_t* __restrict__ obj_row, const int32_t* __restrict__ img_n) {
+  constexpr int RG = THREADS / 32, ROWS = RG * NI;
+  constexpr int STAGE_BYTES = ROWS * 128 + ROWS * 16;
+  extern __shared__ __align__(16) uint8_t ring[];
+  __shared__ __align__(16) float red[2][RG][64];
+  __shared__ __align__(16) float redw[RG][4][64];
+  const int b = blockIdx.y;
+  const int n = img_n[b];
+  const long long t0 = obj_row[b];
+  const long long p0 = pair_row[b];
+  const int rg = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 64 + 2 * lane;
+  const __nv_bfloat16* src0 = dz + p0 * lddz + blockIdx.x * 64;
+  const float4* geo0 = geo + p0;
+
+  auto issue = [&](int s) {
+    uint8_t* dst = ring + (s % STAGES) * STAGE_BYTES;
+    const __nv_bfloat16* src = src0 + (long long)s * n * lddz;
+    for (int c = threadIdx.x; c < n * 8; c += THREADS) {
+      const int o = c >> 3, part = c & 7;
+      cp_async16(dst + o * 128 + part * 16, src + (long long)o * lddz + part * 8);
+    }
+    if ((int)threadIdx.x < n) cp_async16(dst + ROWS * 128 + threadIdx.x * 16, geo0 + (long long)s * n + threadIdx.x);
+  };
+  auto reduce_du = [&](int s, float& dbv) {  // threads < 64
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < RG; ++r) t += red[s & 1][r][threadIdx.x];
+    du_out[(t0 + s) * ldo + blockIdx.x * 64 + threadIdx.x] = __float2bfloat16(t);
+    dbv += t;
+  };
+
+  float dv[NI][2];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) dv[i][0] = dv[i][1] = 0.0f;
+  float dw[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  float dbv = 0.0f;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < n) issue(s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int s = 0; s < n; ++s) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+    __syncthreads();
+    if (s + STAGES - 1 < n) issue(s + STAGES - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (s > 0 && threadIdx.x < 64) reduce_du(s - 1, dbv);
+    const uint8_t* tile = ring + (s % STAGES) * STAGE_BYTES;
+    const float4* gs = reinterpret_cast<const float4*>(tile + ROWS * 128);
+    float du0 = 0.f, du1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int o = rg + RG * i;
+      if (o < n && o != s) {
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(tile + o * 128 + lane * 4));
+        const float4 g = gs[o];
+        du0 += v.x; du1 += v.y;
+        dv[i][0] += v.x; dv[i][1] += v.y;
+        dw[0][0] = fmaf(v.x, g.x, dw[0][0]); dw[0][1] = fmaf(v.y, g.x, dw[0][1]);
+        dw[1][0] = fmaf(v.x, g.y, dw[1][0]); dw[1][1] = fmaf(v.y, g.y, dw[1][1]);
+        dw[2][0] = fmaf(v.x, g.z, dw[2][0]); dw[2][1] = fmaf(v.y, g.z, dw[2][1]);
+        dw[3][0] = fmaf(v.x, g.w, dw[3][0]); dw[3][1] = fmaf(v.y, g.w, dw[3][1]);
+      }
+    }
+    *reinterpret_cast<float2*>(&red[s & 1][rg][2 * lane]) = make_float2(du0, du1);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (n > 0 && threadIdx.x < 64) reduce_du(n - 1, dbv);
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
     const int o = rg + RG * i;
@@ -571,8 +684,18 @@ extern "C" int dfol_pair_hidden_fwd_tc(const float* uv, int64_t lduv, const floa
                    (reinterpret_cast<uintptr_t>(obj_pos) % 16) == 0 && (reinterpret_cast<uintptr_t>(bias) % 16) == 0,
                "dfol_pair_hidden_fwd_tc: strides must be multiples of 4 and buffers 16-byte aligned");
   DFOL_REQUIRE(max_n >= 1, "dfol_pair_hidden_fwd_tc: empty batch");
-  // small work items (8 subjects x 32 objects) so that the grid is many waves deep: no tail on 148 SMs
-  const int ts = 8;
+  // subjects per block: every block first stages its 32-object V tile (32 KB) and its weights, so blocks as large as
+  // the batch allows (measured: 8 subjects per block 0.150 ms, all 48 subjects 0.120 ms at B = 256, N = 48) while the
+  // grid still fills the GPU (3 resident blocks on each of 148 SMs)
+  static const int ts_env = [] { const char* e = getenv("DFOL_PF_SUBJECTS"); return e ? atoi(e) : 0; }();
+  int ts;
+  if (ts_env > 0) {
+    ts = ((ts_env + 7) / 8) * 8;
+  } else {
+    const long long tiles = (long long)((max_n + PF_TO - 1) / PF_TO) * image_num;
+    ts = max_n <= 64 ? ((max_n + 7) / 8) * 8 : (((max_n + 1) / 2 + 7) / 8) * 8;
+    while (ts > 8 && tiles * ((max_n + ts - 1) / ts) < 3 * 148) ts -= 8;
+  }
   dim3 grid((max_n + PF_TO - 1) / PF_TO, image_num, (max_n + ts - 1) / ts);
   const size_t smem = (size_t)PF_TO * (H / 4) * sizeof(float4);
   cudaStream_t st = (cudaStream_t)stream;
@@ -604,21 +727,62 @@ extern "C" int dfol_pair_hidden_bwd_tc(const void* dz, int64_t lddz, const void*
   if (image_num == 0) return 0;
   DFOL_REQUIRE((H % 64) == 0 && (lddz % 2) == 0 && (ldo % 2) == 0 && max_n >= 1 && max_n <= 128,
                "dfol_pair_hidden_bwd_tc: H %% 64 == 0, even strides, 1 <= max_n <= 128");
-  dim3 grid(H / 64, image_num);
+  // DFOL_PB_MODE: 0 (default) = by image size; 1 = cp.async ring; 64 / 32 = register-pipelined kernel with that
+  // column-chunk width
+  static const int mode_env = [] { const char* e = getenv("DFOL_PB_MODE"); return e ? atoi(e) : 0; }();
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* dzp = reinterpret_cast<const __nv_bfloat16*>(dz);
   const float4* gp = reinterpret_cast<const float4*>(geo);
   __nv_bfloat16* dup = reinterpret_cast<__nv_bfloat16*>(du_out);
   __nv_bfloat16* dvp = reinterpret_cast<__nv_bfloat16*>(dv_out);
-#define DFOL_PB_LAUNCH(RG, NI)                                                                                \
-  pair_hidden_bwd_tc_kernel<RG, NI><<<grid, 32 * RG, 0, st>>>(dzp, lddz, gp, dup, dvp, ldo, dwg, ldw, dbias,   \
-                                                              pair_row, obj_row, img_n)
-  // 4 row groups (128 threads) for small images: H/64 * B blocks of 128 threads fit the GPU in one wave
-  if (max_n <= 32) DFOL_PB_LAUNCH(4, 8);
-  else if (max_n <= 48) DFOL_PB_LAUNCH(4, 12);
-  else if (max_n <= 64) DFOL_PB_LAUNCH(8, 8);
-  else if (max_n <= 104) DFOL_PB_LAUNCH(8, 13);
-  else DFOL_PB_LAUNCH(8, 16);
+  // (measured, B = 256: N = 48 0.119 ms ring / 0.126 registers; N = 64 0.205 / 0.244; N = 100 0.486 / 0.467 -- the
+  //  256-thread ring kernels need 122 registers, two blocks per SM)
+  if ((mode_env == 0 ? max_n <= 64 : mode_env == 1) && (lddz % 8) == 0 && (reinterpret_cast<uintptr_t>(dz) % 16) == 0) {
+    dim3 grid(H / 64, image_num);
+#define DFOL_PBA_LAUNCH(T, NI, STAGES)                                                                            \
+  {                                                                                                               \
+    auto kern = pair_hidden_bwd_async_kernel<T, NI, STAGES>;                                                      \
+    const int smem = STAGES * ((T / 32) * NI) * 144;                                                              \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                                \
+    kern<<<grid, T, smem, st>>>(dzp, lddz, gp, dup, dvp, ldo, dwg, ldw, dbias, pair_row, obj_row, img_n);         \
+  }
+    static const int stages_env = [] { const char* e = getenv("DFOL_PB_STAGES"); return e ? atoi(e) : 0; }();
+    if (max_n <= 32) DFOL_PBA_LAUNCH(128, 8, 4)
+    else if (max_n <= 48) {
+      if (stages_env == 6) DFOL_PBA_LAUNCH(128, 12, 6)
+      else if (stages_env == 3) DFOL_PBA_LAUNCH(128, 12, 3)
+      else DFOL_PBA_LAUNCH(128, 12, 4)
+    }
+    else if (max_n <= 64) DFOL_PBA_LAUNCH(256, 8, 4)
+    else if (max_n <= 104) {
+      if (stages_env == 6) DFOL_PBA_LAUNCH(256, 13, 6)
+      else if (stages_env == 3) DFOL_PBA_LAUNCH(256, 13, 3)
+      else DFOL_PBA_LAUNCH(256, 13, 4)
+    }
+    else DFOL_PBA_LAUNCH(256, 16, 4)
+#undef DFOL_PBA_LAUNCH
+    return finish_launch("dfol_pair_hidden_bwd_tc");
+  }
+  const int cw = mode_env == 32 || (mode_env == 0 && max_n <= 32) ? 32 : 64;
+  dim3 grid(H / cw, image_num);
+#define DFOL_PB_LAUNCH(T, NI, CW, MINB)                                                                              \
+  pair_hidden_bwd_tc_kernel<T, NI, CW, MINB><<<grid, T, 0, st>>>(dzp, lddz, gp, dup, dvp, ldo, dwg, ldw, dbias,      \
+                                                                 pair_row, obj_row, img_n)
+  if (cw == 64) {
+    // one warp per row: 4 row groups (128 threads) for small images
+    if (max_n <= 32) DFOL_PB_LAUNCH(128, 8, 64, 5);
+    else if (max_n <= 48) DFOL_PB_LAUNCH(128, 12, 64, 5);
+    else if (max_n <= 64) DFOL_PB_LAUNCH(256, 8, 64, 2);
+    else if (max_n <= 104) DFOL_PB_LAUNCH(256, 13, 64, 2);
+    else DFOL_PB_LAUNCH(256, 16, 64, 2);
+  } else {
+    // half a warp per row: 8 row groups per 128 threads, H/32 * B blocks
+    if (max_n <= 32) DFOL_PB_LAUNCH(128, 4, 32, 8);
+    else if (max_n <= 48) DFOL_PB_LAUNCH(128, 6, 32, 7);
+    else if (max_n <= 64) DFOL_PB_LAUNCH(128, 8, 32, 6);
+    else if (max_n <= 104) DFOL_PB_LAUNCH(256, 7, 32, 3);
+    else DFOL_PB_LAUNCH(256, 8, 32, 3);
+  }
 #undef DFOL_PB_LAUNCH
   return finish_launch("dfol_pair_hidden_bwd_tc");
 }
