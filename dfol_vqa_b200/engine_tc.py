@@ -9,6 +9,8 @@ Weights stay fp32 (master copy, optimiser state); their bf16 operand copies -- p
 -- are refreshed by ONE batched cast launch per step (dfol_cast_jobs).
 """
 
+import os
+
 import numpy as np
 import torch
 
@@ -53,6 +55,7 @@ class _Operands(object):
         self.wa2t = buf(Ha, Ep)     # dgrad operand of attribute layer 2: [in, out]
         self.wr2t = buf(H, Ep)      # dgrad operand of relation layer 2
         self.wcat_t = buf(F, Kc)    # dgrad operand of the three first layers that read obj: [F, Ha | H | H]
+        self.we_t = buf(Ep, _roundup(C, 64))  # dgrad operand of the table layer (dense gradients of query-type programs)
         jobs = []
 
         def job(src, rows, cols, dst, out_rows, dcols, transpose=0):
@@ -72,6 +75,7 @@ class _Operands(object):
         job(a0.weight[:, :F], Ha, F, self.wcat_t[:, :Hap], F, Hap, 1)
         job(r0.weight[:, :F], H, F, self.wcat_t[:, Hap:Hap + Hp], F, Hp, 1)
         job(r0.weight[:, ldo:ldo + F], H, F, self.wcat_t[:, Hap + Hp:], F, Hp, 1)
+        job(emb.weight, C, E, self.we_t, E, self.we_t.shape[1], 1)
         arr = np.array(jobs, dtype=_JOB_DTYPE)
         self.max_elems = int(max(int(j[6]) * int(j[8]) for j in jobs))
         self.jobs = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
@@ -370,13 +374,26 @@ class TensorCorePath(object):
                  h_last.stride(0), E, ptr(dz), dz.stride(0), cols, ptr(dW), ptr(db), ptr(d_below), float(keep), st)
             return dz
         assert keep == 1.0 or rows_total < (1 << 22), 'dropout: the dense table backward is meant for object rows'
-        # many columns per image (option lists of query-type programs): dense d logits + fp32 GEMMs
+        # many columns per image (option lists of query-type programs): dense d logits, then plain GEMMs
         from .engine import gemm_f32, _split_for
         Cn = dW.shape[0]
         dl = torch.zeros(rows_total, Cn, device=dev, dtype=torch.float32)
         call('dfol_table_grad_dense', ptr(g), ptr(tabs['goff']), ptr(tabs['col']), ptr(tabs['img']), tabs['count'],
              ptr(ll), ptr(blk), ptr(stride), ptr(row0), ptr(img_rows), ptr(dl), Cn, st)
         call('dfol_colsum', ptr(dl), Cn, rows_total, Cn, ptr(db), st)
+        if keep == 1.0 and W is self.w.emb.weight and os.environ.get('DFOL_DENSE_FP32', '0') != '1':
+            # tensor cores: d logits as a bf16 operand (like every other gradient operand of this mode);
+            # dW += dl^T . h (MN-major wgrad), dZ = (dl . W) * sigmoid'(h) in the dgrad epilogue
+            ops = self.operands(dev)
+            Cp = ops.we_t.shape[1]
+            dl16 = torch.empty(rows_total, Cp, device=dev, dtype=torch.bfloat16)
+            call('dfol_cast_bf16', ptr(dl), Cn, ptr(dl16), Cp, rows_total, Cn, st)
+            del dl
+            self._wgrad(dl16, Cn, h_last, E, dW, st)
+            # (N = the padded width: rows E.. of we_t are zero and sigmoid' of the zero padding of h is zero)
+            self._dgrad(dl16, ops.we_t, dz, cols, Cp, h_last, K.MUL_SIGMOID_GRAD, st)
+            call('dfol_colsum_bf16', ptr(dz), cols, rows_total, E, ptr(d_below), st)
+            return dz
         h32 = h_last[:, :E].float()
         sk = _split_for(rows_total)
         gemm_f32(dl.t(), h32, dW, accumulate=(sk == 1), split_k=sk, stream=st)

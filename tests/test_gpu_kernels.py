@@ -263,7 +263,7 @@ def test_gemm_bf16_tcgen05_dgrad(M, N, K, mode):
     assert torch.allclose(dX.double(), ref, rtol=1.5e-2, atol=1.5e-2), (dX.double() - ref).abs().max()
 
 
-@pytest.mark.parametrize('terminal', ['verify_rel', 'exist', 'and'])
+@pytest.mark.parametrize('terminal', ['verify_rel', 'exist', 'and', 'query_attr'])
 def test_bf16_mode_training_gradients(terminal):
     """Training step in bf16 tensor-core mode: loss within 2e-2, gradients within a few percent of each tensor's
     scale of the fp32 oracle (mixed precision: bf16 operands, fp32 accumulation / master weights)."""
