@@ -22,14 +22,18 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ lp,
       if (d_lp) d_lp[i] = scale * ((p - y) / fmaxf((1.0f - p) * p, 1e-12f)) * p;
     }
   } else if (kind == 1) {
-    if (i < n_seg) {
-      const int a = seg[i], b = seg[i + 1];
+    // one warp per option list (query-type questions have ~100 options): coalesced reads, warp sums
+    const int w = i >> 5, lane = threadIdx.x & 31;
+    if (w < n_seg) {
+      const int a = seg[w], b = seg[w + 1];
       float s = 0.f, dot = 0.f;
-      for (int k = a; k < b; ++k) { s += expf(lp[k]); dot += target[k] * lp[k]; }
-      local = slog(s) - dot;
+      for (int k = a + lane; k < b; k += 32) { s += expf(lp[k]); dot += target[k] * lp[k]; }
+      s = warp_sum(s);
+      dot = warp_sum(dot);
+      if (lane == 0) local = slog(s) - dot;
       if (d_lp) {
         const float inv = (s >= kLogEps) ? 1.0f / s : 0.0f;
-        for (int k = a; k < b; ++k) d_lp[k] = scale * (expf(lp[k]) * inv - target[k]);
+        for (int k = a + lane; k < b; k += 32) d_lp[k] = scale * (expf(lp[k]) * inv - target[k]);
       }
     }
   } else {
@@ -95,9 +99,9 @@ extern "C" int dfol_loss_fwd_bwd(const float* lp, const float* target, const int
   DFOL_REQUIRE(lp && loss_out, "dfol_loss_fwd_bwd: null pointer");
   DFOL_REQUIRE(kind == 2 || target, "dfol_loss_fwd_bwd: target missing");
   DFOL_REQUIRE(kind != 1 || seg, "dfol_loss_fwd_bwd: segments missing");
-  const int work = (kind == 1) ? n_seg : n_lp;
+  const long long work = (kind == 1) ? 32ll * n_seg : n_lp;
   if (work == 0) return 0;
-  loss_kernel<<<(work + 255) / 256, 256, 0, (cudaStream_t)stream>>>(lp, target, seg, n_seg, n_lp, kind, scale,
+  loss_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(lp, target, seg, n_seg, n_lp, kind, scale,
                                                                    loss_out, d_lp);
   return finish_launch("dfol_loss_fwd_bwd");
 }
