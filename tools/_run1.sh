@@ -1,10 +1,10 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -2
-timeout 300 python bench.py --no-cpu-baseline --workload c2 > gpurun_out/r1d_bench_train_c2.json 2>gpurun_out/c2.err; tail -3 gpurun_out/c2.err
+for k in 1 8 16 32; do
+DFOL_WG_MIN_KB=$k timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_wg$k.json 2>gpurun_out/wg.err
 python - <<PY
 import json
-l=[x for x in open('gpurun_out/r1d_bench_train_c2.json') if x.startswith('{')][-1]
+l=[x for x in open('gpurun_out/bench_wg$k.json') if x.startswith('{')][-1]
 d=json.loads(l)
-print('c2', round(d['ms_per_step'],4), round(d['value']), 'e2e', round(d['e2e']['value']))
-for k,v in list(d['kernels'].items())[:14]: print('  ',k, round(v['ms_per_step'],4))
+print('min_kb=$k', round(d['ms_per_step'],4), ' '.join('%s=%.4f' % (k.replace('gemm_bf16_tc_',''), v['ms_per_step']) for k,v in d['kernels'].items() if 'wgrad' in k))
 PY
+done
