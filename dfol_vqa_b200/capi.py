@@ -11,7 +11,8 @@ from ctypes import c_float, c_int, c_int64, c_uint64, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdfol_b200.so')
+# DFOL_LIB_PATH: another build of the same ABI (A/B timing of kernel variants); the default is the in-tree library
+LIB_PATH = os.environ.get('DFOL_LIB_PATH') or os.path.join(_HERE, 'libdfol_b200.so')
 _lib = None
 
 
