@@ -41,7 +41,7 @@ def _layout(counts):
             'pair_row': dev(torch.cat([torch.zeros(1, dtype=torch.long), (n * n).cumsum(0)]), torch.int32)}
 
 
-@pytest.mark.parametrize('counts', [[48] * 5, [5, 12, 3, 33, 16, 1], [100, 64]])
+@pytest.mark.parametrize('counts', [[48] * 5, [5, 12, 3, 33, 16, 1], [100, 64], [20, 31, 7, 32], [64, 50, 2], [128, 3]])
 def test_pair_hidden_fwd_bwd_tc(counts):
     from dfol_vqa_b200.capi import call, ptr, stream_ptr
     g = torch.Generator().manual_seed(len(counts) + counts[0])
