@@ -2,6 +2,7 @@
 // backward) and the backward of the table layer.  Every kernel here streams its big operand exactly once with
 // 128-byte warp transactions and keeps its reductions in registers / shared memory (see include/dfol_b200.h).
 #include <cstdlib>
+#include <type_traits>
 #include <cuda_bf16.h>
 
 #include "dfol_common.cuh"
@@ -518,92 +519,104 @@ __global__ void __launch_bounds__(32 * NC * TB_RP) table_layer_bwd_tc_kernel(
     if (lane == 0 && t != 0.0f) atomicAdd(db + wrow_s[j], t);
   }
   const bool e_ok = e < E, st_ok = e < out_cols;
-  float2 wj[S], dwj[S], colsum = make_float2(0.f, 0.f);
+  // The row loop is specialised on the number of slices of THIS image (block-uniform): images that use fewer slices
+  // than the launch maximum S run code without the predicated-off FMAs of the missing ones (9 of 12 at c3).
+  auto run = [&](auto sb_tag) {
+    constexpr int SB = decltype(sb_tag)::value;   // 0: generic (S slots guarded by Sb); > 0: exactly SB slices
+    constexpr int SN = SB > 0 ? SB : S;
+    float2 wj[SN], dwj[SN], colsum = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int j = 0; j < S; ++j) {
-    dwj[j] = make_float2(0.f, 0.f);
-    wj[j] = (j < Sb && e_ok) ? *reinterpret_cast<const float2*>(W + (long long)wrow_s[j] * ldw + e)
-                             : make_float2(0.f, 0.f);
-  }
-  constexpr int UN = 8;  // rows in flight per warp
-  // row pointers advance by a fixed stride: no 64-bit multiply per access
-  const __nv_bfloat16* hp = hs + (r0 + rp) * ldh + e;
-  __nv_bfloat16* zp = dZ + (r0 + rp) * lddz + e;
-  const long long hstep = (long long)TB_RP * ldh, zstep = (long long)TB_RP * lddz;
-  for (int l0 = rp; l0 < cn; l0 += TB_RP * UN, hp += UN * hstep, zp += UN * zstep) {
-    uint32_t hraw[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      hraw[u] = 0u;
-      if (l0 + TB_RP * u < cn && e_ok) hraw[u] = *reinterpret_cast<const uint32_t*>(hp + u * hstep);
+    for (int j = 0; j < SN; ++j) {
+      dwj[j] = make_float2(0.f, 0.f);
+      wj[j] = ((SB > 0 || j < Sb) && e_ok) ? *reinterpret_cast<const float2*>(W + (long long)wrow_s[j] * ldw + e)
+                               : make_float2(0.f, 0.f);
     }
+    constexpr int UN = 8;  // rows in flight per warp
+    // row pointers advance by a fixed stride: no 64-bit multiply per access
+    const __nv_bfloat16* hp = hs + (r0 + rp) * ldh + e;
+    __nv_bfloat16* zp = dZ + (r0 + rp) * lddz + e;
+    const long long hstep = (long long)TB_RP * ldh, zstep = (long long)TB_RP * lddz;
+    for (int l0 = rp; l0 < cn; l0 += TB_RP * UN, hp += UN * hstep, zp += UN * zstep) {
+      uint32_t hraw[UN];
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int l = l0 + TB_RP * u;
-      if (l < cn) {
-        const float2 hv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hraw[u]));
-        float ox = 0.f, oy = 0.f;
+      for (int u = 0; u < UN; ++u) {
+        hraw[u] = 0u;
+        if (l0 + TB_RP * u < cn && e_ok) hraw[u] = *reinterpret_cast<const uint32_t*>(hp + u * hstep);
+      }
 #pragma unroll
-        for (int j = 0; j < S; ++j) {
-          if (j < Sb) {  // block-uniform: images that use fewer slices than the batch maximum skip the rest
-            const float dzl = dz_s[j][l];
-            if (PK) {
-              const uint64_t d2 = pack2(dzl, dzl);
-              const uint64_t o2 = fma2(d2, pack2(wj[j].x, wj[j].y), pack2(ox, oy));
-              const uint64_t w2 = fma2(d2, pack2(hv.x, hv.y), pack2(dwj[j].x, dwj[j].y));
-              unpack2(o2, ox, oy);
-              unpack2(w2, dwj[j].x, dwj[j].y);
-            } else {
-              ox = fmaf(dzl, wj[j].x, ox);
-              oy = fmaf(dzl, wj[j].y, oy);
-              dwj[j].x = fmaf(dzl, hv.x, dwj[j].x);
-              dwj[j].y = fmaf(dzl, hv.y, dwj[j].y);
+      for (int u = 0; u < UN; ++u) {
+        const int l = l0 + TB_RP * u;
+        if (l < cn) {
+          const float2 hv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hraw[u]));
+          float ox = 0.f, oy = 0.f;
+#pragma unroll
+          for (int j = 0; j < SN; ++j) {
+            if (SB > 0 || j < Sb) {  // (generic form: block-uniform guard)
+              const float dzl = dz_s[j][l];
+              if (PK) {
+                const uint64_t d2 = pack2(dzl, dzl);
+                const uint64_t o2 = fma2(d2, pack2(wj[j].x, wj[j].y), pack2(ox, oy));
+                const uint64_t w2 = fma2(d2, pack2(hv.x, hv.y), pack2(dwj[j].x, dwj[j].y));
+                unpack2(o2, ox, oy);
+                unpack2(w2, dwj[j].x, dwj[j].y);
+              } else {
+                ox = fmaf(dzl, wj[j].x, ox);
+                oy = fmaf(dzl, wj[j].y, oy);
+                dwj[j].x = fmaf(dzl, hv.x, dwj[j].x);
+                dwj[j].y = fmaf(dzl, hv.y, dwj[j].y);
+              }
             }
           }
-        }
-        if (DROP) {
-          const float hx = hv.x * keep, hy = hv.y * keep;
-          ox *= (hv.x != 0.0f ? inv_keep : 0.0f) * hx * (1.0f - hx);
-          oy *= (hv.y != 0.0f ? inv_keep : 0.0f) * hy * (1.0f - hy);
-        } else {
-          ox *= hv.x * (1.0f - hv.x);
-          oy *= hv.y * (1.0f - hv.y);
-        }
-        colsum.x += ox;
-        colsum.y += oy;
-        if (st_ok) {  // columns E .. out_cols are the zero K-padding of the next GEMM (h = 0 there)
-          if (accumulate && e_ok) {
-            const float2 pv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zp + u * zstep));
-            ox += pv.x;
-            oy += pv.y;
+          if (DROP) {
+            const float hx = hv.x * keep, hy = hv.y * keep;
+            ox *= (hv.x != 0.0f ? inv_keep : 0.0f) * hx * (1.0f - hx);
+            oy *= (hv.y != 0.0f ? inv_keep : 0.0f) * hy * (1.0f - hy);
+          } else {
+            ox *= hv.x * (1.0f - hv.x);
+            oy *= hv.y * (1.0f - hv.y);
           }
-          *reinterpret_cast<__nv_bfloat162*>(zp + u * zstep) = __floats2bfloat162_rn(ox, oy);
+          colsum.x += ox;
+          colsum.y += oy;
+          if (st_ok) {  // columns E .. out_cols are the zero K-padding of the next GEMM (h = 0 there)
+            if (accumulate && e_ok) {
+              const float2 pv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zp + u * zstep));
+              ox += pv.x;
+              oy += pv.y;
+            }
+            *reinterpret_cast<__nv_bfloat162*>(zp + u * zstep) = __floats2bfloat162_rn(ox, oy);
+          }
         }
       }
     }
-  }
-  // block reductions over the row phases: dbelow (column sums of dZ) and the dW rows, one atomic per column
-  *reinterpret_cast<float2*>(&red_s[rp][e]) = colsum;
-  __syncthreads();
-  for (int x = threadIdx.x; x < E; x += THREADS) {
-    float t = 0.f;
-#pragma unroll
-    for (int r = 0; r < TB_RP; ++r) t += red_s[r][x];
-    if (dbelow != nullptr && t != 0.0f) atomicAdd(dbelow + x, t);
-  }
-#pragma unroll
-  for (int j = 0; j < S; ++j) {
-    if (j >= Sb) break;
-    __syncthreads();
-    *reinterpret_cast<float2*>(&red_s[rp][e]) = dwj[j];
+    // block reductions over the row phases: dbelow (column sums of dZ) and the dW rows, one atomic per column
+    *reinterpret_cast<float2*>(&red_s[rp][e]) = colsum;
     __syncthreads();
     for (int x = threadIdx.x; x < E; x += THREADS) {
       float t = 0.f;
 #pragma unroll
       for (int r = 0; r < TB_RP; ++r) t += red_s[r][x];
-      if (t != 0.0f) atomicAdd(dW + (long long)wrow_s[j] * ldw + x, t);
+      if (dbelow != nullptr && t != 0.0f) atomicAdd(dbelow + x, t);
     }
-  }
+#pragma unroll
+    for (int j = 0; j < SN; ++j) {
+      if (SB == 0 && j >= Sb) break;
+      __syncthreads();
+      *reinterpret_cast<float2*>(&red_s[rp][e]) = dwj[j];
+      __syncthreads();
+      for (int x = threadIdx.x; x < E; x += THREADS) {
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < TB_RP; ++r) t += red_s[r][x];
+        if (t != 0.0f) atomicAdd(dW + (long long)wrow_s[j] * ldw + x, t);
+      }
+    }
+  };
+  if (Sb == S) run(std::integral_constant<int, S>());
+  else if (S > 1 && Sb == S - 1) run(std::integral_constant<int, (S > 1 ? S - 1 : 1)>());
+  else if (S > 2 && Sb == S - 2) run(std::integral_constant<int, (S > 2 ? S - 2 : 1)>());
+  else if (S > 4 && Sb == S - 3) run(std::integral_constant<int, (S > 4 ? S - 3 : 1)>());
+  else run(std::integral_constant<int, 0>());
+
 }
 
 // ---------------------------------------------------------------------------------------------------------
