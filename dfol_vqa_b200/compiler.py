@@ -18,6 +18,8 @@ What is resolved here, on the host, once per batch (reference behaviour in paren
 
 import re
 
+import os
+
 import numpy as np
 
 from . import capi
@@ -59,7 +61,8 @@ class CompiledPrograms(object):
     __slots__ = ('instr', 'q_instr', 'opts', 'lp_num', 'kind', 'options', 'seg', 'names', 'question_num',
                  'g_attr_size', 'g_rel_size', 'attr_slices', 'rel_slices', 'terminal', 'lp_owner', 'device_cache',
                  'alg_bytes', 'slot_wrow', 'img_slot', 'slot_blk', 'rel_slot_size', 'max_slots', 'mod_plan',
-                 'mod_descs', 'mod_rows', 'slot_after', 'slot_names', 'mod_cache', 'mod_tok', 'mod_opcol', 'mod_relflag', 'blob', 'blob_layout', 'slice_meta')
+                 'mod_descs', 'mod_rows', 'slot_after', 'slot_names', 'mod_cache', 'mod_tok', 'mod_opcol', 'mod_relflag', 'blob',
+                 'blob_layout', 'slice_meta', 'layout_arrays', 'layout_meta')
 
 
 def _slice_table(slices, B):
@@ -90,7 +93,9 @@ def _pack_tables(cp):
         arrays['seg'] = cp.seg
     if cp.img_slot is not None:
         arrays.update(slot_wrow=cp.slot_wrow, img_slot=cp.img_slot, slot_blk=cp.slot_blk)
-    cp.slice_meta = {}
+    for name, a in cp.layout_arrays.items():  # scene layout tables (engine.SceneLayout.of_compiled)
+        arrays['lay.' + name] = a
+    cp.slice_meta = {'lay': {}}
     for key, slices in (('attr_slices', cp.attr_slices), ('rel_slices', cp.rel_slices)):
         tables, meta = _slice_table(slices, B)
         cp.slice_meta[key] = meta
@@ -139,7 +144,8 @@ def upload_tables(cp, device):
 
 class ProgramCompiler(object):
 
-    def __init__(self, ontology, normalize=True, hard_mode=False, relation_slots=False, modulated=False):
+    def __init__(self, ontology, normalize=True, hard_mode=False, relation_slots=False, modulated=False,
+                 concept_num=None):
         """modulated: attention-transfer modulations are active (FastGQAInterpreter built with the three attention
         networks): every filter-like / relate-like sub-operator of a slot that has at least one non-blank predicate gets
         one row of (alpha, beta, c, d) per predicate (FilterBatch.forward / RelateBatch.forward apply_modulations,
@@ -153,8 +159,12 @@ class ProgramCompiler(object):
         self.normalize = normalize
         self.hard_mode = hard_mode
         self.relation_slots = relation_slots
+        # pair rows only for the images whose program reads a relation (needs the slots; tests switch it off to compare)
+        self.demand_pairs = os.environ.get('DFOL_DENSE_PAIRS', '0') != '1'
         self.modulated = modulated
         self._rel_concept = list(ontology._relation_index)
+        # rows of the embedding layer = columns of the attribute table (the layout tables are packed per batch)
+        self.concept_num = concept_num if concept_num is not None else len(ontology._vocabulary['idx_to_arg'])
         self._a2i = ontology._vocabulary['arg_to_idx']
         self._rel_rev = ontology._relation_reveresed_index
         self._option_cache = {}
@@ -557,5 +567,16 @@ class ProgramCompiler(object):
         else:
             cp.img_slot = cp.slot_wrow = cp.slot_blk = None
             cp.rel_slot_size = cp.max_slots = 0
+        # scene layout tables, packed with the bytecode.  With relation slots the pair rows are demand-driven too: an
+        # image whose program reads no relation likelihood gets none (engine.layout_tables); the dense pair tables ride
+        # along for the paths that need every pair row (training-mode dropout)
+        from .engine import layout_tables
+        C, nR = self.concept_num, len(self._rel_concept)
+        mask = (np.diff(cp.img_slot) > 0) if (use_slots and self.demand_pairs) else None
+        cp.layout_arrays, cp.layout_meta = layout_tables(object_counts, C, nR, mask)
+        if mask is not None:
+            dense, dmeta = layout_tables(object_counts, C, nR, None)
+            cp.layout_arrays['img_nn_d'], cp.layout_arrays['pair_row_d'] = dense['img_nn'], dense['pair_row']
+            cp.layout_meta['P_dense'] = dmeta['P']
         cp.pack_tables()
         return cp

@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(THREADS, MINB) pair_hidden_bwd_tc_kernel(
   __shared__ float4 gsm[2][NRG * NI];
   const int b = blockIdx.y;
   const int n = img_n[b];
+  if (n == 0) return;  // image without pair rows (demand-driven: its program reads no relation)
   const long long t0 = obj_row[b];
   const long long p0 = pair_row[b];
   const int rg = threadIdx.x / LPR, l = threadIdx.x % LPR;
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(THREADS) pair_hidden_bwd_async_kernel(
   __shared__ __align__(16) float redw[RG][4][64];
   const int b = blockIdx.y;
   const int n = img_n[b];
+  if (n == 0) return;  // image without pair rows
   const long long t0 = obj_row[b];
   const long long p0 = pair_row[b];
   const int rg = threadIdx.x >> 5, lane = threadIdx.x & 31;

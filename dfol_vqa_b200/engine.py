@@ -21,55 +21,103 @@ def _roundup(x, m):
     return (x + m - 1) // m * m
 
 
+def layout_tables(counts, concept_num, relation_num, pair_mask=None):
+    """Host (numpy) row / offset tables of one program batch + its scalar sizes.
+
+    ``pair_mask`` (bool per image, tensor-core mode with demand-driven relation slots): images whose program reads no
+    relation likelihood get NO pair rows -- the pair-level chain (hidden layer, layer 2, slot columns and their
+    backward) runs over the images that need it only.  No output depends on the skipped rows and their gradient
+    contribution is exactly zero (the reference evaluates them and never reads them, classifier_oracle.py:154)."""
+    n = np.asarray(counts, dtype=np.int64)
+    assert n.ndim == 1 and n.size > 0 and int(n.min()) >= 1, 'every image needs at least one object'
+    npair = n if pair_mask is None else np.where(np.asarray(pair_mask, dtype=bool), n, 0)
+    a_stride = (n + 3) // 4 * 4
+    r_stride = (n * n + 3) // 4 * 4
+    attr_blk = concept_num * np.concatenate([[0], np.cumsum(a_stride)])
+    rel_blk = relation_num * np.concatenate([[0], np.cumsum(r_stride)])
+    arrays = {
+        'img_n': n.astype(np.int32), 'img_np': npair.astype(np.int32), 'img_nn': (npair * npair).astype(np.int32),
+        'obj_row': np.concatenate([[0], np.cumsum(n)]).astype(np.int32),
+        'pair_row': np.concatenate([[0], np.cumsum(npair * npair)]).astype(np.int32),
+        'attr_stride': a_stride.astype(np.int32), 'rel_stride': r_stride.astype(np.int32),
+        'attr_blk': attr_blk[:-1].astype(np.int64), 'rel_blk': rel_blk[:-1].astype(np.int64),
+        'obj_img': np.repeat(np.arange(n.size, dtype=np.int32), n),
+    }
+    meta = {'counts': [int(v) for v in n], 'B': int(n.size), 'T': int(n.sum()), 'P': int((npair * npair).sum()),
+            'max_n': int(n.max()), 'max_np': int(npair.max()), 'attr_size': int(attr_blk[-1]),
+            'rel_size': int(rel_blk[-1]), 'masked': pair_mask is not None,
+            'pair_images': int((npair > 0).sum())}
+    assert meta['P'] < 2 ** 31 and meta['T'] < 2 ** 31
+    return arrays, meta
+
+
 class SceneLayout(object):
     """Row/offset tables of one program batch (see the layout comment in include/dfol_b200.h)."""
 
     _cache = {}
+    _cache_bytes = 0
+    _CACHE_LIMIT = 64 << 20
 
-    def __init__(self, counts, concept_num, relation_num, device):
-        n = np.asarray(counts, dtype=np.int64)
-        assert n.ndim == 1 and n.size > 0 and int(n.min()) >= 1, 'every image needs at least one object'
-        self.counts = [int(v) for v in n]
-        self.B = int(n.size)
-        self.T = int(n.sum())
-        self.P = int((n * n).sum())
-        self.max_n = int(n.max())
-        a_stride = (n + 3) // 4 * 4
-        r_stride = (n * n + 3) // 4 * 4
-        obj_row = np.concatenate([[0], np.cumsum(n)])
-        pair_row = np.concatenate([[0], np.cumsum(n * n)])
-        attr_blk = concept_num * np.concatenate([[0], np.cumsum(a_stride)])
-        rel_blk = relation_num * np.concatenate([[0], np.cumsum(r_stride)])
-        self.attr_size = int(attr_blk[-1])
-        self.rel_size = int(rel_blk[-1])
-        assert self.P < 2 ** 31 and self.T < 2 ** 31
+    def __init__(self, counts, concept_num, relation_num, device, pair_mask=None, tables=None):
+        """``tables``: (device views, meta) of tables that were already uploaded with the batch's packed blob
+        (compiler._pack_tables) -- no copy is issued then."""
+        if tables is None:
+            arrays, meta = layout_tables(counts, concept_num, relation_num, pair_mask)
+            views = {k: torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
+                     for k, a in arrays.items()}
+        else:
+            views, meta = tables
+        self.__dict__.update(meta)
+        self.device = device
+        for k, v in views.items():
+            setattr(self, k, v)
+        self._pair_img = None
+        self.nbytes = sum(int(v.numel()) * v.element_size() for v in views.values())
 
-        def dev(a, dtype):
-            return torch.from_numpy(np.ascontiguousarray(a.astype(dtype))).to(device, non_blocking=True)
-
-        self.img_n = dev(n, np.int32)
-        self.img_nn = dev(n * n, np.int32)
-        self.obj_row = dev(obj_row, np.int32)
-        self.pair_row = dev(pair_row, np.int32)
-        self.attr_stride = dev(a_stride, np.int32)
-        self.rel_stride = dev(r_stride, np.int32)
-        self.attr_blk = dev(attr_blk[:-1], np.int64)
-        self.rel_blk = dev(rel_blk[:-1], np.int64)
-        img = torch.arange(self.B, device=device, dtype=torch.int32)
-        self.obj_img = torch.repeat_interleave(img, self.img_n.long())
-        self.pair_img = torch.repeat_interleave(img, self.img_nn.long())
-        self.a_stride_host = a_stride
-        self.r_stride_host = r_stride
+    @property
+    def pair_img(self):
+        """image of every pair row (P int32; only the fp32 / dropout / fused-inference paths read it: built on demand)"""
+        if self._pair_img is None:
+            img = torch.arange(self.B, device=self.device, dtype=torch.int32)
+            self._pair_img = torch.repeat_interleave(img, self.img_nn.long(), output_size=self.P)
+            self.nbytes += self.P * 4
+        return self._pair_img
 
     @classmethod
-    def get(cls, counts, concept_num, relation_num, device):
-        key = (tuple(int(c) for c in counts), concept_num, relation_num, str(device))
+    def get(cls, counts, concept_num, relation_num, device, pair_mask=None):
+        """Layout built from the object counts alone (tests, tools, callers without a compiled batch).  The cache is
+        bounded by bytes; batches that went through the compiler carry their layout tables in their own packed blob
+        (``of_compiled``) and never come here."""
+        mask_key = None if pair_mask is None else tuple(bool(m) for m in pair_mask)
+        key = (tuple(int(c) for c in counts), concept_num, relation_num, str(device), mask_key)
         hit = cls._cache.get(key)
         if hit is None:
-            if len(cls._cache) > 64:
+            if cls._cache_bytes > cls._CACHE_LIMIT or len(cls._cache) > 64:
                 cls._cache.clear()
-            hit = cls(counts, concept_num, relation_num, device)
+                cls._cache_bytes = 0
+            hit = cls(counts, concept_num, relation_num, device, pair_mask)
             cls._cache[key] = hit
+            cls._cache_bytes += hit.nbytes + 4 * hit.P
+        return hit
+
+    @classmethod
+    def of_compiled(cls, cp, device, dense_pairs=False):
+        """Layout of a compiled batch from the tables packed into its blob at compile (= collate) time: lives and dies
+        with the batch's device tables, costs no extra copy and no host synchronisation.  ``dense_pairs``: pair rows for
+        every image (dropout path), whatever the programs read."""
+        from .compiler import upload_tables
+        cache = upload_tables(cp, device)
+        key = 'layout_dense' if dense_pairs else 'layout'
+        hit = cache.get(key)
+        if hit is None:
+            meta = dict(cp.layout_meta)
+            views = dict(cache['lay'])
+            if dense_pairs and meta['masked']:
+                views['img_np'], views['img_nn'], views['pair_row'] = views['img_n'], views['img_nn_d'], views['pair_row_d']
+                meta.update(P=meta['P_dense'], max_np=meta['max_n'], masked=False, pair_images=meta['B'])
+            views.pop('img_nn_d', None)
+            views.pop('pair_row_d', None)
+            hit = cache[key] = cls(None, None, None, device, tables=(views, meta))
         return hit
 
 

@@ -118,8 +118,14 @@ class TensorCorePath(object):
         thr = int(os.environ.get('DFOL_SLOTS_TC_MIN', '1'))   # measured faster for every slot count (c1: 0.11 -> 0.07 ms)
         return cp.max_slots >= thr
 
-    @staticmethod
-    def _tc(A16, B16, C, N, Kp, bias, act, st, table=None):
+    _P = -1   # pair rows of the scene being processed: kernel tags say "P" instead of the (batch-dependent) number
+
+    @classmethod
+    def _rows(cls, m):
+        return 'P' if m == cls._P else '%d' % m
+
+    @classmethod
+    def _tc(cls, A16, B16, C, N, Kp, bias, act, st, table=None):
         """C = epilogue(A16[:, :Kp] @ B16[:N, :Kp]^T) on the tensor cores (dfol_gemm_bf16_tc)."""
         M = A16.shape[0]
         if table is None:
@@ -131,27 +137,28 @@ class TensorCorePath(object):
                     ptr(table.get('img_n')))
             diag = table.get('diag', DEFAULT_LL)
         if capi.trace is not None:
-            capi.next_meta = {'tag': 'gemm_bf16_tc[%dx%dx%d]%s' % (M, N, Kp, ' table' if store else ''),
+            capi.next_meta = {'tag': 'gemm_bf16_tc[%sx%dx%d]%s' % (cls._rows(M), N, Kp, ' table' if store else ''),
                               'flops': 2.0 * M * N * Kp}
         call('dfol_gemm_bf16_tc', ptr(A16), A16.stride(0), ptr(B16), B16.stride(0), ptr(C), ldc, ptr(bias), M, N, Kp,
              act, out_bf16, store, maps[0], maps[1], maps[2], maps[3], maps[4], diag, st)
 
-    @staticmethod
-    def _dgrad(dZ, Wt, dX, N, Kp, h_saved, mul_mode, st, keep=1.0):
+    @classmethod
+    def _dgrad(cls, dZ, Wt, dX, N, Kp, h_saved, mul_mode, st, keep=1.0):
         """dX[:, :cols(dX)] = (dZ . Wt^T) * act'(h_saved); dX may be a column block of a wider buffer."""
         M = dZ.shape[0]
         if capi.trace is not None:
-            capi.next_meta = {'tag': 'gemm_bf16_tc_dgrad[%dx%dx%d]' % (M, N, Kp), 'flops': 2.0 * M * N * Kp}
+            capi.next_meta = {'tag': 'gemm_bf16_tc_dgrad[%sx%dx%d]' % (cls._rows(M), N, Kp), 'flops': 2.0 * M * N * Kp}
         call('dfol_gemm_bf16_tc_dgrad', ptr(dZ), dZ.stride(0), ptr(Wt), Wt.stride(0), ptr(dX), dX.stride(0), dX.shape[1], M,
              N, Kp, ptr(h_saved), 0 if h_saved is None else h_saved.stride(0), mul_mode, float(keep), st)
 
-    @staticmethod
-    def _wgrad(A, Mc, B, Nc, C, st):
+    @classmethod
+    def _wgrad(cls, A, Mc, B, Nc, C, st):
         """C[Mc, Nc] (fp32 view) += A[:, :Mc]^T . B[:, :Nc] (reduction over rows)."""
         rows = A.shape[0]
         if capi.trace is not None:
-            capi.next_meta = {'tag': 'gemm_bf16_tc_wgrad[%dx%dx%d]' % (Mc, Nc, rows), 'flops': 2.0 * Mc * Nc * rows,
-                              'bytes': 2.0 * rows * (A.stride(0) + B.stride(0)) if rows > 100000 else 0.0}
+            capi.next_meta = {'tag': 'gemm_bf16_tc_wgrad[%dx%dx%s]' % (Mc, Nc, cls._rows(rows)),
+                              'flops': 2.0 * Mc * Nc * rows,
+                              'bytes': 2.0 * rows * (A.stride(0) + B.stride(0)) if rows == cls._P else 0.0}
         call('dfol_gemm_bf16_tc_wgrad', ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(C), C.stride(0), Mc, Nc, rows,
              st)
 
@@ -178,6 +185,7 @@ class TensorCorePath(object):
             T = features.shape[0]
             assert features.dtype == torch.float32 and features.stride(1) == 1 and features.shape[1] == D + 6
         assert T == layout.T
+        TensorCorePath._P = layout.P
         ops.refresh(st, training)
         sc = Scene()
         sc.layout, sc.features, sc.tc, sc.dropout = layout, features, True, dropout
@@ -235,6 +243,16 @@ class TensorCorePath(object):
         sc.attr_h = [h1a, h2a]
 
         # relation chain: U|V in one GEMM, pair hidden layer, layer 2, relation table
+        if layout.P == 0:
+            # demand-driven pair rows: no program of this batch reads a relation likelihood -> no pair-level work at all
+            assert cp is not None and cp.img_slot is not None
+            dc = self.engine.upload_programs(cp, dev)
+            sc.rel_ll = torch.empty(max(cp.rel_slot_size, 1), device=dev, dtype=torch.float32)
+            sc.rel_blk, sc.rel_slots = dc['slot_blk'], True
+            sc.rel_h, sc.uv = [None, None], None
+            sc.geo = torch.empty(0, 4, device=dev, dtype=torch.float32) if training else None
+            main.wait_event(ev_attr)
+            return sc
         first = w.rel[0]
         h1r = bf(layout.P, p['Hp'])
         if dropout is None:
@@ -252,14 +270,14 @@ class TensorCorePath(object):
                 bm = bf(layout.B * H, Kp1)
                 call('dfol_pair_hidden_fwd_mma', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo,
                      ptr(first.weight[:, 2 * ldo:]), first.weight.stride(0), ptr(first.bias), ptr(h1r), p['Hp'], H,
-                     ptr(geo), ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_n), layout.B, layout.max_n,
+                     ptr(geo), ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_np), layout.B, layout.max_n,
                      ptr(bm), st)
             else:
                 if capi.trace is not None:
                     capi.next_meta = {'tag': 'pair_hidden_fwd_tc', 'bytes': 2.0 * layout.P * p['Hp']}
                 call('dfol_pair_hidden_fwd_tc', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo,
                      ptr(first.weight[:, 2 * ldo:]), first.weight.stride(0), ptr(first.bias), ptr(h1r), p['Hp'], H,
-                     ptr(geo), ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_n), layout.B, layout.max_n,
+                     ptr(geo), ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_np), layout.B, layout.max_n,
                      st)
         else:
             # an independent mask per pair element breaks the U[s] + V[o] factorisation: the first layer runs as one
@@ -298,7 +316,7 @@ class TensorCorePath(object):
                 # the backward pass needs the layer-2 activation (or the image uses many relations): GEMM with bf16
                 # store, then the demand-driven relation columns from the stored activation
                 if capi.trace is not None:
-                    capi.next_meta = {'tag': 'pair_layer_fwd_cluster[%dx%dx%d]' % (layout.P, E, p['Hp']),
+                    capi.next_meta = {'tag': 'pair_layer_fwd_cluster[Px%dx%d]' % (E, p['Hp']),
                                       'flops': 2.0 * layout.P * E * p['Hp'],
                                       'bytes': 2.0 * layout.P * (p['Hp'] + p['Ep'])}
                 call('dfol_pair_layer_fwd_cluster', ptr(h1r), p['Hp'], ptr(ops.wr2), p['Hp'], ptr(h2r), p['Ep'],
@@ -316,18 +334,18 @@ class TensorCorePath(object):
                     call('dfol_rel_slots_fwd_tc', ptr(h2r), p['Ep'], layout.P, E, p['Ep'], ptr(w.emb.weight),
                          w.emb.weight.stride(0), ptr(w.emb.bias), ptr(dc['slot_wrow']), ptr(dc['img_slot']),
                          cp.max_slots, ptr(dc['slot_blk']), ptr(layout.rel_stride), ptr(layout.pair_row),
-                         ptr(layout.img_nn), ptr(layout.img_n), layout.B, layout.max_n ** 2, DEFAULT_LL, ptr(wb),
+                         ptr(layout.img_nn), ptr(layout.img_np), layout.B, layout.max_n ** 2, DEFAULT_LL, ptr(wb),
                          ptr(rel_ll), st)
                 else:
                     call('dfol_rel_slots_fwd', ptr(h2r), p['Ep'], E, ptr(w.emb.weight), w.emb.weight.stride(0),
                          ptr(w.emb.bias), ptr(dc['slot_wrow']), ptr(dc['img_slot']), cp.max_slots,
                          ptr(dc['slot_blk']), ptr(layout.rel_stride), ptr(layout.pair_row), ptr(layout.img_nn),
-                         ptr(layout.img_n), layout.B, layout.max_n ** 2, DEFAULT_LL, ptr(rel_ll), st)
+                         ptr(layout.img_np), layout.B, layout.max_n ** 2, DEFAULT_LL, ptr(rel_ll), st)
             else:
                 # inference: layer 2 + relation columns in one persistent tcgen05 kernel; the P x E activation is
                 # consumed in registers and never written
                 if capi.trace is not None:
-                    capi.next_meta = {'tag': 'pair_layer_fwd_tc[%dx%dx%d]+slots' % (layout.P, E, p['Hp']),
+                    capi.next_meta = {'tag': 'pair_layer_fwd_tc[Px%dx%d]+slots' % (E, p['Hp']),
                                       'flops': 2.0 * layout.P * E * p['Hp']}
                 call('dfol_pair_layer_fwd_tc', ptr(h1r), p['Hp'], ptr(ops.wr2), p['Hp'], None, p['Ep'], p['Ep'],
                      ptr(w.rel[1].bias), layout.P, E, p['Hp'], K.ACT_SIGMOID, ptr(w.emb.weight),
@@ -418,6 +436,7 @@ class TensorCorePath(object):
         F, D, ldo, Ha, H, E = d['F'], d['D'], d['ldo'], d['Ha'], d['H'], d['E']
         Hap, Hp, Ep, Kc = p['Hap'], p['Hp'], p['Ep'], p['Kc']
         T, P = lay.T, lay.P
+        TensorCorePath._P = P
         if getattr(scene, 'dropout', None) is not None:
             return self._backward_dropout(cp, scene, tape, d_lp, grads)
         assert scene.geo is not None, 'scene was built without training buffers'
@@ -475,7 +494,7 @@ class TensorCorePath(object):
             self._wgrad(dz2r, E, h1r, H, G(r1.weight), st)
             dz1r = torch.empty(P, Hp, device=dev, dtype=torch.bfloat16)
             if capi.trace is not None:
-                capi.next_meta = {'tag': 'pair_layer_dgrad_cluster[%dx%dx%d]' % (P, H, Ep), 'flops': 2.0 * P * H * Ep,
+                capi.next_meta = {'tag': 'pair_layer_dgrad_cluster[Px%dx%d]' % (H, Ep), 'flops': 2.0 * P * H * Ep,
                                   'bytes': 2.0 * P * (Ep + 2 * Hp)}
             call('dfol_pair_layer_dgrad_cluster', ptr(dz2r), Ep, ptr(ops.wr2t), Ep, ptr(dz1r), Hp, Hp, P, H, Ep,
                  ptr(h1r), Hp, K.MUL_ELU_GRAD, 1.0, st)
@@ -484,7 +503,7 @@ class TensorCorePath(object):
                 capi.next_meta = {'tag': 'pair_hidden_bwd_tc', 'bytes': 2.0 * P * H + 16.0 * P}
             call('dfol_pair_hidden_bwd_tc', ptr(dz1r), Hp, ptr(scene.geo), ptr(dcat[:, Hap:]), ptr(dcat[:, Hap + Hp:]),
                  Kc, ptr(gw1[:, 2 * ldo:]), gw1.stride(0), ptr(G(r0.bias)), H, ptr(lay.pair_row), ptr(lay.obj_row),
-                 ptr(lay.img_n), lay.B, lay.max_n, st)
+                 ptr(lay.img_np), lay.B, lay.max_n, st)
             if not merged:
                 self._wgrad(dcat[:, Hap:], H, scene.obj16, ldo, gw1[:, :ldo], st)
                 self._wgrad(dcat[:, Hap + Hp:], H, scene.obj16, ldo, gw1[:, ldo:2 * ldo], st)

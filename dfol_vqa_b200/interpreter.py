@@ -159,7 +159,8 @@ class FastGQAInterpreter(nn.Module):
                                       linear_layers(oracle._embedding_network)[0])
         self._engine = ReasoningEngine(self._weights, ontology._relation_index, self._gemm_mode)
         self._compiler = ProgramCompiler(ontology, normalize=oracle._normalize, hard_mode=hard_mode,
-                                         relation_slots=(self._gemm_mode == 'bf16'), modulated=self._has_modulator)
+                                         relation_slots=(self._gemm_mode == 'bf16'), modulated=self._has_modulator,
+                                         concept_num=self._weights.emb.weight.shape[0])
         self._attention = None
         if self._has_modulator:
             # the reference registers the SAME three networks under every operator module; the first registration
@@ -239,7 +240,8 @@ class FastGQAInterpreter(nn.Module):
             if host is not None:
                 host._dfol_compiled = cache
         # (the bytecode depends on the compiler's table layout and on whether modulation rows are assigned)
-        key = (bool(give_answer and self._hard_mode), self._compiler.relation_slots, self._compiler.modulated)
+        key = (bool(give_answer and self._hard_mode), self._compiler.relation_slots, self._compiler.modulated,
+               self._compiler.demand_pairs)
         if key not in cache:
             cache[key] = self._compiler.compile(pb, self._object_counts(pb), give_answer=give_answer)
         return cache[key]
@@ -291,10 +293,9 @@ class FastGQAInterpreter(nn.Module):
         for k, pb in enumerate(program_batch_list):
             drop_k = None if dropout is None else (dropout[0], dropout[1] + k)  # independent masks per sub-batch
             feats = self._features_of(pb)
-            counts = self._object_counts(pb)
-            layout = SceneLayout.get(counts, self._weights.emb.weight.shape[0], len(self._ontology._relation_index),
-                                     feats[1].device if isinstance(feats, tuple) else feats.device)
             cp = self.compiled(pb, give_answer)
+            layout = SceneLayout.of_compiled(cp, feats[1].device if isinstance(feats, tuple) else feats.device,
+                                             dense_pairs=drop_k is not None)
             att = self.modulator(cp, modulator_switch)
             sink = {} if return_trace else None
             lp = _ReasoningFunction.apply(self._engine, cp, layout, feats, need_grad, att, sink, drop_k, len(params),
@@ -450,10 +451,8 @@ class FusedTrainStep(object):
             feats = interp._features_of(pb)
             dev = feats[1].device if isinstance(feats, tuple) else feats.device
             st = capi.stream_ptr(dev)
-            counts = interp._object_counts(pb)
-            layout = SceneLayout.get(counts, interp._weights.emb.weight.shape[0],
-                                     len(interp._ontology._relation_index), dev)
             cp = interp.compiled(pb, False)
+            layout = SceneLayout.of_compiled(cp, dev, dense_pairs=drop_k is not None)
             scene = self.engine.build_scene(feats, layout, keep_for_backward=self.oracle_trainable, cp=cp,
                                             dropout=drop_k)
             att = interp.modulator(cp)
@@ -475,11 +474,16 @@ class FusedTrainStep(object):
                 att.backward(mod_ctx, scene.d_mods, self.grads)
         return self.scalars[0]
 
+    def reduce_gradients(self):
+        """Sum of the flat gradient bucket over the data-parallel ranks (one NCCL all-reduce; replaces the reduce-add
+        of nn.DataParallel, reference nn/interpreter/data_parallel.py:54-57)."""
+        if self.world > 1:
+            self.bucket.all_reduce(self.group)
+
     def optimizer_step(self):
         dev = self.flat.device
         st = capi.stream_ptr(dev)
-        if self.world > 1:
-            self.bucket.all_reduce(self.group)
+        self.reduce_gradients()
         self.step_count += 1
         call('dfol_sumsq', ptr(self.flat_grad), self.flat_grad.numel(), ptr(self.scalars[1:]), st)
         call('dfol_adam_step', ptr(self.flat), ptr(self.flat_grad), ptr(self.m), ptr(self.v), self.flat.numel(),

@@ -36,23 +36,31 @@ class HostStepPipeline(object):
         return db, ev
 
     def run(self, host_batches):
-        """Runs the step over ``host_batches`` (a sequence); returns the list of results as CPU tensors."""
+        """Runs the step over ``host_batches`` (any iterable, e.g. a DataLoader that lowers the programs in worker
+        processes: it is pulled one batch ahead of the compute); returns the list of results as CPU tensors."""
         compute = torch.cuda.current_stream(self.device)
-        n = len(host_batches)
+        it = iter(host_batches)
         results, pending = [], None
-        nxt = self._stage(host_batches[0]) if n else None
-        for i in range(n):
+
+        def stage_next():
+            hb = next(it, None)
+            return None if hb is None else self._stage(hb)
+
+        nxt = stage_next()
+        i = 0
+        while nxt is not None:
             db, ev = nxt
-            if i + 1 < n:
-                nxt = self._stage(host_batches[i + 1])
+            nxt = stage_next()
             compute.wait_event(ev)
-            tables = tuple(cp.device_cache['blob'] for cp in getattr(db, '_dfol_compiled', {}).values()
-                           if cp.device_cache is not None)
-            for t in (db._object_features, db._object_batch_index) + tuple(getattr(db, '_staged', None) or ()) + tables:
-                if t is not None:
-                    t.record_stream(compute)
+            # everything to_cuda allocated on the copy stream (features, batch index, staged tensors, packed program
+            # tables, loss targets) is consumed on the compute stream: without record_stream the caching allocator
+            # could hand a block back to the copy stream -- and the staging of batch i+2 overwrite it -- while step i
+            # has not run yet
+            for t in db._dfol_device_tensors:
+                t.record_stream(compute)
             out = self.step_fn(db).detach()
             slot = i & 1
+            i += 1
             if self._host[slot] is None or self._host[slot].shape != out.shape or self._host[slot].dtype != out.dtype:
                 self._host[slot] = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
             self._host[slot].copy_(out, non_blocking=True)

@@ -111,10 +111,11 @@ class ProgramBatch(object):
         for cp in compiled.values():  # packed program tables: one async copy per batch
             if not isinstance(cp.blob, torch.Tensor):
                 cp.blob = torch.from_numpy(cp.blob).pin_memory()
-        if compiled and self._answers is not None and not hasattr(self, '_dfol_targets_host'):
-            from .interpreter import targets_of   # loss targets (trainer.py:185-230): collate-time, pinned
-            self._dfol_targets_host = torch.from_numpy(
-                targets_of(next(iter(compiled.values())), self._answers)).pin_memory()
+        if compiled and self._answers is not None:
+            if not hasattr(self, '_dfol_targets_host'):
+                from .interpreter import targets_of   # loss targets (trainer.py:185-230): collate-time work
+                self._dfol_targets_host = torch.from_numpy(targets_of(next(iter(compiled.values())), self._answers))
+            self._dfol_targets_host = self._dfol_targets_host.pin_memory()
         return self
 
     _staged = None
@@ -157,6 +158,13 @@ class ProgramBatch(object):
             if answers_t is not None:
                 pb._dfol_targets = answers_t.cuda(device, non_blocking=non_blocking)
         pb._dfol_host = self
+        # every device tensor this call allocated (on the CURRENT stream, which may be a copy stream): a consumer on
+        # another stream must record_stream() all of them (HostStepPipeline does) before the batch can be dropped
+        pb._dfol_device_tensors = [t for t in (feats, bidx, getattr(pb, '_dfol_targets', None)) + tuple(staged or ())
+                                   if isinstance(t, torch.Tensor)]
+        for cp in getattr(self, '_dfol_compiled', {}).values():
+            if cp.device_cache is not None:
+                pb._dfol_device_tensors.append(cp.device_cache['blob'])
         return pb
 
 
@@ -248,6 +256,6 @@ def attach_compiled(program_batch, compiler, give_answer=False):
     cache = getattr(program_batch, '_dfol_compiled', None)
     if cache is None:
         cache = program_batch._dfol_compiled = {}
-    key = (bool(give_answer and compiler.hard_mode), compiler.relation_slots, compiler.modulated)
+    key = (bool(give_answer and compiler.hard_mode), compiler.relation_slots, compiler.modulated, compiler.demand_pairs)
     cache[key] = compiler.compile(program_batch, counts, give_answer=give_answer)
     return program_batch

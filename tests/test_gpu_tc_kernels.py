@@ -359,7 +359,7 @@ def test_rel_slots_tensor_core_kernel_matches_simt(terminal, n_max, ragged, monk
     # valid entries: n_b^2 per slot (slices are padded to a multiple of 4 floats; the padding is never read)
     valid = torch.zeros(tables['tc'].numel(), dtype=torch.bool)
     for b, n in enumerate(counts):
-        stride = int(layout.r_stride_host[b])
+        stride = int(layout.rel_stride[b])
         for j in range(int(cp.img_slot[b + 1] - cp.img_slot[b])):
             off = int(cp.slot_blk[b]) + j * stride
             valid[off:off + n * n] = True
