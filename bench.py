@@ -48,7 +48,10 @@ WORKLOADS = {
     # name: batch per GPU, objects, terminals (one type per batch, as the reference sampler does), hops, relate prob
     'c1': dict(batch=256, n=48, terminals=('exist', 'verify_attrs', 'verify_rel', 'and', 'or'), hops=(1, 3),
                relate_prob=0.35, desc='curriculum stage-1 shape: binary questions, B=256/GPU, N=48, <=3 hops'),
-    'c2': dict(batch=512, n=48, terminals=('query_attr', 'choose_attr'), hops=(6, 8), relate_prob=0.3,
+    # (neg_prob: at the trained-like operating point p(attribute) ~ 0.02, so six positive filters in a row drive every
+    # attention to the 1e-20 clamp and the whole batch degenerates to constants with zero gradient; mostly-negated
+    # filters keep the long chains in the non-degenerate regime -- same instructions, same bytes, meaningful numbers)
+    'c2': dict(batch=512, n=48, terminals=('query_attr', 'choose_attr'), hops=(6, 8), relate_prob=0.3, neg_prob=0.85,
                desc='open questions (query/choose over attribute categories), B=512/GPU, N=48, >=6 hops'),
     'c3': dict(batch=256, n=100, terminals=('chain9',), hops=(9, 9), relate_prob=1.0,
                desc='relation-heavy long programs: N=100, 9 relate hops, B=256/GPU'),
@@ -72,7 +75,7 @@ def make_workload_questions(ont, wl, batch, seed, index=0):
     if term == 'chain9':
         return synth.make_relation_chain_questions(ont, batch, 9, seed=seed)
     return synth.make_questions(ont, batch, term, wl['hops'][0], wl['hops'][1], seed=seed,
-                                relate_prob=wl['relate_prob'])
+                                relate_prob=wl['relate_prob'], neg_prob=wl.get('neg_prob', 0.2))
 
 
 def build_model(args, device):
