@@ -577,6 +577,7 @@ class ProgramCompiler(object):
         if mask is not None:
             dense, dmeta = layout_tables(object_counts, C, nR, None)
             cp.layout_arrays['img_nn_d'], cp.layout_arrays['pair_row_d'] = dense['img_nn'], dense['pair_row']
-            cp.layout_meta['P_dense'] = dmeta['P']
+            cp.layout_arrays['pair_tile_d'] = dense['pair_tile']
+            cp.layout_meta['P_dense'], cp.layout_meta['pair_tiles_dense'] = dmeta['P'], dmeta['pair_tiles']
         cp.pack_tables()
         return cp

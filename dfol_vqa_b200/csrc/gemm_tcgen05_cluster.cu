@@ -14,6 +14,7 @@
 //                       the 128B-swizzled shared tile, conflict free), bf16 result written to a swizzled shared tile
 //                       and stored with cp.async.bulk.tensor (full 128-byte lines) -- no per-thread global access.
 // Every mbarrier wait is bounded (trap instead of hanging the GPU).
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace dfol {
@@ -36,6 +37,7 @@ struct ClParams {
   int cluster_size;     // CTAs per cluster (the launch attribute)
   int n_store;          // stored width of C (64-column boxes entirely beyond it are skipped)
   float keep;           // < 1: the multiplier operand holds post-dropout activations (0 / h / keep)
+  int prefetch;         // tiles of L2 prefetch distance (0 = off)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -70,6 +72,11 @@ __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t*
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void cl_prefetch_l2(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
                : "memory");
 }
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
@@ -160,6 +167,18 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
         tma_load_2d(&tmap_b, &b_full, b_tiles + (size_t)kb * b_kb_bytes, kb * CL_BK, n0);
       int it = 0, local = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+        // The A ring holds one tile per SM (64 KB): too few bytes in flight for the HBM latency.  The tiles this
+        // cluster will need next are pulled into L2 by bulk prefetches (no shared memory involved), so that the ring's
+        // own loads are L2 hits.
+        for (int ahead = (local == 0 ? 1 : p.prefetch); p.prefetch > 0 && ahead <= p.prefetch; ++ahead) {
+          const int pt = tile + ahead * num_clusters;
+          if (pt >= num_tiles) break;
+          for (int kb = 0; kb < num_kb; ++kb)
+            for (uint32_t j = rank; j < CL_ABOX; j += CS)
+              cl_prefetch_l2(&tmap_a, kb * CL_BK, pt * CL_BM + (int)j * (CL_BM / CL_ABOX));
+          if (HAS_E)
+            for (int j = 0; j < nbox; ++j) cl_prefetch_l2(&tmap_e, n0 + 64 * j, pt * CL_BM);
+        }
         if (HAS_E) {
           const int eb = local % CL_EC;
           mbar_wait(&e_empty[eb], (uint32_t)((local / CL_EC) & 1) ^ 1u);  // the store that used this buffer has read it
@@ -338,6 +357,8 @@ static int launch_cluster(const char* who, const void* A, int64_t lda, const voi
                "%s: multiplier operand must be 16-byte aligned with ld %% 8 == 0", who);
   ClParams p;
   p.bias = bias; p.M = M; p.N = N; p.K = K; p.act = act; p.mul_mode = mul_mode; p.keep = keep;
+  static const int pf_env = [] { const char* e = getenv("DFOL_CL_PREFETCH"); return e ? atoi(e) : 1; }();
+  p.prefetch = pf_env;   // (measured at c3: dgrad 1.08 ms without, 0.97 ms at distance 1, 0.98 at 2, 1.31 at 4)
   // columns per CTA and cluster size.  Two CTAs (half of the stored width each, whole 64-column boxes) measured best:
   // clusters of 3-4 CTAs leave room for a 7-8 stage A ring but run 2x slower (every ring stage is released by a
   // commit from every CTA of the cluster, and the lockstep of 3-4 SMs costs more than the deeper ring gains).

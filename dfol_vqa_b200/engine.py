@@ -42,10 +42,13 @@ def layout_tables(counts, concept_num, relation_num, pair_mask=None):
         'attr_stride': a_stride.astype(np.int32), 'rel_stride': r_stride.astype(np.int32),
         'attr_blk': attr_blk[:-1].astype(np.int64), 'rel_blk': rel_blk[:-1].astype(np.int64),
         'obj_img': np.repeat(np.arange(n.size, dtype=np.int32), n),
+        # 128-row tiles of the pair rows, per image (persistent tcgen05 kernels walk (image, tile) pairs)
+        'pair_tile': np.concatenate([[0], np.cumsum((npair * npair + 127) // 128)]).astype(np.int32),
     }
     meta = {'counts': [int(v) for v in n], 'B': int(n.size), 'T': int(n.sum()), 'P': int((npair * npair).sum()),
             'max_n': int(n.max()), 'max_np': int(npair.max()), 'attr_size': int(attr_blk[-1]),
             'rel_size': int(rel_blk[-1]), 'masked': pair_mask is not None,
+            'pair_tiles': int(((npair * npair + 127) // 128).sum()),
             'pair_images': int((npair > 0).sum())}
     assert meta['P'] < 2 ** 31 and meta['T'] < 2 ** 31
     return arrays, meta
@@ -114,9 +117,11 @@ class SceneLayout(object):
             views = dict(cache['lay'])
             if dense_pairs and meta['masked']:
                 views['img_np'], views['img_nn'], views['pair_row'] = views['img_n'], views['img_nn_d'], views['pair_row_d']
-                meta.update(P=meta['P_dense'], max_np=meta['max_n'], masked=False, pair_images=meta['B'])
-            views.pop('img_nn_d', None)
-            views.pop('pair_row_d', None)
+                views['pair_tile'] = views['pair_tile_d']
+                meta.update(P=meta['P_dense'], max_np=meta['max_n'], masked=False, pair_images=meta['B'],
+                            pair_tiles=meta['pair_tiles_dense'])
+            for k in ('img_nn_d', 'pair_row_d', 'pair_tile_d'):
+                views.pop(k, None)
             hit = cache[key] = cls(None, None, None, device, tables=(views, meta))
         return hit
 

@@ -376,12 +376,29 @@ class TensorCorePath(object):
     # -------------------------------------------------------------------------------------------- backward
 
     def _table_backward(self, g, tabs, ll, blk, stride, row0, img_rows, max_rows, rows_total, W, dW, db, h_last,
-                        d_below, st, tag, keep=1.0, remask=None):
+                        d_below, st, tag, keep=1.0, remask=None, tile_tab=None):
         """dZ (bf16, rows x padded width) of the layer below a table layer, from the compact gradient slices."""
         dev = ll.device
         E = W.shape[1]
         cols = h_last.shape[1]
         dz = torch.empty(rows_total, cols, device=dev, dtype=torch.bfloat16)
+        # (measured: the SIMT kernel's cost grows with the slices per image -- c3, 9-12 slices: 1.75 ms against 1.01 ms;
+        # c2 / c4: 0.60 against 0.37 ms -- while with the 1-3 slices of c1 it is level: 0.17 against 0.18 ms)
+        mma_min = int(os.environ.get('DFOL_TBL_MMA_MIN', '4'))
+        if (tile_tab is not None and mma_min <= tabs['max_per_image'] <= 32 and keep == 1.0 and 128 <= cols <= 320
+                and cols % 64 == 0):
+            # tcgen05 version (table_layer_bwd_mma.cu): the three contractions of the tile as MMAs, H read once
+            if capi.trace is not None:
+                S = tabs['max_per_image']
+                capi.next_meta = {'tag': 'table_layer_bwd_mma[%s]' % tag, 'bytes': 4.0 * rows_total * cols,
+                                  'flops': 2.0 * rows_total * cols * (2 * (16 if S <= 16 else 32) + 16)}
+            wb = torch.empty(len(tabs['img_slice']) - 1, 32 * cols, device=dev, dtype=torch.bfloat16)
+            call('dfol_table_layer_bwd_mma', ptr(g), ptr(tabs['goff']), ptr(tabs['col']), ptr(tabs['wrow']),
+                 ptr(tabs['img_slice']), len(tabs['img_slice']) - 1, tabs['max_per_image'], ptr(ll), ptr(blk),
+                 ptr(stride), ptr(row0), ptr(img_rows), ptr(tile_tab[0]), tile_tab[1], rows_total, ptr(W), W.stride(0),
+                 ptr(h_last), h_last.stride(0), E, ptr(dz), dz.stride(0), cols, ptr(dW), ptr(db), ptr(d_below), ptr(wb),
+                 st)
+            return dz
         if tabs['max_per_image'] <= 24:
             if capi.trace is not None:
                 passes = max(1, (tabs['max_per_image'] + 11) // 12)
@@ -479,7 +496,8 @@ class TensorCorePath(object):
             if scene.rel_slots:
                 dz2r = self._table_backward(g_rel, sr, scene.rel_ll, scene.rel_blk, lay.rel_stride, lay.pair_row,
                                             lay.img_nn, lay.max_n ** 2, P, w.emb.weight, G(w.emb.weight),
-                                            G(w.emb.bias), scene.rel_h[1], G(r1.bias), st, 'rel')
+                                            G(w.emb.bias), scene.rel_h[1], G(r1.bias), st, 'rel',
+                                            tile_tab=(lay.pair_tile, lay.pair_tiles))
             else:
                 nR = scene.w_rel.shape[0]
                 dw_rel = torch.zeros(nR, E, device=dev, dtype=torch.float32)

@@ -382,6 +382,19 @@ int dfol_table_layer_bwd_tc(const float* g, const int32_t* slice_goff, const int
                             const void* h_saved, int64_t ldh, int E, void* dZ, int64_t lddz, int out_cols, float* dW,
                             float* db, float* dbelow, float keep, void* stream);
 
+/* The same backward on the tensor cores (csrc/table_layer_bwd_mma.cu; tensor-core mode, no dropout, 128 <= cols <= 320,
+ * at most 32 slices per image): per 128-row tile of H (TMA) three tcgen05 contractions -- dZ = (DZ . Wslices) * h(1-h)
+ * written in place and stored by TMA, dW^T += H^T . DZ accumulated per image in TMEM, dbelow += dZ^T . 1 accumulated per
+ * CTA -- so H is read once and dZ written once.  tile_start[b] = prefix sums of ceil(img_rows[b] / 128)
+ * (images + 1 entries, total_tiles = the last one); wb_workspace: images * 32 * cols bf16 (per-image slice rows of W). */
+int dfol_table_layer_bwd_mma(const float* g, const int32_t* slice_goff, const int32_t* slice_col,
+                             const int32_t* slice_wrow, const int32_t* img_slice, int image_num, int max_slices,
+                             const float* ll, const int64_t* blk, const int32_t* stride, const int32_t* row0,
+                             const int32_t* img_rows, const int32_t* tile_start, int total_tiles, int64_t total_rows,
+                             const float* W, int64_t ldw, const void* h_saved, int64_t ldh, int E, void* dZ,
+                             int64_t lddz, int cols, float* dW, float* db, float* dbelow, void* wb_workspace,
+                             void* stream);
+
 /* Demand-driven relation table (tensor-core mode; replaces computing all nR columns of
  * ClassifierOracle.compute_all_log_likelihood_2, classifier_oracle.py:154, when the batch's programs are known):
  * image b owns slots [img_slot[b], img_slot[b+1]); slot j evaluates row slot_wrow[j] of the embedding layer:

@@ -277,3 +277,96 @@ def test_two_rank_nccl_gradients_equal_single_rank(mode, tmp_path):
     # all-reduce) differs
     tol = 1e-5 if mode == 'fp32' else 2e-3
     assert float((got['flat_grad'] - ref).abs().max()) <= tol * float(ref.abs().max()) + 1e-9
+
+
+# ------------------------------------------------------------------------------------------ table-layer backward (MMA)
+
+@pytest.mark.parametrize('counts,max_s', [([48] * 20, 3), ([100, 37, 64, 11], 12), ([16, 48, 5, 48, 33, 2, 48], 16),
+                                          ([48] * 8, 24), ([12, 100], 30), ([48] * 300, 2)])
+def test_table_layer_bwd_mma_matches_simt(counts, max_s):
+    """dfol_table_layer_bwd_mma (tcgen05: dZ = (DZ . Wslices) * h(1-h) in place, dW^T += H^T . DZ, column sums) against
+    the SIMT kernel dfol_table_layer_bwd_tc on the same inputs: dZ2 (bf16), dW rows, db, and the bias gradient of the
+    layer below.  Images with zero slices, partial last tiles (n^2 % 128 != 0) and up to 32 slices per image."""
+    from dfol_vqa_b200.capi import call, ptr, stream_ptr
+    from dfol_vqa_b200.engine import layout_tables
+    g = torch.Generator().manual_seed(sum(counts) + max_s)
+    E, cols, C = 300, 320, 50
+    arrays, meta = layout_tables(counts, C, 7, None)
+    B, P = len(counts), meta['P']
+    # slices: image b has s_b in [0, max_s] slices, each with a table column (< 7 distinct "slots") and a W row
+    s_b = torch.randint(0, max_s + 1, (B,), generator=g).tolist()
+    s_b[0] = max_s
+    if B > 2:
+        s_b[1] = 0
+    img_slice = [0]
+    goff, col, wrow = [], [], []
+    off = 0
+    for b, n in enumerate(counts):
+        for j in range(s_b[b]):
+            goff.append(off)
+            col.append(int(torch.randint(0, 7, (1,), generator=g)))
+            wrow.append(int(torch.randint(0, C, (1,), generator=g)))
+            off += (n * n + 3) // 4 * 4
+        img_slice.append(len(goff))
+    dev = lambda a, dt: torch.tensor(a if len(a) else [0], dtype=dt).cuda()
+    gvals = torch.randn(max(off, 4), generator=g) * 0.5
+    gvals[torch.rand(gvals.shape, generator=g) < 0.2] = 0.0
+    gvals = gvals.cuda()
+    stride = torch.from_numpy(arrays['rel_stride']).cuda()
+    blk = torch.from_numpy(arrays['rel_blk']).cuda()
+    ll = (-torch.rand(meta['rel_size'], generator=g) * 3.0).cuda()
+    W = (torch.randn(C, E, generator=g) * 0.3).cuda()
+    H = torch.zeros(P, cols, dtype=torch.bfloat16)
+    H[:, :E] = torch.rand(P, E, generator=g).bfloat16()
+    H = H.cuda()
+    row0 = torch.from_numpy(arrays['pair_row']).cuda()
+    rows = torch.from_numpy(arrays['img_nn']).cuda()
+    tiles = torch.from_numpy(arrays['pair_tile']).cuda()
+    t_goff, t_col, t_wrow, t_is = dev(goff, torch.int32), dev(col, torch.int32), dev(wrow, torch.int32), dev(img_slice, torch.int32)
+    outs = {}
+    for name in ('simt', 'mma'):
+        dZ = torch.full((P, cols), float('nan'), device='cuda', dtype=torch.bfloat16)
+        dW = torch.zeros(C, E, device='cuda')
+        db = torch.zeros(C, device='cuda')
+        dbelow = torch.zeros(E, device='cuda')
+        if name == 'simt':
+            if max_s > 24:
+                continue
+            call('dfol_table_layer_bwd_tc', ptr(gvals), ptr(t_goff), ptr(t_col), ptr(t_wrow), ptr(t_is), B,
+                 max(counts) ** 2, max(s_b), ptr(ll), ptr(blk), ptr(stride), ptr(row0), ptr(rows), ptr(W), E, ptr(H),
+                 cols, E, ptr(dZ), cols, cols, ptr(dW), ptr(db), ptr(dbelow), 1.0, stream_ptr())
+        else:
+            wb = torch.empty(B, 32 * cols, device='cuda', dtype=torch.bfloat16)
+            call('dfol_table_layer_bwd_mma', ptr(gvals), ptr(t_goff), ptr(t_col), ptr(t_wrow), ptr(t_is), B, max(s_b),
+                 ptr(ll), ptr(blk), ptr(stride), ptr(row0), ptr(rows), ptr(tiles), meta['pair_tiles'], P, ptr(W), E,
+                 ptr(H), cols, E, ptr(dZ), cols, cols, ptr(dW), ptr(db), ptr(dbelow), ptr(wb), stream_ptr())
+        torch.cuda.synchronize()
+        outs[name] = (dZ.float().cpu(), dW.cpu(), db.cpu(), dbelow.cpu())
+    # fp64 reference of the same formulas (dz rounded nowhere)
+    Hd, Wd = H.double().cpu(), W.double().cpu()
+    dZr = torch.zeros(P, cols, dtype=torch.float64)
+    dWr = torch.zeros(C, E, dtype=torch.float64)
+    dbr = torch.zeros(C, dtype=torch.float64)
+    gc, llc = gvals.double().cpu(), ll.double().cpu()
+    for b, n in enumerate(counts):
+        r0, nn = int(arrays['pair_row'][b]), n * n
+        for j in range(img_slice[b], img_slice[b + 1]):
+            lo = int(arrays['rel_blk'][b]) + col[j] * int(arrays['rel_stride'][b])
+            dz = gc[goff[j]:goff[j] + nn] * (1.0 - torch.exp(llc[lo:lo + nn]))
+            dZr[r0:r0 + nn, :E] += dz[:, None] * Wd[wrow[j]][None, :]
+            dWr[wrow[j]] += dz @ Hd[r0:r0 + nn, :E]
+            dbr[wrow[j]] += dz.sum()
+    dZr = dZr * Hd * (1 - Hd)
+    dZm, dWm, dbm, dbelm = outs['mma']
+    assert bool(torch.isfinite(dZm).all())
+    sc = float(dZr.abs().max())
+    assert float((dZm.double() - dZr).abs().max()) <= 1.5e-2 * sc + 1e-6
+    assert float((dWm.double() - dWr).abs().max()) <= 1e-2 * float(dWr.abs().max()) + 1e-5
+    assert float((dbm.double() - dbr).abs().max()) <= 1e-4 * float(dbr.abs().max()) + 1e-5
+    cs = dZm.double().sum(0)[:E]   # the kernel sums its own bf16 results
+    assert float((dbelm.double() - cs).abs().max()) <= 2e-3 * float(cs.abs().max()) + 1e-4
+    if 'simt' in outs:
+        dZs, dWs, dbs, dbels = outs['simt']
+        assert float((dZm - dZs).abs().max()) <= 1.5e-2 * sc + 1e-6
+        assert float((dWm - dWs).abs().max()) <= 1e-2 * float(dWs.abs().max()) + 1e-5
+        assert float((dbelm - dbels).abs().max()) <= 1e-2 * float(dbels.abs().max()) + 1e-4
