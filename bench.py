@@ -268,7 +268,10 @@ class LoweringDataset(object):
     object count of every image; the main process attaches the step's pinned feature tensor."""
 
     def __init__(self, question_lists, counts, compiler, give_answer, steps):
-        self.q, self.counts, self.compiler, self.give_answer, self.steps = question_lists, counts, compiler, give_answer, steps
+        import numpy as np
+        import torch
+        self.q, self.compiler, self.give_answer, self.steps = question_lists, compiler, give_answer, steps
+        self.bidx = [torch.from_numpy(np.repeat(np.arange(len(c), dtype=np.int64), c)) for c in counts]
 
     def __len__(self):
         return self.steps
@@ -277,13 +280,15 @@ class LoweringDataset(object):
         import torch
         from dfol_vqa_b200.programs import ProgramCollater, attach_compiled
         k = i % len(self.q)
-        bidx = torch.repeat_interleave(torch.arange(len(self.counts[k])), torch.tensor(self.counts[k]))
-        pb = ProgramCollater(1, lambda q: (None, bidx)).collate(json.loads(self.q[k]))[0]
+        pb = ProgramCollater(1, lambda q: (None, self.bidx[k])).collate(json.loads(self.q[k]))[0]
         attach_compiled(pb, self.compiler, give_answer=self.give_answer)
-        if self.give_answer is False and pb._answers is not None:
+        if not self.give_answer and pb._answers is not None:
             from dfol_vqa_b200.interpreter import targets_of
             cp = next(iter(pb._dfol_compiled.values()))
             pb._dfol_targets_host = torch.from_numpy(targets_of(cp, pb._answers))
+            # the training step reads the packed tables and the targets only: the op-slot objects (argument strings)
+            # and the option lists stay in the worker instead of being pickled to the trainer every step
+            pb.strip_for_training()
         return k, pb
 
 
@@ -616,7 +621,9 @@ class Bench(object):
             pb.pin_memory()   # packed tables + targets (features are pinned already)
             return pb
 
-        loader = DataLoader(ds, batch_size=None, shuffle=False, num_workers=workers,
+        # pin_memory: the loader's pin thread (not the training thread) unpickles the workers' results and pins the packed
+        # tables / targets through ProgramBatch.pin_memory()
+        loader = DataLoader(ds, batch_size=None, shuffle=False, num_workers=workers, pin_memory=True,
                             prefetch_factor=4 if workers > 0 else None, persistent_workers=False)
         it = iter(loader)
         pipeline.run([attach(next(it)) for _ in range(warmup)])

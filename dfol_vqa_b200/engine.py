@@ -352,11 +352,12 @@ class ReasoningEngine(object):
              ptr(g_attr), ptr(g_rel), ptr(getattr(scene, 'd_mods', None)), st)
         return g_attr, g_rel
 
-    def backward(self, cp, scene, tape, d_lp, grads):
+    def backward(self, cp, scene, tape, d_lp, grads, early_hook=None):
         """d loss / d parameters given d loss / d lp.  ``grads``: dict param tensor id -> fp32 grad tensor of the
-        parameter's shape (accumulated into; callers zero them)."""
+        parameter's shape (accumulated into; callers zero them).  ``early_hook``: called (tensor-core mode) once every
+        gradient except the first-layer / featurizer weights and the featurizer bias is final on the current stream."""
         if self.gemm_mode == 'bf16':
-            return self.tc.backward(cp, scene, tape, d_lp, grads)
+            return self.tc.backward(cp, scene, tape, d_lp, grads, early_hook)
         w = self.w
         lay = scene.layout
         dev = scene.attr_ll.device

@@ -442,7 +442,7 @@ class TensorCorePath(object):
         call('dfol_cast_bf16', ptr(d), E, ptr(dz), cols, rows_total, E, st)
         return dz
 
-    def backward(self, cp, scene, tape, d_lp, grads):
+    def backward(self, cp, scene, tape, d_lp, grads, early_hook=None):
         eng = self.engine
         w = self.w
         lay = scene.layout
@@ -455,7 +455,7 @@ class TensorCorePath(object):
         T, P = lay.T, lay.P
         TensorCorePath._P = P
         if getattr(scene, 'dropout', None) is not None:
-            return self._backward_dropout(cp, scene, tape, d_lp, grads)
+            return self._backward_dropout(cp, scene, tape, d_lp, grads)   # (no early hook: one all-reduce at the end)
         assert scene.geo is not None, 'scene was built without training buffers'
 
         def G(prm):
@@ -527,6 +527,10 @@ class TensorCorePath(object):
                 self._wgrad(dcat[:, Hap + Hp:], H, scene.obj16, ldo, gw1[:, ldo:2 * ldo], st)
 
         main.wait_event(ev_attr)  # dcat[:, :Hap] and the attribute-side gradients are complete
+        if early_hook is not None:
+            # table layers, second layers, pair hidden layer and all biases but the featurizer's are done: their share
+            # of the gradient bucket can be all-reduced while the first-layer / featurizer kernels below run
+            early_hook()
         if merged:
             gw1 = G(r0.weight)
             if capi.trace is not None:

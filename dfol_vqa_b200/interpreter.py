@@ -409,11 +409,26 @@ class FusedTrainStep(object):
         # the optimizer sees the trainable parameters only (VQATrainer.get_parameter_list); frozen oracle tensors
         # (sample_config.yaml freezes all four networks) stay out of the bucket and get scratch gradient buffers
         self.attention_params = [p for p in interpreter.attention_parameters() if p.requires_grad]
-        params = [p for p in oracle_params if p.requires_grad] + self.attention_params
+        # Bucket order = [gradients that are final LATE in the backward pass | those that are final EARLY]: the
+        # first-layer / featurizer weights (and the featurizer bias, and the attention networks) are written by the last
+        # kernels of the step; every other oracle gradient is complete once the table layers, the second layers and the
+        # pair hidden layer have run.  With several ranks the EARLY segment is all-reduced on a communication stream
+        # while the remaining backward kernels run (reference: the reduce-add of nn.DataParallel, data_parallel.py:54-57)
+        w = interpreter._weights
+        late_ids = {id(w.feat.weight), id(w.feat.bias), id(w.attr[0].weight), id(w.rel[0].weight)}
+        trainable = [p for p in oracle_params if p.requires_grad]
+        late = [p for p in trainable if id(p) in late_ids] + self.attention_params
+        early = [p for p in trainable if id(p) not in late_ids]
+        params = late + early
         assert params, 'nothing to train'
         self.params = params
         self.oracle_trainable = any(p.requires_grad for p in oracle_params)
         dev = params[0].device
+        self.early_offset = sum(p.numel() for p in late)
+        self.early_numel = sum(p.numel() for p in early)
+        self._early_work = None
+        self._comm_stream = None
+        self.overlap = os.environ.get('DFOL_AR_OVERLAP', '1') != '0'
         self.bucket = FlatBucket(params)
         self.flat, self.flat_grad, self.grads = self.bucket.flat, self.bucket.flat_grad, dict(self.bucket.grads)
         for p in oracle_params:
@@ -467,17 +482,43 @@ class FusedTrainStep(object):
             call('dfol_loss_fwd_bwd', ptr(lp), ptr(target), ptr(seg), cp.question_num, cp.lp_num, cp.kind, scale,
                  ptr(self.scalars), ptr(d_lp), st)
             if self.oracle_trainable:
-                self.engine.backward(cp, scene, tape, d_lp, self.grads)
+                last = k == len(program_batch_list) - 1
+                hook = self._reduce_early if (last and self.world > 1 and self.overlap and self.early_numel) else None
+                self.engine.backward(cp, scene, tape, d_lp, self.grads, early_hook=hook)
             else:
                 self.engine.program_backward(cp, scene, tape, d_lp)
             if mod_ctx is not None and self.attention_params:
                 att.backward(mod_ctx, scene.d_mods, self.grads)
         return self.scalars[0]
 
+    def _reduce_early(self):
+        """Called by the backward pass at the point where the EARLY segment of the bucket is final: its all-reduce starts
+        on the communication stream, behind an event of the compute stream, and overlaps the rest of the backward."""
+        dev = self.flat.device
+        main = torch.cuda.current_stream(dev)
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._comm_stream.wait_event(ev)
+        with torch.cuda.stream(self._comm_stream):
+            self._early_work = torch.distributed.all_reduce(self.flat_grad[self.early_offset:],
+                                                            op=torch.distributed.ReduceOp.SUM, group=self.group,
+                                                            async_op=True)
+
     def reduce_gradients(self):
-        """Sum of the flat gradient bucket over the data-parallel ranks (one NCCL all-reduce; replaces the reduce-add
-        of nn.DataParallel, reference nn/interpreter/data_parallel.py:54-57)."""
-        if self.world > 1:
+        """Sum of the flat gradient bucket over the data-parallel ranks (NCCL; replaces the reduce-add of
+        nn.DataParallel, reference nn/interpreter/data_parallel.py:54-57): one all-reduce, or -- when the backward pass
+        started the early segment on the communication stream -- the late segment now and a wait for the early one."""
+        if self.world <= 1:
+            return
+        if self._early_work is not None:
+            if self.early_offset:
+                torch.distributed.all_reduce(self.flat_grad[:self.early_offset], op=torch.distributed.ReduceOp.SUM,
+                                             group=self.group)
+            self._early_work.wait()   # the compute stream waits for the communication stream
+            self._early_work = None
+        else:
             self.bucket.all_reduce(self.group)
 
     def optimizer_step(self):

@@ -118,6 +118,22 @@ class ProgramBatch(object):
             self._dfol_targets_host = self._dfol_targets_host.pin_memory()
         return self
 
+    def strip_for_training(self):
+        """Drops what FusedTrainStep never reads from a COMPILED batch -- the op-slot objects with their argument
+        strings, the answer strings (the loss targets are already a tensor), the per-question option lists -- so that a
+        DataLoader worker hands the trainer a few hundred KB of packed tables instead of pickling Python object graphs.
+        The result dict of FastGQAInterpreter.forward needs them: do not strip batches meant for evaluation."""
+        assert getattr(self, '_dfol_compiled', None), 'strip_for_training: compile the batch first (attach_compiled)'
+        self._op_batch_list, self._dependencies, self._original_dicts = [], [], None
+        import numpy as np
+        for cp in self._dfol_compiled.values():
+            cp.options, cp.names, cp.mod_descs, cp.slot_names = [], [], cp.mod_descs if cp.mod_rows else [], []
+            # every table the kernels read is in the packed blob: the arrays / tuple lists it was packed from stay behind
+            # (the step needs the instruction COUNT only)
+            cp.instr = np.empty((cp.instr.shape[0], 0), dtype=np.int32)
+            cp.attr_slices = cp.rel_slices = cp.layout_arrays = cp.opts = cp.slot_after = None
+        return self
+
     _staged = None
 
     def stage_bf16(self, drop_fp32=False):
@@ -144,6 +160,7 @@ class ProgramBatch(object):
         pb = ProgramBatch(torch.device('cuda', device) if isinstance(device, int) else device, self._op_batch_list,
                           self._dependencies, self._answers, feats, bidx, self._original_dicts, self._meta_data)
         pb._staged = staged
+        pb._batch_size = self._batch_size   # (a batch stripped for training has no op slots to count from)
         # collate-time products of the fused path (compiled bytecode, object counts, targets) travel with the batch
         for key in ('_dfol_compiled', '_dfol_counts', '_dfol_targets'):
             if hasattr(self, key):
