@@ -31,6 +31,7 @@ struct TcParams {
   // optional epilogue multiplier (backward): v *= act'(h) with h = mul_src[m * ld_mul + n] (bf16), DFOL_MUL_*
   const __nv_bfloat16* mul_src; long long ld_mul; int mul_mode;
   float keep;  // < 1: mul_src holds post-dropout activations (0 / h / keep): act' at h = src * keep, factor (src != 0) / keep
+  int exact;   // accurate expf / log1pf activations (fp32 parity mode on split-bf16 operands) instead of the MUFU forms
 };
 
 template <int ACT>
@@ -150,7 +151,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc_kernel(const __grid_c
       if (!row_ok) continue;
       float v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = act_fast<ACT>(__uint_as_float(r[j]) + bias_s[c0 + j]);
+      for (int j = 0; j < 16; ++j) {
+        const float x = __uint_as_float(r[j]) + bias_s[c0 + j];
+        v[j] = p.exact ? act_apply(x, ACT) : act_fast<ACT>(x);
+      }
       if (STORE != ST_TABLE && p.mul_mode != DFOL_MUL_NONE && c0 + 16 <= n_valid) {
         const uint4* hp = reinterpret_cast<const uint4*>(p.mul_src + (long long)m * p.ld_mul + n0 + c0);
         const uint4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
@@ -254,7 +258,7 @@ static int launch_tc(const char* who, const void* A, int64_t lda, const void* B,
                      const float* bias, int M, int N, int K, int act, int out_bf16, int store, const int32_t* row_img,
                      const int32_t* img_row, const int64_t* img_blk, const int32_t* img_stride, const int32_t* img_n,
                      float diag_value, const void* mul_src, int64_t ld_mul, int mul_mode, int store_cols,
-                     void* stream, float keep = 1.0f) {
+                     void* stream, float keep = 1.0f, int exact = 0) {
   DFOL_REQUIRE(keep > 0.0f && keep <= 1.0f, "%s: keep = 1 - dropout p must be in (0, 1]", who);
   DFOL_REQUIRE(A && B && C, "%s: null pointer", who);
   DFOL_REQUIRE(M > 0 && N > 0 && K > 0 && (K % TC_BK) == 0, "%s: K must be a positive multiple of 64", who);
@@ -286,6 +290,7 @@ static int launch_tc(const char* who, const void* A, int64_t lda, const void* B,
   p.diag_value = diag_value;
   p.mul_src = reinterpret_cast<const __nv_bfloat16*>(mul_src); p.ld_mul = ld_mul; p.mul_mode = mul_mode;
   p.keep = keep;
+  p.exact = exact;
   const int stage_bytes = (TC_BM + BN) * TC_BK * 2;
   int stages = (110 * 1024) / stage_bytes;  // two CTAs per SM
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -322,4 +327,86 @@ extern "C" int dfol_gemm_bf16_tc_dgrad(const void* dZ, int64_t lddz, const void*
                                        int64_t ldh, int mul_mode, float keep, void* stream) {
   return launch_tc("dfol_gemm_bf16_tc_dgrad", dZ, lddz, Wt, ldwt, dX, lddx, nullptr, M, N, K, DFOL_ACT_NONE, 1, 0,
                    nullptr, nullptr, nullptr, nullptr, nullptr, 0.0f, h_saved, ldh, mul_mode, store_cols, stream, keep);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 parity mode on the tensor cores: an fp32 operand x is split into three bf16 parts x = h + m + l
+// (h = bf16(x), m = bf16(x - h), l = bf16(x - h - m): 24 mantissa bits) and the product a . b is evaluated as the six
+// terms hl + lh + mm + hm + mh + hh (the dropped ml + lm + ll are below 2^-24 relative) by ONE bf16 GEMM over operands
+// concatenated along K: A' = [Ah | Al | Am | Ah | Am | Ah], B' = [Bl | Bh | Bm | Bm | Bh | Bh], fp32 accumulation in
+// TMEM.  The same tcgen05 kernels as the bf16 mode, six times the MMA work, fp32-level results.
+namespace dfol {
+// Block order = ascending magnitude of the product terms: (hl, lh, mm) ~ 2^-16, (hm, mh) ~ 2^-8, hh last.  The tensor
+// core's fp32 accumulation truncates at the magnitude of the running sum: adding the small terms FIRST keeps their
+// low bits (measured: hh first leaves a relative bias of ~1.4e-5 at K = 2048, small terms first ~3e-6).
+//   pattern 0 (A side): h l m h m h      pattern 1 (B side): l h m m h h
+template <int STACKED>
+__global__ void __launch_bounds__(256) split3_bf16_kernel(const float* __restrict__ src, long long lds, long long rows,
+                                                          int cols, __nv_bfloat16* __restrict__ dst, long long ldd,
+                                                          int Kp, int pattern) {
+  // one thread = 8 consecutive columns of one row: 16-byte stores into each of the six blocks
+  const int width = STACKED ? (int)ldd : Kp;          // columns covered per block (multiple of 8)
+  const int groups = width / 8;
+  const long long total = rows * (long long)groups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / groups;
+    const int c0 = (int)(idx - r * groups) * 8;
+    float x[8];
+    const float* sp = src + r * lds + c0;
+    if (c0 + 8 <= cols && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0)) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(sp)), b = __ldg(reinterpret_cast<const float4*>(sp) + 1);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = (c0 + j < cols) ? __ldg(sp + j) : 0.0f;
+    }
+    uint32_t hp[4], mp[4], lp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+      const float2 hf = __bfloat1622float2(h);
+      const float r0 = x[2 * j] - hf.x, r1 = x[2 * j + 1] - hf.y;
+      const __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
+      const float2 mf = __bfloat1622float2(m);
+      const __nv_bfloat162 l = __floats2bfloat162_rn(r0 - mf.x, r1 - mf.y);
+      hp[j] = *reinterpret_cast<const uint32_t*>(&h);
+      mp[j] = *reinterpret_cast<const uint32_t*>(&m);
+      lp[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    const uint4 H = make_uint4(hp[0], hp[1], hp[2], hp[3]), Mv = make_uint4(mp[0], mp[1], mp[2], mp[3]),
+                L = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      // A side: h l m h m h ; B side: l h m m h h
+      const uint4 v = pattern == 0 ? (k == 1 ? L : ((k == 2 || k == 4) ? Mv : H))
+                                   : (k == 0 ? L : ((k == 2 || k == 3) ? Mv : H));
+      __nv_bfloat16* dp = STACKED ? dst + (k * rows + r) * ldd + c0 : dst + r * ldd + (long long)k * Kp + c0;
+      *reinterpret_cast<uint4*>(dp) = v;
+    }
+  }
+}
+}  // namespace dfol
+
+extern "C" int dfol_split3_bf16(const float* src, int64_t lds, int64_t rows, int cols, void* dst, int64_t ldd, int Kp,
+                                int pattern, int stacked, void* stream) {
+  DFOL_REQUIRE(src && dst && rows > 0 && cols > 0, "dfol_split3_bf16: bad arguments");
+  DFOL_REQUIRE(stacked ? (ldd >= cols && (ldd % 8) == 0) : (Kp >= cols && (Kp % 8) == 0 && ldd >= 6ll * Kp && (ldd % 8) == 0),
+               "dfol_split3_bf16: destination too narrow or not a multiple of 8 columns");
+  DFOL_REQUIRE((reinterpret_cast<uintptr_t>(dst) % 16) == 0, "dfol_split3_bf16: destination must be 16-byte aligned");
+  const long long total = rows * (long long)((stacked ? ldd : Kp) / 8);
+  const long long want = (total + 255) / 256;
+  const int blocks = (int)(want < 148 * 32 ? want : 148 * 32);
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
+  if (stacked) split3_bf16_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, rows, cols, d, ldd, Kp, pattern);
+  else split3_bf16_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, rows, cols, d, ldd, Kp, pattern);
+  return finish_launch("dfol_split3_bf16");
+}
+
+extern "C" int dfol_gemm_bf16_tc_exact(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                                       int store_cols, const float* bias, int M, int N, int K, int act, int store,
+                                       const int32_t* row_img, const int32_t* img_row, const int64_t* img_blk,
+                                       const int32_t* img_stride, const int32_t* img_n, float diag_value, void* stream) {
+  return launch_tc("dfol_gemm_bf16_tc_exact", A, lda, B, ldb, C, ldc, bias, M, N, K, act, 0, store, row_img, img_row,
+                   img_blk, img_stride, img_n, diag_value, nullptr, 0, DFOL_MUL_NONE, store_cols, stream, 1.0f, 1);
 }

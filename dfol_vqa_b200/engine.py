@@ -126,12 +126,91 @@ class SceneLayout(object):
         return hit
 
 
+# fp32 parity mode: contractions large enough for the tensor cores run there as split-bf16 GEMMs (x = h + m + l, six
+# product terms, fp32 TMEM accumulation: csrc/gemm_tcgen05.cu dfol_split3_bf16); small ones, strided operands the TMA
+# maps cannot describe, and DFOL_FP32_SIMT=1 use the SIMT kernel (exact fp32 FMA chain).
+_FP32_TC_MIN_WORK = 1 << 24
+
+
+def _fp32_tc_enabled():
+    import os
+    return os.environ.get('DFOL_FP32_SIMT', '0') != '1'
+
+
+def _split3(x, pattern, stacked, Kp, st):
+    """Concatenated three-way bf16 split of the row-major fp32 matrix view ``x`` (rows, cols)."""
+    rows, cols = x.shape
+    if stacked:
+        ld = _roundup(cols, 8)
+        out = torch.empty(6 * rows, ld, device=x.device, dtype=torch.bfloat16)   # (pad columns are written as zeros)
+    else:
+        ld = 6 * Kp
+        out = torch.empty(rows, ld, device=x.device, dtype=torch.bfloat16)
+    call('dfol_split3_bf16', ptr(x), x.stride(0), rows, cols, ptr(out), ld, Kp, pattern, int(stacked), st)
+    return out
+
+
+def _gemm_f32_tc(A, B, C, bias, act, accumulate, split_k, table, st):
+    """Tensor-core evaluation of gemm_f32's contract; returns False when the operand layout is not one of the three forms
+    the path uses (NT: activations x weight^T, NN: gradient x weight, TN: gradient^T x activations)."""
+    M, Kd = A.shape
+    N = B.shape[1]
+    a_row = A.stride(1) == 1 and A.stride(0) >= Kd
+    b_col = B.stride(0) == 1 and B.stride(1) >= Kd          # B = W^T view of a row-major W [N, K]
+    b_row = B.stride(1) == 1 and B.stride(0) >= N           # B row-major [K, N]
+    a_col = A.stride(0) == 1 and A.stride(1) >= M           # A = X^T view of a row-major X [K, M]
+    if a_col and b_row and table is None and bias is None and act == K.ACT_NONE:
+        # TN (weight gradient): C[M, N] (+)= X^T . B, reduction over the Kd rows of X and B -> MN-major wgrad kernel
+        X = A.t()
+        if capi.trace is not None:
+            capi.next_meta = {'tag': 'gemm_f32_tc_wgrad[%dx%dx%d]' % (M, N, Kd), 'flops': 12.0 * M * N * Kd}
+        if not accumulate and split_k == 1:
+            C.zero_()
+        xa, xb = _split3(X, 0, True, 0, st), _split3(B, 1, True, 0, st)
+        assert C.stride(1) == 1
+        call('dfol_gemm_bf16_tc_wgrad', ptr(xa), xa.stride(0), ptr(xb), xb.stride(0), ptr(C), C.stride(0), M, N,
+             6 * Kd, st)
+        return True
+    if not a_row:
+        return False
+    if b_col:
+        W = B.t()                                            # row-major [N, K]
+    elif b_row:
+        W = B.t().contiguous()                               # NN (input gradient): small weight matrix, transposed once
+    else:
+        return False
+    Kp = _roundup(Kd, 64)
+    xa, xb = _split3(A, 0, False, Kp, st), _split3(W, 1, False, Kp, st)
+    if table is None:
+        out = C if not accumulate else torch.empty(M, N, device=C.device, dtype=torch.float32)
+        assert out.stride(1) == 1
+        ldc, store, maps, diag = out.stride(0), 0, (None, None, None, None, None), 0.0
+    else:
+        out, ldc, store = C, 0, 1
+        maps = (ptr(table['row_img']), ptr(table['img_row']), ptr(table['img_blk']), ptr(table['img_stride']),
+                ptr(table.get('img_n')))
+        diag = table.get('diag', DEFAULT_LL)
+    if capi.trace is not None:
+        capi.next_meta = {'tag': 'gemm_f32_tc[%dx%dx%d]%s' % (M, N, Kd, ' table' if store else ''),
+                          'flops': 12.0 * M * N * Kd}
+    call('dfol_gemm_bf16_tc_exact', ptr(xa), 6 * Kp, ptr(xb), 6 * Kp, ptr(out), ldc, N, ptr(bias), M, N, 6 * Kp, act,
+         store, maps[0], maps[1], maps[2], maps[3], maps[4], diag, st)
+    if accumulate and table is None:
+        C += out
+    return True
+
+
 def gemm_f32(A, B, C, bias=None, act=K.ACT_NONE, accumulate=False, split_k=1, mul_src=None, mul_mode=K.MUL_NONE,
              table=None, stream=None):
     """C = epilogue(A @ B) with A (M,K) and B (K,N) arbitrary-stride fp32 views; see dfol_gemm_f32."""
     M, Kd = A.shape
     Kb, N = B.shape
     assert Kd == Kb
+    if (mul_src is None and float(M) * N * Kd >= _FP32_TC_MIN_WORK and min(M, N) >= 16 and _fp32_tc_enabled()
+            and M < 65535 * 128):
+        st = stream if stream is not None else capi.stream_ptr(A.device)
+        if _gemm_f32_tc(A, B, C, bias, act, accumulate, split_k, table, st):
+            return
     if table is None:
         assert C.shape == (M, N) and C.stride(1) == 1
         ldc, store, maps, diag = C.stride(0), 0, (None, None, None, None, None), 0.0

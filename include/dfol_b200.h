@@ -101,6 +101,20 @@ int dfol_gemm_bf16_tc_wgrad_seg(const void* A, int64_t lda, const void* B, int64
                                 float* C1, int64_t ldc1, float* C2, int64_t ldc2, int seg_rows, int M, int N, int64_t K,
                                 void* stream);
 
+/* fp32 parity mode on the tensor cores (split-bf16: x = h + m + l, six product terms, one bf16 GEMM over operands
+ * concatenated along K, fp32 TMEM accumulation; replaces the fp32 nn.Linear arithmetic of classifier_oracle.py:145-156
+ * with results at fp32 level).  dfol_split3_bf16 writes the concatenated operand of an fp32 matrix: pattern 0 (A side:
+ * h l m h m h) or 1 (B side: l h m m h h; smallest product terms first, hh last); stacked == 0: dst[r, k*Kp + c] (K-concatenated, zero padded to Kp, for
+ * dfol_gemm_bf16_tc_exact); stacked != 0: dst[(k*rows + r), c] (row-concatenated, for dfol_gemm_bf16_tc_wgrad).
+ * dfol_gemm_bf16_tc_exact = dfol_gemm_bf16_tc with fp32 output, accurate (expf / log1pf) activations and an explicit
+ * stored width. */
+int dfol_split3_bf16(const float* src, int64_t lds, int64_t rows, int cols, void* dst, int64_t ldd, int Kp, int pattern,
+                     int stacked, void* stream);
+int dfol_gemm_bf16_tc_exact(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                            int store_cols, const float* bias, int M, int N, int K, int act, int store,
+                            const int32_t* row_img, const int32_t* img_row, const int64_t* img_blk,
+                            const int32_t* img_stride, const int32_t* img_n, float diag_value, void* stream);
+
 /* Batched operand preparation: job j casts (and, if transpose != 0, transposes) the fp32 view src[rows][cols]
  * (row stride lds) into columns [0, dcols) of the bf16 rows dst[out_rows][ldd], zero beyond the source extent.
  * `jobs` is a DEVICE array of job_num records of dfol_cast_job_size() bytes:
