@@ -52,6 +52,63 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ lp,
   }
 }
 
+// Answers on the device (eval / predict path; reference: the per-op .cpu().numpy().tolist() of batch_gqa_ops.py:222-225,
+// :404-407, :744-748 and util.find_max_ind util.py:64-66).  One warp per question:
+//   mode 0 (binary)  : best = exp(lp) > 0.5 (1 = yes), count = 1
+//   mode 1 (options) : p = exp(lp) over the question's option segment; the answer set is {k : p_k == max p and
+//                      p_k > threshold} (exact ties, as find_max_ind); first = first member, count = size of the set,
+//                      sel[k] = membership
+//   mode 2 (compare) : argmax of the two entries (first wins a tie, as numpy.argmax)
+// so the host reads 12 bytes per question instead of the whole log-probability vector (5 KB for a 1356-noun query) and
+// only touches the membership bytes of questions whose answer is not a single option.
+__global__ void __launch_bounds__(256) answers_kernel(const float* __restrict__ lp, const int32_t* __restrict__ seg,
+                                                      int n_q, int mode, float threshold, int32_t* __restrict__ first,
+                                                      int32_t* __restrict__ count, float* __restrict__ best_lp,
+                                                      uint8_t* __restrict__ sel) {
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (q >= n_q) return;
+  if (mode == 0) {
+    if (lane == 0) {
+      const float x = lp[q];
+      first[q] = expf(x) > 0.5f ? 1 : 0;
+      count[q] = 1;
+      best_lp[q] = x;
+    }
+    return;
+  }
+  const int a = seg[q], b = seg[q + 1];
+  if (mode == 2) {
+    if (lane == 0) {
+      const int k = lp[a + 1] > lp[a] ? 1 : 0;
+      first[q] = k;
+      count[q] = 1;
+      best_lp[q] = lp[a + k];
+    }
+    return;
+  }
+  float mx = -1.0f;
+  for (int k = a + lane; k < b; k += 32) mx = fmaxf(mx, expf(lp[k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  int cnt = 0, fst = 0x7fffffff;
+  for (int k = a + lane; k < b; k += 32) {
+    const float pk = expf(lp[k]);
+    const bool in = (pk == mx) && (pk > threshold);
+    if (sel != nullptr) sel[k] = in ? 1 : 0;
+    if (in) { ++cnt; fst = min(fst, k - a); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    fst = min(fst, __shfl_xor_sync(0xffffffffu, fst, o));
+  }
+  if (lane == 0) {
+    first[q] = cnt > 0 ? fst : -1;
+    count[q] = cnt;
+    best_lp[q] = cnt > 0 ? lp[a + fst] : 0.0f;
+  }
+}
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* out) {
   __shared__ float red[8];
   float acc = 0.f;
@@ -129,4 +186,15 @@ extern "C" int dfol_adam_step(float* p, const float* g, float* m, float* v, int6
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, sumsq, clip_norm, lr, beta1, beta2, eps,
                                                        weight_decay, bc1, sqrtf(bc2));
   return finish_launch("dfol_adam_step");
+}
+
+extern "C" int dfol_answers(const float* lp, const int32_t* seg, int question_num, int mode, float threshold,
+                            int32_t* first, int32_t* count, float* best_lp, uint8_t* sel, void* stream) {
+  DFOL_REQUIRE(lp && first && count && best_lp && (mode == 0 || seg), "dfol_answers: null pointer");
+  DFOL_REQUIRE(mode >= 0 && mode <= 2, "dfol_answers: mode must be 0 (binary), 1 (options) or 2 (compare)");
+  if (question_num == 0) return 0;
+  const int blocks = (question_num * 32 + 255) / 256;
+  dfol::answers_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(lp, seg, question_num, mode, threshold, first, count,
+                                                                best_lp, sel);
+  return dfol::finish_launch("dfol_answers");
 }

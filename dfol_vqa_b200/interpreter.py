@@ -341,18 +341,63 @@ class FastGQAInterpreter(nn.Module):
         elif kind == BINARY:
             options = ['no', 'yes']
         if give_answer:
-            host = lp.detach().cpu().numpy()
             start = 0
             for cp in metas:
-                a, alp = self._answers(cp, host[start:start + cp.lp_num])
+                a, alp = self._answers_device(cp, lp.detach()[start:start + cp.lp_num])
                 answer += a
                 answer_lp += alp
                 start += cp.lp_num
         return {'answer': answer, 'log_probability': lp, 'options': options, 'variable_set': None, 'type': kind,
                 'cumulative_loss': 0, 'variable_sets_num': 0, 'answer_log_probability': answer_lp}
 
+    def _answers_device(self, cp, lp):
+        """Answer lists of one compiled batch with the decision made ON THE DEVICE (dfol_answers: yes / no, argmax with
+        find_max_ind's exact-tie semantics and the likelihood threshold, compare): the host reads 12 bytes per question
+        and builds the answer strings; the membership bytes and log-probabilities of a question are only fetched when
+        its answer is not a single option (exact ties).  Reference: batch_gqa_ops.py:222-225, :404-407, :744-748,
+        util.py:64-66."""
+        if cp.kind == STATEMENT:
+            return [[n] for n in cp.names], []
+        dev = lp.device
+        Q = cp.question_num
+        mode = 0 if cp.kind == BINARY else (2 if cp.terminal == 'compare' else 1)
+        seg = None if mode == 0 else self._engine.upload_programs(cp, dev)['seg']
+        out = torch.empty(3 * Q, device=dev, dtype=torch.int32)
+        sel = torch.empty(cp.lp_num, device=dev, dtype=torch.uint8) if mode == 1 else None
+        lp = lp.contiguous()
+        call('dfol_answers', ptr(lp), ptr(seg), Q, mode, float(self._likelihood_threshold), ptr(out[:Q]),
+             ptr(out[Q:2 * Q]), ptr(out[2 * Q:]), ptr(sel), capi.stream_ptr(dev))
+        host = out.cpu().numpy()
+        first, count = host[:Q], host[Q:2 * Q]
+        best = host[2 * Q:].view(np.float32)
+        if mode == 0:
+            p = np.exp(best)
+            ans = [['yes'] if f else ['no'] for f in first]
+            alp = [[math.log(float(v))] if f else [math.log(1.0 - float(v))] for v, f in zip(p, first)]
+            return ans, alp
+        if mode == 2:
+            return [[opt[k]] for opt, k in zip(cp.options, first)], [[float(v)] for v in best]
+        ans, alp = [], []
+        sel_host = lp_host = None
+        for q, opts in enumerate(cp.options):
+            if count[q] == 1:
+                ans.append([opts[first[q]]])
+                alp.append([float(best[q])])
+            elif count[q] == 0:
+                ans.append([])
+                alp.append([])
+            else:   # exact ties: every option attaining the maximum (find_max_ind)
+                if sel_host is None:
+                    sel_host, lp_host = sel.cpu().numpy(), lp.cpu().numpy()
+                a, b = int(cp.seg[q]), int(cp.seg[q + 1])
+                keep = sel_host[a:b] != 0
+                ans.append([o for o, k in zip(opts, keep) if k])
+                alp.append([float(v) for v, k in zip(lp_host[a:b], keep) if k])
+        return ans, alp
+
     def _answers(self, cp, lp):
-        """Host-side answer lists from the log-probabilities (reference: batch_gqa_ops.py:222-225, 404-407, 744-748,
+        """Host-side answer lists from the log-probabilities (the same semantics evaluated with numpy; the tests hold
+        the device version to it) (reference: batch_gqa_ops.py:222-225, 404-407, 744-748,
         util.find_max_ind util.py:64-66)."""
         if cp.kind == STATEMENT:
             return [[n] for n in cp.names], []

@@ -427,6 +427,14 @@ int dfol_table_grad_dense(const float* g, const int32_t* slice_goff, const int32
                           const int32_t* stride, const int32_t* row0, const int32_t* img_rows, float* dZ,
                           int64_t lddz, void* stream);
 
+/* Answers on the device (eval / predict; reference: batch_gqa_ops.py:222-225, :404-407, :744-748, util.find_max_ind
+ * util.py:64-66).  mode 0 binary (first = exp(lp) > 0.5), mode 1 option lists (segments seg[q]..seg[q+1]: the answer set
+ * is every option whose probability equals the maximum exactly and exceeds `threshold`; first = first member or -1,
+ * count = size, sel[k] = membership, may be NULL), mode 2 compare (argmax of the two entries).  best_lp = log-probability
+ * of the first member. */
+int dfol_answers(const float* lp, const int32_t* seg, int question_num, int mode, float threshold, int32_t* first,
+                 int32_t* count, float* best_lp, uint8_t* sel, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Optimiser step on the flat parameter bucket: clip_grad_norm_ + Adam (trainer.py:438-441,
  * gqa_interpreter_experiments.py:261: torch.optim.Adam(lr, weight_decay) = L2 added to the gradient).

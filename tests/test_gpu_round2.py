@@ -370,3 +370,40 @@ def test_table_layer_bwd_mma_matches_simt(counts, max_s):
         assert float((dZm - dZs).abs().max()) <= 1.5e-2 * sc + 1e-6
         assert float((dWm - dWs).abs().max()) <= 1e-2 * float(dWs.abs().max()) + 1e-5
         assert float((dbelm - dbels).abs().max()) <= 1e-2 * float(dbels.abs().max()) + 1e-4
+
+
+# ------------------------------------------------------------------------------------------ device-side answers (f4)
+
+@pytest.mark.parametrize('terminal', ['exist', 'query_attr', 'choose_attr', 'compare'])
+def test_device_answers_match_host_semantics(terminal):
+    """dfol_answers (decision on the device, 12 bytes per question read back) against the numpy statement of the same
+    rules (find_max_ind exact ties, likelihood threshold, yes/no at p > 0.5, compare argmax), on log-probabilities with
+    forced exact ties, all-below-threshold questions and p == 0.5 boundaries."""
+    from dfol_vqa_b200 import synth
+    from dfol_vqa_b200.ontology import synthetic_ontology
+    dims = dict(box=256, feat=64, hidden=32, emb=48)
+    ont = synthetic_ontology(300, 40, 6, 5, seed=3, embedding_dim=48)
+    interp = helpers.build_interpreter(ont, dims, seed=5, gemm_mode='fp32', likelihood_threshold=1e-3)
+    questions = synth.make_questions(ont, 24, terminal, 1, 3, seed=61)
+    counts = synth.object_counts(24, 12, True, seed=62)
+    feats, bidx = synth.make_object_features(counts, 256, seed=63)
+    pbs = helpers.to_cuda(_collate(questions, feats, bidx))
+    cp = interp.compiled(pbs[0], True)
+    g = torch.Generator().manual_seed(7)
+    lp = -torch.rand(cp.lp_num, generator=g) * 6.0
+    if cp.seg is not None and terminal != 'compare':
+        for q in range(0, cp.question_num, 3):       # exact ties at the maximum
+            a, b = int(cp.seg[q]), int(cp.seg[q + 1])
+            if b - a >= 2:
+                lp[a:b] -= 1.0
+                lp[a] = lp[b - 1] = -0.25
+        a, b = int(cp.seg[1]), int(cp.seg[2])
+        lp[a:b] = -9.0                               # every option below the likelihood threshold
+    elif cp.seg is None:
+        lp[0], lp[1] = math.log(0.5), math.log(0.5) + 1e-4
+    dev_ans, dev_alp = interp._answers_device(cp, lp.cuda())
+    host_ans, host_alp = interp._answers(cp, lp.numpy())
+    assert dev_ans == host_ans
+    assert len(dev_alp) == len(host_alp)
+    for x, y in zip(dev_alp, host_alp):
+        assert np.allclose(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64), rtol=1e-6, atol=1e-7)
