@@ -93,6 +93,8 @@ _SIGNATURES = {
                                         c_int, P, c_int64, c_int, P, P, P, c_float, P]),
     'dfol_table_layer_bwd_mma': (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, c_int, c_int64, P, c_int64, P,
                                          c_int64, c_int, P, c_int64, c_int, P, P, P, P, P]),
+    'dfol_pair_chain_fwd': (c_int, [P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, P, P, c_int64, c_int, P, c_int64, P,
+                                    P, P, P, P, c_int64, c_int, c_int, P]),
     'dfol_split3_bf16': (c_int, [P, c_int64, c_int64, c_int, P, c_int64, c_int, c_int, c_int, P]),
     'dfol_gemm_bf16_tc_exact': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, P, c_int, c_int, c_int, c_int, c_int, P,
                                         P, P, P, P, c_float, P]),

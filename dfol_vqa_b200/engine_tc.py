@@ -260,7 +260,15 @@ class TensorCorePath(object):
             self._tc(obj16, ops.wuv, uv, 2 * H, p['Op'], None, K.ACT_NONE, st)
             geo = torch.empty(layout.P, 4, device=dev, dtype=torch.float32) if training else None
             import os
-            if 2 * layout.max_n + 5 <= 256 and H <= 256 and os.environ.get('DFOL_PAIR_HIDDEN_MMA', '0') == '1':
+            # one kernel for the hidden layer AND layer 2 (pair_chain_fwd.cu): the hidden layer is produced straight into
+            # the shared-memory A operand of the layer-2 GEMM and never read back from HBM (bit-identical results)
+            chain = (cp is not None and cp.img_slot is not None and H == 256 and p['Hp'] == 256 and 192 < p['Ep'] <= 384
+                     and os.environ.get('DFOL_PAIR_CHAIN', '0') == '1'
+                     and os.environ.get('DFOL_FUSED_INFERENCE', '0') != '1')
+            if chain:
+                if not training:
+                    h1r = None
+            elif 2 * layout.max_n + 5 <= 256 and H <= 256 and os.environ.get('DFOL_PAIR_HIDDEN_MMA', '0') == '1':
                 # one-hot grouped GEMM on the tensor cores (pair_hidden_mma.cu).  Opt-in: correct, but its first version
                 # (one tile per CTA, row-per-lane 32-byte stores) measures 0.181 ms against 0.163 ms for the SIMT kernel at
                 # c1 and 1.13 against 0.63 ms at c3 (192 KB of shared memory: one CTA per SM, no overlap of its phases)
@@ -280,6 +288,7 @@ class TensorCorePath(object):
                      ptr(geo), ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_np), layout.B, layout.max_n,
                      st)
         else:
+            chain = False
             # an independent mask per pair element breaks the U[s] + V[o] factorisation: the first layer runs as one
             # tcgen05 GEMM over the materialised, masked pair matrix (the reference's formulation,
             # batch_gqa_boxfeatures_pipeline.py:260-281)
@@ -315,12 +324,23 @@ class TensorCorePath(object):
             if not fused:
                 # the backward pass needs the layer-2 activation (or the image uses many relations): GEMM with bf16
                 # store, then the demand-driven relation columns from the stored activation
-                if capi.trace is not None:
-                    capi.next_meta = {'tag': 'pair_layer_fwd_cluster[Px%dx%d]' % (E, p['Hp']),
-                                      'flops': 2.0 * layout.P * E * p['Hp'],
-                                      'bytes': 2.0 * layout.P * (p['Hp'] + p['Ep'])}
-                call('dfol_pair_layer_fwd_cluster', ptr(h1r), p['Hp'], ptr(ops.wr2), p['Hp'], ptr(h2r), p['Ep'],
-                     p['Ep'], ptr(w.rel[1].bias), layout.P, E, p['Hp'], K.ACT_SIGMOID, st)
+                if chain:
+                    if capi.trace is not None:
+                        capi.next_meta = {'tag': 'pair_chain_fwd[Px%dx%d]' % (E, p['Hp']),
+                                          'flops': 2.0 * layout.P * E * p['Hp'] + 10.0 * layout.P * H,
+                                          'bytes': 2.0 * layout.P * ((p['Hp'] if training else 0) + p['Ep'])}
+                    call('dfol_pair_chain_fwd', ptr(uv), uv.stride(0), ptr(obj[:, F:]), ldo,
+                         ptr(first.weight[:, 2 * ldo:]), first.weight.stride(0), ptr(first.bias), ptr(ops.wr2), p['Hp'],
+                         ptr(w.rel[1].bias), ptr(h2r), p['Ep'], p['Ep'], ptr(h1r), p['Hp'], ptr(geo),
+                         ptr(layout.pair_img), ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_n), layout.P, E,
+                         H, st)
+                else:
+                    if capi.trace is not None:
+                        capi.next_meta = {'tag': 'pair_layer_fwd_cluster[Px%dx%d]' % (E, p['Hp']),
+                                          'flops': 2.0 * layout.P * E * p['Hp'],
+                                          'bytes': 2.0 * layout.P * (p['Hp'] + p['Ep'])}
+                    call('dfol_pair_layer_fwd_cluster', ptr(h1r), p['Hp'], ptr(ops.wr2), p['Hp'], ptr(h2r), p['Ep'],
+                         p['Ep'], ptr(w.rel[1].bias), layout.P, E, p['Hp'], K.ACT_SIGMOID, st)
                 drop(h2r, E, DROP_EMB_REL)
                 if capi.trace is not None:
                     capi.next_meta = {'tag': 'rel_slots_fwd', 'bytes': 2.0 * layout.P * p['Ep'] * max(

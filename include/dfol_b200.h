@@ -409,6 +409,19 @@ int dfol_table_layer_bwd_mma(const float* g, const int32_t* slice_goff, const in
                              int64_t lddz, int cols, float* dW, float* db, float* dbelow, void* wb_workspace,
                              void* stream);
 
+/* Pair-level forward chain in one kernel (csrc/pair_chain_fwd.cu; tensor-core mode, hidden width 256, no dropout):
+ *   H1[(s,o), :] = elu(U[s] + V[o] + Wg . geo(s,o) + b1)   produced straight into the shared-memory A operand of
+ *   H2 = sigmoid(H1 . W2^T + b2)                           the layer-2 tcgen05 GEMM (cluster of two CTAs, W2 resident)
+ * (batch_gqa_boxfeatures_pipeline.py:257-279 + classifier_oracle.py:154).  uv = [U | V] fp32 (T, 2H), obj_pos = normalised
+ * boxes, wg = geometry columns of the first Linear (ldw = its row stride), W2 bf16 [N, H]; pair_img[row] = image of a pair
+ * row.  h1_out / geo_out (training: saved for the backward pass) may be NULL -- the forward pass itself never reads H1
+ * from memory.  Results are bit-identical to dfol_pair_hidden_fwd_tc followed by dfol_pair_layer_fwd_cluster. */
+int dfol_pair_chain_fwd(const float* uv, int64_t lduv, const float* obj_pos, int64_t ldpos, const float* wg, int64_t ldw,
+                        const float* bias1, const void* W2, int64_t ldw2, const float* bias2, void* H2, int64_t ldh2,
+                        int store_cols, void* h1_out, int64_t ldh1, void* geo_out, const int32_t* pair_img,
+                        const int32_t* pair_row, const int32_t* obj_row, const int32_t* img_n, int64_t M, int N, int H,
+                        void* stream);
+
 /* Demand-driven relation table (tensor-core mode; replaces computing all nR columns of
  * ClassifierOracle.compute_all_log_likelihood_2, classifier_oracle.py:154, when the batch's programs are known):
  * image b owns slots [img_slot[b], img_slot[b+1]); slot j evaluates row slot_wrow[j] of the embedding layer:

@@ -407,3 +407,56 @@ def test_device_answers_match_host_semantics(terminal):
     assert len(dev_alp) == len(host_alp)
     for x, y in zip(dev_alp, host_alp):
         assert np.allclose(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64), rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------ fused pair-level forward
+
+@pytest.mark.parametrize('terminal,n_max,ragged,batch', [('verify_rel', 48, False, 12), ('exist', 37, True, 20),
+                                                         ('choose_rel', 100, False, 6), ('verify_rel', 5, True, 9),
+                                                         ('exist', 48, False, 150)])
+def test_pair_chain_fwd_is_bit_identical_to_the_unfused_kernels(terminal, n_max, ragged, batch, monkeypatch):
+    """dfol_pair_chain_fwd (hidden layer produced into the shared-memory A operand of the layer-2 tcgen05 GEMM, halves
+    exchanged between the two CTAs of a cluster through DSMEM bulk copies) against dfol_pair_hidden_fwd_tc +
+    dfol_pair_layer_fwd_cluster: H1, the geometry table, H2 and the relation slot table, bit for bit -- training
+    (H1 stored) and inference (H1 never materialised)."""
+    from dfol_vqa_b200 import synth
+    from dfol_vqa_b200.engine import SceneLayout
+    from dfol_vqa_b200.ontology import synthetic_ontology
+    dims = dict(box=2048, feat=512, hidden=256, emb=300)
+    ont = synthetic_ontology(400, 60, 6, 5, seed=3, embedding_dim=300)
+    questions = synth.make_questions(ont, batch, terminal, 1, 3, seed=71, relate_prob=0.4)
+    counts = synth.object_counts(batch, n_max, ragged, seed=72)
+    feats, bidx = synth.make_object_features(counts, 2048, seed=73)
+    interp = helpers.build_interpreter(ont, dims, seed=5, gemm_mode='bf16', emb_bias=-4.0)
+    pb = helpers.to_cuda(_collate(questions, feats, bidx))[0]
+    cp = interp.compiled(pb, False)
+    layout = SceneLayout.of_compiled(cp, torch.device('cuda', 0))
+    if layout.P == 0:
+        pytest.skip('no relation in this batch')
+    out = {}
+    for training in (True, False):
+        for chain in ('1', '0'):
+            monkeypatch.setenv('DFOL_PAIR_CHAIN', chain)
+            with torch.no_grad():
+                sc = interp._engine.build_scene(pb._object_features.float(), layout, keep_for_backward=training, cp=cp)
+            torch.cuda.synchronize()
+            out[(training, chain)] = (None if sc.rel_h[0] is None else sc.rel_h[0].clone(), sc.rel_h[1].clone(),
+                                      None if sc.geo is None else sc.geo.clone(), sc.rel_ll.clone())
+    # valid table entries: n_b^2 per slot (slices are padded to a multiple of 4 floats; the padding is never written)
+    valid = torch.zeros(out[(True, '1')][3].numel(), dtype=torch.bool)
+    for b, n in enumerate(counts):
+        for j in range(int(cp.img_slot[b + 1] - cp.img_slot[b])):
+            off = int(cp.slot_blk[b]) + j * int(layout.rel_stride[b])
+            valid[off:off + n * n] = True
+    valid = valid.cuda()
+    for training in (True, False):
+        h1a, h2a, ga, lla = out[(training, '1')]
+        h1b, h2b, gb, llb = out[(training, '0')]
+        assert bool(torch.isfinite(h2a.float()).all())
+        assert torch.equal(h2a, h2b)
+        assert torch.equal(lla[valid], llb[valid])
+        if training:
+            assert torch.equal(h1a, h1b)
+            assert torch.equal(ga, gb)
+        else:
+            assert h1a is None
