@@ -12,10 +12,12 @@ A *step* is one pass of the hot path over one batch of B questions per GPU:
 N > 1 is launched by torchrun (one rank per GPU, NCCL); questions are sharded by rank (independent scene graphs, no
 data-path collective), weak scaling: every rank runs the same per-GPU workload.
 
-Default workloads (BASELINE.json configs): N = 1 -> the headline line is c3 (the largest single-GPU configuration) and
-carries the complete results of c1, c2 and c4 (one GPU's share) under ``configs``; N > 1 -> c4, the data-parallel
-full-curriculum mixture (512 questions per GPU: global batch 4096 at 8 GPUs, one terminal type per batch as the
-reference sampler draws them, data_pipeline.py:808-820).  ``--workload X --only`` times one workload alone.
+Default workload (BASELINE.json configs): c4 at every N -- the data-parallel full-curriculum mixture the metric is quoted
+on "at 1/2/4/8 B200" (512 questions per GPU: global batch 4096 at 8 GPUs, all 13 terminal types, one type per batch as
+the reference sampler draws them, data_pipeline.py:808-820), so that the per-N lines are the same workload.  At N = 1
+the line also carries the complete results (value, e2e, roofline, logic_roofline, kernel table) of the single-GPU
+configurations c1, c2 and c3 (the largest: N = 100, nine relate hops) under ``configs``.  ``--workload X --only`` times
+one workload alone.
 
 Prints ONE JSON line (rank 0):
   value        questions/s with the inputs resident in HBM (CUDA events around exactly K steps, max over ranks)
@@ -236,9 +238,11 @@ def cpu_baseline(args, workload, seconds=12.0):
 
 
 def default_workload(args):
-    if args.workload:
-        return args.workload
-    return 'c3' if args.gpus <= 1 else 'c4'
+    """c4 at every N: BASELINE.json quotes its metric 'at 1/2/4/8 B200' on configs[4] (the data-parallel full-curriculum
+    mixture, 512 questions per GPU = 4096 global at 8), and the driver computes the scaling efficiency from the per-N
+    values of THIS line -- they have to be the same workload.  The single-GPU configurations c1, c2 and c3 (the largest)
+    ride along in full under ``configs`` at N = 1."""
+    return args.workload or 'c4'
 
 
 def run_reference(args):
@@ -539,8 +543,11 @@ class Bench(object):
             d = per[key]
             t_ach = d['flops'] / (d['ms'] * 1e-3) / 1e12
             h_ach = d['bytes'] / (d['ms'] * 1e-3) / 1e9
-            # the oracle's contractions are tensor-bound, everything else on the path is HBM-bound
-            tensor = d['flops'] > 0
+            # the oracle's GEMMs (featurizer, attribute chain, pair-level layers and their dgrad / wgrad)
+            # are reported against the tensor roofline; everything else on the path -- the logic ops, the pair hidden
+            # layer, the table-layer backward (a K = 16..32 contraction: 24-40 FLOP/B, far below the ~210 FLOP/B ridge,
+            # whichever unit evaluates it) -- against the HBM roofline.  Both fractions are always printed.
+            tensor = d['flops'] > 0 and key.startswith(('gemm_', 'pair_layer_', 'pair_chain'))
             roof = {'kernel': key, 'entry_point': d['entry'], 'bound': 'tensor' if tensor else 'hbm',
                     'achieved': t_ach if tensor else h_ach, 'peak': t_peak if tensor else h_peak,
                     'unit': 'TFLOP/s' if tensor else 'GB/s', 'frac': (t_ach / t_peak) if tensor else (h_ach / h_peak),
@@ -690,7 +697,7 @@ def main():
     bench = Bench(args)
     headline = default_workload(args)
     nested = [] if (args.only or args.workload or bench.world > 1 or args.calibrate or args.train_dropout > 0
-                    or args.gemm != 'bf16') else ['c1', 'c2', 'c4']
+                    or args.gemm != 'bf16') else ['c1', 'c2', 'c3']
     res = bench.run_workload(headline, args.steps, args.warmup, headline=True)
     configs = {}
     for w in nested:

@@ -153,12 +153,30 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_h)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
-      // (L2 bulk prefetches of the tiles ahead were measured here: -3 % time, but ncu showed the DRAM reads DOUBLE --
-      // 3.33 GB against 1.64 GB of tile data at c3, the prefetched lines are not the ones the later loads hit -- removed)
+      // The two shared stages hold one tile in flight while one is being worked on: not enough bytes in flight to cover
+      // the HBM latency.  The NEXT tile is therefore pulled into L2 by a bulk prefetch (no shared memory needed) while
+      // this one is loaded, so that its own load is an L2 hit.  Distance ONE tile: at three tiles ahead the prefetched
+      // lines were evicted by the kernel's own store stream before use (ncu: 3.33 GB of DRAM reads against 1.64 GB of
+      // tile data at c3 -- the L2 turns over in ~20 us at 6 TB/s).
+      TmTile u = t;
+      auto prefetch_next = [&]() {
+        while (u.valid()) {
+          u.load(p, SP);
+          const bool active = u.Sb > 0;
+          if (active) {
+            const int row = p.row0[u.b] + u.c;
+            for (int k = 0; k < NB; ++k) tm_prefetch_l2(&tmap_h, 64 * k, row);
+          }
+          u.next(p);
+          if (active) return;
+        }
+      };
+      prefetch_next();   // (tile 0: about to be loaded anyway; moves the cursor to tile 1)
       int i = 0;
       for (; t.valid(); t.next(p)) {
         t.load(p, SP);
         if (t.Sb <= 0) continue;
+        prefetch_next();
         const int buf = i & 1;
         const uint32_t n = (uint32_t)(i >> 1);
         mbar_wait(&buf_free[buf], (n & 1) ^ 1);
@@ -201,10 +219,27 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
         const uint32_t n = (uint32_t)(i >> 1);
         mbar_wait(&h_full[buf], n & 1);
         mbar_wait(&dz_full[buf], n & 1);
-        mbar_wait(&acc_empty, (uint32_t)(i & 1) ^ 1u);   // the epilogue of tile i-1 has drained the accumulators
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t hs = smem_u32(h_tile(buf)), ws = smem_u32(w_tile(buf));
         const uint32_t ds = smem_u32(dz_tiles + (size_t)buf * 2 * WBOX);
+        const bool fresh = (t.b != prev_b);
+        // MMA-B: dWt[block m] += H2^T . DZ   (A: H2 boxes MN-major, M = column, K = row; B: DZ K-major, N = slice).  Within
+        // an image it only ADDS to its own accumulators, so it is issued BEFORE waiting for the epilogue of the previous
+        // tile (off the epilogue -> MMA-A -> epilogue path); the first tile of an image overwrites them and has to wait
+        // until the previous image's rows have been flushed (the flush precedes the acc_empty arrival).
+        auto issue_dw = [&]() {
+          for (int k = 0; k < ((p.debug & 4) ? 1 : TM_BM / 16); ++k) {
+            const uint64_t db = make_smem_desc(ds + (uint32_t)(k >> 2) * WBOX + 32u * (k & 3));
+            for (int m = 0; m < mblocks; ++m) {
+              const int mb = min(2 * m, NB - 2);
+              umma_bf16(tmem_base + TM_DW_COL + (uint32_t)(m * SP), tm_desc_mn(hs + (uint32_t)mb * TM_BOX + 2048u * k, TM_BOX),
+                        db, idB, (fresh && k == 0) ? 0u : 1u);
+            }
+          }
+        };
+        if (!fresh) issue_dw();
+        mbar_wait(&acc_empty, (uint32_t)(i & 1) ^ 1u);   // the epilogue of tile i-1 has drained the accumulators
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // MMA-A: acc = DZ . Wslots   (A: DZ MN-major, M = row, K = slice; B: Wslots MN-major, K = slice, N = column)
 #pragma unroll
         for (int k = 0; k < SP / 16; ++k) {
@@ -214,16 +249,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
             umma_bf16(tmem_base + TM_ACC_COL + (uint32_t)n_lo, da, tm_desc_mn(ws + 3 * WBOX + 2048u * k, WBOX), idA_hi,
                       k > 0 ? 1u : 0u);
         }
-        // MMA-B: dWt[block m] += H2^T . DZ   (A: H2 boxes MN-major, M = column, K = row; B: DZ K-major, N = slice)
-        const bool fresh = (t.b != prev_b);
-        for (int k = 0; k < ((p.debug & 4) ? 1 : TM_BM / 16); ++k) {
-          const uint64_t db = make_smem_desc(ds + (uint32_t)(k >> 2) * WBOX + 32u * (k & 3));
-          for (int m = 0; m < mblocks; ++m) {
-            const int mb = min(2 * m, NB - 2);
-            umma_bf16(tmem_base + TM_DW_COL + (uint32_t)(m * SP), tm_desc_mn(hs + (uint32_t)mb * TM_BOX + 2048u * k, TM_BOX),
-                      db, idB, (fresh && k == 0) ? 0u : 1u);
-          }
-        }
+        if (fresh) issue_dw();
         umma_commit(&mma_done);
         umma_commit(&dz_free[buf]);
         prev_b = t.b;
