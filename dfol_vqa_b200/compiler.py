@@ -379,8 +379,13 @@ class ProgramCompiler(object):
                              ga1=attr_slice(q, ncol) if ncol >= 0 else -1, grr=rel_slice(q, col),
                              mod=at(base_rel, q), mod2=at(base_sel, q))
                         names[q] = nms[q] if name_valid[q] else 'entity'
-                    elif mask[q] > 0 and modulated and (has_sel or has_rel):
-                        raise NotImplementedError('blank relation of a participating question with attention transfer')
+                    elif mask[q] > 0:
+                        # The reference would turn the attention into select(name) here (RelateBatch passes both roles
+                        # through and GQARelateBatch returns the freshly selected one, batch_gqa_ops.py:364-371,
+                        # batch_base_ops.py:568-569).  No GQA program has a relate without a relation
+                        # (gqa_preprocess.py:292-361): refused loudly rather than evaluated differently.
+                        raise NotImplementedError('relate / verify_rel of a participating question without a relation '
+                                                  '(blank predicate) is outside the hot path')
                 if name == 'verify_rel':
                     assert all(m > 0 for m in mask), 'one terminal operator per program batch'
                     for q in range(B):
@@ -495,10 +500,12 @@ class ProgramCompiler(object):
                 break
 
         if result['kind'] is None:
-            # last slot is not terminal: implicit 'end' (batch_gqa_interpreter.py:75-76)
+            # last slot is not terminal: implicit 'end' (batch_gqa_interpreter.py:75-76).  The reference calls
+            # self._ops['end'](op_id, world, x, not is_training, pqm) WITHOUT forwarding hard_mode (GQAEndBatch.forward
+            # defaults it to False, batch_gqa_ops.py:768-773): the implicit end is always the soft quantifier
             close_slot()
             for q in range(B):
-                emit(q, K.OP_EXIST, out=q)
+                emit(q, K.OP_EXIST, out=q, soft=True)
             lp_num = B
             result.update(kind=STATEMENT, terminal='end', lp_owner=list(range(B)))
 

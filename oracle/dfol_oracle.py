@@ -345,7 +345,8 @@ class OracleInterpreter(object):
             trace.append(x)
         if result is None:  # implicit 'end' (batch_gqa_interpreter.py:75-76, GQAEndBatch :768-780)
             atts, names = trace[-1]
-            lp = torch.stack([self._agg(a, give_answer) for a in atts])
+            # (the reference does not forward hard_mode to the implicit end: always the soft quantifier)
+            lp = torch.stack([exists(a) for a in atts])
             result = {'log_probability': lp, 'type': STATEMENT, 'options': [],
                       'answer': [[n] for n in names] if give_answer else []}
         result['trace'] = trace
