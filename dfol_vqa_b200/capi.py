@@ -18,7 +18,7 @@ _lib = None
 
 class K(object):
     """Constants of include/dfol_b200.h."""
-    ABI_VERSION = 4
+    ABI_VERSION = 5
     ACT_NONE, ACT_ELU, ACT_SIGMOID, ACT_LOGSIGMOID = 0, 1, 2, 3
     MUL_NONE, MUL_SIGMOID_GRAD, MUL_ELU_GRAD = 0, 1, 2
     INSTR_WORDS = 12
@@ -51,8 +51,8 @@ _SIGNATURES = {
     'dfol_act_grad_mul': (c_int, [P, c_int64, P, c_int64, c_int64, c_int, c_int, P]),
     'dfol_program_fwd': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, c_int, P]),
     'dfol_program_bwd': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, c_int, P, P, P, P]),
-    'dfol_program_fwd_fast': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, c_int, P]),
-    'dfol_program_bwd_fast': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, c_int, P, P, P, P]),
+    'dfol_program_fwd_fast': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int, P]),
+    'dfol_program_bwd_fast': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int, P, P, P, P]),
     'dfol_loss_fwd_bwd': (c_int, [P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
     'dfol_table_layer_bwd': (c_int, [P, P, P, P, P, c_int, P, P, P, P, P, P, c_int64, P, c_int64, c_int, P,
                                      c_int64, P, P, P]),
@@ -61,7 +61,7 @@ _SIGNATURES = {
     'dfol_gemm_bf16_tc_dgrad': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, c_int64,
                                         c_int, c_float, P]),
     'dfol_rel_slots_fwd': (c_int, [P, c_int64, c_int, P, c_int64, P, P, P, c_int, P, P, P, P, P, c_int, c_int,
-                                   c_float, P, P]),
+                                   c_float, P, P, P]),
     'dfol_pair_layer_fwd_tc': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, P, c_int, c_int, c_int, c_int, P,
                                        c_int64, P, P, P, c_int, P, P, P, P, P, c_float, P, P]),
     'dfol_pair_layer_dgrad_tc': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, c_int64,
@@ -74,7 +74,7 @@ _SIGNATURES = {
     'dfol_pair_hidden_fwd_mma': (c_int, [P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int, P, P, P, P, c_int,
                                          c_int, P, P]),
     'dfol_rel_slots_fwd_tc': (c_int, [P, c_int64, c_int64, c_int, c_int, P, c_int64, P, P, P, c_int, P, P, P, P, P, c_int,
-                                      c_int, c_float, P, P, P]),
+                                      c_int, c_float, P, P, P, P]),
     'dfol_lstm_cell_fwd': (c_int, [P, c_int64, P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int, P]),
     'dfol_lstm_cell_bwd': (c_int, [P, P, P, c_int, P, P, P, P, c_int64, P, P, P, P, P, P, c_int, P]),
     'dfol_mod_out_fwd': (c_int, [P, P, P, P, P, c_int, c_int, P, P, c_int, P]),

@@ -26,18 +26,15 @@ struct BwdShared {
 
 __device__ __forceinline__ void bwd_option_denominators(const Image& im, const int32_t* opts, int count, float* den,
                                                         BlockScratch& sc) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float acc[NCHUNK];
 #pragma unroll
   for (int j = 0; j < NCHUNK; ++j) acc[j] = 0.f;
-  for (int k = w; k < count; k += PROG_WARPS) {
-    const int col = opts[k] & ~DFOL_OPT_NEG;
+  const int lane = threadIdx.x & 31;
+  for_options<8>(im, opts, count, [&](int, int, const auto& raw) {
 #pragma unroll
-    for (int j = 0; j < NCHUNK; ++j) {
-      const int t = lane + 32 * j;
-      if (t < im.n) acc[j] += DFOL_EXPF(attr_raw(im, col, t));
-    }
-  }
+    for (int j = 0; j < DFOL_NC_OF(raw); ++j)
+      if (lane + 32 * j < im.n) acc[j] += DFOL_EXPF(raw[j]);
+  });
   reduce_columns(acc, im.n, den, sc, false);
 }
 
@@ -48,23 +45,27 @@ __device__ __forceinline__ float option_nrm(const Image& im, int word, int t, bo
   return r;
 }
 
+__device__ __forceinline__ float option_nrm_of(float r, int t, bool normalise, const float* den) {
+  if (normalise) r -= slog(den[t]);
+  return r;
+}
+
 // Softmax correction of the option normalisation: d raw_j = d nrm_j - (sum_k d nrm_k) * exp(raw_j) / den.
 // g slices currently hold d nrm_k; tot[t] = sum_k d nrm_k[t].
 __device__ __forceinline__ void attr_softmax_correction(const Image& im, const int32_t* op, int count, float* gslice,
                                                         const float* den, const float* tot) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int k = w; k < count; k += PROG_WARPS) {
-    const int col = op[k] & ~DFOL_OPT_NEG;
+  const int lane = threadIdx.x & 31;
+  for_options<8>(im, op, count, [&](int k, int, const auto& raw) {
 #pragma unroll
-    for (int j = 0; j < NCHUNK; ++j) {
+    for (int j = 0; j < DFOL_NC_OF(raw); ++j) {
       const int t = lane + 32 * j;
       if (t < im.n) {
         const float d = den[t];
         const float inv = (d >= kLogEps) ? 1.0f / d : 0.0f;
-        gslice[(long long)k * im.astride + t] -= tot[t] * DFOL_EXPF(attr_raw(im, col, t)) * inv;
+        gslice[(long long)k * im.astride + t] -= tot[t] * DFOL_EXPF(raw[j]) * inv;
       }
     }
-  }
+  });
   __syncthreads();
 }
 
@@ -123,8 +124,8 @@ __device__ __forceinline__ void relate_backward(int n, const LL& L, const float*
   __syncthreads();
 }
 
-template <bool MOD>
-static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
+template <bool MOD, bool PTAB>
+static __global__ void __launch_bounds__(PROG_THREADS, MOD ? 1 : PROG_MIN_BLOCKS) program_bwd_kernel(
     const int32_t* __restrict__ instr, const int32_t* __restrict__ q_instr, const int32_t* __restrict__ opts,
     const float* __restrict__ attr_ll, const int64_t* __restrict__ attr_blk, const int32_t* __restrict__ attr_stride,
     const float* __restrict__ rel_ll, const int64_t* __restrict__ rel_blk, const int32_t* __restrict__ rel_stride,
@@ -132,7 +133,7 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
     const float* __restrict__ tape, int tape_stride, float* __restrict__ g_attr, float* __restrict__ g_rel,
     float* __restrict__ d_mods
 #ifdef DFOL_PROGRAM_FAST
-    , int ring_nbuf, int ring_tile_floats
+    , const float* __restrict__ rel_p, int ring_nbuf, int ring_tile_floats
 #endif
     ) {
   __shared__ __align__(16) BwdShared sm;
@@ -147,45 +148,88 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
   const int n = im.n;
   const int ip0 = q_instr[q], ip1 = q_instr[q + 1];
 
-  if (tid < MAXN) { sm.g[tid] = 0.f; sm.gs[tid] = 0.f; sm.saved[tid] = 0.f; sm.cur[tid] = 0.f; }
+  if (tid < MAXN) {
+    sm.g[tid] = 0.f; sm.gs[tid] = 0.f; sm.saved[tid] = 0.f; sm.cur[tid] = 0.f; sm.den[tid] = 0.f; sm.tot[tid] = 0.f;
+  }
 #ifdef DFOL_PROGRAM_FAST
-  // relate tiles of this program, streamed through the shared-memory ring in REVERSE execution order
+  // relate tiles of this program, streamed through the shared-memory ring in REVERSE execution order.  The bytecode is
+  // staged in shared memory first (one parallel read instead of a chain of dependent global loads per instruction).
   extern __shared__ __align__(128) float ring_mem[];
   __shared__ __align__(8) uint64_t ring_full[8];
   __shared__ int rel_ip[MAX_REL];
-  __shared__ int rel_count;
+  __shared__ int rel_count, rel_beyond, push_ip;
+  __shared__ int32_t code_s[MAX_CODE * DFOL_INSTR_WORDS];
   TileRing ring{ring_mem, ring_nbuf, ring_tile_floats, ring_full};
-  auto issue_tile = [&](int j) {  // elected thread: tile of the j-th relate counted from the END -> slot j % nbuf
-    const int col = instr[(long long)rel_ip[rel_count - 1 - j] * DFOL_INSTR_WORDS + DFOL_I_A0];
-    const int b = j % ring.nbuf;
-    const uint32_t bytes = (uint32_t)im.rstride * 4u;
-    mbar_expect_tx(&ring.full[b], bytes);
-    bulk_load(ring.buf + (size_t)b * ring.tile_floats, im.rel + (long long)col * im.rstride, bytes, &ring.full[b]);
-  };
+  const float* ring_src = PTAB ? rel_p + rel_blk[q] : im.rel;
+  const int code_n = min(ip1 - ip0, MAX_CODE);
+  for (int i = tid; i < code_n * DFOL_INSTR_WORDS; i += PROG_THREADS)
+    code_s[i] = instr[(long long)ip0 * DFOL_INSTR_WORDS + i];
   if (tid == 0) {
-    int c = 0;
-    for (int ip = ip0; ip < ip1 && c < MAX_REL; ++ip)
-      if (instr[(long long)ip * DFOL_INSTR_WORDS + DFOL_I_OP] == DFOL_OP_RELATE) rel_ip[c++] = ip;
-    rel_count = c;
     for (int b = 0; b < ring.nbuf; ++b) mbar_init(&ring.full[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int j = 0; j < c && j < ring.nbuf; ++j) issue_tile(j);
+    push_ip = -1;
   }
   __syncthreads();
-  // relates beyond the ring capacity (the LAST ones in execution order, met first here) use direct loads
-  int total_rel = 0;
-  for (int ip = ip0; ip < ip1; ++ip)
-    total_rel += instr[(long long)ip * DFOL_INSTR_WORDS + DFOL_I_OP] == DFOL_OP_RELATE;
+  auto issue_tile = [&](int j, int b) {  // elected thread: tile of the j-th ring-served relate counted from the END
+    const int col = code_s[(rel_ip[rel_count - 1 - j] - ip0) * DFOL_INSTR_WORDS + DFOL_I_A0];
+    const uint32_t bytes = (uint32_t)im.rstride * 4u;
+    mbar_expect_tx(&ring.full[b], bytes);
+    bulk_load(ring.buf + (size_t)b * ring.tile_floats, ring_src + (long long)col * im.rstride, bytes, &ring.full[b]);
+  };
+  if (w == 0) {  // warp 0 compacts the relate hops of the staged instructions (ballot + prefix popcount)
+    int base = 0;
+    for (int c0 = 0; c0 < code_n; c0 += 32) {
+      const int idx = c0 + lane;
+      const int op = idx < code_n ? code_s[idx * DFOL_INSTR_WORDS + DFOL_I_OP] : 0;
+      const unsigned m = __ballot_sync(0xffffffffu, op == DFOL_OP_RELATE);
+      if (op == DFOL_OP_RELATE) rel_ip[base + __popc(m & ((1u << lane) - 1u))] = ip0 + idx;
+      if (op == DFOL_OP_PUSH) push_ip = ip0 + idx;
+      base += __popc(m);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      int beyond = 0;  // programs longer than the staged window: their last relates use direct loads
+      for (int ip = ip0 + code_n; ip < ip1; ++ip) {
+        const int op = instr[(long long)ip * DFOL_INSTR_WORDS + DFOL_I_OP];
+        beyond += op == DFOL_OP_RELATE;
+        if (op == DFOL_OP_PUSH) push_ip = ip;
+      }
+      rel_count = base;
+      rel_beyond = beyond;
+      for (int j = 0; j < base && j < ring.nbuf; ++j) issue_tile(j, j);
+    }
+  }
+  __syncthreads();
   int rel_seen = 0;  // relates met so far walking backwards
-#endif
+  int ring_slot = 0;
+  uint32_t ring_phase = 0;
+  // the first branch's final attention is the tape row of the PUSH instruction
+  if (push_ip >= 0 && tid < n) sm.saved[tid] = tape[(long long)push_ip * tape_stride + tid];
+  auto fetch_instr = [&](int ip) -> Instr {
+    if (ip - ip0 < MAX_CODE) {
+      const int32_t* c = code_s + (ip - ip0) * DFOL_INSTR_WORDS;
+      Instr J;
+      J.op = c[DFOL_I_OP]; J.flags = c[DFOL_I_FLAGS]; J.a0 = c[DFOL_I_A0]; J.a1 = c[DFOL_I_A1]; J.a2 = c[DFOL_I_A2];
+      J.out = c[DFOL_I_OUT]; J.ga0 = c[DFOL_I_GA0]; J.ga1 = c[DFOL_I_GA1]; J.gr = c[DFOL_I_GR];
+      J.mod = c[DFOL_I_MOD]; J.mod2 = c[DFOL_I_MOD2];
+      return J;
+    }
+    return load_instr(instr, ip);
+  };
+#else
   // the first branch's final attention is the tape row of the PUSH instruction
   for (int ip = ip0; ip < ip1; ++ip)
     if (instr[(long long)ip * DFOL_INSTR_WORDS + DFOL_I_OP] == DFOL_OP_PUSH && tid < n)
       sm.saved[tid] = tape[(long long)ip * tape_stride + tid];
+#endif
   __syncthreads();
 
   for (int ip = ip1 - 1; ip >= ip0; --ip) {
+#ifdef DFOL_PROGRAM_FAST
+    const Instr I = fetch_instr(ip);
+#else
     const Instr I = load_instr(instr, ip);
+#endif
     const bool neg = I.flags & DFOL_F_NEG, rt = I.flags & DFOL_F_ROUNDTRIP;
     const bool normalise = I.flags & DFOL_F_NORMALISE;
     __syncthreads();
@@ -217,36 +261,47 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
       case DFOL_OP_RELATE: {
         const bool nneg = I.flags & DFOL_F_NAME_NEG, nrt = I.flags & DFOL_F_NAME_ROUNDTRIP;
         const Mod mr = DFOL_LOAD_MOD(I.mod), ms = DFOL_LOAD_MOD(I.mod2);
-        float nw0 = 0.0f;  // prior of the new object before its modulation
-        if (tid < n) {
-          nw0 = (I.a1 >= 0) ? post_ll(attr_raw(im, I.a1, tid), nneg, nrt) : 0.0f;
-          sm.nw[tid] = mod_apply(ms, nw0);
-          sm.dres[tid] = sm.g[tid];
-          sm.tmp[tid] = 0.f;
-        }
-        __syncthreads();
         const bool subj = I.flags & DFOL_F_SUBJECT;
-        const float* a_s = subj ? sm.nw : sm.cur;
-        const float* a_o = subj ? sm.cur : sm.nw;
+        float nw0 = 0.0f;  // prior of the new object before its modulation
 #ifdef DFOL_PROGRAM_FAST
-        const int j = rel_seen - (total_rel - rel_count);  // position among the ring-served relates, from the end
+        const int j = rel_seen - rel_beyond;  // position among the ring-served relates, from the end
         ++rel_seen;
         if (j >= 0) {
-          const int b = j % ring.nbuf;
-          mbar_wait(&ring.full[b], (uint32_t)(j / ring.nbuf) & 1u);
-          const float* tile = ring.buf + (size_t)b * ring.tile_floats;
-          relate_forward_tile(n, tile, neg, rt, a_s, a_o, subj, sm.res, sm.inner, sm.den, sm.sc);
-          if (mr.on) {  // gradient through the modulation of the posterior: sm.g (d out) -> sm.dres (d res)
-            float dm[4] = {0.f, 0.f, 0.f, 0.f};
-            if (tid < n) sm.dres[tid] = mod_grad(mr, sm.res[tid], sm.g[tid], dm);
-            block_write_dm(dm, d_mods, I.mod, sm.sc);
+          if (tid < n) {
+            nw0 = (I.a1 >= 0) ? post_ll(attr_raw(im, I.a1, tid), nneg, nrt) : 0.0f;
+            sm.nw[tid] = mod_apply(ms, nw0);
+            sm.dres[tid] = sm.g[tid];
+            sm.den[tid] = __expf(sm.cur[tid]);
           }
-          relate_backward_tile(n, tile, neg, rt, a_s, subj, sm.dres, sm.inner, sm.den, sm.tot, sm.tmp, g_rel + I.gr,
-                               sm.sc);
-          if (tid == 0 && j + ring.nbuf < rel_count) issue_tile(j + ring.nbuf);
+          mbar_wait(&ring.full[ring_slot], ring_phase);
+          __syncthreads();
+          float dm[4] = {0.f, 0.f, 0.f, 0.f};
+          // the thread that ends up with object x's product turns d loss / d out[x] into the common factor of x's pair
+          // gradients (through the modulation of the posterior when there is one)
+          hop_backward<PTAB>(n, ring.buf + (size_t)ring_slot * ring.tile_floats, neg, sm.den, subj, sm.tot, sm.tmp,
+                             g_rel + I.gr, sm.sc, [&](int x, float Q) -> float {
+                               float d = sm.g[x];
+                               if (mr.on) {
+                                 d = mod_grad(mr, sm.nw[x] + slog(1.0f - Q), d, dm);
+                                 sm.dres[x] = d;
+                               }
+                               return hop_cfactor(d, Q);
+                             });
+          if (tid == 0 && j + ring.nbuf < rel_count) issue_tile(j + ring.nbuf, ring_slot);
+          if (++ring_slot == ring.nbuf) { ring_slot = 0; ring_phase ^= 1u; }
+          if (mr.on) block_write_dm(dm, d_mods, I.mod, sm.sc);
         } else
 #endif
         {
+          if (tid < n) {
+            nw0 = (I.a1 >= 0) ? post_ll(attr_raw(im, I.a1, tid), nneg, nrt) : 0.0f;
+            sm.nw[tid] = mod_apply(ms, nw0);
+            sm.dres[tid] = sm.g[tid];
+            sm.tmp[tid] = 0.f;
+          }
+          __syncthreads();
+          const float* a_s = subj ? sm.nw : sm.cur;
+          const float* a_o = subj ? sm.cur : sm.nw;
           RelOption L{&im, nullptr, 1, 0, false, rt, I.a0, neg};
           relate_forward(n, L, a_s, a_o, subj, sm.res, sm.inner, sm.sc);
           if (mr.on) {
@@ -304,15 +359,14 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
 #pragma unroll
         for (int j = 0; j < NCHUNK; ++j) acc[j] = 0.f;
         const bool modulated = MOD && I.mod >= 0;
-        for (int k = w; k < I.a1; k += PROG_WARPS) {
+        for_options<4>(im, op, I.a1, [&](int k, int word, const auto& raw) {
           const Mod mk = DFOL_LOAD_MOD(modulated ? I.mod + k : -1);
 #pragma unroll
-          for (int j = 0; j < NCHUNK; ++j) {
+          for (int j = 0; j < DFOL_NC_OF(raw); ++j) {
             const int t = lane + 32 * j;
-            if (t < n)
-              acc[j] += mod_apply(mk, sm.cur[t] + post_ll(attr_raw(im, op[k] & ~DFOL_OPT_NEG, t), op[k] & DFOL_OPT_NEG, rt));
+            if (t < n) acc[j] += mod_apply(mk, sm.cur[t] + post_ll(raw[j], word & DFOL_OPT_NEG, rt));
           }
-        }
+        });
         reduce_columns(acc, n, sm.res, sm.sc, false);
         float S;
         exists_block(sm.res, n, false, sm.sc, &S);
@@ -325,21 +379,21 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < NCHUNK; ++j) acc[j] = 0.f;
-        for (int k = w; k < I.a1; k += PROG_WARPS) {
+        for_options<4>(im, op, I.a1, [&](int k, int word, const auto& raws) {
           const Mod mk = DFOL_LOAD_MOD(modulated ? I.mod + k : -1);
           float dm[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < NCHUNK; ++j) {
+          for (int j = 0; j < DFOL_NC_OF(raws); ++j) {
             const int t = lane + 32 * j;
             if (t < n) {
-              const float raw = attr_raw(im, op[k] & ~DFOL_OPT_NEG, t);
-              const float dx = mod_grad(mk, sm.cur[t] + post_ll(raw, op[k] & DFOL_OPT_NEG, rt), sm.tmp[t], dm);
+              const float raw = raws[j];
+              const float dx = mod_grad(mk, sm.cur[t] + post_ll(raw, word & DFOL_OPT_NEG, rt), sm.tmp[t], dm);
               acc[j] += dx;
-              g_attr[I.ga0 + (long long)k * im.astride + t] = dx * post_ll_grad(raw, op[k] & DFOL_OPT_NEG, rt);
+              g_attr[I.ga0 + (long long)k * im.astride + t] = dx * post_ll_grad(raw, word & DFOL_OPT_NEG, rt);
             }
           }
           if (mk.on) warp_write_dm(dm, d_mods, I.mod + k);
-        }
+        });
         if (modulated) reduce_columns(acc, n, sm.g, sm.sc, false);  // d cur = sum_k dx_k (unmodulated: a1 * datt, above)
         break;
       }
@@ -354,15 +408,15 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
         if (I.op != DFOL_OP_CHOOSE_ATTR) {
           // first pass: Q = sum_k lnot(v_k) exactly as in the forward kernel
           float part = 0.f;
-          for (int k = w; k < I.a1; k += PROG_WARPS) {
-            const bool kneg = op[k] & DFOL_OPT_NEG;
+          for_options<4>(im, op, I.a1, [&](int k, int word, const auto& raw) {
+            const bool kneg = word & DFOL_OPT_NEG;
             const Mod m1 = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1), m2 = DFOL_LOAD_MOD(I.mod2 >= 0 ? I.mod2 + k : -1);
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-            for (int j = 0; j < NCHUNK; ++j) {
+            for (int j = 0; j < DFOL_NC_OF(raw); ++j) {
               const int t = lane + 32 * j;
               if (t < n) {
-                const float l = post_ll(option_nrm(im, op[k], t, normalise, sm.den), kneg, rt);
+                const float l = post_ll(option_nrm_of(raw[j], t, normalise, sm.den), kneg, rt);
                 if (I.op == DFOL_OP_ALL_SAME) {
                   const float a = sm.cur[t];
                   s1 += roundtrip(lnot(a + lnot(mod_apply(m1, a + l))));
@@ -375,7 +429,7 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
             s1 = warp_sum(s1);
             if (I.op == DFOL_OP_ALL_SAME) part += lnot(roundtrip(s1));
             else { s2 = warp_sum(s2); part += lnot(lnot(s1) + lnot(s2)); }
-          }
+          });
           const float Q = block_sum(lane == 0 ? part : 0.f, sm.sc);
           float dlp = d_lp[I.out];
           if (I.flags & DFOL_F_NEGATE_RESULT) dlp *= lnot_grad(lnot(Q));
@@ -384,18 +438,19 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
         float acc_g[NCHUNK], acc_gs[NCHUNK], acc_tot[NCHUNK];
 #pragma unroll
         for (int j = 0; j < NCHUNK; ++j) { acc_g[j] = 0.f; acc_gs[j] = 0.f; acc_tot[j] = 0.f; }
-        for (int k = w; k < I.a1; k += PROG_WARPS) {
-          const bool kneg = op[k] & DFOL_OPT_NEG;
+        for_options<4>(im, op, I.a1, [&](int k, int word, const auto& raw) {
+          constexpr int NC = DFOL_NC_OF(raw);
+          const bool kneg = word & DFOL_OPT_NEG;
           const Mod m1 = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1), m2 = DFOL_LOAD_MOD(I.mod2 >= 0 ? I.mod2 + k : -1);
           float dm1[4] = {0.f, 0.f, 0.f, 0.f}, dm2[4] = {0.f, 0.f, 0.f, 0.f};
-          float nrm[NCHUNK], l[NCHUNK], xm1[NCHUNK], xm2[NCHUNK];  // xm: modulated filter outputs
+          float nrm[NC], l[NC], xm1[NC], xm2[NC];  // xm: modulated filter outputs
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-          for (int j = 0; j < NCHUNK; ++j) {
+          for (int j = 0; j < NC; ++j) {
             const int t = lane + 32 * j;
             nrm[j] = 0.f; l[j] = 0.f; xm1[j] = 0.f; xm2[j] = 0.f;
             if (t < n) {
-              nrm[j] = option_nrm(im, op[k], t, normalise, sm.den);
+              nrm[j] = option_nrm_of(raw[j], t, normalise, sm.den);
               l[j] = post_ll(nrm[j], kneg, rt);
               if (I.op == DFOL_OP_CHOOSE_ATTR) { xm1[j] = mod_apply(m1, sm.cur[t] + l[j]); s1 += lnot(xm1[j]); }
               else if (I.op == DFOL_OP_ALL_SAME) {
@@ -421,7 +476,7 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
             d2 = dv * lnot_grad(s2);
           }
 #pragma unroll
-          for (int j = 0; j < NCHUNK; ++j) {
+          for (int j = 0; j < NC; ++j) {
             const int t = lane + 32 * j;
             if (t < n) {
               float dl;
@@ -451,7 +506,7 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
           }
           if (m1.on) warp_write_dm(dm1, d_mods, I.mod + k);
           if (m2.on) warp_write_dm(dm2, d_mods, I.mod2 + k);
-        }
+        });
         reduce_columns(acc_g, n, sm.g, sm.sc, false);
         if (I.op == DFOL_OP_TWO_SAME) reduce_columns(acc_gs, n, sm.gs, sm.sc, false);
         if (normalise) {
@@ -571,37 +626,45 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_bwd_kernel(
 using namespace dfol;
 
 #ifdef DFOL_PROGRAM_FAST
-#define DFOL_PROGRAM_BWD_ENTRY dfol_program_bwd_fast
-#else
-#define DFOL_PROGRAM_BWD_ENTRY dfol_program_bwd
-#endif
-
-extern "C" int DFOL_PROGRAM_BWD_ENTRY(const int32_t* instr, const int32_t* q_instr, const int32_t* opts,
-                                      int question_num, const float* attr_ll, const int64_t* attr_blk,
-                                      const int32_t* attr_stride, const float* rel_ll, const int64_t* rel_blk,
-                                      const int32_t* rel_stride, const int32_t* img_n, const float* mods,
-                                      const float* d_lp, const float* tape, int tape_stride, float* g_attr,
-                                      float* g_rel, float* d_mods, void* stream) {
+extern "C" int dfol_program_bwd_fast(const int32_t* instr, const int32_t* q_instr, const int32_t* opts,
+                                     int question_num, const float* attr_ll, const int64_t* attr_blk,
+                                     const int32_t* attr_stride, const float* rel_ll, const float* rel_p,
+                                     const int64_t* rel_blk, const int32_t* rel_stride, const int32_t* img_n,
+                                     const float* mods, const float* d_lp, const float* tape, int tape_stride,
+                                     float* g_attr, float* g_rel, float* d_mods, void* stream) {
   DFOL_REQUIRE(instr && q_instr && attr_ll && attr_blk && attr_stride && rel_ll && rel_blk && rel_stride && img_n &&
                    d_lp && tape && g_attr && g_rel,
-               "dfol_program_bwd: null pointer");
-  DFOL_REQUIRE((mods == nullptr) == (d_mods == nullptr), "dfol_program_bwd: mods and d_mods go together");
+               "dfol_program_bwd_fast: null pointer");
+  DFOL_REQUIRE((mods == nullptr) == (d_mods == nullptr), "dfol_program_bwd_fast: mods and d_mods go together");
   if (question_num == 0) return 0;
-#ifdef DFOL_PROGRAM_FAST
   DFOL_REQUIRE(tape_stride >= 1 && tape_stride <= MAXN, "dfol_program_bwd_fast: tape_stride = max objects rounded to 4");
   const int tile_floats = (tape_stride * tape_stride + 31) / 32 * 32;
   int nbuf = (96 * 1024) / (tile_floats * 4);
   nbuf = nbuf < 1 ? 1 : (nbuf > 4 ? 4 : nbuf);
   const size_t smem = (size_t)nbuf * tile_floats * 4;
-  cudaFuncSetAttribute(mods ? program_bwd_kernel<true> : program_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  (mods ? program_bwd_kernel<true> : program_bwd_kernel<false>)<<<question_num, PROG_THREADS, smem, (cudaStream_t)stream>>>(
+  auto kern = mods ? (rel_p ? program_bwd_kernel<true, true> : program_bwd_kernel<true, false>)
+                   : (rel_p ? program_bwd_kernel<false, true> : program_bwd_kernel<false, false>);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<question_num, PROG_THREADS, smem, (cudaStream_t)stream>>>(
       instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, mods, d_lp, tape,
-      tape_stride, g_attr, g_rel, d_mods, nbuf, tile_floats);
+      tape_stride, g_attr, g_rel, d_mods, rel_p, nbuf, tile_floats);
   return finish_launch("dfol_program_bwd_fast");
+}
 #else
-  (mods ? program_bwd_kernel<true> : program_bwd_kernel<false>)<<<question_num, PROG_THREADS, 0, (cudaStream_t)stream>>>(
+extern "C" int dfol_program_bwd(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
+                                const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
+                                const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride,
+                                const int32_t* img_n, const float* mods, const float* d_lp, const float* tape,
+                                int tape_stride, float* g_attr, float* g_rel, float* d_mods, void* stream) {
+  DFOL_REQUIRE(instr && q_instr && attr_ll && attr_blk && attr_stride && rel_ll && rel_blk && rel_stride && img_n &&
+                   d_lp && tape && g_attr && g_rel,
+               "dfol_program_bwd: null pointer");
+  DFOL_REQUIRE((mods == nullptr) == (d_mods == nullptr), "dfol_program_bwd: mods and d_mods go together");
+  if (question_num == 0) return 0;
+  (mods ? program_bwd_kernel<true, false> : program_bwd_kernel<false, false>)<<<question_num, PROG_THREADS, 0,
+                                                                                 (cudaStream_t)stream>>>(
       instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, mods, d_lp, tape,
       tape_stride, g_attr, g_rel, d_mods);
   return finish_launch("dfol_program_bwd");
-#endif
 }
+#endif

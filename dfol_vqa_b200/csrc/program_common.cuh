@@ -7,8 +7,10 @@ namespace dfol {
 
 #ifdef DFOL_PROGRAM_FAST
 constexpr int PROG_THREADS = 512;  // 16 warps per question: twice the rows of a relation tile in flight
+constexpr int PROG_MIN_BLOCKS = 2;  // two questions per SM (64 registers per thread)
 #else
 constexpr int PROG_THREADS = 256;
+constexpr int PROG_MIN_BLOCKS = 1;
 #endif
 constexpr int PROG_WARPS = PROG_THREADS / 32;
 constexpr int MAXN = 128;  // objects per image supported by the interpreter kernels (GQA: <= 100)
@@ -160,6 +162,47 @@ __device__ __forceinline__ void reduce_columns(const float acc[NCHUNK], int n, f
   __syncthreads();
 }
 
+// Option lists (query / choose / verify / same over up to ~1400 attribute options): a warp takes U options per pass and
+// issues the U option words, then all U table rows, before it touches any of them -- U independent global loads in
+// flight per lane instead of a chain of (word -> row) round trips per option (an 1356-option query spent ~85 dependent
+// HBM latencies per warp and pass).  NC = 32-object chunks per row (2 for images of <= 64 objects).  Options are visited
+// in the same order as a plain strided loop, so per-warp accumulations round identically.
+//   body(k, word, raw): warp-uniform call for option k; raw[j] = table entry of object lane + 32 j (0 beyond n).
+template <int U, int NC, class Body>
+__device__ __forceinline__ void for_options_nc(const Image& im, const int32_t* __restrict__ op, int count, Body body) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int k0 = w; k0 < count; k0 += PROG_WARPS * U) {
+    int word[U];
+    float raw[U][NC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + u * PROG_WARPS;
+      word[u] = (k < count) ? __ldg(op + k) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + u * PROG_WARPS;
+      const float* row = im.attr + (long long)(word[u] & ~DFOL_OPT_NEG) * im.astride;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int t = lane + 32 * j;
+        raw[u][j] = (k < count && t < im.n) ? __ldg(row + t) : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + u * PROG_WARPS;
+      if (k < count) body(k, word[u], raw[u]);
+    }
+  }
+}
+template <int U, class Body>
+__device__ __forceinline__ void for_options(const Image& im, const int32_t* __restrict__ op, int count, Body body) {
+  if (im.n <= 64) for_options_nc<U, 2>(im, op, count, body);
+  else for_options_nc<U, NCHUNK>(im, op, count, body);
+}
+#define DFOL_NC_OF(raw) ((int)(sizeof(raw) / sizeof(float)))
+
 // log P(exists) over att[0..n): lnot(sum_t lnot(att_t))  (BatchVariableSet.log_probability,
 // batch_base_types.py:113-123); hard mode: lnot(min_t lnot(att_t)) (:104-112).  Also returns S.
 __device__ __forceinline__ float exists_block(const float* att, int n, bool hard, BlockScratch& sc, float* s_out) {
@@ -235,13 +278,15 @@ __device__ __forceinline__ void relate_forward(int n, const LL& L, const float* 
 #ifdef DFOL_PROGRAM_FAST
 // ---------------------------------------------------------------------------------------------------------
 // Tensor-core-mode interpreter: the N x N relation tile of every relate hop is streamed into shared memory by a
-// bulk-async copy (one elected thread, mbarrier completion) through a ring of tile buffers, so the tile of hop h+1 ..
-// h+nbuf-1 is in flight while hop h computes: the table loads never sit on the dependent chain of the attention
-// vector.  The hop itself is evaluated in probability space,
-//   res[s] = a[s] + slog(1 - prod_{o != s} max(1 - e^{ll[s,o]} e^{a'[o]}, eps))
-// (one MUFU.EX2 per pair instead of an exp and a log; identical to sum_o slog(1 - e^{ll+a'}) up to fp32 rounding).
+// bulk-async copy (one elected thread, mbarrier completion) through a ring of tile buffers, so the tiles of hops
+// h+1 .. h+nbuf-1 are in flight while hop h computes: the table loads never sit on the dependent chain of the
+// attention vector.  The hop itself is evaluated in probability space,
+//   res[x] = prior[x] + slog(1 - prod_{y != x} (1 - p[x,y] e^{a[y]}))
+// (identical to sum_y slog(1 - e^{ll + a}) up to fp32 rounding).  When the scene supplies the PROBABILITY table
+// (PTAB: p = e^{ll} written next to ll by the slot kernels, 0 on self pairs) a pair costs one FFMA and one FMUL and no
+// MUFU; with the log table alone it costs one MUFU.EX2 more.
 constexpr int MAX_CODE = 48;  // instructions per program staged in shared memory
-constexpr int MAX_REL = 64;  // relate hops per program served by the ring (longer programs fall back to direct loads)
+constexpr int MAX_REL = 64;   // relate hops per program served by the ring (longer programs fall back to direct loads)
 
 struct TileRing {
   float* buf;
@@ -249,372 +294,330 @@ struct TileRing {
   uint64_t* full;
 };
 
-// post-processed likelihood of a raw tile entry and its derivative w.r.t. the raw entry
-__device__ __forceinline__ float tile_post(float raw, bool neg, bool rt) {
-  const float c = fminf(raw, 0.0f);
-  return neg ? lnot(c) : (rt ? roundtrip(c) : c);
-}
-
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-
-// t = max(1 - e^{post(raw)} * e_other, eps) for the four pairs of one float4 of a tile row
-__device__ __forceinline__ float4 tile_terms(float4 r, float4 eo, bool neg, bool rt) {
-  float4 t;
-  t.x = fmaxf(1.0f - __expf(tile_post(r.x, neg, rt)) * eo.x, kLogEps);
-  t.y = fmaxf(1.0f - __expf(tile_post(r.y, neg, rt)) * eo.y, kLogEps);
-  t.z = fmaxf(1.0f - __expf(tile_post(r.z, neg, rt)) * eo.z, kLogEps);
-  t.w = fmaxf(1.0f - __expf(tile_post(r.w, neg, rt)) * eo.w, kLogEps);
-  return t;
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-// Lean forward hop: the products Q_x = prod_{y != x} max(1 - e^{post(ll)} e^{a_other[y]}, eps) of the kept role, left
-// in inner[] (subject role) or as per-warp partial products in sc.colacc (object role: relate_kept_q multiplies
-// them).  ea[] = e^{a_other} must be visible to the block; ONE barrier, at the end.
-__device__ __forceinline__ void relate_tile_products(int n, const float* __restrict__ tile, bool neg, bool rt,
-                                                     const float* ea, bool subject_role, float* inner,
-                                                     BlockScratch& sc) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if ((n & 3) == 0 && !neg && !rt) {
-    constexpr float kLog2e = 1.4426950408889634f;
-    const int o4 = 4 * lane;
-    const bool act = o4 < n;
-    const float* rowp = tile + w * n + o4;
-    const int step = PROG_WARPS * n;
-    if (subject_role) {
-      const float4 eo = act ? *reinterpret_cast<const float4*>(ea + o4) : make_float4(1.f, 1.f, 1.f, 1.f);
-      for (int s = w; s < n; s += 2 * PROG_WARPS, rowp += 2 * step) {
-        const bool two = s + PROG_WARPS < n;
-        float q0 = 1.f, q1 = 1.f;
-        if (act) {
-          const float4 r0 = *reinterpret_cast<const float4*>(rowp);
-          const float4 r1 = two ? *reinterpret_cast<const float4*>(rowp + step)
-                                : make_float4(-100.f, -100.f, -100.f, -100.f);
-          q0 = (fmaf(-ex2_approx(r0.x * kLog2e), eo.x, 1.0f) *
-                fmaf(-ex2_approx(r0.y * kLog2e), eo.y, 1.0f)) *
-               (fmaf(-ex2_approx(r0.z * kLog2e), eo.z, 1.0f) *
-                fmaf(-ex2_approx(r0.w * kLog2e), eo.w, 1.0f));
-          q1 = (fmaf(-ex2_approx(r1.x * kLog2e), eo.x, 1.0f) *
-                fmaf(-ex2_approx(r1.y * kLog2e), eo.y, 1.0f)) *
-               (fmaf(-ex2_approx(r1.z * kLog2e), eo.z, 1.0f) *
-                fmaf(-ex2_approx(r1.w * kLog2e), eo.w, 1.0f));
-        }
+// Geometry of a hop: LPR lanes share a tile row (lane l of the group owns the objects 4l .. 4l+3), a warp holds
+// RS = 32 / LPR row groups, the block NS = 16 RS of them; group g owns the rows g, g + NS, ... (at most NR).
+//   n <= 32: LPR 8, NR 1;  n <= 64: LPR 16, NR 2;  n <= 128: LPR 32, NR 8.
+// The NR per-row partial results of a lane are reduced over the LPR lanes of the group by a TRANSPOSED butterfly: each
+// of the first log2(NR) steps halves the number of values a lane carries, so 8 rows cost 9 shuffles instead of 40.
+// On return every lane holds the complete result of row index `ri` of its group.
+template <int LPR, int NR, bool PROD>
+__device__ __forceinline__ float rows_reduce(float (&v)[NR], int l, int& ri) {
+  constexpr unsigned FULL = 0xffffffffu;
+  ri = 0;
+  int cnt = NR;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          q0 *= __shfl_xor_sync(0xffffffffu, q0, o);
-          q1 *= __shfl_xor_sync(0xffffffffu, q1, o);
-        }
-        if (lane == 0) {
-          inner[s] = q0;
-          if (two) inner[s + PROG_WARPS] = q1;
+  for (int d = LPR / 2; d >= 1; d >>= 1) {
+    if (cnt > 1) {
+      const bool hi = (l & d) != 0;
+      cnt >>= 1;
+#pragma unroll
+      for (int i = 0; i < NR / 2; ++i) {
+        if (i < cnt) {
+          const float keep = hi ? v[i + cnt] : v[i];
+          const float send = hi ? v[i] : v[i + cnt];
+          const float got = __shfl_xor_sync(FULL, send, d);
+          v[i] = PROD ? keep * got : keep + got;
         }
       }
+      ri += hi ? cnt : 0;
     } else {
-      float4 acc = make_float4(1.f, 1.f, 1.f, 1.f);
-      for (int s = w; s < n; s += PROG_WARPS, rowp += step) {
-        if (act) {
-          const float4 r = *reinterpret_cast<const float4*>(rowp);
-          const float es = ea[s];
-          acc.x *= fmaf(-ex2_approx(r.x * kLog2e), es, 1.0f);
-          acc.y *= fmaf(-ex2_approx(r.y * kLog2e), es, 1.0f);
-          acc.z *= fmaf(-ex2_approx(r.z * kLog2e), es, 1.0f);
-          acc.w *= fmaf(-ex2_approx(r.w * kLog2e), es, 1.0f);
-        }
-      }
-      if (o4 < MAXN) *reinterpret_cast<float4*>(&sc.colacc[w][o4]) = acc;
+      const float got = __shfl_xor_sync(FULL, v[0], d);
+      v[0] = PROD ? v[0] * got : v[0] + got;
     }
+  }
+  return v[0];
+}
+
+// per-column accumulators of the row groups of one warp combined (lanes with the same l), then parked in colacc[w]
+template <int LPR, bool PROD>
+__device__ __forceinline__ void park_columns(float4 acc, int lane, int w, BlockScratch& sc) {
+  constexpr unsigned FULL = 0xffffffffu;
+#pragma unroll
+  for (int d = LPR; d < 32; d <<= 1) {
+    const float gx = __shfl_xor_sync(FULL, acc.x, d), gy = __shfl_xor_sync(FULL, acc.y, d);
+    const float gz = __shfl_xor_sync(FULL, acc.z, d), gw = __shfl_xor_sync(FULL, acc.w, d);
+    if (PROD) { acc.x *= gx; acc.y *= gy; acc.z *= gz; acc.w *= gw; }
+    else { acc.x += gx; acc.y += gy; acc.z += gz; acc.w += gw; }
+  }
+  if (lane < LPR) *reinterpret_cast<float4*>(&sc.colacc[w][4 * lane]) = acc;
+}
+
+// Probabilities p'[s, 4l .. 4l+3] of one tile row after the logic cell's post-processing: p (plain / round trip, which
+// differs from the identity only below 1e-20) or max(1 - p, eps) (negated relation); zero outside the image and on the
+// self pair, so that neither the products nor the gradients need a test.  `orig` receives the un-negated p (NEG only).
+template <bool PTAB, bool NEG, bool ALIGNED>
+__device__ __forceinline__ float4 hop_row(const float* __restrict__ tile, int n, int s, int l, bool row_ok,
+                                          float4* orig) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  const int o0 = 4 * l;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (orig) *orig = r;
+  if (!(row_ok && o0 < n)) return r;
+  const float* src = tile + s * n + o0;
+  bool v1 = true, v2 = true, v3 = true;
+  if (ALIGNED) {
+    r = *reinterpret_cast<const float4*>(src);
   } else {
-    float acc[NCHUNK];
-#pragma unroll
-    for (int j = 0; j < NCHUNK; ++j) acc[j] = 1.f;
-    for (int s = w; s < n; s += PROG_WARPS) {
-      const float es = ea[s];
-      const float* row = tile + s * n;
-      float rowprod = 1.f;
-#pragma unroll
-      for (int j = 0; j < NCHUNK; ++j) {
-        const int o = lane + 32 * j;
-        if (o < n && o != s) {
-          const float t = fmaxf(1.0f - __expf(tile_post(row[o], neg, rt)) * (subject_role ? ea[o] : es), kLogEps);
-          if (subject_role) rowprod *= t;
-          else acc[j] *= t;
-        }
-      }
-      if (subject_role) {
-        rowprod = warp_prod(rowprod);
-        if (lane == 0) inner[s] = rowprod;
-      }
-    }
-    if (!subject_role) {
-#pragma unroll
-      for (int j = 0; j < NCHUNK; ++j) sc.colacc[w][lane + 32 * j] = acc[j];
-    }
+    v1 = o0 + 1 < n; v2 = o0 + 2 < n; v3 = o0 + 3 < n;
+    r.x = src[0];
+    r.y = v1 ? src[1] : 0.f;
+    r.z = v2 ? src[2] : 0.f;
+    r.w = v3 ? src[3] : 0.f;
   }
-  __syncthreads();
+  if (PTAB && !NEG) return r;  // zeros outside the row and on the diagonal already
+  if (!PTAB) {
+    r.x = ex2_approx(r.x * kLog2e); r.y = ex2_approx(r.y * kLog2e);
+    r.z = ex2_approx(r.z * kLog2e); r.w = ex2_approx(r.w * kLog2e);
+  }
+  if (NEG) {
+    if (orig) *orig = r;
+    r.x = fmaxf(1.0f - r.x, kLogEps); r.y = fmaxf(1.0f - r.y, kLogEps);
+    r.z = fmaxf(1.0f - r.z, kLogEps); r.w = fmaxf(1.0f - r.w, kLogEps);
+  }
+  if (!ALIGNED) {
+    if (!v1) r.y = 0.f;
+    if (!v2) r.z = 0.f;
+    if (!v3) r.w = 0.f;
+  }
+  if ((s >> 2) == l) {  // self pair
+    const int d = s & 3;
+    if (d == 0) r.x = 0.f; else if (d == 1) r.y = 0.f; else if (d == 2) r.z = 0.f; else r.w = 0.f;
+  }
+  return r;
 }
 
-__device__ __forceinline__ float relate_kept_q(int x, bool subject_role, const float* inner, const BlockScratch& sc) {
-  if (subject_role) return inner[x];
-  float q = 1.f;
-#pragma unroll
-  for (int i = 0; i < PROG_WARPS; ++i) q *= sc.colacc[i][x];
-  return q;
+template <bool ALIGNED>
+__device__ __forceinline__ void hop_store4(float* __restrict__ dst, int n, int o0, float4 v) {
+  if (ALIGNED) {
+    *reinterpret_cast<float4*>(dst) = v;
+  } else {
+    dst[0] = v.x;
+    if (o0 + 1 < n) dst[1] = v.y;
+    if (o0 + 2 < n) dst[2] = v.z;
+    if (o0 + 3 < n) dst[3] = v.w;
+  }
 }
 
-// inner[] receives the products Q (NOT their logarithm); ea[] (n floats of scratch) the exponentials of the other
-// role's attention, both re-used by relate_backward_tile.
-// Fast path (n % 4 == 0): a warp owns a row, lane l the four objects 4l..4l+3 (one LDS.128 per row and lane); the
-// self pair needs no test unless the relation is negated: its raw entry is -30, so 1 - e^{-30} e^{a} == 1.0f.
-__device__ __forceinline__ void relate_forward_tile(int n, const float* __restrict__ tile, bool neg, bool rt,
-                                                    const float* a_subj, const float* a_obj, bool subject_role,
-                                                    float* res, float* inner, float* ea, BlockScratch& sc) {
+// Forward hop.  ea[0..MAXN) = e^{attention of the other role} (zero beyond n), prior[] = the kept role's prior.
+// finish(x, Q) is called once per object x of the kept role with Q = prod_y (1 - p'[x,y] ea[y]), by the lane that
+// ends up holding the row (subject role) or by thread x (object role); it must not read anything another thread's
+// finish writes.  Ends with a block barrier (all tile reads and all finish calls done).
+template <int LPR, int NR, bool PTAB, bool NEG, bool ALIGNED, class Finish>
+__device__ __forceinline__ void hop_forward_t(int n, const float* __restrict__ tile, const float* ea, bool subject_role,
+                                              BlockScratch& sc, Finish finish) {
+  constexpr int RS = 32 / LPR, NS = PROG_WARPS * RS;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x < n) ea[threadIdx.x] = __expf(subject_role ? a_obj[threadIdx.x] : a_subj[threadIdx.x]);
-  __syncthreads();
-  if ((n & 3) == 0) {
-    const int o4 = 4 * lane;
-    const bool act = o4 < n;
-    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
-    const float4 eo = (act && subject_role) ? *reinterpret_cast<const float4*>(ea + o4) : one;
-    float4 acc = one;
-    if (!neg && !rt) {
-      // plain relation (the common case): raw <= 0 by construction (log-sigmoid table entries, -30 on self pairs), so
-      // min(raw, 0) is the identity and t = 1 - e^raw * e_other needs no clamp in
-      // the product (a zero factor gives slog(1 - 0) = 0 exactly as the clamped one does).  Two rows per iteration
-      // for instruction-level parallelism; res[] is finished for all rows at once after the loop.
-      constexpr float kLog2e = 1.4426950408889634f;
-      const float* rowp = tile + w * n + o4;
-      const int step = PROG_WARPS * n;
-      if (subject_role) {
-        for (int s = w; s < n; s += 2 * PROG_WARPS, rowp += 2 * step) {
-          const bool two = s + PROG_WARPS < n;
-          float q0 = 1.f, q1 = 1.f;
-          if (act) {
-            const float4 r0 = *reinterpret_cast<const float4*>(rowp);
-            const float4 r1 = two ? *reinterpret_cast<const float4*>(rowp + step) : make_float4(-100.f, -100.f, -100.f, -100.f);
-            q0 = (fmaf(-ex2_approx(r0.x * kLog2e), eo.x, 1.0f) *
-                  fmaf(-ex2_approx(r0.y * kLog2e), eo.y, 1.0f)) *
-                 (fmaf(-ex2_approx(r0.z * kLog2e), eo.z, 1.0f) *
-                  fmaf(-ex2_approx(r0.w * kLog2e), eo.w, 1.0f));
-            q1 = (fmaf(-ex2_approx(r1.x * kLog2e), eo.x, 1.0f) *
-                  fmaf(-ex2_approx(r1.y * kLog2e), eo.y, 1.0f)) *
-                 (fmaf(-ex2_approx(r1.z * kLog2e), eo.z, 1.0f) *
-                  fmaf(-ex2_approx(r1.w * kLog2e), eo.w, 1.0f));
-          }
+  const int l = lane % LPR, g = w * RS + lane / LPR;
+  if (subject_role) {
+    const float4 eo = *reinterpret_cast<const float4*>(ea + 4 * l);
+    float q[NR];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            q0 *= __shfl_xor_sync(0xffffffffu, q0, o);
-            q1 *= __shfl_xor_sync(0xffffffffu, q1, o);
-          }
-          if (lane == 0) {
-            inner[s] = q0;
-            if (two) inner[s + PROG_WARPS] = q1;
-          }
-        }
-        __syncthreads();
-        if (threadIdx.x < n) res[threadIdx.x] = a_subj[threadIdx.x] + slog(1.0f - inner[threadIdx.x]);
-        __syncthreads();
-        return;
-      }
-      for (int s = w; s < n; s += PROG_WARPS, rowp += step) {
-        if (act) {
-          const float4 r = *reinterpret_cast<const float4*>(rowp);
-          const float es = ea[s];
-          acc.x *= fmaf(-ex2_approx(r.x * kLog2e), es, 1.0f);
-          acc.y *= fmaf(-ex2_approx(r.y * kLog2e), es, 1.0f);
-          acc.z *= fmaf(-ex2_approx(r.z * kLog2e), es, 1.0f);
-          acc.w *= fmaf(-ex2_approx(r.w * kLog2e), es, 1.0f);
-        }
-      }
-    } else {
-      for (int s = w; s < n; s += PROG_WARPS) {
-        float4 t = one;
-        if (act) {
-          const float4 r = *reinterpret_cast<const float4*>(tile + s * n + o4);
-          const float es = ea[s];
-          t = tile_terms(r, subject_role ? eo : make_float4(es, es, es, es), neg, rt);
-          if (neg && (s >> 2) == lane) {  // negated relation: the self pair must be skipped explicitly
-            const int d = s & 3;
-            if (d == 0) t.x = 1.f; else if (d == 1) t.y = 1.f; else if (d == 2) t.z = 1.f; else t.w = 1.f;
-          }
-        }
-        if (subject_role) {
-          const float q = warp_prod((t.x * t.y) * (t.z * t.w));
-          if (lane == 0) { inner[s] = q; res[s] = a_subj[s] + slog(1.0f - q); }
-        } else {
-          acc.x *= t.x; acc.y *= t.y; acc.z *= t.z; acc.w *= t.w;
-        }
-      }
+    for (int i = 0; i < NR; ++i) {
+      const int s = g + NS * i;
+      const float4 r = hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
+      q[i] = (fmaf(-r.x, eo.x, 1.0f) * fmaf(-r.y, eo.y, 1.0f)) * (fmaf(-r.z, eo.z, 1.0f) * fmaf(-r.w, eo.w, 1.0f));
     }
-    if (!subject_role) {
-      __syncthreads();
-      *reinterpret_cast<float4*>(&sc.colacc[w][o4]) = acc;
-      __syncthreads();
-      if (threadIdx.x < n) {
-        float q = 1.f;
+    int ri;
+    const float Q = rows_reduce<LPR, NR, true>(q, l, ri);
+    const int s = g + NS * ri;
+    if ((l & (LPR / NR - 1)) == 0 && s < n) finish(s, Q);
+  } else {
+    float4 acc = make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
-        for (int i = 0; i < PROG_WARPS; ++i) q *= sc.colacc[i][threadIdx.x];
-        inner[threadIdx.x] = q;
-        res[threadIdx.x] = a_obj[threadIdx.x] + slog(1.0f - q);
-      }
+    for (int i = 0; i < NR; ++i) {
+      const int s = g + NS * i;
+      const float4 r = hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
+      const float es = (s < n) ? ea[s] : 0.0f;
+      acc.x *= fmaf(-r.x, es, 1.0f); acc.y *= fmaf(-r.y, es, 1.0f);
+      acc.z *= fmaf(-r.z, es, 1.0f); acc.w *= fmaf(-r.w, es, 1.0f);
     }
-    __syncthreads();
-    return;
-  }
-  float acc[NCHUNK];
-#pragma unroll
-  for (int j = 0; j < NCHUNK; ++j) acc[j] = 1.f;
-  for (int s = w; s < n; s += PROG_WARPS) {
-    const float es = ea[s];
-    const float* row = tile + s * n;
-    float rowprod = 1.f;
-#pragma unroll
-    for (int j = 0; j < NCHUNK; ++j) {
-      const int o = lane + 32 * j;
-      if (o < n && o != s) {
-        const float p = __expf(tile_post(row[o], neg, rt)) * (subject_role ? ea[o] : es);
-        const float t = fmaxf(1.0f - p, kLogEps);
-        if (subject_role) rowprod *= t;
-        else acc[j] *= t;
-      }
-    }
-    if (subject_role) {
-      rowprod = warp_prod(rowprod);
-      if (lane == 0) { inner[s] = rowprod; res[s] = a_subj[s] + slog(1.0f - rowprod); }
-    }
-  }
-  if (!subject_role) {
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < NCHUNK; ++j) sc.colacc[w][lane + 32 * j] = acc[j];
+    park_columns<LPR, true>(acc, lane, w, sc);
     __syncthreads();
     if (threadIdx.x < n) {
-      float q = 1.f;
+      float Q = 1.f;
 #pragma unroll
-      for (int i = 0; i < PROG_WARPS; ++i) q *= sc.colacc[i][threadIdx.x];
-      inner[threadIdx.x] = q;
-      res[threadIdx.x] = a_obj[threadIdx.x] + slog(1.0f - q);
+      for (int i = 0; i < PROG_WARPS; ++i) Q *= sc.colacc[i][threadIdx.x];
+      finish((int)threadIdx.x, Q);
     }
   }
   __syncthreads();
 }
 
-// d slog(1 - Q) / d log Q given the product Q
-__device__ __forceinline__ float lnot_grad_q(float q) {
-  const float u = 1.0f - q;
-  return (u >= kLogEps) ? __fdividef(-q, u) : 0.0f;
+template <bool PTAB, class Finish>
+__device__ __forceinline__ void hop_forward(int n, const float* __restrict__ tile, bool neg, const float* ea,
+                                            bool subject_role, BlockScratch& sc, Finish finish) {
+#define DFOL_HOP_FWD(LPR, NR)                                                                              \
+  {                                                                                                        \
+    if ((n & 3) == 0) {                                                                                    \
+      if (!neg) hop_forward_t<LPR, NR, PTAB, false, true>(n, tile, ea, subject_role, sc, finish);         \
+      else hop_forward_t<LPR, NR, PTAB, true, true>(n, tile, ea, subject_role, sc, finish);               \
+    } else {                                                                                               \
+      if (!neg) hop_forward_t<LPR, NR, PTAB, false, false>(n, tile, ea, subject_role, sc, finish);        \
+      else hop_forward_t<LPR, NR, PTAB, true, false>(n, tile, ea, subject_role, sc, finish);              \
+    }                                                                                                      \
+  }
+  if (n <= 32) DFOL_HOP_FWD(8, 1)
+  else if (n <= 64) DFOL_HOP_FWD(16, 2)
+  else DFOL_HOP_FWD(32, 8)
+#undef DFOL_HOP_FWD
 }
 
-// du/d(l+a) factor -p/(1-p) (zero where the clamp is active) of one pair, p = e^{post(raw)} * e_other
-__device__ __forceinline__ float tile_lgrad(float raw, float eo, bool neg, bool rt) {
-  const float p = __expf(tile_post(raw, neg, rt)) * eo;
-  const float u = 1.0f - p;
-  return (u >= kLogEps) ? __fdividef(-p, u) : 0.0f;
+// c = dres * Q / (1 - Q): d loss / d(-log Q)... the common factor of the pair gradients of one kept object
+// (du[x,y] = c[x] * m / (1 - m), m = p'[x,y] ea[y]); zero where the clamp of slog(1 - Q) is active.
+__device__ __forceinline__ float hop_cfactor(float dres, float Q) {
+  const float u = 1.0f - Q;
+  return (u >= kLogEps) ? dres * __fdividef(Q, u) : 0.0f;
 }
 
-// Backward of relate_forward_tile (same contract as relate_backward); dq[] is n floats of scratch.
-__device__ __forceinline__ void relate_backward_tile(int n, const float* __restrict__ tile, bool neg, bool rt,
-                                                     const float* a_subj, bool subject_role, const float* dres,
-                                                     const float* inner, const float* ea, float* dq, float* g_other,
-                                                     float* __restrict__ gslice, BlockScratch& sc) {
+// d loss / d(l + a) of the four pairs of a lane: ce = c * ea per pair; a vanished factor (1 - m == 0) made Q and c zero,
+// so the clamped reciprocal yields 0 exactly as the reference's clamp backward does
+__device__ __forceinline__ float4 hop_du(float4 r, float4 ce, float4 e) {
+  float4 du;
+  du.x = (ce.x * r.x) * rcp_approx(fmaxf(fmaf(-r.x, e.x, 1.0f), kLogEps));
+  du.y = (ce.y * r.y) * rcp_approx(fmaxf(fmaf(-r.y, e.y, 1.0f), kLogEps));
+  du.z = (ce.z * r.z) * rcp_approx(fmaxf(fmaf(-r.z, e.z, 1.0f), kLogEps));
+  du.w = (ce.w * r.w) * rcp_approx(fmaxf(fmaf(-r.w, e.w, 1.0f), kLogEps));
+  return du;
+}
+// gradient w.r.t. the RAW table entry: identity for a plain relation, -p / (1 - p) through the negation
+template <bool NEG>
+__device__ __forceinline__ float4 hop_draw(float4 du, float4 p) {
+  if (!NEG) return du;
+  float4 dn;
+  dn.x = (1.0f - p.x >= kLogEps) ? du.x * __fdividef(-p.x, 1.0f - p.x) : 0.0f;
+  dn.y = (1.0f - p.y >= kLogEps) ? du.y * __fdividef(-p.y, 1.0f - p.y) : 0.0f;
+  dn.z = (1.0f - p.z >= kLogEps) ? du.z * __fdividef(-p.z, 1.0f - p.z) : 0.0f;
+  dn.w = (1.0f - p.w >= kLogEps) ? du.w * __fdividef(-p.w, 1.0f - p.w) : 0.0f;
+  return dn;
+}
+
+// Backward hop (re-evaluates the products).  cfac(x, Q) -> c[x] is called once per kept object (same calling convention
+// as `finish` above; it may write per-object results for the caller).  cbuf: MAXN floats of scratch; g_other[0..n)
+// receives d loss / d(attention of the other role); gslice (n x n, global) d loss / d raw table entry.
+// Ends with a block barrier.
+template <int LPR, int NR, bool PTAB, bool NEG, bool ALIGNED, class CFac>
+__device__ __forceinline__ void hop_backward_t(int n, const float* __restrict__ tile, const float* ea,
+                                               bool subject_role, float* cbuf, float* g_other,
+                                               float* __restrict__ gslice, BlockScratch& sc, CFac cfac) {
+  constexpr int RS = 32 / LPR, NS = PROG_WARPS * RS;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x < n) dq[threadIdx.x] = dres[threadIdx.x] * lnot_grad_q(inner[threadIdx.x]);
-  __syncthreads();
-  if ((n & 3) == 0) {
-    const int o4 = 4 * lane;
-    const bool act = o4 < n;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 eo = (act && subject_role) ? *reinterpret_cast<const float4*>(ea + o4) : zero;
-    const float4 dqo = (act && !subject_role) ? *reinterpret_cast<const float4*>(dq + o4) : zero;
-    float4 acc = zero;
-    for (int s = w; s < n; s += PROG_WARPS) {
-      float rowsum = 0.f;
-      if (act) {
-        const float4 r = *reinterpret_cast<const float4*>(tile + s * n + o4);
-        const float es = ea[s], dS_row = dq[s];
-        float4 du;
-        if (subject_role) {
-          du.x = dS_row * tile_lgrad(r.x, eo.x, neg, rt);
-          du.y = dS_row * tile_lgrad(r.y, eo.y, neg, rt);
-          du.z = dS_row * tile_lgrad(r.z, eo.z, neg, rt);
-          du.w = dS_row * tile_lgrad(r.w, eo.w, neg, rt);
-        } else {
-          du.x = dqo.x * tile_lgrad(r.x, es, neg, rt);
-          du.y = dqo.y * tile_lgrad(r.y, es, neg, rt);
-          du.z = dqo.z * tile_lgrad(r.z, es, neg, rt);
-          du.w = dqo.w * tile_lgrad(r.w, es, neg, rt);
-        }
-        if ((s >> 2) == lane) {  // self pair: no gradient
-          const int d = s & 3;
-          if (d == 0) du.x = 0.f; else if (d == 1) du.y = 0.f; else if (d == 2) du.z = 0.f; else du.w = 0.f;
-        }
-        if (subject_role) { acc.x += du.x; acc.y += du.y; acc.z += du.z; acc.w += du.w; }
-        else rowsum = (du.x + du.y) + (du.z + du.w);
-        float4 dn;
-        dn.x = du.x * post_ll_grad(r.x, neg, rt);
-        dn.y = du.y * post_ll_grad(r.y, neg, rt);
-        dn.z = du.z * post_ll_grad(r.z, neg, rt);
-        dn.w = du.w * post_ll_grad(r.w, neg, rt);
-        *reinterpret_cast<float4*>(gslice + s * n + o4) = dn;
+  const int l = lane % LPR, g = w * RS + lane / LPR;
+  const int o0 = 4 * l;
+  if (subject_role) {
+    const float4 eo = *reinterpret_cast<const float4*>(ea + o0);
+    {
+      float q[NR];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const int s = g + NS * i;
+        const float4 r = hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
+        q[i] = (fmaf(-r.x, eo.x, 1.0f) * fmaf(-r.y, eo.y, 1.0f)) * (fmaf(-r.z, eo.z, 1.0f) * fmaf(-r.w, eo.w, 1.0f));
       }
-      if (!subject_role) {
-        rowsum = warp_sum(rowsum);
-        if (lane == 0) g_other[s] += rowsum;
+      int ri;
+      const float Q = rows_reduce<LPR, NR, true>(q, l, ri);
+      const int s = g + NS * ri;
+      if ((l & (LPR / NR - 1)) == 0 && s < n) cbuf[s] = cfac(s, Q);
+    }
+    __syncwarp();  // the rows of a group are produced and consumed inside one warp
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int s = g + NS * i;
+      if (s < n && o0 < n) {
+        float4 p0;
+        const float4 r = hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, true, &p0);
+        const float c = cbuf[s];
+        const float4 du = hop_du(r, make_float4(c * eo.x, c * eo.y, c * eo.z, c * eo.w), eo);
+        acc.x += du.x; acc.y += du.y; acc.z += du.z; acc.w += du.w;
+        hop_store4<ALIGNED>(gslice + s * n + o0, n, o0, hop_draw<NEG>(du, p0));
       }
     }
-    if (subject_role) {
-      __syncthreads();
-      *reinterpret_cast<float4*>(&sc.colacc[w][o4]) = acc;
-      __syncthreads();
-      if (threadIdx.x < n) {
-        float t = 0.f;
+    park_columns<LPR, false>(acc, lane, w, sc);
+    __syncthreads();
+    if (threadIdx.x < n) {
+      float t = 0.f;
 #pragma unroll
-        for (int i = 0; i < PROG_WARPS; ++i) t += sc.colacc[i][threadIdx.x];
-        g_other[threadIdx.x] += t;
+      for (int i = 0; i < PROG_WARPS; ++i) t += sc.colacc[i][threadIdx.x];
+      g_other[threadIdx.x] = t;
+    }
+  } else {
+    {
+      float4 acc = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const int s = g + NS * i;
+        const float4 r = hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
+        const float es = (s < n) ? ea[s] : 0.0f;
+        acc.x *= fmaf(-r.x, es, 1.0f); acc.y *= fmaf(-r.y, es, 1.0f);
+        acc.z *= fmaf(-r.z, es, 1.0f); acc.w *= fmaf(-r.w, es, 1.0f);
       }
+      park_columns<LPR, true>(acc, lane, w, sc);
     }
     __syncthreads();
-    return;
-  }
-  float acc[NCHUNK];
+    if (threadIdx.x < MAXN) {
+      float c = 0.f;
+      if (threadIdx.x < n) {
+        float Q = 1.f;
 #pragma unroll
-  for (int j = 0; j < NCHUNK; ++j) acc[j] = 0.f;
-  for (int s = w; s < n; s += PROG_WARPS) {
-    const float es = ea[s];
-    const float dS_row = dq[s];
-    const float* row = tile + s * n;
-    float rowsum = 0.f;
+        for (int i = 0; i < PROG_WARPS; ++i) Q *= sc.colacc[i][threadIdx.x];
+        c = cfac((int)threadIdx.x, Q);
+      }
+      cbuf[threadIdx.x] = c;
+    }
+    __syncthreads();
+    const float4 c4 = *reinterpret_cast<const float4*>(cbuf + o0);
+    float rs[NR];
 #pragma unroll
-    for (int j = 0; j < NCHUNK; ++j) {
-      const int o = lane + 32 * j;
-      if (o < n) {
-        float dn = 0.0f;
-        if (o != s) {
-          const float raw = row[o];
-          const float lg = tile_lgrad(raw, subject_role ? ea[o] : es, neg, rt);
-          float du;
-          if (subject_role) {
-            du = dS_row * lg;
-            acc[j] += du;
-          } else {
-            du = dq[o] * lg;
-            rowsum += du;
-          }
-          dn = du * post_ll_grad(raw, neg, rt);
-        }
-        gslice[s * n + o] = dn;
+    for (int i = 0; i < NR; ++i) {
+      const int s = g + NS * i;
+      rs[i] = 0.f;
+      if (s < n && o0 < n) {
+        float4 p0;
+        const float4 r = hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, true, &p0);
+        const float es = ea[s];
+        const float4 du = hop_du(r, make_float4(c4.x * es, c4.y * es, c4.z * es, c4.w * es),
+                                 make_float4(es, es, es, es));
+        rs[i] = (du.x + du.y) + (du.z + du.w);
+        hop_store4<ALIGNED>(gslice + s * n + o0, n, o0, hop_draw<NEG>(du, p0));
       }
     }
-    if (!subject_role) {
-      rowsum = warp_sum(rowsum);
-      if (lane == 0) g_other[s] += rowsum;
-    }
+    int ri;
+    const float t = rows_reduce<LPR, NR, false>(rs, l, ri);
+    const int s = g + NS * ri;
+    if ((l & (LPR / NR - 1)) == 0 && s < n) g_other[s] = t;
   }
-  if (subject_role) reduce_columns(acc, n, g_other, sc, true);
   __syncthreads();
+}
+
+template <bool PTAB, class CFac>
+__device__ __forceinline__ void hop_backward(int n, const float* __restrict__ tile, bool neg, const float* ea,
+                                             bool subject_role, float* cbuf, float* g_other,
+                                             float* __restrict__ gslice, BlockScratch& sc, CFac cfac) {
+#define DFOL_HOP_BWD(LPR, NR)                                                                                        \
+  {                                                                                                                  \
+    if ((n & 3) == 0) {                                                                                              \
+      if (!neg) hop_backward_t<LPR, NR, PTAB, false, true>(n, tile, ea, subject_role, cbuf, g_other, gslice, sc, cfac); \
+      else hop_backward_t<LPR, NR, PTAB, true, true>(n, tile, ea, subject_role, cbuf, g_other, gslice, sc, cfac);    \
+    } else {                                                                                                         \
+      if (!neg) hop_backward_t<LPR, NR, PTAB, false, false>(n, tile, ea, subject_role, cbuf, g_other, gslice, sc, cfac); \
+      else hop_backward_t<LPR, NR, PTAB, true, false>(n, tile, ea, subject_role, cbuf, g_other, gslice, sc, cfac);   \
+    }                                                                                                                \
+  }
+  if (n <= 32) DFOL_HOP_BWD(8, 1)
+  else if (n <= 64) DFOL_HOP_BWD(16, 2)
+  else DFOL_HOP_BWD(32, 8)
+#undef DFOL_HOP_BWD
 }
 #endif  // DFOL_PROGRAM_FAST
 

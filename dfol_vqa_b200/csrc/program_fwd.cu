@@ -37,19 +37,22 @@ __device__ __forceinline__ void select_into(float* dst, const Image& im, int col
 // classifier_oracle.py:61-80): den[t] = sum_k exp(raw_k[t]).
 __device__ __forceinline__ void option_denominators(const Image& im, const int32_t* opts, int count, float* den,
                                                     BlockScratch& sc) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float acc[NCHUNK];
 #pragma unroll
   for (int j = 0; j < NCHUNK; ++j) acc[j] = 0.f;
-  for (int k = w; k < count; k += PROG_WARPS) {
-    const int col = opts[k] & ~DFOL_OPT_NEG;
+  const int lane = threadIdx.x & 31;
+  for_options<8>(im, opts, count, [&](int, int, const auto& raw) {
 #pragma unroll
-    for (int j = 0; j < NCHUNK; ++j) {
-      const int t = lane + 32 * j;
-      if (t < im.n) acc[j] += DFOL_EXPF(attr_raw(im, col, t));
-    }
-  }
+    for (int j = 0; j < DFOL_NC_OF(raw); ++j)
+      if (lane + 32 * j < im.n) acc[j] += DFOL_EXPF(raw[j]);
+  });
   reduce_columns(acc, im.n, den, sc, false);
+}
+
+// post-processed likelihood of option `word` at object t from its already loaded raw table entry
+__device__ __forceinline__ float option_ll_of(float r, int word, int t, bool normalise, bool rt, const float* den) {
+  if (normalise) r -= slog(den[t]);
+  return post_ll(r, (word & DFOL_OPT_NEG) != 0, rt);
 }
 
 __device__ __forceinline__ float option_ll(const Image& im, int word, int t, bool normalise, bool rt,
@@ -78,15 +81,15 @@ __device__ __forceinline__ float warp_exists(const float x[NCHUNK], int n, bool 
   return lnot(s);
 }
 
-template <bool MOD>
-static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
+template <bool MOD, bool PTAB>
+static __global__ void __launch_bounds__(PROG_THREADS, MOD ? 1 : PROG_MIN_BLOCKS) program_fwd_kernel(
     const int32_t* __restrict__ instr, const int32_t* __restrict__ q_instr, const int32_t* __restrict__ opts,
     const float* __restrict__ attr_ll, const int64_t* __restrict__ attr_blk, const int32_t* __restrict__ attr_stride,
     const float* __restrict__ rel_ll, const int64_t* __restrict__ rel_blk, const int32_t* __restrict__ rel_stride,
     const int32_t* __restrict__ img_n, const float* __restrict__ mods, float* __restrict__ lp_out,
     float* __restrict__ tape, int tape_stride
 #ifdef DFOL_PROGRAM_FAST
-    , int ring_nbuf, int ring_tile_floats
+    , const float* __restrict__ rel_p, int ring_nbuf, int ring_tile_floats
 #endif
     ) {
   __shared__ __align__(16) FwdShared sm;
@@ -103,8 +106,10 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
   im.rstride = rel_stride[q];
   const int n = im.n;
 
-  if (tid < MAXN) { sm.cur[tid] = 0.f; sm.saved[tid] = 0.f; }
+  if (tid < MAXN) { sm.cur[tid] = 0.f; sm.saved[tid] = 0.f; sm.den[tid] = 0.f; }
 #ifdef DFOL_PROGRAM_FAST
+  // the ring streams the probability tiles when the scene supplies them (same blocks and strides as the log table)
+  const float* ring_src = PTAB ? rel_p + rel_blk[q] : im.rel;
   // relate tiles of this program, in execution order, streamed through the shared-memory ring
   extern __shared__ __align__(128) float ring_mem[];
   __shared__ __align__(8) uint64_t ring_full[8];
@@ -125,12 +130,11 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto issue_tile = [&](int k) {  // elected thread: tile of the k-th relate -> ring slot k % nbuf
+  auto issue_tile = [&](int k, int b) {  // elected thread: tile of the k-th relate -> ring slot b = k % nbuf
     const int col = code_s[(rel_ip[k] - ip_first) * DFOL_INSTR_WORDS + DFOL_I_A0];
-    const int b = k % ring.nbuf;
     const uint32_t bytes = (uint32_t)im.rstride * 4u;
     mbar_expect_tx(&ring.full[b], bytes);
-    bulk_load(ring.buf + (size_t)b * ring.tile_floats, im.rel + (long long)col * im.rstride, bytes, &ring.full[b]);
+    bulk_load(ring.buf + (size_t)b * ring.tile_floats, ring_src + (long long)col * im.rstride, bytes, &ring.full[b]);
   };
   if (tid < code_n) {
     const int op = code_s[tid * DFOL_INSTR_WORDS + DFOL_I_OP];
@@ -149,10 +153,12 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
     __syncwarp();
     if (lane == 0) {
       rel_count = base;
-      for (int k = 0; k < base && k < ring.nbuf; ++k) issue_tile(k);
+      for (int k = 0; k < base && k < ring.nbuf; ++k) issue_tile(k, k);
     }
   }
   int krel = 0;
+  int ring_slot = 0;          // slot of the krel-th relate and the parity of its mbarrier phase (no division per hop)
+  uint32_t ring_phase = 0;
 #endif
   __syncthreads();
 
@@ -244,30 +250,29 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
 #ifdef DFOL_PROGRAM_FAST
         if (krel < rel_count) {
           // phase A (thread-local): prior of the new object from the prefetched name row, e^{cur} of the other role
-          float nwv = 0.0f;
           DFOL_TSTAMP(0);
           const Mod mr = DFOL_LOAD_MOD(I.mod), ms = DFOL_LOAD_MOD(I.mod2);
           if (tid < n) {
+            float nwv = 0.0f;
             if (I.a1 >= 0) nwv = post_ll(cur_raw, I.flags & DFOL_F_NAME_NEG, I.flags & DFOL_F_NAME_ROUNDTRIP);
-            nwv = mod_apply(ms, nwv);
+            sm.nw[tid] = mod_apply(ms, nwv);
             sm.den[tid] = __expf(sm.cur[tid]);
           }
-          const int b = krel % ring.nbuf;
           DFOL_TSTAMP(1);
-          mbar_wait(&ring.full[b], (uint32_t)(krel / ring.nbuf) & 1u);
+          mbar_wait(&ring.full[ring_slot], ring_phase);
           DFOL_TSTAMP(2);
           __syncthreads();
           DFOL_TSTAMP(3);
-          // phase B: products over the tile (one barrier at its end)
-          relate_tile_products(n, ring.buf + (size_t)b * ring.tile_floats, neg, rt, sm.den, subj, sm.inner, sm.sc);
+          // phase B: products over the tile; the thread that ends up holding object x's product writes its posterior,
+          // which replaces the attention (the products read e^{cur} in sm.den, never sm.cur)
+          hop_forward<PTAB>(n, ring.buf + (size_t)ring_slot * ring.tile_floats, neg, sm.den, subj, sm.sc,
+                            [&](int x, float Q) { sm.cur[x] = mod_apply(mr, sm.nw[x] + slog(1.0f - Q)); });
           DFOL_TSTAMP(4);
           // every thread is past its last read of the slot: refill it with the tile nbuf hops ahead
-          if (tid == 0 && krel + ring.nbuf < rel_count) issue_tile(krel + ring.nbuf);
-          // phase C (thread-local): posterior of the kept role replaces the attention
-          if (tid < n) sm.cur[tid] = mod_apply(mr, nwv + slog(1.0f - relate_kept_q(tid, subj, sm.inner, sm.sc)));
-          __syncthreads();
+          if (tid == 0 && krel + ring.nbuf < rel_count) issue_tile(krel + ring.nbuf, ring_slot);
           DFOL_TSTAMP(5);
           ++krel;
+          if (++ring_slot == ring.nbuf) { ring_slot = 0; ring_phase ^= 1u; }
           break;
         }
         ++krel;
@@ -315,14 +320,14 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
         float acc[NCHUNK];
 #pragma unroll
         for (int j = 0; j < NCHUNK; ++j) acc[j] = 0.f;
-        for (int k = w; k < I.a1; k += PROG_WARPS) {
+        for_options<4>(im, op, I.a1, [&](int k, int word, const auto& raw) {
           const Mod mk = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1);
 #pragma unroll
-          for (int j = 0; j < NCHUNK; ++j) {
+          for (int j = 0; j < DFOL_NC_OF(raw); ++j) {
             const int t = lane + 32 * j;
-            if (t < n) acc[j] += mod_apply(mk, sm.cur[t] + option_ll(im, op[k], t, false, rt, nullptr));
+            if (t < n) acc[j] += mod_apply(mk, sm.cur[t] + option_ll_of(raw[j], word, t, false, rt, nullptr));
           }
-        }
+        });
         reduce_columns(acc, n, sm.res, sm.sc, false);
         const float lp = exists_block(sm.res, n, hard, sm.sc, nullptr);
         if (tid == 0) lp_out[I.out] = lp;
@@ -332,17 +337,19 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
       case DFOL_OP_CHOOSE_ATTR: {
         const int32_t* op = opts + I.a0;
         if (normalise) option_denominators(im, op, I.a1, sm.den, sm.sc);
-        for (int k = w; k < I.a1; k += PROG_WARPS) {
+        for_options<8>(im, op, I.a1, [&](int k, int word, const auto& raw) {
           const Mod mk = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1);
           float x[NCHUNK];
 #pragma unroll
           for (int j = 0; j < NCHUNK; ++j) {
             const int t = lane + 32 * j;
-            x[j] = (t < n) ? mod_apply(mk, sm.cur[t] + option_ll(im, op[k], t, normalise, rt, sm.den)) : 0.f;
+            x[j] = 0.f;
+            if (j < DFOL_NC_OF(raw) && t < n)
+              x[j] = mod_apply(mk, sm.cur[t] + option_ll_of(raw[j < DFOL_NC_OF(raw) ? j : 0], word, t, normalise, rt, sm.den));
           }
           const float lp = warp_exists(x, n, hard, nullptr);
           if (lane == 0) lp_out[I.out + k] = lp;
-        }
+        });
         __syncthreads();
         break;
       }
@@ -352,16 +359,16 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
         const int32_t* op = opts + I.a0;
         if (normalise) option_denominators(im, op, I.a1, sm.den, sm.sc);
         float part = 0.f;
-        for (int k = w; k < I.a1; k += PROG_WARPS) {
+        for_options<4>(im, op, I.a1, [&](int k, int word, const auto& raw) {
           const Mod mk = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1);
           float s = 0.f;
           bool first = true;
 #pragma unroll
-          for (int j = 0; j < NCHUNK; ++j) {
+          for (int j = 0; j < DFOL_NC_OF(raw); ++j) {
             const int t = lane + 32 * j;
             if (t < n) {
               const float a = sm.cur[t];
-              const float y = lnot(a + lnot(mod_apply(mk, a + option_ll(im, op[k], t, normalise, rt, sm.den))));
+              const float y = lnot(a + lnot(mod_apply(mk, a + option_ll_of(raw[j], word, t, normalise, rt, sm.den))));
               const float r = roundtrip(y);
               if (hard) { s = first ? r : fminf(s, r); first = false; }
               else s += r;
@@ -369,7 +376,7 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
           }
           s = hard ? warp_min(s) : warp_sum(s);
           part += lnot(roundtrip(s));
-        }
+        });
         float Q = block_sum(lane == 0 ? part : 0.f, sm.sc);
         float lp = lnot(Q);
         if (I.flags & DFOL_F_NEGATE_RESULT) lp = lnot(lp);
@@ -381,20 +388,23 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
         const int32_t* op = opts + I.a0;
         if (normalise) option_denominators(im, op, I.a1, sm.den, sm.sc);
         float part = 0.f;
-        for (int k = w; k < I.a1; k += PROG_WARPS) {
+        for_options<4>(im, op, I.a1, [&](int k, int word, const auto& raw) {
           const Mod m1 = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1), m2 = DFOL_LOAD_MOD(I.mod2 >= 0 ? I.mod2 + k : -1);
           float x1[NCHUNK], x2[NCHUNK];
 #pragma unroll
           for (int j = 0; j < NCHUNK; ++j) {
             const int t = lane + 32 * j;
-            const float l = (t < n) ? option_ll(im, op[k], t, normalise, rt, sm.den) : 0.f;
-            x1[j] = (t < n) ? mod_apply(m1, sm.saved[t] + l) : 0.f;
-            x2[j] = (t < n) ? mod_apply(m2, sm.cur[t] + l) : 0.f;
+            x1[j] = x2[j] = 0.f;
+            if (j < DFOL_NC_OF(raw) && t < n) {
+              const float l = option_ll_of(raw[j < DFOL_NC_OF(raw) ? j : 0], word, t, normalise, rt, sm.den);
+              x1[j] = mod_apply(m1, sm.saved[t] + l);
+              x2[j] = mod_apply(m2, sm.cur[t] + l);
+            }
           }
           const float e1 = warp_exists(x1, n, hard, nullptr);
           const float e2 = warp_exists(x2, n, hard, nullptr);
           part += lnot(e1 + e2);
-        }
+        });
         float Q = block_sum(lane == 0 ? part : 0.f, sm.sc);
         float lp = lnot(Q);
         if (I.flags & DFOL_F_NEGATE_RESULT) lp = lnot(lp);
@@ -461,11 +471,6 @@ static __global__ void __launch_bounds__(PROG_THREADS) program_fwd_kernel(
 
 using namespace dfol;
 
-#ifdef DFOL_PROGRAM_FAST
-#define DFOL_PROGRAM_FWD_ENTRY dfol_program_fwd_fast
-#else
-#define DFOL_PROGRAM_FWD_ENTRY dfol_program_fwd
-#endif
 
 #ifdef DFOL_PROG_TIMING
 extern "C" int dfol_prog_timing_read(long long* host, int n) {
@@ -473,32 +478,45 @@ extern "C" int dfol_prog_timing_read(long long* host, int n) {
 }
 #endif
 
-extern "C" int DFOL_PROGRAM_FWD_ENTRY(const int32_t* instr, const int32_t* q_instr, const int32_t* opts,
-                                      int question_num, const float* attr_ll, const int64_t* attr_blk,
-                                      const int32_t* attr_stride, const float* rel_ll, const int64_t* rel_blk,
-                                      const int32_t* rel_stride, const int32_t* img_n, const float* mods,
-                                      float* lp_out, float* tape, int tape_stride, void* stream) {
+#ifdef DFOL_PROGRAM_FAST
+extern "C" int dfol_program_fwd_fast(const int32_t* instr, const int32_t* q_instr, const int32_t* opts,
+                                     int question_num, const float* attr_ll, const int64_t* attr_blk,
+                                     const int32_t* attr_stride, const float* rel_ll, const float* rel_p,
+                                     const int64_t* rel_blk, const int32_t* rel_stride, const int32_t* img_n,
+                                     const float* mods, float* lp_out, float* tape, int tape_stride, void* stream) {
   DFOL_REQUIRE(instr && q_instr && attr_ll && attr_blk && attr_stride && rel_ll && rel_blk && rel_stride && img_n &&
                    lp_out,
-               "dfol_program_fwd: null pointer");
-  DFOL_REQUIRE(tape == nullptr || tape_stride >= 1, "dfol_program_fwd: bad tape stride");
+               "dfol_program_fwd_fast: null pointer");
   if (question_num == 0) return 0;
-#ifdef DFOL_PROGRAM_FAST
   // ring of relation-tile buffers: as many (up to 4) as fit in ~96 KB so that two blocks share an SM
   DFOL_REQUIRE(tape_stride >= 1 && tape_stride <= MAXN, "dfol_program_fwd_fast: tape_stride = max objects rounded to 4");
   const int tile_floats = (tape_stride * tape_stride + 31) / 32 * 32;
   int nbuf = (96 * 1024) / (tile_floats * 4);
   nbuf = nbuf < 1 ? 1 : (nbuf > 4 ? 4 : nbuf);
   const size_t smem = (size_t)nbuf * tile_floats * 4;
-  cudaFuncSetAttribute(mods ? program_fwd_kernel<true> : program_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  (mods ? program_fwd_kernel<true> : program_fwd_kernel<false>)<<<question_num, PROG_THREADS, smem, (cudaStream_t)stream>>>(
+  auto kern = mods ? (rel_p ? program_fwd_kernel<true, true> : program_fwd_kernel<true, false>)
+                   : (rel_p ? program_fwd_kernel<false, true> : program_fwd_kernel<false, false>);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<question_num, PROG_THREADS, smem, (cudaStream_t)stream>>>(
       instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, mods, lp_out, tape,
-      tape_stride, nbuf, tile_floats);
+      tape_stride, rel_p, nbuf, tile_floats);
   return finish_launch("dfol_program_fwd_fast");
+}
 #else
-  (mods ? program_fwd_kernel<true> : program_fwd_kernel<false>)<<<question_num, PROG_THREADS, 0, (cudaStream_t)stream>>>(
+extern "C" int dfol_program_fwd(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
+                                const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
+                                const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride,
+                                const int32_t* img_n, const float* mods, float* lp_out, float* tape, int tape_stride,
+                                void* stream) {
+  DFOL_REQUIRE(instr && q_instr && attr_ll && attr_blk && attr_stride && rel_ll && rel_blk && rel_stride && img_n &&
+                   lp_out,
+               "dfol_program_fwd: null pointer");
+  DFOL_REQUIRE(tape == nullptr || tape_stride >= 1, "dfol_program_fwd: bad tape stride");
+  if (question_num == 0) return 0;
+  (mods ? program_fwd_kernel<true, false> : program_fwd_kernel<false, false>)<<<question_num, PROG_THREADS, 0,
+                                                                                 (cudaStream_t)stream>>>(
       instr, q_instr, opts, attr_ll, attr_blk, attr_stride, rel_ll, rel_blk, rel_stride, img_n, mods, lp_out, tape,
       tape_stride);
   return finish_launch("dfol_program_fwd");
-#endif
 }
+#endif

@@ -27,6 +27,7 @@ struct RsParams {
   const int32_t* slot_wrow; const int32_t* img_slot; const int64_t* slot_blk; const int32_t* stride;
   const int32_t* row0; const int32_t* img_rows; const int32_t* img_n;
   float diag; float* ll;
+  float* pp;  // optional probability table e^{ll} (0 on self pairs), same layout
 };
 
 __global__ void __launch_bounds__(RS_THREADS) rel_slots_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -99,7 +100,8 @@ __global__ void __launch_bounds__(RS_THREADS) rel_slots_tc_kernel(const __grid_c
 #pragma unroll
     for (int j = 0; j < RS_BN; ++j) bj[j] = (j < Sb) ? __ldg(p.bias + __ldg(p.slot_wrow + j0 + j)) : 0.0f;
     const long long st = p.stride[b];
-    float* dst = p.ll + p.slot_blk[b] + (long long)p.first * st + l;
+    const long long doff = p.slot_blk[b] + (long long)p.first * st + l;
+    float* dst = p.ll + doff;
     mbar_wait(&tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t r[16];
@@ -110,7 +112,9 @@ __global__ void __launch_bounds__(RS_THREADS) rel_slots_tc_kernel(const __grid_c
       for (int j = 0; j < RS_BN; ++j) {
         if (j < Sb) {
           const float x = __uint_as_float(r[j]) + bj[j];
-          dst[(long long)j * st] = is_diag ? p.diag : fminf(x, 0.0f) - __logf(1.0f + __expf(-fabsf(x)));
+          const float e = __expf(-fabsf(x));
+          dst[(long long)j * st] = is_diag ? p.diag : fminf(x, 0.0f) - __logf(1.0f + e);
+          if (p.pp != nullptr) p.pp[doff + (long long)j * st] = is_diag ? 0.0f : __fdividef(x >= 0.0f ? 1.0f : e, 1.0f + e);
         }
       }
     }
@@ -145,7 +149,7 @@ extern "C" int dfol_rel_slots_fwd_tc(const void* h_saved, int64_t ldh, int64_t t
                                      int64_t ldw, const float* bias, const int32_t* slot_wrow, const int32_t* img_slot,
                                      int max_slots, const int64_t* slot_blk, const int32_t* stride, const int32_t* row0,
                                      const int32_t* img_rows, const int32_t* img_n, int image_num, int max_rows,
-                                     float diag_value, void* wb_workspace, float* ll, void* stream) {
+                                     float diag_value, void* wb_workspace, float* ll, float* p_out, void* stream) {
   const char* who = "dfol_rel_slots_fwd_tc";
   DFOL_REQUIRE(h_saved && W && bias && slot_wrow && img_slot && slot_blk && stride && row0 && img_rows && img_n && ll &&
                    wb_workspace,
@@ -172,7 +176,7 @@ extern "C" int dfol_rel_slots_fwd_tc(const void* h_saved, int64_t ldh, int64_t t
     rel_slot_weights_kernel<<<image_num, 256, 0, st>>>(W, ldw, E, slot_wrow, img_slot, first, wb, K);
     RsParams p;
     p.K = K; p.first = first; p.bias = bias; p.slot_wrow = slot_wrow; p.img_slot = img_slot; p.slot_blk = slot_blk;
-    p.stride = stride; p.row0 = row0; p.img_rows = img_rows; p.img_n = img_n; p.diag = diag_value; p.ll = ll;
+    p.stride = stride; p.row0 = row0; p.img_rows = img_rows; p.img_n = img_n; p.diag = diag_value; p.ll = ll; p.pp = p_out;
     dim3 grid((max_rows + RS_BM - 1) / RS_BM, image_num);
     rel_slots_tc_kernel<<<grid, RS_THREADS, smem, st>>>(ma, mb, p);
   }

@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(256) rel_slots_fwd_kernel(
     const float* __restrict__ bias, const int32_t* __restrict__ slot_wrow, const int32_t* __restrict__ img_slot,
     int first, const int64_t* __restrict__ slot_blk, const int32_t* __restrict__ stride,
     const int32_t* __restrict__ row0, const int32_t* __restrict__ img_rows, const int32_t* __restrict__ img_n,
-    float diag, float* __restrict__ ll) {
+    float diag, float* __restrict__ ll, float* __restrict__ pp) {
   __shared__ float zs[S][TB_ROWS];
   const int b = blockIdx.y;
   const int rows = img_rows[b];
@@ -701,8 +701,11 @@ __global__ void __launch_bounds__(256) rel_slots_fwd_kernel(
     const int j = idx / cn, l = idx - j * cn;
     const int lg = c + l;
     const float x = zs[j][l] + __ldg(bias + slot_wrow[j0 + j]);
-    const float v = fminf(x, 0.0f) - __logf(1.0f + __expf(-fabsf(x)));
-    ll[base + (long long)j * stride[b] + l] = ((lg / n) == (lg % n)) ? diag : v;
+    const float e = __expf(-fabsf(x));
+    const float v = fminf(x, 0.0f) - __logf(1.0f + e);
+    const bool is_diag = (lg / n) == (lg % n);
+    ll[base + (long long)j * stride[b] + l] = is_diag ? diag : v;
+    if (pp != nullptr) pp[base + (long long)j * stride[b] + l] = is_diag ? 0.0f : __fdividef(x >= 0.0f ? 1.0f : e, 1.0f + e);
   }
 }
 
@@ -895,7 +898,7 @@ extern "C" int dfol_rel_slots_fwd(const void* h_saved, int64_t ldh, int E, const
                                   const float* bias, const int32_t* slot_wrow, const int32_t* img_slot, int max_slots,
                                   const int64_t* slot_blk, const int32_t* stride, const int32_t* row0,
                                   const int32_t* img_rows, const int32_t* img_n, int image_num, int max_rows,
-                                  float diag_value, float* ll, void* stream) {
+                                  float diag_value, float* ll, float* p_out, void* stream) {
   DFOL_REQUIRE(h_saved && W && bias && slot_wrow && img_slot && slot_blk && stride && row0 && img_rows && img_n && ll,
                "dfol_rel_slots_fwd: null pointer");
   if (image_num == 0 || max_rows == 0 || max_slots == 0) return 0;
@@ -909,7 +912,7 @@ extern "C" int dfol_rel_slots_fwd(const void* h_saved, int64_t ldh, int E, const
     const int left = max_slots - first;
 #define DFOL_RS_LAUNCH(S)                                                                                          \
   rel_slots_fwd_kernel<S, 5><<<grid, 256, 0, st>>>(hp, ldh, E, W, ldw, bias, slot_wrow, img_slot, first, slot_blk,  \
-                                                   stride, row0, img_rows, img_n, diag_value, ll)
+                                                   stride, row0, img_rows, img_n, diag_value, ll, p_out)
     if (left <= 1) { DFOL_RS_LAUNCH(1); first += 1; }
     else if (left == 2) { DFOL_RS_LAUNCH(2); first += 2; }
     else if (left <= 4) { DFOL_RS_LAUNCH(4); first += 4; }

@@ -401,10 +401,13 @@ class ReasoningEngine(object):
         tape = torch.empty(max(n_instr, 1) * stride, device=dev, dtype=torch.float32) if save_tape else None
         if capi.trace is not None:
             capi.next_meta = {'tag': 'program_fwd', 'bytes': cp.alg_bytes}
-        entry = 'dfol_program_fwd_fast' if self.gemm_mode == 'bf16' else 'dfol_program_fwd'
-        call(entry, ptr(d['instr']), ptr(d['q_instr']), ptr(d['opts']), cp.question_num,
-             ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride), ptr(scene.rel_ll), ptr(scene.rel_blk),
-             ptr(lay.rel_stride), ptr(lay.img_n), ptr(getattr(scene, 'mods', None)), ptr(lp), ptr(tape), stride, st)
+        fast = self.gemm_mode == 'bf16'
+        # tensor-core mode: the probability table (scene.rel_p, written by the slot kernels) feeds the relate hops
+        rel = (ptr(scene.rel_ll), ptr(getattr(scene, 'rel_p', None))) if fast else (ptr(scene.rel_ll),)
+        call('dfol_program_fwd_fast' if fast else 'dfol_program_fwd', ptr(d['instr']), ptr(d['q_instr']),
+             ptr(d['opts']), cp.question_num, ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride), *rel,
+             ptr(scene.rel_blk), ptr(lay.rel_stride), ptr(lay.img_n), ptr(getattr(scene, 'mods', None)), ptr(lp),
+             ptr(tape), stride, st)
         return lp[:cp.lp_num], tape
 
     # ------------------------------------------------------------------------------------------ backward
@@ -424,11 +427,12 @@ class ReasoningEngine(object):
         g_rel = torch.zeros(cp.g_rel_size, device=dev, dtype=torch.float32)
         if capi.trace is not None:
             capi.next_meta = {'tag': 'program_bwd', 'bytes': 2.0 * cp.alg_bytes}
-        entry = 'dfol_program_bwd_fast' if self.gemm_mode == 'bf16' else 'dfol_program_bwd'
-        call(entry, ptr(d['instr']), ptr(d['q_instr']), ptr(d['opts']), cp.question_num,
-             ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride), ptr(scene.rel_ll), ptr(scene.rel_blk),
-             ptr(lay.rel_stride), ptr(lay.img_n), ptr(getattr(scene, 'mods', None)), ptr(d_lp), ptr(tape), stride,
-             ptr(g_attr), ptr(g_rel), ptr(getattr(scene, 'd_mods', None)), st)
+        fast = self.gemm_mode == 'bf16'
+        rel = (ptr(scene.rel_ll), ptr(getattr(scene, 'rel_p', None))) if fast else (ptr(scene.rel_ll),)
+        call('dfol_program_bwd_fast' if fast else 'dfol_program_bwd', ptr(d['instr']), ptr(d['q_instr']),
+             ptr(d['opts']), cp.question_num, ptr(scene.attr_ll), ptr(lay.attr_blk), ptr(lay.attr_stride), *rel,
+             ptr(scene.rel_blk), ptr(lay.rel_stride), ptr(lay.img_n), ptr(getattr(scene, 'mods', None)), ptr(d_lp),
+             ptr(tape), stride, ptr(g_attr), ptr(g_rel), ptr(getattr(scene, 'd_mods', None)), st)
         return g_attr, g_rel
 
     def backward(self, cp, scene, tape, d_lp, grads, early_hook=None):

@@ -19,6 +19,7 @@ from .capi import K, call, ptr
 
 DEFAULT_LL = -30.0
 
+_REL_PTAB = os.environ.get('DFOL_REL_PTAB', '1') != '0'   # measurement switch
 _JOB_DTYPE = np.dtype([('src', np.uint64), ('lds', np.int64), ('rows', np.int32), ('cols', np.int32),
                        ('dst', np.uint64), ('ldd', np.int64), ('out_rows', np.int32), ('transpose', np.int32),
                        ('dcols', np.int32), ('pad', np.int32)], align=True)
@@ -321,6 +322,9 @@ class TensorCorePath(object):
         if slots:
             dc = self.engine.upload_programs(cp, dev)
             rel_ll = torch.empty(cp.rel_slot_size, device=dev, dtype=torch.float32)
+            # probability table e^{ll} next to the log table (operand of the probability-space relate hop;
+            # DFOL_REL_PTAB=0: the hop exponentiates the log tiles itself)
+            rel_p = torch.empty(cp.rel_slot_size, device=dev, dtype=torch.float32) if _REL_PTAB else None
             if not fused:
                 # the backward pass needs the layer-2 activation (or the image uses many relations): GEMM with bf16
                 # store, then the demand-driven relation columns from the stored activation
@@ -355,12 +359,14 @@ class TensorCorePath(object):
                          w.emb.weight.stride(0), ptr(w.emb.bias), ptr(dc['slot_wrow']), ptr(dc['img_slot']),
                          cp.max_slots, ptr(dc['slot_blk']), ptr(layout.rel_stride), ptr(layout.pair_row),
                          ptr(layout.img_nn), ptr(layout.img_np), layout.B, layout.max_n ** 2, DEFAULT_LL, ptr(wb),
-                         ptr(rel_ll), st)
+                         ptr(rel_ll), ptr(rel_p), st)
+                    sc.rel_p = rel_p
                 else:
                     call('dfol_rel_slots_fwd', ptr(h2r), p['Ep'], E, ptr(w.emb.weight), w.emb.weight.stride(0),
                          ptr(w.emb.bias), ptr(dc['slot_wrow']), ptr(dc['img_slot']), cp.max_slots,
                          ptr(dc['slot_blk']), ptr(layout.rel_stride), ptr(layout.pair_row), ptr(layout.img_nn),
-                         ptr(layout.img_np), layout.B, layout.max_n ** 2, DEFAULT_LL, ptr(rel_ll), st)
+                         ptr(layout.img_np), layout.B, layout.max_n ** 2, DEFAULT_LL, ptr(rel_ll), ptr(rel_p), st)
+                    sc.rel_p = rel_p
             else:
                 # inference: layer 2 + relation columns in one persistent tcgen05 kernel; the P x E activation is
                 # consumed in registers and never written

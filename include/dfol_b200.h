@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFOL_ABI_VERSION 4
+#define DFOL_ABI_VERSION 5
 
 /* activation codes (RegularMLP / EmbeddingLayer, gqa_interpreter_experiments.py:28-33, :71-72) */
 #define DFOL_ACT_NONE 0
@@ -279,17 +279,22 @@ int dfol_program_bwd(const int32_t* instr, const int32_t* q_instr, const int32_t
 
 /* Tensor-core-mode builds of the two interpreter kernels (same contract, tape_stride = largest object count rounded
  * up to 4): MUFU exp/log approximations; the N x N tile of every relate hop is fetched with a bulk-async copy into a
- * ring of shared-memory buffers ahead of the hop that reads it, and the hop is evaluated in probability space (one
- * exponential per pair).  Results agree with the exact kernels to fp32 rounding of the approximations (bf16-mode
- * tolerance of the answer logits: 2e-2). */
+ * ring of shared-memory buffers ahead of the hop that reads it, and the hop is evaluated in probability space:
+ *   res[x] = prior[x] + slog(1 - prod_{y != x} (1 - p[x,y] e^{a[y]})),
+ * a warp taking up to eight rows in one pass (a transposed shuffle butterfly reduces them together) and the lane that
+ * ends up with a row writing its posterior.  rel_p (optional, NULL = absent): the PROBABILITY table p = e^{ll}, same
+ * blocks / strides as rel_ll, zero on self pairs (written by dfol_rel_slots_fwd[_tc]); with it a pair costs one FFMA and
+ * one FMUL, without it one MUFU.EX2 more.  rel_ll is still read by choose_rel and by programs beyond the ring's reach.
+ * Results agree with the exact kernels to fp32 rounding of the approximations (bf16-mode tolerance of the answer
+ * logits: 2e-2). */
 int dfol_program_fwd_fast(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
                           const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
-                          const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride,
+                          const float* rel_ll, const float* rel_p, const int64_t* rel_blk, const int32_t* rel_stride,
                           const int32_t* img_n, const float* mods, float* lp_out, float* tape, int tape_stride,
                           void* stream);
 int dfol_program_bwd_fast(const int32_t* instr, const int32_t* q_instr, const int32_t* opts, int question_num,
                           const float* attr_ll, const int64_t* attr_blk, const int32_t* attr_stride,
-                          const float* rel_ll, const int64_t* rel_blk, const int32_t* rel_stride,
+                          const float* rel_ll, const float* rel_p, const int64_t* rel_blk, const int32_t* rel_stride,
                           const int32_t* img_n, const float* mods, const float* d_lp, const float* tape,
                           int tape_stride, float* g_attr, float* g_rel, float* d_mods, void* stream);
 
@@ -351,7 +356,7 @@ int dfol_rel_slots_fwd_tc(const void* h_saved, int64_t ldh, int64_t total_rows, 
                           const float* bias, const int32_t* slot_wrow, const int32_t* img_slot, int max_slots,
                           const int64_t* slot_blk, const int32_t* stride, const int32_t* row0, const int32_t* img_rows,
                           const int32_t* img_n, int image_num, int max_rows, float diag_value, void* wb_workspace,
-                          float* ll, void* stream);
+                          float* ll, float* p_out, void* stream);
 
 /* Loss of VQATrainer._compute_loss (nsvqa/train/trainer.py:181-262) and its derivative w.r.t. lp.
  * kind 0 BINARY: BCE(exp(lp), target) summed; 1 QUERY: sum_q slog(sum_{k in q} e^{lp_k}) - sum_k target_k lp_k
@@ -430,7 +435,9 @@ int dfol_pair_chain_fwd(const float* uv, int64_t lduv, const float* obj_pos, int
 int dfol_rel_slots_fwd(const void* h_saved, int64_t ldh, int E, const float* W, int64_t ldw, const float* bias,
                        const int32_t* slot_wrow, const int32_t* img_slot, int max_slots, const int64_t* slot_blk,
                        const int32_t* stride, const int32_t* row0, const int32_t* img_rows, const int32_t* img_n,
-                       int image_num, int max_rows, float diag_value, float* ll, void* stream);
+                       int image_num, int max_rows, float diag_value, float* ll, float* p_out, void* stream);
+/* p_out (optional, NULL = not written; also on dfol_rel_slots_fwd_tc): the probability table sigmoid(.) = e^{ll} in the
+ * same layout, zero on self pairs -- the operand of the probability-space relate hop of dfol_program_{fwd,bwd}_fast. */
 
 /* Dense variant for tables where images touch many columns (attribute options): scatters the slices into a zeroed
  * dense (rows x columns) matrix with logsigmoid' applied, dZ[row0[b] + l, col_j] += g_j[l] * (1 - exp(LL_j[l]));

@@ -372,12 +372,19 @@ def test_pair_layer_fwd_slot_epilogue(counts, slots_per_image, store):
         assert torch.allclose(H2[:, :E].double(), h2, rtol=1.5e-2, atol=1.5e-2)
         assert bool((H2[:, E:] == 0).all())
         ll2 = torch.full_like(ll, float('nan'))
+        pp2 = torch.full_like(ll, float('nan'))
         call('dfol_rel_slots_fwd', ptr(H2), ldc, E, ptr(We), E, ptr(be), ptr(d['slot_wrow']), ptr(d['img_slot']),
              max(slots_per_image), ptr(d['blk']), ptr(d['stride']), ptr(d['pair_row']), ptr(d['img_nn']),
-             ptr(d['img_n']), len(counts), max(counts) ** 2, -30.0, ptr(ll2), stream_ptr())
+             ptr(d['img_n']), len(counts), max(counts) ** 2, -30.0, ptr(ll2), ptr(pp2), stream_ptr())
         torch.cuda.synchronize()
         got2 = ll2.double().cpu()
         assert torch.allclose(got2[mask], ref[mask], rtol=2e-2, atol=2e-2), (got2[mask] - ref[mask]).abs().max()
+        # the probability table: e^{ll}, zero on self pairs (ll = -30)
+        p2 = pp2.double().cpu()
+        diag = mask & (got2 == -30.0)
+        assert bool((p2[diag] == 0).all())
+        off = mask & ~diag
+        assert torch.allclose(p2[off], got2[off].exp(), rtol=1e-5, atol=1e-30)
 
 
 @pytest.mark.parametrize('M,N,K', [(1000, 256, 320), (4608 + 5, 256, 320), (300, 64, 64), (40000, 256, 320)])
