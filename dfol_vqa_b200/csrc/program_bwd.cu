@@ -159,6 +159,7 @@ static __global__ void __launch_bounds__(PROG_THREADS, MOD ? 1 : PROG_MIN_BLOCKS
   __shared__ int rel_ip[MAX_REL];
   __shared__ int rel_count, rel_beyond, push_ip;
   __shared__ int32_t code_s[MAX_CODE * DFOL_INSTR_WORDS];
+  __shared__ int32_t opt_s[OPT_STAGE];  // option words of the instruction being executed
   TileRing ring{ring_mem, ring_nbuf, ring_tile_floats, ring_full};
   const float* ring_src = PTAB ? rel_p + rel_blk[q] : im.rel;
   const int code_n = min(ip1 - ip0, MAX_CODE);
@@ -354,7 +355,11 @@ static __global__ void __launch_bounds__(PROG_THREADS, MOD ? 1 : PROG_MIN_BLOCKS
       }
 
       case DFOL_OP_VERIFY_ATTRS: {
+#ifdef DFOL_PROGRAM_FAST
+        const int32_t* op = stage_options(opts + I.a0, I.a1, opt_s);
+#else
         const int32_t* op = opts + I.a0;
+#endif
         float acc[NCHUNK];
 #pragma unroll
         for (int j = 0; j < NCHUNK; ++j) acc[j] = 0.f;
@@ -401,9 +406,42 @@ static __global__ void __launch_bounds__(PROG_THREADS, MOD ? 1 : PROG_MIN_BLOCKS
       case DFOL_OP_CHOOSE_ATTR:
       case DFOL_OP_ALL_SAME:
       case DFOL_OP_TWO_SAME: {
+#ifdef DFOL_PROGRAM_FAST
+        const int32_t* op = stage_options(opts + I.a0, I.a1, opt_s);
+#else
         const int32_t* op = opts + I.a0;
+#endif
         float* gslice = g_attr + I.ga0;
         if (normalise) bwd_option_denominators(im, op, I.a1, sm.den, sm.sc);
+#ifdef DFOL_PROGRAM_FAST
+        if (I.op == DFOL_OP_CHOOSE_ATTR && !(MOD && I.mod >= 0)) {
+          // probability space (see options_pspace_nc): products, c_k, gradients of the (k, t) entries in one pass
+          if (tid < MAXN) {
+            float a = 0.f, wv = 0.f;
+            if (tid < n) {
+              a = __expf(sm.cur[tid]);
+              wv = normalise ? __fdividef(a, fmaxf(sm.den[tid], kLogEps)) : a;
+            }
+            sm.inner[tid] = a;
+            sm.res[tid] = wv;
+          }
+          __syncthreads();
+          float acc_g[NCHUNK], acc_tot[NCHUNK];
+#pragma unroll
+          for (int j = 0; j < NCHUNK; ++j) { acc_g[j] = 0.f; acc_tot[j] = 0.f; }
+          auto no_sink = [](int, float) {};
+          if (n <= 64)
+            options_pspace_nc<8, 2, true, false>(im, op, I.a1, sm.inner, sm.res, d_lp + I.out, gslice, acc_g, acc_tot, no_sink);
+          else
+            options_pspace_nc<4, NCHUNK, true, false>(im, op, I.a1, sm.inner, sm.res, d_lp + I.out, gslice, acc_g, acc_tot, no_sink);
+          reduce_columns(acc_g, n, sm.g, sm.sc, false);
+          if (normalise) {
+            reduce_columns(acc_tot, n, sm.tot, sm.sc, false);
+            attr_softmax_correction(im, op, I.a1, gslice, sm.den, sm.tot);
+          }
+          break;
+        }
+#endif
         float dQ = 0.f;
         if (I.op != DFOL_OP_CHOOSE_ATTR) {
           // first pass: Q = sum_k lnot(v_k) exactly as in the forward kernel
@@ -587,7 +625,11 @@ static __global__ void __launch_bounds__(PROG_THREADS, MOD ? 1 : PROG_MIN_BLOCKS
         }
         if (normalise) {
           // softmax correction per pair: d raw_j = d nrm_j - (sum_k d nrm_k) exp(raw_j) / den
-          const int32_t* op = opts + I.a0;
+  #ifdef DFOL_PROGRAM_FAST
+        const int32_t* op = stage_options(opts + I.a0, I.a1, opt_s);
+#else
+        const int32_t* op = opts + I.a0;
+#endif
           float* gs = g_rel + I.gr;
           for (int e = tid; e < n * n; e += PROG_THREADS) {
             const int s = e / n, o = e - s * n;

@@ -162,44 +162,47 @@ __device__ __forceinline__ void reduce_columns(const float acc[NCHUNK], int n, f
   __syncthreads();
 }
 
-// Option lists (query / choose / verify / same over up to ~1400 attribute options): a warp takes U options per pass and
-// issues the U option words, then all U table rows, before it touches any of them -- U independent global loads in
-// flight per lane instead of a chain of (word -> row) round trips per option (an 1356-option query spent ~85 dependent
-// HBM latencies per warp and pass).  NC = 32-object chunks per row (2 for images of <= 64 objects).  Options are visited
-// in the same order as a plain strided loop, so per-warp accumulations round identically.
+// Option lists (query / choose / verify / same over up to ~1750 attribute options): a warp takes U options per pass and
+// issues all U table rows before it touches any of them -- U independent global loads in flight per lane instead of a
+// chain of (word -> row) round trips per option (a 1749-option query spent ~110 dependent HBM latencies per warp and
+// pass; the probability-space query path below additionally keeps the rows of pass i+1 in flight under pass i).  The option words come from
+// `op`, which the tensor-core build points at a shared-memory copy of the list (stage_options), so that no row address
+// waits on a global load.  NC = 32-object chunks per row (2 for images of <= 64 objects).  Options are visited in the
+// same order as a plain strided loop, so per-warp accumulations round identically.
 //   body(k, word, raw): warp-uniform call for option k; raw[j] = table entry of object lane + 32 j (0 beyond n).
+template <int U, int NC>
+__device__ __forceinline__ void options_load(const Image& im, const int32_t* op, int count, int k0, float (&dst)[U][NC]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int k = k0 + u * PROG_WARPS;
+    const bool ok = k < count;
+    const int word = ok ? op[k] : 0;
+    const float* row = im.attr + (long long)(word & ~DFOL_OPT_NEG) * im.astride;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int t = lane + 32 * j;
+      dst[u][j] = (ok && t < im.n) ? __ldg(row + t) : 0.0f;
+    }
+  }
+}
 template <int U, int NC, class Body>
-__device__ __forceinline__ void for_options_nc(const Image& im, const int32_t* __restrict__ op, int count, Body body) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+__device__ __forceinline__ void for_options_nc(const Image& im, const int32_t* op, int count, Body body) {
+  const int w = threadIdx.x >> 5;
   for (int k0 = w; k0 < count; k0 += PROG_WARPS * U) {
-    int word[U];
     float raw[U][NC];
+    options_load<U, NC>(im, op, count, k0, raw);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int k = k0 + u * PROG_WARPS;
-      word[u] = (k < count) ? __ldg(op + k) : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int k = k0 + u * PROG_WARPS;
-      const float* row = im.attr + (long long)(word[u] & ~DFOL_OPT_NEG) * im.astride;
-#pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        const int t = lane + 32 * j;
-        raw[u][j] = (k < count && t < im.n) ? __ldg(row + t) : 0.0f;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int k = k0 + u * PROG_WARPS;
-      if (k < count) body(k, word[u], raw[u]);
+      if (k < count) body(k, op[k], raw[u]);
     }
   }
 }
 template <int U, class Body>
-__device__ __forceinline__ void for_options(const Image& im, const int32_t* __restrict__ op, int count, Body body) {
+__device__ __forceinline__ void for_options(const Image& im, const int32_t* op, int count, Body body) {
   if (im.n <= 64) for_options_nc<U, 2>(im, op, count, body);
-  else for_options_nc<U, NCHUNK>(im, op, count, body);
+  else for_options_nc<(U > 4 ? 4 : U), NCHUNK>(im, op, count, body);
 }
 #define DFOL_NC_OF(raw) ((int)(sizeof(raw) / sizeof(float)))
 
@@ -419,13 +422,19 @@ __device__ __forceinline__ void hop_forward_t(int n, const float* __restrict__ t
   constexpr int RS = 32 / LPR, NS = PROG_WARPS * RS;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int l = lane % LPR, g = w * RS + lane / LPR;
+  // Common case (probability tiles, plain relation, n % 4 == 0): NO predication.  Rows / columns outside the image read
+  // a clamped (valid, finite) address and are neutralised by the zero entries of ea[] beyond n (factor 1 - p * 0 = 1);
+  // the products of row slots >= n are computed and dropped.
+  constexpr bool LEAN = PTAB && !NEG && ALIGNED;
+  const float* lean_col = tile + min(4 * l, n - 4);
   if (subject_role) {
     const float4 eo = *reinterpret_cast<const float4*>(ea + 4 * l);
     float q[NR];
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
       const int s = g + NS * i;
-      const float4 r = hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
+      const float4 r = LEAN ? *reinterpret_cast<const float4*>(lean_col + min(s, n - 1) * n)
+                            : hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
       q[i] = (fmaf(-r.x, eo.x, 1.0f) * fmaf(-r.y, eo.y, 1.0f)) * (fmaf(-r.z, eo.z, 1.0f) * fmaf(-r.w, eo.w, 1.0f));
     }
     int ri;
@@ -436,9 +445,10 @@ __device__ __forceinline__ void hop_forward_t(int n, const float* __restrict__ t
     float4 acc = make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
-      const int s = g + NS * i;
-      const float4 r = hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
-      const float es = (s < n) ? ea[s] : 0.0f;
+      const int s = g + NS * i;   // s < MAXN always: ea[s] is zero for s >= n
+      const float4 r = LEAN ? *reinterpret_cast<const float4*>(lean_col + min(s, n - 1) * n)
+                            : hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
+      const float es = LEAN ? ea[s] : ((s < n) ? ea[s] : 0.0f);
       acc.x *= fmaf(-r.x, es, 1.0f); acc.y *= fmaf(-r.y, es, 1.0f);
       acc.z *= fmaf(-r.z, es, 1.0f); acc.w *= fmaf(-r.w, es, 1.0f);
     }
@@ -514,6 +524,9 @@ __device__ __forceinline__ void hop_backward_t(int n, const float* __restrict__ 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int l = lane % LPR, g = w * RS + lane / LPR;
   const int o0 = 4 * l;
+  // (LEAN: see hop_forward_t -- clamped addresses instead of predication; cbuf[] and ea[] are zero beyond n)
+  constexpr bool LEAN = PTAB && !NEG && ALIGNED;
+  const float* lean_col = tile + min(o0, n - 4);
   if (subject_role) {
     const float4 eo = *reinterpret_cast<const float4*>(ea + o0);
     {
@@ -521,7 +534,8 @@ __device__ __forceinline__ void hop_backward_t(int n, const float* __restrict__ 
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
         const int s = g + NS * i;
-        const float4 r = hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
+        const float4 r = LEAN ? *reinterpret_cast<const float4*>(lean_col + min(s, n - 1) * n)
+                              : hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
         q[i] = (fmaf(-r.x, eo.x, 1.0f) * fmaf(-r.y, eo.y, 1.0f)) * (fmaf(-r.z, eo.z, 1.0f) * fmaf(-r.w, eo.w, 1.0f));
       }
       int ri;
@@ -534,7 +548,13 @@ __device__ __forceinline__ void hop_backward_t(int n, const float* __restrict__ 
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
       const int s = g + NS * i;
-      if (s < n && o0 < n) {
+      if (LEAN) {
+        const float4 r = *reinterpret_cast<const float4*>(lean_col + min(s, n - 1) * n);
+        const float c = cbuf[s];   // zero for s >= n
+        const float4 du = hop_du(r, make_float4(c * eo.x, c * eo.y, c * eo.z, c * eo.w), eo);
+        acc.x += du.x; acc.y += du.y; acc.z += du.z; acc.w += du.w;
+        if (s < n && o0 < n) *reinterpret_cast<float4*>(gslice + s * n + o0) = du;
+      } else if (s < n && o0 < n) {
         float4 p0;
         const float4 r = hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, true, &p0);
         const float c = cbuf[s];
@@ -557,8 +577,9 @@ __device__ __forceinline__ void hop_backward_t(int n, const float* __restrict__ 
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
         const int s = g + NS * i;
-        const float4 r = hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
-        const float es = (s < n) ? ea[s] : 0.0f;
+        const float4 r = LEAN ? *reinterpret_cast<const float4*>(lean_col + min(s, n - 1) * n)
+                              : hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
+        const float es = LEAN ? ea[s] : ((s < n) ? ea[s] : 0.0f);
         acc.x *= fmaf(-r.x, es, 1.0f); acc.y *= fmaf(-r.y, es, 1.0f);
         acc.z *= fmaf(-r.z, es, 1.0f); acc.w *= fmaf(-r.w, es, 1.0f);
       }
@@ -582,7 +603,14 @@ __device__ __forceinline__ void hop_backward_t(int n, const float* __restrict__ 
     for (int i = 0; i < NR; ++i) {
       const int s = g + NS * i;
       rs[i] = 0.f;
-      if (s < n && o0 < n) {
+      if (LEAN) {   // c4 is zero for objects >= n, ea[s] for rows >= n
+        const float4 r = *reinterpret_cast<const float4*>(lean_col + min(s, n - 1) * n);
+        const float es = ea[s];
+        const float4 du = hop_du(r, make_float4(c4.x * es, c4.y * es, c4.z * es, c4.w * es),
+                                 make_float4(es, es, es, es));
+        rs[i] = (du.x + du.y) + (du.z + du.w);
+        if (s < n && o0 < n) *reinterpret_cast<float4*>(gslice + s * n + o0) = du;
+      } else if (s < n && o0 < n) {
         float4 p0;
         const float4 r = hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, true, &p0);
         const float es = ea[s];
@@ -618,6 +646,114 @@ __device__ __forceinline__ void hop_backward(int n, const float* __restrict__ ti
   else if (n <= 64) DFOL_HOP_BWD(16, 2)
   else DFOL_HOP_BWD(32, 8)
 #undef DFOL_HOP_BWD
+}
+
+// ---- option lists in probability space (choose_attr / query_attr, soft quantifier, no modulation) ----
+//   lp_k = slog(1 - Q_k),  Q_k = prod_t (1 - term_kt),  term_kt = a_t e^{raw_kt} / den_t   (negated option: a_t - that)
+// at_s[] = e^{cur}, wt_s[] = at / max(den, eps) (at itself when the list is not normalised), both ZERO beyond n.
+// A warp takes 8 options per pass (rows of the next pass already in flight), every lane multiplies its objects' factors
+// and ONE transposed butterfly reduces the 8 products.  BWD: the lane that ends up with option k turns d loss / d lp_k
+// into c_k = d_lp Q / (1 - Q), the eight c are broadcast back and every lane emits the gradients of its (k, t) entries:
+//   d loss / d cur_t += c_k term / (1 - term),   d loss / d nrm_kt = +- c_k x / (1 - term),  x = a_t e^{raw} / den_t
+// (the softmax correction of the normalisation is the caller's second pass, as in the log-space path).
+constexpr int OPT_STAGE = 2048;  // option words of one instruction staged in shared memory
+
+__device__ __forceinline__ const int32_t* stage_options(const int32_t* __restrict__ op, int count, int32_t* stage) {
+  if (count > OPT_STAGE) return op;
+  __syncthreads();  // previous users of the staging area
+  for (int i = threadIdx.x; i < count; i += PROG_THREADS) stage[i] = __ldg(op + i);
+  __syncthreads();
+  return stage;
+}
+
+// lane that holds row index u after rows_reduce<32, U, .> (U = 8 or 4)
+template <int U>
+__device__ __forceinline__ int reduce_src_lane(int u) {
+  return U == 8 ? (((u & 4) ? 16 : 0) | ((u & 2) ? 8 : 0) | ((u & 1) ? 4 : 0)) : (((u & 2) ? 16 : 0) | ((u & 1) ? 8 : 0));
+}
+
+template <int U, int NC, bool BWD, bool PREFETCH, class LpSink>
+__device__ __forceinline__ void options_pspace_nc(const Image& im, const int32_t* op, int count, const float* at_s,
+                                                  const float* wt_s, const float* __restrict__ d_lp,
+                                                  float* __restrict__ gslice, float (&acc_g)[NCHUNK],
+                                                  float (&acc_tot)[NCHUNK], LpSink lp_sink) {
+  static_assert(U == 8 || U == 4, "options per warp pass");
+  constexpr float kLog2e = 1.4426950408889634f;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float at[NC], wt[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) { at[j] = at_s[lane + 32 * j]; wt[j] = wt_s[lane + 32 * j]; }
+  float raw[U][NC];
+  if constexpr (PREFETCH) {
+    if (w < count) options_load<U, NC>(im, op, count, w, raw);
+  }
+  for (int k0 = w; k0 < count; k0 += PROG_WARPS * U) {
+    float nxt[PREFETCH ? U : 1][NC];
+    const int k1 = k0 + PROG_WARPS * U;
+    if constexpr (PREFETCH) {
+      if (k1 < count) options_load<U, NC>(im, op, count, k1, nxt);
+    } else {
+      options_load<U, NC>(im, op, count, k0, raw);
+    }
+    float v[U];
+    unsigned negmask = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + u * PROG_WARPS;
+      const bool ok = k < count;
+      const bool neg = ok && (op[k] & DFOL_OPT_NEG) != 0;
+      negmask |= neg ? (1u << u) : 0u;
+      float prod = 1.0f;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const float e = ex2_approx(raw[u][j] * kLog2e);
+        raw[u][j] = e;  // kept for the gradient pass
+        const float x = wt[j] * e;
+        prod *= 1.0f - (neg ? at[j] - x : x);
+      }
+      v[u] = ok ? prod : 1.0f;
+    }
+    int ri;
+    const float Q = rows_reduce<32, U, true>(v, lane, ri);
+    const int kq = k0 + ri * PROG_WARPS;
+    const bool writer = (lane & (32 / U - 1)) == 0 && kq < count;
+    if (!BWD) {
+      if (writer) lp_sink(kq, Q);
+    } else {
+      float c = 0.0f;
+      if (writer) {
+        const float uu = 1.0f - Q;
+        c = (uu >= kLogEps) ? d_lp[kq] * __fdividef(Q, uu) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float cu = __shfl_sync(0xffffffffu, c, reduce_src_lane<U>(u));
+        const int k = k0 + u * PROG_WARPS;
+        if (k < count) {  // warp-uniform
+          const bool neg = (negmask >> u) & 1u;
+#pragma unroll
+          for (int j = 0; j < NC; ++j) {
+            const int t = lane + 32 * j;
+            const float x = wt[j] * raw[u][j];
+            const float term = neg ? at[j] - x : x;
+            const float cf = cu * rcp_approx(fmaxf(1.0f - term, kLogEps));
+            const float dn = neg ? -(cf * x) : cf * x;
+            acc_g[j] += cf * term;
+            acc_tot[j] += dn;
+            if (t < im.n) gslice[(long long)k * im.astride + t] = dn;
+          }
+        }
+      }
+    }
+    if constexpr (PREFETCH) {
+      if (k1 < count) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int j = 0; j < NC; ++j) raw[u][j] = nxt[u][j];
+      }
+    }
+  }
 }
 #endif  // DFOL_PROGRAM_FAST
 

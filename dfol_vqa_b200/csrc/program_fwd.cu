@@ -120,6 +120,7 @@ static __global__ void __launch_bounds__(PROG_THREADS, MOD ? 1 : PROG_MIN_BLOCKS
   // together with the attribute column each instruction will want prefetched and the list of its relate hops
   __shared__ int32_t code_s[MAX_CODE * DFOL_INSTR_WORDS];
   __shared__ int pre_col_s[MAX_CODE];
+  __shared__ int32_t opt_s[OPT_STAGE];  // option words of the instruction being executed
   const int ip_first = q_instr[q];
   const int ip_last = q_instr[q + 1];
   const int code_n = min(ip_last - ip_first, MAX_CODE);
@@ -316,7 +317,11 @@ static __global__ void __launch_bounds__(PROG_THREADS, MOD ? 1 : PROG_MIN_BLOCKS
 
       case DFOL_OP_VERIFY_ATTRS: {
         // sum over the question's attributes of (a + ll_k), then exists (GQAVerifyAttrsBatch :452-473)
+#ifdef DFOL_PROGRAM_FAST
+        const int32_t* op = stage_options(opts + I.a0, I.a1, opt_s);
+#else
         const int32_t* op = opts + I.a0;
+#endif
         float acc[NCHUNK];
 #pragma unroll
         for (int j = 0; j < NCHUNK; ++j) acc[j] = 0.f;
@@ -335,8 +340,35 @@ static __global__ void __launch_bounds__(PROG_THREADS, MOD ? 1 : PROG_MIN_BLOCKS
       }
 
       case DFOL_OP_CHOOSE_ATTR: {
+#ifdef DFOL_PROGRAM_FAST
+        const int32_t* op = stage_options(opts + I.a0, I.a1, opt_s);
+#else
         const int32_t* op = opts + I.a0;
+#endif
         if (normalise) option_denominators(im, op, I.a1, sm.den, sm.sc);
+#ifdef DFOL_PROGRAM_FAST
+        if (!hard && !(MOD && I.mod >= 0)) {
+          // probability space: a_t = e^{cur}, w_t = a_t / den_t; 8 options per warp pass, one transposed reduction
+          if (tid < MAXN) {
+            float a = 0.f, wv = 0.f;
+            if (tid < n) {
+              a = __expf(sm.cur[tid]);
+              wv = normalise ? __fdividef(a, fmaxf(sm.den[tid], kLogEps)) : a;
+            }
+            sm.inner[tid] = a;
+            sm.res[tid] = wv;
+          }
+          __syncthreads();
+          float unused_g[NCHUNK], unused_t[NCHUNK];
+          auto sink = [&](int k, float Q) { lp_out[I.out + k] = slog(1.0f - Q); };
+          if (n <= 64)
+            options_pspace_nc<8, 2, false, true>(im, op, I.a1, sm.inner, sm.res, nullptr, nullptr, unused_g, unused_t, sink);
+          else
+            options_pspace_nc<4, NCHUNK, false, true>(im, op, I.a1, sm.inner, sm.res, nullptr, nullptr, unused_g, unused_t, sink);
+          __syncthreads();
+          break;
+        }
+#endif
         for_options<8>(im, op, I.a1, [&](int k, int word, const auto& raw) {
           const Mod mk = DFOL_LOAD_MOD(I.mod >= 0 ? I.mod + k : -1);
           float x[NCHUNK];
@@ -356,7 +388,11 @@ static __global__ void __launch_bounds__(PROG_THREADS, MOD ? 1 : PROG_MIN_BLOCKS
 
       case DFOL_OP_ALL_SAME: {
         // per option: q_k = forall_t lnot(a + lnot(a + ll_k)); lp = lnot(sum_k lnot(q_k))  (:582-608)
+#ifdef DFOL_PROGRAM_FAST
+        const int32_t* op = stage_options(opts + I.a0, I.a1, opt_s);
+#else
         const int32_t* op = opts + I.a0;
+#endif
         if (normalise) option_denominators(im, op, I.a1, sm.den, sm.sc);
         float part = 0.f;
         for_options<4>(im, op, I.a1, [&](int k, int word, const auto& raw) {
@@ -385,7 +421,11 @@ static __global__ void __launch_bounds__(PROG_THREADS, MOD ? 1 : PROG_MIN_BLOCKS
       }
 
       case DFOL_OP_TWO_SAME: {
+#ifdef DFOL_PROGRAM_FAST
+        const int32_t* op = stage_options(opts + I.a0, I.a1, opt_s);
+#else
         const int32_t* op = opts + I.a0;
+#endif
         if (normalise) option_denominators(im, op, I.a1, sm.den, sm.sc);
         float part = 0.f;
         for_options<4>(im, op, I.a1, [&](int k, int word, const auto& raw) {

@@ -182,6 +182,8 @@ def _programs_world(terminal, batch, n_max, ragged, seed, relate_prob=0.6, neg_r
 @pytest.mark.parametrize('terminal,n_max,ragged,neg_rel', [
     ('chain', 48, False, False), ('verify_rel', 37, True, False), ('choose_rel', 24, True, False),
     ('query_attr', 48, False, False), ('and', 100, False, False),
+    # option lists in probability space: long lists (several passes per warp), > 64 objects, ragged counts
+    ('query_attr', 100, True, False), ('query_attr', 20, True, False), ('choose_attr', 37, True, False),
     # every hop geometry (8 / 16 / 32 lanes per tile row), aligned and ragged object counts, negated relations
     ('chain', 30, True, False), ('chain', 32, False, True), ('chain', 61, True, True), ('chain', 64, False, False),
     ('chain', 100, False, True), ('chain', 125, True, False), ('chain', 128, False, False), ('chain', 99, True, True)])
