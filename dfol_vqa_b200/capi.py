@@ -107,6 +107,7 @@ _SIGNATURES = {
     'dfol_table_grad_dense': (c_int, [P, P, P, P, c_int, P, P, P, P, P, P, c_int64, P]),
     'dfol_answers': (c_int, [P, P, c_int, c_int, c_float, P, P, P, P, P]),
     'dfol_sumsq': (c_int, [P, c_int64, P, P]),
+    'dfol_l1_regularize': (c_int, [P, P, c_int64, c_float, c_float, P, P]),
     'dfol_adam_step': (c_int, [P, P, P, P, c_int64, P, c_float, c_float, c_float, c_float, c_float, c_float, c_int,
                                P]),
 }

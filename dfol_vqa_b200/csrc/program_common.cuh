@@ -6,8 +6,14 @@
 namespace dfol {
 
 #ifdef DFOL_PROGRAM_FAST
-constexpr int PROG_THREADS = 512;  // 16 warps per question: twice the rows of a relation tile in flight
-constexpr int PROG_MIN_BLOCKS = 2;  // two questions per SM (64 registers per thread)
+#ifndef DFOL_PROG_THREADS
+#define DFOL_PROG_THREADS 512
+#endif
+constexpr int PROG_THREADS = DFOL_PROG_THREADS;  // 16 warps per question: twice the rows of a relation tile in flight
+#ifndef DFOL_PROG_MIN_BLOCKS
+#define DFOL_PROG_MIN_BLOCKS (1024 / DFOL_PROG_THREADS)
+#endif
+constexpr int PROG_MIN_BLOCKS = DFOL_PROG_MIN_BLOCKS;  // two questions per SM (64 registers per thread)
 #else
 constexpr int PROG_THREADS = 256;
 constexpr int PROG_MIN_BLOCKS = 1;
@@ -433,6 +439,8 @@ __device__ __forceinline__ void hop_forward_t(int n, const float* __restrict__ t
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
       const int s = g + NS * i;
+      q[i] = 1.0f;
+      if (LPR == 32 && s >= n) continue;   // (a warp = one row group: warp-uniform)
       const float4 r = LEAN ? *reinterpret_cast<const float4*>(lean_col + min(s, n - 1) * n)
                             : hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
       q[i] = (fmaf(-r.x, eo.x, 1.0f) * fmaf(-r.y, eo.y, 1.0f)) * (fmaf(-r.z, eo.z, 1.0f) * fmaf(-r.w, eo.w, 1.0f));
@@ -446,6 +454,7 @@ __device__ __forceinline__ void hop_forward_t(int n, const float* __restrict__ t
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
       const int s = g + NS * i;   // s < MAXN always: ea[s] is zero for s >= n
+      if (LPR == 32 && s >= n) continue;
       const float4 r = LEAN ? *reinterpret_cast<const float4*>(lean_col + min(s, n - 1) * n)
                             : hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
       const float es = LEAN ? ea[s] : ((s < n) ? ea[s] : 0.0f);
@@ -477,9 +486,9 @@ __device__ __forceinline__ void hop_forward(int n, const float* __restrict__ til
       else hop_forward_t<LPR, NR, PTAB, true, false>(n, tile, ea, subject_role, sc, finish);              \
     }                                                                                                      \
   }
-  if (n <= 32) DFOL_HOP_FWD(8, 1)
-  else if (n <= 64) DFOL_HOP_FWD(16, 2)
-  else DFOL_HOP_FWD(32, 8)
+  if (n <= 32) DFOL_HOP_FWD(8, (32 + 4 * PROG_WARPS - 1) / (4 * PROG_WARPS))
+  else if (n <= 64) DFOL_HOP_FWD(16, 64 / (2 * PROG_WARPS))
+  else DFOL_HOP_FWD(32, MAXN / PROG_WARPS)
 #undef DFOL_HOP_FWD
 }
 
@@ -534,6 +543,8 @@ __device__ __forceinline__ void hop_backward_t(int n, const float* __restrict__ 
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
         const int s = g + NS * i;
+        q[i] = 1.0f;
+        if (LPR == 32 && s >= n) continue;   // warp-uniform
         const float4 r = LEAN ? *reinterpret_cast<const float4*>(lean_col + min(s, n - 1) * n)
                               : hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
         q[i] = (fmaf(-r.x, eo.x, 1.0f) * fmaf(-r.y, eo.y, 1.0f)) * (fmaf(-r.z, eo.z, 1.0f) * fmaf(-r.w, eo.w, 1.0f));
@@ -548,6 +559,7 @@ __device__ __forceinline__ void hop_backward_t(int n, const float* __restrict__ 
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
       const int s = g + NS * i;
+      if (LPR == 32 && s >= n) continue;   // warp-uniform
       if (LEAN) {
         const float4 r = *reinterpret_cast<const float4*>(lean_col + min(s, n - 1) * n);
         const float c = cbuf[s];   // zero for s >= n
@@ -577,6 +589,7 @@ __device__ __forceinline__ void hop_backward_t(int n, const float* __restrict__ 
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
         const int s = g + NS * i;
+        if (LPR == 32 && s >= n) continue;   // warp-uniform
         const float4 r = LEAN ? *reinterpret_cast<const float4*>(lean_col + min(s, n - 1) * n)
                               : hop_row<PTAB, NEG, ALIGNED>(tile, n, s, l, s < n, nullptr);
         const float es = LEAN ? ea[s] : ((s < n) ? ea[s] : 0.0f);
@@ -603,6 +616,7 @@ __device__ __forceinline__ void hop_backward_t(int n, const float* __restrict__ 
     for (int i = 0; i < NR; ++i) {
       const int s = g + NS * i;
       rs[i] = 0.f;
+      if (LPR == 32 && s >= n) continue;   // warp-uniform
       if (LEAN) {   // c4 is zero for objects >= n, ea[s] for rows >= n
         const float4 r = *reinterpret_cast<const float4*>(lean_col + min(s, n - 1) * n);
         const float es = ea[s];
@@ -642,9 +656,9 @@ __device__ __forceinline__ void hop_backward(int n, const float* __restrict__ ti
       else hop_backward_t<LPR, NR, PTAB, true, false>(n, tile, ea, subject_role, cbuf, g_other, gslice, sc, cfac);   \
     }                                                                                                                \
   }
-  if (n <= 32) DFOL_HOP_BWD(8, 1)
-  else if (n <= 64) DFOL_HOP_BWD(16, 2)
-  else DFOL_HOP_BWD(32, 8)
+  if (n <= 32) DFOL_HOP_BWD(8, (32 + 4 * PROG_WARPS - 1) / (4 * PROG_WARPS))
+  else if (n <= 64) DFOL_HOP_BWD(16, 64 / (2 * PROG_WARPS))
+  else DFOL_HOP_BWD(32, MAXN / PROG_WARPS)
 #undef DFOL_HOP_BWD
 }
 

@@ -126,6 +126,27 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   }
 }
 
+// L1 regularisation of VQATrainer._compute_loss (trainer.py:257-259): loss += lambda * ||theta||_1 / numel.
+// g += coef * sign(p) (torch's subgradient: sign(0) = 0); loss_out[0] += loss_coef * sum |p|.
+__global__ void __launch_bounds__(256) l1_kernel(const float* __restrict__ p, float* __restrict__ g, long long n,
+                                                 float coef, float loss_coef, float* loss_out) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = p[i];
+    acc += fabsf(v);
+    g[i] += (v > 0.0f) ? coef : (v < 0.0f ? -coef : 0.0f);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss_out != nullptr) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    atomicAdd(loss_out, loss_coef * t);
+  }
+}
+
 // torch.nn.utils.clip_grad_norm_ (coef = clip / (norm + 1e-6), clamped to 1) followed by torch.optim.Adam
 // (L2 weight decay folded into the gradient, bias-corrected moments, eps added after the sqrt).
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -170,6 +191,16 @@ extern "C" int dfol_sumsq(const float* g, int64_t n, float* out, void* stream) {
   if (blocks > 148 * 8) blocks = 148 * 8;
   sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, n, out);
   return finish_launch("dfol_sumsq");
+}
+
+extern "C" int dfol_l1_regularize(const float* p, float* g, int64_t n, float coef, float loss_coef, float* loss_out,
+                                  void* stream) {
+  DFOL_REQUIRE(p && g, "dfol_l1_regularize: null pointer");
+  if (n == 0) return 0;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  l1_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, n, coef, loss_coef, loss_out);
+  return finish_launch("dfol_l1_regularize");
 }
 
 extern "C" int dfol_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq,

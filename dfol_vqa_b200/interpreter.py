@@ -443,8 +443,12 @@ class FusedTrainStep(object):
     """
 
     def __init__(self, interpreter, lr=1e-4, weight_decay=1e-10, clip_norm=0.65, betas=(0.9, 0.999), eps=1e-8,
-                 process_group=None):
+                 process_group=None, l1_lambda=0.0):
         self.interp = interpreter
+        # config key ``l1_lambda`` (trainer.py:257-259): loss += l1_lambda * ||theta||_1 / numel over the trainable
+        # parameters, scaled by 1 / batch with the rest of the loss (:434-435)
+        self.l1_lambda = float(l1_lambda)
+        self._last_total = 1
         self.engine = interpreter._engine
         self.lr, self.wd, self.clip = lr, weight_decay, clip_norm
         self.betas, self.eps = betas, eps
@@ -504,6 +508,7 @@ class FusedTrainStep(object):
         dropout = interp._dropout_for(True)
         total = global_question_num or sum(pb.batch_size() for pb in program_batch_list)
         scale = 1.0 / float(total)
+        self._last_total = total
         self.flat_grad.zero_()
         self.scalars.zero_()
         for k, pb in enumerate(program_batch_list):
@@ -571,6 +576,11 @@ class FusedTrainStep(object):
         st = capi.stream_ptr(dev)
         self.reduce_gradients()
         self.step_count += 1
+        if self.l1_lambda > 0.0:
+            # added ONCE, after the data-parallel sum; every rank reports 1 / world of the term in its loss share
+            coef = self.l1_lambda / (float(self.flat.numel()) * float(self._last_total))
+            call('dfol_l1_regularize', ptr(self.flat), ptr(self.flat_grad), self.flat.numel(), coef,
+                 coef / float(self.world), ptr(self.scalars), st)
         call('dfol_sumsq', ptr(self.flat_grad), self.flat_grad.numel(), ptr(self.scalars[1:]), st)
         call('dfol_adam_step', ptr(self.flat), ptr(self.flat_grad), ptr(self.m), ptr(self.v), self.flat.numel(),
              ptr(self.scalars[1:]), self.clip, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,

@@ -460,6 +460,9 @@ int dfol_answers(const float* lp, const int32_t* seg, int question_num, int mode
  * gqa_interpreter_experiments.py:261: torch.optim.Adam(lr, weight_decay) = L2 added to the gradient).
  * dfol_sumsq: out[0] += sum g^2.  dfol_adam_step: coef = min(1, clip / (sqrt(sumsq[0]) + 1e-6)) applied to g. */
 int dfol_sumsq(const float* g, int64_t n, float* out, void* stream);
+/* L1 regularisation of the loss (trainer.py:257-259, config key l1_lambda): g += coef * sign(p),
+ * loss_out[0] += loss_coef * sum |p| (loss_out may be NULL).  Callers pass coef = lambda / (numel * batch). */
+int dfol_l1_regularize(const float* p, float* g, int64_t n, float coef, float loss_coef, float* loss_out, void* stream);
 int dfol_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq, float clip_norm,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
 

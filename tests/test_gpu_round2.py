@@ -460,3 +460,33 @@ def test_pair_chain_fwd_is_bit_identical_to_the_unfused_kernels(terminal, n_max,
             assert torch.equal(ga, gb)
         else:
             assert h1a is None
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_l1_lambda_matches_trainer_semantics(mode):
+    """config key ``l1_lambda`` (reference trainer.py:257-259 and :434-435): loss += lambda * ||theta||_1 / numel, the sum
+    scaled by 1 / batch -- the gradient bucket gains lambda * sign(theta) / (numel * batch), the reported loss the term."""
+    from dfol_vqa_b200 import synth
+    from dfol_vqa_b200.ontology import synthetic_ontology
+    from dfol_vqa_b200.interpreter import FusedTrainStep
+    dims = dict(box=2048, feat=512, hidden=256, emb=300)
+    ont = synthetic_ontology(400, 60, 6, 5, seed=3, embedding_dim=300)
+    questions = synth.make_questions(ont, 8, 'verify_rel', 1, 3, seed=64)
+    counts = synth.object_counts(8, 24, True, seed=65)
+    feats, bidx = synth.make_object_features(counts, 2048, seed=66)
+    lam = 3000.0   # large: the term must stand clear of the run-to-run noise of the atomically reduced task gradients
+    out = {}
+    for l1 in (0.0, lam):
+        interp = helpers.build_interpreter(ont, dims, seed=5, gemm_mode=mode, emb_bias=-4.0)
+        pbs = helpers.to_cuda(_collate(questions, feats, bidx))
+        step = FusedTrainStep(interp, l1_lambda=l1)
+        theta = step.flat.clone()
+        loss = step.step(pbs)
+        torch.cuda.synchronize()
+        out[l1] = (theta, step.flat_grad.clone(), float(loss))
+    theta, g0, loss0 = out[0.0]
+    _, g1, loss1 = out[lam]
+    coef = lam / (theta.numel() * 8)
+    assert torch.allclose(g1 - g0, coef * torch.sign(theta), rtol=0, atol=1e-3 * coef + 1e-5 * float(g0.abs().max()))
+    want = coef * float(theta.abs().sum())
+    assert abs((loss1 - loss0) - want) <= 1e-4 * max(want, abs(loss0))
