@@ -184,6 +184,19 @@ class ClockSampler(object):
 
 
 def cpu_baseline(args, workload, seconds=12.0):
+    """The CPU oracle port on the host cores (bounded sample of the workload).  The fp32 CPU path can produce a
+    probability one ulp above 1 on an unlucky sample (binary_cross_entropy then refuses it, exactly as the reference's
+    own loss would, trainer.py:196): such a sample is re-drawn, up to three times."""
+    last = None
+    for attempt in range(3):
+        try:
+            return _cpu_baseline_once(args, workload, seconds, question_seed=5 + 101 * attempt)
+        except RuntimeError as exc:
+            last = exc
+    raise last
+
+
+def _cpu_baseline_once(args, workload, seconds, question_seed):
     """The CPU oracle port (oracle/dfol_oracle.py) on the host cores: full train (or infer) step -- collation included,
     as in the reference's step -- on a bounded sample of the same workload."""
     import torch
@@ -208,7 +221,7 @@ def cpu_baseline(args, workload, seconds=12.0):
         for k, v in nets[key].state_dict().items():
             params[prefix + '.' + k] = v.clone().requires_grad_(args.mode == 'train')
     sample_b = args.cpu_sample
-    qs = make_workload_questions(ont, wl, sample_b, 5, index=0)
+    qs = make_workload_questions(ont, wl, sample_b, question_seed, index=0)
     feats, bidx = synth.make_object_features([wl['n']] * sample_b, DIMS['box'], seed=6)
 
     def one_step():
