@@ -653,9 +653,17 @@ class Bench(object):
 
         # pin_memory: the loader's pin thread (not the training thread) unpickles the workers' results and pins the packed
         # tables / targets through ProgramBatch.pin_memory()
+        # The workers are forked: they inherit every live CUDA tensor of this process, and freeing one whose streams were
+        # recorded (HostStepPipeline) calls into a CUDA context the child does not have -- a cyclic-GC run in a worker
+        # that finds inherited garbage kills it.  Collect the garbage here and freeze what is left out of the
+        # children's collector.
+        import gc
+        gc.collect()
+        gc.freeze()
         loader = DataLoader(ds, batch_size=None, shuffle=False, num_workers=workers, pin_memory=True,
                             prefetch_factor=4 if workers > 0 else None, persistent_workers=False)
         it = iter(loader)
+        gc.unfreeze()
         pipeline.run([attach(next(it)) for _ in range(warmup)])
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

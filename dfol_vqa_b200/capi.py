@@ -75,6 +75,9 @@ _SIGNATURES = {
                                          c_int, P, P]),
     'dfol_rel_slots_fwd_tc': (c_int, [P, c_int64, c_int64, c_int, c_int, P, c_int64, P, P, P, c_int, P, P, P, P, P, c_int,
                                       c_int, c_float, P, P, P, P]),
+    'dfol_mod_tape_record_size': (c_int, []),
+    'dfol_mod_tape_fwd': (c_int, [P, c_int, c_int, P, P, P, P, P, P, P, P, P, c_int, c_int, P, P, P, P, P]),
+    'dfol_mod_tape_bwd': (c_int, [P, c_int, c_int, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, P]),
     'dfol_lstm_cell_fwd': (c_int, [P, c_int64, P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int, P]),
     'dfol_lstm_cell_bwd': (c_int, [P, P, P, c_int, P, P, P, P, c_int64, P, P, P, P, P, P, c_int, P]),
     'dfol_mod_out_fwd': (c_int, [P, P, P, P, P, c_int, c_int, P, P, c_int, P]),

@@ -231,8 +231,10 @@ def test_fast_interpreter_with_modulations_matches_exact(terminal, n_max, ragged
 
 @pytest.mark.parametrize('terminal,n_max', [('verify_rel', 20), ('query_attr', 12), ('choose_rel', 16),
                                             ('two_same', 10), ('compare', 14), ('and', 18)])
-def test_native_modulator_matches_torch_statement(terminal, n_max):
-    """modulator_cuda.NativeAttentionTransfer (hand-written LSTM-cell / output-layer kernels, hand-derived backward)
+@pytest.mark.parametrize('tape', [True, False])
+def test_native_modulator_matches_torch_statement(terminal, n_max, tape, monkeypatch):
+    """modulator_cuda.NativeAttentionTransfer (tape: the two persistent kernels of csrc/modulator_tape.cu; not tape: one
+    launch per step; hand-written LSTM-cell / output-layer kernels, hand-derived backward)
     against modulator.AttentionTransfer (torch ops + autograd; held to the recorded reference runs by the CPU tests) at
     the reference's real dimensions (318-wide features, state 50): modulation rows and all 10 parameter gradients."""
     from test_gpu_tc_kernels import _programs_world
@@ -240,6 +242,8 @@ def test_native_modulator_matches_torch_statement(terminal, n_max):
     from dfol_vqa_b200.modulator import AttentionTransfer
     from dfol_vqa_b200.modulator_cuda import NativeAttentionTransfer
     from dfol_vqa_b200.networks import build_attention_networks
+    from dfol_vqa_b200 import modulator_cuda
+    monkeypatch.setattr(modulator_cuda, '_USE_TAPE', tape)
     ont, dims, pbs = _programs_world(terminal, 24, n_max, True, seed=77)
     torch.manual_seed(11)
     nets = build_attention_networks(dims['emb'], 50)
