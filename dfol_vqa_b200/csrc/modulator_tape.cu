@@ -8,18 +8,17 @@
 // issue ~100 launches plus the allocations between them: ~1.2 ms of a 3.3 ms calibrator-training step.
 //
 // Here the host compiles the SAME sequence of steps into an array of records once per program batch (program-only
-// data: pool offsets, row counts, owner / mask tables) and ONE cooperative kernel walks it: both W_hh matrices and the
-// output layer stay in shared memory for the whole tape, a record's rows are spread over the grid in 8-row chunks and
-// a grid-wide barrier separates dependent records.  The backward kernel walks the tape in reverse (BPTT) with the
-// hand-derived cell / output-layer backward of modulator_kernels.cu; the parameter gradients stay GEMM-shaped
-// reductions over d pre of all cell rows, done by the caller afterwards.
+// data: pool offsets, row counts, owner / mask tables) and ONE kernel per pass walks it with both W_hh matrices and the
+// output layer resident in shared memory.  The chain is sequential per QUESTION only -- no step mixes the rows of two
+// questions -- so every block owns a contiguous range of questions and executes the whole tape for the rows of its
+// own questions: a step's rows are either one per question or the (question-sorted) predicate rows of an option list,
+// whose sub-range a block finds by binary search in the step's `part` map.  Dependent steps are separated by
+// __syncthreads() only: no grid barrier, no cooperative launch.  The backward kernel walks the tape in reverse (BPTT)
+// with the hand-derived cell / output-layer backward of modulator_kernels.cu; the parameter gradients stay
+// GEMM-shaped reductions over d pre of all cell rows, done by the caller afterwards.
 //
 // States live in ONE fp32 pool (offsets in floats, -1 = the all-zero state); the gradient pool has the same layout.
-#include <cooperative_groups.h>
-
 #include "dfol_common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace dfol {
 
@@ -43,7 +42,25 @@ struct TapeRec {
   int64_t out_h, out_c;    // result
   const int64_t* owner;    // CELL: row -> source row (expand); SQUEEZE: row -> destination row
   const float* mask;       // CELL / GATE: 0/1 per row
+  const int64_t* part;     // row -> question (non-decreasing), NULL = row i belongs to question i
 };
+
+// rows [r0, r1) of a step that belong to the questions [q0, q1) of this block
+__device__ __forceinline__ int tape_lower_bound(const int64_t* part, int rows, int q) {
+  int lo = 0, hi = rows;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (part[mid] < q) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ void tape_row_range(const TapeRec& R, int q0, int q1, int* range) {
+  // (called by every thread between two barriers; thread 0 publishes, the caller's next barrier makes it visible)
+  if (threadIdx.x == 0) {
+    if (R.part == nullptr) { range[0] = min(q0, R.rows); range[1] = min(q1, R.rows); }
+    else { range[0] = tape_lower_bound(R.part, R.rows, q0); range[1] = tape_lower_bound(R.part, R.rows, q1); }
+  }
+}
 
 struct TapeNets {
   const float* w_hh[2];   // [4S][S]
@@ -58,12 +75,12 @@ __device__ __forceinline__ const float* at(const float* pool, int64_t off) { ret
 __device__ __forceinline__ float* at(float* pool, int64_t off) { return off >= 0 ? pool + off : nullptr; }
 
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(TAPE_THREADS, 1) mod_tape_fwd_kernel(
+__global__ void __launch_bounds__(TAPE_THREADS, 2) mod_tape_fwd_kernel(
     const TapeRec* __restrict__ recs, int n_rec, float* __restrict__ pool, const float* __restrict__ xproj_f,
     const float* __restrict__ xproj_b, TapeNets nets, float* __restrict__ saved_f, float* __restrict__ saved_b,
-    float* __restrict__ mods, float* __restrict__ cat) {
-  cg::grid_group grid = cg::this_grid();
+    float* __restrict__ mods, float* __restrict__ cat, int questions) {
   extern __shared__ float smem[];
+  __shared__ int range[2];
   const int S = nets.S, n_out = nets.n_out;
   float* wt[2] = {smem, smem + 4 * S * S};          // W_hh transposed: wt[k * 4S + g * S + j]
   float* wo = smem + 8 * S * S;                     // [n_out][2S]
@@ -81,11 +98,14 @@ __global__ void __launch_bounds__(TAPE_THREADS, 1) mod_tape_fwd_kernel(
   for (int idx = threadIdx.x; idx < n_out; idx += TAPE_THREADS) bo[idx] = nets.b_out[idx];
   __syncthreads();
   const int j = threadIdx.x % TAPE_MAXS, lr = threadIdx.x / TAPE_MAXS;
-  const long long gtid = (long long)blockIdx.x * TAPE_THREADS + threadIdx.x;
-  const long long gthreads = (long long)gridDim.x * TAPE_THREADS;
+  const int q0 = (int)(((long long)questions * blockIdx.x) / gridDim.x);
+  const int q1 = (int)(((long long)questions * (blockIdx.x + 1)) / gridDim.x);
 
   for (int r = 0; r < n_rec; ++r) {
     const TapeRec R = recs[r];
+    tape_row_range(R, q0, q1, range);
+    __syncthreads();  // the previous step's results and this step's row range are visible to the whole block
+    const int r0 = range[0], r1 = range[1];
     if (R.kind == TAPE_CELL) {
       const float* xproj = (R.net == 0 ? xproj_f : xproj_b) + (long long)R.base * 4 * S;
       float* saved = (R.net == 0 ? saved_f : saved_b) + (long long)R.base * 7 * S;
@@ -99,9 +119,9 @@ __global__ void __launch_bounds__(TAPE_THREADS, 1) mod_tape_fwd_kernel(
       float* c_out = at(pool, R.out_c);
       const float* w = wt[R.net];
       const float* b = bh[R.net];
-      for (int chunk = blockIdx.x; chunk * TAPE_ROWS < R.rows; chunk += gridDim.x) {
-        const int row = chunk * TAPE_ROWS + lr;
-        const bool act = row < R.rows && j < S;
+      for (int c0 = r0; c0 < r1; c0 += TAPE_ROWS) {
+        const int row = c0 + lr;
+        const bool act = row < r1 && j < S;
         long long src = 0;
         float cin = 0.f;
         __syncthreads();  // hin of the previous chunk has been consumed
@@ -143,7 +163,7 @@ __global__ void __launch_bounds__(TAPE_THREADS, 1) mod_tape_fwd_kernel(
       const float* bhs = at(pool, R.add_h);
       float* m = mods + (long long)R.base * n_out;
       float* c = cat + (long long)R.base * 2 * S;
-      for (long long t = gtid; t < (long long)R.rows * n_out; t += gthreads) {
+      for (long long t = (long long)r0 * n_out + threadIdx.x; t < (long long)r1 * n_out; t += TAPE_THREADS) {
         const long long row = t / n_out;
         const int o = (int)(t - row * n_out);
         const float* w = wo + o * 2 * S;
@@ -163,7 +183,7 @@ __global__ void __launch_bounds__(TAPE_THREADS, 1) mod_tape_fwd_kernel(
       const float* sc = at(pool, R.in_c);
       float* oh = at(pool, R.out_h);
       float* oc = at(pool, R.out_c);
-      for (long long t = gtid; t < (long long)R.rows * S; t += gthreads) {
+      for (long long t = (long long)r0 * S + threadIdx.x; t < (long long)r1 * S; t += TAPE_THREADS) {
         const long long row = t / S;
         const int k = (int)(t - row * S);
         const long long dst = R.owner[row];
@@ -177,25 +197,26 @@ __global__ void __launch_bounds__(TAPE_THREADS, 1) mod_tape_fwd_kernel(
       const float* oc = at(pool, R.add_c);
       float* dh = at(pool, R.out_h);
       float* dc = at(pool, R.out_c);
-      for (long long t = gtid; t < (long long)R.rows * S; t += gthreads) {
+      for (long long t = (long long)r0 * S + threadIdx.x; t < (long long)r1 * S; t += TAPE_THREADS) {
         const bool keep = R.mask[t / S] > 0.f;
         dh[t] = keep ? nh[t] : (oh ? oh[t] : 0.f);
         dc[t] = keep ? nc[t] : (oc ? oc[t] : 0.f);
       }
     }
-    grid.sync();
+    __syncthreads();  // range[] may be rewritten
   }
 }
 
 // ------------------------------------------------------------------------------------------------ backward
 // gpool: gradients of every pool state (same offsets, zero-filled before the launch).  dpre_f / dpre_b (R x 4S) and dzo
 // (R x n_out) are zero-filled by the caller; steps that are not live leave their rows zero.
-__global__ void __launch_bounds__(TAPE_THREADS, 1) mod_tape_bwd_kernel(
+__global__ void __launch_bounds__(TAPE_THREADS, 2) mod_tape_bwd_kernel(
     const TapeRec* __restrict__ recs, int n_rec, float* __restrict__ gpool, TapeNets nets,
     const float* __restrict__ saved_f, const float* __restrict__ saved_b, const float* __restrict__ mods,
-    const float* __restrict__ d_mods, float* __restrict__ dpre_f, float* __restrict__ dpre_b, float* __restrict__ dzo) {
-  cg::grid_group grid = cg::this_grid();
+    const float* __restrict__ d_mods, float* __restrict__ dpre_f, float* __restrict__ dpre_b, float* __restrict__ dzo,
+    int questions) {
   extern __shared__ float smem[];
+  __shared__ int range[2];
   const int S = nets.S, n_out = nets.n_out;
   float* w[2] = {smem, smem + 4 * S * S};   // W_hh row-major [4S][S]
   float* wo = smem + 8 * S * S;             // [n_out][2S]
@@ -205,19 +226,22 @@ __global__ void __launch_bounds__(TAPE_THREADS, 1) mod_tape_bwd_kernel(
   for (int idx = threadIdx.x; idx < n_out * 2 * S; idx += TAPE_THREADS) wo[idx] = nets.w_out[idx];
   __syncthreads();
   const int j = threadIdx.x % TAPE_MAXS, lr = threadIdx.x / TAPE_MAXS;
-  const long long gtid = (long long)blockIdx.x * TAPE_THREADS + threadIdx.x;
-  const long long gthreads = (long long)gridDim.x * TAPE_THREADS;
+  const int q0 = (int)(((long long)questions * blockIdx.x) / gridDim.x);
+  const int q1 = (int)(((long long)questions * (blockIdx.x + 1)) / gridDim.x);
 
   for (int r = n_rec - 1; r >= 0; --r) {
     const TapeRec R = recs[r];
-    if (!R.live) continue;  // (grid-uniform: nobody waits at a barrier for a skipped step)
+    if (!R.live) continue;  // (block-uniform)
+    tape_row_range(R, q0, q1, range);
+    __syncthreads();
+    const int r0 = range[0], r1 = range[1];
     if (R.kind == TAPE_OUT) {
       const float* m = mods + (long long)R.base * n_out;
       const float* dm = d_mods + (long long)R.base * n_out;
       float* dz = dzo + (long long)R.base * n_out;
       float* d_fh = at(gpool, R.in_h);
       float* d_bh = at(gpool, R.add_h);
-      for (long long t = gtid; t < (long long)R.rows * 2 * S; t += gthreads) {
+      for (long long t = (long long)r0 * 2 * S + threadIdx.x; t < (long long)r1 * 2 * S; t += TAPE_THREADS) {
         const long long row = t / (2 * S);
         const int k = (int)(t - row * 2 * S);
         float acc = 0.f;
@@ -242,9 +266,9 @@ __global__ void __launch_bounds__(TAPE_THREADS, 1) mod_tape_bwd_kernel(
       float* d_fb_h = at(gpool, R.fb_h);
       float* d_fb_c = at(gpool, R.fb_c);
       const float* wn = w[R.net];
-      for (int chunk = blockIdx.x; chunk * TAPE_ROWS < R.rows; chunk += gridDim.x) {
-        const int row = chunk * TAPE_ROWS + lr;
-        const bool act = row < R.rows && j < S;
+      for (int c0 = r0; c0 < r1; c0 += TAPE_ROWS) {
+        const int row = c0 + lr;
+        const bool act = row < r1 && j < S;
         float dcin = 0.f;
         __syncthreads();
         if (act) {
@@ -288,7 +312,7 @@ __global__ void __launch_bounds__(TAPE_THREADS, 1) mod_tape_bwd_kernel(
       float* sc = at(gpool, R.in_c);
       const float* oh = at(gpool, R.out_h);
       const float* oc = at(gpool, R.out_c);
-      for (long long t = gtid; t < (long long)R.rows * S; t += gthreads) {
+      for (long long t = (long long)r0 * S + threadIdx.x; t < (long long)r1 * S; t += TAPE_THREADS) {
         const long long row = t / S;
         const int k = (int)(t - row * S);
         const long long src = R.owner[row];
@@ -302,26 +326,22 @@ __global__ void __launch_bounds__(TAPE_THREADS, 1) mod_tape_bwd_kernel(
       float* oc = at(gpool, R.add_c);
       const float* dh = at(gpool, R.out_h);
       const float* dc = at(gpool, R.out_c);
-      for (long long t = gtid; t < (long long)R.rows * S; t += gthreads) {
+      for (long long t = (long long)r0 * S + threadIdx.x; t < (long long)r1 * S; t += TAPE_THREADS) {
         const bool keep = R.mask[t / S] > 0.f;
         if (keep) { nh[t] += dh[t]; nc[t] += dc[t]; }
         else if (oh) { oh[t] += dh[t]; oc[t] += dc[t]; }
       }
     }
-    grid.sync();
+    __syncthreads();
   }
 }
 
-static int tape_grid(const void* kernel, size_t smem, int rows_max) {
-  int dev = 0, sms = 0, per_sm = 0;
+static int tape_grid(int questions) {
+  int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TAPE_THREADS, smem);
-  if (per_sm < 1) return 0;
-  // no more blocks than the widest step has chunks: the grid barrier gets cheaper with fewer participants
-  int want = (rows_max + TAPE_ROWS - 1) / TAPE_ROWS;
-  if (want < 1) want = 1;
-  return want < sms ? want : sms;
+  const int want = 2 * sms;  // two blocks per SM (80 KB of weights each)
+  return questions < want ? questions : want;
 }
 
 }  // namespace dfol
@@ -330,7 +350,7 @@ using namespace dfol;
 
 extern "C" int dfol_mod_tape_record_size(void) { return (int)sizeof(TapeRec); }
 
-extern "C" int dfol_mod_tape_fwd(const void* records, int n_rec, int rows_max, float* pool, const float* xproj_f,
+extern "C" int dfol_mod_tape_fwd(const void* records, int n_rec, int questions, float* pool, const float* xproj_f,
                                  const float* xproj_b, const float* w_hh_f, const float* b_hh_f, const float* w_hh_b,
                                  const float* b_hh_b, const float* w_out, const float* b_out, int S, int n_out,
                                  float* saved_f, float* saved_b, float* mods, float* cat, void* stream) {
@@ -343,21 +363,18 @@ extern "C" int dfol_mod_tape_fwd(const void* records, int n_rec, int rows_max, f
   const size_t smem = (size_t)(8 * S * S + n_out * 2 * S + n_out + 8 * S) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(mod_tape_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return (int)e; }
-  const int blocks = tape_grid((const void*)mod_tape_fwd_kernel, smem, rows_max);
-  DFOL_REQUIRE(blocks >= 1, "%s: the kernel does not fit on an SM", who);
-  const TapeRec* recs = reinterpret_cast<const TapeRec*>(records);
+  DFOL_REQUIRE(questions >= 1, "%s: no questions", who);
+  const int blocks = tape_grid(questions);
   TapeNets nets;
   nets.w_hh[0] = w_hh_f; nets.w_hh[1] = w_hh_b; nets.b_hh[0] = b_hh_f; nets.b_hh[1] = b_hh_b;
   nets.w_out = w_out; nets.b_out = b_out; nets.S = S; nets.n_out = n_out;
-  void* args[] = {(void*)&recs, (void*)&n_rec, (void*)&pool, (void*)&xproj_f, (void*)&xproj_b, (void*)&nets,
-                  (void*)&saved_f, (void*)&saved_b, (void*)&mods, (void*)&cat};
-  e = cudaLaunchCooperativeKernel((const void*)mod_tape_fwd_kernel, dim3(blocks), dim3(TAPE_THREADS), args, smem,
-                                  (cudaStream_t)stream);
-  if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return (int)e; }
+  mod_tape_fwd_kernel<<<blocks, TAPE_THREADS, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const TapeRec*>(records), n_rec, pool, xproj_f, xproj_b, nets, saved_f, saved_b, mods, cat,
+      questions);
   return finish_launch(who);
 }
 
-extern "C" int dfol_mod_tape_bwd(const void* records, int n_rec, int rows_max, float* grad_pool, const float* w_hh_f,
+extern "C" int dfol_mod_tape_bwd(const void* records, int n_rec, int questions, float* grad_pool, const float* w_hh_f,
                                  const float* w_hh_b, const float* w_out, int S, int n_out, const float* saved_f,
                                  const float* saved_b, const float* mods, const float* d_mods, float* dpre_f,
                                  float* dpre_b, float* dzo, void* stream) {
@@ -370,16 +387,13 @@ extern "C" int dfol_mod_tape_bwd(const void* records, int n_rec, int rows_max, f
   const size_t smem = (size_t)(8 * S * S + n_out * 2 * S) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(mod_tape_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return (int)e; }
-  const int blocks = tape_grid((const void*)mod_tape_bwd_kernel, smem, rows_max);
-  DFOL_REQUIRE(blocks >= 1, "%s: the kernel does not fit on an SM", who);
-  const TapeRec* recs = reinterpret_cast<const TapeRec*>(records);
+  DFOL_REQUIRE(questions >= 1, "%s: no questions", who);
+  const int blocks = tape_grid(questions);
   TapeNets nets;
   nets.w_hh[0] = w_hh_f; nets.w_hh[1] = w_hh_b; nets.b_hh[0] = nullptr; nets.b_hh[1] = nullptr;
   nets.w_out = w_out; nets.b_out = nullptr; nets.S = S; nets.n_out = n_out;
-  void* args[] = {(void*)&recs, (void*)&n_rec, (void*)&grad_pool, (void*)&nets, (void*)&saved_f, (void*)&saved_b,
-                  (void*)&mods, (void*)&d_mods, (void*)&dpre_f, (void*)&dpre_b, (void*)&dzo};
-  e = cudaLaunchCooperativeKernel((const void*)mod_tape_bwd_kernel, dim3(blocks), dim3(TAPE_THREADS), args, smem,
-                                  (cudaStream_t)stream);
-  if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return (int)e; }
+  mod_tape_bwd_kernel<<<blocks, TAPE_THREADS, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const TapeRec*>(records), n_rec, grad_pool, nets, saved_f, saved_b, mods, d_mods, dpre_f, dpre_b,
+      dzo, questions);
   return finish_launch(who);
 }

@@ -32,7 +32,8 @@ _USE_TAPE = os.environ.get('DFOL_MOD_TAPE', '1') != '0'
 _REC_DTYPE = np.dtype([('kind', np.int32), ('net', np.int32), ('rows', np.int32), ('base', np.int32),
                        ('live', np.int32), ('pad', np.int32), ('in_h', np.int64), ('in_c', np.int64),
                        ('add_h', np.int64), ('add_c', np.int64), ('fb_h', np.int64), ('fb_c', np.int64),
-                       ('out_h', np.int64), ('out_c', np.int64), ('owner', np.uint64), ('mask', np.uint64)])
+                       ('out_h', np.int64), ('out_c', np.int64), ('owner', np.uint64), ('mask', np.uint64),
+                       ('part', np.uint64)])
 _CELL, _OUT, _SQUEEZE, _GATE = 0, 1, 2, 3
 
 
@@ -313,12 +314,23 @@ class NativeAttentionTransfer(object):
             t.alloc(rows)
             return t
 
-        def rec(kind, net=0, rows=0, base=0, a=None, b=None, fb=None, out=None, owner=None, mask=None):
+        def part_of(slot_key, rows):
+            """row -> question map of a step of slot ``slot_key``: the (question-sorted) owner list of the slot's option
+            predicates, or None when the step has one row per question."""
+            i, k = slot_key
+            own = plan['owners'].get((i, 'filter' if k.startswith('filter') else k))
+            if own is None or rows != own.shape[0]:
+                assert rows == B, (slot_key, rows, B)
+                return None
+            return own
+
+        def rec(kind, net=0, rows=0, base=0, a=None, b=None, fb=None, out=None, owner=None, mask=None, part=None):
             none = TS()
             a, b, fb, out = a or none, b or none, fb or none, out or none
             recs.append({'kind': kind, 'net': net, 'rows': rows, 'base': base, 'a': a, 'b': b, 'fb': fb, 'out': out,
                          'owner': 0 if owner is None else owner.data_ptr(),
-                         'mask': 0 if mask is None else mask.data_ptr()})
+                         'mask': 0 if mask is None else mask.data_ptr(),
+                         'part': 0 if part is None else part.data_ptr()})
 
         class Ops(object):
             @staticmethod
@@ -335,18 +347,20 @@ class NativeAttentionTransfer(object):
                     if fb.off is None:
                         fb.alloc(rows)   # the pool is zero-filled: a materialised zero state
                 rec(_CELL, 0 if net == 'f' else 1, rows, base, a=state,
-                    b=add if (add is not None and add.off is not None) else None, fb=fb, out=out, owner=owner, mask=mask)
+                    b=add if (add is not None and add.off is not None) else None, fb=fb, out=out, owner=owner, mask=mask,
+                    part=part_of(slot_key, rows))
                 return out
 
             @staticmethod
             def out_layer(slot_key, fstate, bstate):
                 base, rows = plan['base'][slot_key]
-                rec(_OUT, 0, rows, base, a=fstate, b=bstate)
+                rec(_OUT, 0, rows, base, a=fstate, b=bstate, part=part_of(slot_key, rows))
 
             @staticmethod
             def squeeze(state, owner):
                 out = new_state(B)
-                rec(_SQUEEZE, 0, state.rows, 0, a=state, out=out, owner=owner)
+                assert owner.shape[0] == state.rows
+                rec(_SQUEEZE, 0, state.rows, 0, a=state, out=out, owner=owner, part=owner)
                 return out
 
             @staticmethod
@@ -354,6 +368,7 @@ class NativeAttentionTransfer(object):
                 if old.off is None:
                     old.alloc(new.rows)
                 out = new_state(new.rows)
+                assert new.rows == B
                 rec(_GATE, 0, new.rows, 0, a=new, b=old, out=out, mask=mask)
                 return out
 
@@ -376,11 +391,10 @@ class NativeAttentionTransfer(object):
         arr = np.zeros(len(recs), dtype=_REC_DTYPE)
         for i, r in enumerate(recs):
             arr[i] = (r['kind'], r['net'], r['rows'], r['base'], r['live'], 0, r['a'].h(), r['a'].c(), r['b'].h(),
-                      r['b'].c(), r['fb'].h(), r['fb'].c(), r['out'].h(), r['out'].c(), r['owner'], r['mask'])
+                      r['b'].c(), r['fb'].h(), r['fb'].c(), r['out'].h(), r['out'].c(), r['owner'], r['mask'], r['part'])
         assert capi.lib().dfol_mod_tape_record_size() == _REC_DTYPE.itemsize
         dev_recs = torch.from_numpy(arr.view(np.uint8)).to(dev)
-        hit = {'recs': dev_recs, 'n': len(recs), 'rows_max': int(max([r['rows'] for r in recs] + [1])),
-               'pool': max(cursor[0], 4), 'host': arr}
+        hit = {'recs': dev_recs, 'n': len(recs), 'questions': B, 'pool': max(cursor[0], 4), 'host': arr}
         cp.mod_cache[key] = hit
         return hit
 
@@ -400,7 +414,7 @@ class NativeAttentionTransfer(object):
         pool, saved_f, saved_b, cat = _carve(dev, [tp['pool'], R * 7 * S, R * 7 * S, R * 2 * S])
         saved_f, saved_b, cat = saved_f.view(R, 7 * S), saved_b.view(R, 7 * S), cat.view(R, 2 * S)
         mods = torch.empty(R, n_out, device=dev, dtype=torch.float32)
-        call('dfol_mod_tape_fwd', ptr(tp['recs']), tp['n'], tp['rows_max'], ptr(pool), ptr(x_f), ptr(x_b),
+        call('dfol_mod_tape_fwd', ptr(tp['recs']), tp['n'], tp['questions'], ptr(pool), ptr(x_f), ptr(x_b),
              ptr(self.fwd.weight_hh), ptr(self.fwd.bias_hh), ptr(self.bwd.weight_hh), ptr(self.bwd.bias_hh),
              ptr(self.lin.weight), ptr(self.lin.bias), S, n_out, ptr(saved_f), ptr(saved_b), ptr(mods), ptr(cat), st)
         ctx = {'tape_plan': tp, 'saved': {'f': saved_f, 'b': saved_b}, 'cat': cat, 'mods': mods, 'plan': plan, 'R': R,
@@ -423,7 +437,7 @@ class NativeAttentionTransfer(object):
             gpool, dpf, dpb, dzo = _carve(dev, [tp['pool'], R * 4 * S, R * 4 * S, R * n_out])
             dpre = {'f': dpf.view(R, 4 * S), 'b': dpb.view(R, 4 * S)}
             dzo = dzo.view(R, n_out)
-            call('dfol_mod_tape_bwd', ptr(tp['recs']), tp['n'], tp['rows_max'], ptr(gpool), ptr(self.fwd.weight_hh),
+            call('dfol_mod_tape_bwd', ptr(tp['recs']), tp['n'], tp['questions'], ptr(gpool), ptr(self.fwd.weight_hh),
                  ptr(self.bwd.weight_hh), ptr(self.lin.weight), S, n_out, ptr(saved['f']), ptr(saved['b']), ptr(mods),
                  ptr(d_mods), ptr(dpre['f']), ptr(dpre['b']), ptr(dzo), st)
             return self._parameter_gradients(dpre, dzo, saved, cat, F_all, R, grads, st)

@@ -342,20 +342,21 @@ int dfol_mod_out_fwd(const float* fh, const float* bh, const int64_t* owner, con
 int dfol_mod_out_bwd(const float* d_mods, const float* mods, const int64_t* owner, const float* w_out, int S, int n_out,
                      float* dzo, float* d_fh, float* d_bh, int rows, void* stream);
 
-/* The same passes as TWO persistent cooperative kernels (csrc/modulator_tape.cu): the caller compiles the sequence of
- * steps of a program batch into `records` (device array of n_rec records of dfol_mod_tape_record_size() bytes:
+/* The same passes as TWO persistent kernels (csrc/modulator_tape.cu): the caller compiles the sequence of steps of a
+ * program batch into `records` (device array of n_rec records of dfol_mod_tape_record_size() bytes:
  *   { int32 kind (0 cell, 1 output layer, 2 squeeze, 3 gate), net, rows, base, live, pad;
  *     int64 in_h, in_c, add_h, add_c, fb_h, fb_c, out_h, out_c  -- offsets (floats) into the state pool, -1 = zero state;
- *     const int64* owner; const float* mask }),
- * both W_hh and the output layer stay in shared memory for the whole tape, a grid barrier separates dependent steps.
+ *     const int64* owner; const float* mask; const int64* part (row -> question, non-decreasing; NULL = identity) }),
+ * both W_hh and the output layer stay in shared memory for the whole tape; the chain is sequential per question only, so
+ * every block executes the tape for the rows of its own questions and dependent steps need a block barrier only.
  * pool / grad_pool: zero-filled by the caller; saved_* (R x 7S), cat (R x 2S), dpre_* (R x 4S), dzo (R x n_out) as in the
- * per-step kernels above (zero-filled: steps that do not run leave their rows untouched).  rows_max = widest step. */
+ * per-step kernels above (zero-filled: steps that do not run leave their rows untouched). */
 int dfol_mod_tape_record_size(void);
-int dfol_mod_tape_fwd(const void* records, int n_rec, int rows_max, float* pool, const float* xproj_f,
+int dfol_mod_tape_fwd(const void* records, int n_rec, int questions, float* pool, const float* xproj_f,
                       const float* xproj_b, const float* w_hh_f, const float* b_hh_f, const float* w_hh_b,
                       const float* b_hh_b, const float* w_out, const float* b_out, int S, int n_out, float* saved_f,
                       float* saved_b, float* mods, float* cat, void* stream);
-int dfol_mod_tape_bwd(const void* records, int n_rec, int rows_max, float* grad_pool, const float* w_hh_f,
+int dfol_mod_tape_bwd(const void* records, int n_rec, int questions, float* grad_pool, const float* w_hh_f,
                       const float* w_hh_b, const float* w_out, int S, int n_out, const float* saved_f,
                       const float* saved_b, const float* mods, const float* d_mods, float* dpre_f, float* dpre_b,
                       float* dzo, void* stream);
