@@ -18,7 +18,7 @@ _lib = None
 
 class K(object):
     """Constants of include/dfol_b200.h."""
-    ABI_VERSION = 5
+    ABI_VERSION = 6
     ACT_NONE, ACT_ELU, ACT_SIGMOID, ACT_LOGSIGMOID = 0, 1, 2, 3
     MUL_NONE, MUL_SIGMOID_GRAD, MUL_ELU_GRAD = 0, 1, 2
     INSTR_WORDS = 12
@@ -70,6 +70,8 @@ _SIGNATURES = {
                                             P]),
     'dfol_pair_layer_dgrad_cluster': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P,
                                               c_int64, c_int, c_float, P]),
+    'dfol_pair_layer_dgrad_wgrad_cluster': (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P,
+                                                    c_int64, c_int, c_float, P, c_int64, c_int, P]),
     'dfol_cast_jobs': (c_int, [P, c_int, c_int64, P]),
     'dfol_pair_hidden_fwd_mma': (c_int, [P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int, P, P, P, P, c_int,
                                          c_int, P, P]),

@@ -13,6 +13,13 @@
 //   warps 2..9        : epilogue: tcgen05.ld, bias + activation or activation-derivative multiplier (operand read from
 //                       the 128B-swizzled shared tile, conflict free), bf16 result written to a swizzled shared tile
 //                       and stored with cp.async.bulk.tensor (full 128-byte lines) -- no per-thread global access.
+// Fused weight gradient (WG, dgrad only): the dgrad already holds both operands of dW = dZ^T . H of its layer in shared
+// memory -- every 128 x 64 block of dZ passes through the A ring and this CTA's columns of the saved activation H sit
+// in the epilogue operand tile.  Per ring stage the MMA warp issues, after the four K-major dgrad MMAs, eight MN-major
+// MMAs (reduction over the tile's 128 rows) dWt[this CTA's H columns, the stage's 64 dZ columns] += H^T . dZ into a
+// second TMEM accumulator that lives for the whole kernel (K columns next to a single-buffered dgrad accumulator, which
+// the epilogue copies to registers and releases at once); one red.global.add pass per CTA at the end.  The separate
+// wgrad launch, which re-read dZ and H from HBM, disappears.
 // Every mbarrier wait is bounded (trap instead of hanging the GPU).
 #include <cstdlib>
 #include "tc_common.cuh"
@@ -27,6 +34,7 @@ constexpr int CL_MAX_KB = 5;
 constexpr int CL_ABOX = 2;        // row boxes per A block, dealt round-robin to the CTAs of the cluster
 constexpr int CL_EC = 3;          // in-place operand/result tiles of the dgrad (operand prefetched two tiles ahead)
 constexpr int CL_MAX_CH = 6;      // 16-column chunks per epilogue warp (192 / 2 / 16)
+constexpr int CL_WG_CH = 4;       // the same with the fused weight gradient (BNh = 128: 64 columns held in registers)
 
 struct ClParams {
   const float* bias;
@@ -38,6 +46,12 @@ struct ClParams {
   int n_store;          // stored width of C (64-column boxes entirely beyond it are skipped)
   float keep;           // < 1: the multiplier operand holds post-dropout activations (0 / h / keep)
   int prefetch;         // tiles of L2 prefetch distance (0 = off)
+  float* dW;            // WG: C_w[K, N] += A^T . E (fp32, red.global.add), row stride lddw
+  long long lddw;
+  int K_real;           // WG: rows of dW (columns of A that carry a weight row)
+  int ec;               // in-place operand/result tiles of the dgrad in use (2..CL_EC)
+  int mc;               // 1: every A block is fetched once per cluster (multicast); 0: every CTA loads its own copy
+  int debug;            // DFOL_CL_DEBUG ablation bits (timing experiments only; results are wrong when set)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -86,6 +100,18 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
       : "memory");
 }
 
+// MN-major operand, 128-byte swizzle: rows of 128 B are the reduction index (groups of 8 rows 1024 B apart), 64-element
+// blocks along M/N are `lbo` bytes apart (gemm_tcgen05_wgrad.cu has the layout in full)
+__device__ __forceinline__ uint64_t cl_smem_desc_mn(uint32_t smem_addr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // byte offset of the 16-byte piece `piece` (0..7) of row `row` inside a [rows][64] bf16 box with 128-byte swizzle
 __device__ __forceinline__ uint32_t swz128(int row, int piece) {
   return (uint32_t)(row * 128 + ((piece ^ (row & 7)) << 4));
@@ -102,7 +128,7 @@ __device__ __forceinline__ float cl_act(float x) {
   return x;
 }
 
-template <int ACT, bool HAS_E>
+template <int ACT, bool HAS_E, bool WG>
 __global__ void __launch_bounds__(CL_THREADS, 1)
     gemm_bf16_tc_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_e,
@@ -115,8 +141,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
   __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ __align__(8) uint64_t e_full[CL_EC];
   __shared__ __align__(8) uint64_t e_empty[CL_EC];
+  __shared__ __align__(8) uint64_t w_full;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float bias_s[192];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank(), CS = (uint32_t)p.cluster_size;
@@ -137,12 +163,15 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
   // then overwritten IN PLACE with the result (dgrad: double buffered so the next operand load overlaps)
   uint8_t* c_tile = a_tiles + (size_t)p.stages * a_bytes;
   const uint32_t ec_bytes = (uint32_t)nbox * box_bytes;
+  // bias of this CTA's columns (forward only: the region exists only without an epilogue operand)
+  float* bias_s = reinterpret_cast<float*>(c_tile + (size_t)(HAS_E ? p.ec : 1) * ec_bytes);
 
   if (threadIdx.x == 0) {
     mbar_init(&b_full, 1);
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], CS); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], p.mc ? CS : 1u); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     for (int i = 0; i < CL_EC; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 1); }
+    mbar_init(&w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -150,8 +179,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
                  "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  for (int i = threadIdx.x; i < 192; i += CL_THREADS)
-    bias_s[i] = (p.bias != nullptr && i < BNh && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
+  if (!HAS_E)
+    for (int i = threadIdx.x; i < 192; i += CL_THREADS)
+      bias_s[i] = (p.bias != nullptr && i < BNh && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   cluster_sync_all();  // both CTAs' barriers are initialised before any multicast load / remote arrival
@@ -165,9 +195,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
       mbar_expect_tx(&b_full, (uint32_t)num_kb * b_kb_bytes);
       for (int kb = 0; kb < num_kb; ++kb)
         tma_load_2d(&tmap_b, &b_full, b_tiles + (size_t)kb * b_kb_bytes, kb * CL_BK, n0);
-      int it = 0, local = 0;
+      int local = 0, s = 0, eb = 0;
+      uint32_t phase = 0, eph = 0;      // ring / operand-tile slots and parities as running counters (no divisions)
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
-        // The A ring holds one tile per SM (64 KB): too few bytes in flight for the HBM latency.  The tiles this
+        // The A ring holds at most one tile per SM: too few bytes in flight for the HBM latency.  The tiles this
         // cluster will need next are pulled into L2 by bulk prefetches (no shared memory involved), so that the ring's
         // own loads are L2 hits.
         for (int ahead = (local == 0 ? 1 : p.prefetch); p.prefetch > 0 && ahead <= p.prefetch; ++ahead) {
@@ -180,22 +211,27 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
             for (int j = 0; j < nbox; ++j) cl_prefetch_l2(&tmap_e, n0 + 64 * j, pt * CL_BM);
         }
         if (HAS_E) {
-          const int eb = local % CL_EC;
-          mbar_wait(&e_empty[eb], (uint32_t)((local / CL_EC) & 1) ^ 1u);  // the store that used this buffer has read it
+          mbar_wait(&e_empty[eb], eph ^ 1u);  // the store that used this buffer has read it
           mbar_expect_tx(&e_full[eb], ec_bytes);
           for (int j = 0; j < nbox; ++j)
             tma_load_2d(&tmap_e, &e_full[eb], c_tile + (size_t)eb * ec_bytes + (size_t)j * box_bytes, n0 + 64 * j,
                         tile * CL_BM);
+          if (++eb == p.ec) { eb = 0; eph ^= 1u; }
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t phase = (it / p.stages) & 1;
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&a_empty[s], phase ^ 1);  // released by the MMAs of ALL CTAs of the cluster
           mbar_expect_tx(&a_full[s], a_bytes);
           // the row boxes of the block are dealt round-robin to the CTAs; each is multicast to every ring
-          for (uint32_t j = rank; j < CL_ABOX; j += CS)
-            tma_load_2d_mc(&tmap_a, &a_full[s], a_tiles + (size_t)s * a_bytes + j * (a_bytes / CL_ABOX), kb * CL_BK,
-                           tile * CL_BM + (int)j * (CL_BM / CL_ABOX), cmask);
+          if (p.mc) {
+            for (uint32_t j = rank; j < CL_ABOX; j += CS)
+              tma_load_2d_mc(&tmap_a, &a_full[s], a_tiles + (size_t)s * a_bytes + j * (a_bytes / CL_ABOX), kb * CL_BK,
+                             tile * CL_BM + (int)j * (CL_BM / CL_ABOX), cmask);
+          } else {
+            for (uint32_t j = 0; j < CL_ABOX; ++j)
+              tma_load_2d(&tmap_a, &a_full[s], a_tiles + (size_t)s * a_bytes + j * (a_bytes / CL_ABOX), kb * CL_BK,
+                          tile * CL_BM + (int)j * (CL_BM / CL_ABOX));
+          }
+          if (++s == p.stages) { s = 0; phase ^= 1u; }
         }
       }
     }
@@ -204,27 +240,55 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNh >> 3) << 17) |
                              ((uint32_t)(CL_BM >> 4) << 24);
       mbar_wait(&b_full, 0);
-      int it = 0, local = 0;
+      // WG: M = this CTA's BNh columns of E, N = the 64 columns of dZ in the ring stage, both operands MN-major
+      const uint32_t idesc_w = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+                               ((uint32_t)(BNh >> 4) << 24);
+      int local = 0, s = 0, eb = 0;
+      uint32_t phase = 0, eph = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
-        const int buf = local & 1;
-        const uint32_t use = (uint32_t)(local >> 1);
-        mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+        // WG: one dgrad accumulator (columns 0..BNh), the weight-gradient accumulator behind it
+        const int buf = WG ? 0 : (local & 1);
+        const uint32_t use = WG ? (uint32_t)local : (uint32_t)(local >> 1);
+        if (WG) {
+          mbar_wait(&e_full[eb], eph);  // the H tile is an MMA operand too
+        } else {
+          mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t phase = (it / p.stages) & 1;
+        const uint32_t e_addr = smem_u32(c_tile + (size_t)eb * ec_bytes);
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&a_full[s], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = make_smem_desc(smem_u32(a_tiles + (size_t)s * a_bytes));
+          const uint32_t a_addr = smem_u32(a_tiles + (size_t)s * a_bytes);
+          if (WG) {
+            // weight-gradient MMAs first: they do not touch the dgrad accumulator, which the epilogue of the previous
+            // tile may still be copying to registers
+            const uint64_t we = cl_smem_desc_mn(e_addr, box_bytes), wa = cl_smem_desc_mn(a_addr, box_bytes);
+            const uint32_t accw = tmem_base + (uint32_t)(BNh + CL_BK * kb);
+            if (!(p.debug & 1))
+#pragma unroll
+            for (int k = 0; k < CL_BM / 16; ++k)   // 16 rows = two 8-row groups = 2048 B = +128 in the address field
+              umma_bf16(accw, we + 128 * k, wa + 128 * k, idesc_w, (local > 0 || k > 0) ? 1u : 0u);
+            if (kb == 0) {
+              mbar_wait(&acc_empty[0], (use & 1) ^ 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+          }
+          const uint64_t da = make_smem_desc(a_addr);
           const uint64_t db = make_smem_desc(smem_u32(b_tiles + (size_t)kb * b_kb_bytes));
+          if (!(p.debug & 2))
 #pragma unroll
           for (int k = 0; k < CL_BK / 16; ++k)
             umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit_mc(&a_empty[s], cmask);  // the stage is free everywhere once every CTA's MMAs have read it
+          if (p.mc) umma_commit_mc(&a_empty[s], cmask);  // the stage is free everywhere once every CTA's MMAs have read it
+          else umma_commit(&a_empty[s]);
+          if (++s == p.stages) { s = 0; phase ^= 1u; }
         }
         umma_commit(&acc_full[buf]);
+        if (++eb == p.ec) { eb = 0; eph ^= 1u; }
       }
+      if (WG) umma_commit(&w_full);
     }
   } else {
     // ---------------- epilogue: warps 2..9; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 ----------------
@@ -235,39 +299,56 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
     const int cbeg = ch * cw;
     const int nchunks = cw / 16;
     const bool issuer = (warp == 2 && lane == 0);
-    int local = 0;
+    const bool early = p.ec < CL_EC;   // two operand tiles: a tile's buffer goes back as soon as its store has read it
+    int local = 0, eb = 0, eb_prev = 0;
+    uint32_t eph = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
-      const int buf = local & 1;
-      const uint32_t use = (uint32_t)(local >> 1);
+      const int buf = WG ? 0 : (local & 1);
+      const uint32_t use = WG ? (uint32_t)local : (uint32_t)(local >> 1);
       mbar_wait(&acc_full[buf], use & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint8_t* stage = c_tile + (HAS_E ? (size_t)(local % CL_EC) * ec_bytes : 0);
+      uint8_t* stage = c_tile + (HAS_E ? (size_t)eb * ec_bytes : 0);
       if (HAS_E) {
-        // the previous tile's store has had a whole MMA phase to read its buffer: hand that buffer back to the
-        // producer now, a full tile before it is needed again
-        if (issuer && local >= 1) {
+        // (three operand tiles) the previous tile's store has had a whole MMA phase to read its buffer: hand that
+        // buffer back to the producer now, a full tile before it is needed again
+        if (issuer && local >= 1 && !early) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          cl_mbar_arrive(&e_empty[(local - 1) % CL_EC]);
+          cl_mbar_arrive(&e_empty[eb_prev]);
         }
-        mbar_wait(&e_full[local % CL_EC], (uint32_t)((local / CL_EC) & 1));
+        mbar_wait(&e_full[eb], eph);
       } else {
         // the previous tile's TMA store must have finished READING the staging tile before it is overwritten
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         cl_named_bar(1, 256);
       }
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + cbeg);
-      uint32_t r[2][16];
-      tmem_ld16(trow, r[0]);
+      constexpr int NR = WG ? CL_WG_CH : 2;
+      uint32_t r[NR][16];
+      if (WG) {
+        // single accumulator: copy this thread's columns to registers and hand the accumulator straight back, so the
+        // next tile's MMAs run under this tile's epilogue arithmetic
+#pragma unroll
+        for (int c = 0; c < CL_WG_CH; ++c)
+          if (c < nchunks) tmem_ld16(trow + (uint32_t)(16 * c), r[c % NR]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) cl_mbar_arrive(&acc_empty[0]);
+      } else {
+        tmem_ld16(trow, r[0]);
+      }
 #pragma unroll
       for (int c = 0; c < CL_MAX_CH; ++c) {
-        if (c >= nchunks) break;
+        if (c >= nchunks || (p.debug & 4)) break;
         const int c0 = cbeg + 16 * c;  // column inside this CTA's half
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c + 1 < nchunks) tmem_ld16(trow + (uint32_t)(16 * (c + 1)), r[(c + 1) & 1]);
+        if (!WG) {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c + 1 < nchunks) tmem_ld16(trow + (uint32_t)(16 * (c + 1)), r[(c + 1) % NR]);
+        }
         const int box = c0 >> 6, piece = (c0 & 63) >> 3;  // 16-byte piece index of the chunk's first 8 columns
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = cl_act<ACT>(__uint_as_float(r[c & 1][j]) + bias_s[c0 + j]);
+        for (int j = 0; j < 16; ++j) v[j] = cl_act<ACT>(__uint_as_float(r[c % NR][j]) + (HAS_E ? 0.0f : bias_s[c0 + j]));
         if (HAS_E) {
           const uint8_t* eb = stage + (size_t)box * box_bytes;
           const uint4 h0 = *reinterpret_cast<const uint4*>(eb + swz128(row, piece));
@@ -306,10 +387,12 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
         *reinterpret_cast<uint4*>(cb + swz128(row, piece)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(cb + swz128(row, piece + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
-      // accumulator buffer and operand tile are free again
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) cl_mbar_arrive(&acc_empty[buf]);
+      if (!WG) {
+        // accumulator buffer and operand tile are free again
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) cl_mbar_arrive(&acc_empty[buf]);
+      }
       // staging tile complete -> one thread stores it with TMA (rows beyond M / columns beyond the map are clipped)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       cl_named_bar(1, 256);
@@ -319,6 +402,32 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
         for (int j = 0; j < my_boxes; ++j)
           tma_store_2d(&tmap_c, stage + (size_t)j * box_bytes, n0 + 64 * j, tile * CL_BM);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (HAS_E && early) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          cl_mbar_arrive(&e_empty[eb]);
+        }
+      }
+      eb_prev = eb;
+      if (++eb == p.ec) { eb = 0; eph ^= 1u; }
+    }
+    if (WG && local > 0) {
+      // weight gradient of this CTA: lanes = its columns of E (columns n0.. of dW), TMEM columns BNh.. = rows of dW;
+      // consecutive lanes add to consecutive addresses
+      mbar_wait(&w_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int kw = p.K / 2;                       // dW rows of this column half (multiple of 16: K % 64 == 0 ...)
+      const uint32_t wrow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)BNh;
+      const int col = n0 + row;
+      for (int k0 = ch * kw; k0 < (ch + 1) * kw && k0 < p.K_real; k0 += 16) {
+        uint32_t w[16];
+        tmem_ld16(wrow + (uint32_t)k0, w);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (col < p.N) {
+          float* dst = p.dW + (long long)k0 * p.lddw + col;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (k0 + j < p.K_real) atomicAdd(dst + (long long)j * p.lddw, __uint_as_float(w[j]));
+        }
       }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -340,7 +449,8 @@ using namespace dfol;
 
 static int launch_cluster(const char* who, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                           int store_cols, const float* bias, int M, int N, int K, int act, const void* E, int64_t lde,
-                          int mul_mode, void* stream, float keep = 1.0f) {
+                          int mul_mode, void* stream, float keep = 1.0f, float* dW = nullptr, int64_t lddw = 0,
+                          int k_real = 0) {
   DFOL_REQUIRE(A && B && C, "%s: null pointer", who);
   DFOL_REQUIRE(keep > 0.0f && keep <= 1.0f, "%s: keep = 1 - dropout p must be in (0, 1]", who);
   DFOL_REQUIRE(M > 0 && N > 0 && K > 0 && (K % CL_BK) == 0 && K <= CL_BK * CL_MAX_KB,
@@ -367,22 +477,37 @@ static int launch_cluster(const char* who, const void* A, int64_t lda, const voi
   const int CS = (n_store + p.BNh - 1) / p.BNh;
   p.n_store = n_store;
   p.cluster_size = CS;
+  p.dW = dW; p.lddw = lddw; p.K_real = k_real;
+  static const int dbg_env = [] { const char* e = getenv("DFOL_CL_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = dbg_env;
+  static const int mc_env = [] { const char* e = getenv("DFOL_CL_MC"); return e ? atoi(e) : 1; }();
+  p.mc = mc_env;
+  if (dW != nullptr) {
+    DFOL_REQUIRE(has_e && p.BNh == 128 && p.BNh + K <= 512 && k_real > 0 && k_real <= K && lddw >= N,
+                 "%s: the fused weight gradient needs 65..256 output columns, K <= 384 and a multiplier operand", who);
+  }
   const int num_kb = K / CL_BK;
   const size_t b_bytes = (size_t)num_kb * p.BNh * CL_BK * 2;
   const size_t box = (size_t)CL_BM * 128;
-  const size_t tiles_bytes = (size_t)(p.BNh / 64) * box * (has_e ? CL_EC : 1);  // dgrad: in-place operand/result tiles
+  static const int ec_env = [] { const char* e = getenv("DFOL_CL_EC"); return e ? atoi(e) : 0; }();
+  // (with the fused weight gradient the ring needs the room more than the operand tiles do: two tiles, four stages)
+  p.ec = (ec_env >= 2 && ec_env <= CL_EC) ? ec_env : (dW != nullptr ? 2 : CL_EC);
+  const size_t tiles_bytes = (size_t)(p.BNh / 64) * box * (has_e ? p.ec : 1);  // dgrad: in-place operand/result tiles
   const size_t a_stage = (size_t)CL_BM * CL_BK * 2;
-  const size_t budget = 224 * 1024;  // + ~2 KB static (barriers, bias) <= 227 KB
+  DFOL_REQUIRE(!has_e || bias == nullptr, "%s: the multiplier epilogue has no bias", who);
+  const size_t bias_bytes = has_e ? 0 : 192 * sizeof(float);
+  const size_t budget = 232448 - 1536 - bias_bytes;  // 227 KB - static shared memory (barriers: < 1.5 KB)
   DFOL_REQUIRE(b_bytes + tiles_bytes + 2 * a_stage + 1024 <= budget, "%s: does not fit in shared memory", who);
   int stages = (int)((budget - 1024 - b_bytes - tiles_bytes) / a_stage);
   if (stages > CL_MAX_STAGES) stages = CL_MAX_STAGES;
   p.stages = stages;
-  const size_t smem = b_bytes + tiles_bytes + (size_t)stages * a_stage + 1024;
+  const size_t smem = b_bytes + tiles_bytes + (size_t)stages * a_stage + 1024 + bias_bytes;
   ClKernel kernel;
-  if (has_e) kernel = gemm_bf16_tc_cluster_kernel<DFOL_ACT_NONE, true>;
-  else if (act == DFOL_ACT_SIGMOID) kernel = gemm_bf16_tc_cluster_kernel<DFOL_ACT_SIGMOID, false>;
-  else if (act == DFOL_ACT_ELU) kernel = gemm_bf16_tc_cluster_kernel<DFOL_ACT_ELU, false>;
-  else kernel = gemm_bf16_tc_cluster_kernel<DFOL_ACT_NONE, false>;
+  if (has_e && dW != nullptr) kernel = gemm_bf16_tc_cluster_kernel<DFOL_ACT_NONE, true, true>;
+  else if (has_e) kernel = gemm_bf16_tc_cluster_kernel<DFOL_ACT_NONE, true, false>;
+  else if (act == DFOL_ACT_SIGMOID) kernel = gemm_bf16_tc_cluster_kernel<DFOL_ACT_SIGMOID, false, false>;
+  else if (act == DFOL_ACT_ELU) kernel = gemm_bf16_tc_cluster_kernel<DFOL_ACT_ELU, false, false>;
+  else kernel = gemm_bf16_tc_cluster_kernel<DFOL_ACT_NONE, false, false>;
   DFOL_REQUIRE(!has_e || act == DFOL_ACT_NONE, "%s: the multiplier epilogue has no activation", who);
   {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -436,4 +561,15 @@ extern "C" int dfol_pair_layer_dgrad_cluster(const void* dZ, int64_t lddz, const
                                              int64_t ldh, int mul_mode, float keep, void* stream) {
   return launch_cluster("dfol_pair_layer_dgrad_cluster", dZ, lddz, Wt, ldwt, dX, lddx, store_cols, nullptr, M, N, K,
                         DFOL_ACT_NONE, h_saved, ldh, mul_mode, stream, keep);
+}
+
+/* dgrad + weight gradient of the same layer in one pass over dZ and h_saved:
+ *   dX = (dZ . Wt^T) * act'(h_saved)   and   dW[k, n] += sum_rows dZ[row, k] * h_saved[row, n]   (k < k_real) */
+extern "C" int dfol_pair_layer_dgrad_wgrad_cluster(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX,
+                                                   int64_t lddx, int store_cols, int M, int N, int K,
+                                                   const void* h_saved, int64_t ldh, int mul_mode, float keep,
+                                                   float* dW, int64_t lddw, int k_real, void* stream) {
+  DFOL_REQUIRE(dW != nullptr, "dfol_pair_layer_dgrad_wgrad_cluster: null weight gradient");
+  return launch_cluster("dfol_pair_layer_dgrad_wgrad_cluster", dZ, lddz, Wt, ldwt, dX, lddx, store_cols, nullptr, M, N,
+                        K, DFOL_ACT_NONE, h_saved, ldh, mul_mode, stream, keep, dW, lddw, k_real);
 }

@@ -29,6 +29,8 @@ def _roundup(x, m):
     return (x + m - 1) // m * m
 
 
+_FUSE_WGRAD = os.environ.get('DFOL_FUSE_WGRAD', '1') != '0'
+
 class _Operands(object):
     """bf16 operand copies of the 12 parameter tensors + the device job table that refreshes them."""
 
@@ -162,6 +164,24 @@ class TensorCorePath(object):
                               'bytes': 2.0 * rows * (A.stride(0) + B.stride(0)) if rows == cls._P else 0.0}
         call('dfol_gemm_bf16_tc_wgrad', ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(C), C.stride(0), Mc, Nc, rows,
              st)
+
+    @classmethod
+    def _pair_dgrad_wgrad(cls, dz2, w2t, dz1, h1, gW2, P, H, Hp, E, Ep, keep, st):
+        """Backward of the pair-level second layer: dZ1 = (dZ2 . W2) * elu'(H1) and dW2 += dZ2^T . H1.  One launch
+        (``dfol_pair_layer_dgrad_wgrad_cluster``: both products from the operands the dgrad holds in shared memory, dZ2 and H1
+        read from HBM once) when the layer fits its TMEM budget; ``DFOL_FUSE_WGRAD=0`` keeps the two launches."""
+        fused = _FUSE_WGRAD and 128 < Hp <= 256 and 128 + Ep <= 512
+        if not fused:
+            cls._wgrad(dz2, E, h1, H, gW2, st)
+        if capi.trace is not None:
+            capi.next_meta = {'tag': 'pair_layer_dgrad%s_cluster[Px%dx%d]' % ('_wgrad' if fused else '', H, Ep),
+                              'flops': (4.0 if fused else 2.0) * P * H * Ep, 'bytes': 2.0 * P * (Ep + 2 * Hp)}
+        if fused:
+            call('dfol_pair_layer_dgrad_wgrad_cluster', ptr(dz2), Ep, ptr(w2t), Ep, ptr(dz1), Hp, Hp, P, H, Ep, ptr(h1),
+                 Hp, K.MUL_ELU_GRAD, keep, ptr(gW2), gW2.stride(0), E, st)
+        else:
+            call('dfol_pair_layer_dgrad_cluster', ptr(dz2), Ep, ptr(w2t), Ep, ptr(dz1), Hp, Hp, P, H, Ep, ptr(h1), Hp,
+                 K.MUL_ELU_GRAD, keep, st)
 
     # -------------------------------------------------------------------------------------------- forward
 
@@ -535,13 +555,8 @@ class TensorCorePath(object):
                 G(w.emb.weight).index_add_(0, ridx, dw_rel)
                 G(w.emb.bias).index_add_(0, ridx, db_rel)
             h1r = scene.rel_h[0]
-            self._wgrad(dz2r, E, h1r, H, G(r1.weight), st)
             dz1r = torch.empty(P, Hp, device=dev, dtype=torch.bfloat16)
-            if capi.trace is not None:
-                capi.next_meta = {'tag': 'pair_layer_dgrad_cluster[Px%dx%d]' % (H, Ep), 'flops': 2.0 * P * H * Ep,
-                                  'bytes': 2.0 * P * (Ep + 2 * Hp)}
-            call('dfol_pair_layer_dgrad_cluster', ptr(dz2r), Ep, ptr(ops.wr2t), Ep, ptr(dz1r), Hp, Hp, P, H, Ep,
-                 ptr(h1r), Hp, K.MUL_ELU_GRAD, 1.0, st)
+            self._pair_dgrad_wgrad(dz2r, ops.wr2t, dz1r, h1r, G(r1.weight), P, H, Hp, E, Ep, 1.0, st)
             gw1 = G(r0.weight)
             if capi.trace is not None:
                 capi.next_meta = {'tag': 'pair_hidden_bwd_tc', 'bytes': 2.0 * P * H + 16.0 * P}
@@ -628,10 +643,8 @@ class TensorCorePath(object):
             dz2r = self._table_backward(g_rel, sr, scene.rel_ll, scene.rel_blk, lay.rel_stride, lay.pair_row,
                                         lay.img_nn, lay.max_n ** 2, P, w.emb.weight, G(w.emb.weight), G(w.emb.bias),
                                         h2r, G(r1.bias), st, 'rel', keep)
-            self._wgrad(dz2r, E, h1r, H, G(r1.weight), st)
             dz1r = torch.empty(P, Hp, device=dev, dtype=torch.bfloat16)
-            call('dfol_pair_layer_dgrad_cluster', ptr(dz2r), Ep, ptr(ops.wr2t), Ep, ptr(dz1r), Hp, Hp, P, H, Ep,
-                 ptr(h1r), Hp, K.MUL_ELU_GRAD, keep, st)
+            self._pair_dgrad_wgrad(dz2r, ops.wr2t, dz1r, h1r, G(r1.weight), P, H, Hp, E, Ep, keep, st)
             del dz2r
             call('dfol_colsum_bf16', ptr(dz1r), Hp, P, H, ptr(G(r0.bias)), st)
             pm, w1 = scene.pm, scene.w1_16

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFOL_ABI_VERSION 5
+#define DFOL_ABI_VERSION 6
 
 /* activation codes (RegularMLP / EmbeddingLayer, gqa_interpreter_experiments.py:28-33, :71-72) */
 #define DFOL_ACT_NONE 0
@@ -152,6 +152,15 @@ int dfol_pair_layer_fwd_cluster(const void* A, int64_t lda, const void* B, int64
 int dfol_pair_layer_dgrad_cluster(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX, int64_t lddx,
                                   int store_cols, int M, int N, int K, const void* h_saved, int64_t ldh, int mul_mode,
                                   float keep, void* stream);
+/* The same dgrad with the WEIGHT GRADIENT of the layer fused in (backward of nn.Linear, classifier_oracle.py:149-154 via
+ * autograd): dW[k, n] += sum_rows dZ[row, k] * h_saved[row, n] for k < k_real (fp32, red.global.add), accumulated in a
+ * second TMEM accumulator from the operands the dgrad already holds in shared memory (MN-major tcgen05 MMAs over the
+ * tile's 128 rows) -- dZ and h_saved are read from HBM once for both products.  Needs 65..256 output columns (N) and
+ * K <= 384 (128 + K TMEM columns). */
+int dfol_pair_layer_dgrad_wgrad_cluster(const void* dZ, int64_t lddz, const void* Wt, int64_t ldwt, void* dX,
+                                        int64_t lddx, int store_cols, int M, int N, int K, const void* h_saved,
+                                        int64_t ldh, int mul_mode, float keep, float* dW, int64_t lddw, int k_real,
+                                        void* stream);
 
 /* fp32 -> bf16 cast with row padding: dst[r*ldd + c] = bf16(src[r*lds + c]) for c < cols, 0 for cols <= c < ldd */
 int dfol_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);

@@ -406,3 +406,36 @@ def test_pair_layer_dgrad_resident_gemm(M, N, K, mode, impl):
     if mode == 2:
         ref = ref * torch.where(h > 0, torch.ones_like(h), h + 1)
     assert torch.allclose(dX.double(), ref, rtol=1.5e-2, atol=1.5e-2), (dX.double() - ref).abs().max()
+
+
+@pytest.mark.parametrize('M,N,K,k_real', [(1000, 256, 320, 300), (4608 * 3 + 5, 256, 320, 300), (40000, 192, 256, 256),
+                                          (300000, 256, 320, 300)])
+@pytest.mark.parametrize('mode,keep', [(2, 1.0), (1, 1.0), (2, 0.9)])
+def test_pair_layer_dgrad_with_fused_weight_gradient(M, N, K, k_real, mode, keep):
+    """dfol_pair_layer_dgrad_wgrad_cluster: the dgrad result is bit-identical to the plain cluster dgrad and the fused
+    weight gradient equals dZ^T . h_saved (fp64 statement of nn.Linear's backward) and the stand-alone wgrad kernel."""
+    from dfol_vqa_b200.capi import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(M + mode)
+    dZ = torch.randn(M, K, generator=g)
+    dZ[:, k_real:] = 0
+    dZ = dZ.cuda().bfloat16()
+    Wt = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
+    Hs = torch.rand(M, N, generator=g) - (0.3 if mode == 2 else 0.0)
+    if keep < 1.0:
+        Hs = Hs * (torch.rand(M, N, generator=g) < keep) / keep
+    Hs = Hs.cuda().bfloat16()
+    dX0 = torch.full((M, N), float('nan'), device='cuda', dtype=torch.bfloat16)
+    dX1 = torch.full((M, N), float('nan'), device='cuda', dtype=torch.bfloat16)
+    base = torch.randn(k_real, N, generator=g).cuda()
+    dW, dW_sep = base.clone(), base.clone()
+    call('dfol_pair_layer_dgrad_cluster', ptr(dZ), K, ptr(Wt), K, ptr(dX0), N, 0, M, N, K, ptr(Hs), N, mode, keep,
+         stream_ptr())
+    call('dfol_pair_layer_dgrad_wgrad_cluster', ptr(dZ), K, ptr(Wt), K, ptr(dX1), N, 0, M, N, K, ptr(Hs), N, mode, keep,
+         ptr(dW), N, k_real, stream_ptr())
+    call('dfol_gemm_bf16_tc_wgrad', ptr(dZ), K, ptr(Hs), N, ptr(dW_sep), N, k_real, N, M, stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(dX0, dX1)
+    ref = base.double().cpu() + dZ.double().cpu()[:, :k_real].t() @ Hs.double().cpu()
+    scale = float((ref - base.double().cpu()).abs().max())
+    assert float((dW.double().cpu() - ref).abs().max()) <= 1e-4 * scale + 1e-4
+    assert float((dW - dW_sep).abs().max()) <= 1e-4 * scale + 1e-4
