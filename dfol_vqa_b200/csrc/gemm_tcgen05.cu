@@ -89,14 +89,15 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc_kernel(const __grid_c
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+      int s = 0;
+      uint32_t phase = 0;   // ring slot and parity as running counters (no division on the single-thread path)
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t phase = (kb / p.stages) & 1;
         mbar_wait(&empty_bar[s], phase ^ 1);
         mbar_expect_tx(&full_bar[s], stage_bytes);
         uint8_t* sa = tiles + (size_t)s * stage_bytes;
         tma_load_2d(&tmap_a, &full_bar[s], sa, kb * TC_BK, m0);
         tma_load_2d(&tmap_b, &full_bar[s], sa + a_bytes, kb * TC_BK, n0);
+        if (++s == p.stages) { s = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -104,9 +105,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc_kernel(const __grid_c
       // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                              ((uint32_t)(TC_BM >> 4) << 24);
+      int s = 0;
+      uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t phase = (kb / p.stages) & 1;
         mbar_wait(&full_bar[s], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc_kernel(const __grid_c
           umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        if (++s == p.stages) { s = 0; phase ^= 1u; }
       }
       umma_commit(&tmem_full_bar);   // accumulator complete
     }

@@ -12,7 +12,12 @@
 //                       tcgen05.commit.multicast releases a ring stage in ALL CTAs of the cluster.
 //   warps 2..9        : epilogue: tcgen05.ld, bias + activation or activation-derivative multiplier (operand read from
 //                       the 128B-swizzled shared tile, conflict free), bf16 result written to a swizzled shared tile
-//                       and stored with cp.async.bulk.tensor (full 128-byte lines) -- no per-thread global access.
+//                       -- no per-thread global access.
+//   warp 10 (one lane): store warp: waits until the eight epilogue warps have published the tile, issues the
+//                       cp.async.bulk.tensor store (full 128-byte lines) and hands the buffer back once the store has
+//                       read it.  (Clock stamps, DFOL_CL_TRACE=1: with the store issued by an epilogue thread, the ~1500
+//                       cycles a bulk store needs to read 32-48 KB and a 256-thread barrier sat inside every tile's
+//                       epilogue, which is the role that paces these kernels.)
 // Fused weight gradient (WG, dgrad only): the dgrad already holds both operands of dW = dZ^T . H of its layer in shared
 // memory -- every 128 x 64 block of dZ passes through the A ring and this CTA's columns of the saved activation H sit
 // in the epilogue operand tile.  Per ring stage the MMA warp issues, after the four K-major dgrad MMAs, eight MN-major
@@ -21,6 +26,7 @@
 // the epilogue copies to registers and releases at once); one red.global.add pass per CTA at the end.  The separate
 // wgrad launch, which re-read dZ and H from HBM, disappears.
 // Every mbarrier wait is bounded (trap instead of hanging the GPU).
+#include <cstdio>
 #include <cstdlib>
 #include "tc_common.cuh"
 
@@ -28,12 +34,13 @@ namespace dfol {
 
 constexpr int CL_BM = 128;
 constexpr int CL_BK = 64;
-constexpr int CL_THREADS = 64 + 256;
+constexpr int CL_THREADS = 64 + 256 + 32;   // producer, MMA issuer, 8 epilogue warps, store warp
 constexpr int CL_MAX_STAGES = 8;
 constexpr int CL_MAX_KB = 5;
 constexpr int CL_ABOX = 2;        // row boxes per A block, dealt round-robin to the CTAs of the cluster
 constexpr int CL_EC = 3;          // in-place operand/result tiles of the dgrad (operand prefetched two tiles ahead)
 constexpr int CL_MAX_CH = 6;      // 16-column chunks per epilogue warp (192 / 2 / 16)
+constexpr int CL_MAX_BOX = 3;     // 64-column boxes per staging tile (BNh <= 192)
 constexpr int CL_WG_CH = 4;       // the same with the fused weight gradient (BNh = 128: 64 columns held in registers)
 
 struct ClParams {
@@ -51,6 +58,7 @@ struct ClParams {
   int K_real;           // WG: rows of dW (columns of A that carry a weight row)
   int ec;               // in-place operand/result tiles of the dgrad in use (2..CL_EC)
   int mc;               // 1: every A block is fetched once per cluster (multicast); 0: every CTA loads its own copy
+  long long* trace;     // DFOL_CL_TRACE=1: clock64 stamps of block 0's roles, first 16 tiles ([role: load, mma, epilogue, store][tile][16])
   int debug;            // DFOL_CL_DEBUG ablation bits (timing experiments only; results are wrong when set)
 };
 
@@ -117,6 +125,11 @@ __device__ __forceinline__ uint32_t swz128(int row, int piece) {
   return (uint32_t)(row * 128 + ((piece ^ (row & 7)) << 4));
 }
 
+#define CL_STAMP(role, k)                                                                        \
+  do {                                                                                           \
+    if (p.trace != nullptr && blockIdx.x == 0 && local < 16) p.trace[((role) * 16 + local) * 16 + (k)] = clock64(); \
+  } while (0)
+
 template <int ACT>
 __device__ __forceinline__ float cl_act(float x) {
   if (ACT == DFOL_ACT_ELU) return x > 0.0f ? x : __expf(x) - 1.0f;
@@ -142,6 +155,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
   __shared__ __align__(8) uint64_t e_full[CL_EC];
   __shared__ __align__(8) uint64_t e_empty[CL_EC];
   __shared__ __align__(8) uint64_t w_full;
+  __shared__ __align__(8) uint64_t c_ready[CL_EC][CL_MAX_BOX];   // per 64-column box of a staging tile
+  __shared__ __align__(8) uint64_t c_free[CL_MAX_BOX];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -172,6 +187,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     for (int i = 0; i < CL_EC; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 1); }
     mbar_init(&w_full, 1);
+    for (int b = 0; b < CL_MAX_BOX; ++b) {
+      // epilogue warps that write into box b: four per column half that overlaps it
+      uint32_t cnt = 0;
+      for (int h = 0; h < 2; ++h)
+        if (h * (BNh / 2) < 64 * (b + 1) && (h + 1) * (BNh / 2) > 64 * b) cnt += 4;
+      for (int i = 0; i < CL_EC; ++i) mbar_init(&c_ready[i][b], cnt > 0 ? cnt : 1u);
+      mbar_init(&c_free[b], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -210,8 +233,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
           if (HAS_E)
             for (int j = 0; j < nbox; ++j) cl_prefetch_l2(&tmap_e, n0 + 64 * j, pt * CL_BM);
         }
+        CL_STAMP(0, 0);
         if (HAS_E) {
           mbar_wait(&e_empty[eb], eph ^ 1u);  // the store that used this buffer has read it
+          CL_STAMP(0, 1);
           mbar_expect_tx(&e_full[eb], ec_bytes);
           for (int j = 0; j < nbox; ++j)
             tma_load_2d(&tmap_e, &e_full[eb], c_tile + (size_t)eb * ec_bytes + (size_t)j * box_bytes, n0 + 64 * j,
@@ -220,6 +245,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&a_empty[s], phase ^ 1);  // released by the MMAs of ALL CTAs of the cluster
+          CL_STAMP(0, 2 + kb);
           mbar_expect_tx(&a_full[s], a_bytes);
           // the row boxes of the block are dealt round-robin to the CTAs; each is multicast to every ring
           if (p.mc) {
@@ -249,16 +275,59 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
         // WG: one dgrad accumulator (columns 0..BNh), the weight-gradient accumulator behind it
         const int buf = WG ? 0 : (local & 1);
         const uint32_t use = WG ? (uint32_t)local : (uint32_t)(local >> 1);
+        CL_STAMP(1, 0);
         if (WG) {
           mbar_wait(&e_full[eb], eph);  // the H tile is an MMA operand too
         } else {
           mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
         }
+        CL_STAMP(1, 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
         const uint32_t e_addr = smem_u32(c_tile + (size_t)eb * ec_bytes);
+        if (WG && p.stages == num_kb) {
+          // The ring holds exactly one tile (stage kb = k-block kb, adjacent stages 16 KB apart like the boxes of an
+          // MN-major operand): the weight-gradient MMAs take TWO k-blocks at once (N = 128), which halves the fetches of
+          // their M operand -- MN-major operand reads are what bounds them (~120 cycles per 128 x 64 x 16 MMA measured,
+          // 32 by the tensor pipe).  They go first: they do not touch the dgrad accumulator, which the epilogue of the
+          // previous tile may still be copying to registers.
+          for (int kb = 0; kb < num_kb; kb += 2) {
+            const int nk = min(2, num_kb - kb);
+            for (int q = 0; q < nk; ++q) {
+              mbar_wait(&a_full[kb + q], phase);
+              CL_STAMP(1, 2 + kb + q);
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_addr = smem_u32(a_tiles + (size_t)kb * a_bytes);
+            const uint64_t we = cl_smem_desc_mn(e_addr, box_bytes), wa = cl_smem_desc_mn(a_addr, a_bytes);
+            const uint32_t accw = tmem_base + (uint32_t)(BNh + CL_BK * kb);
+            const uint32_t idw = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                 ((uint32_t)((64 * nk) >> 3) << 17) | ((uint32_t)(BNh >> 4) << 24);
+            if (!(p.debug & 1))
+#pragma unroll
+            for (int k = 0; k < CL_BM / 16; ++k)
+              umma_bf16(accw, we + 128 * k, wa + 128 * k, idw, (local > 0 || k > 0) ? 1u : 0u);
+            if (kb == 0) {
+              mbar_wait(&acc_empty[0], (use & 1) ^ 1);
+              CL_STAMP(1, 8);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            for (int q = 0; q < nk; ++q) {
+              const uint64_t da = make_smem_desc(a_addr + (uint32_t)q * a_bytes);
+              const uint64_t db = make_smem_desc(smem_u32(b_tiles + (size_t)(kb + q) * b_kb_bytes));
+              if (!(p.debug & 2))
+#pragma unroll
+              for (int k = 0; k < CL_BK / 16; ++k)
+                umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb + q > 0 || k > 0) ? 1u : 0u);
+              if (p.mc) umma_commit_mc(&a_empty[kb + q], cmask);
+              else umma_commit(&a_empty[kb + q]);
+            }
+          }
+          phase ^= 1u;
+        } else
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&a_full[s], phase);
+          CL_STAMP(1, 2 + kb);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_addr = smem_u32(a_tiles + (size_t)s * a_bytes);
           if (WG) {
@@ -272,6 +341,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
               umma_bf16(accw, we + 128 * k, wa + 128 * k, idesc_w, (local > 0 || k > 0) ? 1u : 0u);
             if (kb == 0) {
               mbar_wait(&acc_empty[0], (use & 1) ^ 1);
+              CL_STAMP(1, 8);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
           }
@@ -286,11 +356,12 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
           if (++s == p.stages) { s = 0; phase ^= 1u; }
         }
         umma_commit(&acc_full[buf]);
+        CL_STAMP(1, 9);
         if (++eb == p.ec) { eb = 0; eph ^= 1u; }
       }
       if (WG) umma_commit(&w_full);
     }
-  } else {
+  } else if (warp < 10) {
     // ---------------- epilogue: warps 2..9; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 ----------------
     const int quad = warp & 3;
     const int ch = (warp - 2) >> 2;
@@ -298,29 +369,22 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
     const int cw = BNh / 2;
     const int cbeg = ch * cw;
     const int nchunks = cw / 16;
-    const bool issuer = (warp == 2 && lane == 0);
-    const bool early = p.ec < CL_EC;   // two operand tiles: a tile's buffer goes back as soon as its store has read it
-    int local = 0, eb = 0, eb_prev = 0;
+    const bool stamper = (warp == 2 && lane == 0);
+    // derivative factor of the saved activation: 0 elu', 1 sigmoid', 2 either one behind a dropout mask
+    const int emode = (p.keep < 1.0f) ? 2 : (p.mul_mode == DFOL_MUL_SIGMOID_GRAD ? 1 : 0);
+    const int my_boxes = (min(max(p.n_store - n0, 0), BNh) + 63) / 64;   // boxes the store warp stores (and frees)
+    int local = 0, eb = 0;
     uint32_t eph = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
       const int buf = WG ? 0 : (local & 1);
       const uint32_t use = WG ? (uint32_t)local : (uint32_t)(local >> 1);
+      if (stamper) CL_STAMP(2, 0);
       mbar_wait(&acc_full[buf], use & 1);
+      if (stamper) CL_STAMP(2, 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint8_t* stage = c_tile + (HAS_E ? (size_t)eb * ec_bytes : 0);
-      if (HAS_E) {
-        // (three operand tiles) the previous tile's store has had a whole MMA phase to read its buffer: hand that
-        // buffer back to the producer now, a full tile before it is needed again
-        if (issuer && local >= 1 && !early) {
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          cl_mbar_arrive(&e_empty[eb_prev]);
-        }
-        mbar_wait(&e_full[eb], eph);
-      } else {
-        // the previous tile's TMA store must have finished READING the staging tile before it is overwritten
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        cl_named_bar(1, 256);
-      }
+      if (HAS_E) mbar_wait(&e_full[eb], eph);
+      if (stamper) CL_STAMP(2, 2);
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + cbeg);
       constexpr int NR = WG ? CL_WG_CH : 2;
       uint32_t r[NR][16];
@@ -334,12 +398,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) cl_mbar_arrive(&acc_empty[0]);
+        if (stamper) CL_STAMP(2, 3);
       } else {
         tmem_ld16(trow, r[0]);
       }
 #pragma unroll
       for (int c = 0; c < CL_MAX_CH; ++c) {
-        if (c >= nchunks || (p.debug & 4)) break;
+        if (c >= nchunks) break;
         const int c0 = cbeg + 16 * c;  // column inside this CTA's half
         if (!WG) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -350,25 +415,34 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = cl_act<ACT>(__uint_as_float(r[c % NR][j]) + (HAS_E ? 0.0f : bias_s[c0 + j]));
         if (HAS_E) {
-          const uint8_t* eb = stage + (size_t)box * box_bytes;
-          const uint4 h0 = *reinterpret_cast<const uint4*>(eb + swz128(row, piece));
-          const uint4 h1 = *reinterpret_cast<const uint4*>(eb + swz128(row, piece + 1));
+          const uint8_t* eb8 = stage + (size_t)box * box_bytes;
+          const uint4 h0 = *reinterpret_cast<const uint4*>(eb8 + swz128(row, piece));
+          const uint4 h1 = *reinterpret_cast<const uint4*>(eb8 + swz128(row, piece + 1));
           const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          if (emode == 0) {          // elu'(h) = 1 (h > 0), h + 1 (h <= 0)  ==  min(h, 0) + 1
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
-            if (p.keep < 1.0f) {  // act' at h = operand * keep, mask factor (operand != 0) / keep
-              const float ik = 1.0f / p.keep, hx = h.x * p.keep, hy = h.y * p.keep;
+            for (int j = 0; j < 8; ++j) {
+              const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
+              v[2 * j] *= fminf(h.x, 0.0f) + 1.0f;
+              v[2 * j + 1] *= fminf(h.y, 0.0f) + 1.0f;
+            }
+          } else if (emode == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
+              v[2 * j] *= h.x * (1.0f - h.x);
+              v[2 * j + 1] *= h.y * (1.0f - h.y);
+            }
+          } else {                   // act' at h = operand * keep, mask factor (operand != 0) / keep
+            const float ik = 1.0f / p.keep;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
+              const float hx = h.x * p.keep, hy = h.y * p.keep;
               const float gx = (p.mul_mode == DFOL_MUL_SIGMOID_GRAD) ? hx * (1.0f - hx) : (hx > 0.0f ? 1.0f : hx + 1.0f);
               const float gy = (p.mul_mode == DFOL_MUL_SIGMOID_GRAD) ? hy * (1.0f - hy) : (hy > 0.0f ? 1.0f : hy + 1.0f);
               v[2 * j] *= (h.x != 0.0f ? ik : 0.0f) * gx;
               v[2 * j + 1] *= (h.y != 0.0f ? ik : 0.0f) * gy;
-            } else if (p.mul_mode == DFOL_MUL_SIGMOID_GRAD) {
-              v[2 * j] *= h.x * (1.0f - h.x);
-              v[2 * j + 1] *= h.y * (1.0f - h.y);
-            } else {
-              v[2 * j] *= (h.x > 0.0f ? 1.0f : h.x + 1.0f);
-              v[2 * j + 1] *= (h.y > 0.0f ? 1.0f : h.y + 1.0f);
             }
           }
         }
@@ -383,31 +457,28 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
           __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
           pk[j] = *reinterpret_cast<uint32_t*>(&h2);
         }
+        // forward: ONE staging tile -- the store warp must have read the previous tile's box out of it before the
+        // first write into the box; the chunk's arithmetic is already done by then
+        if (!HAS_E && local >= 1 && box < my_boxes && (c == 0 || ((c0 - 16) >> 6) != box))
+          mbar_wait(&c_free[box], (uint32_t)((local - 1) & 1));
         uint8_t* cb = stage + (size_t)box * box_bytes;
         *reinterpret_cast<uint4*>(cb + swz128(row, piece)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(cb + swz128(row, piece + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (c + 1 == nchunks || ((c0 + 16) >> 6) != box) {
+          // this warp's part of the box is complete: publish it to the async proxy and tell the store warp, which
+          // stores the box while the remaining chunks are still being computed
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) cl_mbar_arrive(&c_ready[HAS_E ? eb : 0][box]);
+        }
       }
       if (!WG) {
-        // accumulator buffer and operand tile are free again
+        // accumulator buffer is free again
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) cl_mbar_arrive(&acc_empty[buf]);
       }
-      // staging tile complete -> one thread stores it with TMA (rows beyond M / columns beyond the map are clipped)
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      cl_named_bar(1, 256);
-      if (issuer) {
-        const int my_cols = min(max(p.n_store - n0, 0), BNh);
-        const int my_boxes = (my_cols + 63) / 64;
-        for (int j = 0; j < my_boxes; ++j)
-          tma_store_2d(&tmap_c, stage + (size_t)j * box_bytes, n0 + 64 * j, tile * CL_BM);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (HAS_E && early) {
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          cl_mbar_arrive(&e_empty[eb]);
-        }
-      }
-      eb_prev = eb;
+      if (stamper) CL_STAMP(2, 4);
       if (++eb == p.ec) { eb = 0; eph ^= 1u; }
     }
     if (WG && local > 0) {
@@ -430,7 +501,40 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
         }
       }
     }
-    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else {
+    // ---------------- store warp (warp 10, one lane): staging tile -> global by TMA, off the epilogue's critical path;
+    // the tile's buffer goes back (to the operand loads of the dgrad / to the next tile's epilogue) as soon as the bulk
+    // store has READ it
+    if (lane == 0) {
+      int local = 0, eb = 0;
+      uint32_t eph = 0;
+      const int my_cols = min(max(p.n_store - n0, 0), BNh);
+      const int my_boxes = (my_cols + 63) / 64;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+        const int slot = HAS_E ? eb : 0;
+        const uint32_t par = HAS_E ? eph : (uint32_t)(local & 1);
+        const uint8_t* stage = c_tile + (size_t)slot * ec_bytes;
+        for (int j = 0; j < my_boxes; ++j) {   // box by box, as the epilogue warps complete them
+          mbar_wait(&c_ready[slot][j], par);
+          if (j == 0) CL_STAMP(3, 0);
+          tma_store_2d(&tmap_c, stage + (size_t)j * box_bytes, n0 + 64 * j, tile * CL_BM);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        CL_STAMP(3, 2);
+        if (HAS_E) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          cl_mbar_arrive(&e_empty[eb]);
+        } else {
+          // (bulk groups complete in order: <= k groups pending means the first my_boxes - k boxes have been read)
+          if (my_boxes >= 3) { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); cl_mbar_arrive(&c_free[my_boxes - 3]); }
+          if (my_boxes >= 2) { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); cl_mbar_arrive(&c_free[my_boxes - 2]); }
+          if (my_boxes >= 1) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); cl_mbar_arrive(&c_free[my_boxes - 1]); }
+        }
+        CL_STAMP(3, 1);
+        if (++eb == p.ec) { eb = 0; eph ^= 1u; }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -480,6 +584,12 @@ static int launch_cluster(const char* who, const void* A, int64_t lda, const voi
   p.dW = dW; p.lddw = lddw; p.K_real = k_real;
   static const int dbg_env = [] { const char* e = getenv("DFOL_CL_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = dbg_env;
+  static const int trace_env = [] { const char* e = getenv("DFOL_CL_TRACE"); return e ? atoi(e) : 0; }();
+  p.trace = nullptr;
+  if (trace_env) {
+    cudaMalloc(&p.trace, 4 * 16 * 16 * sizeof(long long));
+    cudaMemset(p.trace, 0, 4 * 16 * 16 * sizeof(long long));
+  }
   static const int mc_env = [] { const char* e = getenv("DFOL_CL_MC"); return e ? atoi(e) : 1; }();
   p.mc = mc_env;
   if (dW != nullptr) {
@@ -490,8 +600,9 @@ static int launch_cluster(const char* who, const void* A, int64_t lda, const voi
   const size_t b_bytes = (size_t)num_kb * p.BNh * CL_BK * 2;
   const size_t box = (size_t)CL_BM * 128;
   static const int ec_env = [] { const char* e = getenv("DFOL_CL_EC"); return e ? atoi(e) : 0; }();
-  // (with the fused weight gradient the ring needs the room more than the operand tiles do: two tiles, four stages)
-  p.ec = (ec_env >= 2 && ec_env <= CL_EC) ? ec_env : (dW != nullptr ? 2 : CL_EC);
+  // two operand tiles (each goes back to the loads as soon as the store warp's bulk store has read it) leave room for a
+  // ring of one whole tile: c4 dgrad 0.314 ms with three tiles / three stages, 0.296 ms with two / five
+  p.ec = (ec_env >= 2 && ec_env <= CL_EC) ? ec_env : 2;
   const size_t tiles_bytes = (size_t)(p.BNh / 64) * box * (has_e ? p.ec : 1);  // dgrad: in-place operand/result tiles
   const size_t a_stage = (size_t)CL_BM * CL_BK * 2;
   DFOL_REQUIRE(!has_e || bias == nullptr, "%s: the multiplier epilogue has no bias", who);
@@ -545,6 +656,22 @@ static int launch_cluster(const char* who, const void* A, int64_t lda, const voi
   {
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ma, mb, mc, me, p);
     if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return (int)e; }
+  }
+  if (p.trace != nullptr) {   // timing experiment: per-tile stamps of block 0 (cycles relative to the first stamp)
+    static long long host[4 * 16 * 16];
+    cudaDeviceSynchronize();
+    cudaMemcpy(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost);
+    cudaFree(p.trace);
+    long long t0 = 0;
+    for (int i = 0; i < 4 * 16 * 16; ++i) if (host[i] && (!t0 || host[i] < t0)) t0 = host[i];
+    static const char* names[4] = {"load", "mma ", "epi ", "stor"};
+    fprintf(stderr, "[%s trace] M=%d N=%d K=%d stages=%d ec=%d wg=%d\n", who, M, N, K, p.stages, p.ec, dW != nullptr);
+    for (int t = 0; t < 12; ++t)
+      for (int r = 0; r < 4; ++r) {
+        fprintf(stderr, "  tile %2d %s:", t, names[r]);
+        for (int k = 0; k < 10; ++k) fprintf(stderr, " %7lld", host[(r * 16 + t) * 16 + k] ? host[(r * 16 + t) * 16 + k] - t0 : -1);
+        fprintf(stderr, "\n");
+      }
   }
   return finish_launch(who);
 }

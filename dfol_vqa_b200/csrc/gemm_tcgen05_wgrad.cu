@@ -75,9 +75,9 @@ __global__ void __launch_bounds__(WG_THREADS) gemm_bf16_tc_wgrad_kernel(const __
       if (lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+        int s = 0;
+        uint32_t phase = 0;   // ring slot and parity as running counters (no division on the single-thread path)
         for (int i = 0; i < num_kb; ++i) {
-          const int s = i % p.stages;
-          const uint32_t phase = (i / p.stages) & 1;
           mbar_wait(&empty_bar[s], phase ^ 1);
           mbar_expect_tx(&full_bar[s], stage_bytes);
           uint8_t* sa = tiles + (size_t)s * stage_bytes;
@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(WG_THREADS) gemm_bf16_tc_wgrad_kernel(const __
           tma_load_2d(&tmap_a, &full_bar[s], sa, m0, krow);
           tma_load_2d(&tmap_a, &full_bar[s], sa + 8192, m0 + 64, krow);
           for (int j = 0; j < nbox; ++j) tma_load_2d(&tmap_b, &full_bar[s], sa + a_bytes + j * 8192, n0 + 64 * j, krow);
+          if (++s == p.stages) { s = 0; phase ^= 1u; }
         }
       }
     } else if (warp == 1) {
@@ -92,9 +93,9 @@ __global__ void __launch_bounds__(WG_THREADS) gemm_bf16_tc_wgrad_kernel(const __
         // D = F32, A = B = BF16, both MN-major (bits 15, 16), N = BN, M = 128
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(WG_BM >> 4) << 24);
+        int s = 0;
+        uint32_t phase = 0;
         for (int i = 0; i < num_kb; ++i) {
-          const int s = i % p.stages;
-          const uint32_t phase = (i / p.stages) & 1;
           mbar_wait(&full_bar[s], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(WG_THREADS) gemm_bf16_tc_wgrad_kernel(const __
             umma_bf16(tmem_base, da + 128 * k, db + 128 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
+          if (++s == p.stages) { s = 0; phase ^= 1u; }
         }
         umma_commit(&tmem_full_bar);
       }
