@@ -11,7 +11,8 @@
 //   MMA-A  acc[128 x C]   = DZ (128 x S) . Wslots (S x C)       K = S (16 or 32 slices, bf16), fp32 in TMEM
 //   MMA-B  dWt[C x S]    += H2^T (C x 128) . DZ (128 x S)       per image, accumulated in TMEM over the image's tiles
 //   epilogue: dZ2 = acc * h (1 - h) written IN PLACE over the H2 tile (bf16, 128-byte swizzle), stored by TMA
-//   MMA-C  colsum[C]     += dZ2^T (C x 128) . ones              accumulated in TMEM over all tiles of the CTA
+//   colsum[C] += column sums of the dZ2 tile, by the epilogue warps from shared memory (registers over all tiles of the
+//                CTA; round 2 had them as a third MMA against a tile of ones: 24 MN-major MMAs, ~4600 cycles per tile)
 // H2 is read once and dZ2 written once (the algorithmic traffic); the operands of MMA-B / MMA-C are the SAME shared
 // tiles seen through MN-major descriptors (rows = K), the slice gradients DZ are one small tile ([S][128] bf16) that
 // serves MMA-A as an MN-major A operand and MMA-B as a K-major B operand.
@@ -22,15 +23,17 @@
 //   warp 1 (lane 0)  tcgen05.mma issuer (+ TMEM allocation)
 //   warps 2-5        DZ builders: thread = row, gathers g and LL of the tile's S slices, writes the DZ tile, keeps the
 //                    db partial sums in registers until the image ends
-//   warps 6-13       epilogue (TMEM lane quadrant = warp % 4, column half = (warp - 6) / 4)
+//   warps 6-13       epilogue (TMEM lane quadrant = warp % 4, column half = (warp - 6) / 4) + column sums
+//   warp 14 (lane 0) store warp: bulk store of the finished tile, hands the buffer back when the store has read it
 // Every mbarrier wait is bounded (trap instead of hanging the GPU).
+#include <cstdio>
 #include <cstdlib>
 #include "tc_common.cuh"
 
 namespace dfol {
 
 constexpr int TM_BM = 128;
-constexpr int TM_THREADS = 64 + 128 + 256;
+constexpr int TM_THREADS = 64 + 128 + 256 + 32;   // producer, MMA issuer, 4 DZ warps, 8 epilogue warps, store warp
 constexpr uint32_t TM_BOX = 128 * 128;   // bytes of one 128-row x 64-column bf16 box
 constexpr int TM_MAX_NB = 5;             // columns <= 320
 constexpr uint32_t TM_ACC_COL = 0, TM_DW_COL = 320, TM_CS_COL = 416;   // TMEM columns (512 allocated)
@@ -44,6 +47,7 @@ struct TmParams {
   int debug;   // ablation switches (DFOL_TBL_DEBUG; results are wrong when set): 1 no gathers, 2 no epilogue math, 4 no MMA-B/C, 8 no store
   __nv_bfloat16* dZ; long long lddz;
   float* dW; long long ldw; float* db; float* dbelow;
+  long long* trace;   // DFOL_TBL_TRACE=1: clock64 stamps of block 0's roles, first 16 active tiles ([role][tile][16])
 };
 
 __device__ __forceinline__ uint64_t tm_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -74,6 +78,11 @@ __device__ __forceinline__ void tm_prefetch_l2(const CUtensorMap* map, int c0, i
 __device__ __forceinline__ uint32_t tm_swz(int row, int piece) {  // 16-byte piece of a 128-byte row, 128B swizzle
   return (uint32_t)(row * 128 + ((piece ^ (row & 7)) << 4));
 }
+
+#define TM_STAMP(role, k)                                                                              \
+  do {                                                                                                 \
+    if (p.trace != nullptr && blockIdx.x == 0 && i < 16) p.trace[((role) * 16 + i) * 16 + (k)] = clock64(); \
+  } while (0)
 
 // walk over the (image, tile) pairs of this CTA
 struct TmTile {
@@ -108,7 +117,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
                                const __grid_constant__ CUtensorMap tmap_z, TmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t h_full[2], dz_full[2], dz_free[2], buf_free[2];
-  __shared__ __align__(8) uint64_t mma_done, acc_empty, dz2_ready, all_done;
+  __shared__ __align__(8) uint64_t mma_done, acc_empty, st_ready, all_done;
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,9 +132,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&h_full[i], 1); mbar_init(&dz_full[i], 128); mbar_init(&dz_free[i], 1); mbar_init(&buf_free[i], 2);
+      mbar_init(&h_full[i], 1); mbar_init(&dz_full[i], 128); mbar_init(&dz_free[i], 1);
+      mbar_init(&buf_free[i], 1u + (uint32_t)p.NB);   // the tile's store has read it + the NB column-sum warps
     }
-    mbar_init(&mma_done, 1); mbar_init(&acc_empty, 8); mbar_init(&dz2_ready, 1); mbar_init(&all_done, 1);
+    mbar_init(&mma_done, 1); mbar_init(&acc_empty, 8); mbar_init(&st_ready, 1); mbar_init(&all_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -179,7 +189,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
         prefetch_next();
         const int buf = i & 1;
         const uint32_t n = (uint32_t)(i >> 1);
+        TM_STAMP(0, 0);
         mbar_wait(&buf_free[buf], (n & 1) ^ 1);
+        TM_STAMP(0, 1);
         mbar_expect_tx(&h_full[buf], stage_bytes);
         const int row = p.row0[t.b] + t.c;
         for (int k = 0; k < NB; ++k) tma_load_2d(&tmap_h, &h_full[buf], h_tile(buf) + (size_t)k * TM_BOX, 64 * k, row);
@@ -197,28 +209,16 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
       const uint32_t idB = id_base | (1u << 15) | ((uint32_t)(SP >> 3) << 17);   // A MN-major, B K-major, N = SP
       const uint32_t idC = id_base | (1u << 15) | ((uint32_t)(16 >> 3) << 17);
       int i = 0, prev_b = -1;
-      auto issue_colsum = [&](int it) {
-        const int cb = it & 1;
-        mbar_wait(&dz2_ready, (uint32_t)(it & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t hs = smem_u32(h_tile(cb)), os = smem_u32(ones_tile);
-        for (int k = 0; k < ((p.debug & 4) ? 1 : TM_BM / 16); ++k) {
-          const uint64_t db = make_smem_desc(os + (uint32_t)(k >> 2) * 2048u + 32u * (k & 3));
-          for (int m = 0; m < mblocks; ++m) {
-            const int mb = min(2 * m, NB - 2);
-            umma_bf16(tmem_base + TM_CS_COL + (uint32_t)(m * 16), tm_desc_mn(hs + (uint32_t)mb * TM_BOX + 2048u * k, TM_BOX),
-                      db, idC, (it == 0 && k == 0) ? 0u : 1u);
-          }
-        }
-        umma_commit(&buf_free[cb]);
-      };
       for (; t.valid(); t.next(p)) {
         t.load(p, SP);
         if (t.Sb <= 0) continue;
         const int buf = i & 1;
         const uint32_t n = (uint32_t)(i >> 1);
+        TM_STAMP(1, 0);
         mbar_wait(&h_full[buf], n & 1);
+        TM_STAMP(1, 1);
         mbar_wait(&dz_full[buf], n & 1);
+        TM_STAMP(1, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t hs = smem_u32(h_tile(buf)), ws = smem_u32(w_tile(buf));
         const uint32_t ds = smem_u32(dz_tiles + (size_t)buf * 2 * WBOX);
@@ -238,7 +238,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
           }
         };
         if (!fresh) issue_dw();
+        TM_STAMP(1, 3);
         mbar_wait(&acc_empty, (uint32_t)(i & 1) ^ 1u);   // the epilogue of tile i-1 has drained the accumulators
+        TM_STAMP(1, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // MMA-A: acc = DZ . Wslots   (A: DZ MN-major, M = row, K = slice; B: Wslots MN-major, K = slice, N = column)
 #pragma unroll
@@ -252,13 +254,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
         if (fresh) issue_dw();
         umma_commit(&mma_done);
         umma_commit(&dz_free[buf]);
+        TM_STAMP(1, 5);
         prev_b = t.b;
-        // MMA-C of the PREVIOUS tile (colsum += dZ2^T . ones over the tile the epilogue has overwritten in place) is
-        // issued behind this tile's MMA-A / MMA-B, so that it is off the path MMA -> epilogue -> MMA
-        if (i > 0) issue_colsum(i - 1);
         ++i;
       }
-      if (i > 0) issue_colsum(i - 1);
       umma_commit(&all_done);
     }
   } else if (warp < 6) {
@@ -273,7 +272,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
       if (t.Sb <= 0) continue;
       const int buf = i & 1;
       const uint32_t n = (uint32_t)(i >> 1);
+      if (l == 0) TM_STAMP(2, 0);
       mbar_wait(&dz_free[buf], (n & 1) ^ 1);
+      if (l == 0) TM_STAMP(2, 1);
       uint8_t* dz = dz_tiles + (size_t)buf * 2 * WBOX + (size_t)(l >> 6) * WBOX;
       const int lc = l & 63;
       const bool ok = l < t.cn;
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tm_arrive(&dz_full[buf]);
+      if (l == 0) TM_STAMP(2, 2);
       if (t.last_of_image) {   // db[wrow_j] += sum over the image's rows handled by this CTA
 #pragma unroll
         for (int j = 0; j < SP; ++j) {
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
       }
       ++i;
     }
-  } else {
+  } else if (warp < 14) {
     // ------------------------------------------------------------------ epilogue (256 threads)
     const int quad = warp & 3;
     const int ch = (warp - 6) >> 2;
@@ -319,8 +321,16 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
     const int chunks = NB * 4;                  // 16-column chunks of the tile
     const int c_begin = ch == 0 ? 0 : (chunks + 1) / 2, c_end = ch == 0 ? (chunks + 1) / 2 : chunks;
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-    bool store_pending = false;
-    int pending_buf = 0;
+    // column sums of dZ2 (bias gradient of the layer below): warp `box` of the epilogue group sums box `box` of the
+    // finished tile from shared memory -- lane = (row quarter, 16-byte piece), eight consecutive lanes read one whole
+    // 128-byte row (conflict free) -- and keeps 8 column sums in registers over all tiles of the CTA.  (As 24 MN-major
+    // tcgen05 MMAs against a tile of ones this cost ~4600 cycles of tensor-pipe time per tile, and the tile's buffer
+    // could not go back to the loads before they had run: clock stamps, DFOL_TBL_TRACE.)
+    float cs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] = 0.0f;
+    const bool cs_thread = te < NB * 32;
+    const int cs_box = te >> 5, cs_rq = (te >> 3) & 3, cs_piece = te & 7;
     int i = 0;
     for (; t.valid(); t.next(p)) {
       t.load(p, SP);
@@ -336,15 +346,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
       }
       const int buf = i & 1;
       const uint32_t n = (uint32_t)(i >> 1);
+      if (issuer) TM_STAMP(3, 0);
       mbar_wait(&mma_done, (uint32_t)(i & 1));
+      if (issuer) TM_STAMP(3, 1);
       mbar_wait(&h_full[buf], n & 1);   // (already complete: acquires the TMA writes for this thread's generic reads)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (issuer && store_pending) {
-        // the previous tile's TMA store has had the whole MMA phase to read its buffer: hand it back to the producer
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        tm_arrive(&buf_free[pending_buf]);
-        store_pending = false;
-      }
+      if (issuer) TM_STAMP(3, 2);
       uint8_t* hb = h_tile(buf);
       uint32_t r[2][16];
       tmem_ld16(trow + TM_ACC_COL + (uint32_t)(16 * c_begin), r[0]);
@@ -373,6 +380,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
         *q0 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *q1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
+      if (issuer) TM_STAMP(3, 3);
       if (t.last_of_image) {
         // flush the image's dW rows: block m of the transposed accumulator holds columns 64 * mb + row
         for (int m = ch; m < mblocks; m += 2) {
@@ -398,23 +406,35 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
         }
       }
       // accumulators drained (and flushed): the next tile's MMAs may overwrite them
+      if (issuer) TM_STAMP(3, 4);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) tm_arrive(&acc_empty);
-      // dZ2 tile complete in shared memory -> visible to the async proxy (TMA store, MMA-C)
+      // dZ2 tile complete in shared memory -> visible to the async proxy (TMA store) and to the column-sum warps
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tm_named_bar(1, 256);
-      if (t.cn == TM_BM) {
-        if (issuer) {
-          for (int k = 0; k < ((p.debug & 8) ? 0 : NB); ++k) tm_store_2d(&tmap_z, hb + (size_t)k * TM_BOX, 64 * k, (int)grow);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          tm_arrive(&dz2_ready);
-          store_pending = true;
-          pending_buf = buf;
+      if (issuer) TM_STAMP(3, 5);
+      if (t.cn == TM_BM && issuer) tm_arrive(&st_ready);   // the store warp stores the tile and frees its buffer
+      if (cs_thread) {
+        const uint8_t* cb = hb + (size_t)cs_box * TM_BOX;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+          const int r = cs_rq * 32 + k;   // (rows beyond the image's last one hold zeros: their DZ rows are zero)
+          const uint4 v = *reinterpret_cast<const uint4*>(cb + tm_swz(r, cs_piece));
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+            cs[2 * j] += f.x;
+            cs[2 * j + 1] += f.y;
+          }
         }
-      } else {
+        __syncwarp();
+        if (lane == 0) tm_arrive(&buf_free[buf]);
+      }
+      if (issuer) TM_STAMP(3, 6);
+      if (t.cn != TM_BM) {
         // partial tile at the end of an image: a box store would run into the next image's rows
-        if (issuer) tm_arrive(&dz2_ready);
         const int pieces = NB * 8;
         for (int idx = te; idx < t.cn * pieces; idx += 256) {
           const int rr = idx / pieces, pc = idx - rr * pieces;
@@ -426,27 +446,40 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
       }
       ++i;
     }
-    if (issuer && store_pending) {
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      tm_arrive(&buf_free[pending_buf]);
-    }
     if (i > 0) {
-      // column sums of dZ2 over this CTA's tiles -> bias gradient of the layer below
-      mbar_wait(&all_done, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int m = ch; m < mblocks; m += 2) {
-        const int mb = min(2 * m, NB - 2);
-        const int e = 64 * mb + row;
-        uint32_t w[16];
-        tmem_ld16(trow + TM_CS_COL + (uint32_t)(m * 16), w);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (p.dbelow != nullptr && e >= 128 * m && e < p.E) {
-          const float v = __uint_as_float(w[0]);
-          if (v != 0.0f) atomicAdd(p.dbelow + e, v);
+      mbar_wait(&all_done, 0);   // (every MMA of the CTA has completed before the accumulators are released)
+      if (cs_thread && p.dbelow != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int e = 64 * cs_box + 8 * cs_piece + j;
+          if (e < p.E && cs[j] != 0.0f) atomicAdd(p.dbelow + e, cs[j]);
         }
       }
     }
-    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else {
+    // ------------------------------------------------------------------ store warp (one lane): dZ2 tile -> global by TMA,
+    // off the epilogue's path; the buffer goes back to the loads as soon as the bulk store has read it
+    if (lane == 0) {
+      int i = 0;
+      uint32_t fulls = 0;
+      for (; t.valid(); t.next(p)) {
+        t.load(p, SP);
+        if (t.Sb <= 0) continue;
+        const int buf = i & 1;
+        if (t.cn == TM_BM) {
+          mbar_wait(&st_ready, fulls & 1u);
+          ++fulls;
+          const long long grow = (long long)p.row0[t.b] + t.c;
+          uint8_t* hb = h_tile(buf);
+          for (int k = 0; k < ((p.debug & 8) ? 0 : NB); ++k) tm_store_2d(&tmap_z, hb + (size_t)k * TM_BOX, 64 * k, (int)grow);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          tm_arrive(&buf_free[buf]);
+        }
+        ++i;
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -512,6 +545,12 @@ extern "C" int dfol_table_layer_bwd_mma(const float* g, const int32_t* slice_gof
   p.images = image_num; p.total_tiles = total_tiles; p.E = E; p.NB = NB;
   static const int dbg = [] { const char* e = getenv("DFOL_TBL_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = dbg;
+  static const int trace_env = [] { const char* e = getenv("DFOL_TBL_TRACE"); return e ? atoi(e) : 0; }();
+  p.trace = nullptr;
+  if (trace_env) {
+    cudaMalloc(&p.trace, 4 * 16 * 16 * sizeof(long long));
+    cudaMemset(p.trace, 0, 4 * 16 * 16 * sizeof(long long));
+  }
   p.dZ = reinterpret_cast<__nv_bfloat16*>(dZ); p.lddz = lddz; p.dW = dW; p.ldw = ldw; p.db = db; p.dbelow = dbelow;
   const size_t wbox = (size_t)SP * 128;
   const size_t smem = 2 * (size_t)NB * (TM_BOX + wbox) + 4 * wbox + 4096 + 1024;
@@ -530,6 +569,22 @@ extern "C" int dfol_table_layer_bwd_mma(const float* g, const int32_t* slice_gof
     e = cudaFuncSetAttribute(table_layer_bwd_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return (int)e; }
     table_layer_bwd_mma_kernel<32><<<grid, TM_THREADS, smem, st>>>(mh, mw, mz, p);
+  }
+  if (p.trace != nullptr) {   // timing experiment: per-tile stamps of block 0 (cycles relative to the first stamp)
+    static long long host[4 * 16 * 16];
+    cudaDeviceSynchronize();
+    cudaMemcpy(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost);
+    cudaFree(p.trace);
+    long long t0 = 0;
+    for (int i = 0; i < 4 * 16 * 16; ++i) if (host[i] && (!t0 || host[i] < t0)) t0 = host[i];
+    static const char* names[4] = {"load", "mma ", "dz  ", "epi "};
+    fprintf(stderr, "[%s trace] tiles=%d SP=%d NB=%d\n", who, total_tiles, SP, NB);
+    for (int t = 0; t < 12; ++t)
+      for (int r = 0; r < 4; ++r) {
+        fprintf(stderr, "  tile %2d %s:", t, names[r]);
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld", host[(r * 16 + t) * 16 + k] ? host[(r * 16 + t) * 16 + k] - t0 : -1);
+        fprintf(stderr, "\n");
+      }
   }
   return finish_launch(who);
 }
