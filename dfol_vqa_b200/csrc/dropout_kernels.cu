@@ -2,7 +2,7 @@
 // EmbeddingLayer: nsvqa/nn/vision/regular_mlp.py:29-32, embedding_layer.py:73; sample_config.yaml: dropout 0.1).
 //
 // The keep/drop decision of element (row, col) of dropout site `site` is a pure function of (seed, site, row, col):
-// Philox4x32-10 keyed by the seed, counter = (group of 8 consecutive columns of the row, site), 16 bits per element,
+// a counter-based hash keyed by the seed, counter = (group of 8 consecutive columns of the row, site), 16 bits per element,
 // keep iff bits >= round(p * 65536); kept elements are scaled by 1 / (1 - p) like torch.nn.functional.dropout.
 // Nothing is stored: every kernel that needs a mask recomputes it, and the parity tests export the very same masks
 // (dfol_dropout_scale on a tensor of ones) for the CPU oracle -- the reference's own RNG stream cannot be matched.
@@ -12,17 +12,25 @@
 
 namespace dfol {
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += W0;
-    k.y += W1;
-  }
-  return c;
+// Four 32-bit words (= 8 elements of 16 bits) per counter: the counter, the site and the seed are folded into one
+// word with odd multipliers, and each output word is a full-avalanche finalizer (the 32-bit finalizer of MurmurHash3:
+// xor-shift 16, multiply, xor-shift 13, multiply, xor-shift 16) of that word advanced by a distinct odd constant and
+// keyed by the second seed word.  ~40 integer instructions per 8 elements; the Philox4x32-10 of round 1 (~80) made
+// the mask generation the issue-bound part of dfol_pair_features_dropout (642 M elements per c1 batch).  A dropout
+// mask needs independent-looking Bernoulli(1 - p) decisions, not a cryptographic stream; tests/test_gpu_dropout.py
+// checks the keep rate per site, row and column and the independence of neighbouring elements and sites.
+__device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint4 drop_words(uint32_t g_lo, uint32_t g_hi, uint32_t site, uint2 k) {
+  const uint32_t h = fmix32(g_lo * 0x9E3779B1u + (g_hi * 0x85EBCA77u ^ site * 0xC2B2AE3Du ^ k.x));
+  return make_uint4(fmix32(h ^ k.y), fmix32((h + 0x27D4EB2Fu) ^ k.y), fmix32((h + 0x165667B1u) ^ k.y),
+                    fmix32((h + 0x7F4A7C15u) ^ k.y));
 }
 
 struct DropSite {
@@ -35,7 +43,7 @@ struct DropSite {
 // scale factors (0 or 1/(1-p)) of the 8 elements of column group `g8` of `row`
 __device__ __forceinline__ void drop_scales8(const DropSite& d, long long row, long long g8, float s[8]) {
   const unsigned long long g = (unsigned long long)row * (unsigned long long)d.groups_per_row + (unsigned long long)g8;
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), d.site, 0u), d.key);
+  const uint4 r = drop_words((uint32_t)g, (uint32_t)(g >> 32), d.site, d.key);
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

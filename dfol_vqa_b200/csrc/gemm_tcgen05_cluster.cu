@@ -288,8 +288,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
         if (WG && p.stages == num_kb) {
           // The ring holds exactly one tile (stage kb = k-block kb, adjacent stages 16 KB apart like the boxes of an
           // MN-major operand): the weight-gradient MMAs take TWO k-blocks at once (N = 128), which halves the fetches of
-          // their M operand -- MN-major operand reads are what bounds them (~120 cycles per 128 x 64 x 16 MMA measured,
-          // 32 by the tensor pipe).  They go first: they do not touch the dgrad accumulator, which the epilogue of the
+          // their M operand -- operand reads from shared memory are what bounds these MMAs (measured per MMA, from the
+          // issue stamps of DFOL_CL_TRACE: 128 x 64 x 16 MN-major ~120 cycles, 128 x 128 x 16 MN-major ~140, the K-major
+          // 128 x 128 x 16 of the dgrad ~93 -- 60-90 B/clk of operand bytes -- against 32 / 64 / 64 by the tensor pipe;
+          // interleaving the independent accumulator chains changes nothing).  They go first: they do not touch the dgrad accumulator, which the epilogue of the
           // previous tile may still be copying to registers.
           for (int kb = 0; kb < num_kb; kb += 2) {
             const int nk = min(2, num_kb - kb);

@@ -310,7 +310,7 @@ int dfol_program_bwd_fast(const int32_t* instr, const int32_t* q_instr, const in
 /* ---------------------------------------------------------------------------------------------------------
  * Training-mode dropout of the oracle networks (nn.Dropout in front of every Linear: nsvqa/nn/vision/regular_mlp.py:
  * 29-32, embedding_layer.py:73; sample_config.yaml: dropout 0.1).  The keep/drop decision of element (row, col) of
- * dropout site `site` is a pure function of (seed, site, row, col) (Philox4x32-10, 16 bits per element); kept elements
+ * dropout site `site` is a pure function of (seed, site, row, col) (counter-based hash, 16 bits per element); kept elements
  * are scaled by 1/(1-p).  dfol_dropout_scale multiplies a row-major matrix in place (run it on a tensor of ones to
  * export a mask); dfol_pair_features_dropout writes the masked relation-network input rows
  * mask .* [obj_s | obj_o | geo(s,o)] of all pairs (batch_gqa_boxfeatures_pipeline.py:260-281), zero beyond 2*width+4.

@@ -48,6 +48,15 @@ def test_mask_statistics_and_determinism(p):
     k = (a > 0).float() - (1.0 - p)
     assert abs(float((k[:, 1:] * k[:, :-1]).mean())) < 5 * p * (1 - p) / (rows * cols) ** 0.5
     assert abs(float((k[1:] * k[:-1]).mean())) < 5 * p * (1 - p) / (rows * cols) ** 0.5
+    # ... nor between sites / seeds, at lag 8 (the next group of the counter) or inside a group; rows and columns keep
+    # at the nominal rate
+    tol = 5 * p * (1 - p) / (rows * cols) ** 0.5
+    for other in (export_mask(rows, cols, 1234, 4, p), export_mask(rows, cols, 1235, 3, p)):
+        assert abs(float((k * ((other > 0).float() - (1.0 - p))).mean())) < tol
+    for lag in (2, 7, 8, 16):
+        assert abs(float((k[:, lag:] * k[:, :-lag]).mean())) < tol
+    assert float(((a > 0).float().mean(1) - (1.0 - p)).abs().max()) < 6 * (p * (1 - p) / cols) ** 0.5
+    assert float(((a > 0).float().mean(0) - (1.0 - p)).abs().max()) < 6 * (p * (1 - p) / rows) ** 0.5
     # the bf16 variant takes the same decisions
     b = export_mask(rows, cols, 1234, 3, p, torch.bfloat16)
     assert torch.equal(b > 0, a > 0)

@@ -8,7 +8,10 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SCALE = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'us': 1e-3, 'ms': 1.0, 'ns': 1e-6, 's': 1e3}
 TAGS = [('gemm_bf16_tc_cluster_kernel<2, 0>', 'pair_layer_fwd_cluster[Px300x256]'),
+        ('gemm_bf16_tc_cluster_kernel<2, 0, 0>', 'pair_layer_fwd_cluster[Px300x256]'),
         ('gemm_bf16_tc_cluster_kernel<0, 1>', 'pair_layer_dgrad_cluster[Px256x320]'),
+        ('gemm_bf16_tc_cluster_kernel<0, 1, 0>', 'pair_layer_dgrad_cluster[Px256x320]'),
+        ('gemm_bf16_tc_cluster_kernel<0, 1, 1>', 'pair_layer_dgrad_wgrad_cluster[Px256x320]'),
         ('table_layer_bwd_mma_kernel', 'table_layer_bwd_mma[rel]'),
         ('pair_hidden_fwd_tc_kernel', 'pair_hidden_fwd_tc'), ('pair_hidden_bwd', 'pair_hidden_bwd_tc'),
         ('rel_slots_tc_kernel', 'rel_slots_fwd_tc'), ('program_fwd_kernel', 'program_fwd'),
@@ -53,9 +56,9 @@ def main():
                     if rd + wr > seen.get(key, 0):
                         seen[key] = rd + wr
                         traffic[key] = rd + wr
-            if 'gemm_bf16_tc_wgrad_kernel' in name and rd + wr > traffic.get('gemm_bf16_tc_wgrad[300x256xP]@' + workload, 0):
+            if 'gemm_bf16_tc_wgrad_kernel' in name and rd + wr > max(2e8, traffic.get('gemm_bf16_tc_wgrad[300x256xP]@' + workload, 0)):   # (pair-level launches only)
                 traffic['gemm_bf16_tc_wgrad[300x256xP]@' + workload] = rd + wr
-            if 'table_layer_bwd_tc_kernel' in name and rd + wr > traffic.get('table_layer_bwd_tc[rel]@' + workload, 0):
+            if 'table_layer_bwd_tc_kernel' in name and rd + wr > max(1e8, traffic.get('table_layer_bwd_tc[rel]@' + workload, 0)):
                 traffic['table_layer_bwd_tc[rel]@' + workload] = rd + wr
     json.dump(traffic, open(os.path.join(REPO, 'profiles', 'r2_traffic.json'), 'w'), indent=1, sort_keys=True)
     print('\n'.join(out))
