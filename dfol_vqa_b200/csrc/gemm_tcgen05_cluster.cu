@@ -10,7 +10,7 @@
 //                       columns.
 //   warp 1 (one lane) : tcgen05.mma issuer, 128 x BNh x 16, fp32 accumulators double buffered in TMEM;
 //                       tcgen05.commit.multicast releases a ring stage in ALL CTAs of the cluster.
-//   warps 2..9        : epilogue: tcgen05.ld, bias + activation or activation-derivative multiplier (operand read from
+//   warps 2..9        : epilogue (8 warps: 4 TMEM lane quadrants x 2 column parts; DFOL_CL_EPI_WARPS): tcgen05.ld, bias + activation or activation-derivative multiplier (operand read from
 //                       the 128B-swizzled shared tile, conflict free), bf16 result written to a swizzled shared tile
 //                       -- no per-thread global access.
 //   warp 10 (one lane): store warp: waits until the eight epilogue warps have published the tile, issues the
@@ -34,14 +34,19 @@ namespace dfol {
 
 constexpr int CL_BM = 128;
 constexpr int CL_BK = 64;
-constexpr int CL_THREADS = 64 + 256 + 32;   // producer, MMA issuer, 8 epilogue warps, store warp
+#ifndef DFOL_CL_EPI_WARPS
+#define DFOL_CL_EPI_WARPS 8   // (16 measured level: forward 0.173 against 0.179 ms at c1 size, dgrad 0.310 against 0.298)
+#endif
+constexpr int CL_EW = DFOL_CL_EPI_WARPS;    // epilogue warps: 4 TMEM lane quadrants x CL_EW / 4 column parts
+constexpr int CL_CP = CL_EW / 4;            // column parts of a CTA's BNh columns
+constexpr int CL_THREADS = 64 + 32 * CL_EW + 32;   // producer, MMA issuer, epilogue warps, store warp
 constexpr int CL_MAX_STAGES = 8;
 constexpr int CL_MAX_KB = 5;
 constexpr int CL_ABOX = 2;        // row boxes per A block, dealt round-robin to the CTAs of the cluster
 constexpr int CL_EC = 3;          // in-place operand/result tiles of the dgrad (operand prefetched two tiles ahead)
-constexpr int CL_MAX_CH = 6;      // 16-column chunks per epilogue warp (192 / 2 / 16)
+constexpr int CL_MAX_CH = 192 / CL_CP / 16;   // 16-column chunks per epilogue warp
 constexpr int CL_MAX_BOX = 3;     // 64-column boxes per staging tile (BNh <= 192)
-constexpr int CL_WG_CH = 4;       // the same with the fused weight gradient (BNh = 128: 64 columns held in registers)
+constexpr int CL_WG_CH = 128 / CL_CP / 16;   // the same with the fused weight gradient (BNh = 128: held in registers)
 
 struct ClParams {
   const float* bias;
@@ -184,14 +189,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
   if (threadIdx.x == 0) {
     mbar_init(&b_full, 1);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], p.mc ? CS : 1u); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], CL_EW); }
     for (int i = 0; i < CL_EC; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], 1); }
     mbar_init(&w_full, 1);
     for (int b = 0; b < CL_MAX_BOX; ++b) {
-      // epilogue warps that write into box b: four per column half that overlaps it
+      // epilogue warps that write into box b: four per column part that overlaps it
       uint32_t cnt = 0;
-      for (int h = 0; h < 2; ++h)
-        if (h * (BNh / 2) < 64 * (b + 1) && (h + 1) * (BNh / 2) > 64 * b) cnt += 4;
+      for (int h = 0; h < CL_CP; ++h)
+        if (h * (BNh / CL_CP) < 64 * (b + 1) && (h + 1) * (BNh / CL_CP) > 64 * b) cnt += 4;
       for (int i = 0; i < CL_EC; ++i) mbar_init(&c_ready[i][b], cnt > 0 ? cnt : 1u);
       mbar_init(&c_free[b], 1);
     }
@@ -363,12 +368,12 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
       }
       if (WG) umma_commit(&w_full);
     }
-  } else if (warp < 10) {
-    // ---------------- epilogue: warps 2..9; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 ----------------
+  } else if (warp < 2 + CL_EW) {
+    // ---------------- epilogue: warps 2..; TMEM lane quadrant = warp % 4, column part = (warp - 2) / 4 ----------------
     const int quad = warp & 3;
     const int ch = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
-    const int cw = BNh / 2;
+    const int cw = BNh / CL_CP;
     const int cbeg = ch * cw;
     const int nchunks = cw / 16;
     const bool stamper = (warp == 2 && lane == 0);
@@ -488,7 +493,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
       // consecutive lanes add to consecutive addresses
       mbar_wait(&w_full, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int kw = p.K / 2;                       // dW rows of this column half (multiple of 16: K % 64 == 0 ...)
+      const int kw = p.K / CL_CP;                   // dW rows of this column part (multiple of 16: K % 64 == 0)
       const uint32_t wrow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)BNh;
       const int col = n0 + row;
       for (int k0 = ch * kw; k0 < (ch + 1) * kw && k0 < p.K_real; k0 += 16) {

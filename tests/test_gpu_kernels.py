@@ -408,7 +408,8 @@ def test_pair_layer_dgrad_resident_gemm(M, N, K, mode, impl):
     assert torch.allclose(dX.double(), ref, rtol=1.5e-2, atol=1.5e-2), (dX.double() - ref).abs().max()
 
 
-@pytest.mark.parametrize('M,N,K,k_real', [(1000, 256, 320, 300), (4608 * 3 + 5, 256, 320, 300), (40000, 192, 256, 256),
+@pytest.mark.parametrize('M,N,K,k_real', [(100, 256, 320, 300), (129, 256, 320, 300), (1000, 256, 320, 300),
+                                          (4608 * 3 + 5, 256, 320, 300), (40000, 192, 256, 256),
                                           (300000, 256, 320, 300)])
 @pytest.mark.parametrize('mode,keep', [(2, 1.0), (1, 1.0), (2, 0.9)])
 def test_pair_layer_dgrad_with_fused_weight_gradient(M, N, K, k_real, mode, keep):
