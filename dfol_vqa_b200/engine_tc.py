@@ -175,7 +175,7 @@ class TensorCorePath(object):
             cls._wgrad(dz2, E, h1, H, gW2, st)
         if capi.trace is not None:
             capi.next_meta = {'tag': 'pair_layer_dgrad%s_cluster[Px%dx%d]' % ('_wgrad' if fused else '', H, Ep),
-                              'flops': (4.0 if fused else 2.0) * P * H * Ep, 'bytes': 2.0 * P * (Ep + 2 * Hp)}
+                              'flops': (4.0 if fused else 2.0) * P * H * E, 'bytes': 2.0 * P * (Ep + 2 * Hp)}   # (algorithmic: E, not the padded Ep)
         if fused:
             call('dfol_pair_layer_dgrad_wgrad_cluster', ptr(dz2), Ep, ptr(w2t), Ep, ptr(dz1), Hp, Hp, P, H, Ep, ptr(h1),
                  Hp, K.MUL_ELU_GRAD, keep, ptr(gW2), gW2.stride(0), E, st)
@@ -437,7 +437,7 @@ class TensorCorePath(object):
             if capi.trace is not None:
                 S = tabs['max_per_image']
                 capi.next_meta = {'tag': 'table_layer_bwd_mma[%s]' % tag, 'bytes': 4.0 * rows_total * cols,
-                                  'flops': 2.0 * rows_total * cols * (2 * (16 if S <= 16 else 32) + 16)}
+                                  'flops': 2.0 * rows_total * cols * (2 * (16 if S <= 16 else 32))}   # MMA-A + MMA-B
             wb = torch.empty(len(tabs['img_slice']) - 1, 32 * cols, device=dev, dtype=torch.bfloat16)
             call('dfol_table_layer_bwd_mma', ptr(g), ptr(tabs['goff']), ptr(tabs['col']), ptr(tabs['wrow']),
                  ptr(tabs['img_slice']), len(tabs['img_slice']) - 1, tabs['max_per_image'], ptr(ll), ptr(blk),
