@@ -47,6 +47,7 @@ struct TmParams {
   int debug;   // ablation switches (DFOL_TBL_DEBUG; results are wrong when set): 1 no gathers, 2 no epilogue math, 4 no MMA-B/C, 8 no store
   __nv_bfloat16* dZ; long long lddz;
   float* dW; long long ldw; float* db; float* dbelow;
+  int trace_first, trace_block;   // DFOL_TBL_TRACE=1+first tile of the window, DFOL_TBL_TRACE_BLOCK
   long long* trace;   // DFOL_TBL_TRACE=1: clock64 stamps of block 0's roles, first 16 active tiles ([role][tile][16])
 };
 
@@ -81,7 +82,8 @@ __device__ __forceinline__ uint32_t tm_swz(int row, int piece) {  // 16-byte pie
 
 #define TM_STAMP(role, k)                                                                              \
   do {                                                                                                 \
-    if (p.trace != nullptr && blockIdx.x == 0 && i < 16) p.trace[((role) * 16 + i) * 16 + (k)] = clock64(); \
+    if (p.trace != nullptr && blockIdx.x == p.trace_block && i >= p.trace_first && i < p.trace_first + 16)                       \
+      p.trace[((role) * 16 + i - p.trace_first) * 16 + (k)] = clock64();                                 \
   } while (0)
 
 // walk over the (image, tile) pairs of this CTA
@@ -547,6 +549,9 @@ extern "C" int dfol_table_layer_bwd_mma(const float* g, const int32_t* slice_gof
   p.debug = dbg;
   static const int trace_env = [] { const char* e = getenv("DFOL_TBL_TRACE"); return e ? atoi(e) : 0; }();
   p.trace = nullptr;
+  p.trace_first = trace_env > 0 ? trace_env - 1 : 0;
+  static const int trace_blk = [] { const char* e = getenv("DFOL_TBL_TRACE_BLOCK"); return e ? atoi(e) : 0; }();
+  p.trace_block = trace_blk;
   if (trace_env) {
     cudaMalloc(&p.trace, 4 * 16 * 16 * sizeof(long long));
     cudaMemset(p.trace, 0, 4 * 16 * 16 * sizeof(long long));
@@ -578,7 +583,7 @@ extern "C" int dfol_table_layer_bwd_mma(const float* g, const int32_t* slice_gof
     long long t0 = 0;
     for (int i = 0; i < 4 * 16 * 16; ++i) if (host[i] && (!t0 || host[i] < t0)) t0 = host[i];
     static const char* names[4] = {"load", "mma ", "dz  ", "epi "};
-    fprintf(stderr, "[%s trace] tiles=%d SP=%d NB=%d\n", who, total_tiles, SP, NB);
+    fprintf(stderr, "[%s trace] tiles=%d SP=%d NB=%d block=%d first=%d\n", who, total_tiles, SP, NB, p.trace_block, p.trace_first);
     for (int t = 0; t < 12; ++t)
       for (int r = 0; r < 4; ++r) {
         fprintf(stderr, "  tile %2d %s:", t, names[r]);
