@@ -39,6 +39,51 @@ class FastBoxFeaturizer(nn.Module):
             raise NotImplementedError('the fused path needs the featurizer network (Linear + Sigmoid)')
         self._featurizer_network = featurizer_network
 
+    def featurize_scene(self, device, objects_list, batch_index, meta_data=None):
+        """BatchGQABoxFeaturizer.featurize_scene (reference nsvqa/data/batch_gqa_boxfeatures_pipeline.py:199-281), default
+        branch (no pre-featurised relations, no ``object_pairs`` supervision), on the CUDA kernels -- forward only.
+
+        Returns the reference's dict: ``attribute_features`` (T, F + 4) = [sigmoid(X Wf^T + b) | box position],
+        ``relation_features`` = {'features': (P', 2 (F + 4) + 4) rows [obj_s | obj_o | dist | asin | sign x | sign y] of
+        all ordered pairs (s, o), s != o, of each image, 'index': [image, s, o] (global object rows)} in the order of
+        util.find_sparse_pair_indices (:87-103: subject-major), and ``object_num``.  FastGQAInterpreter.forward never
+        materialises this matrix (the first relation layer is evaluated as U[s] + V[o] + Wg.geo); this method exists for
+        callers that use the featurizer on its own, as BatchInterpreterBase.build_scene does."""
+        from .capi import K, call, ptr, stream_ptr
+        from .engine import SceneLayout, gemm_f32
+        from .networks import linear_layers
+        meta_data = meta_data or {}
+        if 'relation_features' in meta_data or 'object_pairs' in meta_data:
+            raise NotImplementedError('pre-featurised relations / object_pairs supervision are outside the fused path')
+        (feat,) = linear_layers(self._featurizer_network)
+        x = objects_list.to(device=device, dtype=torch.float32).contiguous()
+        assert x.is_cuda, 'dfol_vqa_b200 runs on CUDA tensors only (no CPU fallback)'
+        T, D = x.shape[0], x.shape[1] - 6
+        F = feat.weight.shape[0]
+        ldo = F + 4
+        st = stream_ptr(x.device)
+        obj = torch.empty(T, ldo, device=x.device, dtype=torch.float32)
+        with torch.no_grad():
+            gemm_f32(x[:, :D], feat.weight.t(), obj[:, :F], feat.bias, K.ACT_SIGMOID, stream=st)
+            call('dfol_box_position', ptr(x), x.stride(0), D, ptr(obj), ldo, F, T, st)
+            counts = torch.bincount(batch_index.to(x.device)).tolist()
+            lay = SceneLayout.get(counts, 1, 1, x.device)
+            width = 2 * ldo + 4
+            pm = torch.empty(lay.P, width, device=x.device, dtype=torch.float32)
+            if lay.P:
+                call('dfol_pair_features_dropout', ptr(obj), ldo, ldo, F, ptr(pm), width, width, 0, ptr(lay.pair_row),
+                     ptr(lay.obj_row), ptr(lay.img_n), ptr(lay.pair_img), lay.P, 0, 0, 0.0, st)
+            # (s, o) of every pair row, self pairs dropped: index bookkeeping of the reference's return value
+            img = lay.pair_img.long()
+            n = lay.img_n.long()[img]
+            local = torch.arange(lay.P, device=x.device) - lay.pair_row.long()[img]
+            s_loc, o_loc = local // n.clamp(min=1), local % n.clamp(min=1)
+            keep = s_loc != o_loc
+            base = lay.obj_row.long()[img]
+            index = [img[keep], (base + s_loc)[keep], (base + o_loc)[keep]]
+            relation = pm[keep] if bool(keep.any()) else None
+        return {'attribute_features': obj, 'relation_features': {'features': relation, 'index': index}, 'object_num': T}
+
 
 class FastClassifierOracle(nn.Module):
 
@@ -51,6 +96,53 @@ class FastClassifierOracle(nn.Module):
         self._embedding_network = embedding_network
         self._normalize = normalize
         self._cached = cached
+
+    def get_embedding(self, tokens, meta_data, device):
+        """OracleBase.get_embedding (reference nsvqa/nn/vision/base_oracle.py:45-55): word embeddings of concept tokens
+        (the calibrator's input), from the batch's pre-gathered table when it has one, else from the ontology."""
+        import numpy as np
+        if meta_data is not None:
+            try:
+                ind = [meta_data['index'][t] for t in tokens]
+                return meta_data['embedding'][ind, :]
+            except KeyError:
+                pass
+        return torch.from_numpy(np.asarray(self._ontology.get_embeddings(tokens))).float().to(device)
+
+    def compute_all_log_likelihood_2(self, object_features, pair_object_features):
+        """ClassifierOracle.compute_all_log_likelihood_2 (reference nsvqa/nn/vision/classifier_oracle.py:145-156) on the
+        CUDA GEMM kernels, forward only: (T, C) log-likelihoods of every concept for every object and (P', R)
+        log-likelihoods of every relation for every pair row (the embedding layer restricted to
+        ``ontology._relation_index``, i.e. the columns the reference slices).  Dense row-major results, as the reference
+        returns them; FastGQAInterpreter.forward uses the per-image table layout and demand-driven relation columns
+        instead."""
+        from .capi import K, stream_ptr
+        from .engine import gemm_f32
+        from .networks import linear_layers
+        (emb,) = linear_layers(self._embedding_network)
+
+        def chain(net, h, weight, bias):
+            layers = linear_layers(net)
+            st = stream_ptr(h.device)
+            for i, layer in enumerate(layers):
+                out = torch.empty(h.shape[0], layer.weight.shape[0], device=h.device, dtype=torch.float32)
+                gemm_f32(h, layer.weight.t(), out, layer.bias, K.ACT_ELU if i < len(layers) - 1 else K.ACT_SIGMOID,
+                         stream=st)
+                h = out
+            out = torch.empty(h.shape[0], weight.shape[0], device=h.device, dtype=torch.float32)
+            gemm_f32(h, weight.t(), out, bias, K.ACT_LOGSIGMOID, stream=st)
+            return out
+
+        with torch.no_grad():
+            x = object_features.float().contiguous()
+            assert x.is_cuda, 'dfol_vqa_b200 runs on CUDA tensors only (no CPU fallback)'
+            attr = chain(self._attribute_network, x, emb.weight, emb.bias)
+            rel = None
+            if pair_object_features is not None:
+                ridx = torch.as_tensor(self._ontology._relation_index, device=x.device, dtype=torch.long)
+                rel = chain(self._relation_network, pair_object_features.float().contiguous(),
+                            emb.weight[ridx].contiguous(), emb.bias[ridx].contiguous())
+        return attr, rel
 
 
 class _ReasoningFunction(torch.autograd.Function):
@@ -262,6 +354,22 @@ class FastGQAInterpreter(nn.Module):
             raise RuntimeError('dfol_vqa_b200 runs on CUDA only (no CPU fallback): move the program batch to the '
                                'GPU first (ProgramBatch.to_cuda)')
         return feats.float().contiguous()
+
+    def build_scene(self, device, object_features, batch_index, meta_data=None, is_training=False):
+        """BatchInterpreterBase.build_scene (reference nsvqa/nn/interpreter/batch_base_interpreter.py:45-70): featurizer +
+        visual oracle of a collated batch of images.  Returns the engine's ``Scene`` (per-image attribute / relation
+        log-likelihood tables in the layout of include/dfol_b200.h: the role of the reference's BatchWorld) instead of
+        dense (T, C) / (P', R) tensors.  Without a compiled program batch every relation column is evaluated
+        (fp32 parity mode; the tensor-core mode builds its demand-driven relation slots from the programs, in
+        ``forward``)."""
+        from .engine import SceneLayout
+        feats = object_features.to(device=device, dtype=torch.float32).contiguous()
+        assert feats.is_cuda, 'dfol_vqa_b200 runs on CUDA tensors only (no CPU fallback)'
+        counts = torch.bincount(batch_index.to(feats.device)).tolist()
+        w = self._weights
+        lay = SceneLayout.get(counts, w.emb.weight.shape[0], len(self._engine.rel_index_host), feats.device)
+        with torch.no_grad():
+            return self._engine.build_scene(feats, lay, keep_for_backward=is_training)
 
     def _dropout_for(self, is_training):
         """None, or (p, seed) of this forward pass: nn.Dropout is active when the module is in train() mode and the

@@ -127,6 +127,59 @@ def test_scene_tables_match_reference_golden():
         assert bool((blk[:, [i * n + i for i in range(n)]] == -30.0).all())
 
 
+def test_inner_module_surfaces_match_reference_golden():
+    """The inner surfaces of the three modules -- FastBoxFeaturizer.featurize_scene (reference
+    batch_gqa_boxfeatures_pipeline.py:199-281), FastClassifierOracle.compute_all_log_likelihood_2
+    (classifier_oracle.py:145-156), FastGQAInterpreter.build_scene (batch_base_interpreter.py:45-70) -- against the values
+    the UNMODIFIED reference returned from the same calls (recorded in the golden's ``scene`` entry)."""
+    path = [p for p in helpers.golden_files() if 'verify_rel' in p][0]
+    case = helpers.load_golden(path)
+    ont = helpers.ontology_of(case)
+    interp = helpers.build_interpreter(ont, case['dims'], case['state'])
+    ref = case['ref32']['scene']
+    dev = torch.device('cuda', 0)
+    feats, bidx = case['features'], case['batch_index']
+    out = interp._featurizer.featurize_scene(dev, feats, bidx, {})
+    assert out['object_num'] == feats.shape[0]
+    for mine, theirs in zip(out['relation_features']['index'], ref['index']):
+        assert torch.equal(mine.cpu(), theirs.long())
+    # the feature rows themselves against the oracle's restatement of the same function
+    F = case['dims']['feat']
+    f = torch.sigmoid(torch.nn.functional.linear(feats[:, :-6], case['state']['_featurizer._featurizer_network._network.1.weight'],
+                                                 case['state']['_featurizer._featurizer_network._network.1.bias']))
+    assert torch.allclose(out['attribute_features'][:, :F].cpu(), f, rtol=1e-5, atol=1e-6)
+    img, s, o = (t.long() for t in ref['index'])
+    objs = out['attribute_features'].cpu()
+    rel = out['relation_features']['features'].cpu()
+    assert rel.shape == (img.numel(), 2 * (F + 4) + 4)
+    assert torch.equal(rel[:, :F + 4], objs[s]) and torch.equal(rel[:, F + 4:2 * (F + 4)], objs[o])
+    pos = objs[:, F:]
+    dy = pos[s, 1] + pos[s, 3] / 2 - pos[o, 1] - pos[o, 3] / 2
+    dist = torch.sqrt((pos[s, 0] + pos[s, 2] / 2 - pos[o, 0] - pos[o, 2] / 2) ** 2 + dy ** 2)
+    geo = torch.stack([dist, torch.asin(dy / dist.clamp(min=1e-10)), (pos[o, 0] - pos[s, 0]).sign(),
+                       (pos[o, 1] - pos[s, 1]).sign()], dim=1)
+    assert torch.allclose(rel[:, 2 * (F + 4):], geo, rtol=1e-5, atol=1e-6)
+    attr_ll, rel_ll = interp._oracle.compute_all_log_likelihood_2(out['attribute_features'],
+                                                                  out['relation_features']['features'])
+    assert torch.allclose(attr_ll.cpu(), ref['attr'], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rel_ll.cpu(), ref['rel'], rtol=1e-5, atol=1e-6)
+    scene = interp.build_scene(dev, feats, bidx, {})
+    from dfol_vqa_b200.engine import SceneLayout
+    C, nR = len(ont._vocabulary['idx_to_arg']), len(ont._relation_index)
+    layout = SceneLayout.get(case['counts'], C, nR, dev)
+    direct = interp._engine.build_scene(feats.cuda(), layout)
+    a_blk, a_str = layout.attr_blk.cpu(), layout.attr_stride.cpu()
+    r_blk, r_str = layout.rel_blk.cpu(), layout.rel_stride.cpu()
+    for b, n in enumerate(case['counts']):   # (the padding between table slices is uninitialised: valid entries only)
+        for mine, theirs, blk, stride, rows, width in ((scene.attr_ll, direct.attr_ll, a_blk, a_str, C, n),
+                                                       (scene.rel_ll, direct.rel_ll, r_blk, r_str, nR, n * n)):
+            lo, ld = int(blk[b]), int(stride[b])
+            assert torch.equal(mine[lo:lo + rows * ld].view(rows, ld)[:, :width],
+                               theirs[lo:lo + rows * ld].view(rows, ld)[:, :width])
+    with pytest.raises(AssertionError):
+        interp._oracle.compute_all_log_likelihood_2(out['attribute_features'].cpu(), None)   # no CPU fallback
+
+
 @pytest.mark.parametrize('terminal,batch,n_max,ragged', [
     ('exist', 16, 48, False), ('verify_rel', 12, 37, True), ('query_attr', 8, 24, True), ('choose_rel', 8, 100, False),
     ('and', 10, 48, True), ('two_same', 6, 31, True), ('compare', 6, 20, True), ('all_same', 6, 17, True)])
