@@ -168,6 +168,81 @@ __global__ void __launch_bounds__(256) pair_features_dropout_kernel(
   }
 }
 
+// The same for the tensor-core path (bf16 rows, width % 4 == 0, 16-byte aligned rows), restructured around what repeats:
+// a block owns PFD_ROWS consecutive pair rows, a thread owns ONE column group of 8 and every second row, so that
+//   * the subject half of a row ([obj_s], the same for the n rows of a subject) stays in registers,
+//   * the geometry (sqrt, asin) is evaluated by the one thread whose group holds it, not by all 32 lanes of a row warp,
+//   * no lanes idle on the ragged tail of 136 groups over 32 lanes (the row-per-warp kernel: 4.25 passes per row),
+// and the keep decisions are taken two at a time (packed 16-bit compare) on the bf16 words.  Same masks, same values.
+constexpr int PFD_ROWS = 64;
+
+__global__ void __launch_bounds__(288) pair_features_dropout_bf16_kernel(
+    const float* __restrict__ obj, long long ldobj, int width, int pos_col, __nv_bfloat16* __restrict__ out,
+    long long ldout, int groups, const int32_t* __restrict__ pair_row, const int32_t* __restrict__ obj_row,
+    const int32_t* __restrict__ img_n, const int32_t* __restrict__ pair_img, long long pairs, DropSite d) {
+  const int rsub = threadIdx.x / groups, g8 = threadIdx.x - rsub * groups;
+  if (rsub >= 2) return;
+  const long long r_end = min(pairs, ((long long)blockIdx.x + 1) * PFD_ROWS);
+  const int in_cols = 2 * width + 4;
+  // segment of each half (4 columns) of this thread's group: 0 subject, 1 object, 2 geometry, 3 zero padding
+  int seg[2], off[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = g8 * 8 + 4 * h;
+    seg[h] = c < width ? 0 : (c < 2 * width ? 1 : (c < in_cols ? 2 : 3));
+    off[h] = seg[h] == 0 ? c : c - width;
+  }
+  // kept elements are scaled by 1 / (1 - p); the drop threshold replicated into both 16-bit halves
+  const uint32_t thr2 = d.thresh | (d.thresh << 16);
+  int b = -1, n = 1, s = 0, o = 0;
+  const float* os = obj;
+  const float* ob = obj;
+  float4 subj[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+  for (long long r = (long long)blockIdx.x * PFD_ROWS + rsub; r < r_end; r += 2) {
+    const int bn = pair_img[r];
+    bool new_subject = false;
+    if (bn != b) {
+      b = bn;
+      n = img_n[b];
+      const int local = (int)(r - pair_row[b]);
+      s = local / n;
+      o = local - s * n;
+      ob = obj + (long long)obj_row[b] * ldobj;
+      new_subject = true;
+    } else {
+      o += 2;
+      while (o >= n) { o -= n; ++s; new_subject = true; }
+    }
+    if (new_subject) {
+      os = ob + (long long)s * ldobj;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (seg[h] == 0) subj[h] = *reinterpret_cast<const float4*>(os + off[h]);
+    }
+    const float* oo = ob + (long long)o * ldobj;
+    const unsigned long long g = (unsigned long long)r * (unsigned long long)d.groups_per_row + (unsigned long long)g8;
+    const uint4 w = drop_words((uint32_t)g, (uint32_t)(g >> 32), d.site, d.key);
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+    uint32_t pk[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 x = subj[h];
+      if (seg[h] == 1) x = *reinterpret_cast<const float4*>(oo + off[h]);
+      else if (seg[h] == 2) {
+        float geo[4];
+        drop_pair_geometry(os + pos_col, oo + pos_col, geo);
+        x = make_float4(geo[0], geo[1], geo[2], geo[3]);
+      } else if (seg[h] == 3) x = make_float4(0.f, 0.f, 0.f, 0.f);
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x * d.scale, x.y * d.scale);
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(x.z * d.scale, x.w * d.scale);
+      // element 2i of the group takes the low, 2i + 1 the high 16 bits of word i; keep iff bits >= threshold
+      pk[2 * h] = *reinterpret_cast<const uint32_t*>(&lo) & __vcmpgeu2(ws[2 * h], thr2);
+      pk[2 * h + 1] = *reinterpret_cast<const uint32_t*>(&hi) & __vcmpgeu2(ws[2 * h + 1], thr2);
+    }
+    *reinterpret_cast<uint4*>(out + r * ldout + g8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
 // Backward of the pair-feature gather: d_obj[t, c] += sum_o dpm[(t,o), c] + sum_s dpm[(s,t), width + c] (+ addend[t, c])
 // (the geometry columns carry no parameter gradient).  One block per object row, threads over columns.
 template <class T>
@@ -239,6 +314,15 @@ extern "C" int dfol_pair_features_dropout(const float* obj, int64_t ldobj, int w
   DFOL_REQUIRE(p >= 0.0f && p < 1.0f, "dfol_pair_features_dropout: p must be in [0, 1)");
   if (pairs == 0) return 0;
   const DropSite d = make_site(seed, site, p, 2 * width + 4);
+  const int groups = out_cols / 8;
+  if (is_bf16 && (out_cols % 8) == 0 && (ldout % 8) == 0 && (width % 4) == 0 && (ldobj % 4) == 0 && (pos_col % 4) == 0 &&
+      2 * groups <= 288 && d.thresh < 65536u && (reinterpret_cast<uintptr_t>(obj) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const long long nblk = (pairs + PFD_ROWS - 1) / PFD_ROWS;
+    pair_features_dropout_bf16_kernel<<<(unsigned)nblk, 288, 0, (cudaStream_t)stream>>>(
+        obj, ldobj, width, pos_col, (__nv_bfloat16*)out, ldout, groups, pair_row, obj_row, img_n, pair_img, pairs, d);
+    return finish_launch("dfol_pair_features_dropout");
+  }
   const long long warps = pairs;
   const int blocks = (int)((warps + 7) / 8 < 148 * 16 ? (warps + 7) / 8 : 148 * 16);
   if (is_bf16)

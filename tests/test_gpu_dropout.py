@@ -92,6 +92,15 @@ def test_pair_features_dropout_matches_torch():
     off = torch.cat([(torch.arange(n * n) // n != torch.arange(n * n) % n) for n in counts]).cuda()
     assert torch.allclose(out[off][:, :cols], ref[off], rtol=1e-6, atol=1e-6)
     assert bool((out[:, cols:] == 0).all())
+    # the bf16 kernel of the tensor-core path (block per 64 rows, thread per column group): the same masks and values,
+    # i.e. exactly the fp32 rows rounded to bf16 (self pairs included: the geometry of a self pair is 0 / 0 / 0 / 0)
+    out16 = torch.full((P, cols + 4), float('nan'), device='cuda', dtype=torch.bfloat16)
+    call('dfol_pair_features_dropout', ptr(obj), width, width, F, ptr(out16), cols + 4, cols + 4, 1,
+         ptr(layout.pair_row), ptr(layout.obj_row), ptr(layout.img_n), ptr(layout.pair_img), P, 77, 3, 0.3,
+         stream_ptr(obj.device))
+    assert torch.equal(out16[off], out[off].bfloat16())
+    assert torch.equal(out16[~off][:, :2 * width], out[~off][:, :2 * width].bfloat16())
+    assert bool((out16[:, cols:] == 0).all())
 
 
 @pytest.mark.parametrize('name', ['verify_rel', 'query_attr', 'choose_rel', 'and'])
