@@ -9,6 +9,7 @@
 // One 128 x BN output tile per CTA, BN <= 256 chosen by the host so that two CTAs fit on an SM (<= 256 TMEM
 // columns and ~110 KB smem each): while one CTA drains its accumulator through the epilogue the other one issues
 // MMAs.  Every mbarrier wait is bounded (trap instead of hanging the GPU).
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace dfol {
@@ -294,7 +295,9 @@ static int launch_tc(const char* who, const void* A, int64_t lda, const void* B,
   p.keep = keep;
   p.exact = exact;
   const int stage_bytes = (TC_BM + BN) * TC_BK * 2;
-  int stages = (110 * 1024) / stage_bytes;  // two CTAs per SM
+  // two CTAs per SM (DFOL_TC_SMEM_KB: ring budget per CTA for experiments; 200 = one CTA per SM with a deep ring)
+  static const int smem_kb = [] { const char* e = getenv("DFOL_TC_SMEM_KB"); return e && atoi(e) >= 48 ? atoi(e) : 110; }();
+  int stages = (smem_kb * 1024) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 2) stages = 2;
   if (stages > K / TC_BK) stages = K / TC_BK;
