@@ -284,8 +284,23 @@ static int launch_tc(const char* who, const void* A, int64_t lda, const void* B,
     DFOL_REQUIRE(n_store >= N && n_store <= ldc, "%s: N <= store_cols <= ldc", who);
   }
   const int cover = (n_store + 15) / 16 * 16;
-  const int n_tiles = (cover + 255) / 256;
-  const int BN = ((cover + n_tiles - 1) / n_tiles + 15) / 16 * 16;
+  int n_tiles = (cover + 255) / 256;
+  int BN = ((cover + n_tiles - 1) / n_tiles + 15) / 16 * 16;
+  {
+    // wave quantisation: M / 128 row tiles x n_tiles column tiles on 2 x 148 CTA slots.  One more column tile (narrower
+    // BN) can turn "one full wave + a 30 % one" into two nearly full waves of cheaper tiles: cost ~ waves x (BN + 64)
+    // (the 64 stands for the A tile and the fixed part of a tile).  DFOL_TC_WAVE=0 keeps the widest tiles.
+    static const int wave = [] { const char* e = getenv("DFOL_TC_WAVE"); return e ? atoi(e) : 1; }();
+    const long long m_tiles = (M + TC_BM - 1) / TC_BM;
+    const long long slots = 2 * 148;
+    if (wave && store == 0 && m_tiles * n_tiles > slots) {
+      const int n2 = n_tiles + 1;
+      const int BN2 = ((cover + n2 - 1) / n2 + 15) / 16 * 16;
+      const long long c1 = ((m_tiles * n_tiles + slots - 1) / slots) * (BN + 64);
+      const long long c2 = ((m_tiles * n2 + slots - 1) / slots) * (BN2 + 64);
+      if (BN2 >= 64 && c2 < c1) { n_tiles = n2; BN = BN2; }
+    }
+  }
   TcParams p;
   p.C = C; p.ldc = ldc; p.bias = bias; p.M = M; p.N = N; p.K = K; p.n_store = n_store; p.BN = BN;
   p.act = act; p.out_bf16 = out_bf16; p.store = store;
